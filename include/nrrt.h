@@ -1,0 +1,123 @@
+/*
+ * nrrt.h — C ABI of libnrrt.so: the B200 (sm_100a) implementation of the neural-guided RRT* hot path of
+ * cezarywawrzyniak/mgr_sampling_cnn.  This is the drop-in boundary: the reference has no FFI of its
+ * own — its boundary is the Python class surface — so every entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`.
+ *   - Every call enqueues on `stream` (a cudaStream_t passed as void*) and returns; nothing synchronises.
+ *   - Return value: 0 on success, a negative NrrtError otherwise; nrrt_last_error() gives the message (thread-local).
+ *   - The library allocates nothing persistent and keeps no state besides that message.
+ *   - Positions are (y,x) in 2D and (x,y,z) = array axes (0,1,2) in 3D, exactly as in the reference.
+ */
+#ifndef NRRT_H_
+#define NRRT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRRT_VERSION 100
+
+typedef enum NrrtError {
+    NRRT_OK = 0,
+    NRRT_ERR_BAD_ARG = -1,      /* bad shape / null pointer / unsupported size */
+    NRRT_ERR_WORKSPACE = -2,    /* workspace too small */
+    NRRT_ERR_CUDA = -3,         /* a CUDA runtime call failed (message has the CUDA error string) */
+    NRRT_ERR_UNSUPPORTED = -4   /* device is not sm_100 or shared memory budget exceeded */
+} NrrtError;
+
+/* Per-task status written to NrrtPlanOut.status. */
+typedef enum NrrtTaskStatus {
+    NRRT_SOLVED = 0,               /* goal_reached() returned True            (rrt_star.py:203-208) */
+    NRRT_MAX_ITER_BEST_EFFORT = 1, /* loop ran out; path ends at best_node    (rrt_star.py:210-211) */
+    NRRT_NO_NODE_CONNECTED = 2,    /* best_node is None -> reference returns [] (find_path(None)) */
+    NRRT_SAMPLER_STUCK = 3         /* bounded rejection hit max_reject; the reference would spin forever
+                                      (rrt_star.py:64-68 / ThreeD_neural_rrt.py:81-108) */
+} NrrtTaskStatus;
+
+/* Planner configuration = the constructor arguments of the four reference RRTStar classes
+ * (rrt_star.py:49-61, neural_rrt.py:50-64, ThreeD_rrt_star.py:50-62, ThreeD_neural_rrt.py:54-68). */
+typedef struct NrrtPlanParams {
+    int32_t dim;            /* 2 or 3 */
+    int32_t shape[3];       /* occ_map.shape; 2D: (map_height, map_width, 1) */
+    int32_t max_iterations; /* MAX_ITERATIONS (5000 in the reference) */
+    int32_t node_stride;    /* rows per task in pos/cost/parent outputs; must be >= max_iterations + 2 */
+    int32_t max_reject;     /* bound on consecutive rejected draws inside one sample */
+    int32_t path_cap;       /* points per task in path_idx (0 = no path extraction) */
+    double goal_threshold;  /* GOAL_THRESHOLD: 5.0 (2D) / 3.0 (3D) */
+    double neural_bias;     /* neural_bias (0.75 in the reference); ignored when cdf == NULL */
+    uint64_t seed;          /* Philox key of the sample stream */
+} NrrtPlanParams;
+
+/* Per-task outputs; all arrays caller-allocated, fixed stride, any pointer marked optional may be NULL. */
+typedef struct NrrtPlanOut {
+    double* pos;        /* optional [B][node_stride][dim]  Node.position, insertion order (node index) */
+    double* cost;       /* required [B][node_stride]       Node.cost (also the kernel's working storage) */
+    int32_t* parent;    /* required [B][node_stride]       index of Node.parent, -1 for the start node */
+    int32_t* n_nodes;   /* [B] len(self.nodes) */
+    int32_t* iterations;/* [B] iteration_no returned by rrt_star() (1-based) */
+    int32_t* status;    /* [B] NrrtTaskStatus */
+    int32_t* goal_node; /* [B] index of the goal-reaching node (== n_nodes, stored but not counted) or -1 */
+    int32_t* best_node; /* [B] self.best_node index or -1 */
+    double* best_dist;  /* [B] self.best_distance */
+    int32_t* path_n;    /* optional [B] number of points of find_path() (rrt_star.py:163-172) */
+    int32_t* path_idx;  /* optional [B][path_cap] node indices start -> end */
+    double* path_len;   /* optional [B] calculate_length(path) (test_network_and_algorithms.py:52-56) */
+    int32_t* trace;     /* optional [B][trace_cap][4] (iteration, kind 0=connect 1=loop A 2=loop B, node j, verdict):
+                           the collision tests the reference would execute, in its order */
+    int32_t* trace_n;   /* optional [B] number of trace records produced (may exceed trace_cap) */
+    int32_t trace_cap;
+} NrrtPlanOut;
+
+int nrrt_version(void);
+const char* nrrt_last_error(void);
+
+/* Number of uint32 words of one bit-packed occupancy map (bit c of word c>>5 = cell c row-major, 1 = FREE). */
+size_t nrrt_words_per_map(int64_t cells);
+
+/* Bit-pack occupancy maps.  Replaces the per-cell tests `occ_map[y, x] != 0` (2D free, rrt_star.py:67,120) and
+ * `occ_map[x, y, z] == 0` (3D free, ThreeD_rrt_star.py:69,128).  dtype: 0 = uint8, 1 = float32, 2 = float64.
+ * occ: [n_maps][cells];  bits: [n_maps][nrrt_words_per_map(cells)]. */
+int nrrt_pack_occupancy(const void* occ, int dtype, int free_is_nonzero, int n_maps, int64_t cells, uint32_t* bits,
+                        void* stream);
+
+/* CNN-output post-processing + CDF of the neural sampler, hoisted out of the per-draw path:
+ *   2D (three_d = 0): h = clamp(logits,-3,1) + 10                      neural_rrt.py:351 + :64
+ *   3D (three_d = 1): v=(l-min)/(max-min); v[v<=0.96]=0; h = v - 250   ThreeD_neural_rrt.py:339-346 + :68
+ *   mode 2        : h = logits as given (already the planner-side heat map)
+ *   then w = h - min(h); p = w / np.sum(w); cdf = np.cumsum(p)         neural_rrt.py:74-86 (fp32, NumPy rounding)
+ * logits, cdf: [B][cells] float32.  workspace: nrrt_cdf_workspace_bytes(B, cells) bytes. */
+size_t nrrt_cdf_workspace_bytes(int B, int64_t cells);
+int nrrt_cdf_build(const float* logits, int mode, int B, int64_t cells, float* cdf, void* workspace, size_t ws_bytes,
+                   void* stream);
+
+/* Draw the sample point of every iteration of every task:
+ * generate_random_sample (rrt_star.py:63-68, ThreeD_rrt_star.py:64-70), generate_neural_sample
+ * (neural_rrt.py:73-99, ThreeD_neural_rrt.py:80-110) and the `random.random() < neural_bias` switch (neural_rrt.py:225).
+ * cdf == NULL selects the uniform-only modules.  samples: [B][max_iterations][dim] int16.
+ * task_ids[b] is the Philox stream id of task b; draw_status[b] = 0 or NRRT_SAMPLER_STUCK; n_draws optional. */
+int nrrt_draw_samples(const NrrtPlanParams* p, const uint32_t* occ_bits, const int32_t* task_to_map, const float* cdf,
+                      const int32_t* task_ids, int B, int16_t* samples, int8_t* neural_flag, int64_t* n_draws,
+                      int32_t* draw_status, void* stream);
+
+/* RRT* main loop for B independent tasks (rrt_star.py:184-215 and twins): nearest neighbour, steer, collision test,
+ * near set, choose-parent, rewire, goal test; one task per CTA.  radius: [max_iterations] fp64 table of
+ * compute_search_radius (rrt_star.py:174-182), computed by the host with Python `math`.
+ * samples as produced by nrrt_draw_samples (or pre-drawn by the caller: parity level A).
+ * draw_status may be NULL; tasks with draw_status != 0 are skipped and report that status.
+ * queue_counter: one int32 of device scratch (zeroed by the call). */
+int nrrt_plan_batch(const NrrtPlanParams* p, const uint32_t* occ_bits, const int32_t* task_to_map, const double* radius,
+                    const int16_t* samples, const int32_t* starts, const int32_t* goals, const int32_t* draw_status,
+                    const NrrtPlanOut* out, int B, int32_t* queue_counter, void* stream);
+
+/* Shared memory one planner CTA needs for these params (bytes), and CTAs per SM the launch will get (info only). */
+int nrrt_plan_smem_bytes(const NrrtPlanParams* p, size_t* bytes, int* ctas_per_sm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRRT_H_ */

@@ -1,0 +1,63 @@
+"""ctypes binding of libnrrt.so (include/nrrt.h).  There is no CPU fallback: a missing library is a hard error."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnrrt.so")
+
+NRRT_SOLVED, NRRT_MAX_ITER_BEST_EFFORT, NRRT_NO_NODE_CONNECTED, NRRT_SAMPLER_STUCK = 0, 1, 2, 3
+
+
+class NrrtError(RuntimeError):
+    pass
+
+
+class NrrtPlanParams(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("shape", C.c_int32 * 3), ("max_iterations", C.c_int32), ("node_stride", C.c_int32),
+                ("max_reject", C.c_int32), ("path_cap", C.c_int32), ("goal_threshold", C.c_double),
+                ("neural_bias", C.c_double), ("seed", C.c_uint64)]
+
+
+class NrrtPlanOut(C.Structure):
+    _fields_ = [("pos", C.c_void_p), ("cost", C.c_void_p), ("parent", C.c_void_p), ("n_nodes", C.c_void_p),
+                ("iterations", C.c_void_p), ("status", C.c_void_p), ("goal_node", C.c_void_p), ("best_node", C.c_void_p),
+                ("best_dist", C.c_void_p), ("path_n", C.c_void_p), ("path_idx", C.c_void_p), ("path_len", C.c_void_p),
+                ("trace", C.c_void_p), ("trace_n", C.c_void_p), ("trace_cap", C.c_int32)]
+
+
+_SIGNATURES = {
+    "nrrt_version": (C.c_int, []),
+    "nrrt_last_error": (C.c_char_p, []),
+    "nrrt_words_per_map": (C.c_size_t, [C.c_int64]),
+    "nrrt_pack_occupancy": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
+    "nrrt_cdf_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int64]),
+    "nrrt_cdf_build": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrrt_draw_samples": (C.c_int, [C.POINTER(NrrtPlanParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrrt_plan_batch": (C.c_int, [C.POINTER(NrrtPlanParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.POINTER(NrrtPlanOut), C.c_int, C.c_void_p, C.c_void_p]),
+    "nrrt_plan_smem_bytes": (C.c_int, [C.POINTER(NrrtPlanParams), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+_lib = None
+
+
+def load():
+    """Load libnrrt.so; raise loudly when the CUDA extension has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NrrtError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(nvcc, sm_100a). mgr_sampling_cnn_b200 has no CPU or PyTorch fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise NrrtError(f"libnrrt error {rc}: {load().nrrt_last_error().decode()}")

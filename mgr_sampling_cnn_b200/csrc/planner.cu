@@ -1,0 +1,458 @@
+// planner.cu — the RRT* main loop of the reference, one planning task per CTA (sm_100a).
+//
+// Replaces  rrt_star.py:70-215, neural_rrt.py:101-249, ThreeD_rrt_star.py:72-224, ThreeD_neural_rrt.py:112-265
+// (find_nearest_neighbor, steer, can_connect_nodes, is_collision_free, rewire_tree, find_nearby_nodes, goal_reached,
+// find_path, rrt_star) and calculate_length (test_network_and_algorithms.py:52-56).  Numeric contract: SURVEY.md
+// Appendix A — fp64, every product/sum rounded separately except the FMA chain of np.linalg.norm in the collision
+// test; nearest neighbour = lowest index among minimal sqrt'ed distances; near set uses `<=` on the sqrt'ed distance.
+//
+// Layout per CTA (dynamic shared memory):
+//   pos[DIM][cap] fp64 (SoA, node index = insertion order) | occupancy bit grid of the task's map | near bit-mask |
+//   reduction slots.  cost[] and parent[] live in the caller's output arrays in global memory (L2): they are touched
+//   only for the ~20 near nodes of an iteration, which keeps the CTA at 111 KiB so two 2D tasks share one SM.
+// Parallelism inside an iteration: the two O(n) scans run over all threads; every warp evaluates the connect test
+// redundantly (no barrier); choose-parent/rewire candidates are tested speculatively, one candidate per warp at a time,
+// 100 samples over 32 lanes.  The outcome of loop A does not depend on evaluation order (it is the lexicographic
+// minimum of (cost, index) over the free candidates), so speculation is exact; TRACE mode replays the reference's
+// sequential order on warp 0 to emit exactly the collision calls the reference makes.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "nrrt_common.cuh"
+
+namespace {
+
+constexpr int kWarp = 32;
+
+struct PlanArgs {
+    NrrtPlanParams p;
+    const uint32_t* occ_bits;
+    const int32_t* task_to_map;
+    const double* radius;
+    const int16_t* samples;
+    const int32_t* starts;
+    const int32_t* goals;
+    const int32_t* draw_status;
+    NrrtPlanOut out;
+    int B;
+    int32_t* queue;
+    int words_per_map;
+    int cap;         // node capacity in shared memory (>= max_iterations + 2, even)
+    int mask_words;  // words of the near mask
+};
+
+struct Slot {
+    double v;
+    int j;
+    int pad;
+};
+
+// lexicographic "reference order" combine for the nearest-neighbour reduction: lower sqrt(s) wins, ties -> lower j.
+// sqrt is only evaluated when the squares are within 2^-50 relative (squares alone mis-order sqrt ties).
+__device__ __forceinline__ bool nn_a_wins(double sa, int ja, double sb, int jb) {
+    if (sa == sb) return ja < jb;
+    const double lo = fmin(sa, sb), hi = fmax(sa, sb);
+    if (hi <= __dmul_rn(lo, NRRT_K_HI)) {
+        const double da = sqrt(sa), db = sqrt(sb);
+        return da < db || (da == db && ja < jb);
+    }
+    return sa < sb;
+}
+
+// is_collision_free (rrt_star.py:108-123 / ThreeD_rrt_star.py:115-132), one warp, 100 samples over lanes.
+// Grid bit = 1 means the reference treats the cell as free.
+template <int DIM>
+__device__ __forceinline__ bool collision_free_warp(const double (&p1)[DIM], const double (&p2)[DIM],
+                                                    const uint32_t* __restrict__ grid, const int (&shape)[3], int lane) {
+    double dl[DIM];
+    bool same = true;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        dl[k] = __dsub_rn(p1[k], p2[k]);
+        same = same && (p1[k] == p2[k]);
+    }
+    if (same) return false;  // `if point1 == point2: return False`
+    double q = __dmul_rn(dl[0], dl[0]);  // np.linalg.norm -> ddot: FMA chain
+    q = __fma_rn(dl[1], dl[1], q);
+    if (DIM == 3) q = __fma_rn(dl[DIM - 1], dl[DIM - 1], q);
+    const double D = sqrt(q);
+    const double step = __ddiv_rn(D, 99.0);  // np.linspace(0, D, 100)
+#pragma unroll 1
+    for (int i = lane; i < 100 + kWarp - 1 - ((100 + kWarp - 1) % kWarp); i += kWarp) {
+        bool blocked = false;
+        if (i < 100) {
+            const double t = (i == 99) ? D : __dmul_rn((double)i, step);
+            int idx = 0;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) {
+                const double v = __dsub_rn(p1[k], __ddiv_rn(__dmul_rn(t, dl[k]), D));
+                int ci = __double2int_rz(v);  // int(): truncation toward zero
+                ci = max(0, min(ci, shape[k] - 1));
+                idx = idx * shape[k] + ci;
+            }
+            blocked = ((grid[idx >> 5] >> (idx & 31)) & 1u) == 0u;
+        }
+        if (__any_sync(0xffffffffu, blocked)) return false;
+    }
+    return true;
+}
+
+template <int DIM, int NT, bool TRACE>
+__global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const PlanArgs a) {
+    constexpr int NW = NT / kWarp;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* pos = reinterpret_cast<double*>(smem_raw);                       // [DIM][cap]
+    uint32_t* grid = reinterpret_cast<uint32_t*>(pos + (size_t)DIM * a.cap); // [words_per_map] (padded to 4)
+    uint32_t* mask = grid + ((a.words_per_map + 3) & ~3);                    // [mask_words]
+    Slot* slot_nn = reinterpret_cast<Slot*>(mask + ((a.mask_words + 3) & ~3)); // [2][NW]
+    Slot* slot_a = slot_nn + 2 * NW;                                         // [NW]
+    __shared__ int s_task;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cap = a.cap;
+    const int max_iter = a.p.max_iterations;
+    const int shape[3] = {a.p.shape[0], a.p.shape[1], DIM == 3 ? a.p.shape[2] : 1};
+    const double thr = a.p.goal_threshold;
+    int cur_map = -1;
+
+    for (;;) {
+        __syncthreads();  // previous task fully retired (smem reuse, s_task reuse)
+        if (tid == 0) s_task = atomicAdd(a.queue, 1);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= a.B) break;
+
+        double* cost = a.out.cost + (size_t)task * a.p.node_stride;
+        int32_t* parent = a.out.parent + (size_t)task * a.p.node_stride;
+        int32_t* trace = TRACE ? a.out.trace + (size_t)task * a.out.trace_cap * 4 : nullptr;
+        int trace_n = 0;
+
+        if (a.draw_status && a.draw_status[task] != 0) {  // sampler gave up: report and skip
+            if (tid == 0) {
+                a.out.n_nodes[task] = 1; a.out.iterations[task] = 0; a.out.status[task] = a.draw_status[task];
+                a.out.goal_node[task] = -1; a.out.best_node[task] = -1; a.out.best_dist[task] = INFINITY;
+                if (a.out.path_n) a.out.path_n[task] = 0;
+                if (a.out.path_len) a.out.path_len[task] = 0.0;
+                if (a.out.trace_n) a.out.trace_n[task] = 0;
+            }
+            continue;
+        }
+
+        // ---- stage the task's occupancy bits (16-byte loads; consecutive tasks of one map reuse the copy) ----
+        const int map = a.task_to_map[task];
+        if (map != cur_map) {
+            const uint4* src = reinterpret_cast<const uint4*>(a.occ_bits + (size_t)map * a.words_per_map);
+            uint4* dst = reinterpret_cast<uint4*>(grid);
+            for (int i = tid; i < (a.words_per_map >> 2); i += NT) dst[i] = __ldg(src + i);
+            for (int i = (a.words_per_map & ~3) + tid; i < a.words_per_map; i += NT)
+                grid[i] = __ldg(a.occ_bits + (size_t)map * a.words_per_map + i);
+            cur_map = map;
+        }
+        double goal[DIM];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) goal[k] = (double)a.goals[task * DIM + k];
+        if (tid < DIM) pos[tid * cap] = (double)a.starts[task * DIM + tid];  // self.nodes = [Node(start)]
+        if (tid == 0) { cost[0] = 0.0; parent[0] = -1; }
+        __syncthreads();
+
+        int n = 1, best_node = -1, goal_node = -1, iters = 0;
+        double best = INFINITY;
+        const int16_t* smp_base = a.samples + (size_t)task * max_iter * DIM;
+
+        for (int it = 0; it < max_iter; ++it) {
+            iters = it + 1;
+            const double r = __ldg(a.radius + it);
+            double smp[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) smp[k] = (double)__ldg(smp_base + it * DIM + k);
+
+            // ---- find_nearest_neighbor: scan + argmin (strict <, lowest index wins) ----
+            double bs = INFINITY;
+            int bj = 0x7fffffff;
+            for (int j = tid; j < n; j += NT) {
+                double pj[DIM];
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) pj[k] = pos[k * cap + j];
+                const double s = nrrt_sqdist<DIM>(pj, smp);
+                if (s < bs) {
+                    bool take = true;
+                    if (s > __dmul_rn(bs, NRRT_K_LO)) take = sqrt(s) < sqrt(bs);  // sqrt-tie hazard, rare
+                    if (take) { bs = s; bj = j; }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+                if (!nn_a_wins(bs, bj, os, oj)) { bs = os; bj = oj; }
+            }
+            Slot* snn = slot_nn + (it & 1) * NW;
+            if (lane == 0) { snn[warp].v = bs; snn[warp].j = bj; }
+            __syncthreads();  // (1)
+            bs = snn[0].v; bj = snn[0].j;
+#pragma unroll
+            for (int w = 1; w < NW; ++w) {
+                const double os = snn[w].v;
+                const int oj = snn[w].j;
+                if (!nn_a_wins(bs, bj, os, oj)) { bs = os; bj = oj; }
+            }
+            const int ni = bj;
+
+            // ---- steer (rrt_star.py:82-98; A.4 with x*x for x**2) ----
+            double from[DIM], dr[DIM], npos[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) { from[k] = pos[k * cap + ni]; dr[k] = __dsub_rn(smp[k], from[k]); }
+            double s2 = __dadd_rn(__dmul_rn(dr[0], dr[0]), __dmul_rn(dr[1], dr[1]));
+            if (DIM == 3) s2 = __dadd_rn(s2, __dmul_rn(dr[DIM - 1], dr[DIM - 1]));
+            double dist = sqrt(s2);
+            if (dist > r) {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) dr[k] = __ddiv_rn(__dmul_rn(dr[k], r), dist);
+            }
+            s2 = __dadd_rn(__dmul_rn(dr[0], dr[0]), __dmul_rn(dr[1], dr[1]));
+            if (DIM == 3) s2 = __dadd_rn(s2, __dmul_rn(dr[DIM - 1], dr[DIM - 1]));
+            dist = sqrt(s2);
+            const double ncost0 = __dadd_rn(cost[ni], dist);
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) npos[k] = __dadd_rn(from[k], dr[k]);
+
+            // ---- can_connect_nodes: every warp evaluates the same test (no barrier needed) ----
+            const bool connect = collision_free_warp<DIM>(from, npos, grid, shape, lane);
+            if (TRACE && tid == 0) {
+                if (trace_n < a.out.trace_cap) {
+                    int32_t* t = trace + 4 * trace_n;
+                    t[0] = iters; t[1] = 0; t[2] = ni; t[3] = connect ? 1 : 0;
+                }
+                ++trace_n;
+            }
+            if (!connect) continue;
+
+            // ---- find_nearby_nodes: euclid(new, node) <= r, as a bit mask in insertion order ----
+            const double r2 = __dmul_rn(r, r);
+            const double r2lo = __dmul_rn(r2, NRRT_K_LO), r2hi = __dmul_rn(r2, NRRT_K_HI);
+            for (int base = 0; base < n; base += NT) {
+                const int j = base + tid;
+                bool in = false;
+                if (j < n) {
+                    double pj[DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) pj[k] = pos[k * cap + j];
+                    const double s = nrrt_sqdist<DIM>(npos, pj);
+                    in = (s <= r2lo) ? true : ((s >= r2hi) ? false : (sqrt(s) <= r));
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, in);
+                if (lane == 0 && (base >> 5) + warp < a.mask_words) mask[(base >> 5) + warp] = m;
+            }
+            __syncthreads();  // (2)
+            const int nwords = (n + 31) >> 5;
+
+            // ---- loop A: choose parent.  Result = lexicographic min (cost, index) over free candidates < ncost0 ----
+            double wbest = ncost0;
+            int wpar = -1;
+            for (int w = TRACE ? 0 : warp; w < nwords; w += TRACE ? 1 : NW) {
+                if (TRACE && warp != 0) break;
+                const uint32_t m = mask[w];
+                if (m == 0u) continue;
+                const int j = (w << 5) + lane;
+                const bool has = (m >> lane) & 1u;
+                double pj[DIM], cj = INFINITY;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) pj[k] = 0.0;
+                if (has) {
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) pj[k] = pos[k * cap + j];
+                    cj = __dadd_rn(cost[j], sqrt(nrrt_sqdist<DIM>(pj, npos)));
+                }
+                uint32_t cand = __ballot_sync(0xffffffffu, has && cj < ncost0);
+                while (cand) {
+                    const int b = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    double p1[DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) p1[k] = __shfl_sync(0xffffffffu, pj[k], b);
+                    const double cb = __shfl_sync(0xffffffffu, cj, b);
+                    if (!(cb < wbest)) continue;  // reference would not call is_collision_free here (uniform per warp)
+                    const bool fr = collision_free_warp<DIM>(p1, npos, grid, shape, lane);
+                    if (TRACE && lane == 0) {
+                        if (trace_n < a.out.trace_cap) {
+                            int32_t* t = trace + 4 * trace_n;
+                            t[0] = iters; t[1] = 1; t[2] = (w << 5) + b; t[3] = fr ? 1 : 0;
+                        }
+                        ++trace_n;
+                    }
+                    if (fr) { wbest = cb; wpar = (w << 5) + b; }
+                }
+            }
+            if (lane == 0) { slot_a[warp].v = wbest; slot_a[warp].j = wpar; }
+            __syncthreads();  // (3)
+            double ncost = ncost0;
+            int npar = ni;
+            bool have = false;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const double c = slot_a[w].v;
+                const int j = slot_a[w].j;
+                if (j >= 0 && (!have || c < ncost || (c == ncost && j < npar))) { ncost = c; npar = j; have = true; }
+            }
+
+            // ---- loop B: rewire neighbours through the new node (index n); costs are not propagated ----
+            for (int w = TRACE ? 0 : warp; w < nwords; w += TRACE ? 1 : NW) {
+                if (TRACE && warp != 0) break;
+                const uint32_t m = mask[w];
+                if (m == 0u) continue;
+                const int j = (w << 5) + lane;
+                const bool has = (m >> lane) & 1u;
+                double pj[DIM], cj = 0.0, cur = 0.0;
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) pj[k] = 0.0;
+                if (has) {
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) pj[k] = pos[k * cap + j];
+                    cj = __dadd_rn(ncost, sqrt(nrrt_sqdist<DIM>(npos, pj)));
+                    cur = cost[j];
+                }
+                uint32_t cand = __ballot_sync(0xffffffffu, has && cj < cur);
+                while (cand) {
+                    const int b = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    double p2[DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) p2[k] = __shfl_sync(0xffffffffu, pj[k], b);
+                    const bool fr = collision_free_warp<DIM>(npos, p2, grid, shape, lane);
+                    if (TRACE && lane == 0) {
+                        if (trace_n < a.out.trace_cap) {
+                            int32_t* t = trace + 4 * trace_n;
+                            t[0] = iters; t[1] = 2; t[2] = (w << 5) + b; t[3] = fr ? 1 : 0;
+                        }
+                        ++trace_n;
+                    }
+                    if (fr && lane == b) { parent[j] = n; cost[j] = cj; }
+                }
+            }
+
+            // ---- goal_reached + append (rrt_star.py:156-161, :201-209) ----
+            const double dg = sqrt(nrrt_sqdist<DIM>(npos, goal));
+            if (dg < best) { best = dg; best_node = n; }
+            const bool reached = dg <= thr;
+            if (tid < DIM) pos[tid * cap + n] = reached ? goal[tid] : npos[tid];  // goal_node.position = self.goal
+            if (tid == 0) { cost[n] = ncost; parent[n] = npar; }
+            if (reached) { goal_node = n; break; }
+            ++n;
+            __syncthreads();  // (4) new node visible to the next scan; mask / slot_a free for reuse
+        }
+        __syncthreads();
+
+        // ---- epilogue: scalars, find_path + calculate_length, optional tree dump ----
+        const int n_tot = n + (goal_node >= 0 ? 1 : 0);
+        if (a.out.pos) {
+            double* opos = a.out.pos + (size_t)task * a.p.node_stride * DIM;
+            for (int i = tid; i < n_tot * DIM; i += NT) opos[i] = pos[(i % DIM) * cap + i / DIM];
+        }
+        if (tid == 0) {
+            a.out.n_nodes[task] = n;
+            a.out.iterations[task] = iters;
+            a.out.status[task] = goal_node >= 0 ? NRRT_SOLVED
+                                                : (best_node >= 0 ? NRRT_MAX_ITER_BEST_EFFORT : NRRT_NO_NODE_CONNECTED);
+            a.out.goal_node[task] = goal_node;
+            a.out.best_node[task] = best_node;
+            a.out.best_dist[task] = best;
+            if (TRACE && a.out.trace_n) a.out.trace_n[task] = trace_n;
+            if (a.out.path_n) {
+                const int end = goal_node >= 0 ? goal_node : best_node;
+                int m = 0;
+                for (int j = end; j >= 0 && m <= n_tot; j = parent[j]) ++m;  // find_path: walk to the root
+                if (m > n_tot) m = 0;  // parent cycle (the reference would never return): report no path
+                a.out.path_n[task] = m;
+                double len = 0.0;
+                if (a.out.path_idx && m <= a.p.path_cap) {
+                    int32_t* pi = a.out.path_idx + (size_t)task * a.p.path_cap;
+                    int q = m;
+                    for (int j = end; j >= 0; j = parent[j]) pi[--q] = j;  // path.reverse()
+                    for (int q2 = 0; q2 + 1 < m; ++q2) {                   // calculate_length: forward fp64 sum
+                        double u[DIM], v[DIM];
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) { u[k] = pos[k * cap + pi[q2]]; v[k] = pos[k * cap + pi[q2 + 1]]; }
+                        len = __dadd_rn(len, sqrt(nrrt_sqdist<DIM>(u, v)));
+                    }
+                } else if (m > 0) {
+                    len = NAN;  // path longer than path_cap: length not reported
+                }
+                if (a.out.path_len) a.out.path_len[task] = len;
+            }
+        }
+    }
+}
+
+struct SmemPlan {
+    size_t bytes;
+    int cap, mask_words, nt;
+};
+
+SmemPlan smem_plan(const NrrtPlanParams& p, int words_per_map) {
+    SmemPlan s;
+    s.nt = p.dim == 2 ? 256 : 512;
+    s.cap = (p.max_iterations + 2 + 1) & ~1;
+    s.mask_words = (s.cap + 31) / 32;
+    const int nw = s.nt / 32;
+    s.bytes = (size_t)p.dim * s.cap * 8 + (size_t)((words_per_map + 3) & ~3) * 4 + (size_t)((s.mask_words + 3) & ~3) * 4 +
+              (size_t)3 * nw * sizeof(Slot);
+    return s;
+}
+
+template <int DIM, int NT, bool TRACE>
+int launch_plan(const PlanArgs& a, size_t smem, cudaStream_t st) {
+    auto kern = plan_kernel<DIM, NT, TRACE>;
+    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0, per_sm = 0;
+    NRRT_CUDA_TRY(cudaGetDevice(&dev));
+    NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    NRRT_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+    if (per_sm < 1) return nrrt_fail(NRRT_ERR_UNSUPPORTED, "planner CTA needs %zu B of shared memory: does not fit", smem);
+    const int grid = a.B < sms * per_sm ? a.B : sms * per_sm;  // persistent CTAs pulling tasks from the queue
+    kern<<<grid, NT, smem, st>>>(a);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+}  // namespace
+
+extern "C" int nrrt_plan_smem_bytes(const NrrtPlanParams* p, size_t* bytes, int* ctas_per_sm) {
+    NRRT_REQUIRE(p && (p->dim == 2 || p->dim == 3), "dim must be 2 or 3");
+    const int64_t cells = (int64_t)p->shape[0] * p->shape[1] * (p->dim == 3 ? p->shape[2] : 1);
+    const SmemPlan s = smem_plan(*p, (int)nrrt_words_per_map(cells));
+    if (bytes) *bytes = s.bytes;
+    if (ctas_per_sm) *ctas_per_sm = (int)((233472 - 0) / (s.bytes + 1024));
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_plan_batch(const NrrtPlanParams* p, const uint32_t* occ_bits, const int32_t* task_to_map,
+                               const double* radius, const int16_t* samples, const int32_t* starts, const int32_t* goals,
+                               const int32_t* draw_status, const NrrtPlanOut* out, int B, int32_t* queue_counter,
+                               void* stream) {
+    NRRT_REQUIRE(p && out, "null params/out");
+    NRRT_REQUIRE(p->dim == 2 || p->dim == 3, "dim must be 2 or 3, got %d", p->dim);
+    NRRT_REQUIRE(B >= 0, "negative batch");
+    NRRT_REQUIRE(p->max_iterations >= 1 && p->max_iterations <= 32000, "max_iterations out of range: %d", p->max_iterations);
+    NRRT_REQUIRE(p->node_stride >= p->max_iterations + 2, "node_stride %d < max_iterations + 2", p->node_stride);
+    NRRT_REQUIRE(occ_bits && task_to_map && radius && samples && starts && goals && queue_counter, "null input pointer");
+    NRRT_REQUIRE(out->cost && out->parent && out->n_nodes && out->iterations && out->status && out->goal_node &&
+                     out->best_node && out->best_dist, "null required output pointer");
+    for (int k = 0; k < p->dim; ++k) NRRT_REQUIRE(p->shape[k] >= 1 && p->shape[k] <= 32767, "bad shape[%d]=%d", k, p->shape[k]);
+    const int64_t cells = (int64_t)p->shape[0] * p->shape[1] * (p->dim == 3 ? p->shape[2] : 1);
+    NRRT_REQUIRE(cells < (int64_t)1 << 31, "map too large");
+    if (B == 0) return NRRT_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    PlanArgs a;
+    a.p = *p; a.occ_bits = occ_bits; a.task_to_map = task_to_map; a.radius = radius; a.samples = samples;
+    a.starts = starts; a.goals = goals; a.draw_status = draw_status; a.out = *out; a.B = B; a.queue = queue_counter;
+    a.words_per_map = (int)nrrt_words_per_map(cells);
+    const SmemPlan s = smem_plan(*p, a.words_per_map);
+    a.cap = s.cap; a.mask_words = s.mask_words;
+    if (s.bytes > 232448) return nrrt_fail(NRRT_ERR_UNSUPPORTED, "planner needs %zu B shared memory (> 227 KiB): map or max_iterations too large", s.bytes);
+    const bool tracing = out->trace != nullptr && out->trace_cap > 0;
+    NRRT_CUDA_TRY(cudaMemsetAsync(queue_counter, 0, sizeof(int32_t), st));
+    if (p->dim == 2) return tracing ? launch_plan<2, 256, true>(a, s.bytes, st) : launch_plan<2, 256, false>(a, s.bytes, st);
+    return tracing ? launch_plan<3, 512, true>(a, s.bytes, st) : launch_plan<3, 512, false>(a, s.bytes, st);
+}

@@ -1,0 +1,410 @@
+// sampler.cu — occupancy bit-packing, the neural sampler's CDF (built once per task) and the per-iteration sample draws.
+//
+// Replaces  generate_random_sample (rrt_star.py:63-68, ThreeD_rrt_star.py:64-70), generate_neural_sample
+// (neural_rrt.py:73-99, ThreeD_neural_rrt.py:80-110), the sampler switch (neural_rrt.py:225-228) and the CNN-output
+// post-processing (neural_rrt.py:350-355 + :64; ThreeD_neural_rrt.py:339-346 + :68).  Numeric contract: SURVEY.md A.8 —
+// fp32 weights, NumPy's pairwise np.sum tree, strictly sequential fp32 np.cumsum, searchsorted compared in fp64.
+//
+// The reference rebuilds the CDF on every draw (O(N) per sample); the map never changes during a plan, so the CDF is a
+// per-task constant: built once here, then each draw is a 32-ary warp search (4 dependent probes for 2^18 cells).
+#include <algorithm>
+#include <vector>
+
+#include "nrrt_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// occupancy bit-packing: bit = 1 iff the reference treats the cell as free
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_kernel(const T* __restrict__ occ, int free_is_nonzero, int64_t cells, int words_per_map,
+                            uint32_t* __restrict__ bits) {
+    const int map = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+    const T* src = occ + (size_t)map * cells;
+    uint32_t* dst = bits + (size_t)map * words_per_map;
+    for (int w0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; w0 < words_per_map; w0 += warps_per_grid * 32) {
+        uint32_t mine = 0;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const int64_t c = ((int64_t)(w0 + r) << 5) + lane;
+            bool fr = false;
+            if (c < cells) {
+                const bool nz = src[c] != (T)0;
+                fr = free_is_nonzero ? nz : !nz;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, fr);
+            if (r == lane) mine = m;
+        }
+        if (w0 + lane < words_per_map) dst[w0 + lane] = mine;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// CDF build.  stats[b] = {vmin, vmax, m (= min of h), S (= np.sum of w)}
+// ------------------------------------------------------------------------------------------------------------------
+struct LeafOp {
+    int32_t a, b;  // leaf: (offset, len)   combine: (dst slot, src slot)
+};
+
+// planner-side heat value h_j from the raw network output (SURVEY a21 + a3/a4); all fp32, each op rounded separately
+__device__ __forceinline__ float heat_value(float x, int mode, float vmin, float vmax) {
+    if (mode == 0) return __fadd_rn(fminf(fmaxf(x, -3.0f), 1.0f), 10.0f);  // clamp(-3,1) ; heat_map[0] + 10
+    if (mode == 1) {
+        const float v = __fdiv_rn(__fsub_rn(x, vmin), __fsub_rn(vmax, vmin));  // (v - min) / (max - min) * 1.0
+        const float masked = (v > 0.96f) ? v : 0.0f;                           // v[~(v > 0.96)] = 0
+        return __fsub_rn(masked, 250.0f);                                      // heat_map - 250
+    }
+    return x;
+}
+
+__device__ __forceinline__ float block_reduce_min(float v, float* red, bool is_max) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, t) : fminf(v, t);
+    }
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float r = red[0];
+    for (int w = 1; w < nw; ++w) r = is_max ? fmaxf(r, red[w]) : fminf(r, red[w]);
+    return r;
+}
+
+// One CTA per task: min/max, then NumPy's pairwise sum of w = h - m with the exact tree (leaves of <=128 elements with
+// 8 strided accumulators, binary combine tree as laid out by the host in `ops`).
+__global__ void __launch_bounds__(256) cdf_stats_kernel(const float* __restrict__ logits, int mode, int64_t cells,
+                                                        const LeafOp* __restrict__ leaves, int n_leaves,
+                                                        const LeafOp* __restrict__ ops, const int32_t* __restrict__ level_off,
+                                                        int n_levels, float4* __restrict__ stats) {
+    extern __shared__ float leaf_sum[];  // [n_leaves]
+    __shared__ float red[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const float* x = logits + (size_t)b * cells;
+
+    float vmin = 0.f, vmax = 0.f;
+    if (mode == 1) {
+        float lo = INFINITY, hi = -INFINITY;
+        for (int64_t j = tid; j < cells; j += blockDim.x) { const float v = __ldg(x + j); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        vmin = block_reduce_min(lo, red, false);
+        vmax = block_reduce_min(hi, red, true);
+    }
+    float m = INFINITY;
+    for (int64_t j = tid; j < cells; j += blockDim.x) m = fminf(m, heat_value(__ldg(x + j), mode, vmin, vmax));
+    m = block_reduce_min(m, red, false);
+
+    for (int l = tid; l < n_leaves; l += blockDim.x) {
+        const int off = leaves[l].a, len = leaves[l].b;
+        const float* a = x + off;
+        float res;
+        if (len < 8) {
+            res = __fsub_rn(heat_value(__ldg(a), mode, vmin, vmax), m);
+            for (int i = 1; i < len; ++i) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + i), mode, vmin, vmax), m));
+        } else {
+            float r[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __fsub_rn(heat_value(__ldg(a + k), mode, vmin, vmax), m);
+            int i = 8;
+            for (; i < len - (len % 8); i += 8) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], __fsub_rn(heat_value(__ldg(a + i + k), mode, vmin, vmax), m));
+            }
+            res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                            __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+            for (; i < len; ++i) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + i), mode, vmin, vmax), m));
+        }
+        leaf_sum[l] = res;
+    }
+    __syncthreads();
+    for (int lv = 0; lv < n_levels; ++lv) {  // deepest level first; left child's slot accumulates
+        const int lo = level_off[lv], hi = level_off[lv + 1];
+        for (int o = lo + tid; o < hi; o += blockDim.x) leaf_sum[ops[o].a] = __fadd_rn(leaf_sum[ops[o].a], leaf_sum[ops[o].b]);
+        __syncthreads();
+    }
+    if (tid == 0) stats[b] = make_float4(vmin, vmax, m, leaf_sum[0]);
+}
+
+// Sequential fp32 cumsum with NumPy's rounding, 32 tasks per warp (lane = task): a [32 tasks x 32 cells] tile is loaded
+// with coalesced rows, p = fl32(w / S) is computed element-parallel, the tile is transposed through shared memory and
+// every lane carries its own task's running sum through its row.
+__global__ void __launch_bounds__(32) cdf_chain_kernel(const float* __restrict__ logits, int mode, int B, int64_t cells,
+                                                       const float4* __restrict__ stats, float* __restrict__ cdf) {
+    __shared__ float tile[32][33];
+    const int lane = threadIdx.x;
+    const int b0 = blockIdx.x * 32;
+    const int rows = min(32, B - b0);
+    const int my_task = b0 + lane;
+    float acc = 0.f;
+    bool first = true;
+    float4 st_row[1];
+    (void)st_row;
+    for (int64_t c0 = 0; c0 < cells; c0 += 32) {
+        const int64_t c = c0 + lane;
+#pragma unroll 4
+        for (int r = 0; r < rows; ++r) {
+            const float4 st = __ldg(stats + b0 + r);
+            float p = 0.f;
+            if (c < cells) {
+                const float h = heat_value(__ldg(logits + (size_t)(b0 + r) * cells + c), mode, st.x, st.y);
+                p = __fdiv_rn(__fsub_rn(h, st.z), st.w);
+            }
+            tile[r][lane] = p;
+        }
+        __syncwarp();
+        if (lane < rows) {
+            const int nc = (int)min((int64_t)32, cells - c0);
+            for (int q = 0; q < nc; ++q) {
+                const float p = tile[lane][q];
+                acc = first ? p : __fadd_rn(acc, p);
+                first = false;
+                tile[lane][q] = acc;
+            }
+        }
+        __syncwarp();
+        if (c < cells) {
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) cdf[(size_t)(b0 + r) * cells + c] = tile[r][lane];
+        }
+        __syncwarp();
+    }
+    (void)my_task;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// per-iteration sample draws, one warp per task
+// ------------------------------------------------------------------------------------------------------------------
+struct DrawArgs {
+    NrrtPlanParams p;
+    const uint32_t* occ_bits;
+    const int32_t* task_to_map;
+    const float* cdf;
+    const int32_t* task_ids;
+    int B;
+    int16_t* samples;
+    int8_t* neural_flag;
+    int64_t* n_draws;
+    int32_t* draw_status;
+    int words_per_map;
+    int64_t cells;
+};
+
+// first index j in [0, n] with !(cdf[j] < u) (np.searchsorted side='left', fp64 compare, NaN sorts last), 32-ary search
+__device__ __forceinline__ int64_t cdf_search_warp(const float* __restrict__ cdf, int64_t n, double u, int lane) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t len = hi - lo;
+        const int64_t step = (len + 31) >> 5;
+        const int64_t q = lo + (int64_t)(lane + 1) * step - 1;
+        bool ge = true;
+        if (q < hi) ge = !((double)__ldg(cdf + q) < u);
+        const uint32_t bal = __ballot_sync(0xffffffffu, ge);
+        const int f = bal ? (__ffs(bal) - 1) : 32;
+        const int64_t qf = lo + (int64_t)(f + 1) * step - 1;
+        lo = lo + (int64_t)f * step;
+        hi = (f < 32 && qf < hi) ? qf : hi;
+        if (lo > hi) lo = hi;
+    }
+    return lo;
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= a.B) return;
+    const uint32_t* grid = a.occ_bits + (size_t)a.task_to_map[b] * a.words_per_map;
+    const float* cdf = a.cdf ? a.cdf + (size_t)b * a.cells : nullptr;
+    const uint32_t stream_id = (uint32_t)a.task_ids[b];
+    const uint64_t seed = a.p.seed;
+    const int s0 = a.p.shape[0], s1 = a.p.shape[1], s2 = DIM == 3 ? a.p.shape[2] : 1;
+    const int max_iter = a.p.max_iterations;
+    int16_t* out = a.samples + (size_t)b * max_iter * DIM;
+
+    uint64_t k = 0, blk = ~0ull;
+    double u_lane = 0.0;
+    auto next_u = [&]() -> double {  // draws are generated 32 at a time (one per lane) and consumed in order
+        if ((k >> 5) != blk) {
+            blk = k >> 5;
+            u_lane = nrrt_uniform(seed, stream_id, (blk << 5) + lane);
+        }
+        const double u = __shfl_sync(0xffffffffu, u_lane, (int)(k & 31));
+        ++k;
+        return u;
+    };
+    auto randint0 = [&](int n) -> int {  // random.randint(0, n - 1) on the shared stream
+        const int v = __double2int_rd(__dmul_rn(next_u(), (double)n));
+        return min(v, n - 1);
+    };
+    auto is_free = [&](int64_t idx) -> bool { return (__ldg(grid + (idx >> 5)) >> (idx & 31)) & 1u; };
+
+    int status = 0;
+    int16_t keep[DIM];
+    int8_t keep_flag = 0;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) keep[d] = 0;
+    int it = 0;
+    for (; it < max_iter && status == 0; ++it) {
+        bool use_neural = false;
+        if (cdf) use_neural = next_u() < a.p.neural_bias;  // random.random() < self.neural_bias
+        int c[3] = {0, 0, 0};
+        int rej = 0;
+        for (;;) {
+            if (use_neural) {
+                const double u = next_u();  // random.uniform(0, 1) = 0 + (1 - 0) * random()
+                int64_t idx = cdf_search_warp(cdf, a.cells, u, lane);
+                idx = idx > a.cells - 1 ? a.cells - 1 : idx;  // min(max(index, 0), N - 1)
+                if (DIM == 2) { c[0] = (int)(idx / s1); c[1] = (int)(idx % s1); break; }
+                const int64_t yz = (int64_t)s1 * s2;
+                c[0] = (int)(idx / yz); c[1] = (int)((idx % yz) / s2); c[2] = (int)(idx % s2);
+                if (is_free(idx)) break;
+            } else if (DIM == 2) {
+                const int x = randint0(s1);  // x = randint(0, map_width - 1)
+                const int y = randint0(s0);  // y = randint(0, map_height - 1)
+                if (is_free((int64_t)y * s1 + x)) { c[0] = y; c[1] = x; break; }
+            } else {
+                const int x = randint0(s1);  // map_width = shape[1] (sic), indexes axis 0
+                const int y = randint0(s0);
+                const int z = randint0(s2);
+                const int xi = min(x, s0 - 1), yi = min(y, s1 - 1);
+                if (is_free(((int64_t)xi * s1 + yi) * s2 + z)) { c[0] = x; c[1] = y; c[2] = z; break; }
+            }
+            if (++rej >= a.p.max_reject) { status = NRRT_SAMPLER_STUCK; break; }
+        }
+        if (lane == (it & 31)) {
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) keep[d] = (int16_t)c[d];
+            keep_flag = (int8_t)use_neural;
+        }
+        if ((it & 31) == 31 || it == max_iter - 1 || status != 0) {  // flush up to 32 samples, one per lane
+            const int base = it & ~31;
+            if (base + lane <= it) {
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) out[(size_t)(base + lane) * DIM + d] = keep[d];
+                if (a.neural_flag) a.neural_flag[(size_t)b * max_iter + base + lane] = keep_flag;
+            }
+        }
+    }
+    if (lane == 0) {
+        a.draw_status[b] = status;
+        if (a.n_draws) a.n_draws[b] = (int64_t)k;
+    }
+}
+
+// NumPy pairwise-sum tree for n elements (numpy/_core/src/umath/loops_utils.h.src pairwise_sum):
+// leaves in array order; combine ops grouped by depth, deepest first; every op adds the right child's slot into the
+// left child's slot, so slot 0 ends up holding the root.
+struct Tree {
+    std::vector<LeafOp> leaves;
+    std::vector<std::vector<LeafOp>> by_depth;
+    int build(int64_t off, int64_t n, int depth) {  // returns the slot holding this subtree's sum
+        if (n <= 128) {
+            leaves.push_back({(int32_t)off, (int32_t)n});
+            return (int)leaves.size() - 1;
+        }
+        int64_t n2 = n / 2;
+        n2 -= n2 % 8;
+        const int l = build(off, n2, depth + 1);
+        const int r = build(off + n2, n - n2, depth + 1);
+        if ((int)by_depth.size() <= depth) by_depth.resize(depth + 1);
+        by_depth[depth].push_back({l, r});
+        return l;
+    }
+};
+
+}  // namespace
+
+extern "C" size_t nrrt_words_per_map(int64_t cells) { return (size_t)((((cells + 31) >> 5) + 3) & ~(int64_t)3); }
+
+extern "C" int nrrt_pack_occupancy(const void* occ, int dtype, int free_is_nonzero, int n_maps, int64_t cells,
+                                   uint32_t* bits, void* stream) {
+    NRRT_REQUIRE(occ && bits, "null pointer");
+    NRRT_REQUIRE(n_maps >= 0 && cells > 0 && cells < ((int64_t)1 << 31), "bad sizes");
+    NRRT_REQUIRE(dtype >= 0 && dtype <= 2, "dtype must be 0 (u8), 1 (f32) or 2 (f64)");
+    if (n_maps == 0) return NRRT_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int wpm = (int)nrrt_words_per_map(cells);
+    const int warps_needed = (wpm + 31) / 32;
+    dim3 grid((unsigned)std::min(64, (warps_needed + 7) / 8), (unsigned)n_maps);
+    if (dtype == 0) pack_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)occ, free_is_nonzero, cells, wpm, bits);
+    else if (dtype == 1) pack_kernel<float><<<grid, 256, 0, st>>>((const float*)occ, free_is_nonzero, cells, wpm, bits);
+    else pack_kernel<double><<<grid, 256, 0, st>>>((const double*)occ, free_is_nonzero, cells, wpm, bits);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" size_t nrrt_cdf_workspace_bytes(int B, int64_t cells) {
+    const size_t max_leaves = (size_t)(cells / 64 + 2);  // every leaf of a split has > 64 elements
+    return align_up((size_t)B * sizeof(float4), 256) + align_up(max_leaves * sizeof(LeafOp), 256) * 2 + 256 * sizeof(int32_t);
+}
+
+extern "C" int nrrt_cdf_build(const float* logits, int mode, int B, int64_t cells, float* cdf, void* workspace,
+                              size_t ws_bytes, void* stream) {
+    NRRT_REQUIRE(logits && cdf && workspace, "null pointer");
+    NRRT_REQUIRE(mode >= 0 && mode <= 2, "mode must be 0 (2D), 1 (3D) or 2 (raw heat map)");
+    NRRT_REQUIRE(B >= 0 && cells > 0 && cells < ((int64_t)1 << 31), "bad sizes");
+    if (ws_bytes < nrrt_cdf_workspace_bytes(B, cells)) return nrrt_fail(NRRT_ERR_WORKSPACE, "cdf workspace too small: %zu < %zu", ws_bytes, nrrt_cdf_workspace_bytes(B, cells));
+    if (B == 0) return NRRT_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+
+    Tree t;
+    t.build(0, cells, 0);
+    std::vector<LeafOp> ops;
+    std::vector<int32_t> level_off;
+    level_off.push_back(0);
+    for (int d = (int)t.by_depth.size() - 1; d >= 0; --d) {
+        ops.insert(ops.end(), t.by_depth[d].begin(), t.by_depth[d].end());
+        level_off.push_back((int32_t)ops.size());
+    }
+    NRRT_REQUIRE(level_off.size() <= 256, "pairwise tree too deep");
+    const size_t max_leaves = (size_t)(cells / 64 + 2);
+    NRRT_REQUIRE(t.leaves.size() <= max_leaves && ops.size() <= max_leaves, "pairwise tree larger than workspace");
+
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float4* stats = reinterpret_cast<float4*>(ws);
+    ws += align_up((size_t)B * sizeof(float4), 256);
+    LeafOp* d_leaves = reinterpret_cast<LeafOp*>(ws);
+    ws += align_up(max_leaves * sizeof(LeafOp), 256);
+    LeafOp* d_ops = reinterpret_cast<LeafOp*>(ws);
+    ws += align_up(max_leaves * sizeof(LeafOp), 256);
+    int32_t* d_level = reinterpret_cast<int32_t*>(ws);
+    // pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may die at scope exit
+    NRRT_CUDA_TRY(cudaMemcpyAsync(d_leaves, t.leaves.data(), t.leaves.size() * sizeof(LeafOp), cudaMemcpyHostToDevice, st));
+    if (!ops.empty()) NRRT_CUDA_TRY(cudaMemcpyAsync(d_ops, ops.data(), ops.size() * sizeof(LeafOp), cudaMemcpyHostToDevice, st));
+    NRRT_CUDA_TRY(cudaMemcpyAsync(d_level, level_off.data(), level_off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+
+    const size_t smem = t.leaves.size() * sizeof(float);
+    NRRT_REQUIRE(smem <= 200 * 1024, "map too large for the leaf-sum buffer");
+    NRRT_CUDA_TRY(cudaFuncSetAttribute(cdf_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cdf_stats_kernel<<<B, 256, smem, st>>>(logits, mode, cells, d_leaves, (int)t.leaves.size(), d_ops, d_level,
+                                           (int)level_off.size() - 1, stats);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    cdf_chain_kernel<<<(B + 31) / 32, 32, 0, st>>>(logits, mode, B, cells, stats, cdf);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_draw_samples(const NrrtPlanParams* p, const uint32_t* occ_bits, const int32_t* task_to_map,
+                                 const float* cdf, const int32_t* task_ids, int B, int16_t* samples, int8_t* neural_flag,
+                                 int64_t* n_draws, int32_t* draw_status, void* stream) {
+    NRRT_REQUIRE(p && occ_bits && task_to_map && task_ids && samples && draw_status, "null pointer");
+    NRRT_REQUIRE(p->dim == 2 || p->dim == 3, "dim must be 2 or 3, got %d", p->dim);
+    NRRT_REQUIRE(B >= 0 && p->max_iterations >= 1 && p->max_reject >= 1, "bad sizes");
+    if (B == 0) return NRRT_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    DrawArgs a;
+    a.p = *p; a.occ_bits = occ_bits; a.task_to_map = task_to_map; a.cdf = cdf; a.task_ids = task_ids; a.B = B;
+    a.samples = samples; a.neural_flag = neural_flag; a.n_draws = n_draws; a.draw_status = draw_status;
+    a.cells = (int64_t)p->shape[0] * p->shape[1] * (p->dim == 3 ? p->shape[2] : 1);
+    a.words_per_map = (int)nrrt_words_per_map(a.cells);
+    const int warps = 4;
+    if (p->dim == 2) draw_kernel<2><<<(B + warps - 1) / warps, warps * 32, 0, st>>>(a);
+    else draw_kernel<3><<<(B + warps - 1) / warps, warps * 32, 0, st>>>(a);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}

@@ -1,0 +1,230 @@
+"""Batched planning engine: thousands of independent RRT* tasks per call on one B200 through libnrrt.so.
+
+PyTorch is used for device memory and streams only; every computation on the planning path is a hand-written CUDA
+kernel behind the C ABI in include/nrrt.h.  The reference's Python classes (`rrt_star.RRTStar` etc.) are thin B=1 views
+over this engine (see the sibling drop-in modules).
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NrrtPlanOut, NrrtPlanParams, check
+
+HEAT_MODE_2D, HEAT_MODE_3D, HEAT_MODE_RAW = 0, 1, 2
+_DTYPE_CODE = {torch.uint8: 0, torch.bool: 0, torch.float32: 1, torch.float64: 2}
+_radius_cache = {}
+
+
+def radius_table(dim: int, shape: Sequence[int], max_iterations: int) -> np.ndarray:
+    """compute_search_radius for i = 1..max_iterations (rrt_star.py:174-182, ThreeD_rrt_star.py:183-191).
+
+    Task-independent, so it is evaluated once on the host with Python `math` — exactly the reference's expression,
+    including the 3D volume `map_width * map_height * map_width` (ThreeD_rrt_star.py:187) and r_1 = 0.
+    """
+    key = (dim, tuple(int(s) for s in shape), int(max_iterations))
+    tab = _radius_cache.get(key)
+    if tab is None:
+        if dim == 2:
+            map_height, map_width = key[1][:2]
+            volume = map_width * map_height
+        else:
+            map_height, map_width, _ = key[1][:3]
+            volume = map_width * map_height * map_width
+        lebesgue = math.pow(math.pi, dim / 2.0) / math.gamma((dim / 2.0) + 1)
+        tab = np.empty(max_iterations, dtype=np.float64)
+        for i in range(1, max_iterations + 1):
+            tab[i - 1] = math.pow(2 * (1 + 1.0 / dim) * (volume / lebesgue) * (math.log(i) / i), 1.0 / dim)
+        _radius_cache[key] = tab
+    return tab
+
+
+def _dev(t, dtype=None, device=None):
+    if isinstance(t, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(t))
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if device is not None and t.device != device:
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.NrrtError("mgr_sampling_cnn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device(device if device is not None else "cuda")
+
+
+def pack_occupancy(occ_maps, dim: int, device=None) -> torch.Tensor:
+    """[n_maps, *shape] occupancy (uint8 / float32 / float64) -> bit-packed [n_maps, words] uint32 (1 = free).
+
+    2D: free iff value != 0 (rrt_star.py:67,120).  3D: free iff value == 0 (ThreeD_rrt_star.py:69,128).
+    """
+    device = _require_cuda(device)
+    occ = _dev(occ_maps, device=device)
+    if occ.dtype == torch.bool:
+        occ = occ.view(torch.uint8)
+    if occ.dtype not in _DTYPE_CODE:
+        occ = occ.to(torch.float32)
+    n_maps = occ.shape[0]
+    cells = int(np.prod(occ.shape[1:]))
+    lib = _lib.load()
+    words = lib.nrrt_words_per_map(cells)
+    bits = torch.empty((n_maps, words), dtype=torch.int32, device=device)
+    check(lib.nrrt_pack_occupancy(_ptr(occ), _DTYPE_CODE[occ.dtype], 1 if dim == 2 else 0, n_maps, cells, _ptr(bits),
+                                  _stream_ptr(device)))
+    return bits
+
+
+def build_cdf(logits, mode: int, device=None) -> torch.Tensor:
+    """Network output (or a ready heat map, mode RAW) [B, cells...] float32 -> sampler CDF [B, cells] float32.
+
+    Post-processing + `generate_neural_sample`'s normalisation/cumsum with NumPy's fp32 rounding,
+    hoisted out of the per-draw path.
+    """
+    device = _require_cuda(device)
+    x = _dev(logits, torch.float32, device)
+    B = x.shape[0]
+    x = x.reshape(B, -1)
+    cells = x.shape[1]
+    lib = _lib.load()
+    ws_bytes = lib.nrrt_cdf_workspace_bytes(B, cells)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+    cdf = torch.empty((B, cells), dtype=torch.float32, device=device)
+    check(lib.nrrt_cdf_build(_ptr(x), mode, B, cells, _ptr(cdf), _ptr(ws), ws_bytes, _stream_ptr(device)))
+    return cdf
+
+
+@dataclass
+class PlanResult:
+    """Per-task results (device tensors).  Mirrors NrrtPlanOut in include/nrrt.h."""
+    n_nodes: torch.Tensor
+    iterations: torch.Tensor
+    status: torch.Tensor
+    goal_node: torch.Tensor
+    best_node: torch.Tensor
+    best_dist: torch.Tensor
+    path_n: torch.Tensor
+    path_idx: torch.Tensor
+    path_len: torch.Tensor
+    cost: torch.Tensor
+    parent: torch.Tensor
+    pos: Optional[torch.Tensor] = None
+    samples: Optional[torch.Tensor] = None
+    neural_flag: Optional[torch.Tensor] = None
+    n_draws: Optional[torch.Tensor] = None
+    trace: Optional[torch.Tensor] = None
+    trace_n: Optional[torch.Tensor] = None
+
+    def solved_fraction(self) -> float:
+        return float((self.status == _lib.NRRT_SOLVED).float().mean().item())
+
+    def path_points(self, b: int) -> np.ndarray:
+        """find_path() of task b as an (m, dim) float64 array (needs keep_tree=True)."""
+        if self.pos is None:
+            raise ValueError("plan_batch(keep_tree=True) is required for path_points")
+        m = int(self.path_n[b].item())
+        idx = self.path_idx[b, :m].long()
+        return self.pos[b, idx].cpu().numpy()
+
+
+class PlannerBuffers:
+    """Caller-owned device buffers for one (dim, B, max_iterations) configuration, reusable across calls."""
+
+    def __init__(self, dim, B, max_iterations, path_cap, keep_tree, trace_cap, device):
+        stride = max_iterations + 2
+        self.node_stride = stride
+        i32, f64 = torch.int32, torch.float64
+        z = lambda *s, dtype=i32: torch.empty(s, dtype=dtype, device=device)  # noqa: E731
+        self.cost = z(B, stride, dtype=f64)
+        self.parent = z(B, stride)
+        self.pos = z(B, stride, dim, dtype=f64) if keep_tree else None
+        self.n_nodes, self.iterations, self.status = z(B), z(B), z(B)
+        self.goal_node, self.best_node = z(B), z(B)
+        self.best_dist = z(B, dtype=f64)
+        self.path_n = z(B)
+        self.path_idx = z(B, max(path_cap, 1))
+        self.path_len = z(B, dtype=f64)
+        self.trace = z(B, trace_cap, 4) if trace_cap > 0 else None
+        self.trace_n = z(B) if trace_cap > 0 else None
+        self.samples = z(B, max_iterations, dim, dtype=torch.int16)
+        self.neural_flag = z(B, max_iterations, dtype=torch.int8)
+        self.n_draws = z(B, dtype=torch.int64)
+        self.draw_status = z(B)
+        self.queue = z(1)
+
+
+def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, shape: Sequence[int],
+               max_iterations: int = 5000, goal_threshold: Optional[float] = None, cdf: Optional[torch.Tensor] = None,
+               neural_bias: float = 0.75, seed: int = 0, task_ids=None, samples=None, keep_tree: bool = False,
+               trace_cap: int = 0, path_cap: int = 512, max_reject: int = 100000,
+               buffers: Optional[PlannerBuffers] = None) -> PlanResult:
+    """Run B independent RRT* plans (`RRTStar(...).rrt_star()` of the four reference modules) on the current stream.
+
+    occ_bits   [n_maps, words] from pack_occupancy;  task_to_map [B];  starts/goals [B, dim] int (reference order:
+               (y, x) in 2D, (x, y, z) in 3D);  cdf [B, cells] from build_cdf selects the neural modules, None the uniform ones.
+    samples    optional pre-drawn sample points [B, max_iterations, dim] int16 (parity level A); otherwise they are
+               drawn on the device from the Philox stream (seed, task_ids[b]).
+    """
+    device = occ_bits.device
+    if device.type != "cuda":
+        raise _lib.NrrtError("occ_bits must live on a CUDA device")
+    lib = _lib.load()
+    shape = [int(s) for s in shape]
+    if goal_threshold is None:
+        goal_threshold = 5.0 if dim == 2 else 3.0
+    starts = _dev(starts, torch.int32, device).reshape(-1, dim)
+    goals = _dev(goals, torch.int32, device).reshape(-1, dim)
+    B = starts.shape[0]
+    task_to_map = _dev(task_to_map, torch.int32, device).reshape(-1)
+    task_ids = _dev(np.arange(B, dtype=np.int32) if task_ids is None else task_ids, torch.int32, device).reshape(-1)
+    if not (goals.shape[0] == B and task_to_map.shape[0] == B and task_ids.shape[0] == B):
+        raise ValueError("starts, goals, task_to_map and task_ids must agree on the batch size")
+    radius = _dev(radius_table(dim, shape, max_iterations), torch.float64, device)
+    buf = buffers or PlannerBuffers(dim, B, max_iterations, path_cap, keep_tree, trace_cap, device)
+
+    p = NrrtPlanParams()
+    p.dim = dim
+    for k in range(3):
+        p.shape[k] = shape[k] if k < len(shape) else 1
+    p.max_iterations, p.node_stride, p.max_reject, p.path_cap = max_iterations, buf.node_stride, max_reject, path_cap
+    p.goal_threshold, p.neural_bias, p.seed = float(goal_threshold), float(neural_bias), int(seed) & (2 ** 64 - 1)
+    st = _stream_ptr(device)
+
+    draw_status = None
+    if samples is None:
+        if cdf is not None:
+            cdf = _dev(cdf, torch.float32, device)
+        check(lib.nrrt_draw_samples(C.byref(p), _ptr(occ_bits), _ptr(task_to_map), _ptr(cdf), _ptr(task_ids), B,
+                                    _ptr(buf.samples), _ptr(buf.neural_flag), _ptr(buf.n_draws), _ptr(buf.draw_status), st))
+        samples_t, draw_status = buf.samples, buf.draw_status
+    else:
+        samples_t = _dev(samples, torch.int16, device).reshape(B, max_iterations, dim)
+
+    out = NrrtPlanOut()
+    out.pos, out.cost, out.parent = _ptr(buf.pos), _ptr(buf.cost), _ptr(buf.parent)
+    out.n_nodes, out.iterations, out.status = _ptr(buf.n_nodes), _ptr(buf.iterations), _ptr(buf.status)
+    out.goal_node, out.best_node, out.best_dist = _ptr(buf.goal_node), _ptr(buf.best_node), _ptr(buf.best_dist)
+    out.path_n, out.path_idx, out.path_len = _ptr(buf.path_n), _ptr(buf.path_idx), _ptr(buf.path_len)
+    out.trace, out.trace_n, out.trace_cap = _ptr(buf.trace), _ptr(buf.trace_n), trace_cap
+    check(lib.nrrt_plan_batch(C.byref(p), _ptr(occ_bits), _ptr(task_to_map), _ptr(radius), _ptr(samples_t), _ptr(starts),
+                              _ptr(goals), _ptr(draw_status), C.byref(out), B, _ptr(buf.queue), st))
+    return PlanResult(n_nodes=buf.n_nodes, iterations=buf.iterations, status=buf.status, goal_node=buf.goal_node,
+                      best_node=buf.best_node, best_dist=buf.best_dist, path_n=buf.path_n, path_idx=buf.path_idx,
+                      path_len=buf.path_len, cost=buf.cost, parent=buf.parent, pos=buf.pos, samples=samples_t,
+                      neural_flag=buf.neural_flag if samples is None else None,
+                      n_draws=buf.n_draws if samples is None else None, trace=buf.trace, trace_n=buf.trace_n)
