@@ -117,6 +117,64 @@ int nrrt_plan_batch(const NrrtPlanParams* p, const uint32_t* occ_bits, const int
 /* Shared memory one planner CTA needs for these params (bytes), and CTAs per SM the launch will get (info only). */
 int nrrt_plan_smem_bytes(const NrrtPlanParams* p, size_t* bytes, int* ctas_per_sm);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * CNN forward (UNet_cooler.forward train.py:171-203, ThreeD_UNet_cooler.forward ThreeD_train.py:169-204).
+ * Activations are fp16 channels-last (NHWC / NDHWC); accumulation is fp32 in tensor memory.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef enum NrrtConvKind {
+    NRRT_CONV_K3S1 = 0,  /* nn.Conv2d/3d(k=3, s=1, p=1): encoder stem, ResNet blocks, decoder convs */
+    NRRT_CONV_K3S2 = 1,  /* nn.Conv2d/3d(k=3, s=2, p=1): first conv of layer2/3/4 */
+    NRRT_CONV_K1S2 = 2,  /* nn.Conv2d/3d(k=1, s=2):      ResNet downsample branch */
+    NRRT_CONV_K1S1 = 3,  /* nn.Conv2d/3d(k=1) */
+    NRRT_CONVT_K2S2 = 4  /* nn.ConvTranspose2d/3d(k=2, s=2): upconv6/7/8 */
+} NrrtConvKind;
+
+/* One fused layer: out = [relu2(post_scale * ] relu( scale * conv(in) + shift + residual ) [ + post_shift)].
+ * weight: fp16 [rows][taps][cin], rows = cout (conv) or groups*cout (ConvTranspose: group g = (a*2+b) in 2D,
+ *         ((a*2+b)*2+c) in 3D for output offset (a,b[,c])), taps in (kd, kh, kw) order; scale/shift: fp32 [rows]. */
+typedef struct NrrtConvLayer {
+    int32_t dims;            /* 2 or 3 */
+    int32_t kind;            /* NrrtConvKind */
+    int32_t n, in_d, in_h, in_w;   /* input grid (in_d ignored in 2D) */
+    int32_t cin;             /* input channels read (multiple of 64) */
+    int32_t cout;            /* output channels (multiple of 32; rows must tile by 64) */
+    const void* in;          /* fp16, first channel of the slice to read */
+    int64_t in_cstride;      /* channels per pixel of the input buffer */
+    const void* weight;
+    const float* scale;
+    const float* shift;
+    void* out;               /* fp16 output buffer base */
+    int64_t out_cstride;     /* channels per pixel of the output buffer (concat target) */
+    int64_t out_coffset;     /* first output channel inside that buffer */
+    const void* res;         /* optional fp16 residual, same pixel grid as out */
+    int64_t res_cstride, res_coffset;
+    int32_t relu;
+    const float* post_scale; /* optional second affine + ReLU (3D stem: conv, ReLU, BatchNorm3d, ReLU) */
+    const float* post_shift;
+} NrrtConvLayer;
+
+int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);
+
+/* First layer (Cin = 3 in 2D, 1 in 3D; fp32 NCHW / NCDHW input as the reference feeds it) -> fp16 channels-last with
+ * `cout_pad` channels (cout real, the rest zero), + bias, ReLU.  weight fp32 [cout][cin][taps], bias fp32 [cout]. */
+int nrrt_stem_conv(int dims, const float* x, int n, int cin, int d, int h, int w, const float* weight, const float* bias,
+                   int cout, int cout_pad, void* out, void* stream);
+
+/* Coordinate branch (train.py:179-190): the four conv_coords_* layers (3x3 Conv2d + ReLU) on the (B,1,2,2) / (B,1,2,3)
+ * coords tensor in fp32.  weights/biases: 4 pointers, PyTorch layout [cout][cin][3][3].  feats: 4 output pointers,
+ * fp32 [B][gh*gw][C] with C = 64, 128, 256, 512. */
+int nrrt_coords_branch(const float* coords, int B, int gh, int gw, const float* const* weights, const float* const* biases,
+                       float* const* feats, void* stream);
+
+/* F.interpolate(feat, size, mode='bilinear'/'trilinear', align_corners=True) of a (gh x gw [x 1]) coordinate feature,
+ * written as fp16 into channels [out_coffset, out_coffset + C) of a channels-last buffer (the torch.cat target). */
+int nrrt_coords_fill(const float* feat, int B, int gh, int gw, int C, int dims, int od, int oh, int ow, void* out,
+                     int64_t out_cstride, int64_t out_coffset, void* stream);
+
+/* final_conv (1x1, C -> 1): fp16 channels-last in, fp32 logits out [B][pixels]. */
+int nrrt_head_1x1(const void* in, int64_t pixels, int C, int64_t in_cstride, const float* weight, float bias, float* logits,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

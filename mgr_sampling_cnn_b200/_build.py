@@ -12,6 +12,8 @@ SOURCES = {
     "abi.cu": [],
     "planner.cu": ["--fmad=false"],
     "sampler.cu": ["--fmad=false"],
+    "conv_tc.cu": [],
+    "conv_aux.cu": [],
 }
 COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
           "-I", os.path.join(_ROOT, "include"), "-I", CSRC]

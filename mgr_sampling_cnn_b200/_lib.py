@@ -25,6 +25,14 @@ class NrrtPlanOut(C.Structure):
                 ("trace", C.c_void_p), ("trace_n", C.c_void_p), ("trace_cap", C.c_int32)]
 
 
+class NrrtConvLayer(C.Structure):
+    _fields_ = [("dims", C.c_int32), ("kind", C.c_int32), ("n", C.c_int32), ("in_d", C.c_int32), ("in_h", C.c_int32),
+                ("in_w", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("in_", C.c_void_p), ("in_cstride", C.c_int64),
+                ("weight", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("out", C.c_void_p),
+                ("out_cstride", C.c_int64), ("out_coffset", C.c_int64), ("res", C.c_void_p), ("res_cstride", C.c_int64),
+                ("res_coffset", C.c_int64), ("relu", C.c_int32), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p)]
+
+
 _SIGNATURES = {
     "nrrt_version": (C.c_int, []),
     "nrrt_last_error": (C.c_char_p, []),
@@ -37,6 +45,13 @@ _SIGNATURES = {
     "nrrt_plan_batch": (C.c_int, [C.POINTER(NrrtPlanParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.POINTER(NrrtPlanOut), C.c_int, C.c_void_p, C.c_void_p]),
     "nrrt_plan_smem_bytes": (C.c_int, [C.POINTER(NrrtPlanParams), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "nrrt_conv_layer": (C.c_int, [C.POINTER(NrrtConvLayer), C.c_void_p]),
+    "nrrt_stem_conv": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nrrt_coords_branch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrrt_coords_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "nrrt_head_1x1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

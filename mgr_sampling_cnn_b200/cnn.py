@@ -1,0 +1,285 @@
+"""Host side of the CNN forward: packs the reference models' parameters for the tensor-core kernels and runs the layer
+graph of UNet_cooler.forward (train.py:171-203) / ThreeD_UNet_cooler.forward (ThreeD_train.py:169-204) through
+libnrrt.so.  PyTorch holds the parameters and the device buffers; every FLOP of the forward is a hand-written kernel
+(nrrt_conv_layer = tcgen05 implicit GEMM; nrrt_stem_conv / nrrt_coords_* / nrrt_head_1x1 = small CUDA-core kernels).
+
+Activations are fp16 channels-last.  The three `torch.cat` calls of the decoder never copy: producers write straight
+into channel slices of the concat buffers and TMA reads slices back out.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+K3S1, K3S2, K1S2, K1S1, CONVT = 0, 1, 2, 3, 4
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _fold_bn(bn, conv_bias, cout, device):
+    """eval-mode BatchNorm (+ optional conv bias) -> per-channel (scale, shift) in fp32."""
+    if bn is None:
+        scale = torch.ones(cout, dtype=torch.float32, device=device)
+        shift = torch.zeros(cout, dtype=torch.float32, device=device) if conv_bias is None else conv_bias.detach().float().to(device)
+        return scale.contiguous(), shift.contiguous()
+    g, b = bn.weight.detach().float().to(device), bn.bias.detach().float().to(device)
+    mu, var = bn.running_mean.detach().float().to(device), bn.running_var.detach().float().to(device)
+    scale = g / torch.sqrt(var + bn.eps)
+    shift = b - mu * scale
+    if conv_bias is not None:
+        shift = shift + conv_bias.detach().float().to(device) * scale
+    return scale.contiguous(), shift.contiguous()
+
+
+def _pack_conv_weight(w, cin_pad, device):
+    """[cout, cin, (kd,) kh, kw] -> fp16 [cout, taps, cin_pad] (taps in (kd, kh, kw) order, zero-padded channels)."""
+    w = w.detach().to(device=device, dtype=torch.float32)
+    cout, cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    w = w.reshape(cout, cin, taps).permute(0, 2, 1)  # [cout, taps, cin]
+    out = torch.zeros((cout, taps, cin_pad), dtype=torch.float16, device=device)
+    out[:, :, :cin] = w.to(torch.float16)
+    return out.contiguous()
+
+
+def _pack_convT_weight(w, device):
+    """ConvTranspose k=2 s=2 weight [cin, cout, (2,) 2, 2] -> fp16 [groups*cout, cin]; group g = offsets in (d,h,w) order."""
+    w = w.detach().to(device=device, dtype=torch.float32)
+    cin, cout = w.shape[0], w.shape[1]
+    groups = w[0, 0].numel()
+    w = w.reshape(cin, cout, groups).permute(2, 1, 0)  # [g, cout, cin]
+    return w.reshape(groups * cout, cin).to(torch.float16).contiguous()
+
+
+class _Layer(object):
+    """One nrrt_conv_layer call with its packed parameters (kept alive here)."""
+
+    def __init__(self, dims, kind, cin, cout, weight, scale, shift, relu, post=None):
+        self.dims, self.kind, self.cin, self.cout = dims, kind, cin, cout
+        self.weight, self.scale, self.shift, self.relu = weight, scale, shift, relu
+        self.post = post
+
+    def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0):
+        """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W)."""
+        L = _lib.NrrtConvLayer()
+        L.dims, L.kind = self.dims, self.kind
+        L.n, L.in_d, L.in_h, L.in_w = x.shape[0], grid[0], grid[1], grid[2]
+        L.cin, L.cout = self.cin, self.cout
+        esz = 2
+        L.in_ = C.c_void_p(x.data_ptr() + x_coff * esz)
+        L.in_cstride = x.shape[-1]
+        L.weight, L.scale, L.shift = _ptr(self.weight), _ptr(self.scale), _ptr(self.shift)
+        L.out, L.out_cstride, L.out_coffset = _ptr(out), out.shape[-1], out_coff
+        if res is not None:
+            L.res, L.res_cstride, L.res_coffset = _ptr(res), res.shape[-1], res_coff
+        L.relu = 1 if self.relu else 0
+        if self.post is not None:
+            L.post_scale, L.post_shift = _ptr(self.post[0]), _ptr(self.post[1])
+        check(lib.nrrt_conv_layer(C.byref(L), stream))
+
+
+class UNetPlan(object):
+    """Packed parameters + buffer plan of one UNet_cooler / ThreeD_UNet_cooler instance on one device."""
+
+    def __init__(self, model, dims, device):
+        self.dims, self.device = dims, device
+        self.lib = _lib.load()
+        d = dims
+        dev = device
+
+        def conv(m, kind, bn=None, relu=True, cin_pad=None, post=None):
+            cin_pad = cin_pad or m.in_channels
+            scale, shift = _fold_bn(bn, m.bias, m.out_channels, dev)
+            return _Layer(d, kind, cin_pad, m.out_channels, _pack_conv_weight(m.weight, cin_pad, dev), scale, shift, relu, post)
+
+        def convT(m):
+            groups = 2 ** d
+            scale = torch.ones(groups * m.out_channels, dtype=torch.float32, device=dev)
+            shift = m.bias.detach().float().to(dev).repeat(groups).contiguous()
+            return _Layer(d, CONVT, m.in_channels, m.out_channels, _pack_convT_weight(m.weight, dev), scale, shift, False)
+
+        def first_conv(seq):  # the Conv inside a torchvision Conv3DSimple is the module itself; 2D convs are plain
+            return seq
+
+        # ---- stem ----
+        if d == 2:
+            stem_seq = model.conv1  # Conv2d(3,32) ReLU Conv2d(32,64) ReLU            (train.py:118-123)
+            post = None
+        else:
+            stem_seq = model.conv1[0]  # r3d stem with stem[0] replaced                  (ThreeD_train.py:113-118)
+            bn = model.conv1[1]        # + BatchNorm3d(64) + ReLU left over from torchvision's BasicStem
+            post = _fold_bn(bn, None, 64, dev)
+        c0, c1 = stem_seq[0], stem_seq[2]
+        self.stem_w = c0.weight.detach().float().to(dev).reshape(c0.out_channels, -1).contiguous()
+        self.stem_b = c0.bias.detach().float().to(dev).contiguous()
+        self.stem_cin, self.stem_cout = c0.in_channels, c0.out_channels
+        self.stem2 = conv(c1, K3S1, None, True, cin_pad=64, post=post)
+
+        # ---- encoder: torchvision BasicBlocks ----
+        def blocks(layer):
+            out = []
+            for blk in layer:
+                if d == 2:
+                    cv1, cv2, b1, b2 = blk.conv1, blk.conv2, blk.bn1, blk.bn2
+                else:  # VideoResNet BasicBlock: conv1 = Sequential(Conv3DSimple, BN, ReLU), conv2 = Sequential(Conv3DSimple, BN)
+                    cv1, b1, cv2, b2 = blk.conv1[0], blk.conv1[1], blk.conv2[0], blk.conv2[1]
+                s2 = cv1.stride[0] == 2
+                ds = None
+                if blk.downsample is not None:
+                    ds = conv(blk.downsample[0], K1S2 if s2 else K1S1, blk.downsample[1], relu=False)
+                out.append((conv(cv1, K3S2 if s2 else K3S1, b1, True), conv(cv2, K3S1, b2, True), ds))
+            return out
+
+        self.enc = [blocks(model.conv2), blocks(model.conv3), blocks(model.conv4), blocks(model.conv5)]
+
+        # ---- coordinate branch (fp32, tiny) ----
+        self.cw = [m[0].weight.detach().float().to(dev).contiguous() for m in
+                   (model.conv_coords_64, model.conv_coords_128, model.conv_coords_256, model.conv_coords_512)]
+        self.cb = [m[0].bias.detach().float().to(dev).contiguous() for m in
+                   (model.conv_coords_64, model.conv_coords_128, model.conv_coords_256, model.conv_coords_512)]
+        self.cw_ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in self.cw])
+        self.cb_ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in self.cb])
+
+        # ---- decoder ----
+        self.up6, self.up7, self.up8 = convT(model.upconv6), convT(model.upconv7), convT(model.upconv8)
+        self.c6 = (conv(model.conv6[0], K3S1), conv(model.conv6[2], K3S1))
+        self.c7 = (conv(model.conv7[0], K3S1), conv(model.conv7[2], K3S1))
+        self.c8 = (conv(model.conv8[0], K3S1), conv(model.conv8[2], K3S1))
+        self.head_w = model.final_conv.weight.detach().float().to(dev).reshape(-1).contiguous()
+        self.head_b = float(model.final_conv.bias.detach().float().item())
+        self._bufs = {}
+
+    # activation buffers for a micro-batch of B samples on grid (D, H, W)
+    def _buffers(self, B, grid):
+        key = (B,) + tuple(grid)
+        bufs = self._bufs.get(key)
+        if bufs is None:
+            dev = self.device
+            D, H, W = grid
+
+            def buf(level, ch):
+                s = 2 ** level
+                shape = (B, D // s if self.dims == 3 else 1, H // s, W // s, ch)
+                return torch.empty(shape, dtype=torch.float16, device=dev)
+
+            bufs = {
+                "t0": buf(0, 64), "x1": buf(0, 64), "a0": buf(0, 64), "b0": buf(0, 64),
+                "cat8": buf(0, 192), "j": buf(0, 128), "k": buf(0, 64),
+                "a1": buf(1, 128), "b1": buf(1, 128), "d1": buf(1, 128), "cat7": buf(1, 384), "g7": buf(1, 256), "i": buf(1, 128),
+                "a2": buf(2, 256), "b2": buf(2, 256), "d2": buf(2, 256), "cat6": buf(2, 1024), "g6": buf(2, 512), "h": buf(2, 256),
+                "a3": buf(3, 512), "b3": buf(3, 512), "d3": buf(3, 512), "x5": buf(3, 1024),
+            }
+            P = 4 if self.dims == 2 else 6
+            bufs["feats"] = [torch.empty((B, P, c), dtype=torch.float32, device=dev) for c in (64, 128, 256, 512)]
+            bufs["feat_ptrs"] = (C.c_void_p * 4)(*[t.data_ptr() for t in bufs["feats"]])
+            self._bufs = {key: bufs}  # keep one configuration resident
+        return bufs
+
+    def activation_bytes(self, B, grid):
+        b = self._buffers(B, grid)
+        return sum(t.numel() * t.element_size() for t in b.values() if isinstance(t, torch.Tensor))
+
+    def forward(self, x, coords):
+        """x: fp32 (B,3,H,W) / (B,D,H,W) on self.device; coords: fp32 (B,1,2,2) / (B,1,2,3).  Returns fp32 logits
+        (B,1,H,W) / (B,1,D,H,W)."""
+        lib, dims = self.lib, self.dims
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        x = x.contiguous().float()
+        coords = coords.contiguous().float()
+        B = x.shape[0]
+        if dims == 2:
+            grid = (1, x.shape[2], x.shape[3])
+            if x.shape[1] != 3:
+                raise ValueError("UNet_cooler expects (B, 3, H, W)")
+        else:
+            grid = (x.shape[1], x.shape[2], x.shape[3])
+        if any(g % 8 for g in grid[(0 if dims == 3 else 1):]):
+            raise ValueError("spatial sizes must be multiples of 8 (three stride-2 stages)")
+        bf = self._buffers(B, grid)
+        g = [tuple(max(v // (2 ** lv), 1) if (dims == 3 or i > 0) else 1 for i, v in enumerate(grid)) for lv in range(4)]
+
+        # stem
+        check(lib.nrrt_stem_conv(dims, _ptr(x), B, self.stem_cin, grid[0], grid[1], grid[2], _ptr(self.stem_w),
+                                 _ptr(self.stem_b), self.stem_cout, 64, _ptr(bf["t0"]), st))
+        self.stem2.run(lib, st, bf["t0"], 0, g[0], bf["x1"], 0)
+
+        # encoder; the last conv of every stage writes into its concat buffer slice
+        def stage(blks, xin, xin_off, gin, gout, a, b, dsb, final, final_off):
+            (c1, c2, ds), (c3, c4, _) = blks
+            if ds is not None:
+                ds.run(lib, st, xin, xin_off, gin, dsb, 0)
+                res, res_off = dsb, 0
+            else:
+                res, res_off = xin, xin_off
+            c1.run(lib, st, xin, xin_off, gin, a, 0)
+            c2.run(lib, st, a, 0, gout, b, 0, res, res_off)
+            c3.run(lib, st, b, 0, gout, a, 0)
+            c4.run(lib, st, a, 0, gout, final, final_off, b, 0)
+
+        stage(self.enc[0], bf["x1"], 0, g[0], g[0], bf["a0"], bf["b0"], None, bf["cat8"], 64)
+        stage(self.enc[1], bf["cat8"], 64, g[0], g[1], bf["a1"], bf["b1"], bf["d1"], bf["cat7"], 128)
+        stage(self.enc[2], bf["cat7"], 128, g[1], g[2], bf["a2"], bf["b2"], bf["d2"], bf["cat6"], 512)
+        stage(self.enc[3], bf["cat6"], 512, g[2], g[3], bf["a3"], bf["b3"], bf["d3"], bf["x5"], 0)
+
+        # coordinate branch + align_corners interpolation into the concat slices (train.py:179-190)
+        gh, gw = coords.shape[2], coords.shape[3]
+        check(lib.nrrt_coords_branch(_ptr(coords), B, gh, gw, self.cw_ptrs, self.cb_ptrs, bf["feat_ptrs"], st))
+        for feat, ch, name, off, lv in ((0, 64, "cat8", 128, 0), (1, 128, "cat7", 256, 1), (2, 256, "cat6", 768, 2),
+                                        (3, 512, "x5", 512, 3)):
+            t = bf[name]
+            check(lib.nrrt_coords_fill(_ptr(bf["feats"][feat]), B, gh, gw, ch, dims, g[lv][0], g[lv][1], g[lv][2], _ptr(t),
+                                       t.shape[-1], off, st))
+
+        # decoder
+        self.up6.run(lib, st, bf["x5"], 0, g[3], bf["cat6"], 0)
+        self.c6[0].run(lib, st, bf["cat6"], 0, g[2], bf["g6"], 0)
+        self.c6[1].run(lib, st, bf["g6"], 0, g[2], bf["h"], 0)
+        self.up7.run(lib, st, bf["h"], 0, g[2], bf["cat7"], 0)
+        self.c7[0].run(lib, st, bf["cat7"], 0, g[1], bf["g7"], 0)
+        self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
+        self.up8.run(lib, st, bf["i"], 0, g[1], bf["cat8"], 0)
+        self.c8[0].run(lib, st, bf["cat8"], 0, g[0], bf["j"], 0)
+        self.c8[1].run(lib, st, bf["j"], 0, g[0], bf["k"], 0)
+
+        pixels = B * grid[0] * grid[1] * grid[2]
+        logits = torch.empty((B, 1) + (tuple(grid) if dims == 3 else tuple(grid[1:])), dtype=torch.float32, device=self.device)
+        check(lib.nrrt_head_1x1(_ptr(bf["k"]), pixels, 64, 64, _ptr(self.head_w), self.head_b, _ptr(logits), st))
+        return logits
+
+
+class CudaForwardMixin(object):
+    """forward() for the drop-in model classes: eval-mode inference through UNetPlan, micro-batched."""
+    _nrrt_dims = 2
+    micro_batch = 8
+
+    def _plan(self, device):
+        plan = getattr(self, "_nrrt_plan", None)
+        if plan is None or plan.device != device:
+            plan = UNetPlan(self, self._nrrt_dims, device)
+            object.__setattr__(self, "_nrrt_plan", plan)
+        return plan
+
+    def invalidate_plan(self):
+        """Call after changing parameters in place (load_state_dict does it automatically)."""
+        object.__setattr__(self, "_nrrt_plan", None)
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.invalidate_plan()
+        return out
+
+    def forward(self, x, coords):
+        if self.training:
+            raise _lib.NrrtError("mgr_sampling_cnn_b200 implements inference only: call model.eval() first "
+                                 "(training is out of scope, DESIGN.md)")
+        if not x.is_cuda:
+            raise _lib.NrrtError("forward() needs CUDA tensors: there is no CPU fallback (the oracle lives in oracle/)")
+        plan = self._plan(x.device)
+        with torch.no_grad():
+            outs = [plan.forward(x[i:i + self.micro_batch], coords[i:i + self.micro_batch])
+                    for i in range(0, x.shape[0], self.micro_batch)]
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)

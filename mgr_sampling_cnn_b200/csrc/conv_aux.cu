@@ -1,0 +1,210 @@
+// conv_aux.cu — the small CUDA-core pieces of the CNN forward that are not GEMM-shaped: the 3-/1-channel stem
+// convolution, the coordinate branch (4 tiny convs on a 2x2 / 2x3 grid), its align_corners interpolation into the
+// concat buffers, and the 1x1 output head.  (train.py:118-149,171-203; ThreeD_train.py:112-147,169-204.)
+#include <cuda_fp16.h>
+
+#include "nrrt_common.cuh"
+
+namespace {
+
+// ---- stem: direct 3x3(x3) convolution, Cin <= 4, fp32 NCHW in -> fp16 channels-last out, bias + ReLU --------------
+template <int DIMS>
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, int n, int cin, int D, int H, int W,
+                                                   const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
+                                                   int cout_pad, __half* __restrict__ out) {
+    extern __shared__ float s_w[];  // [cout][cin*taps] + bias[cout]
+    constexpr int TAPS = DIMS == 3 ? 27 : 9;
+    const int kk = cin * TAPS;
+    for (int i = threadIdx.x; i < cout * kk; i += blockDim.x) s_w[i] = wgt[i];
+    for (int i = threadIdx.x; i < cout; i += blockDim.x) s_w[cout * kk + i] = bias[i];
+    __syncthreads();
+    const long long pixels = (long long)n * D * H * W;
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < pixels; pix += (long long)gridDim.x * blockDim.x) {
+        long long t = pix;
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H); t /= H;
+        const int d = (int)(t % D);
+        const int b = (int)(t / D);
+        float in[4 * TAPS];
+        for (int c = 0; c < cin; ++c) {
+            int q = 0;
+            for (int dz = (DIMS == 3 ? -1 : 0); dz <= (DIMS == 3 ? 1 : 0); ++dz)
+                for (int dy = -1; dy <= 1; ++dy)
+                    for (int dx = -1; dx <= 1; ++dx, ++q) {
+                        const int zz = d + dz, yy = h + dy, xx = w + dx;
+                        const bool ok = zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
+                        in[c * TAPS + q] = ok ? __ldg(x + ((((long long)b * cin + c) * D + zz) * H + yy) * W + xx) : 0.f;
+                    }
+        }
+        __half* o = out + pix * cout_pad;
+        for (int co = 0; co < cout; co += 8) {
+            uint4 ov;
+            __half2* hv = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float a0 = s_w[cout * kk + co + 2 * e], a1 = s_w[cout * kk + co + 2 * e + 1];
+                for (int k = 0; k < kk; ++k) {
+                    a0 = fmaf(in[k], s_w[(co + 2 * e) * kk + k], a0);
+                    a1 = fmaf(in[k], s_w[(co + 2 * e + 1) * kk + k], a1);
+                }
+                hv[e] = __floats2half2_rn(fmaxf(a0, 0.f), fmaxf(a1, 0.f));
+            }
+            *reinterpret_cast<uint4*>(o + co) = ov;
+        }
+        for (int co = cout; co < cout_pad; co += 8) *reinterpret_cast<uint4*>(o + co) = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// ---- coordinate branch: one CTA per task; 3x3 conv, padding 1, on a (gh x gw) grid with gh, gw <= 3 ---------------
+__global__ void __launch_bounds__(256) coords_kernel(const float* __restrict__ coords, int gh, int gw,
+                                                     const float* w0, const float* b0, const float* w1, const float* b1,
+                                                     const float* w2, const float* b2, const float* w3, const float* b3,
+                                                     float* f0, float* f1, float* f2, float* f3) {
+    const int b = blockIdx.x, P = gh * gw;
+    const float* wts[4] = {w0, w1, w2, w3};
+    const float* bs[4] = {b0, b1, b2, b3};
+    float* outs[4] = {f0 + (size_t)b * P * 64, f1 + (size_t)b * P * 128, f2 + (size_t)b * P * 256, f3 + (size_t)b * P * 512};
+    const int cins[4] = {1, 64, 128, 256}, couts[4] = {64, 128, 256, 512};
+    const float* in = coords + (size_t)b * P;  // (1, gh, gw) -> [P][1]
+    for (int l = 0; l < 4; ++l) {
+        const int cin = cins[l], cout = couts[l];
+        for (int o = threadIdx.x; o < P * cout; o += blockDim.x) {
+            const int co = o % cout, pp = o / cout, y = pp / gw, x = pp % gw;
+            float acc = bs[l][co];
+            for (int ky = 0; ky < 3; ++ky) {
+                const int yy = y + ky - 1;
+                if (yy < 0 || yy >= gh) continue;
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int xx = x + kx - 1;
+                    if (xx < 0 || xx >= gw) continue;
+                    const float* ip = in + (size_t)(yy * gw + xx) * cin;
+                    const float* wp = wts[l] + ((size_t)co * cin) * 9 + ky * 3 + kx;
+                    for (int ci = 0; ci < cin; ++ci) acc = fmaf(ip[ci], __ldg(wp + (size_t)ci * 9), acc);
+                }
+            }
+            outs[l][(size_t)pp * cout + co] = fmaxf(acc, 0.f);
+        }
+        __syncthreads();  // global writes of this CTA visible to its own threads for the next layer
+        in = outs[l];
+    }
+}
+
+// ---- align_corners interpolation of the (gh x gw [x 1]) feature into a channel slice (PyTorch's fp32 formulas) -------
+// Output pixels are ordered (b, a0, a1, a2); a0 interpolates the gh axis, a1 the gw axis, a2 is constant
+// (2D: (H, W, 1); 3D: `coords.unsqueeze(-1)` makes the source (2, 3, 1), so the last output axis has a single source cell).
+__global__ void __launch_bounds__(256) coords_fill_kernel(const float* __restrict__ feat, int B, int gh, int gw, int C,
+                                                          int A0, int A1, int A2, __half* __restrict__ out,
+                                                          long long cstride, long long coffset) {
+    const int cv = C / 8;  // 8 channels (16 bytes) per thread
+    const long long total = (long long)B * A0 * A1 * A2 * cv;
+    const float rh = A0 > 1 ? (float)(gh - 1) / (float)(A0 - 1) : 0.f;  // area_pixel_compute_scale, align_corners=True
+    const float rw = A1 > 1 ? (float)(gw - 1) / (float)(A1 - 1) : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        const long long pix = i / cv;
+        long long t = pix / A2;
+        const int x = (int)(t % A1); t /= A1;
+        const int y = (int)(t % A0);
+        const int b = (int)(t / A0);
+        const float h1r = rh * y, w1r = rw * x;
+        const int h1 = (int)h1r, w1 = (int)w1r;
+        const int h1p = h1 < gh - 1 ? 1 : 0, w1p = w1 < gw - 1 ? 1 : 0;
+        const float h1l = h1r - h1, h0l = 1.f - h1l, w1l = w1r - w1, w0l = 1.f - w1l;
+        const float* f00 = feat + ((size_t)b * gh * gw + (size_t)h1 * gw + w1) * C + c8 * 8;
+        const float* f01 = f00 + (size_t)w1p * C;
+        const float* f10 = f00 + (size_t)h1p * gw * C;
+        const float* f11 = f10 + (size_t)w1p * C;
+        uint4 ov;
+        __half2* hv = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float r[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int c = e * 2 + q;
+                r[q] = h0l * (w0l * __ldg(f00 + c) + w1l * __ldg(f01 + c)) + h1l * (w0l * __ldg(f10 + c) + w1l * __ldg(f11 + c));
+            }
+            hv[e] = __floats2half2_rn(r[0], r[1]);
+        }
+        *reinterpret_cast<uint4*>(out + pix * cstride + coffset + c8 * 8) = ov;
+    }
+}
+
+// ---- 1x1 head: C -> 1, fp32 logits --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) head_kernel(const __half* __restrict__ in, long long pixels, int C, long long cstride,
+                                                   const float* __restrict__ wgt, float bias, float* __restrict__ logits) {
+    extern __shared__ float s_wh[];
+    for (int i = threadIdx.x; i < C; i += blockDim.x) s_wh[i] = wgt[i];
+    __syncthreads();
+    for (long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x; pix < pixels; pix += (long long)gridDim.x * blockDim.x) {
+        const uint4* ip = reinterpret_cast<const uint4*>(in + pix * cstride);
+        float acc = bias;
+        for (int c8 = 0; c8 < C / 8; ++c8) {
+            const uint4 v = __ldg(ip + c8);
+            const __half2* hv = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(hv[e]);
+                acc = fmaf(f.x, s_wh[c8 * 8 + 2 * e], acc);
+                acc = fmaf(f.y, s_wh[c8 * 8 + 2 * e + 1], acc);
+            }
+        }
+        logits[pix] = acc;
+    }
+}
+
+int grid_for(long long work, int block) {
+    long long g = (work + block - 1) / block;
+    return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+}  // namespace
+
+extern "C" int nrrt_stem_conv(int dims, const float* x, int n, int cin, int d, int h, int w, const float* weight,
+                              const float* bias, int cout, int cout_pad, void* out, void* stream) {
+    NRRT_REQUIRE(x && weight && bias && out, "null pointer");
+    NRRT_REQUIRE((dims == 2 || dims == 3) && cin >= 1 && cin <= 4 && cout % 8 == 0 && cout_pad % 8 == 0 && cout_pad >= cout, "bad stem shape");
+    if (dims == 2) d = 1;
+    const int taps = dims == 3 ? 27 : 9;
+    const size_t smem = ((size_t)cout * cin * taps + cout) * sizeof(float);
+    const long long pixels = (long long)n * d * h * w;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dims == 2) stem_kernel<2><<<grid_for(pixels, 256), 256, smem, st>>>(x, n, cin, d, h, w, weight, bias, cout, cout_pad, (__half*)out);
+    else stem_kernel<3><<<grid_for(pixels, 256), 256, smem, st>>>(x, n, cin, d, h, w, weight, bias, cout, cout_pad, (__half*)out);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_coords_branch(const float* coords, int B, int gh, int gw, const float* const* weights,
+                                  const float* const* biases, float* const* feats, void* stream) {
+    NRRT_REQUIRE(coords && weights && biases && feats, "null pointer");
+    NRRT_REQUIRE(B >= 0 && gh >= 1 && gh <= 3 && gw >= 1 && gw <= 3, "coords grid must be at most 3x3");
+    if (B == 0) return NRRT_OK;
+    coords_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coords, gh, gw, weights[0], biases[0], weights[1], biases[1],
+                                                                         weights[2], biases[2], weights[3], biases[3], feats[0],
+                                                                         feats[1], feats[2], feats[3]);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_coords_fill(const float* feat, int B, int gh, int gw, int C, int dims, int od, int oh, int ow, void* out,
+                                int64_t out_cstride, int64_t out_coffset, void* stream) {
+    NRRT_REQUIRE(feat && out && C % 8 == 0 && out_cstride % 8 == 0 && out_coffset % 8 == 0, "bad coords_fill arguments");
+    const int a0 = dims == 2 ? oh : od, a1 = dims == 2 ? ow : oh, a2 = dims == 2 ? 1 : ow;
+    const long long total = (long long)B * a0 * a1 * a2 * (C / 8);
+    if (total == 0) return NRRT_OK;
+    coords_fill_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(feat, B, gh, gw, C, a0, a1, a2, (__half*)out,
+                                                                                                out_cstride, out_coffset);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_head_1x1(const void* in, int64_t pixels, int C, int64_t in_cstride, const float* weight, float bias,
+                             float* logits, void* stream) {
+    NRRT_REQUIRE(in && weight && logits && C % 8 == 0 && in_cstride % 8 == 0, "bad head arguments");
+    if (pixels == 0) return NRRT_OK;
+    head_kernel<<<grid_for(pixels, 256), 256, C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>((const __half*)in, pixels, C,
+                                                                                                           in_cstride, weight, bias, logits);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}

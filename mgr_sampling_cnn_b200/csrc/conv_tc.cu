@@ -1,0 +1,477 @@
+// conv_tc.cu — implicit-GEMM convolution on the sm_100a tensor cores (tcgen05.mma, TMEM accumulators, TMA operands).
+//
+// Replaces the dense contraction of UNet_cooler.forward / ThreeD_UNet_cooler.forward (train.py:171-203,
+// ThreeD_train.py:169-204): every Conv2d/Conv3d 3x3(x3) stride 1/2, the 1x1(x1) stride-2 ResNet downsamples and the
+// ConvTranspose k=2 s=2 layers, with the eval-mode BatchNorm + bias folded into a per-channel scale/shift, the residual
+// add and the ReLU fused into the epilogue.
+//
+// GEMM view:  D[pixel, cout] = sum_{tap, cin} X[pixel + tap, cin] * W[cout, tap, cin]
+//   M = 128 output pixels per CTA tile: a (bd x bh x bw) box of the NDHWC activation tensor.  Each tap is ONE TMA tiled
+//       load of that box shifted by the tap offset (out-of-bounds rows are zero-filled by TMA = the conv padding), so
+//       no im2col buffer and no padded copies exist anywhere; stride-2 layers use the tensor map's element strides.
+//   N = BLOCK_N output channels (64/128/256) = one tcgen05.mma instruction wide.
+//   K = 64 input channels per pipeline stage (one 128-byte swizzle row), taps x Cin/64 stages per tile.
+// Warp roles (192 threads, persistent CTAs, static tile schedule): warp 0 TMA producer, warp 1 MMA issuer,
+// warps 2-5 epilogue (TMEM -> registers -> scale/shift/residual/ReLU -> fp16 NDHWC stores, 16-byte vectors).
+// Two accumulator stages in TMEM (2 x BLOCK_N columns) overlap the epilogue of tile i with the MMAs of tile i+1.
+// ConvTranspose(k=2,s=2) is the same GEMM with 4 (2D) / 8 (3D) weight groups stacked along N and a pixel-shuffle store.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+#include "nrrt_common.cuh"
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // fp16 elements = 128 bytes = one SWIZZLE_128B row
+constexpr int kThreads = 192;
+constexpr int kMaxTaps = 27;
+
+struct ConvParams {
+    int N, D, H, W;           // tile-space grid (conv: output grid; convT: input grid)
+    int bw, bh, bd, rows;     // tile box, rows = bw*bh*bd <= 128
+    int tiles_w, tiles_h, tiles_d, m_tiles;
+    int stride;               // input coordinate = tile coordinate * stride + tap offset
+    int stride_d;             // same for the depth axis (1 in 2D)
+    int ntaps, cin_chunks, n_tiles;
+    int8_t tap[kMaxTaps][4];  // (dx, dy, dz) including -pad
+    // epilogue
+    __half* out;
+    long long out_cstride, out_coffset;
+    int oD, oH, oW;           // output grid
+    int up, up_d;             // 1 = same grid; 2 = ConvTranspose pixel shuffle (up_d for the depth axis)
+    int cout;                 // channels per weight group (== total rows when up == 1)
+    const float* scale;
+    const float* shift;
+    const float* scale2;  // optional second affine + ReLU
+    const float* shift2;
+    const __half* res;
+    long long res_cstride, res_coffset;
+    int relu;
+    uint32_t a_bytes, b_bytes;
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+            "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"): start address >> 4,
+// LBO (unused for swizzled K-major) = 1, SBO = 1024 B between 8-row groups, version 1, layout type 2 = 128B swizzle.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout {
+    static constexpr uint32_t a_stage = kBlockM * 128;
+    static constexpr uint32_t b_stage = BLOCK_N * 128;
+    static constexpr uint32_t off_b = STAGES * a_stage;
+    static constexpr uint32_t off_bar = off_b + STAGES * b_stage;
+    static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4) * 8;
+    static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;         // scale/shift [2 acc stages][4][BLOCK_N] floats
+    static constexpr uint32_t total = off_ss + 2 * 4 * BLOCK_N * 4 + 1024;  // + slack for manual 1024-B alignment
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ ConvParams p) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = base + L::off_bar;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
+    float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int k_iters = p.ntaps * p.cin_chunks;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L::off_tmem),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_tile = tile % p.n_tiles;
+                int m = tile / p.n_tiles;
+                const int tw = m % p.tiles_w; m /= p.tiles_w;
+                const int th = m % p.tiles_h; m /= p.tiles_h;
+                const int td = m % p.tiles_d;
+                const int n = m / p.tiles_d;
+                const int w0 = tw * p.bw * p.stride, h0 = th * p.bh * p.stride, d0 = td * p.bd * p.stride_d;
+                for (int t = 0; t < p.ntaps; ++t) {
+                    const int cw = w0 + p.tap[t][0], ch = h0 + p.tap[t][1], cd = d0 + p.tap[t][2];
+                    for (int c = 0; c < p.cin_chunks; ++c) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        mbar_expect_tx(full_bar(stage), p.a_bytes + p.b_bytes);
+                        tma_load_5d(base + stage * L::a_stage, &map_a, full_bar(stage), c * kBlockK, cw, ch, cd, n);
+                        tma_load_2d(base + L::off_b + stage * L::b_stage, &map_b, full_bar(stage),
+                                    (t * p.cin_chunks + c) * kBlockK, n_tile * BLOCK_N);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_N);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(base + stage * L::a_stage);
+                    const uint64_t bdesc = make_smem_desc(base + L::off_b + stage * L::b_stage);
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / 16; ++kk)  // UMMA_K = 16: +32 bytes inside the swizzle row
+                        tc_mma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                    tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit(tfull_bar(acc));  // accumulator complete
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 =====
+        const int sub = warp & 3;
+        const int row = sub * 32 + lane;
+        const int et = threadIdx.x - 64;  // 0..127
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int n_tile = tile % p.n_tiles;
+            int m = tile / p.n_tiles;
+            const int tw = m % p.tiles_w; m /= p.tiles_w;
+            const int th = m % p.tiles_h; m /= p.tiles_h;
+            const int td = m % p.tiles_d;
+            const int n = m / p.tiles_d;
+            // per-tile scale/shift staging (double-buffered by accumulator stage)
+            float* sc = ss + acc * 4 * BLOCK_N;
+            float* sh = sc + BLOCK_N;
+            float* sc2 = sh + BLOCK_N;
+            float* sh2 = sc2 + BLOCK_N;
+            for (int i = et; i < BLOCK_N; i += 128) {
+                sc[i] = __ldg(p.scale + n_tile * BLOCK_N + i);
+                sh[i] = __ldg(p.shift + n_tile * BLOCK_N + i);
+                if (p.scale2) {
+                    sc2[i] = __ldg(p.scale2 + n_tile * BLOCK_N + i);
+                    sh2[i] = __ldg(p.shift2 + n_tile * BLOCK_N + i);
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+
+            const int wl = row % p.bw, hl = (row / p.bw) % p.bh, dl = row / (p.bw * p.bh);
+            const int w = tw * p.bw + wl, h = th * p.bh + hl, d = td * p.bd + dl;
+            const bool valid = row < p.rows && w < p.W && h < p.H && d < p.D;
+
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tc_ld32(taddr + (uint32_t)(c * 32), v);
+                if (valid) {
+                    const int col = n_tile * BLOCK_N + c * 32;  // first GEMM column of this chunk
+                    const int g = col / p.cout, co = col - g * p.cout;
+                    int od = d, oh = h, ow = w;
+                    if (p.up == 2) {
+                        if (p.up_d == 2) { od = 2 * d + (g >> 2); oh = 2 * h + ((g >> 1) & 1); ow = 2 * w + (g & 1); }
+                        else { oh = 2 * h + (g >> 1); ow = 2 * w + (g & 1); }
+                    }
+                    const long long pix = (((long long)n * p.oD + od) * p.oH + oh) * p.oW + ow;
+                    float f[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), sc[c * 32 + i], sh[c * 32 + i]);
+                    if (p.res) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coffset + co);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint4 rv = __ldg(rp + q);
+                            const __half2* hv = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 t2 = __half22float2(hv[e]);
+                                f[q * 8 + e * 2] += t2.x;
+                                f[q * 8 + e * 2 + 1] += t2.y;
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+                    }
+                    if (p.scale2) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(f[i], sc2[c * 32 + i], sh2[c * 32 + i]), 0.0f);
+                    }
+                    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_coffset + co);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint4 ov;
+                        __half2* hv = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a = fminf(fmaxf(f[q * 8 + e * 2], -65504.f), 65504.f);
+                            const float b = fminf(fmaxf(f[q * 8 + e * 2 + 1], -65504.f), 65504.f);
+                            hv[e] = __floats2half2_rn(a, b);
+                        }
+                        op[q] = ov;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
+    using L = SmemLayout<BLOCK_N, STAGES>;
+    auto kern = conv_gemm_kernel<BLOCK_N, STAGES>;
+    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    const int total = p.m_tiles * p.n_tiles;
+    const int grid = total < sms ? total : sms;
+    kern<<<grid, kThreads, L::total, st>>>(ma, mb, p);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+void pick_box(int W, int H, int D, int& bw, int& bh, int& bd) {
+    // Largest box of <= 128 pixels that tiles the grid with the least waste (dims need not be powers of two).
+    double best = -1;
+    bw = bh = bd = 1;
+    for (int d = 1; d <= std::min(D, 128); ++d)
+        for (int h = 1; h <= std::min(H, 128 / d); ++h) {
+            const int w = std::min(W, 128 / (d * h));
+            if (w < 1) continue;
+            const double tiles = (double)((W + w - 1) / w) * ((H + h - 1) / h) * ((D + d - 1) / d);
+            const double eff = (double)W * H * D / (tiles * 128.0);
+            // among equally full tilings prefer the smallest halo (taps of neighbouring rows re-read the same pixels)
+            const double halo = (double)(w + 2) * (h + 2) * (D > 1 ? d + 2 : 1) / ((double)w * h * d);
+            const double score = eff - 1e-3 * halo;
+            if (score > best) { best = score; bw = w; bh = h; bd = d; }
+        }
+}
+
+}  // namespace
+
+extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
+    NRRT_REQUIRE(l && l->in && l->weight && l->scale && l->shift && l->out, "null pointer in conv layer");
+    NRRT_REQUIRE(l->dims == 2 || l->dims == 3, "dims must be 2 or 3");
+    NRRT_REQUIRE(l->kind >= 0 && l->kind <= 4, "unknown conv kind %d", l->kind);
+    NRRT_REQUIRE(l->cin > 0 && l->cin % 64 == 0, "Cin must be a multiple of 64 (got %d)", l->cin);
+    NRRT_REQUIRE(l->cout > 0 && l->cout % 32 == 0, "Cout must be a multiple of 32 (got %d)", l->cout);
+    NRRT_REQUIRE(l->in_cstride % 8 == 0 && l->out_cstride % 8 == 0 && l->out_coffset % 8 == 0, "channel strides/offsets must be multiples of 8");
+    NRRT_REQUIRE(((uintptr_t)l->in & 15) == 0 && ((uintptr_t)l->weight & 15) == 0 && ((uintptr_t)l->out & 15) == 0, "pointers must be 16-byte aligned");
+    if (l->res) NRRT_REQUIRE(l->res_cstride % 8 == 0 && l->res_coffset % 8 == 0 && ((uintptr_t)l->res & 15) == 0, "bad residual layout");
+    EncodeTiledFn encode = get_encode_fn();
+    if (!encode) return nrrt_fail(NRRT_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const bool three_d = l->dims == 3;
+    const int N = l->n, iD = three_d ? l->in_d : 1, iH = l->in_h, iW = l->in_w;
+    NRRT_REQUIRE(N >= 1 && iD >= 1 && iH >= 1 && iW >= 1, "bad input dims");
+
+    ConvParams p = {};
+    int stride = 1, ksz = 3, pad = 1, up = 1;
+    switch (l->kind) {
+        case NRRT_CONV_K3S1: break;
+        case NRRT_CONV_K3S2: stride = 2; break;
+        case NRRT_CONV_K1S2: stride = 2; ksz = 1; pad = 0; break;
+        case NRRT_CONV_K1S1: ksz = 1; pad = 0; break;
+        case NRRT_CONVT_K2S2: ksz = 1; pad = 0; up = 2; break;
+    }
+    auto out_dim = [&](int i) { return (i + 2 * pad - ksz) / stride + 1; };
+    p.N = N;
+    p.W = out_dim(iW); p.H = out_dim(iH); p.D = three_d ? out_dim(iD) : 1;
+    p.stride = stride; p.stride_d = three_d ? stride : 1;
+    pick_box(p.W, p.H, p.D, p.bw, p.bh, p.bd);
+    p.rows = p.bw * p.bh * p.bd;
+    p.tiles_w = (p.W + p.bw - 1) / p.bw; p.tiles_h = (p.H + p.bh - 1) / p.bh; p.tiles_d = (p.D + p.bd - 1) / p.bd;
+    const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_d * N;
+    NRRT_REQUIRE(m_tiles < (1ll << 30), "too many tiles");
+    p.m_tiles = (int)m_tiles;
+    p.ntaps = 0;
+    for (int dz = 0; dz < (three_d ? ksz : 1); ++dz)
+        for (int dy = 0; dy < ksz; ++dy)
+            for (int dx = 0; dx < ksz; ++dx) {
+                p.tap[p.ntaps][0] = (int8_t)(dx - pad); p.tap[p.ntaps][1] = (int8_t)(dy - pad);
+                p.tap[p.ntaps][2] = (int8_t)(three_d ? dz - pad : 0); p.tap[p.ntaps][3] = 0;
+                ++p.ntaps;
+            }
+    p.cin_chunks = l->cin / 64;
+    const int groups = up == 2 ? (three_d ? 8 : 4) : 1;
+    const int rows_total = groups * l->cout;
+    const int block_n = rows_total % 256 == 0 ? 256 : (rows_total % 128 == 0 ? 128 : 64);
+    NRRT_REQUIRE(rows_total % block_n == 0, "Cout (x groups) = %d must be a multiple of 64", rows_total);
+    p.n_tiles = rows_total / block_n;
+    p.out = (__half*)l->out; p.out_cstride = l->out_cstride; p.out_coffset = l->out_coffset;
+    p.up = up; p.up_d = (up == 2 && three_d) ? 2 : 1;
+    p.oW = p.W * up; p.oH = p.H * up; p.oD = p.D * p.up_d;
+    p.cout = l->cout;
+    p.scale = l->scale; p.shift = l->shift;
+    p.scale2 = l->post_scale; p.shift2 = l->post_shift;
+    NRRT_REQUIRE((l->post_scale == nullptr) == (l->post_shift == nullptr), "post_scale and post_shift go together");
+    p.res = (const __half*)l->res; p.res_cstride = l->res_cstride; p.res_coffset = l->res_coffset;
+    p.relu = l->relu;
+    p.a_bytes = (uint32_t)p.rows * 128u;
+    p.b_bytes = (uint32_t)block_n * 128u;
+
+    // activation map: dims (C, W, H, D, N) over the caller's NDHWC buffer (channel slice of in_cstride-wide rows)
+    CUtensorMap ma, mb;
+    {
+        const cuuint64_t gdim[5] = {(cuuint64_t)l->cin, (cuuint64_t)iW, (cuuint64_t)iH, (cuuint64_t)iD, (cuuint64_t)N};
+        const cuuint64_t cs = (cuuint64_t)l->in_cstride * 2;
+        const cuuint64_t gstr[4] = {cs, cs * iW, cs * iW * iH, cs * iW * iH * iD};
+        const cuuint32_t box[5] = {64, (cuuint32_t)(p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)(p.bd * p.stride_d), 1};
+        const cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)p.stride_d, 1};
+        const CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(l->in), gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d (box %d,%d,%d stride %d)", (int)r, p.bw, p.bh, p.bd, stride);
+    }
+    {
+        const cuuint64_t ktot = (cuuint64_t)p.ntaps * l->cin;
+        const cuuint64_t gdim[2] = {ktot, (cuuint64_t)rows_total};
+        const cuuint64_t gstr[1] = {ktot * 2};
+        const cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = encode(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(l->weight), gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    }
+    int dev = 0, sms = 0;
+    NRRT_CUDA_TRY(cudaGetDevice(&dev));
+    NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (block_n == 256) return launch_conv<256, 4>(ma, mb, p, sms, st);
+    if (block_n == 128) return launch_conv<128, 6>(ma, mb, p, sms, st);
+    return launch_conv<64, 8>(ma, mb, p, sms, st);
+}

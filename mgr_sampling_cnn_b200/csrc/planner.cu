@@ -435,13 +435,13 @@ extern "C" int nrrt_plan_batch(const NrrtPlanParams* p, const uint32_t* occ_bits
     NRRT_REQUIRE(B >= 0, "negative batch");
     NRRT_REQUIRE(p->max_iterations >= 1 && p->max_iterations <= 32000, "max_iterations out of range: %d", p->max_iterations);
     NRRT_REQUIRE(p->node_stride >= p->max_iterations + 2, "node_stride %d < max_iterations + 2", p->node_stride);
+    if (B == 0) return NRRT_OK;
     NRRT_REQUIRE(occ_bits && task_to_map && radius && samples && starts && goals && queue_counter, "null input pointer");
     NRRT_REQUIRE(out->cost && out->parent && out->n_nodes && out->iterations && out->status && out->goal_node &&
                      out->best_node && out->best_dist, "null required output pointer");
     for (int k = 0; k < p->dim; ++k) NRRT_REQUIRE(p->shape[k] >= 1 && p->shape[k] <= 32767, "bad shape[%d]=%d", k, p->shape[k]);
     const int64_t cells = (int64_t)p->shape[0] * p->shape[1] * (p->dim == 3 ? p->shape[2] : 1);
     NRRT_REQUIRE(cells < (int64_t)1 << 31, "map too large");
-    if (B == 0) return NRRT_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
     PlanArgs a;

@@ -392,10 +392,11 @@ extern "C" int nrrt_cdf_build(const float* logits, int mode, int B, int64_t cell
 extern "C" int nrrt_draw_samples(const NrrtPlanParams* p, const uint32_t* occ_bits, const int32_t* task_to_map,
                                  const float* cdf, const int32_t* task_ids, int B, int16_t* samples, int8_t* neural_flag,
                                  int64_t* n_draws, int32_t* draw_status, void* stream) {
-    NRRT_REQUIRE(p && occ_bits && task_to_map && task_ids && samples && draw_status, "null pointer");
+    NRRT_REQUIRE(p, "null params");
     NRRT_REQUIRE(p->dim == 2 || p->dim == 3, "dim must be 2 or 3, got %d", p->dim);
     NRRT_REQUIRE(B >= 0 && p->max_iterations >= 1 && p->max_reject >= 1, "bad sizes");
     if (B == 0) return NRRT_OK;
+    NRRT_REQUIRE(occ_bits && task_to_map && task_ids && samples && draw_status, "null pointer");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     DrawArgs a;
     a.p = *p; a.occ_bits = occ_bits; a.task_to_map = task_to_map; a.cdf = cdf; a.task_ids = task_ids; a.B = B;

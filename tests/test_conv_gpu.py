@@ -1,0 +1,167 @@
+"""GPU: the tcgen05 implicit-GEMM convolution layer (nrrt_conv_layer) against torch fp32 convolutions on the same
+fp16-rounded operands, then the whole UNet forward against the fp32 oracle (tolerance <= 1e-2 abs, BASELINE north star)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from mgr_sampling_cnn_b200 import _lib, cnn
+from oracle import cnn_oracle
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _cl(x):  # NC(D)HW fp32 -> channels-last fp16 [B, D, H, W, C] (D = 1 in 2D)
+    if x.dim() == 4:
+        return x.permute(0, 2, 3, 1).unsqueeze(1).contiguous().half()
+    return x.permute(0, 2, 3, 4, 1).contiguous().half()
+
+
+def _from_cl(t, dims):  # [B, D, H, W, C] fp16 -> NC(D)HW fp32
+    t = t.float()
+    return t[:, 0].permute(0, 3, 1, 2) if dims == 2 else t.permute(0, 4, 1, 2, 3)
+
+
+def _run_layer(dims, kind, x, w, scale, shift, relu, dev, res=None, out_ctot=None, out_off=0, in_ctot=None, in_off=0,
+               post=None):
+    cin = x.shape[1]
+    if kind == cnn.CONVT:
+        cout = w.shape[1]
+        wp = cnn._pack_convT_weight(w, dev)
+        groups = 2 ** dims
+        scale, shift = scale.repeat(groups), shift.repeat(groups)
+        up = 2
+    else:
+        cout = w.shape[0]
+        wp = cnn._pack_conv_weight(w, cin, dev)
+        up = 1
+    layer = cnn._Layer(dims, kind, cin, cout, wp, scale.float().contiguous(), shift.float().contiguous(), relu, post)
+    xin = _cl(x)
+    if in_ctot:
+        big = torch.randn(xin.shape[:-1] + (in_ctot,), device=dev).half()
+        big[..., in_off:in_off + cin] = xin
+        xin = big
+    grid = tuple(xin.shape[1:4])
+    stride = 2 if kind in (cnn.K3S2, cnn.K1S2) else 1
+    og = tuple((g if (dims == 3 or i > 0) else 1) for i, g in enumerate(grid))
+    og = tuple(((g - 1) // stride + 1) * up if (dims == 3 or i > 0) else 1 for i, g in enumerate(og))
+    out = torch.full((x.shape[0],) + og + (out_ctot or cout,), 7.0, dtype=torch.float16, device=dev)
+    resb = _cl(res) if res is not None else None
+    layer.run(_lib.load(), None, xin, in_off, grid, out, out_off, resb, 0)
+    torch.cuda.synchronize()
+    return out
+
+
+def _ref(dims, kind, x, w, scale, shift, relu, res=None, post=None):
+    xh, wh = x.half().float(), w.half().float()
+    conv = F.conv2d if dims == 2 else F.conv3d
+    if kind == cnn.CONVT:
+        y = (F.conv_transpose2d if dims == 2 else F.conv_transpose3d)(xh, wh, stride=2)
+    elif kind == cnn.K3S1:
+        y = conv(xh, wh, padding=1)
+    elif kind == cnn.K3S2:
+        y = conv(xh, wh, stride=2, padding=1)
+    elif kind == cnn.K1S2:
+        y = conv(xh, wh, stride=2)
+    else:
+        y = conv(xh, wh)
+    shp = (1, -1) + (1,) * dims
+    y = y * scale.view(shp) + shift.view(shp)
+    if res is not None:
+        y = y + res.half().float()
+    if relu:
+        y = F.relu(y)
+    if post is not None:
+        y = F.relu(y * post[0].view(shp) + post[1].view(shp))
+    return y
+
+
+def _check(out, ref, dims, cout, off=0):
+    got = _from_cl(out[..., off:off + cout], dims)
+    err = (got - ref).abs().max().item()
+    tol = 2e-3 * max(ref.abs().max().item(), 1.0) + 1e-3
+    assert err <= tol, f"max abs err {err} > {tol}"
+
+
+CASES = [
+    # dims, kind, B, cin, cout, spatial
+    (2, cnn.K1S1, 2, 64, 64, (16, 16)),      # plain GEMM, one K stage
+    (2, cnn.K1S1, 1, 256, 128, (24, 40)),    # 4 K stages, N = 128, ragged tiles
+    (2, cnn.K3S1, 2, 64, 64, (16, 16)),
+    (2, cnn.K3S1, 1, 128, 256, (40, 24)),
+    (2, cnn.K3S1, 1, 192, 512, (16, 32)),    # two N tiles of 256
+    (2, cnn.K3S2, 2, 64, 128, (32, 32)),
+    (2, cnn.K1S2, 2, 64, 128, (32, 32)),
+    (2, cnn.CONVT, 2, 128, 64, (16, 16)),    # 4 groups x 64 = one N tile of 256
+    (2, cnn.CONVT, 1, 256, 128, (8, 24)),    # 4 groups x 128 = two N tiles
+    (3, cnn.K1S1, 1, 64, 64, (8, 8, 8)),
+    (3, cnn.K3S1, 1, 64, 64, (8, 8, 16)),
+    (3, cnn.K3S1, 2, 128, 128, (10, 10, 10)),  # 5x5x5 boxes (125 rows)
+    (3, cnn.K3S2, 1, 64, 128, (16, 16, 16)),
+    (3, cnn.K1S2, 1, 64, 128, (16, 16, 16)),
+    (3, cnn.CONVT, 1, 128, 64, (4, 8, 8)),     # 8 groups x 64 = two N tiles of 256
+]
+
+
+@pytest.mark.parametrize("dims,kind,B,cin,cout,sp", CASES)
+def test_conv_layer_matches_torch(dims, kind, B, cin, cout, sp, cuda_device):
+    g = torch.Generator(device="cpu").manual_seed(cin * 7 + cout + kind)
+    dev = cuda_device
+    x = torch.randn((B, cin) + sp, generator=g).to(dev)
+    k = 1 if kind in (cnn.K1S1, cnn.K1S2) else (2 if kind == cnn.CONVT else 3)
+    wshape = ((cin, cout) if kind == cnn.CONVT else (cout, cin)) + (k,) * dims
+    w = (torch.randn(wshape, generator=g) / np.sqrt(cin * k ** dims)).to(dev)
+    scale = (torch.rand(cout, generator=g) + 0.5).to(dev)
+    shift = torch.randn(cout, generator=g).to(dev)
+    out = _run_layer(dims, kind, x, w, scale, shift, True, dev)
+    _check(out, _ref(dims, kind, x, w, scale, shift, True), dims, cout)
+
+
+def test_conv_layer_residual_slices_and_post_affine(cuda_device):
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(1)
+    x = torch.randn((2, 64, 16, 16), generator=g).to(dev)
+    w = (torch.randn((128, 64, 3, 3), generator=g) / 24).to(dev)
+    scale, shift = (torch.rand(128, generator=g) + 0.5).to(dev), torch.randn(128, generator=g).to(dev)
+    res = torch.randn((2, 128, 16, 16), generator=g).to(dev)
+    post = ((torch.rand(128, generator=g) + 0.5).to(dev), torch.randn(128, generator=g).to(dev))
+    # input read from channels [64,128) of a 192-wide buffer; output written to channels [32,160) of a 192-wide buffer
+    out = _run_layer(2, cnn.K3S1, x, w, scale, shift, True, dev, res=res, out_ctot=192, out_off=32, in_ctot=192, in_off=64,
+                     post=post)
+    _check(out, _ref(2, cnn.K3S1, x, w, scale, shift, True, res, post), 2, 128, off=32)
+    assert (out[..., :32] == 7.0).all() and (out[..., 160:] == 7.0).all()  # neighbours of the slice untouched
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+@pytest.mark.parametrize("bn", [False, True])
+def test_unet_forward_matches_reference_golden(three_d, bn, cuda_device):
+    """The golden logits were produced by the UNMODIFIED reference model on CPU fp32 (oracle/gen_golden.py)."""
+    from mgr_sampling_cnn_b200 import ThreeD_train, train
+    g = H.load(("cnn3d_seed0" if three_d else "cnn2d_seed0") + ("_bn" if bn else ""))
+    torch.manual_seed(0)
+    model = (ThreeD_train.ThreeD_UNet_cooler() if three_d else train.UNet_cooler()).eval()
+    if bn:
+        cnn_oracle.randomize_bn(model, 0)
+    model = model.to(cuda_device)
+    y = model(torch.from_numpy(g["x"]).to(cuda_device), torch.from_numpy(g["coords"]).to(cuda_device))
+    torch.cuda.synchronize()
+    assert y.shape == g["logits"].shape and y.dtype == torch.float32
+    err = np.abs(y.cpu().numpy() - g["logits"]).max()
+    assert err <= 1e-2, f"max abs err {err}"
+
+
+def test_unet_forward_full_size_2d_vs_fp32_oracle(cuda_device):
+    """512x512 maps from the repo's generator, pixel coordinates as the reference feeds them (un-normalised)."""
+    from mgr_sampling_cnn_b200 import train, workload
+    wl = workload.make_2d(3)
+    torch.manual_seed(0)
+    model = train.UNet_cooler().eval().to(cuda_device)
+    x = torch.from_numpy((wl.occ_maps[wl.task_to_map] != 0).astype(np.float32))[:, None].repeat(1, 3, 1, 1).to(cuda_device)
+    coords = torch.from_numpy(wl.coords).to(cuda_device)
+    y = model(x, coords)
+    with torch.no_grad():
+        ref = cnn_oracle.forward({k: v.float() for k, v in model.state_dict().items()}, x, coords, 2)
+    torch.cuda.synchronize()
+    err = (y - ref).abs().max().item()
+    assert err <= 1e-2, f"max abs err {err} (ref range {ref.min().item():.3f}..{ref.max().item():.3f})"
