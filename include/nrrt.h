@@ -160,6 +160,12 @@ int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);
 int nrrt_stem_conv(int dims, const float* x, int n, int cin, int d, int h, int w, const float* weight, const float* bias,
                    int cout, int cout_pad, void* out, void* stream);
 
+/* Same layer fed straight from the resident uint8 occupancy maps: sample b reads map task_to_map[b] and every input
+ * channel is the dataset's {0,1} normalisation of it, x = (occ != 0) (train.py:41-44, ThreeD_train.py:46-50), so the
+ * (B,3,H,W) fp32 tensor the reference materialises per task never exists. */
+int nrrt_stem_conv_maps(int dims, const uint8_t* occ_maps, const int32_t* task_to_map, int n, int cin, int d, int h, int w,
+                        const float* weight, const float* bias, int cout, int cout_pad, void* out, void* stream);
+
 /* Coordinate branch (train.py:179-190): the four conv_coords_* layers (3x3 Conv2d + ReLU) on the (B,1,2,2) / (B,1,2,3)
  * coords tensor in fp32.  weights/biases: 4 pointers, PyTorch layout [cout][cin][3][3].  feats: 4 output pointers,
  * fp32 [B][gh*gw][C] with C = 64, 128, 256, 512. */

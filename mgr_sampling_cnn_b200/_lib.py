@@ -48,6 +48,8 @@ _SIGNATURES = {
     "nrrt_conv_layer": (C.c_int, [C.POINTER(NrrtConvLayer), C.c_void_p]),
     "nrrt_stem_conv": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nrrt_stem_conv_maps": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nrrt_coords_branch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrrt_coords_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
@@ -56,6 +58,12 @@ _SIGNATURES = {
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 _lib = None
+launches = 0  # kernels of libnrrt.so launched through the Python wrappers (bench.py reports it as gpu_launches)
+
+
+def count_launch(n: int = 1):
+    global launches
+    launches += n
 
 
 def load():

@@ -20,6 +20,43 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _prod(v):
+    out = 1
+    for a in v:
+        out *= int(a)
+    return out
+
+
+class ConvProfiler(object):
+    """CUDA-event timing of individual nrrt_conv_layer launches (bench.py's roofline leg).  Events are recorded on the
+    launching stream around a sampled subset of launches; totals are read after a synchronize."""
+
+    def __init__(self):
+        self.active = False
+        self.records = []  # (flops, start_event, end_event)
+
+    class _Ctx(object):
+        def __init__(self, prof, flops):
+            self.prof, self.flops = prof, flops
+
+        def __enter__(self):
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+        def __exit__(self, *exc):
+            self.b.record()
+            self.prof.records.append((self.flops, self.a, self.b))
+
+    def launch(self, flops):
+        return ConvProfiler._Ctx(self, flops)
+
+    def totals(self):
+        """(launches, total flops, total milliseconds) of everything recorded so far; call after a synchronize."""
+        ms = sum(a.elapsed_time(b) for _, a, b in self.records)
+        return len(self.records), sum(f for f, _, _ in self.records), ms
+
+
 def _fold_bn(bn, conv_bias, cout, device):
     """eval-mode BatchNorm (+ optional conv bias) -> per-channel (scale, shift) in fp32."""
     if bn is None:
@@ -58,13 +95,33 @@ def _pack_convT_weight(w, device):
 class _Layer(object):
     """One nrrt_conv_layer call with its packed parameters (kept alive here)."""
 
-    def __init__(self, dims, kind, cin, cout, weight, scale, shift, relu, post=None):
+    def __init__(self, dims, kind, cin, cout, weight, scale, shift, relu, post=None, cin_real=None):
         self.dims, self.kind, self.cin, self.cout = dims, kind, cin, cout
         self.weight, self.scale, self.shift, self.relu = weight, scale, shift, relu
         self.post = post
+        self.cin_real = cin_real or cin
+        self.profiler = None
+
+    def flops(self, batch, grid):
+        """Algorithmic FLOPs (2 x MACs with the true Cin) of this layer on input grid (D, H, W)."""
+        sp = [g for i, g in enumerate(grid) if self.dims == 3 or i > 0]
+        if self.kind == CONVT:
+            return 2.0 * batch * _prod(sp) * (2 ** self.dims) * self.cout * self.cin_real
+        stride = 2 if self.kind in (K3S2, K1S2) else 1
+        taps = (3 ** self.dims) if self.kind in (K3S1, K3S2) else 1
+        return 2.0 * batch * _prod([(g - 1) // stride + 1 for g in sp]) * self.cout * taps * self.cin_real
 
     def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0):
         """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W)."""
+        prof = self.profiler
+        if prof is not None and prof.active:
+            with prof.launch(self.flops(x.shape[0], grid)):
+                self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff)
+        else:
+            self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff)
+
+    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff):
+        _lib.count_launch()
         L = _lib.NrrtConvLayer()
         L.dims, L.kind = self.dims, self.kind
         L.n, L.in_d, L.in_h, L.in_w = x.shape[0], grid[0], grid[1], grid[2]
@@ -94,7 +151,8 @@ class UNetPlan(object):
         def conv(m, kind, bn=None, relu=True, cin_pad=None, post=None):
             cin_pad = cin_pad or m.in_channels
             scale, shift = _fold_bn(bn, m.bias, m.out_channels, dev)
-            return _Layer(d, kind, cin_pad, m.out_channels, _pack_conv_weight(m.weight, cin_pad, dev), scale, shift, relu, post)
+            return _Layer(d, kind, cin_pad, m.out_channels, _pack_conv_weight(m.weight, cin_pad, dev), scale, shift, relu, post,
+                          cin_real=m.in_channels)
 
         def convT(m):
             groups = 2 ** d
@@ -152,6 +210,7 @@ class UNetPlan(object):
         self.head_w = model.final_conv.weight.detach().float().to(dev).reshape(-1).contiguous()
         self.head_b = float(model.final_conv.bias.detach().float().item())
         self._bufs = {}
+        self.profiler = None
 
     # activation buffers for a micro-batch of B samples on grid (D, H, W)
     def _buffers(self, B, grid):
@@ -183,28 +242,70 @@ class UNetPlan(object):
         b = self._buffers(B, grid)
         return sum(t.numel() * t.element_size() for t in b.values() if isinstance(t, torch.Tensor))
 
-    def forward(self, x, coords):
+    def layers(self):
+        out = [self.stem2, self.up6, self.up7, self.up8] + list(self.c6) + list(self.c7) + list(self.c8)
+        for stg in self.enc:
+            for c1, c2, ds in stg:
+                out += [c1, c2] + ([ds] if ds is not None else [])
+        return out
+
+    def set_profiler(self, prof):
+        self.profiler = prof
+        for l in self.layers():
+            l.profiler = prof
+
+    def flops_per_sample(self, grid):
+        """Algorithmic FLOPs of the tensor-core layers for one sample on input grid (D, H, W) (excludes the 3-/1-channel
+        stem conv, the coordinate branch and the 1x1 head, which run on CUDA cores)."""
+        g = [tuple(max(v // (2 ** lv), 1) if (self.dims == 3 or i > 0) else 1 for i, v in enumerate(grid)) for lv in range(4)]
+        tot = self.stem2.flops(1, g[0])
+        gin = [g[0], g[0], g[1], g[2]]
+        for s_i, stg in enumerate(self.enc):
+            gout = g[s_i]
+            (c1, c2, ds), (c3, c4, _) = stg
+            tot += c1.flops(1, gin[s_i]) + c2.flops(1, gout) + c3.flops(1, gout) + c4.flops(1, gout)
+            if ds is not None:
+                tot += ds.flops(1, gin[s_i])
+        tot += self.up6.flops(1, g[3]) + self.c6[0].flops(1, g[2]) + self.c6[1].flops(1, g[2])
+        tot += self.up7.flops(1, g[2]) + self.c7[0].flops(1, g[1]) + self.c7[1].flops(1, g[1])
+        tot += self.up8.flops(1, g[1]) + self.c8[0].flops(1, g[0]) + self.c8[1].flops(1, g[0])
+        return tot
+
+    def forward(self, x, coords, logits_out=None):
         """x: fp32 (B,3,H,W) / (B,D,H,W) on self.device; coords: fp32 (B,1,2,2) / (B,1,2,3).  Returns fp32 logits
         (B,1,H,W) / (B,1,D,H,W)."""
-        lib, dims = self.lib, self.dims
-        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         x = x.contiguous().float()
-        coords = coords.contiguous().float()
-        B = x.shape[0]
-        if dims == 2:
+        if self.dims == 2:
             grid = (1, x.shape[2], x.shape[3])
             if x.shape[1] != 3:
                 raise ValueError("UNet_cooler expects (B, 3, H, W)")
         else:
             grid = (x.shape[1], x.shape[2], x.shape[3])
+        return self._forward(x.shape[0], grid, coords, logits_out, x=x)
+
+    def forward_maps(self, occ_maps, task_to_map, coords, logits_out=None):
+        """Same forward fed from resident uint8 occupancy maps [n_maps, (D,) H, W] + task_to_map [B] (int32): the
+        network input of sample b is the {0,1}-normalised map task_to_map[b] replicated over the input channels."""
+        grid = (1,) + tuple(occ_maps.shape[1:]) if self.dims == 2 else tuple(occ_maps.shape[1:])
+        return self._forward(task_to_map.shape[0], grid, coords, logits_out, occ=occ_maps, t2m=task_to_map)
+
+    def _forward(self, B, grid, coords, logits_out, x=None, occ=None, t2m=None):
+        lib, dims = self.lib, self.dims
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        coords = coords.contiguous().float()
         if any(g % 8 for g in grid[(0 if dims == 3 else 1):]):
             raise ValueError("spatial sizes must be multiples of 8 (three stride-2 stages)")
         bf = self._buffers(B, grid)
         g = [tuple(max(v // (2 ** lv), 1) if (dims == 3 or i > 0) else 1 for i, v in enumerate(grid)) for lv in range(4)]
 
         # stem
-        check(lib.nrrt_stem_conv(dims, _ptr(x), B, self.stem_cin, grid[0], grid[1], grid[2], _ptr(self.stem_w),
-                                 _ptr(self.stem_b), self.stem_cout, 64, _ptr(bf["t0"]), st))
+        _lib.count_launch()
+        if x is not None:
+            check(lib.nrrt_stem_conv(dims, _ptr(x), B, self.stem_cin, grid[0], grid[1], grid[2], _ptr(self.stem_w),
+                                     _ptr(self.stem_b), self.stem_cout, 64, _ptr(bf["t0"]), st))
+        else:
+            check(lib.nrrt_stem_conv_maps(dims, _ptr(occ), _ptr(t2m), B, self.stem_cin, grid[0], grid[1], grid[2],
+                                          _ptr(self.stem_w), _ptr(self.stem_b), self.stem_cout, 64, _ptr(bf["t0"]), st))
         self.stem2.run(lib, st, bf["t0"], 0, g[0], bf["x1"], 0)
 
         # encoder; the last conv of every stage writes into its concat buffer slice
@@ -227,6 +328,7 @@ class UNetPlan(object):
 
         # coordinate branch + align_corners interpolation into the concat slices (train.py:179-190)
         gh, gw = coords.shape[2], coords.shape[3]
+        _lib.count_launch(5)
         check(lib.nrrt_coords_branch(_ptr(coords), B, gh, gw, self.cw_ptrs, self.cb_ptrs, bf["feat_ptrs"], st))
         for feat, ch, name, off, lv in ((0, 64, "cat8", 128, 0), (1, 128, "cat7", 256, 1), (2, 256, "cat6", 768, 2),
                                         (3, 512, "x5", 512, 3)):
@@ -246,7 +348,10 @@ class UNetPlan(object):
         self.c8[1].run(lib, st, bf["j"], 0, g[0], bf["k"], 0)
 
         pixels = B * grid[0] * grid[1] * grid[2]
-        logits = torch.empty((B, 1) + (tuple(grid) if dims == 3 else tuple(grid[1:])), dtype=torch.float32, device=self.device)
+        logits = logits_out
+        if logits is None:
+            logits = torch.empty((B, 1) + (tuple(grid) if dims == 3 else tuple(grid[1:])), dtype=torch.float32, device=self.device)
+        _lib.count_launch()
         check(lib.nrrt_head_1x1(_ptr(bf["k"]), pixels, 64, 64, _ptr(self.head_w), self.head_b, _ptr(logits), st))
         return logits
 

@@ -9,7 +9,8 @@ namespace {
 
 // ---- stem: direct 3x3(x3) convolution, Cin <= 4, fp32 NCHW in -> fp16 channels-last out, bias + ReLU --------------
 template <int DIMS>
-__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, int n, int cin, int D, int H, int W,
+__global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, const uint8_t* __restrict__ occ,
+                                                   const int32_t* __restrict__ t2m, int n, int cin, int D, int H, int W,
                                                    const float* __restrict__ wgt, const float* __restrict__ bias, int cout,
                                                    int cout_pad, __half* __restrict__ out) {
     extern __shared__ float s_w[];  // [cout][cin*taps] + bias[cout]
@@ -26,6 +27,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
         const int d = (int)(t % D);
         const int b = (int)(t / D);
         float in[4 * TAPS];
+        const uint8_t* omap = occ ? occ + (size_t)__ldg(t2m + b) * D * H * W : nullptr;
         for (int c = 0; c < cin; ++c) {
             int q = 0;
             for (int dz = (DIMS == 3 ? -1 : 0); dz <= (DIMS == 3 ? 1 : 0); ++dz)
@@ -33,7 +35,13 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
                     for (int dx = -1; dx <= 1; ++dx, ++q) {
                         const int zz = d + dz, yy = h + dy, xx = w + dx;
                         const bool ok = zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
-                        in[c * TAPS + q] = ok ? __ldg(x + ((((long long)b * cin + c) * D + zz) * H + yy) * W + xx) : 0.f;
+                        float v = 0.f;
+                        if (ok) {
+                            // map mode: every input channel is the {0,1}-normalised occupancy map (train.py:41-44)
+                            if (omap) v = __ldg(omap + ((long long)zz * H + yy) * W + xx) != 0 ? 1.f : 0.f;
+                            else v = __ldg(x + ((((long long)b * cin + c) * D + zz) * H + yy) * W + xx);
+                        }
+                        in[c * TAPS + q] = v;
                     }
         }
         __half* o = out + pix * cout_pad;
@@ -160,19 +168,30 @@ int grid_for(long long work, int block) {
 
 }  // namespace
 
-extern "C" int nrrt_stem_conv(int dims, const float* x, int n, int cin, int d, int h, int w, const float* weight,
-                              const float* bias, int cout, int cout_pad, void* out, void* stream) {
-    NRRT_REQUIRE(x && weight && bias && out, "null pointer");
+static int stem_launch(int dims, const float* x, const uint8_t* occ, const int32_t* t2m, int n, int cin, int d, int h, int w,
+                       const float* weight, const float* bias, int cout, int cout_pad, void* out, void* stream) {
+    NRRT_REQUIRE((x || (occ && t2m)) && weight && bias && out, "null pointer");
     NRRT_REQUIRE((dims == 2 || dims == 3) && cin >= 1 && cin <= 4 && cout % 8 == 0 && cout_pad % 8 == 0 && cout_pad >= cout, "bad stem shape");
     if (dims == 2) d = 1;
     const int taps = dims == 3 ? 27 : 9;
     const size_t smem = ((size_t)cout * cin * taps + cout) * sizeof(float);
     const long long pixels = (long long)n * d * h * w;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (dims == 2) stem_kernel<2><<<grid_for(pixels, 256), 256, smem, st>>>(x, n, cin, d, h, w, weight, bias, cout, cout_pad, (__half*)out);
-    else stem_kernel<3><<<grid_for(pixels, 256), 256, smem, st>>>(x, n, cin, d, h, w, weight, bias, cout, cout_pad, (__half*)out);
+    if (dims == 2) stem_kernel<2><<<grid_for(pixels, 256), 256, smem, st>>>(x, occ, t2m, n, cin, d, h, w, weight, bias, cout, cout_pad, (__half*)out);
+    else stem_kernel<3><<<grid_for(pixels, 256), 256, smem, st>>>(x, occ, t2m, n, cin, d, h, w, weight, bias, cout, cout_pad, (__half*)out);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
+}
+
+extern "C" int nrrt_stem_conv(int dims, const float* x, int n, int cin, int d, int h, int w, const float* weight,
+                              const float* bias, int cout, int cout_pad, void* out, void* stream) {
+    return stem_launch(dims, x, nullptr, nullptr, n, cin, d, h, w, weight, bias, cout, cout_pad, out, stream);
+}
+
+extern "C" int nrrt_stem_conv_maps(int dims, const uint8_t* occ_maps, const int32_t* task_to_map, int n, int cin, int d, int h,
+                                   int w, const float* weight, const float* bias, int cout, int cout_pad, void* out,
+                                   void* stream) {
+    return stem_launch(dims, nullptr, occ_maps, task_to_map, n, cin, d, h, w, weight, bias, cout, cout_pad, out, stream);
 }
 
 extern "C" int nrrt_coords_branch(const float* coords, int B, int gh, int gw, const float* const* weights,

@@ -85,12 +85,13 @@ def pack_occupancy(occ_maps, dim: int, device=None) -> torch.Tensor:
     lib = _lib.load()
     words = lib.nrrt_words_per_map(cells)
     bits = torch.empty((n_maps, words), dtype=torch.int32, device=device)
+    _lib.count_launch()
     check(lib.nrrt_pack_occupancy(_ptr(occ), _DTYPE_CODE[occ.dtype], 1 if dim == 2 else 0, n_maps, cells, _ptr(bits),
                                   _stream_ptr(device)))
     return bits
 
 
-def build_cdf(logits, mode: int, device=None) -> torch.Tensor:
+def build_cdf(logits, mode: int, device=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Network output (or a ready heat map, mode RAW) [B, cells...] float32 -> sampler CDF [B, cells] float32.
 
     Post-processing + `generate_neural_sample`'s normalisation/cumsum with NumPy's fp32 rounding,
@@ -104,7 +105,8 @@ def build_cdf(logits, mode: int, device=None) -> torch.Tensor:
     lib = _lib.load()
     ws_bytes = lib.nrrt_cdf_workspace_bytes(B, cells)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
-    cdf = torch.empty((B, cells), dtype=torch.float32, device=device)
+    cdf = torch.empty((B, cells), dtype=torch.float32, device=device) if out is None else out
+    _lib.count_launch(2)
     check(lib.nrrt_cdf_build(_ptr(x), mode, B, cells, _ptr(cdf), _ptr(ws), ws_bytes, _stream_ptr(device)))
     return cdf
 
@@ -209,6 +211,7 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
     if samples is None:
         if cdf is not None:
             cdf = _dev(cdf, torch.float32, device)
+        _lib.count_launch()
         check(lib.nrrt_draw_samples(C.byref(p), _ptr(occ_bits), _ptr(task_to_map), _ptr(cdf), _ptr(task_ids), B,
                                     _ptr(buf.samples), _ptr(buf.neural_flag), _ptr(buf.n_draws), _ptr(buf.draw_status), st))
         samples_t, draw_status = buf.samples, buf.draw_status
@@ -221,6 +224,7 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
     out.goal_node, out.best_node, out.best_dist = _ptr(buf.goal_node), _ptr(buf.best_node), _ptr(buf.best_dist)
     out.path_n, out.path_idx, out.path_len = _ptr(buf.path_n), _ptr(buf.path_idx), _ptr(buf.path_len)
     out.trace, out.trace_n, out.trace_cap = _ptr(buf.trace), _ptr(buf.trace_n), trace_cap
+    _lib.count_launch()
     check(lib.nrrt_plan_batch(C.byref(p), _ptr(occ_bits), _ptr(task_to_map), _ptr(radius), _ptr(samples_t), _ptr(starts),
                               _ptr(goals), _ptr(draw_status), C.byref(out), B, _ptr(buf.queue), st))
     return PlanResult(n_nodes=buf.n_nodes, iterations=buf.iterations, status=buf.status, goal_node=buf.goal_node,
@@ -228,3 +232,105 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
                       path_len=buf.path_len, cost=buf.cost, parent=buf.parent, pos=buf.pos, samples=samples_t,
                       neural_flag=buf.neural_flag if samples is None else None,
                       n_draws=buf.n_draws if samples is None else None, trace=buf.trace, trace_n=buf.trace_n)
+
+
+class GuidedPlanner(object):
+    """The whole hot path for a batch of tasks: CNN probability maps -> sampler CDFs -> sample draws -> guided RRT*.
+
+    Equivalent to running, for every task, `model(image, coords)` + post-processing + `neural_rrt.RRTStar(...).rrt_star()`
+    (neural_rrt.py:319-369, test_network_and_algorithms.py:107-134; 3D twins), but batched on one GPU.  `model` is a
+    `train.UNet_cooler` / `ThreeD_train.ThreeD_UNet_cooler` from this package (eval mode, on the CUDA device).
+    """
+
+    def __init__(self, model, dim: int, shape: Sequence[int], max_iterations: int = 5000,
+                 goal_threshold: Optional[float] = None, neural_bias: float = 0.75, micro_batch: Optional[int] = None,
+                 pipeline_batch: int = 4096, path_cap: int = 512, max_reject: int = 100000):
+        self.model, self.dim, self.shape = model, dim, tuple(int(s) for s in shape)
+        self.max_iterations, self.neural_bias = max_iterations, neural_bias
+        self.goal_threshold = goal_threshold if goal_threshold is not None else (5.0 if dim == 2 else 3.0)
+        self.micro_batch = micro_batch or (8 if dim == 2 else 4)
+        self.pipeline_batch, self.path_cap, self.max_reject = pipeline_batch, path_cap, max_reject
+        self.device = next(model.parameters()).device
+        if self.device.type != "cuda":
+            raise _lib.NrrtError("GuidedPlanner needs the model on a CUDA device")
+        self.cells = int(np.prod(self.shape))
+        self._bufs = None
+        self._logits = None
+        self._cdf = None
+        self.profile_every = 0
+
+    def _ensure(self, B):
+        if self._bufs is None or self._logits.shape[0] != B:
+            self._logits = torch.empty((B, self.cells), dtype=torch.float32, device=self.device)
+            self._cdf = torch.empty((B, self.cells), dtype=torch.float32, device=self.device)
+            self._bufs = PlannerBuffers(self.dim, B, self.max_iterations, self.path_cap, False, 0, self.device)
+
+    def probability_maps(self, occ_maps: torch.Tensor, task_to_map: torch.Tensor, coords: torch.Tensor,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """CNN logits [B, cells] fp32 for tasks (occ_maps[task_to_map[b]], coords[b]); occ_maps uint8 on the device."""
+        plan = self.model._plan(self.device)
+        B = task_to_map.shape[0]
+        out = out if out is not None else torch.empty((B, self.cells), dtype=torch.float32, device=self.device)
+        mb = self.micro_batch
+        for mbi, i in enumerate(range(0, B, mb)):
+            if plan.profiler is not None:  # bench.py: time the conv launches of every n-th micro-batch
+                plan.profiler.active = self.profile_every > 0 and mbi % self.profile_every == 0
+            plan.forward_maps(occ_maps, task_to_map[i:i + mb], coords[i:i + mb], logits_out=out[i:i + mb])
+        return out
+
+    def plan(self, occ_maps, task_to_map, starts, goals, coords, seed: int = 0, task_ids=None, record_events=False):
+        """occ_maps [n_maps, *shape] uint8 (2D: 0 = obstacle; 3D: 0 = free), host or device; the rest per task.
+        Returns a list of PlanResult views (one per pipeline batch) concatenated into one PlanResult of host-side
+        friendly device tensors."""
+        dev = self.device
+        occ = _dev(occ_maps, torch.uint8, dev)
+        t2m = _dev(task_to_map, torch.int32, dev).reshape(-1)
+        starts = _dev(starts, torch.int32, dev).reshape(-1, self.dim)
+        goals = _dev(goals, torch.int32, dev).reshape(-1, self.dim)
+        coords = _dev(coords, torch.float32, dev)
+        B = t2m.shape[0]
+        ids = _dev(np.arange(B, dtype=np.int32) if task_ids is None else task_ids, torch.int32, dev).reshape(-1)
+        bits = pack_occupancy(occ, self.dim, dev)
+        mode = HEAT_MODE_2D if self.dim == 2 else HEAT_MODE_3D
+        outs = []
+        ev = []
+        for b0 in range(0, B, self.pipeline_batch):
+            b1 = min(B, b0 + self.pipeline_batch)
+            n = b1 - b0
+            self._ensure(n)
+            if record_events:
+                ev.append([torch.cuda.Event(enable_timing=True) for _ in range(4)])
+                ev[-1][0].record()
+            self.probability_maps(occ, t2m[b0:b1], coords[b0:b1], out=self._logits)
+            if record_events:
+                ev[-1][1].record()
+            build_cdf(self._logits, mode, dev, out=self._cdf)
+            if record_events:
+                ev[-1][2].record()
+            res = plan_batch(bits, t2m[b0:b1], starts[b0:b1], goals[b0:b1], dim=self.dim, shape=self.shape,
+                             max_iterations=self.max_iterations, goal_threshold=self.goal_threshold, cdf=self._cdf,
+                             neural_bias=self.neural_bias, seed=seed, task_ids=ids[b0:b1], path_cap=self.path_cap,
+                             max_reject=self.max_reject, buffers=self._bufs)
+            if record_events:
+                ev[-1][3].record()
+            if B > self.pipeline_batch:  # buffers are reused by the next pipeline batch: keep a compact copy
+                res = PlanResult(**{k: (v.clone() if isinstance(v, torch.Tensor) and k in _COMPACT else None)
+                                    for k, v in res.__dict__.items()})
+            outs.append(res)
+        self._events = ev
+        if len(outs) == 1:
+            return outs[0]
+        return PlanResult(**{k: (torch.cat([getattr(o, k) for o in outs]) if k in _COMPACT else None)
+                             for k in outs[0].__dict__})
+
+    def stage_ms(self):
+        """(cnn, cdf, draw+plan) milliseconds of the last plan(record_events=True) call, after a synchronize."""
+        c = d = p = 0.0
+        for e in self._events:
+            c += e[0].elapsed_time(e[1])
+            d += e[1].elapsed_time(e[2])
+            p += e[2].elapsed_time(e[3])
+        return c, d, p
+
+
+_COMPACT = ("n_nodes", "iterations", "status", "goal_node", "best_node", "best_dist", "path_n", "path_idx", "path_len")
