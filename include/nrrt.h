@@ -114,6 +114,17 @@ int nrrt_plan_batch(const NrrtPlanParams* p, const uint32_t* occ_bits, const int
                     const int16_t* samples, const int32_t* starts, const int32_t* goals, const int32_t* draw_status,
                     const NrrtPlanOut* out, int B, int32_t* queue_counter, void* stream);
 
+/* Batched stand-alone primitives behind the reference's individually callable methods.
+ * nrrt_collision_free: is_collision_free(p1, p2) (rrt_star.py:108-123 / ThreeD_rrt_star.py:115-132) for S segments;
+ *   seg_map[s] selects the occupancy map; p1, p2: [S][dim] fp64; verdict[s] = 1 (free) / 0.
+ * nrrt_tree_search: for Q query points over one tree of n nodes ([n][dim] fp64, insertion order):
+ *   nearest[q] = find_nearest_neighbor (rrt_star.py:70-80); near_mask[q][(n+31)/32] (optional) = bit j set iff
+ *   euclid(query, node_j) <= radii[q] (find_nearby_nodes, rrt_star.py:149-154). */
+int nrrt_collision_free(int dim, const int32_t* shape_host, const uint32_t* occ_bits, const int32_t* seg_map, const double* p1,
+                        const double* p2, int S, int32_t* verdict, void* stream);
+int nrrt_tree_search(int dim, const double* nodes, int n, const double* queries, const double* radii, int Q,
+                     int32_t* nearest, uint32_t* near_mask, void* stream);
+
 /* Shared memory one planner CTA needs for these params (bytes), and CTAs per SM the launch will get (info only). */
 int nrrt_plan_smem_bytes(const NrrtPlanParams* p, size_t* bytes, int* ctas_per_sm);
 
@@ -167,7 +178,7 @@ int nrrt_stem_conv_maps(int dims, const uint8_t* occ_maps, const int32_t* task_t
                         const float* weight, const float* bias, int cout, int cout_pad, void* out, void* stream);
 
 /* Coordinate branch (train.py:179-190): the four conv_coords_* layers (3x3 Conv2d + ReLU) on the (B,1,2,2) / (B,1,2,3)
- * coords tensor in fp32.  weights/biases: 4 pointers, PyTorch layout [cout][cin][3][3].  feats: 4 output pointers,
+ * coords tensor in fp32.  weights: 4 pointers, fp32 [tap = ky*3+kx][cin][cout] (transposed from PyTorch's [cout][cin][3][3]); biases: 4 pointers.  feats: 4 output pointers,
  * fp32 [B][gh*gw][C] with C = 64, 128, 256, 512. */
 int nrrt_coords_branch(const float* coords, int B, int gh, int gw, const float* const* weights, const float* const* biases,
                        float* const* feats, void* stream);
@@ -176,6 +187,12 @@ int nrrt_coords_branch(const float* coords, int B, int gh, int gw, const float* 
  * written as fp16 into channels [out_coffset, out_coffset + C) of a channels-last buffer (the torch.cat target). */
 int nrrt_coords_fill(const float* feat, int B, int gh, int gw, int C, int dims, int od, int oh, int ow, void* out,
                      int64_t out_cstride, int64_t out_coffset, void* stream);
+
+/* Encoder reuse: the encoder (conv1 .. conv5) sees only the occupancy map, and the benchmark has 10 tasks per map, so it
+ * runs once per distinct map; this copies channels [src_coffset, +C) of sample index[b] of a channels-last fp16 buffer
+ * into channels [dst_coffset, +C) of sample b of another (the task's torch.cat buffer, train.py:181,184,187,190). */
+int nrrt_gather_channels(const void* src, int64_t src_cstride, int64_t src_coffset, void* dst, int64_t dst_cstride,
+                         int64_t dst_coffset, int C, int64_t pixels, const int32_t* index, int B, void* stream);
 
 /* final_conv (1x1, C -> 1): fp16 channels-last in, fp32 logits out [B][pixels]. */
 int nrrt_head_1x1(const void* in, int64_t pixels, int C, int64_t in_cstride, const float* weight, float bias, float* logits,

@@ -45,6 +45,10 @@ _SIGNATURES = {
     "nrrt_plan_batch": (C.c_int, [C.POINTER(NrrtPlanParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.POINTER(NrrtPlanOut), C.c_int, C.c_void_p, C.c_void_p]),
     "nrrt_plan_smem_bytes": (C.c_int, [C.POINTER(NrrtPlanParams), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "nrrt_collision_free": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p]),
+    "nrrt_tree_search": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p]),
     "nrrt_conv_layer": (C.c_int, [C.POINTER(NrrtConvLayer), C.c_void_p]),
     "nrrt_stem_conv": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
@@ -53,6 +57,8 @@ _SIGNATURES = {
     "nrrt_coords_branch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrrt_coords_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "nrrt_gather_channels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64,
+                                       C.c_void_p, C.c_int, C.c_void_p]),
     "nrrt_head_1x1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
 }
 

@@ -195,8 +195,9 @@ class UNetPlan(object):
         self.enc = [blocks(model.conv2), blocks(model.conv3), blocks(model.conv4), blocks(model.conv5)]
 
         # ---- coordinate branch (fp32, tiny) ----
-        self.cw = [m[0].weight.detach().float().to(dev).contiguous() for m in
-                   (model.conv_coords_64, model.conv_coords_128, model.conv_coords_256, model.conv_coords_512)]
+        # [cout][cin][3][3] -> [tap][cin][cout]: the kernel's threads run over cout
+        self.cw = [m[0].weight.detach().float().to(dev).permute(2, 3, 1, 0).reshape(9, m[0].in_channels, m[0].out_channels).contiguous()
+                   for m in (model.conv_coords_64, model.conv_coords_128, model.conv_coords_256, model.conv_coords_512)]
         self.cb = [m[0].bias.detach().float().to(dev).contiguous() for m in
                    (model.conv_coords_64, model.conv_coords_128, model.conv_coords_256, model.conv_coords_512)]
         self.cw_ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in self.cw])
@@ -212,34 +213,41 @@ class UNetPlan(object):
         self._bufs = {}
         self.profiler = None
 
-    # activation buffers for a micro-batch of B samples on grid (D, H, W)
-    def _buffers(self, B, grid):
-        key = (B,) + tuple(grid)
+    # activation buffers: encoder set for Be samples (distinct maps), decoder set for B samples (tasks), grid (D, H, W)
+    def _buffers(self, B, Be, grid, shared_encoder):
+        key = (B, Be, shared_encoder) + tuple(grid)
         bufs = self._bufs.get(key)
         if bufs is None:
             dev = self.device
             D, H, W = grid
 
-            def buf(level, ch):
+            def buf(n, level, ch):
                 s = 2 ** level
-                shape = (B, D // s if self.dims == 3 else 1, H // s, W // s, ch)
+                shape = (n, D // s if self.dims == 3 else 1, H // s, W // s, ch)
                 return torch.empty(shape, dtype=torch.float16, device=dev)
 
             bufs = {
-                "t0": buf(0, 64), "x1": buf(0, 64), "a0": buf(0, 64), "b0": buf(0, 64),
-                "cat8": buf(0, 192), "j": buf(0, 128), "k": buf(0, 64),
-                "a1": buf(1, 128), "b1": buf(1, 128), "d1": buf(1, 128), "cat7": buf(1, 384), "g7": buf(1, 256), "i": buf(1, 128),
-                "a2": buf(2, 256), "b2": buf(2, 256), "d2": buf(2, 256), "cat6": buf(2, 1024), "g6": buf(2, 512), "h": buf(2, 256),
-                "a3": buf(3, 512), "b3": buf(3, 512), "d3": buf(3, 512), "x5": buf(3, 1024),
+                "t0": buf(Be, 0, 64), "x1": buf(Be, 0, 64), "a0": buf(Be, 0, 64), "b0": buf(Be, 0, 64),
+                "a1": buf(Be, 1, 128), "b1": buf(Be, 1, 128), "d1": buf(Be, 1, 128),
+                "a2": buf(Be, 2, 256), "b2": buf(Be, 2, 256), "d2": buf(Be, 2, 256),
+                "a3": buf(Be, 3, 512), "b3": buf(Be, 3, 512), "d3": buf(Be, 3, 512),
+                "cat8": buf(B, 0, 192), "j": buf(B, 0, 128), "k": buf(B, 0, 64),
+                "cat7": buf(B, 1, 384), "g7": buf(B, 1, 256), "i": buf(B, 1, 128),
+                "cat6": buf(B, 2, 1024), "g6": buf(B, 2, 512), "h": buf(B, 2, 256),
+                "x5": buf(B, 3, 1024),
             }
+            if shared_encoder:  # per-map encoder outputs, gathered into every task's concat slices afterwards
+                bufs.update({"e2": buf(Be, 0, 64), "e3": buf(Be, 1, 128), "e4": buf(Be, 2, 256), "e5": buf(Be, 3, 512)})
             P = 4 if self.dims == 2 else 6
             bufs["feats"] = [torch.empty((B, P, c), dtype=torch.float32, device=dev) for c in (64, 128, 256, 512)]
             bufs["feat_ptrs"] = (C.c_void_p * 4)(*[t.data_ptr() for t in bufs["feats"]])
-            self._bufs = {key: bufs}  # keep one configuration resident
+            if len(self._bufs) >= 2:  # keep two configurations resident (full and ragged last micro-batch)
+                self._bufs.pop(next(iter(self._bufs)))
+            self._bufs[key] = bufs
         return bufs
 
     def activation_bytes(self, B, grid):
-        b = self._buffers(B, grid)
+        b = self._buffers(B, B, grid, False)
         return sum(t.numel() * t.element_size() for t in b.values() if isinstance(t, torch.Tensor))
 
     def layers(self):
@@ -283,19 +291,39 @@ class UNetPlan(object):
             grid = (x.shape[1], x.shape[2], x.shape[3])
         return self._forward(x.shape[0], grid, coords, logits_out, x=x)
 
-    def forward_maps(self, occ_maps, task_to_map, coords, logits_out=None):
+    def forward_maps(self, occ_maps, task_to_map, coords, logits_out=None, enc_maps=None, enc_index=None, feats=None):
         """Same forward fed from resident uint8 occupancy maps [n_maps, (D,) H, W] + task_to_map [B] (int32): the
-        network input of sample b is the {0,1}-normalised map task_to_map[b] replicated over the input channels."""
-        grid = (1,) + tuple(occ_maps.shape[1:]) if self.dims == 2 else tuple(occ_maps.shape[1:])
-        return self._forward(task_to_map.shape[0], grid, coords, logits_out, occ=occ_maps, t2m=task_to_map)
+        network input of sample b is the {0,1}-normalised map task_to_map[b] replicated over the input channels.
 
-    def _forward(self, B, grid, coords, logits_out, x=None, occ=None, t2m=None):
+        Encoder reuse: the encoder (conv1..conv5) depends on the map only, so callers that know several tasks share a
+        map pass `enc_maps` [Be] (distinct map ids, int32) and `enc_index` [B] (task -> row of enc_maps): the encoder
+        then runs on Be samples and its four outputs are gathered into every task's concat buffers."""
+        grid = (1,) + tuple(occ_maps.shape[1:]) if self.dims == 2 else tuple(occ_maps.shape[1:])
+        B = coords.shape[0]
+        if enc_maps is None:
+            return self._forward(B, grid, coords, logits_out, occ=occ_maps, t2m=task_to_map, feats=feats)
+        return self._forward(B, grid, coords, logits_out, occ=occ_maps, t2m=enc_maps, enc_index=enc_index, feats=feats)
+
+    def coords_features(self, coords):
+        """The four conv_coords_* feature vectors for a whole batch of tasks in one launch: 4 x fp32 [B, P, C]."""
+        coords = coords.contiguous().float()
+        B, P = coords.shape[0], coords.shape[2] * coords.shape[3]
+        feats = [torch.empty((B, P, c), dtype=torch.float32, device=self.device) for c in (64, 128, 256, 512)]
+        ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in feats])
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.count_launch()
+        check(self.lib.nrrt_coords_branch(_ptr(coords), B, coords.shape[2], coords.shape[3], self.cw_ptrs, self.cb_ptrs, ptrs, st))
+        return feats
+
+    def _forward(self, B, grid, coords, logits_out, x=None, occ=None, t2m=None, enc_index=None, feats=None):
         lib, dims = self.lib, self.dims
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         coords = coords.contiguous().float()
         if any(g % 8 for g in grid[(0 if dims == 3 else 1):]):
             raise ValueError("spatial sizes must be multiples of 8 (three stride-2 stages)")
-        bf = self._buffers(B, grid)
+        shared = enc_index is not None
+        Be = t2m.shape[0] if shared else B
+        bf = self._buffers(B, Be, grid, shared)
         g = [tuple(max(v // (2 ** lv), 1) if (dims == 3 or i > 0) else 1 for i, v in enumerate(grid)) for lv in range(4)]
 
         # stem
@@ -304,7 +332,7 @@ class UNetPlan(object):
             check(lib.nrrt_stem_conv(dims, _ptr(x), B, self.stem_cin, grid[0], grid[1], grid[2], _ptr(self.stem_w),
                                      _ptr(self.stem_b), self.stem_cout, 64, _ptr(bf["t0"]), st))
         else:
-            check(lib.nrrt_stem_conv_maps(dims, _ptr(occ), _ptr(t2m), B, self.stem_cin, grid[0], grid[1], grid[2],
+            check(lib.nrrt_stem_conv_maps(dims, _ptr(occ), _ptr(t2m), Be, self.stem_cin, grid[0], grid[1], grid[2],
                                           _ptr(self.stem_w), _ptr(self.stem_b), self.stem_cout, 64, _ptr(bf["t0"]), st))
         self.stem2.run(lib, st, bf["t0"], 0, g[0], bf["x1"], 0)
 
@@ -321,19 +349,31 @@ class UNetPlan(object):
             c3.run(lib, st, b, 0, gout, a, 0)
             c4.run(lib, st, a, 0, gout, final, final_off, b, 0)
 
-        stage(self.enc[0], bf["x1"], 0, g[0], g[0], bf["a0"], bf["b0"], None, bf["cat8"], 64)
-        stage(self.enc[1], bf["cat8"], 64, g[0], g[1], bf["a1"], bf["b1"], bf["d1"], bf["cat7"], 128)
-        stage(self.enc[2], bf["cat7"], 128, g[1], g[2], bf["a2"], bf["b2"], bf["d2"], bf["cat6"], 512)
-        stage(self.enc[3], bf["cat6"], 512, g[2], g[3], bf["a3"], bf["b3"], bf["d3"], bf["x5"], 0)
+        # where each encoder stage's output lives: its slice of the task's concat buffer, or (shared encoder) a per-map buffer
+        fin = ([(bf["e2"], 0), (bf["e3"], 0), (bf["e4"], 0), (bf["e5"], 0)] if shared else
+               [(bf["cat8"], 64), (bf["cat7"], 128), (bf["cat6"], 512), (bf["x5"], 0)])
+        stage(self.enc[0], bf["x1"], 0, g[0], g[0], bf["a0"], bf["b0"], None, fin[0][0], fin[0][1])
+        stage(self.enc[1], fin[0][0], fin[0][1], g[0], g[1], bf["a1"], bf["b1"], bf["d1"], fin[1][0], fin[1][1])
+        stage(self.enc[2], fin[1][0], fin[1][1], g[1], g[2], bf["a2"], bf["b2"], bf["d2"], fin[2][0], fin[2][1])
+        stage(self.enc[3], fin[2][0], fin[2][1], g[2], g[3], bf["a3"], bf["b3"], bf["d3"], fin[3][0], fin[3][1])
+        if shared:
+            for (src, _), (dst, off), ch, lv in zip(fin, [(bf["cat8"], 64), (bf["cat7"], 128), (bf["cat6"], 512), (bf["x5"], 0)],
+                                                    (64, 128, 256, 512), range(4)):
+                _lib.count_launch()
+                check(lib.nrrt_gather_channels(_ptr(src), src.shape[-1], 0, _ptr(dst), dst.shape[-1], off, ch,
+                                               _prod(g[lv]), _ptr(enc_index), B, st))
 
         # coordinate branch + align_corners interpolation into the concat slices (train.py:179-190)
         gh, gw = coords.shape[2], coords.shape[3]
-        _lib.count_launch(5)
-        check(lib.nrrt_coords_branch(_ptr(coords), B, gh, gw, self.cw_ptrs, self.cb_ptrs, bf["feat_ptrs"], st))
+        if feats is None:
+            _lib.count_launch()
+            check(lib.nrrt_coords_branch(_ptr(coords), B, gh, gw, self.cw_ptrs, self.cb_ptrs, bf["feat_ptrs"], st))
+            feats = bf["feats"]
         for feat, ch, name, off, lv in ((0, 64, "cat8", 128, 0), (1, 128, "cat7", 256, 1), (2, 256, "cat6", 768, 2),
                                         (3, 512, "x5", 512, 3)):
             t = bf[name]
-            check(lib.nrrt_coords_fill(_ptr(bf["feats"][feat]), B, gh, gw, ch, dims, g[lv][0], g[lv][1], g[lv][2], _ptr(t),
+            _lib.count_launch()
+            check(lib.nrrt_coords_fill(_ptr(feats[feat]), B, gh, gw, ch, dims, g[lv][0], g[lv][1], g[lv][2], _ptr(t),
                                        t.shape[-1], off, st))
 
         # decoder

@@ -63,37 +63,63 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     }
 }
 
-// ---- coordinate branch: one CTA per task; 3x3 conv, padding 1, on a (gh x gw) grid with gh, gw <= 3 ---------------
-__global__ void __launch_bounds__(256) coords_kernel(const float* __restrict__ coords, int gh, int gw,
+// ---- coordinate branch: 3x3 conv (padding 1) + ReLU on a (gh x gw) grid with gh, gw <= 3, four levels --------------
+// kTB tasks per CTA share every weight read; thread = output channel (weights pre-transposed to [tap][cin][cout] so
+// the warp's loads are coalesced); inputs of the kTB tasks sit in shared memory and are read as broadcasts.
+constexpr int kTB = 4;
+constexpr int kMaxP = 9;
+
+__global__ void __launch_bounds__(256) coords_kernel(const float* __restrict__ coords, int B, int gh, int gw,
                                                      const float* w0, const float* b0, const float* w1, const float* b1,
                                                      const float* w2, const float* b2, const float* w3, const float* b3,
                                                      float* f0, float* f1, float* f2, float* f3) {
-    const int b = blockIdx.x, P = gh * gw;
+    __shared__ float s_in[kTB * kMaxP * 256];
+    const int P = gh * gw;
+    const int t0 = blockIdx.x * kTB;
+    const int nt = min(kTB, B - t0);
     const float* wts[4] = {w0, w1, w2, w3};
     const float* bs[4] = {b0, b1, b2, b3};
-    float* outs[4] = {f0 + (size_t)b * P * 64, f1 + (size_t)b * P * 128, f2 + (size_t)b * P * 256, f3 + (size_t)b * P * 512};
+    float* outs[4] = {f0, f1, f2, f3};
     const int cins[4] = {1, 64, 128, 256}, couts[4] = {64, 128, 256, 512};
-    const float* in = coords + (size_t)b * P;  // (1, gh, gw) -> [P][1]
     for (int l = 0; l < 4; ++l) {
         const int cin = cins[l], cout = couts[l];
-        for (int o = threadIdx.x; o < P * cout; o += blockDim.x) {
-            const int co = o % cout, pp = o / cout, y = pp / gw, x = pp % gw;
-            float acc = bs[l][co];
-            for (int ky = 0; ky < 3; ++ky) {
-                const int yy = y + ky - 1;
-                if (yy < 0 || yy >= gh) continue;
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int xx = x + kx - 1;
-                    if (xx < 0 || xx >= gw) continue;
-                    const float* ip = in + (size_t)(yy * gw + xx) * cin;
-                    const float* wp = wts[l] + ((size_t)co * cin) * 9 + ky * 3 + kx;
-                    for (int ci = 0; ci < cin; ++ci) acc = fmaf(ip[ci], __ldg(wp + (size_t)ci * 9), acc);
+        // stage the inputs of this CTA's tasks: [t][p][ci]
+        const float* src = l == 0 ? coords + (size_t)t0 * P : outs[l - 1] + (size_t)t0 * P * cin;
+        for (int i = threadIdx.x; i < nt * P * cin; i += blockDim.x) s_in[i] = src[i];
+        __syncthreads();
+        for (int co = threadIdx.x; co < cout; co += blockDim.x) {
+            float acc[kTB][kMaxP];
+#pragma unroll
+            for (int t = 0; t < kTB; ++t)
+#pragma unroll
+                for (int pp = 0; pp < kMaxP; ++pp) acc[t][pp] = bs[l][co];
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ky = tap / 3 - 1, kx = tap % 3 - 1;
+                const float* wp = wts[l] + (size_t)tap * cin * cout + co;
+                for (int ci = 0; ci < cin; ++ci) {
+                    const float w = __ldg(wp + (size_t)ci * cout);
+#pragma unroll
+                    for (int pp = 0; pp < kMaxP; ++pp) {
+                        if (pp >= P) break;
+                        const int y = pp / gw + ky, x = pp % gw + kx;
+                        if (y < 0 || y >= gh || x < 0 || x >= gw) continue;
+                        const int sp = y * gw + x;
+#pragma unroll
+                        for (int t = 0; t < kTB; ++t) acc[t][pp] = fmaf(s_in[(t * P + sp) * cin + ci], w, acc[t][pp]);
+                    }
                 }
             }
-            outs[l][(size_t)pp * cout + co] = fmaxf(acc, 0.f);
+#pragma unroll
+            for (int t = 0; t < kTB; ++t) {
+                if (t >= nt) break;
+#pragma unroll
+                for (int pp = 0; pp < kMaxP; ++pp) {
+                    if (pp >= P) break;
+                    outs[l][((size_t)(t0 + t) * P + pp) * cout + co] = fmaxf(acc[t][pp], 0.f);
+                }
+            }
         }
-        __syncthreads();  // global writes of this CTA visible to its own threads for the next layer
-        in = outs[l];
+        __syncthreads();  // this CTA's global writes are visible to its own threads; s_in is free again
     }
 }
 
@@ -122,6 +148,14 @@ __global__ void __launch_bounds__(256) coords_fill_kernel(const float* __restric
         const float* f01 = f00 + (size_t)w1p * C;
         const float* f10 = f00 + (size_t)h1p * gw * C;
         const float* f11 = f10 + (size_t)w1p * C;
+        float v00[8], v01[8], v10[8], v11[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {  // 16-byte loads: the four corner vectors of this thread's 8 channels
+            *reinterpret_cast<float4*>(v00 + 4 * q) = __ldg(reinterpret_cast<const float4*>(f00) + q);
+            *reinterpret_cast<float4*>(v01 + 4 * q) = __ldg(reinterpret_cast<const float4*>(f01) + q);
+            *reinterpret_cast<float4*>(v10 + 4 * q) = __ldg(reinterpret_cast<const float4*>(f10) + q);
+            *reinterpret_cast<float4*>(v11 + 4 * q) = __ldg(reinterpret_cast<const float4*>(f11) + q);
+        }
         uint4 ov;
         __half2* hv = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
@@ -130,7 +164,7 @@ __global__ void __launch_bounds__(256) coords_fill_kernel(const float* __restric
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int c = e * 2 + q;
-                r[q] = h0l * (w0l * __ldg(f00 + c) + w1l * __ldg(f01 + c)) + h1l * (w0l * __ldg(f10 + c) + w1l * __ldg(f11 + c));
+                r[q] = h0l * (w0l * v00[c] + w1l * v01[c]) + h1l * (w0l * v10[c] + w1l * v11[c]);
             }
             hv[e] = __floats2half2_rn(r[0], r[1]);
         }
@@ -158,6 +192,24 @@ __global__ void __launch_bounds__(256) head_kernel(const __half* __restrict__ in
             }
         }
         logits[pix] = acc;
+    }
+}
+
+// ---- encoder reuse: copy a channel slice of per-map features into every task's concat buffer ----------------------
+__global__ void __launch_bounds__(256) gather_channels_kernel(const __half* __restrict__ src, long long src_cstride,
+                                                              long long src_coffset, __half* __restrict__ dst,
+                                                              long long dst_cstride, long long dst_coffset, int C,
+                                                              long long pixels, const int32_t* __restrict__ index, int B) {
+    const int cv = C / 8;
+    const long long total = (long long)B * pixels * cv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i % cv);
+        const long long t = i / cv;
+        const long long pix = t % pixels;
+        const int b = (int)(t / pixels);
+        const long long sp = (long long)__ldg(index + b) * pixels + pix;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + sp * src_cstride + src_coffset + c8 * 8));
+        *reinterpret_cast<uint4*>(dst + ((long long)b * pixels + pix) * dst_cstride + dst_coffset + c8 * 8) = v;
     }
 }
 
@@ -199,7 +251,7 @@ extern "C" int nrrt_coords_branch(const float* coords, int B, int gh, int gw, co
     NRRT_REQUIRE(coords && weights && biases && feats, "null pointer");
     NRRT_REQUIRE(B >= 0 && gh >= 1 && gh <= 3 && gw >= 1 && gw <= 3, "coords grid must be at most 3x3");
     if (B == 0) return NRRT_OK;
-    coords_kernel<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coords, gh, gw, weights[0], biases[0], weights[1], biases[1],
+    coords_kernel<<<(B + kTB - 1) / kTB, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coords, B, gh, gw, weights[0], biases[0], weights[1], biases[1],
                                                                          weights[2], biases[2], weights[3], biases[3], feats[0],
                                                                          feats[1], feats[2], feats[3]);
     NRRT_CUDA_TRY(cudaGetLastError());
@@ -214,6 +266,19 @@ extern "C" int nrrt_coords_fill(const float* feat, int B, int gh, int gw, int C,
     if (total == 0) return NRRT_OK;
     coords_fill_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(feat, B, gh, gw, C, a0, a1, a2, (__half*)out,
                                                                                                 out_cstride, out_coffset);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_gather_channels(const void* src, int64_t src_cstride, int64_t src_coffset, void* dst, int64_t dst_cstride,
+                                    int64_t dst_coffset, int C, int64_t pixels, const int32_t* index, int B, void* stream) {
+    NRRT_REQUIRE(src && dst && index, "null pointer");
+    NRRT_REQUIRE(C % 8 == 0 && src_cstride % 8 == 0 && src_coffset % 8 == 0 && dst_cstride % 8 == 0 && dst_coffset % 8 == 0,
+                 "channel counts/offsets must be multiples of 8");
+    const long long total = (long long)B * pixels * (C / 8);
+    if (total <= 0) return NRRT_OK;
+    gather_channels_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __half*)src, src_cstride, src_coffset, (__half*)dst, dst_cstride, dst_coffset, C, pixels, index, B);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

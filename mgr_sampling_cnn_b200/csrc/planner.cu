@@ -62,10 +62,17 @@ __device__ __forceinline__ bool nn_a_wins(double sa, int ja, double sb, int jb) 
 
 // is_collision_free (rrt_star.py:108-123 / ThreeD_rrt_star.py:115-132), one warp, 100 samples over lanes.
 // Grid bit = 1 means the reference treats the cell as free.
+//
+// The reference evaluates c_k = int(p1_k - ((t_i * d_k) / D)) with three separately rounded operations per coordinate;
+// the fp64 division dominates the cost.  A sample's cell is decided by floor(), so the exact arithmetic only matters
+// when the value is within rounding distance of an integer.  Fast path: v' = fma(-t_i, d_k / D, p1_k) differs from the
+// reference value by < 1e-9 (a few ulps of a number <= 2^15), so whenever v' is farther than 1e-6 from every integer
+// both truncate to the same cell; otherwise (segment ends on integer cells, axis-parallel moves, coincidences) the
+// lane re-evaluates the reference's exact sequence.  t = 0 and d_k = 0 are exact without any division.
 template <int DIM>
 __device__ __forceinline__ bool collision_free_warp(const double (&p1)[DIM], const double (&p2)[DIM],
                                                     const uint32_t* __restrict__ grid, const int (&shape)[3], int lane) {
-    double dl[DIM];
+    double dl[DIM], u[DIM];
     bool same = true;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
@@ -78,15 +85,24 @@ __device__ __forceinline__ bool collision_free_warp(const double (&p1)[DIM], con
     if (DIM == 3) q = __fma_rn(dl[DIM - 1], dl[DIM - 1], q);
     const double D = sqrt(q);
     const double step = __ddiv_rn(D, 99.0);  // np.linspace(0, D, 100)
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) u[k] = __ddiv_rn(dl[k], D);
 #pragma unroll 1
-    for (int i = lane; i < 100 + kWarp - 1 - ((100 + kWarp - 1) % kWarp); i += kWarp) {
+    for (int i = lane; i < 128; i += kWarp) {
         bool blocked = false;
         if (i < 100) {
             const double t = (i == 99) ? D : __dmul_rn((double)i, step);
             int idx = 0;
 #pragma unroll
             for (int k = 0; k < DIM; ++k) {
-                const double v = __dsub_rn(p1[k], __ddiv_rn(__dmul_rn(t, dl[k]), D));
+                double v;
+                if (i == 0 || dl[k] == 0.0) {
+                    v = p1[k];  // (0 * d) / D = +-0 and p1 - +-0 = p1: exact
+                } else {
+                    v = __fma_rn(-t, u[k], p1[k]);
+                    if (fabs(v - rint(v)) <= 1e-6)  // rounding could change the cell: the reference's exact sequence
+                        v = __dsub_rn(p1[k], __ddiv_rn(__dmul_rn(t, dl[k]), D));
+                }
                 int ci = __double2int_rz(v);  // int(): truncation toward zero
                 ci = max(0, min(ci, shape[k] - 1));
                 idx = idx * shape[k] + ci;
@@ -159,13 +175,22 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
         int n = 1, best_node = -1, goal_node = -1, iters = 0;
         double best = INFINITY;
         const int16_t* smp_base = a.samples + (size_t)task * max_iter * DIM;
+        double r_next = __ldg(a.radius);
+        int16_t smp_next[DIM];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) smp_next[k] = __ldg(smp_base + k);
 
         for (int it = 0; it < max_iter; ++it) {
             iters = it + 1;
-            const double r = __ldg(a.radius + it);
+            const double r = r_next;
             double smp[DIM];
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) smp[k] = (double)__ldg(smp_base + it * DIM + k);
+            for (int k = 0; k < DIM; ++k) smp[k] = (double)smp_next[k];
+            if (it + 1 < max_iter) {  // next iteration's inputs travel while this one computes
+                r_next = __ldg(a.radius + it + 1);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) smp_next[k] = __ldg(smp_base + (it + 1) * DIM + k);
+            }
 
             // ---- find_nearest_neighbor: scan + argmin (strict <, lowest index wins) ----
             double bs = INFINITY;
@@ -383,6 +408,113 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
         }
     }
 }
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stand-alone batched primitives behind the reference's individually callable methods (same device functions as the
+// planner kernel): is_collision_free, find_nearest_neighbor, find_nearby_nodes.
+// ------------------------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void __launch_bounds__(128) collision_kernel(const uint32_t* __restrict__ occ_bits, int words_per_map,
+                                                        const int32_t* __restrict__ seg_map, const double* __restrict__ p1,
+                                                        const double* __restrict__ p2, int S, int s0, int s1, int s2,
+                                                        int32_t* __restrict__ verdict) {
+    const int lane = threadIdx.x & 31;
+    const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (s >= S) return;
+    const int shape[3] = {s0, s1, s2};
+    double a[DIM], b[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) { a[k] = p1[(size_t)s * DIM + k]; b[k] = p2[(size_t)s * DIM + k]; }
+    const bool fr = collision_free_warp<DIM>(a, b, occ_bits + (size_t)seg_map[s] * words_per_map, shape, lane);
+    if (lane == 0) verdict[s] = fr ? 1 : 0;
+}
+
+// one CTA per query: nearest node index (strict <, lowest index on ties of the sqrt'ed distance) and the near mask
+template <int DIM>
+__global__ void __launch_bounds__(256) search_kernel(const double* __restrict__ nodes, int n, const double* __restrict__ queries,
+                                                     const double* __restrict__ radii, int32_t* __restrict__ nearest,
+                                                     uint32_t* __restrict__ near_mask, int mask_words) {
+    __shared__ Slot slots[8];
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double qp[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) qp[k] = queries[(size_t)q * DIM + k];
+    double bs = INFINITY;
+    int bj = 0x7fffffff;
+    for (int j = tid; j < n; j += 256) {
+        double pj[DIM];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) pj[k] = nodes[(size_t)j * DIM + k];
+        const double s = nrrt_sqdist<DIM>(pj, qp);
+        if (s < bs) {
+            bool take = true;
+            if (s > __dmul_rn(bs, NRRT_K_LO)) take = sqrt(s) < sqrt(bs);
+            if (take) { bs = s; bj = j; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (!nn_a_wins(bs, bj, os, oj)) { bs = os; bj = oj; }
+    }
+    if (lane == 0) { slots[warp].v = bs; slots[warp].j = bj; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (!nn_a_wins(bs, bj, slots[w].v, slots[w].j)) { bs = slots[w].v; bj = slots[w].j; }
+        nearest[q] = n > 0 ? bj : -1;
+    }
+    if (near_mask) {
+        const double r = radii[q];
+        const double r2 = __dmul_rn(r, r);
+        const double r2lo = __dmul_rn(r2, NRRT_K_LO), r2hi = __dmul_rn(r2, NRRT_K_HI);
+        for (int base = 0; base < n; base += 256) {
+            const int j = base + tid;
+            bool in = false;
+            if (j < n) {
+                double pj[DIM];
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) pj[k] = nodes[(size_t)j * DIM + k];
+                const double s = nrrt_sqdist<DIM>(qp, pj);
+                in = (s <= r2lo) ? true : ((s >= r2hi) ? false : (sqrt(s) <= r));
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, in);
+            if (lane == 0 && (base >> 5) + warp < mask_words) near_mask[(size_t)q * mask_words + (base >> 5) + warp] = m;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int nrrt_collision_free(int dim, const int32_t* shape, const uint32_t* occ_bits, const int32_t* seg_map,
+                                   const double* p1, const double* p2, int S, int32_t* verdict, void* stream) {
+    NRRT_REQUIRE((dim == 2 || dim == 3) && shape && occ_bits && seg_map && p1 && p2 && verdict, "bad collision arguments");
+    if (S <= 0) return NRRT_OK;
+    const int64_t cells = (int64_t)shape[0] * shape[1] * (dim == 3 ? shape[2] : 1);
+    const int wpm = (int)nrrt_words_per_map(cells);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dim == 2) collision_kernel<2><<<(S + 3) / 4, 128, 0, st>>>(occ_bits, wpm, seg_map, p1, p2, S, shape[0], shape[1], 1, verdict);
+    else collision_kernel<3><<<(S + 3) / 4, 128, 0, st>>>(occ_bits, wpm, seg_map, p1, p2, S, shape[0], shape[1], shape[2], verdict);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_tree_search(int dim, const double* nodes, int n, const double* queries, const double* radii, int Q,
+                                int32_t* nearest, uint32_t* near_mask, void* stream) {
+    NRRT_REQUIRE((dim == 2 || dim == 3) && nodes && queries && nearest && n >= 0, "bad search arguments");
+    NRRT_REQUIRE(near_mask == nullptr || radii != nullptr, "near_mask needs radii");
+    if (Q <= 0) return NRRT_OK;
+    const int mask_words = (n + 31) / 32;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dim == 2) search_kernel<2><<<Q, 256, 0, st>>>(nodes, n, queries, radii, nearest, near_mask, mask_words);
+    else search_kernel<3><<<Q, 256, 0, st>>>(nodes, n, queries, radii, nearest, near_mask, mask_words);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+namespace {
 
 struct SmemPlan {
     size_t bytes;

@@ -248,7 +248,7 @@ class GuidedPlanner(object):
         self.model, self.dim, self.shape = model, dim, tuple(int(s) for s in shape)
         self.max_iterations, self.neural_bias = max_iterations, neural_bias
         self.goal_threshold = goal_threshold if goal_threshold is not None else (5.0 if dim == 2 else 3.0)
-        self.micro_batch = micro_batch or (8 if dim == 2 else 4)
+        self.micro_batch = micro_batch or (10 if dim == 2 else 5)  # one / half a map's worth of tasks
         self.pipeline_batch, self.path_cap, self.max_reject = pipeline_batch, path_cap, max_reject
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
@@ -258,6 +258,7 @@ class GuidedPlanner(object):
         self._logits = None
         self._cdf = None
         self.profile_every = 0
+        self.share_encoder = True
 
     def _ensure(self, B):
         if self._bufs is None or self._logits.shape[0] != B:
@@ -266,16 +267,38 @@ class GuidedPlanner(object):
             self._bufs = PlannerBuffers(self.dim, B, self.max_iterations, self.path_cap, False, 0, self.device)
 
     def probability_maps(self, occ_maps: torch.Tensor, task_to_map: torch.Tensor, coords: torch.Tensor,
-                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """CNN logits [B, cells] fp32 for tasks (occ_maps[task_to_map[b]], coords[b]); occ_maps uint8 on the device."""
+                         out: Optional[torch.Tensor] = None, task_to_map_host: Optional[np.ndarray] = None) -> torch.Tensor:
+        """CNN logits [B, cells] fp32 for tasks (occ_maps[task_to_map[b]], coords[b]); occ_maps uint8 on the device.
+
+        The encoder runs once per distinct map of a micro-batch (tasks of one map are adjacent in the reference's
+        task files, generate_tasks.py:18-24), the decoder once per task."""
         plan = self.model._plan(self.device)
         B = task_to_map.shape[0]
         out = out if out is not None else torch.empty((B, self.cells), dtype=torch.float32, device=self.device)
         mb = self.micro_batch
+        t2m_h = task_to_map_host if task_to_map_host is not None else task_to_map.cpu().numpy()
+        # per micro-batch: distinct maps and the task -> encoder-row index, built on the host once and uploaded together
+        enc_maps, enc_index, spans = [], [], []
+        for i in range(0, B, mb):
+            u, inv = np.unique(t2m_h[i:i + mb], return_inverse=True)
+            spans.append((len(enc_maps), len(u)))
+            enc_maps.extend(u.tolist())
+            enc_index.extend(inv.tolist())
+        feats = plan.coords_features(coords)  # the coordinate branch for every task in one launch
+        enc_maps_d = torch.tensor(enc_maps, dtype=torch.int32).to(self.device, non_blocking=True)
+        enc_index_d = torch.tensor(enc_index, dtype=torch.int32).to(self.device, non_blocking=True)
         for mbi, i in enumerate(range(0, B, mb)):
             if plan.profiler is not None:  # bench.py: time the conv launches of every n-th micro-batch
                 plan.profiler.active = self.profile_every > 0 and mbi % self.profile_every == 0
-            plan.forward_maps(occ_maps, task_to_map[i:i + mb], coords[i:i + mb], logits_out=out[i:i + mb])
+            o, n_u = spans[mbi]
+            n = min(mb, B - i)
+            if self.share_encoder and n_u < n:
+                plan.forward_maps(occ_maps, None, coords[i:i + mb], logits_out=out[i:i + mb],
+                                  enc_maps=enc_maps_d[o:o + n_u], enc_index=enc_index_d[i:i + mb],
+                                  feats=[f[i:i + mb] for f in feats])
+            else:
+                plan.forward_maps(occ_maps, task_to_map[i:i + mb], coords[i:i + mb], logits_out=out[i:i + mb],
+                                  feats=[f[i:i + mb] for f in feats])
         return out
 
     def plan(self, occ_maps, task_to_map, starts, goals, coords, seed: int = 0, task_ids=None, record_events=False):
@@ -284,6 +307,7 @@ class GuidedPlanner(object):
         friendly device tensors."""
         dev = self.device
         occ = _dev(occ_maps, torch.uint8, dev)
+        t2m_host = (task_to_map.cpu().numpy() if isinstance(task_to_map, torch.Tensor) else np.asarray(task_to_map)).reshape(-1)
         t2m = _dev(task_to_map, torch.int32, dev).reshape(-1)
         starts = _dev(starts, torch.int32, dev).reshape(-1, self.dim)
         goals = _dev(goals, torch.int32, dev).reshape(-1, self.dim)
@@ -301,7 +325,7 @@ class GuidedPlanner(object):
             if record_events:
                 ev.append([torch.cuda.Event(enable_timing=True) for _ in range(4)])
                 ev[-1][0].record()
-            self.probability_maps(occ, t2m[b0:b1], coords[b0:b1], out=self._logits)
+            self.probability_maps(occ, t2m[b0:b1], coords[b0:b1], out=self._logits, task_to_map_host=t2m_host[b0:b1])
             if record_events:
                 ev[-1][1].record()
             build_cdf(self._logits, mode, dev, out=self._cdf)

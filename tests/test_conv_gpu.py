@@ -165,3 +165,24 @@ def test_unet_forward_full_size_2d_vs_fp32_oracle(cuda_device):
     torch.cuda.synchronize()
     err = (y - ref).abs().max().item()
     assert err <= 1e-2, f"max abs err {err} (ref range {ref.min().item():.3f}..{ref.max().item():.3f})"
+
+
+def test_shared_encoder_equals_per_task_encoder(cuda_device):
+    """GuidedPlanner runs the encoder once per distinct map; logits must equal the per-task forward bit-for-bit."""
+    from mgr_sampling_cnn_b200 import engine, train, workload
+    wl = workload.make_2d(13, size=128)  # 2 maps: 10 + 3 tasks -> micro-batches with 1 and 2 distinct maps
+    torch.manual_seed(0)
+    model = train.UNet_cooler().eval().to(cuda_device)
+    gp = engine.GuidedPlanner(model, 2, wl.shape, micro_batch=6)
+    occ = torch.from_numpy(wl.occ_maps).to(cuda_device)
+    t2m = torch.from_numpy(wl.task_to_map).to(cuda_device)
+    coords = torch.from_numpy(wl.coords).to(cuda_device)
+    a = gp.probability_maps(occ, t2m, coords).clone()
+    gp.share_encoder = False
+    b = gp.probability_maps(occ, t2m, coords).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    x = torch.from_numpy((wl.occ_maps[wl.task_to_map] != 0).astype(np.float32))[:, None].repeat(1, 3, 1, 1).to(cuda_device)
+    with torch.no_grad():
+        ref = cnn_oracle.forward({k: v.float() for k, v in model.state_dict().items()}, x, coords, 2)
+    assert (a.reshape(ref.shape) - ref).abs().max().item() <= 1e-2
