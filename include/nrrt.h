@@ -162,6 +162,9 @@ typedef struct NrrtConvLayer {
     int32_t relu;
     const float* post_scale; /* optional second affine + ReLU (3D stem: conv, ReLU, BatchNorm3d, ReLU) */
     const float* post_shift;
+    const float* poly;       /* optional (2D) fp32 [n][poly_cases][4][cout] from nrrt_coords_poly: the contribution of the
+                                interpolated coordinate channels, added as E0 + ty*E1 + tx*E2 + ty*tx*E3 before the ReLU */
+    int32_t poly_cases;      /* 9 for a 3x3 conv (border cases), 4 for a 2D ConvTranspose (one per output offset) */
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);
@@ -187,6 +190,16 @@ int nrrt_coords_branch(const float* coords, int B, int gh, int gw, const float* 
  * written as fp16 into channels [out_coffset, out_coffset + C) of a channels-last buffer (the torch.cat target). */
 int nrrt_coords_fill(const float* feat, int B, int gh, int gw, int C, int dims, int od, int oh, int ow, void* out,
                      int64_t out_cstride, int64_t out_coffset, void* stream);
+
+/* Coordinate channels folded into an epilogue polynomial (2D).  F.interpolate(..., align_corners=True) of the 2x2
+ * coordinate feature (train.py:180,183,186,189) is bilinear in the pixel position, so a convolution over those channels
+ * is a bilinear function of the output position with per-task coefficients E (derivation in csrc/conv_aux.cu).
+ * feat: fp32 [B][4][Cc] (nrrt_coords_branch output); moments: fp32 [cases][n_uv][Cc][Cout] tap moments of the
+ * coordinate slice of the consumer's weight (n_uv = 4 for 3x3 convs with cases = 9 border cases; n_uv = 1 for
+ * ConvTranspose with cases = 4 output offsets); a = 1/(H-1), b = 1/(W-1) of the consumer's input grid;
+ * E: fp32 [B][cases][4][Cout]. */
+int nrrt_coords_poly(const float* feat, int B, int Cc, const float* moments, int cases, int n_uv, int Cout, float a, float b,
+                     float* E, void* stream);
 
 /* Encoder reuse: the encoder (conv1 .. conv5) sees only the occupancy map, and the benchmark has 10 tasks per map, so it
  * runs once per distinct map; this copies channels [src_coffset, +C) of sample index[b] of a channels-last fp16 buffer

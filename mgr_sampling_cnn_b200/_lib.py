@@ -30,7 +30,8 @@ class NrrtConvLayer(C.Structure):
                 ("in_w", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("in_", C.c_void_p), ("in_cstride", C.c_int64),
                 ("weight", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("out", C.c_void_p),
                 ("out_cstride", C.c_int64), ("out_coffset", C.c_int64), ("res", C.c_void_p), ("res_cstride", C.c_int64),
-                ("res_coffset", C.c_int64), ("relu", C.c_int32), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p)]
+                ("res_coffset", C.c_int64), ("relu", C.c_int32), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p),
+                ("poly", C.c_void_p), ("poly_cases", C.c_int32)]
 
 
 _SIGNATURES = {
@@ -57,6 +58,8 @@ _SIGNATURES = {
     "nrrt_coords_branch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrrt_coords_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "nrrt_coords_poly": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_void_p]),
     "nrrt_gather_channels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64,
                                        C.c_void_p, C.c_int, C.c_void_p]),
     "nrrt_head_1x1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),

@@ -111,16 +111,16 @@ class _Layer(object):
         taps = (3 ** self.dims) if self.kind in (K3S1, K3S2) else 1
         return 2.0 * batch * _prod([(g - 1) // stride + 1 for g in sp]) * self.cout * taps * self.cin_real
 
-    def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0):
+    def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None):
         """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W)."""
         prof = self.profiler
         if prof is not None and prof.active:
             with prof.launch(self.flops(x.shape[0], grid)):
-                self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff)
+                self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly)
         else:
-            self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff)
+            self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly)
 
-    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff):
+    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly=None):
         _lib.count_launch()
         L = _lib.NrrtConvLayer()
         L.dims, L.kind = self.dims, self.kind
@@ -136,6 +136,8 @@ class _Layer(object):
         L.relu = 1 if self.relu else 0
         if self.post is not None:
             L.post_scale, L.post_shift = _ptr(self.post[0]), _ptr(self.post[1])
+        if poly is not None:
+            L.poly, L.poly_cases = _ptr(poly), poly.shape[1]
         check(lib.nrrt_conv_layer(C.byref(L), stream))
 
 
@@ -204,10 +206,50 @@ class UNetPlan(object):
         self.cb_ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in self.cb])
 
         # ---- decoder ----
-        self.up6, self.up7, self.up8 = convT(model.upconv6), convT(model.upconv7), convT(model.upconv8)
-        self.c6 = (conv(model.conv6[0], K3S1), conv(model.conv6[2], K3S1))
-        self.c7 = (conv(model.conv7[0], K3S1), conv(model.conv7[2], K3S1))
-        self.c8 = (conv(model.conv8[0], K3S1), conv(model.conv8[2], K3S1))
+        # 2D: the interpolated coordinate channels are bilinear in the pixel position, so the four layers that consume
+        # them (upconv6, conv6.0, conv7.0, conv8.0) drop those channels from the GEMM K and add their contribution as a
+        # per-task polynomial in the epilogue (nrrt_coords_poly).  3D keeps them as materialised channels (the (2,3,1)
+        # coordinate grid is only piecewise bilinear).
+        self.poly = d == 2
+
+        def conv_sliced(m, keep):
+            """3x3 conv that reads only the first `keep` input channels (the rest are coordinate channels)."""
+            scale, shift = _fold_bn(None, m.bias, m.out_channels, dev)
+            return _Layer(d, K3S1, keep, m.out_channels, _pack_conv_weight(m.weight[:, :keep], keep, dev), scale, shift, True,
+                          cin_real=keep)
+
+        def conv_moments(m, keep):
+            """Tap moments of the coordinate slice: [9 border cases][uv = 00,10,01,11][Cc][Cout] fp32."""
+            wc = m.weight.detach().float().to(dev)[:, keep:]            # [Cout, Cc, 3, 3]
+            off = torch.tensor([-1.0, 0.0, 1.0], device=dev)
+            out = torch.zeros((9, 4) + (wc.shape[1], wc.shape[0]), dtype=torch.float32, device=dev)
+            valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}                # tap indices inside the image per border case
+            for ry in range(3):
+                for rx in range(3):
+                    sub = wc[:, :, valid[ry]][:, :, :, valid[rx]]       # [Cout, Cc, ny, nx]
+                    dy = off[valid[ry]].view(1, 1, -1, 1)
+                    dx = off[valid[rx]].view(1, 1, 1, -1)
+                    for uv, wgt in enumerate((torch.ones_like(dy * dx), dy * torch.ones_like(dx), dx * torch.ones_like(dy), dy * dx)):
+                        out[ry * 3 + rx, uv] = (sub * wgt).sum(dim=(2, 3)).t()
+            return out.contiguous()
+
+        if self.poly:
+            mu = model.upconv6
+            scale = torch.ones(4 * mu.out_channels, dtype=torch.float32, device=dev)
+            shift = mu.bias.detach().float().to(dev).repeat(4).contiguous()
+            self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(mu.weight[:512], dev), scale, shift, False)
+            # ConvTranspose groups g = a*2+b: moments [4][1][Cc][Cout] = the coordinate rows of the weight
+            self.m_up6 = mu.weight.detach().float().to(dev)[512:].permute(2, 3, 0, 1).reshape(4, 1, 512, mu.out_channels).contiguous()
+            self.up7, self.up8 = convT(model.upconv7), convT(model.upconv8)
+            self.c6 = (conv_sliced(model.conv6[0], 768), conv(model.conv6[2], K3S1))
+            self.c7 = (conv_sliced(model.conv7[0], 256), conv(model.conv7[2], K3S1))
+            self.c8 = (conv_sliced(model.conv8[0], 128), conv(model.conv8[2], K3S1))
+            self.m_c6, self.m_c7, self.m_c8 = conv_moments(model.conv6[0], 768), conv_moments(model.conv7[0], 256), conv_moments(model.conv8[0], 128)
+        else:
+            self.up6, self.up7, self.up8 = convT(model.upconv6), convT(model.upconv7), convT(model.upconv8)
+            self.c6 = (conv(model.conv6[0], K3S1), conv(model.conv6[2], K3S1))
+            self.c7 = (conv(model.conv7[0], K3S1), conv(model.conv7[2], K3S1))
+            self.c8 = (conv(model.conv8[0], K3S1), conv(model.conv8[2], K3S1))
         self.head_w = model.final_conv.weight.detach().float().to(dev).reshape(-1).contiguous()
         self.head_b = float(model.final_conv.bias.detach().float().item())
         self._bufs = {}
@@ -226,21 +268,19 @@ class UNetPlan(object):
                 shape = (n, D // s if self.dims == 3 else 1, H // s, W // s, ch)
                 return torch.empty(shape, dtype=torch.float16, device=dev)
 
+            c8w, c7w, c6w, x5w = (128, 256, 768, 512) if self.poly else (192, 384, 1024, 1024)
             bufs = {
                 "t0": buf(Be, 0, 64), "x1": buf(Be, 0, 64), "a0": buf(Be, 0, 64), "b0": buf(Be, 0, 64),
                 "a1": buf(Be, 1, 128), "b1": buf(Be, 1, 128), "d1": buf(Be, 1, 128),
                 "a2": buf(Be, 2, 256), "b2": buf(Be, 2, 256), "d2": buf(Be, 2, 256),
                 "a3": buf(Be, 3, 512), "b3": buf(Be, 3, 512), "d3": buf(Be, 3, 512),
-                "cat8": buf(B, 0, 192), "j": buf(B, 0, 128), "k": buf(B, 0, 64),
-                "cat7": buf(B, 1, 384), "g7": buf(B, 1, 256), "i": buf(B, 1, 128),
-                "cat6": buf(B, 2, 1024), "g6": buf(B, 2, 512), "h": buf(B, 2, 256),
-                "x5": buf(B, 3, 1024),
+                "cat8": buf(B, 0, c8w), "j": buf(B, 0, 128), "k": buf(B, 0, 64),
+                "cat7": buf(B, 1, c7w), "g7": buf(B, 1, 256), "i": buf(B, 1, 128),
+                "cat6": buf(B, 2, c6w), "g6": buf(B, 2, 512), "h": buf(B, 2, 256),
+                "x5": buf(B, 3, x5w),
             }
             if shared_encoder:  # per-map encoder outputs, gathered into every task's concat slices afterwards
                 bufs.update({"e2": buf(Be, 0, 64), "e3": buf(Be, 1, 128), "e4": buf(Be, 2, 256), "e5": buf(Be, 3, 512)})
-            P = 4 if self.dims == 2 else 6
-            bufs["feats"] = [torch.empty((B, P, c), dtype=torch.float32, device=dev) for c in (64, 128, 256, 512)]
-            bufs["feat_ptrs"] = (C.c_void_p * 4)(*[t.data_ptr() for t in bufs["feats"]])
             if len(self._bufs) >= 2:  # keep two configurations resident (full and ragged last micro-batch)
                 self._bufs.pop(next(iter(self._bufs)))
             self._bufs[key] = bufs
@@ -291,7 +331,7 @@ class UNetPlan(object):
             grid = (x.shape[1], x.shape[2], x.shape[3])
         return self._forward(x.shape[0], grid, coords, logits_out, x=x)
 
-    def forward_maps(self, occ_maps, task_to_map, coords, logits_out=None, enc_maps=None, enc_index=None, feats=None):
+    def forward_maps(self, occ_maps, task_to_map, coords, logits_out=None, enc_maps=None, enc_index=None, prep=None):
         """Same forward fed from resident uint8 occupancy maps [n_maps, (D,) H, W] + task_to_map [B] (int32): the
         network input of sample b is the {0,1}-normalised map task_to_map[b] replicated over the input channels.
 
@@ -301,21 +341,41 @@ class UNetPlan(object):
         grid = (1,) + tuple(occ_maps.shape[1:]) if self.dims == 2 else tuple(occ_maps.shape[1:])
         B = coords.shape[0]
         if enc_maps is None:
-            return self._forward(B, grid, coords, logits_out, occ=occ_maps, t2m=task_to_map, feats=feats)
-        return self._forward(B, grid, coords, logits_out, occ=occ_maps, t2m=enc_maps, enc_index=enc_index, feats=feats)
+            return self._forward(B, grid, coords, logits_out, occ=occ_maps, t2m=task_to_map, prep=prep)
+        return self._forward(B, grid, coords, logits_out, occ=occ_maps, t2m=enc_maps, enc_index=enc_index, prep=prep)
 
-    def coords_features(self, coords):
-        """The four conv_coords_* feature vectors for a whole batch of tasks in one launch: 4 x fp32 [B, P, C]."""
+    def coords_prepare(self, coords, grid):
+        """Coordinate branch for a whole batch of tasks in a few launches: the four conv_coords_* feature vectors
+        (fp32 [B, P, C]) and, in 2D, the epilogue polynomials E of the four consumer layers (fp32 [B, cases, 4, Cout])."""
         coords = coords.contiguous().float()
         B, P = coords.shape[0], coords.shape[2] * coords.shape[3]
-        feats = [torch.empty((B, P, c), dtype=torch.float32, device=self.device) for c in (64, 128, 256, 512)]
+        dev = self.device
+        feats = [torch.empty((B, P, c), dtype=torch.float32, device=dev) for c in (64, 128, 256, 512)]
         ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in feats])
-        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         _lib.count_launch()
         check(self.lib.nrrt_coords_branch(_ptr(coords), B, coords.shape[2], coords.shape[3], self.cw_ptrs, self.cb_ptrs, ptrs, st))
-        return feats
+        prep = {"feats": feats}
+        if self.poly:
+            if P != 4:
+                raise ValueError("2D coords must be (B, 1, 2, 2)")
+            g = [tuple(max(v // (2 ** lv), 1) if i > 0 else 1 for i, v in enumerate(grid)) for lv in range(4)]
+            for name, feat, mom, lv in (("e_up6", feats[3], self.m_up6, 3), ("e_c6", feats[2], self.m_c6, 2),
+                                        ("e_c7", feats[1], self.m_c7, 1), ("e_c8", feats[0], self.m_c8, 0)):
+                cases, n_uv, cc, cout = mom.shape
+                E = torch.empty((B, cases, 4, cout), dtype=torch.float32, device=dev)
+                a = 1.0 / (g[lv][1] - 1) if g[lv][1] > 1 else 0.0
+                b = 1.0 / (g[lv][2] - 1) if g[lv][2] > 1 else 0.0
+                _lib.count_launch()
+                check(self.lib.nrrt_coords_poly(_ptr(feat), B, cc, _ptr(mom), cases, n_uv, cout, a, b, _ptr(E), st))
+                prep[name] = E
+        return prep
 
-    def _forward(self, B, grid, coords, logits_out, x=None, occ=None, t2m=None, enc_index=None, feats=None):
+    @staticmethod
+    def slice_prep(prep, i, j):
+        return {k: ([f[i:j] for f in v] if isinstance(v, list) else v[i:j]) for k, v in prep.items()}
+
+    def _forward(self, B, grid, coords, logits_out, x=None, occ=None, t2m=None, enc_index=None, prep=None):
         lib, dims = self.lib, self.dims
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         coords = coords.contiguous().float()
@@ -350,41 +410,39 @@ class UNetPlan(object):
             c4.run(lib, st, a, 0, gout, final, final_off, b, 0)
 
         # where each encoder stage's output lives: its slice of the task's concat buffer, or (shared encoder) a per-map buffer
-        fin = ([(bf["e2"], 0), (bf["e3"], 0), (bf["e4"], 0), (bf["e5"], 0)] if shared else
-               [(bf["cat8"], 64), (bf["cat7"], 128), (bf["cat6"], 512), (bf["x5"], 0)])
+        cat_slots = [(bf["cat8"], 64), (bf["cat7"], 128), (bf["cat6"], 512), (bf["x5"], 0)]
+        fin = [(bf["e2"], 0), (bf["e3"], 0), (bf["e4"], 0), (bf["e5"], 0)] if shared else cat_slots
         stage(self.enc[0], bf["x1"], 0, g[0], g[0], bf["a0"], bf["b0"], None, fin[0][0], fin[0][1])
         stage(self.enc[1], fin[0][0], fin[0][1], g[0], g[1], bf["a1"], bf["b1"], bf["d1"], fin[1][0], fin[1][1])
         stage(self.enc[2], fin[1][0], fin[1][1], g[1], g[2], bf["a2"], bf["b2"], bf["d2"], fin[2][0], fin[2][1])
         stage(self.enc[3], fin[2][0], fin[2][1], g[2], g[3], bf["a3"], bf["b3"], bf["d3"], fin[3][0], fin[3][1])
         if shared:
-            for (src, _), (dst, off), ch, lv in zip(fin, [(bf["cat8"], 64), (bf["cat7"], 128), (bf["cat6"], 512), (bf["x5"], 0)],
-                                                    (64, 128, 256, 512), range(4)):
+            for (src, _), (dst, off), ch, lv in zip(fin, cat_slots, (64, 128, 256, 512), range(4)):
                 _lib.count_launch()
                 check(lib.nrrt_gather_channels(_ptr(src), src.shape[-1], 0, _ptr(dst), dst.shape[-1], off, ch,
                                                _prod(g[lv]), _ptr(enc_index), B, st))
 
-        # coordinate branch + align_corners interpolation into the concat slices (train.py:179-190)
-        gh, gw = coords.shape[2], coords.shape[3]
-        if feats is None:
-            _lib.count_launch()
-            check(lib.nrrt_coords_branch(_ptr(coords), B, gh, gw, self.cw_ptrs, self.cb_ptrs, bf["feat_ptrs"], st))
-            feats = bf["feats"]
-        for feat, ch, name, off, lv in ((0, 64, "cat8", 128, 0), (1, 128, "cat7", 256, 1), (2, 256, "cat6", 768, 2),
-                                        (3, 512, "x5", 512, 3)):
-            t = bf[name]
-            _lib.count_launch()
-            check(lib.nrrt_coords_fill(_ptr(feats[feat]), B, gh, gw, ch, dims, g[lv][0], g[lv][1], g[lv][2], _ptr(t),
-                                       t.shape[-1], off, st))
+        # coordinate branch (train.py:179-190)
+        if prep is None:
+            prep = self.coords_prepare(coords, grid)
+        if not self.poly:  # materialise the interpolated channels into the concat slices
+            gh, gw = coords.shape[2], coords.shape[3]
+            for feat, ch, name, off, lv in ((0, 64, "cat8", 128, 0), (1, 128, "cat7", 256, 1), (2, 256, "cat6", 768, 2),
+                                            (3, 512, "x5", 512, 3)):
+                t = bf[name]
+                _lib.count_launch()
+                check(lib.nrrt_coords_fill(_ptr(prep["feats"][feat]), B, gh, gw, ch, dims, g[lv][0], g[lv][1], g[lv][2], _ptr(t),
+                                           t.shape[-1], off, st))
 
         # decoder
-        self.up6.run(lib, st, bf["x5"], 0, g[3], bf["cat6"], 0)
-        self.c6[0].run(lib, st, bf["cat6"], 0, g[2], bf["g6"], 0)
+        self.up6.run(lib, st, bf["x5"], 0, g[3], bf["cat6"], 0, poly=prep.get("e_up6"))
+        self.c6[0].run(lib, st, bf["cat6"], 0, g[2], bf["g6"], 0, poly=prep.get("e_c6"))
         self.c6[1].run(lib, st, bf["g6"], 0, g[2], bf["h"], 0)
         self.up7.run(lib, st, bf["h"], 0, g[2], bf["cat7"], 0)
-        self.c7[0].run(lib, st, bf["cat7"], 0, g[1], bf["g7"], 0)
+        self.c7[0].run(lib, st, bf["cat7"], 0, g[1], bf["g7"], 0, poly=prep.get("e_c7"))
         self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
         self.up8.run(lib, st, bf["i"], 0, g[1], bf["cat8"], 0)
-        self.c8[0].run(lib, st, bf["cat8"], 0, g[0], bf["j"], 0)
+        self.c8[0].run(lib, st, bf["cat8"], 0, g[0], bf["j"], 0, poly=prep.get("e_c8"))
         self.c8[1].run(lib, st, bf["j"], 0, g[0], bf["k"], 0)
 
         pixels = B * grid[0] * grid[1] * grid[2]

@@ -50,6 +50,9 @@ struct ConvParams {
     const __half* res;
     long long res_cstride, res_coffset;
     int relu;
+    const float* poly;   // optional [N][poly_cases][4][cout]: bilinear epilogue term E0 + ty*E1 + tx*E2 + ty*tx*E3
+    int poly_cases;      // 9 = 3x3 border cases (row case * 3 + column case); else one case per weight group
+    float inv_h, inv_w;  // 1/(H-1), 1/(W-1) of the tile-space grid
     uint32_t a_bytes, b_bytes;
 };
 
@@ -283,6 +286,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     float f[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), sc[c * 32 + i], sh[c * 32 + i]);
+                    if (p.poly) {
+                        int kcase = g;
+                        if (p.poly_cases == 9)
+                            kcase = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
+                        const float ty = (float)h * p.inv_h, tx = (float)w * p.inv_w, tyx = ty * tx;
+                        const float4* e0 = reinterpret_cast<const float4*>(p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co);
+                        const float4* e1 = e0 + p.cout / 4;
+                        const float4* e2 = e1 + p.cout / 4;
+                        const float4* e3 = e2 + p.cout / 4;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 a0 = __ldg(e0 + q), a1 = __ldg(e1 + q), a2 = __ldg(e2 + q), a3 = __ldg(e3 + q);
+                            f[q * 4 + 0] += a0.x + ty * a1.x + tx * a2.x + tyx * a3.x;
+                            f[q * 4 + 1] += a0.y + ty * a1.y + tx * a2.y + tyx * a3.y;
+                            f[q * 4 + 2] += a0.z + ty * a1.z + tx * a2.z + tyx * a3.z;
+                            f[q * 4 + 3] += a0.w + ty * a1.w + tx * a2.w + tyx * a3.w;
+                        }
+                    }
                     if (p.res) {
                         const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coffset + co);
 #pragma unroll
@@ -441,6 +462,15 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     NRRT_REQUIRE((l->post_scale == nullptr) == (l->post_shift == nullptr), "post_scale and post_shift go together");
     p.res = (const __half*)l->res; p.res_cstride = l->res_cstride; p.res_coffset = l->res_coffset;
     p.relu = l->relu;
+    p.poly = l->poly;
+    p.poly_cases = l->poly_cases;
+    p.inv_h = p.H > 1 ? 1.0f / (float)(p.H - 1) : 0.f;
+    p.inv_w = p.W > 1 ? 1.0f / (float)(p.W - 1) : 0.f;
+    if (l->poly) {
+        NRRT_REQUIRE(!three_d, "the polynomial coordinate term is 2D only");
+        NRRT_REQUIRE(((uintptr_t)l->poly & 15) == 0 && l->cout % 4 == 0, "poly must be 16-byte aligned");
+        NRRT_REQUIRE(l->poly_cases == (up == 2 ? groups : 9), "poly_cases must be 9 (3x3 conv) or the number of weight groups (ConvTranspose)");
+    }
     p.a_bytes = (uint32_t)p.rows * 128u;
     p.b_bytes = (uint32_t)block_n * 128u;
 

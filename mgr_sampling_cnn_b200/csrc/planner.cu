@@ -60,6 +60,32 @@ __device__ __forceinline__ bool nn_a_wins(double sa, int ja, double sb, int jb) 
     return sa < sb;
 }
 
+// Rare slow path of the nearest-neighbour scan (two squares within 2^-50 relative): compare like the reference, on the
+// sqrt'ed values.  Kept out of line so the two DSQRT sequences are not if-converted into the hot loop.
+__device__ __noinline__ bool nn_take_slow(double s, double bs) { return sqrt(s) < sqrt(bs); }
+
+// Warp argmin in reference order.  Non-negative doubles order like their bit patterns, so the common case is an integer
+// min + REDUX for the lowest index among exact ties; only when two different squares lie within 8 ulps (the window
+// in which sqrt rounding can merge or reorder them) does the warp fall back to the sqrt-aware combine.
+__device__ __forceinline__ void nn_warp_reduce(double& bs, int& bj) {
+    const long long key = __double_as_longlong(bs);
+    long long kmin = key;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    const bool tie = key == kmin;
+    if (!__any_sync(0xffffffffu, !tie && (key - kmin <= 8))) {
+        bj = (int)__reduce_min_sync(0xffffffffu, tie ? (unsigned)bj : 0x7fffffffu);
+        bs = __longlong_as_double(kmin);
+        return;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+        if (!nn_a_wins(bs, bj, os, oj)) { bs = os; bj = oj; }
+    }
+}
+
 // is_collision_free (rrt_star.py:108-123 / ThreeD_rrt_star.py:115-132), one warp, 100 samples over lanes.
 // Grid bit = 1 means the reference treats the cell as free.
 //
@@ -202,25 +228,37 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
                 const double s = nrrt_sqdist<DIM>(pj, smp);
                 if (s < bs) {
                     bool take = true;
-                    if (s > __dmul_rn(bs, NRRT_K_LO)) take = sqrt(s) < sqrt(bs);  // sqrt-tie hazard, rare
+                    if (s > __dmul_rn(bs, NRRT_K_LO)) take = nn_take_slow(s, bs);  // sqrt-tie hazard, rare
                     if (take) { bs = s; bj = j; }
                 }
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double os = __shfl_xor_sync(0xffffffffu, bs, o);
-                const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                if (!nn_a_wins(bs, bj, os, oj)) { bs = os; bj = oj; }
-            }
+            nn_warp_reduce(bs, bj);
             Slot* snn = slot_nn + (it & 1) * NW;
             if (lane == 0) { snn[warp].v = bs; snn[warp].j = bj; }
             __syncthreads();  // (1)
-            bs = snn[0].v; bj = snn[0].j;
+            {
+                // all threads combine the NW warp results redundantly (no second barrier): integer keys first
+                long long kmin = __double_as_longlong(snn[0].v);
 #pragma unroll
-            for (int w = 1; w < NW; ++w) {
-                const double os = snn[w].v;
-                const int oj = snn[w].j;
-                if (!nn_a_wins(bs, bj, os, oj)) { bs = os; bj = oj; }
+                for (int w = 1; w < NW; ++w) kmin = min(kmin, __double_as_longlong(snn[w].v));
+                bool hazard = false;
+                int jmin = 0x7fffffff;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const long long kw = __double_as_longlong(snn[w].v);
+                    if (kw == kmin) jmin = min(jmin, snn[w].j);
+                    else hazard = hazard || (kw - kmin <= 8);
+                }
+                if (!hazard) {
+                    bs = __longlong_as_double(kmin); bj = jmin;
+                } else {  // two different squares within a few ulps: compare the sqrt'ed values like the reference
+                    bs = snn[0].v; bj = snn[0].j;
+                    for (int w = 1; w < NW; ++w) {
+                        const double os = snn[w].v;
+                        const int oj = snn[w].j;
+                        if (!nn_a_wins(bs, bj, os, oj)) { bs = os; bj = oj; }
+                    }
+                }
             }
             const int ni = bj;
 
@@ -449,16 +487,11 @@ __global__ void __launch_bounds__(256) search_kernel(const double* __restrict__ 
         const double s = nrrt_sqdist<DIM>(pj, qp);
         if (s < bs) {
             bool take = true;
-            if (s > __dmul_rn(bs, NRRT_K_LO)) take = sqrt(s) < sqrt(bs);
+            if (s > __dmul_rn(bs, NRRT_K_LO)) take = nn_take_slow(s, bs);
             if (take) { bs = s; bj = j; }
         }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double os = __shfl_xor_sync(0xffffffffu, bs, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-        if (!nn_a_wins(bs, bj, os, oj)) { bs = os; bj = oj; }
-    }
+    nn_warp_reduce(bs, bj);
     if (lane == 0) { slots[warp].v = bs; slots[warp].j = bj; }
     __syncthreads();
     if (tid == 0) {

@@ -75,8 +75,10 @@ __device__ __forceinline__ float block_reduce_min(float v, float* red, bool is_m
     return r;
 }
 
-// One CTA per task: min/max, then NumPy's pairwise sum of w = h - m with the exact tree (leaves of <=128 elements with
-// 8 strided accumulators, binary combine tree as laid out by the host in `ops`).
+// One CTA per task: min/max, then NumPy's pairwise sum of w = h - m with the exact tree: leaves of <= 128 elements with
+// 8 strided accumulators (8 lanes per leaf, lane k owns accumulator k, so a warp reads four 32-byte sectors per load and
+// the 8-way combine ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is three xor-shuffles), then the binary combine tree laid out
+// by the host in `ops`.  The task's row is read from HBM once (min pass) and from L2 afterwards.
 __global__ void __launch_bounds__(256) cdf_stats_kernel(const float* __restrict__ logits, int mode, int64_t cells,
                                                         const LeafOp* __restrict__ leaves, int n_leaves,
                                                         const LeafOp* __restrict__ ops, const int32_t* __restrict__ level_off,
@@ -85,39 +87,59 @@ __global__ void __launch_bounds__(256) cdf_stats_kernel(const float* __restrict_
     __shared__ float red[32];
     const int b = blockIdx.x, tid = threadIdx.x;
     const float* x = logits + (size_t)b * cells;
+    const bool vec = (cells % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
 
     float vmin = 0.f, vmax = 0.f;
     if (mode == 1) {
         float lo = INFINITY, hi = -INFINITY;
-        for (int64_t j = tid; j < cells; j += blockDim.x) { const float v = __ldg(x + j); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        if (vec) {
+            for (int64_t j = tid; j < cells / 4; j += blockDim.x) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(x) + j);
+                lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
+                hi = fmaxf(fmaxf(hi, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            }
+        } else {
+            for (int64_t j = tid; j < cells; j += blockDim.x) { const float v = __ldg(x + j); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+        }
         vmin = block_reduce_min(lo, red, false);
         vmax = block_reduce_min(hi, red, true);
     }
     float m = INFINITY;
-    for (int64_t j = tid; j < cells; j += blockDim.x) m = fminf(m, heat_value(__ldg(x + j), mode, vmin, vmax));
+    if (vec) {
+        for (int64_t j = tid; j < cells / 4; j += blockDim.x) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + j);
+            m = fminf(fminf(m, fminf(heat_value(v.x, mode, vmin, vmax), heat_value(v.y, mode, vmin, vmax))),
+                      fminf(heat_value(v.z, mode, vmin, vmax), heat_value(v.w, mode, vmin, vmax)));
+        }
+    } else {
+        for (int64_t j = tid; j < cells; j += blockDim.x) m = fminf(m, heat_value(__ldg(x + j), mode, vmin, vmax));
+    }
     m = block_reduce_min(m, red, false);
 
-    for (int l = tid; l < n_leaves; l += blockDim.x) {
-        const int off = leaves[l].a, len = leaves[l].b;
+    const int k = tid & 7;
+    for (int l0 = 0; l0 < n_leaves; l0 += blockDim.x / 8) {
+        const int l = l0 + (tid >> 3);
+        const bool on = l < n_leaves;
+        const int off = on ? leaves[l].a : 0, len = on ? leaves[l].b : 0;
         const float* a = x + off;
-        float res;
-        if (len < 8) {
-            res = __fsub_rn(heat_value(__ldg(a), mode, vmin, vmax), m);
-            for (int i = 1; i < len; ++i) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + i), mode, vmin, vmax), m));
-        } else {
-            float r[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) r[k] = __fsub_rn(heat_value(__ldg(a + k), mode, vmin, vmax), m);
-            int i = 8;
-            for (; i < len - (len % 8); i += 8) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], __fsub_rn(heat_value(__ldg(a + i + k), mode, vmin, vmax), m));
-            }
-            res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                            __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-            for (; i < len; ++i) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + i), mode, vmin, vmax), m));
+        // every lane reaches the three shuffles at the same program point (leaves of one warp may differ in length)
+        float r = 0.f;
+        int i = 0;
+        if (len >= 8) {
+            r = __fsub_rn(heat_value(__ldg(a + k), mode, vmin, vmax), m);
+            for (i = 8; i < len - (len % 8); i += 8) r = __fadd_rn(r, __fsub_rn(heat_value(__ldg(a + i + k), mode, vmin, vmax), m));
         }
-        leaf_sum[l] = res;
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+        float res = r;
+        if (len >= 8) {
+            for (; i < len; ++i) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + i), mode, vmin, vmax), m));
+        } else if (len > 0) {  // n < 8: plain left-to-right sum
+            res = __fsub_rn(heat_value(__ldg(a), mode, vmin, vmax), m);
+            for (int q = 1; q < len; ++q) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + q), mode, vmin, vmax), m));
+        }
+        if (on && k == 0) leaf_sum[l] = res;
     }
     __syncthreads();
     for (int lv = 0; lv < n_levels; ++lv) {  // deepest level first; left child's slot accumulates
@@ -128,50 +150,81 @@ __global__ void __launch_bounds__(256) cdf_stats_kernel(const float* __restrict_
     if (tid == 0) stats[b] = make_float4(vmin, vmax, m, leaf_sum[0]);
 }
 
-// Sequential fp32 cumsum with NumPy's rounding, 32 tasks per warp (lane = task): a [32 tasks x 32 cells] tile is loaded
-// with coalesced rows, p = fl32(w / S) is computed element-parallel, the tile is transposed through shared memory and
-// every lane carries its own task's running sum through its row.
-__global__ void __launch_bounds__(32) cdf_chain_kernel(const float* __restrict__ logits, int mode, int B, int64_t cells,
-                                                       const float4* __restrict__ stats, float* __restrict__ cdf) {
-    __shared__ float tile[32][33];
-    const int lane = threadIdx.x;
+// Sequential fp32 cumsum with NumPy's rounding (fp32 addition is not associative, so every task's running sum is a
+// strictly serial chain).  One CTA = 32 tasks x 4 warps.  Per chunk of 128 cells: all warps turn the raw logits they
+// prefetched into p = fl32(w / S) and park them in a [32 tasks][128] shared tile (coalesced loads, conflict-free
+// transposed tile); warp 0 carries the 32 running sums through the tile, one task per lane; all warps stream the tile
+// back out coalesced.  The global loads of chunk i+1 are issued before the chain of chunk i, so HBM latency is hidden.
+constexpr int kChainCols = 128;
+constexpr int kChainPitch = kChainCols + 1;
+
+__global__ void __launch_bounds__(128) cdf_chain_kernel(const float* __restrict__ logits, int mode, int B, int64_t cells,
+                                                        const float4* __restrict__ stats, float* __restrict__ cdf) {
+    __shared__ float tile[32 * kChainPitch];
+    __shared__ float4 s_stats[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b0 = blockIdx.x * 32;
     const int rows = min(32, B - b0);
-    const int my_task = b0 + lane;
+    if (threadIdx.x < 32) s_stats[threadIdx.x] = threadIdx.x < rows ? __ldg(stats + b0 + threadIdx.x) : make_float4(0, 0, 0, 1);
+    __syncthreads();
+    float raw[8][4];   // this thread's 8 task rows (warp*8 ..) x 4 column groups of the current chunk
+    auto load_chunk = [&](int64_t c0) {
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const int r = warp * 8 + rr;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int64_t c = c0 + lane + 32 * e;
+                raw[rr][e] = (r < rows && c < cells) ? __ldg(logits + (size_t)(b0 + r) * cells + c) : 0.f;
+            }
+        }
+    };
+    load_chunk(0);
     float acc = 0.f;
     bool first = true;
-    float4 st_row[1];
-    (void)st_row;
-    for (int64_t c0 = 0; c0 < cells; c0 += 32) {
-        const int64_t c = c0 + lane;
-#pragma unroll 4
-        for (int r = 0; r < rows; ++r) {
-            const float4 st = __ldg(stats + b0 + r);
-            float p = 0.f;
-            if (c < cells) {
-                const float h = heat_value(__ldg(logits + (size_t)(b0 + r) * cells + c), mode, st.x, st.y);
-                p = __fdiv_rn(__fsub_rn(h, st.z), st.w);
-            }
-            tile[r][lane] = p;
-        }
-        __syncwarp();
-        if (lane < rows) {
-            const int nc = (int)min((int64_t)32, cells - c0);
-            for (int q = 0; q < nc; ++q) {
-                const float p = tile[lane][q];
-                acc = first ? p : __fadd_rn(acc, p);
-                first = false;
-                tile[lane][q] = acc;
+    for (int64_t c0 = 0; c0 < cells; c0 += kChainCols) {
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const int r = warp * 8 + rr;
+            const float4 st = s_stats[r];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float h = heat_value(raw[rr][e], mode, st.x, st.y);
+                tile[r * kChainPitch + lane + 32 * e] = __fdiv_rn(__fsub_rn(h, st.z), st.w);
             }
         }
-        __syncwarp();
-        if (c < cells) {
-#pragma unroll 4
-            for (int r = 0; r < rows; ++r) cdf[(size_t)(b0 + r) * cells + c] = tile[r][lane];
+        if (c0 + kChainCols < cells) load_chunk(c0 + kChainCols);
+        __syncthreads();
+        if (warp == 0 && lane < rows) {
+            const int nc = (int)min((int64_t)kChainCols, cells - c0);
+            float* row = tile + lane * kChainPitch;
+            int q = 0;
+            if (first && nc > 0) { acc = row[0]; q = 1; first = false; }
+            for (; q + 8 <= nc; q += 8) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = row[q + e];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { acc = __fadd_rn(acc, v[e]); v[e] = acc; }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) row[q + e] = v[e];
+            }
+            for (; q < nc; ++q) { acc = __fadd_rn(acc, row[q]); row[q] = acc; }
         }
-        __syncwarp();
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 8; ++rr) {
+            const int r = warp * 8 + rr;
+            if (r < rows) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int64_t c = c0 + lane + 32 * e;
+                    if (c < cells) cdf[(size_t)(b0 + r) * cells + c] = tile[r * kChainPitch + lane + 32 * e];
+                }
+            }
+        }
+        __syncthreads();
     }
-    (void)my_task;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -384,7 +437,7 @@ extern "C" int nrrt_cdf_build(const float* logits, int mode, int B, int64_t cell
     cdf_stats_kernel<<<B, 256, smem, st>>>(logits, mode, cells, d_leaves, (int)t.leaves.size(), d_ops, d_level,
                                            (int)level_off.size() - 1, stats);
     NRRT_CUDA_TRY(cudaGetLastError());
-    cdf_chain_kernel<<<(B + 31) / 32, 32, 0, st>>>(logits, mode, B, cells, stats, cdf);
+    cdf_chain_kernel<<<(B + 31) / 32, 128, 0, st>>>(logits, mode, B, cells, stats, cdf);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

@@ -284,7 +284,8 @@ class GuidedPlanner(object):
             spans.append((len(enc_maps), len(u)))
             enc_maps.extend(u.tolist())
             enc_index.extend(inv.tolist())
-        feats = plan.coords_features(coords)  # the coordinate branch for every task in one launch
+        grid = (1,) + self.shape if self.dim == 2 else self.shape
+        prep = plan.coords_prepare(coords, grid)  # coordinate branch (+ 2D epilogue polynomials) for every task at once
         enc_maps_d = torch.tensor(enc_maps, dtype=torch.int32).to(self.device, non_blocking=True)
         enc_index_d = torch.tensor(enc_index, dtype=torch.int32).to(self.device, non_blocking=True)
         for mbi, i in enumerate(range(0, B, mb)):
@@ -295,10 +296,10 @@ class GuidedPlanner(object):
             if self.share_encoder and n_u < n:
                 plan.forward_maps(occ_maps, None, coords[i:i + mb], logits_out=out[i:i + mb],
                                   enc_maps=enc_maps_d[o:o + n_u], enc_index=enc_index_d[i:i + mb],
-                                  feats=[f[i:i + mb] for f in feats])
+                                  prep=plan.slice_prep(prep, i, i + mb))
             else:
                 plan.forward_maps(occ_maps, task_to_map[i:i + mb], coords[i:i + mb], logits_out=out[i:i + mb],
-                                  feats=[f[i:i + mb] for f in feats])
+                                  prep=plan.slice_prep(prep, i, i + mb))
         return out
 
     def plan(self, occ_maps, task_to_map, starts, goals, coords, seed: int = 0, task_ids=None, record_events=False):
