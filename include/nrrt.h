@@ -165,6 +165,11 @@ typedef struct NrrtConvLayer {
     const float* poly;       /* optional (2D) fp32 [n][poly_cases][4][cout] from nrrt_coords_poly: the contribution of the
                                 interpolated coordinate channels, added as E0 + ty*E1 + tx*E2 + ty*tx*E3 before the ReLU */
     int32_t poly_cases;      /* 9 for a 3x3 conv (border cases), 4 for a 2D ConvTranspose (one per output offset) */
+    const float* head_weight;/* optional fused final_conv (1x1, cout -> 1): when `logits` is set the layer's activation is not
+                                stored (out may be NULL); logits[pixel] = head_bias + sum_c act[c] * head_weight[c] */
+    float head_bias;
+    float* logits;           /* fp32 [n][pixels] */
+    int32_t force_per_tap;   /* testing: use the generic per-tap kernel even where the slab kernel applies */
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);

@@ -31,7 +31,8 @@ class NrrtConvLayer(C.Structure):
                 ("weight", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("out", C.c_void_p),
                 ("out_cstride", C.c_int64), ("out_coffset", C.c_int64), ("res", C.c_void_p), ("res_cstride", C.c_int64),
                 ("res_coffset", C.c_int64), ("relu", C.c_int32), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p),
-                ("poly", C.c_void_p), ("poly_cases", C.c_int32)]
+                ("poly", C.c_void_p), ("poly_cases", C.c_int32), ("head_weight", C.c_void_p), ("head_bias", C.c_float),
+                ("logits", C.c_void_p), ("force_per_tap", C.c_int32)]
 
 
 _SIGNATURES = {

@@ -111,16 +111,19 @@ class _Layer(object):
         taps = (3 ** self.dims) if self.kind in (K3S1, K3S2) else 1
         return 2.0 * batch * _prod([(g - 1) // stride + 1 for g in sp]) * self.cout * taps * self.cin_real
 
-    def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None):
-        """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W)."""
+    force_per_tap = False  # tests: run the generic per-tap kernel where the slab kernel would be chosen
+
+    def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None, head=None):
+        """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W).
+        head = (weight fp32 [cout], bias float, logits fp32 tensor): fuse the 1x1 output head, `out` may be None."""
         prof = self.profiler
         if prof is not None and prof.active:
             with prof.launch(self.flops(x.shape[0], grid)):
-                self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly)
+                self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head)
         else:
-            self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly)
+            self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head)
 
-    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly=None):
+    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly=None, head=None):
         _lib.count_launch()
         L = _lib.NrrtConvLayer()
         L.dims, L.kind = self.dims, self.kind
@@ -130,7 +133,13 @@ class _Layer(object):
         L.in_ = C.c_void_p(x.data_ptr() + x_coff * esz)
         L.in_cstride = x.shape[-1]
         L.weight, L.scale, L.shift = _ptr(self.weight), _ptr(self.scale), _ptr(self.shift)
-        L.out, L.out_cstride, L.out_coffset = _ptr(out), out.shape[-1], out_coff
+        if out is not None:
+            L.out, L.out_cstride, L.out_coffset = _ptr(out), out.shape[-1], out_coff
+        else:
+            L.out_cstride, L.out_coffset = self.cout, 0
+        if head is not None:
+            L.head_weight, L.head_bias, L.logits = _ptr(head[0]), float(head[1]), _ptr(head[2])
+        L.force_per_tap = 1 if self.force_per_tap else 0
         if res is not None:
             L.res, L.res_cstride, L.res_coffset = _ptr(res), res.shape[-1], res_coff
         L.relu = 1 if self.relu else 0
@@ -274,7 +283,7 @@ class UNetPlan(object):
                 "a1": buf(Be, 1, 128), "b1": buf(Be, 1, 128), "d1": buf(Be, 1, 128),
                 "a2": buf(Be, 2, 256), "b2": buf(Be, 2, 256), "d2": buf(Be, 2, 256),
                 "a3": buf(Be, 3, 512), "b3": buf(Be, 3, 512), "d3": buf(Be, 3, 512),
-                "cat8": buf(B, 0, c8w), "j": buf(B, 0, 128), "k": buf(B, 0, 64),
+                "cat8": buf(B, 0, c8w), "j": buf(B, 0, 128),
                 "cat7": buf(B, 1, c7w), "g7": buf(B, 1, 256), "i": buf(B, 1, 128),
                 "cat6": buf(B, 2, c6w), "g6": buf(B, 2, 512), "h": buf(B, 2, 256),
                 "x5": buf(B, 3, x5w),
@@ -443,15 +452,14 @@ class UNetPlan(object):
         self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
         self.up8.run(lib, st, bf["i"], 0, g[1], bf["cat8"], 0)
         self.c8[0].run(lib, st, bf["cat8"], 0, g[0], bf["j"], 0, poly=prep.get("e_c8"))
-        self.c8[1].run(lib, st, bf["j"], 0, g[0], bf["k"], 0)
 
-        pixels = B * grid[0] * grid[1] * grid[2]
+        # conv8.2 + final_conv fused: the 64-channel activation is reduced to the logit in the epilogue
         logits = logits_out
         if logits is None:
             logits = torch.empty((B, 1) + (tuple(grid) if dims == 3 else tuple(grid[1:])), dtype=torch.float32, device=self.device)
-        _lib.count_launch()
-        check(lib.nrrt_head_1x1(_ptr(bf["k"]), pixels, 64, 64, _ptr(self.head_w), self.head_b, _ptr(logits), st))
+        self.c8[1].run(lib, st, bf["j"], 0, g[0], None, 0, head=(self.head_w, self.head_b, logits))
         return logits
+
 
 
 class CudaForwardMixin(object):

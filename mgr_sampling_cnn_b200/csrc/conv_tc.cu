@@ -53,6 +53,9 @@ struct ConvParams {
     const float* poly;   // optional [N][poly_cases][4][cout]: bilinear epilogue term E0 + ty*E1 + tx*E2 + ty*tx*E3
     int poly_cases;      // 9 = 3x3 border cases (row case * 3 + column case); else one case per weight group
     float inv_h, inv_w;  // 1/(H-1), 1/(W-1) of the tile-space grid
+    const float* head_w; // optional fused 1x1 head (cout -> 1): logits[pixel] = head_b + sum_c relu_out[c] * head_w[c]
+    float head_b;
+    float* logits;
     uint32_t a_bytes, b_bytes;
 };
 
@@ -133,6 +136,82 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+}
+
+// Epilogue of 32 accumulator columns of one output pixel: folded-BN scale/shift, polynomial coordinate term, residual,
+// ReLU, optional second affine + ReLU, then either the fp16 store into the output channel slice or (fused 1x1 head) a
+// running dot product with the head weights.  col = first GEMM column, lc = its offset inside the staged scale/shift.
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[32], int col, int lc, int n, int d,
+                                               int h, int w, const float* sc, const float* sh, const float* sc2,
+                                               const float* sh2, float& head_acc) {
+    const int g = col / p.cout, co = col - g * p.cout;
+    int od = d, oh = h, ow = w;
+    if (p.up == 2) {
+        if (p.up_d == 2) { od = 2 * d + (g >> 2); oh = 2 * h + ((g >> 1) & 1); ow = 2 * w + (g & 1); }
+        else { oh = 2 * h + (g >> 1); ow = 2 * w + (g & 1); }
+    }
+    const long long pix = (((long long)n * p.oD + od) * p.oH + oh) * p.oW + ow;
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), sc[lc + i], sh[lc + i]);
+    if (p.poly) {
+        int kcase = g;
+        if (p.poly_cases == 9)
+            kcase = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
+        const float ty = (float)h * p.inv_h, tx = (float)w * p.inv_w, tyx = ty * tx;
+        const float4* e0 = reinterpret_cast<const float4*>(p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co);
+        const float4* e1 = e0 + p.cout / 4;
+        const float4* e2 = e1 + p.cout / 4;
+        const float4* e3 = e2 + p.cout / 4;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 a0 = __ldg(e0 + q), a1 = __ldg(e1 + q), a2 = __ldg(e2 + q), a3 = __ldg(e3 + q);
+            f[q * 4 + 0] += a0.x + ty * a1.x + tx * a2.x + tyx * a3.x;
+            f[q * 4 + 1] += a0.y + ty * a1.y + tx * a2.y + tyx * a3.y;
+            f[q * 4 + 2] += a0.z + ty * a1.z + tx * a2.z + tyx * a3.z;
+            f[q * 4 + 3] += a0.w + ty * a1.w + tx * a2.w + tyx * a3.w;
+        }
+    }
+    if (p.res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coffset + co);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 rv = __ldg(rp + q);
+            const __half2* hv = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 t2 = __half22float2(hv[e]);
+                f[q * 8 + e * 2] += t2.x;
+                f[q * 8 + e * 2 + 1] += t2.y;
+            }
+        }
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+    }
+    if (p.scale2) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(f[i], sc2[lc + i], sh2[lc + i]), 0.0f);
+    }
+    if (p.logits) {  // fused final_conv: the 64-channel activation never goes to memory
+#pragma unroll
+        for (int i = 0; i < 32; ++i) head_acc = fmaf(f[i], __ldg(p.head_w + co + i), head_acc);
+        return;
+    }
+    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_coffset + co);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        uint4 ov;
+        __half2* hv = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = fminf(fmaxf(f[q * 8 + e * 2], -65504.f), 65504.f);
+            const float b = fminf(fmaxf(f[q * 8 + e * 2 + 1], -65504.f), 65504.f);
+            hv[e] = __floats2half2_rn(a, b);
+        }
+        op[q] = ov;
+    }
 }
 
 template <int BLOCK_N, int STAGES>
@@ -270,76 +349,204 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            float head_acc = 0.f;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t v[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), v);
-                if (valid) {
-                    const int col = n_tile * BLOCK_N + c * 32;  // first GEMM column of this chunk
-                    const int g = col / p.cout, co = col - g * p.cout;
-                    int od = d, oh = h, ow = w;
-                    if (p.up == 2) {
-                        if (p.up_d == 2) { od = 2 * d + (g >> 2); oh = 2 * h + ((g >> 1) & 1); ow = 2 * w + (g & 1); }
-                        else { oh = 2 * h + (g >> 1); ow = 2 * w + (g & 1); }
-                    }
-                    const long long pix = (((long long)n * p.oD + od) * p.oH + oh) * p.oW + ow;
-                    float f[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), sc[c * 32 + i], sh[c * 32 + i]);
-                    if (p.poly) {
-                        int kcase = g;
-                        if (p.poly_cases == 9)
-                            kcase = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
-                        const float ty = (float)h * p.inv_h, tx = (float)w * p.inv_w, tyx = ty * tx;
-                        const float4* e0 = reinterpret_cast<const float4*>(p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co);
-                        const float4* e1 = e0 + p.cout / 4;
-                        const float4* e2 = e1 + p.cout / 4;
-                        const float4* e3 = e2 + p.cout / 4;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 a0 = __ldg(e0 + q), a1 = __ldg(e1 + q), a2 = __ldg(e2 + q), a3 = __ldg(e3 + q);
-                            f[q * 4 + 0] += a0.x + ty * a1.x + tx * a2.x + tyx * a3.x;
-                            f[q * 4 + 1] += a0.y + ty * a1.y + tx * a2.y + tyx * a3.y;
-                            f[q * 4 + 2] += a0.z + ty * a1.z + tx * a2.z + tyx * a3.z;
-                            f[q * 4 + 3] += a0.w + ty * a1.w + tx * a2.w + tyx * a3.w;
+                if (valid)
+                    epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sh, sc2, sh2, head_acc);
+            }
+            if (valid && p.logits) p.logits[(((long long)n * p.oD + d) * p.oH + h) * p.oW + w] = head_acc + p.head_b;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// conv_halo_kernel — 2D 3x3 stride-1 layers with <= 128 output channels (layer1, layer2, conv7.2, conv8.x).
+//
+// The per-tap kernel above re-fetches the 128-pixel A tile from L2 for each of the 9 taps; at full resolution with a
+// narrow N that makes the layer L2-bandwidth bound (profiles/conv_layers_r1.md: 20-40 % tensor pipe at 13-17 TB/s of L2
+// reads).  Here a CTA owns a 16x16-pixel output tile = two 16(h) x 8(w) column blocks = M 256 (two M=128 MMAs sharing
+// every B tile), and the activations arrive as SLABS: for input-channel chunk c and horizontal tap dx, an
+// (18 rows x 8 cols) box per column block, shifted by dx.  A slab serves the three vertical taps dy = 0,1,2 by moving
+// the UMMA descriptor's start address down one pixel row (8 pixels x 128 B = 1024 B, so every 8-row swizzle group stays
+// 1024-byte aligned).  L2 -> SMEM traffic per 128 output pixels drops from 9 x 16 KB (A) + 9 x B to 3 x 18 KB + 4.5 x B.
+// Pipelines: A ring (one stage = the two slabs of a (chunk, dx)), B ring (one stage per tap), 2 TMEM accumulator stages
+// of 2 x BLOCK_N columns.  Same warp roles, epilogue and descriptors as conv_gemm_kernel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kSlabBytes = 18 * 8 * 128;  // 18,432: (16 + 2) pixel rows x 8 pixels x 64 channels fp16
+
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+struct HaloLayout {
+    static constexpr uint32_t a_stage = 2 * kSlabBytes;
+    static constexpr uint32_t b_stage = BLOCK_N * 128;
+    static constexpr uint32_t off_b = A_STAGES * a_stage;
+    static constexpr uint32_t off_bar = off_b + B_STAGES * b_stage;
+    static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4) * 8;
+    static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
+    static constexpr uint32_t total = off_ss + 2 * 4 * BLOCK_N * 4 + 1024;
+};
+
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ ConvParams p) {
+    using L = HaloLayout<BLOCK_N, A_STAGES, B_STAGES>;
+    constexpr int TMEM_COLS = 4 * BLOCK_N;  // 2 accumulator stages x 2 column blocks
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = base + L::off_bar;
+    auto afull = [&](int s) { return bar0 + 8u * s; };
+    auto aempty = [&](int s) { return bar0 + 8u * (A_STAGES + s); };
+    auto bfull = [&](int s) { return bar0 + 8u * (2 * A_STAGES + s); };
+    auto bempty = [&](int s) { return bar0 + 8u * (2 * A_STAGES + B_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
+    float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles;  // n_tiles == 1: BLOCK_N covers all output channels
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L::off_tmem),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: same (chunk, dx, dy) order as the MMA issuer consumes =====
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int m = tile;
+                const int tw = m % p.tiles_w; m /= p.tiles_w;
+                const int th = m % p.tiles_h;
+                const int n = m / p.tiles_h;
+                const int w0 = tw * 16, h0 = th * 16;
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(aempty(sa), pa ^ 1u);
+                        mbar_expect_tx(afull(sa), 2 * kSlabBytes);
+                        const uint32_t dst = base + sa * L::a_stage;
+                        tma_load_5d(dst, &map_a, afull(sa), c * kBlockK, w0 - 1 + dx, h0 - 1, 0, n);
+                        tma_load_5d(dst + kSlabBytes, &map_a, afull(sa), c * kBlockK, w0 + 7 + dx, h0 - 1, 0, n);
+                        if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait(bempty(sb), pb ^ 1u);
+                            mbar_expect_tx(bfull(sb), L::b_stage);
+                            tma_load_2d(base + L::off_b + sb * L::b_stage, &map_b, bfull(sb),
+                                        ((dy * 3 + dx) * p.cin_chunks + c) * kBlockK, 0);
+                            if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
                         }
-                    }
-                    if (p.res) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coffset + co);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 rv = __ldg(rp + q);
-                            const __half2* hv = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 t2 = __half22float2(hv[e]);
-                                f[q * 8 + e * 2] += t2.x;
-                                f[q * 8 + e * 2 + 1] += t2.y;
-                            }
-                        }
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-                    }
-                    if (p.scale2) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(f[i], sc2[c * 32 + i], sh2[c * 32 + i]), 0.0f);
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_coffset + co);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint4 ov;
-                        __half2* hv = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float a = fminf(fmaxf(f[q * 8 + e * 2], -65504.f), 65504.f);
-                            const float b = fminf(fmaxf(f[q * 8 + e * 2 + 1], -65504.f), 65504.f);
-                            hv[e] = __floats2half2_rn(a, b);
-                        }
-                        op[q] = ov;
                     }
                 }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_N);
+            int sa = 0, sb = 0, acc = 0;
+            uint32_t pa = 0, pb = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BLOCK_N);
+                uint32_t first = 1;
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(afull(sa), pa);
+                        tc_fence_after();
+                        const uint32_t a_base = base + sa * L::a_stage;
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait(bfull(sb), pb);
+                            tc_fence_after();
+                            const uint64_t bdesc = make_smem_desc(base + L::off_b + sb * L::b_stage);
+#pragma unroll
+                            for (int blk = 0; blk < 2; ++blk) {
+                                // vertical tap dy = start one pixel row (8 px x 128 B) further down the slab
+                                const uint64_t adesc = make_smem_desc(a_base + blk * kSlabBytes + dy * 1024);
+#pragma unroll
+                                for (int kk = 0; kk < kBlockK / 16; ++kk)
+                                    tc_mma_f16(d_tmem + (uint32_t)(blk * BLOCK_N), adesc + (uint64_t)(kk * 2),
+                                               bdesc + (uint64_t)(kk * 2), idesc, (first && kk == 0) ? 0u : 1u);
+                            }
+                            first = 0;
+                            tc_commit(bempty(sb));
+                            if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
+                        }
+                        tc_commit(aempty(sa));
+                        if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+                    }
+                }
+                tc_commit(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 =====
+        const int sub = warp & 3;
+        const int row = sub * 32 + lane;  // row of a column block: (h_l, w_l) = (row / 8, row % 8)
+        const int et = threadIdx.x - 64;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            int m = tile;
+            const int tw = m % p.tiles_w; m /= p.tiles_w;
+            const int th = m % p.tiles_h;
+            const int n = m / p.tiles_h;
+            float* sc = ss + acc * 4 * BLOCK_N;
+            float* sh = sc + BLOCK_N;
+            float* sc2 = sh + BLOCK_N;
+            float* sh2 = sc2 + BLOCK_N;
+            for (int i = et; i < BLOCK_N; i += 128) {
+                sc[i] = __ldg(p.scale + i);
+                sh[i] = __ldg(p.shift + i);
+                if (p.scale2) { sc2[i] = __ldg(p.scale2 + i); sh2[i] = __ldg(p.shift2 + i); }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int h = th * 16 + (row >> 3);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int blk = 0; blk < 2; ++blk) {
+                const int w = tw * 16 + blk * 8 + (row & 7);
+                const bool valid = h < p.H && w < p.W;
+                const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 2 * BLOCK_N + blk * BLOCK_N);
+                float head_acc = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + (uint32_t)(c * 32), v);
+                    if (valid) epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sh, sc2, sh2, head_acc);
+                }
+                if (valid && p.logits) p.logits[((long long)n * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             }
             tc_fence_before();
             __syncwarp();
@@ -385,6 +592,17 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& 
     return NRRT_OK;
 }
 
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
+    using L = HaloLayout<BLOCK_N, A_STAGES, B_STAGES>;
+    auto kern = conv_halo_kernel<BLOCK_N, A_STAGES, B_STAGES>;
+    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    const int grid = p.m_tiles < sms ? p.m_tiles : sms;
+    kern<<<grid, kThreads, L::total, st>>>(ma, mb, p);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
 void pick_box(int W, int H, int D, int& bw, int& bh, int& bd) {
     // Largest box of <= 128 pixels that tiles the grid with the least waste (dims need not be powers of two).
     double best = -1;
@@ -405,7 +623,7 @@ void pick_box(int W, int H, int D, int& bw, int& bh, int& bd) {
 }  // namespace
 
 extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
-    NRRT_REQUIRE(l && l->in && l->weight && l->scale && l->shift && l->out, "null pointer in conv layer");
+    NRRT_REQUIRE(l && l->in && l->weight && l->scale && l->shift, "null pointer in conv layer");
     NRRT_REQUIRE(l->dims == 2 || l->dims == 3, "dims must be 2 or 3");
     NRRT_REQUIRE(l->kind >= 0 && l->kind <= 4, "unknown conv kind %d", l->kind);
     NRRT_REQUIRE(l->cin > 0 && l->cin % 64 == 0, "Cin must be a multiple of 64 (got %d)", l->cin);
@@ -473,6 +691,19 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     }
     p.a_bytes = (uint32_t)p.rows * 128u;
     p.b_bytes = (uint32_t)block_n * 128u;
+    p.head_w = l->head_weight; p.head_b = l->head_bias; p.logits = l->logits;
+    if (l->logits) {
+        NRRT_REQUIRE(l->head_weight && p.n_tiles == 1 && up == 1, "fused head needs head_weight and all output channels in one N tile");
+    } else {
+        NRRT_REQUIRE(l->out, "null output pointer");
+    }
+    // 2D 3x3 stride-1 layers with a narrow N are L2-bound in the per-tap kernel: use the slab (halo-reuse) kernel
+    const bool halo = !three_d && l->kind == NRRT_CONV_K3S1 && p.n_tiles == 1 && block_n <= 128 && !l->force_per_tap;
+    if (halo) {
+        p.bw = 16; p.bh = 16; p.bd = 1; p.rows = 256;
+        p.tiles_w = (p.W + 15) / 16; p.tiles_h = (p.H + 15) / 16; p.tiles_d = 1;
+        p.m_tiles = p.tiles_w * p.tiles_h * N;
+    }
 
     // activation map: dims (C, W, H, D, N) over the caller's NDHWC buffer (channel slice of in_cstride-wide rows)
     CUtensorMap ma, mb;
@@ -480,7 +711,8 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         const cuuint64_t gdim[5] = {(cuuint64_t)l->cin, (cuuint64_t)iW, (cuuint64_t)iH, (cuuint64_t)iD, (cuuint64_t)N};
         const cuuint64_t cs = (cuuint64_t)l->in_cstride * 2;
         const cuuint64_t gstr[4] = {cs, cs * iW, cs * iW * iH, cs * iW * iH * iD};
-        const cuuint32_t box[5] = {64, (cuuint32_t)(p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)(p.bd * p.stride_d), 1};
+        cuuint32_t box[5] = {64, (cuuint32_t)(p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)(p.bd * p.stride_d), 1};
+        if (halo) { box[1] = 8; box[2] = 18; box[3] = 1; }  // one slab: 18 pixel rows x 8 pixels
         const cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)p.stride_d, 1};
         const CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(l->in), gdim, gstr, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -501,6 +733,10 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     int dev = 0, sms = 0;
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (halo) {
+        if (block_n == 128) return launch_halo<128, 4, 4>(ma, mb, p, sms, st);
+        return launch_halo<64, 4, 8>(ma, mb, p, sms, st);
+    }
     if (block_n == 256) return launch_conv<256, 4>(ma, mb, p, sms, st);
     if (block_n == 128) return launch_conv<128, 6>(ma, mb, p, sms, st);
     return launch_conv<64, 8>(ma, mb, p, sms, st);

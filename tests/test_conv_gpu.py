@@ -88,7 +88,10 @@ CASES = [
     # dims, kind, B, cin, cout, spatial
     (2, cnn.K1S1, 2, 64, 64, (16, 16)),      # plain GEMM, one K stage
     (2, cnn.K1S1, 1, 256, 128, (24, 40)),    # 4 K stages, N = 128, ragged tiles
-    (2, cnn.K3S1, 2, 64, 64, (16, 16)),
+    (2, cnn.K3S1, 2, 64, 64, (16, 16)),      # slab kernel (N <= 128), exact 16x16 tiles
+    (2, cnn.K3S1, 2, 64, 64, (24, 40)),      # slab kernel, ragged tiles
+    (2, cnn.K3S1, 1, 128, 128, (16, 48)),    # slab kernel, two K chunks, N = 128
+    (2, cnn.K3S1, 1, 192, 128, (40, 24)),    # slab kernel, three K chunks
     (2, cnn.K3S1, 1, 128, 256, (40, 24)),
     (2, cnn.K3S1, 1, 192, 512, (16, 32)),    # two N tiles of 256
     (2, cnn.K3S2, 2, 64, 128, (32, 32)),
@@ -131,6 +134,32 @@ def test_conv_layer_residual_slices_and_post_affine(cuda_device):
                      post=post)
     _check(out, _ref(2, cnn.K3S1, x, w, scale, shift, True, res, post), 2, 128, off=32)
     assert (out[..., :32] == 7.0).all() and (out[..., 160:] == 7.0).all()  # neighbours of the slice untouched
+
+
+def test_slab_kernel_equals_per_tap_kernel_and_fused_head(cuda_device):
+    """The slab (halo-reuse) kernel and the generic per-tap kernel run the same MMAs in a different order of K: equal
+    up to fp32 accumulation order; the fused 1x1 head equals a separate dot product over the stored activation."""
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn((2, 128, 40, 56), generator=g).to(dev)
+    w = (torch.randn((64, 128, 3, 3), generator=g) / 34).to(dev)
+    scale, shift = (torch.rand(64, generator=g) + 0.5).to(dev), torch.randn(64, generator=g).to(dev)
+    a = _run_layer(2, cnn.K3S1, x, w, scale, shift, True, dev)
+    cnn._Layer.force_per_tap = True
+    try:
+        b = _run_layer(2, cnn.K3S1, x, w, scale, shift, True, dev)
+    finally:
+        cnn._Layer.force_per_tap = False
+    assert (a.float() - b.float()).abs().max().item() <= 4e-3
+    _check(a, _ref(2, cnn.K3S1, x, w, scale, shift, True), 2, 64)
+    # fused head
+    hw = torch.randn(64, generator=g).to(dev)
+    layer = cnn._Layer(2, cnn.K3S1, 128, 64, cnn._pack_conv_weight(w, 128, dev), scale.contiguous(), shift.contiguous(), True)
+    logits = torch.zeros((2, 40, 56), dtype=torch.float32, device=dev)
+    layer.run(_lib.load(), None, _cl(x), 0, (1, 40, 56), None, 0, head=(hw, 0.25, logits))
+    torch.cuda.synchronize()
+    ref = (_ref(2, cnn.K3S1, x, w, scale, shift, True) * hw.view(1, -1, 1, 1)).sum(1) + 0.25
+    assert (logits - ref).abs().max().item() <= 2e-3 * max(ref.abs().max().item(), 1.0)
 
 
 @pytest.mark.parametrize("three_d", [False, True])
