@@ -11,8 +11,8 @@
 //       no im2col buffer and no padded copies exist anywhere; stride-2 layers use the tensor map's element strides.
 //   N = BLOCK_N output channels (64/128/256) = one tcgen05.mma instruction wide.
 //   K = 64 input channels per pipeline stage (one 128-byte swizzle row), taps x Cin/64 stages per tile.
-// Warp roles (192 threads, persistent CTAs, static tile schedule): warp 0 TMA producer, warp 1 MMA issuer,
-// warps 2-5 epilogue (TMEM -> registers -> scale/shift/residual/ReLU -> fp16 NDHWC stores, 16-byte vectors).
+// Warp roles (320 threads, persistent CTAs, static tile schedule): warp 0 TMA producer, warp 1 MMA issuer,
+// warps 2-9 epilogue, two per TMEM lane quarter (TMEM -> registers -> scale/shift/residual/ReLU -> fp16 NDHWC stores).
 // Two accumulator stages in TMEM (2 x BLOCK_N columns) overlap the epilogue of tile i with the MMAs of tile i+1.
 // ConvTranspose(k=2,s=2) is the same GEMM with 4 (2D) / 8 (3D) weight groups stacked along N and a pixel-shuffle store.
 #include <cuda.h>
@@ -26,7 +26,8 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = 128 bytes = one SWIZZLE_128B row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;                  // two warps per TMEM lane quarter
+constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int kMaxTaps = 27;
 
 struct ConvParams {
@@ -71,16 +72,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
+// A macro (not a function) so that profiler samples land on the call site's source line.
+#define mbar_wait(bar, parity)                                                            \
+    asm volatile(                                                                         \
+        "{\n\t.reg .pred p;\n\t"                                                         \
+        "WAIT_LOOP:\n\t"                                                                  \
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"                       \
+        "@p bra WAIT_DONE;\n\t"                                                           \
+        "bra WAIT_LOOP;\n\t"                                                              \
+        "WAIT_DONE:\n\t}" ::"r"((uint32_t)(bar)), "r"((uint32_t)(parity))                 \
+        : "memory")
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
     asm volatile(
@@ -143,7 +144,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 // running dot product with the head weights.  col = first GEMM column, lc = its offset inside the staged scale/shift.
 __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[32], int col, int lc, int n, int d,
                                                int h, int w, const float* sc, const float* sh, const float* sc2,
-                                               const float* sh2, float& head_acc) {
+                                               const float* sh2, const float* pe, int pe_stride, float& head_acc) {
     const int g = col / p.cout, co = col - g * p.cout;
     int od = d, oh = h, ow = w;
     if (p.up == 2) {
@@ -159,13 +160,18 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
         if (p.poly_cases == 9)
             kcase = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
         const float ty = (float)h * p.inv_h, tx = (float)w * p.inv_w, tyx = ty * tx;
-        const float4* e0 = reinterpret_cast<const float4*>(p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co);
-        const float4* e1 = e0 + p.cout / 4;
-        const float4* e2 = e1 + p.cout / 4;
-        const float4* e3 = e2 + p.cout / 4;
+        // interior pixels (and ConvTranspose groups) read the tile's coefficients staged in shared memory; only the
+        // one-pixel image frame, whose tap set differs, goes to global memory
+        const bool staged = p.poly_cases != 9 || kcase == 4;
+        const float4* e0 = staged ? reinterpret_cast<const float4*>(pe + lc)
+                                  : reinterpret_cast<const float4*>(p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co);
+        const int es = staged ? pe_stride / 4 : p.cout / 4;
+        const float4* e1 = e0 + es;
+        const float4* e2 = e1 + es;
+        const float4* e3 = e2 + es;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-            const float4 a0 = __ldg(e0 + q), a1 = __ldg(e1 + q), a2 = __ldg(e2 + q), a3 = __ldg(e3 + q);
+            const float4 a0 = e0[q], a1 = e1[q], a2 = e2[q], a3 = e3[q];
             f[q * 4 + 0] += a0.x + ty * a1.x + tx * a2.x + tyx * a3.x;
             f[q * 4 + 1] += a0.y + ty * a1.y + tx * a2.y + tyx * a3.y;
             f[q * 4 + 2] += a0.z + ty * a1.z + tx * a2.z + tyx * a3.z;
@@ -214,6 +220,34 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
     }
 }
 
+// Per-tile staging by the 256 epilogue threads: scale/shift (+ second affine) and the tile's polynomial coefficients.
+template <int BLOCK_N>
+__device__ __forceinline__ void stage_tile_params(const ConvParams& p, float* dst, int col0, int n, int et, bool affine,
+                                                  bool poly) {
+    if (!affine && !(poly && p.poly)) return;  // nothing changed since this buffer was last filled (uniform per CTA)
+    // every epilogue warp must be done reading the old contents (barriers are skipped on tiles that restage nothing)
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    if (affine)
+    for (int i = et; i < BLOCK_N; i += 32 * kEpiWarps) {
+        dst[i] = __ldg(p.scale + col0 + i);
+        dst[BLOCK_N + i] = __ldg(p.shift + col0 + i);
+        if (p.scale2) {
+            dst[2 * BLOCK_N + i] = __ldg(p.scale2 + col0 + i);
+            dst[3 * BLOCK_N + i] = __ldg(p.shift2 + col0 + i);
+        }
+    }
+    if (p.poly && poly) {
+        const int g = col0 / p.cout, co0 = col0 - g * p.cout;
+        const int kcase = p.poly_cases == 9 ? 4 : g;
+        const float* src = p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co0;
+        for (int i = et; i < 4 * BLOCK_N; i += 32 * kEpiWarps) {
+            const int e = i / BLOCK_N, c = i - e * BLOCK_N;
+            if (co0 + c < p.cout) dst[(4 + e) * BLOCK_N + c] = __ldg(src + (size_t)e * p.cout + c);
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+}
+
 template <int BLOCK_N, int STAGES>
 struct SmemLayout {
     static constexpr uint32_t a_stage = kBlockM * 128;
@@ -221,8 +255,8 @@ struct SmemLayout {
     static constexpr uint32_t off_b = STAGES * a_stage;
     static constexpr uint32_t off_bar = off_b + STAGES * b_stage;
     static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4) * 8;
-    static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;         // scale/shift [2 acc stages][4][BLOCK_N] floats
-    static constexpr uint32_t total = off_ss + 2 * 4 * BLOCK_N * 4 + 1024;  // + slack for manual 1024-B alignment
+    static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;         // [2 acc stages][scale, shift, scale2, shift2, E0..E3][BLOCK_N] floats
+    static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;  // + slack for manual 1024-B alignment
 };
 
 template <int BLOCK_N, int STAGES>
@@ -248,7 +282,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -314,12 +348,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 =====
+        // ===== epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; the two warps of a quarter split the column chunks =====
         const int sub = warp & 3;
+        const int part = (warp - 2) >> 2;
         const int row = sub * 32 + lane;
-        const int et = threadIdx.x - 64;  // 0..127
+        const int et = threadIdx.x - 64;  // 0..255
         int acc = 0;
         uint32_t acc_phase = 0;
+        int last_ntile[2] = {-1, -1}, last_n[2] = {-1, -1};
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int n_tile = tile % p.n_tiles;
             int m = tile / p.n_tiles;
@@ -327,20 +363,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int th = m % p.tiles_h; m /= p.tiles_h;
             const int td = m % p.tiles_d;
             const int n = m / p.tiles_d;
-            // per-tile scale/shift staging (double-buffered by accumulator stage)
-            float* sc = ss + acc * 4 * BLOCK_N;
-            float* sh = sc + BLOCK_N;
-            float* sc2 = sh + BLOCK_N;
-            float* sh2 = sc2 + BLOCK_N;
-            for (int i = et; i < BLOCK_N; i += 128) {
-                sc[i] = __ldg(p.scale + n_tile * BLOCK_N + i);
-                sh[i] = __ldg(p.shift + n_tile * BLOCK_N + i);
-                if (p.scale2) {
-                    sc2[i] = __ldg(p.scale2 + n_tile * BLOCK_N + i);
-                    sh2[i] = __ldg(p.shift2 + n_tile * BLOCK_N + i);
-                }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float* sc = ss + acc * 8 * BLOCK_N;  // double-buffered by accumulator stage
+            stage_tile_params<BLOCK_N>(p, sc, n_tile * BLOCK_N, n, et, last_ntile[acc] != n_tile,
+                                       last_ntile[acc] != n_tile || last_n[acc] != n);
+            last_ntile[acc] = n_tile; last_n[acc] = n;
 
             const int wl = row % p.bw, hl = (row / p.bw) % p.bh, dl = row / (p.bw * p.bh);
             const int w = tw * p.bw + wl, h = th * p.bh + hl, d = td * p.bd + dl;
@@ -350,14 +376,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             float head_acc = 0.f;
+            // fused head: one warp per quarter walks all chunks (the dot product runs over all channels of a pixel)
+            const int c_begin = p.logits ? 0 : part, c_step = p.logits ? 1 : 2;
+            if (!(p.logits && part == 1)) {
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                uint32_t v[32];
-                tc_ld32(taddr + (uint32_t)(c * 32), v);
-                if (valid)
-                    epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sh, sc2, sh2, head_acc);
+                for (int c = c_begin; c < BLOCK_N / 32; c += c_step) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + (uint32_t)(c * 32), v);
+                    if (valid)
+                        epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
+                                       sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc);
+                }
+                if (valid && p.logits) p.logits[(((long long)n * p.oD + d) * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             }
-            if (valid && p.logits) p.logits[(((long long)n * p.oD + d) * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -396,7 +427,7 @@ struct HaloLayout {
     static constexpr uint32_t off_bar = off_b + B_STAGES * b_stage;
     static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4) * 8;
     static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
-    static constexpr uint32_t total = off_ss + 2 * 4 * BLOCK_N * 4 + 1024;
+    static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
 };
 
 template <int BLOCK_N, int A_STAGES, int B_STAGES>
@@ -424,7 +455,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -510,44 +541,38 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
         }
     } else {
-        // ===== epilogue warps 2..5 =====
+        // ===== epilogue warps 2..9: warps 2-5 take column block 0, warps 6-9 column block 1 =====
         const int sub = warp & 3;
+        const int blk = (warp - 2) >> 2;
         const int row = sub * 32 + lane;  // row of a column block: (h_l, w_l) = (row / 8, row % 8)
         const int et = threadIdx.x - 64;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int last_n[2] = {-1, -1};
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int m = tile;
             const int tw = m % p.tiles_w; m /= p.tiles_w;
             const int th = m % p.tiles_h;
             const int n = m / p.tiles_h;
-            float* sc = ss + acc * 4 * BLOCK_N;
-            float* sh = sc + BLOCK_N;
-            float* sc2 = sh + BLOCK_N;
-            float* sh2 = sc2 + BLOCK_N;
-            for (int i = et; i < BLOCK_N; i += 128) {
-                sc[i] = __ldg(p.scale + i);
-                sh[i] = __ldg(p.shift + i);
-                if (p.scale2) { sc2[i] = __ldg(p.scale2 + i); sh2[i] = __ldg(p.shift2 + i); }
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            float* sc = ss + acc * 8 * BLOCK_N;
+            stage_tile_params<BLOCK_N>(p, sc, 0, n, et, last_n[acc] < 0, last_n[acc] != n);
+            last_n[acc] = n;
             const int h = th * 16 + (row >> 3);
+            const int w = tw * 16 + blk * 8 + (row & 7);
+            const bool valid = h < p.H && w < p.W;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 2 * BLOCK_N + blk * BLOCK_N);
+            float head_acc = 0.f;
 #pragma unroll 1
-            for (int blk = 0; blk < 2; ++blk) {
-                const int w = tw * 16 + blk * 8 + (row & 7);
-                const bool valid = h < p.H && w < p.W;
-                const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 2 * BLOCK_N + blk * BLOCK_N);
-                float head_acc = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    uint32_t v[32];
-                    tc_ld32(taddr + (uint32_t)(c * 32), v);
-                    if (valid) epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sh, sc2, sh2, head_acc);
-                }
-                if (valid && p.logits) p.logits[((long long)n * p.oH + h) * p.oW + w] = head_acc + p.head_b;
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tc_ld32(taddr + (uint32_t)(c * 32), v);
+                if (valid)
+                    epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
+                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc);
             }
+            if (valid && p.logits) p.logits[((long long)n * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));
