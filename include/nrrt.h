@@ -170,6 +170,16 @@ typedef struct NrrtConvLayer {
     float head_bias;
     float* logits;           /* fp32 [n][pixels] */
     int32_t force_per_tap;   /* testing: use the generic per-tap kernel even where the slab kernel applies */
+    /* Optional second input (K split): the layer's input channels are [in: cin channels | in2: cin2 channels], the
+     * torch.cat of the reference (train.py:194,197,200) without a concatenated buffer.  in_index / in2_index (int32 [n],
+     * optional) redirect sample b of a source to another row of its buffer: decoder layers read the encoder output of
+     * map index[b], which exists once per map, not once per task.  in_n / in2_n = samples in those buffers (0 = n). */
+    const void* in2;
+    int64_t in2_cstride;
+    int32_t cin2;
+    int32_t in_n, in2_n;
+    const int32_t* in_index;
+    const int32_t* in2_index;
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);

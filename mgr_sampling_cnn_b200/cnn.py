@@ -99,6 +99,7 @@ class _Layer(object):
         self.dims, self.kind, self.cin, self.cout = dims, kind, cin, cout
         self.weight, self.scale, self.shift, self.relu = weight, scale, shift, relu
         self.post = post
+        self.cin2 = 0  # channels read from the second input (K split)
         self.cin_real = cin_real or cin
         self.profiler = None
 
@@ -113,22 +114,34 @@ class _Layer(object):
 
     force_per_tap = False  # tests: run the generic per-tap kernel where the slab kernel would be chosen
 
-    def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None, head=None):
+    def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None, head=None, x2=None,
+            idx=None, idx2=None, n=None):
         """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W).
-        head = (weight fp32 [cout], bias float, logits fp32 tensor): fuse the 1x1 output head, `out` may be None."""
+        head = (weight fp32 [cout], bias float, logits fp32 tensor): fuse the 1x1 output head, `out` may be None.
+        x2: optional second input buffer (K split: channels [x: self.cin | x2: self.cin2]); idx / idx2: optional int32
+        [n] sample indirection of x / x2 (encoder outputs shared per map); n = number of output samples."""
+        n = n if n is not None else (idx.shape[0] if idx is not None else x.shape[0])
+        args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n)
         prof = self.profiler
         if prof is not None and prof.active:
-            with prof.launch(self.flops(x.shape[0], grid)):
-                self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head)
+            with prof.launch(self.flops(n, grid)):
+                self._run(*args)
         else:
-            self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head)
+            self._run(*args)
 
-    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly=None, head=None):
+    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n):
         _lib.count_launch()
         L = _lib.NrrtConvLayer()
         L.dims, L.kind = self.dims, self.kind
-        L.n, L.in_d, L.in_h, L.in_w = x.shape[0], grid[0], grid[1], grid[2]
+        L.n, L.in_d, L.in_h, L.in_w = n, grid[0], grid[1], grid[2]
         L.cin, L.cout = self.cin, self.cout
+        L.in_n = x.shape[0]
+        if idx is not None:
+            L.in_index = _ptr(idx)
+        if x2 is not None:
+            L.in2, L.in2_cstride, L.cin2, L.in2_n = _ptr(x2), x2.shape[-1], self.cin2, x2.shape[0]
+            if idx2 is not None:
+                L.in2_index = _ptr(idx2)
         esz = 2
         L.in_ = C.c_void_p(x.data_ptr() + x_coff * esz)
         L.in_cstride = x.shape[-1]
@@ -221,11 +234,18 @@ class UNetPlan(object):
         # coordinate grid is only piecewise bilinear).
         self.poly = d == 2
 
-        def conv_sliced(m, keep):
-            """3x3 conv that reads only the first `keep` input channels (the rest are coordinate channels)."""
+        def conv_split(m, c_up, c_enc, c_coords_in_gemm):
+            """3x3 decoder conv over torch.cat((up, enc, coords)): source 1 = the task's buffer [up | coords (3D only)],
+            source 2 = the encoder output of the task's map.  Input channels are permuted accordingly."""
+            w = m.weight
+            up, enc, crd = w[:, :c_up], w[:, c_up:c_up + c_enc], w[:, c_up + c_enc:]
+            parts = [up] + ([crd] if c_coords_in_gemm else []) + [enc]
+            wp = torch.cat(parts, dim=1)
             scale, shift = _fold_bn(None, m.bias, m.out_channels, dev)
-            return _Layer(d, K3S1, keep, m.out_channels, _pack_conv_weight(m.weight[:, :keep], keep, dev), scale, shift, True,
-                          cin_real=keep)
+            lay = _Layer(d, K3S1, wp.shape[1] - c_enc, m.out_channels, _pack_conv_weight(wp, wp.shape[1], dev), scale, shift,
+                         True, cin_real=wp.shape[1])
+            lay.cin2 = c_enc
+            return lay
 
         def conv_moments(m, keep):
             """Tap moments of the coordinate slice: [9 border cases][uv = 00,10,01,11][Cc][Cout] fp32."""
@@ -242,23 +262,24 @@ class UNetPlan(object):
                         out[ry * 3 + rx, uv] = (sub * wgt).sum(dim=(2, 3)).t()
             return out.contiguous()
 
+        mu = model.upconv6
+        groups = 2 ** d
+        scale = torch.ones(groups * mu.out_channels, dtype=torch.float32, device=dev)
+        shift = mu.bias.detach().float().to(dev).repeat(groups).contiguous()
         if self.poly:
-            mu = model.upconv6
-            scale = torch.ones(4 * mu.out_channels, dtype=torch.float32, device=dev)
-            shift = mu.bias.detach().float().to(dev).repeat(4).contiguous()
+            # upconv6 reads the encoder output x5 only; its coordinate rows become the polynomial moments
             self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(mu.weight[:512], dev), scale, shift, False)
-            # ConvTranspose groups g = a*2+b: moments [4][1][Cc][Cout] = the coordinate rows of the weight
             self.m_up6 = mu.weight.detach().float().to(dev)[512:].permute(2, 3, 0, 1).reshape(4, 1, 512, mu.out_channels).contiguous()
-            self.up7, self.up8 = convT(model.upconv7), convT(model.upconv8)
-            self.c6 = (conv_sliced(model.conv6[0], 768), conv(model.conv6[2], K3S1))
-            self.c7 = (conv_sliced(model.conv7[0], 256), conv(model.conv7[2], K3S1))
-            self.c8 = (conv_sliced(model.conv8[0], 128), conv(model.conv8[2], K3S1))
             self.m_c6, self.m_c7, self.m_c8 = conv_moments(model.conv6[0], 768), conv_moments(model.conv7[0], 256), conv_moments(model.conv8[0], 128)
         else:
-            self.up6, self.up7, self.up8 = convT(model.upconv6), convT(model.upconv7), convT(model.upconv8)
-            self.c6 = (conv(model.conv6[0], K3S1), conv(model.conv6[2], K3S1))
-            self.c7 = (conv(model.conv7[0], K3S1), conv(model.conv7[2], K3S1))
-            self.c8 = (conv(model.conv8[0], K3S1), conv(model.conv8[2], K3S1))
+            # source 1 = x5 (per map), source 2 = the interpolated coordinate channels (per task)
+            self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(mu.weight, dev), scale, shift, False)
+            self.up6.cin2 = 512
+            self.up6.cin_real = 1024
+        self.up7, self.up8 = convT(model.upconv7), convT(model.upconv8)
+        self.c6 = (conv_split(model.conv6[0], 512, 256, not self.poly), conv(model.conv6[2], K3S1))
+        self.c7 = (conv_split(model.conv7[0], 128, 128, not self.poly), conv(model.conv7[2], K3S1))
+        self.c8 = (conv_split(model.conv8[0], 64, 64, not self.poly), conv(model.conv8[2], K3S1))
         self.head_w = model.final_conv.weight.detach().float().to(dev).reshape(-1).contiguous()
         self.head_b = float(model.final_conv.bias.detach().float().item())
         self._bufs = {}
@@ -277,19 +298,20 @@ class UNetPlan(object):
                 shape = (n, D // s if self.dims == 3 else 1, H // s, W // s, ch)
                 return torch.empty(shape, dtype=torch.float16, device=dev)
 
-            c8w, c7w, c6w, x5w = (128, 256, 768, 512) if self.poly else (192, 384, 1024, 1024)
+            # task-side decoder inputs: the ConvTranspose output, followed (3D) by the interpolated coordinate channels
+            t8w, t7w, t6w = (64, 128, 512) if self.poly else (128, 256, 768)
             bufs = {
                 "t0": buf(Be, 0, 64), "x1": buf(Be, 0, 64), "a0": buf(Be, 0, 64), "b0": buf(Be, 0, 64),
                 "a1": buf(Be, 1, 128), "b1": buf(Be, 1, 128), "d1": buf(Be, 1, 128),
                 "a2": buf(Be, 2, 256), "b2": buf(Be, 2, 256), "d2": buf(Be, 2, 256),
                 "a3": buf(Be, 3, 512), "b3": buf(Be, 3, 512), "d3": buf(Be, 3, 512),
-                "cat8": buf(B, 0, c8w), "j": buf(B, 0, 128),
-                "cat7": buf(B, 1, c7w), "g7": buf(B, 1, 256), "i": buf(B, 1, 128),
-                "cat6": buf(B, 2, c6w), "g6": buf(B, 2, 512), "h": buf(B, 2, 256),
-                "x5": buf(B, 3, x5w),
+                "e2": buf(Be, 0, 64), "e3": buf(Be, 1, 128), "e4": buf(Be, 2, 256), "e5": buf(Be, 3, 512),
+                "t8": buf(B, 0, t8w), "j": buf(B, 0, 128),
+                "t7": buf(B, 1, t7w), "g7": buf(B, 1, 256), "i": buf(B, 1, 128),
+                "t6": buf(B, 2, t6w), "g6": buf(B, 2, 512), "h": buf(B, 2, 256),
             }
-            if shared_encoder:  # per-map encoder outputs, gathered into every task's concat slices afterwards
-                bufs.update({"e2": buf(Be, 0, 64), "e3": buf(Be, 1, 128), "e4": buf(Be, 2, 256), "e5": buf(Be, 3, 512)})
+            if not self.poly:
+                bufs["c5"] = buf(B, 3, 512)  # interpolated coordinate channels at the bottleneck (second input of upconv6)
             if len(self._bufs) >= 2:  # keep two configurations resident (full and ragged last micro-batch)
                 self._bufs.pop(next(iter(self._bufs)))
             self._bufs[key] = bufs
@@ -418,40 +440,36 @@ class UNetPlan(object):
             c3.run(lib, st, b, 0, gout, a, 0)
             c4.run(lib, st, a, 0, gout, final, final_off, b, 0)
 
-        # where each encoder stage's output lives: its slice of the task's concat buffer, or (shared encoder) a per-map buffer
-        cat_slots = [(bf["cat8"], 64), (bf["cat7"], 128), (bf["cat6"], 512), (bf["x5"], 0)]
-        fin = [(bf["e2"], 0), (bf["e3"], 0), (bf["e4"], 0), (bf["e5"], 0)] if shared else cat_slots
-        stage(self.enc[0], bf["x1"], 0, g[0], g[0], bf["a0"], bf["b0"], None, fin[0][0], fin[0][1])
-        stage(self.enc[1], fin[0][0], fin[0][1], g[0], g[1], bf["a1"], bf["b1"], bf["d1"], fin[1][0], fin[1][1])
-        stage(self.enc[2], fin[1][0], fin[1][1], g[1], g[2], bf["a2"], bf["b2"], bf["d2"], fin[2][0], fin[2][1])
-        stage(self.enc[3], fin[2][0], fin[2][1], g[2], g[3], bf["a3"], bf["b3"], bf["d3"], fin[3][0], fin[3][1])
-        if shared:
-            for (src, _), (dst, off), ch, lv in zip(fin, cat_slots, (64, 128, 256, 512), range(4)):
-                _lib.count_launch()
-                check(lib.nrrt_gather_channels(_ptr(src), src.shape[-1], 0, _ptr(dst), dst.shape[-1], off, ch,
-                                               _prod(g[lv]), _ptr(enc_index), B, st))
+        # encoder outputs live once per encoder sample (= per distinct map when the encoder is shared)
+        stage(self.enc[0], bf["x1"], 0, g[0], g[0], bf["a0"], bf["b0"], None, bf["e2"], 0)
+        stage(self.enc[1], bf["e2"], 0, g[0], g[1], bf["a1"], bf["b1"], bf["d1"], bf["e3"], 0)
+        stage(self.enc[2], bf["e3"], 0, g[1], g[2], bf["a2"], bf["b2"], bf["d2"], bf["e4"], 0)
+        stage(self.enc[3], bf["e4"], 0, g[2], g[3], bf["a3"], bf["b3"], bf["d3"], bf["e5"], 0)
 
         # coordinate branch (train.py:179-190)
         if prep is None:
             prep = self.coords_prepare(coords, grid)
-        if not self.poly:  # materialise the interpolated channels into the concat slices
+        if not self.poly:  # 3D: materialise the interpolated channels next to the ConvTranspose outputs
             gh, gw = coords.shape[2], coords.shape[3]
-            for feat, ch, name, off, lv in ((0, 64, "cat8", 128, 0), (1, 128, "cat7", 256, 1), (2, 256, "cat6", 768, 2),
-                                            (3, 512, "x5", 512, 3)):
+            for feat, ch, name, off, lv in ((0, 64, "t8", 64, 0), (1, 128, "t7", 128, 1), (2, 256, "t6", 512, 2), (3, 512, "c5", 0, 3)):
                 t = bf[name]
                 _lib.count_launch()
                 check(lib.nrrt_coords_fill(_ptr(prep["feats"][feat]), B, gh, gw, ch, dims, g[lv][0], g[lv][1], g[lv][2], _ptr(t),
                                            t.shape[-1], off, st))
 
-        # decoder
-        self.up6.run(lib, st, bf["x5"], 0, g[3], bf["cat6"], 0, poly=prep.get("e_up6"))
-        self.c6[0].run(lib, st, bf["cat6"], 0, g[2], bf["g6"], 0, poly=prep.get("e_c6"))
+        # decoder: every torch.cat of the reference is a K split over (task buffer, encoder output of the task's map)
+        ei = enc_index  # None = one encoder sample per task
+        if self.poly:
+            self.up6.run(lib, st, bf["e5"], 0, g[3], bf["t6"], 0, poly=prep.get("e_up6"), idx=ei, n=B)
+        else:
+            self.up6.run(lib, st, bf["e5"], 0, g[3], bf["t6"], 0, x2=bf["c5"], idx=ei, n=B)
+        self.c6[0].run(lib, st, bf["t6"], 0, g[2], bf["g6"], 0, poly=prep.get("e_c6"), x2=bf["e4"], idx2=ei)
         self.c6[1].run(lib, st, bf["g6"], 0, g[2], bf["h"], 0)
-        self.up7.run(lib, st, bf["h"], 0, g[2], bf["cat7"], 0)
-        self.c7[0].run(lib, st, bf["cat7"], 0, g[1], bf["g7"], 0, poly=prep.get("e_c7"))
+        self.up7.run(lib, st, bf["h"], 0, g[2], bf["t7"], 0)
+        self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, poly=prep.get("e_c7"), x2=bf["e3"], idx2=ei)
         self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
-        self.up8.run(lib, st, bf["i"], 0, g[1], bf["cat8"], 0)
-        self.c8[0].run(lib, st, bf["cat8"], 0, g[0], bf["j"], 0, poly=prep.get("e_c8"))
+        self.up8.run(lib, st, bf["i"], 0, g[1], bf["t8"], 0)
+        self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, poly=prep.get("e_c8"), x2=bf["e2"], idx2=ei)
 
         # conv8.2 + final_conv fused: the 64-channel activation is reduced to the logit in the epilogue
         logits = logits_out

@@ -37,6 +37,9 @@ struct ConvParams {
     int stride;               // input coordinate = tile coordinate * stride + tap offset
     int stride_d;             // same for the depth axis (1 in 2D)
     int ntaps, cin_chunks, n_tiles;
+    int split_chunk;          // K chunks [0, split) come from tensor map A, [split, cin_chunks) from tensor map A2
+    const int32_t* idx1;      // optional sample indirection of source 1 / source 2 (encoder outputs shared per map)
+    const int32_t* idx2;
     int8_t tap[kMaxTaps][4];  // (dx, dy, dz) including -pad
     // epilogue
     __half* out;
@@ -261,8 +264,8 @@ struct SmemLayout {
 
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ ConvParams p) {
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ ConvParams p) {
     using L = SmemLayout<BLOCK_N, STAGES>;
     constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
@@ -309,12 +312,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int td = m % p.tiles_d;
                 const int n = m / p.tiles_d;
                 const int w0 = tw * p.bw * p.stride, h0 = th * p.bh * p.stride, d0 = td * p.bd * p.stride_d;
+                const int n1 = p.idx1 ? __ldg(p.idx1 + n) : n, n2 = p.idx2 ? __ldg(p.idx2 + n) : n;
                 for (int t = 0; t < p.ntaps; ++t) {
                     const int cw = w0 + p.tap[t][0], ch = h0 + p.tap[t][1], cd = d0 + p.tap[t][2];
                     for (int c = 0; c < p.cin_chunks; ++c) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         mbar_expect_tx(full_bar(stage), p.a_bytes + p.b_bytes);
-                        tma_load_5d(base + stage * L::a_stage, &map_a, full_bar(stage), c * kBlockK, cw, ch, cd, n);
+                        if (c < p.split_chunk)
+                            tma_load_5d(base + stage * L::a_stage, &map_a, full_bar(stage), c * kBlockK, cw, ch, cd, n1);
+                        else
+                            tma_load_5d(base + stage * L::a_stage, &map_a2, full_bar(stage), (c - p.split_chunk) * kBlockK, cw, ch, cd, n2);
                         tma_load_2d(base + L::off_b + stage * L::b_stage, &map_b, full_bar(stage),
                                     (t * p.cin_chunks + c) * kBlockK, n_tile * BLOCK_N);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -432,8 +439,8 @@ struct HaloLayout {
 
 template <int BLOCK_N, int A_STAGES, int B_STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ ConvParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ ConvParams p) {
     using L = HaloLayout<BLOCK_N, A_STAGES, B_STAGES>;
     constexpr int TMEM_COLS = 4 * BLOCK_N;  // 2 accumulator stages x 2 column blocks
     extern __shared__ uint8_t smem_raw[];
@@ -480,13 +487,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 const int th = m % p.tiles_h;
                 const int n = m / p.tiles_h;
                 const int w0 = tw * 16, h0 = th * 16;
+                const int n1 = p.idx1 ? __ldg(p.idx1 + n) : n, n2 = p.idx2 ? __ldg(p.idx2 + n) : n;
                 for (int c = 0; c < p.cin_chunks; ++c) {
+                    const CUtensorMap* am = c < p.split_chunk ? &map_a : &map_a2;
+                    const int cc = (c < p.split_chunk ? c : c - p.split_chunk) * kBlockK;
+                    const int ns = c < p.split_chunk ? n1 : n2;
                     for (int dx = 0; dx < 3; ++dx) {
                         mbar_wait(aempty(sa), pa ^ 1u);
                         mbar_expect_tx(afull(sa), 2 * kSlabBytes);
                         const uint32_t dst = base + sa * L::a_stage;
-                        tma_load_5d(dst, &map_a, afull(sa), c * kBlockK, w0 - 1 + dx, h0 - 1, 0, n);
-                        tma_load_5d(dst + kSlabBytes, &map_a, afull(sa), c * kBlockK, w0 + 7 + dx, h0 - 1, 0, n);
+                        tma_load_5d(dst, am, afull(sa), cc, w0 - 1 + dx, h0 - 1, 0, ns);
+                        tma_load_5d(dst + kSlabBytes, am, afull(sa), cc, w0 + 7 + dx, h0 - 1, 0, ns);
                         if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
                         for (int dy = 0; dy < 3; ++dy) {
                             mbar_wait(bempty(sb), pb ^ 1u);
@@ -606,24 +617,24 @@ EncodeTiledFn get_encode_fn() {
 }
 
 template <int BLOCK_N, int STAGES>
-int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
     using L = SmemLayout<BLOCK_N, STAGES>;
     auto kern = conv_gemm_kernel<BLOCK_N, STAGES>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < sms ? total : sms;
-    kern<<<grid, kThreads, L::total, st>>>(ma, mb, p);
+    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }
 
 template <int BLOCK_N, int A_STAGES, int B_STAGES>
-int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
+int launch_halo(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
     using L = HaloLayout<BLOCK_N, A_STAGES, B_STAGES>;
     auto kern = conv_halo_kernel<BLOCK_N, A_STAGES, B_STAGES>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int grid = p.m_tiles < sms ? p.m_tiles : sms;
-    kern<<<grid, kThreads, L::total, st>>>(ma, mb, p);
+    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }
@@ -652,6 +663,9 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     NRRT_REQUIRE(l->dims == 2 || l->dims == 3, "dims must be 2 or 3");
     NRRT_REQUIRE(l->kind >= 0 && l->kind <= 4, "unknown conv kind %d", l->kind);
     NRRT_REQUIRE(l->cin > 0 && l->cin % 64 == 0, "Cin must be a multiple of 64 (got %d)", l->cin);
+    NRRT_REQUIRE(l->cin2 >= 0 && l->cin2 % 64 == 0, "Cin2 must be a multiple of 64 (got %d)", l->cin2);
+    if (l->cin2 > 0) NRRT_REQUIRE(l->in2 && l->in2_cstride % 8 == 0 && ((uintptr_t)l->in2 & 15) == 0 && l->in2_n >= 1, "bad second input");
+    NRRT_REQUIRE(l->in_n >= 0, "bad in_n");
     NRRT_REQUIRE(l->cout > 0 && l->cout % 32 == 0, "Cout must be a multiple of 32 (got %d)", l->cout);
     NRRT_REQUIRE(l->in_cstride % 8 == 0 && l->out_cstride % 8 == 0 && l->out_coffset % 8 == 0, "channel strides/offsets must be multiples of 8");
     NRRT_REQUIRE(((uintptr_t)l->in & 15) == 0 && ((uintptr_t)l->weight & 15) == 0 && ((uintptr_t)l->out & 15) == 0, "pointers must be 16-byte aligned");
@@ -690,7 +704,10 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
                 p.tap[p.ntaps][2] = (int8_t)(three_d ? dz - pad : 0); p.tap[p.ntaps][3] = 0;
                 ++p.ntaps;
             }
-    p.cin_chunks = l->cin / 64;
+    const int cin_total = l->cin + l->cin2;
+    p.cin_chunks = cin_total / 64;
+    p.split_chunk = l->cin / 64;
+    p.idx1 = l->in_index; p.idx2 = l->in2_index;
     const int groups = up == 2 ? (three_d ? 8 : 4) : 1;
     const int rows_total = groups * l->cout;
     const int block_n = rows_total % 256 == 0 ? 256 : (rows_total % 128 == 0 ? 128 : 64);
@@ -730,22 +747,27 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         p.m_tiles = p.tiles_w * p.tiles_h * N;
     }
 
-    // activation map: dims (C, W, H, D, N) over the caller's NDHWC buffer (channel slice of in_cstride-wide rows)
-    CUtensorMap ma, mb;
-    {
-        const cuuint64_t gdim[5] = {(cuuint64_t)l->cin, (cuuint64_t)iW, (cuuint64_t)iH, (cuuint64_t)iD, (cuuint64_t)N};
-        const cuuint64_t cs = (cuuint64_t)l->in_cstride * 2;
+    // activation maps: dims (C, W, H, D, N) over the caller's NDHWC buffers (channel slices of cstride-wide rows)
+    CUtensorMap ma, ma2, mb;
+    auto make_act_map = [&](CUtensorMap* m, const void* ptr, int cin, int64_t cstride, int n_samples) -> CUresult {
+        const cuuint64_t gdim[5] = {(cuuint64_t)cin, (cuuint64_t)iW, (cuuint64_t)iH, (cuuint64_t)iD, (cuuint64_t)n_samples};
+        const cuuint64_t cs = (cuuint64_t)cstride * 2;
         const cuuint64_t gstr[4] = {cs, cs * iW, cs * iW * iH, cs * iW * iH * iD};
         cuuint32_t box[5] = {64, (cuuint32_t)(p.bw * stride), (cuuint32_t)(p.bh * stride), (cuuint32_t)(p.bd * p.stride_d), 1};
         if (halo) { box[1] = 8; box[2] = 18; box[3] = 1; }  // one slab: 18 pixel rows x 8 pixels
         const cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, (cuuint32_t)p.stride_d, 1};
-        const CUresult r = encode(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(l->in), gdim, gstr, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    {
+        CUresult r = make_act_map(&ma, l->in, l->cin, l->in_cstride, l->in_n > 0 ? l->in_n : N);
+        if (r == CUDA_SUCCESS && l->cin2 > 0) r = make_act_map(&ma2, l->in2, l->cin2, l->in2_cstride, l->in2_n);
+        else ma2 = ma;
         if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d (box %d,%d,%d stride %d)", (int)r, p.bw, p.bh, p.bd, stride);
     }
     {
-        const cuuint64_t ktot = (cuuint64_t)p.ntaps * l->cin;
+        const cuuint64_t ktot = (cuuint64_t)p.ntaps * cin_total;
         const cuuint64_t gdim[2] = {ktot, (cuuint64_t)rows_total};
         const cuuint64_t gstr[1] = {ktot * 2};
         const cuuint32_t box[2] = {64, (cuuint32_t)block_n};
@@ -759,10 +781,10 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (halo) {
-        if (block_n == 128) return launch_halo<128, 4, 4>(ma, mb, p, sms, st);
-        return launch_halo<64, 4, 8>(ma, mb, p, sms, st);
+        if (block_n == 128) return launch_halo<128, 4, 4>(ma, ma2, mb, p, sms, st);
+        return launch_halo<64, 4, 8>(ma, ma2, mb, p, sms, st);
     }
-    if (block_n == 256) return launch_conv<256, 4>(ma, mb, p, sms, st);
-    if (block_n == 128) return launch_conv<128, 6>(ma, mb, p, sms, st);
-    return launch_conv<64, 8>(ma, mb, p, sms, st);
+    if (block_n == 256) return launch_conv<256, 4>(ma, ma2, mb, p, sms, st);
+    if (block_n == 128) return launch_conv<128, 6>(ma, ma2, mb, p, sms, st);
+    return launch_conv<64, 8>(ma, ma2, mb, p, sms, st);
 }

@@ -162,6 +162,26 @@ def test_slab_kernel_equals_per_tap_kernel_and_fused_head(cuda_device):
     assert (logits - ref).abs().max().item() <= 2e-3 * max(ref.abs().max().item(), 1.0)
 
 
+@pytest.mark.parametrize("cout,sp", [(128, (24, 40)), (256, (16, 24))])  # slab kernel / per-tap kernel
+def test_k_split_two_sources_with_sample_index(cout, sp, cuda_device):
+    """conv(torch.cat((a, b[index]), 1)) without the concatenated buffer: source 2 is indexed per sample."""
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(11)
+    a = torch.randn((5, 64) + sp, generator=g).to(dev)          # per-task part
+    b = torch.randn((2, 128) + sp, generator=g).to(dev)         # per-map part
+    index = torch.tensor([1, 0, 0, 1, 1], dtype=torch.int32, device=dev)
+    w = (torch.randn((cout, 192, 3, 3), generator=g) / 41).to(dev)
+    scale, shift = (torch.rand(cout, generator=g) + 0.5).to(dev), torch.randn(cout, generator=g).to(dev)
+    layer = cnn._Layer(2, cnn.K3S1, 64, cout, cnn._pack_conv_weight(w, 192, dev), scale.contiguous(), shift.contiguous(), True,
+                       cin_real=192)
+    layer.cin2 = 128
+    out = torch.zeros((5, 1) + sp + (cout,), dtype=torch.float16, device=dev)
+    layer.run(_lib.load(), None, _cl(a), 0, (1,) + sp, out, 0, x2=_cl(b), idx2=index)
+    torch.cuda.synchronize()
+    ref = _ref(2, cnn.K3S1, torch.cat((a, b[index.long()]), 1), w, scale, shift, True)
+    _check(out, ref, 2, cout)
+
+
 @pytest.mark.parametrize("three_d", [False, True])
 @pytest.mark.parametrize("bn", [False, True])
 def test_unet_forward_matches_reference_golden(three_d, bn, cuda_device):
