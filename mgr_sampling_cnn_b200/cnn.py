@@ -285,41 +285,45 @@ class UNetPlan(object):
         self._bufs = {}
         self.profiler = None
 
-    # activation buffers: encoder set for Be samples (distinct maps), decoder set for B samples (tasks), grid (D, H, W)
-    def _buffers(self, B, Be, grid, shared_encoder):
-        key = (B, Be, shared_encoder) + tuple(grid)
+    # activation buffers: an encoder set for Be samples (distinct maps) and a decoder set for B samples (tasks)
+    def _cached(self, key, make):
         bufs = self._bufs.get(key)
         if bufs is None:
-            dev = self.device
-            D, H, W = grid
-
-            def buf(n, level, ch):
-                s = 2 ** level
-                shape = (n, D // s if self.dims == 3 else 1, H // s, W // s, ch)
-                return torch.empty(shape, dtype=torch.float16, device=dev)
-
-            # task-side decoder inputs: the ConvTranspose output, followed (3D) by the interpolated coordinate channels
-            t8w, t7w, t6w = (64, 128, 512) if self.poly else (128, 256, 768)
-            bufs = {
-                "t0": buf(Be, 0, 64), "x1": buf(Be, 0, 64), "a0": buf(Be, 0, 64), "b0": buf(Be, 0, 64),
-                "a1": buf(Be, 1, 128), "b1": buf(Be, 1, 128), "d1": buf(Be, 1, 128),
-                "a2": buf(Be, 2, 256), "b2": buf(Be, 2, 256), "d2": buf(Be, 2, 256),
-                "a3": buf(Be, 3, 512), "b3": buf(Be, 3, 512), "d3": buf(Be, 3, 512),
-                "e2": buf(Be, 0, 64), "e3": buf(Be, 1, 128), "e4": buf(Be, 2, 256), "e5": buf(Be, 3, 512),
-                "t8": buf(B, 0, t8w), "j": buf(B, 0, 128),
-                "t7": buf(B, 1, t7w), "g7": buf(B, 1, 256), "i": buf(B, 1, 128),
-                "t6": buf(B, 2, t6w), "g6": buf(B, 2, 512), "h": buf(B, 2, 256),
-            }
-            if not self.poly:
-                bufs["c5"] = buf(B, 3, 512)  # interpolated coordinate channels at the bottleneck (second input of upconv6)
-            if len(self._bufs) >= 2:  # keep two configurations resident (full and ragged last micro-batch)
+            if len(self._bufs) >= 4:  # full + ragged configuration of each set
                 self._bufs.pop(next(iter(self._bufs)))
+            bufs = make()
             self._bufs[key] = bufs
         return bufs
 
+    def _buf(self, n, grid, level, ch):
+        D, H, W = grid
+        s = 2 ** level
+        return torch.empty((n, D // s if self.dims == 3 else 1, H // s, W // s, ch), dtype=torch.float16, device=self.device)
+
+    def _enc_buffers(self, Be, grid):
+        b = lambda lv, ch: self._buf(Be, grid, lv, ch)  # noqa: E731
+        return self._cached(("enc", Be) + tuple(grid), lambda: {
+            "t0": b(0, 64), "x1": b(0, 64), "a0": b(0, 64), "b0": b(0, 64), "e2": b(0, 64),
+            "a1": b(1, 128), "b1": b(1, 128), "d1": b(1, 128), "e3": b(1, 128),
+            "a2": b(2, 256), "b2": b(2, 256), "d2": b(2, 256), "e4": b(2, 256),
+            "a3": b(3, 512), "b3": b(3, 512), "d3": b(3, 512), "e5": b(3, 512)})
+
+    def _dec_buffers(self, B, grid):
+        b = lambda lv, ch: self._buf(B, grid, lv, ch)  # noqa: E731
+        # task-side decoder inputs: the ConvTranspose output, followed (3D) by the interpolated coordinate channels
+        t8w, t7w, t6w = (64, 128, 512) if self.poly else (128, 256, 768)
+
+        def make():
+            d = {"t8": b(0, t8w), "j": b(0, 128), "t7": b(1, t7w), "g7": b(1, 256), "i": b(1, 128),
+                 "t6": b(2, t6w), "g6": b(2, 512), "h": b(2, 256)}
+            if not self.poly:
+                d["c5"] = b(3, 512)  # interpolated coordinate channels at the bottleneck (second input of upconv6)
+            return d
+        return self._cached(("dec", B) + tuple(grid), make)
+
     def activation_bytes(self, B, grid):
-        b = self._buffers(B, B, grid, False)
-        return sum(t.numel() * t.element_size() for t in b.values() if isinstance(t, torch.Tensor))
+        b = list(self._enc_buffers(B, grid).values()) + list(self._dec_buffers(B, grid).values())
+        return sum(t.numel() * t.element_size() for t in b)
 
     def layers(self):
         out = [self.stem2, self.up6, self.up7, self.up8] + list(self.c6) + list(self.c7) + list(self.c8)
@@ -406,45 +410,58 @@ class UNetPlan(object):
     def slice_prep(prep, i, j):
         return {k: ([f[i:j] for f in v] if isinstance(v, list) else v[i:j]) for k, v in prep.items()}
 
-    def _forward(self, B, grid, coords, logits_out, x=None, occ=None, t2m=None, enc_index=None, prep=None):
+    def _levels(self, grid):
+        return [tuple(max(v // (2 ** lv), 1) if (self.dims == 3 or i > 0) else 1 for i, v in enumerate(grid)) for lv in range(4)]
+
+    def encode(self, grid, Be, x=None, occ=None, maps=None):
+        """Encoder (conv1 .. conv5, train.py:173-177) for Be samples: either network inputs x or rows `maps` of the
+        resident uint8 occupancy maps.  Returns the buffer set holding e2..e5 (x2..x5 of the reference)."""
         lib, dims = self.lib, self.dims
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        coords = coords.contiguous().float()
-        if any(g % 8 for g in grid[(0 if dims == 3 else 1):]):
+        if any(v % 8 for v in grid[(0 if dims == 3 else 1):]):
             raise ValueError("spatial sizes must be multiples of 8 (three stride-2 stages)")
-        shared = enc_index is not None
-        Be = t2m.shape[0] if shared else B
-        bf = self._buffers(B, Be, grid, shared)
-        g = [tuple(max(v // (2 ** lv), 1) if (dims == 3 or i > 0) else 1 for i, v in enumerate(grid)) for lv in range(4)]
-
-        # stem
+        bf = self._enc_buffers(Be, grid)
+        g = self._levels(grid)
         _lib.count_launch()
         if x is not None:
-            check(lib.nrrt_stem_conv(dims, _ptr(x), B, self.stem_cin, grid[0], grid[1], grid[2], _ptr(self.stem_w),
+            check(lib.nrrt_stem_conv(dims, _ptr(x), Be, self.stem_cin, grid[0], grid[1], grid[2], _ptr(self.stem_w),
                                      _ptr(self.stem_b), self.stem_cout, 64, _ptr(bf["t0"]), st))
         else:
-            check(lib.nrrt_stem_conv_maps(dims, _ptr(occ), _ptr(t2m), Be, self.stem_cin, grid[0], grid[1], grid[2],
+            check(lib.nrrt_stem_conv_maps(dims, _ptr(occ), _ptr(maps), Be, self.stem_cin, grid[0], grid[1], grid[2],
                                           _ptr(self.stem_w), _ptr(self.stem_b), self.stem_cout, 64, _ptr(bf["t0"]), st))
         self.stem2.run(lib, st, bf["t0"], 0, g[0], bf["x1"], 0)
 
-        # encoder; the last conv of every stage writes into its concat buffer slice
-        def stage(blks, xin, xin_off, gin, gout, a, b, dsb, final, final_off):
+        def stage(blks, xin, gin, gout, a, b, dsb, final):
             (c1, c2, ds), (c3, c4, _) = blks
+            res = xin
             if ds is not None:
-                ds.run(lib, st, xin, xin_off, gin, dsb, 0)
-                res, res_off = dsb, 0
-            else:
-                res, res_off = xin, xin_off
-            c1.run(lib, st, xin, xin_off, gin, a, 0)
-            c2.run(lib, st, a, 0, gout, b, 0, res, res_off)
+                ds.run(lib, st, xin, 0, gin, dsb, 0)
+                res = dsb
+            c1.run(lib, st, xin, 0, gin, a, 0)
+            c2.run(lib, st, a, 0, gout, b, 0, res, 0)
             c3.run(lib, st, b, 0, gout, a, 0)
-            c4.run(lib, st, a, 0, gout, final, final_off, b, 0)
+            c4.run(lib, st, a, 0, gout, final, 0, b, 0)
 
-        # encoder outputs live once per encoder sample (= per distinct map when the encoder is shared)
-        stage(self.enc[0], bf["x1"], 0, g[0], g[0], bf["a0"], bf["b0"], None, bf["e2"], 0)
-        stage(self.enc[1], bf["e2"], 0, g[0], g[1], bf["a1"], bf["b1"], bf["d1"], bf["e3"], 0)
-        stage(self.enc[2], bf["e3"], 0, g[1], g[2], bf["a2"], bf["b2"], bf["d2"], bf["e4"], 0)
-        stage(self.enc[3], bf["e4"], 0, g[2], g[3], bf["a3"], bf["b3"], bf["d3"], bf["e5"], 0)
+        stage(self.enc[0], bf["x1"], g[0], g[0], bf["a0"], bf["b0"], None, bf["e2"])
+        stage(self.enc[1], bf["e2"], g[0], g[1], bf["a1"], bf["b1"], bf["d1"], bf["e3"])
+        stage(self.enc[2], bf["e3"], g[1], g[2], bf["a2"], bf["b2"], bf["d2"], bf["e4"])
+        stage(self.enc[3], bf["e4"], g[2], g[3], bf["a3"], bf["b3"], bf["d3"], bf["e5"])
+        return bf
+
+    def _forward(self, B, grid, coords, logits_out, x=None, occ=None, t2m=None, enc_index=None, prep=None):
+        Be = t2m.shape[0] if enc_index is not None else B
+        enc = self.encode(grid, Be, x=x, occ=occ, maps=t2m)
+        return self.decode(enc, B, grid, coords, prep, enc_index, logits_out)
+
+    def decode(self, enc, B, grid, coords, prep=None, enc_index=None, logits_out=None):
+        """Coordinate branch + decoder (train.py:179-203) for B tasks whose encoder outputs are rows enc_index[b]
+        (None: row b) of the buffer set returned by encode()."""
+        lib, dims = self.lib, self.dims
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        coords = coords.contiguous().float()
+        bf = dict(self._dec_buffers(B, grid))
+        bf.update({k: enc[k] for k in ("e2", "e3", "e4", "e5")})
+        g = self._levels(grid)
 
         # coordinate branch (train.py:179-190)
         if prep is None:

@@ -259,6 +259,7 @@ class GuidedPlanner(object):
         self._cdf = None
         self.profile_every = 0
         self.share_encoder = True
+        self.encoder_batch = 8  # distinct maps per encoder pass
 
     def _ensure(self, B):
         if self._bufs is None or self._logits.shape[0] != B:
@@ -277,29 +278,36 @@ class GuidedPlanner(object):
         out = out if out is not None else torch.empty((B, self.cells), dtype=torch.float32, device=self.device)
         mb = self.micro_batch
         t2m_h = task_to_map_host if task_to_map_host is not None else task_to_map.cpu().numpy()
-        # per micro-batch: distinct maps and the task -> encoder-row index, built on the host once and uploaded together
-        enc_maps, enc_index, spans = [], [], []
-        for i in range(0, B, mb):
-            u, inv = np.unique(t2m_h[i:i + mb], return_inverse=True)
-            spans.append((len(enc_maps), len(u)))
-            enc_maps.extend(u.tolist())
-            enc_index.extend(inv.tolist())
         grid = (1,) + self.shape if self.dim == 2 else self.shape
         prep = plan.coords_prepare(coords, grid)  # coordinate branch (+ 2D epilogue polynomials) for every task at once
-        enc_maps_d = torch.tensor(enc_maps, dtype=torch.int32).to(self.device, non_blocking=True)
-        enc_index_d = torch.tensor(enc_index, dtype=torch.int32).to(self.device, non_blocking=True)
-        for mbi, i in enumerate(range(0, B, mb)):
-            if plan.profiler is not None:  # bench.py: time the conv launches of every n-th micro-batch
-                plan.profiler.active = self.profile_every > 0 and mbi % self.profile_every == 0
-            o, n_u = spans[mbi]
-            n = min(mb, B - i)
-            if self.share_encoder and n_u < n:
-                plan.forward_maps(occ_maps, None, coords[i:i + mb], logits_out=out[i:i + mb],
-                                  enc_maps=enc_maps_d[o:o + n_u], enc_index=enc_index_d[i:i + mb],
-                                  prep=plan.slice_prep(prep, i, i + mb))
-            else:
+        if not self.share_encoder or np.any(np.diff(t2m_h) < 0):
+            # tasks not grouped by map (or sharing disabled): one encoder pass per task
+            for mbi, i in enumerate(range(0, B, mb)):
+                if plan.profiler is not None:
+                    plan.profiler.active = self.profile_every > 0 and mbi % self.profile_every == 0
                 plan.forward_maps(occ_maps, task_to_map[i:i + mb], coords[i:i + mb], logits_out=out[i:i + mb],
                                   prep=plan.slice_prep(prep, i, i + mb))
+            return out
+        # tasks are grouped by map: encode `encoder_batch` distinct maps at a time, then decode their tasks in micro-batches
+        uniq, first = np.unique(t2m_h, return_index=True)
+        G = self.encoder_batch
+        rel = np.searchsorted(uniq, t2m_h).astype(np.int32) % G  # row of the task's map inside its encoder pass
+        uniq_d = torch.from_numpy(uniq.astype(np.int32)).to(self.device, non_blocking=True)
+        rel_d = torch.from_numpy(rel).to(self.device, non_blocking=True)
+        bounds = list(first) + [B]
+        mbi = 0
+        for g0 in range(0, len(uniq), G):
+            g1 = min(len(uniq), g0 + G)
+            if plan.profiler is not None:
+                plan.profiler.active = self.profile_every > 0 and (g0 // G) % max(self.profile_every // G, 1) == 0
+            enc = plan.encode(grid, g1 - g0, occ=occ_maps, maps=uniq_d[g0:g1])
+            lo, hi = bounds[g0], bounds[g1]
+            for i in range(lo, hi, mb):
+                j = min(hi, i + mb)
+                if plan.profiler is not None:
+                    plan.profiler.active = self.profile_every > 0 and mbi % self.profile_every == 0
+                mbi += 1
+                plan.decode(enc, j - i, grid, coords[i:j], plan.slice_prep(prep, i, j), rel_d[i:j], out[i:j])
         return out
 
     def plan(self, occ_maps, task_to_map, starts, goals, coords, seed: int = 0, task_ids=None, record_events=False):
