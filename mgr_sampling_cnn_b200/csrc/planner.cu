@@ -96,45 +96,62 @@ __device__ __forceinline__ void nn_warp_reduce(double& bs, int& bj) {
 // both truncate to the same cell; otherwise (segment ends on integer cells, axis-parallel moves, coincidences) the
 // lane re-evaluates the reference's exact sequence.  t = 0 and d_k = 0 are exact without any division.
 template <int DIM>
-__device__ __forceinline__ bool collision_free_warp(const double (&p1)[DIM], const double (&p2)[DIM],
-                                                    const uint32_t* __restrict__ grid, const int (&shape)[3], int lane) {
-    double dl[DIM], u[DIM];
-    bool same = true;
+struct Segment {  // per-segment constants of is_collision_free, identical in every lane
+    double p1[DIM], dl[DIM], u[DIM], D, step;
+    bool same;
+};
+
+template <int DIM>
+__device__ __forceinline__ Segment<DIM> segment_setup(const double (&p1)[DIM], const double (&p2)[DIM]) {
+    Segment<DIM> sg;
+    sg.same = true;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
-        dl[k] = __dsub_rn(p1[k], p2[k]);
-        same = same && (p1[k] == p2[k]);
+        sg.p1[k] = p1[k];
+        sg.dl[k] = __dsub_rn(p1[k], p2[k]);
+        sg.same = sg.same && (p1[k] == p2[k]);
     }
-    if (same) return false;  // `if point1 == point2: return False`
-    double q = __dmul_rn(dl[0], dl[0]);  // np.linalg.norm -> ddot: FMA chain
-    q = __fma_rn(dl[1], dl[1], q);
-    if (DIM == 3) q = __fma_rn(dl[DIM - 1], dl[DIM - 1], q);
-    const double D = sqrt(q);
-    const double step = __ddiv_rn(D, 99.0);  // np.linspace(0, D, 100)
+    double q = __dmul_rn(sg.dl[0], sg.dl[0]);  // np.linalg.norm -> ddot: FMA chain
+    q = __fma_rn(sg.dl[1], sg.dl[1], q);
+    if (DIM == 3) q = __fma_rn(sg.dl[DIM - 1], sg.dl[DIM - 1], q);
+    sg.D = sqrt(q);
+    sg.step = __ddiv_rn(sg.D, 99.0);  // np.linspace(0, D, 100)
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) u[k] = __ddiv_rn(dl[k], D);
+    for (int k = 0; k < DIM; ++k) sg.u[k] = __ddiv_rn(sg.dl[k], sg.D);
+    return sg;
+}
+
+// sample i (0..99) of the segment: true iff its cell is an obstacle
+template <int DIM>
+__device__ __forceinline__ bool sample_blocked(const Segment<DIM>& sg, int i, const uint32_t* __restrict__ grid,
+                                               const int (&shape)[3]) {
+    const double t = (i == 99) ? sg.D : __dmul_rn((double)i, sg.step);
+    int idx = 0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        double v;
+        if (i == 0 || sg.dl[k] == 0.0) {
+            v = sg.p1[k];  // (0 * d) / D = +-0 and p1 - +-0 = p1: exact
+        } else {
+            v = __fma_rn(-t, sg.u[k], sg.p1[k]);
+            if (fabs(v - rint(v)) <= 1e-6)  // rounding could change the cell: the reference's exact sequence
+                v = __dsub_rn(sg.p1[k], __ddiv_rn(__dmul_rn(t, sg.dl[k]), sg.D));
+        }
+        int ci = __double2int_rz(v);  // int(): truncation toward zero
+        ci = max(0, min(ci, shape[k] - 1));
+        idx = idx * shape[k] + ci;
+    }
+    return ((grid[idx >> 5] >> (idx & 31)) & 1u) == 0u;
+}
+
+template <int DIM>
+__device__ __forceinline__ bool collision_free_warp(const double (&p1)[DIM], const double (&p2)[DIM],
+                                                    const uint32_t* __restrict__ grid, const int (&shape)[3], int lane) {
+    const Segment<DIM> sg = segment_setup<DIM>(p1, p2);
+    if (sg.same) return false;  // `if point1 == point2: return False`
 #pragma unroll 1
     for (int i = lane; i < 128; i += kWarp) {
-        bool blocked = false;
-        if (i < 100) {
-            const double t = (i == 99) ? D : __dmul_rn((double)i, step);
-            int idx = 0;
-#pragma unroll
-            for (int k = 0; k < DIM; ++k) {
-                double v;
-                if (i == 0 || dl[k] == 0.0) {
-                    v = p1[k];  // (0 * d) / D = +-0 and p1 - +-0 = p1: exact
-                } else {
-                    v = __fma_rn(-t, u[k], p1[k]);
-                    if (fabs(v - rint(v)) <= 1e-6)  // rounding could change the cell: the reference's exact sequence
-                        v = __dsub_rn(p1[k], __ddiv_rn(__dmul_rn(t, dl[k]), D));
-                }
-                int ci = __double2int_rz(v);  // int(): truncation toward zero
-                ci = max(0, min(ci, shape[k] - 1));
-                idx = idx * shape[k] + ci;
-            }
-            blocked = ((grid[idx >> 5] >> (idx & 31)) & 1u) == 0u;
-        }
+        const bool blocked = i < 100 && sample_blocked<DIM>(sg, i, grid, shape);
         if (__any_sync(0xffffffffu, blocked)) return false;
     }
     return true;
@@ -202,6 +219,10 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
         double best = INFINITY;
         const int16_t* smp_base = a.samples + (size_t)task * max_iter * DIM;
         double r_next = __ldg(a.radius);
+        double pend[DIM];   // newest node, kept in registers: its shared-memory copy becomes visible at barrier (1)
+        int pend_j = -1;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) pend[k] = 0.0;
         int16_t smp_next[DIM];
 #pragma unroll
         for (int k = 0; k < DIM; ++k) smp_next[k] = __ldg(smp_base + k);
@@ -224,7 +245,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
             for (int j = tid; j < n; j += NT) {
                 double pj[DIM];
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) pj[k] = pos[k * cap + j];
+                for (int k = 0; k < DIM; ++k) pj[k] = (j == pend_j) ? pend[k] : pos[k * cap + j];
                 const double s = nrrt_sqdist<DIM>(pj, smp);
                 if (s < bs) {
                     bool take = true;
@@ -280,16 +301,14 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
 #pragma unroll
             for (int k = 0; k < DIM; ++k) npos[k] = __dadd_rn(from[k], dr[k]);
 
-            // ---- can_connect_nodes: every warp evaluates the same test (no barrier needed) ----
-            const bool connect = collision_free_warp<DIM>(from, npos, grid, shape, lane);
-            if (TRACE && tid == 0) {
-                if (trace_n < a.out.trace_cap) {
-                    int32_t* t = trace + 4 * trace_n;
-                    t[0] = iters; t[1] = 0; t[2] = ni; t[3] = connect ? 1 : 0;
-                }
-                ++trace_n;
+            // ---- can_connect_nodes: warps 0..3 take one round of 25-32 samples each; the verdict is combined by the
+            // barrier that publishes the near mask, which is computed speculatively (the test passes ~95 % of the time)
+            const Segment<DIM> sg0 = segment_setup<DIM>(from, npos);
+            bool my_blocked = sg0.same;
+            if (warp < 4 && !sg0.same) {
+                const int i = warp * kWarp + lane;
+                my_blocked = i < 100 && sample_blocked<DIM>(sg0, i, grid, shape);
             }
-            if (!connect) continue;
 
             // ---- find_nearby_nodes: euclid(new, node) <= r, as a bit mask in insertion order ----
             const double r2 = __dmul_rn(r, r);
@@ -307,16 +326,32 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
                 const uint32_t m = __ballot_sync(0xffffffffu, in);
                 if (lane == 0 && (base >> 5) + warp < a.mask_words) mask[(base >> 5) + warp] = m;
             }
-            __syncthreads();  // (2)
+            const bool connect = __syncthreads_or(my_blocked ? 1 : 0) == 0;  // (2)
+            if (TRACE && tid == 0) {
+                if (trace_n < a.out.trace_cap) {
+                    int32_t* t = trace + 4 * trace_n;
+                    t[0] = iters; t[1] = 0; t[2] = ni; t[3] = connect ? 1 : 0;
+                }
+                ++trace_n;
+            }
+            if (!connect) continue;
             const int nwords = (n + 31) >> 5;
 
             // ---- loop A: choose parent.  Result = lexicographic min (cost, index) over free candidates < ncost0 ----
             double wbest = ncost0;
             int wpar = -1;
-            for (int w = TRACE ? 0 : warp; w < nwords; w += TRACE ? 1 : NW) {
-                if (TRACE && warp != 0) break;
-                const uint32_t m = mask[w];
-                if (m == 0u) continue;
+            // this warp's mask words: w = w_first + w_stride * t.  Lane t fetches word t of each block of 32 and the
+            // non-empty ones are visited in order (most of the ~20 words per warp are empty).
+            const int w_first = TRACE ? 0 : warp, w_stride = TRACE ? 1 : NW;
+            const int my_words = (TRACE && warp != 0) ? 0 : (nwords - w_first + w_stride - 1) / w_stride;
+            for (int tb = 0; tb < my_words; tb += kWarp) {
+              const uint32_t lane_word = (tb + lane < my_words) ? mask[w_first + w_stride * (tb + lane)] : 0u;
+              uint32_t nz = __ballot_sync(0xffffffffu, lane_word != 0u);
+              while (nz) {
+                const int t = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const int w = w_first + w_stride * (tb + t);
+                const uint32_t m = __shfl_sync(0xffffffffu, lane_word, t);
                 const int j = (w << 5) + lane;
                 const bool has = (m >> lane) & 1u;
                 double pj[DIM], cj = INFINITY;
@@ -346,6 +381,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
                     }
                     if (fr) { wbest = cb; wpar = (w << 5) + b; }
                 }
+              }
             }
             if (lane == 0) { slot_a[warp].v = wbest; slot_a[warp].j = wpar; }
             __syncthreads();  // (3)
@@ -360,10 +396,14 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
             }
 
             // ---- loop B: rewire neighbours through the new node (index n); costs are not propagated ----
-            for (int w = TRACE ? 0 : warp; w < nwords; w += TRACE ? 1 : NW) {
-                if (TRACE && warp != 0) break;
-                const uint32_t m = mask[w];
-                if (m == 0u) continue;
+            for (int tb = 0; tb < my_words; tb += kWarp) {
+              const uint32_t lane_word = (tb + lane < my_words) ? mask[w_first + w_stride * (tb + lane)] : 0u;
+              uint32_t nz = __ballot_sync(0xffffffffu, lane_word != 0u);
+              while (nz) {
+                const int t = __ffs(nz) - 1;
+                nz &= nz - 1;
+                const int w = w_first + w_stride * (tb + t);
+                const uint32_t m = __shfl_sync(0xffffffffu, lane_word, t);
                 const int j = (w << 5) + lane;
                 const bool has = (m >> lane) & 1u;
                 double pj[DIM], cj = 0.0, cur = 0.0;
@@ -392,6 +432,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
                     }
                     if (fr && lane == b) { parent[j] = n; cost[j] = cj; }
                 }
+              }
             }
 
             // ---- goal_reached + append (rrt_star.py:156-161, :201-209) ----
@@ -401,8 +442,12 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
             if (tid < DIM) pos[tid * cap + n] = reached ? goal[tid] : npos[tid];  // goal_node.position = self.goal
             if (tid == 0) { cost[n] = ncost; parent[n] = npar; }
             if (reached) { goal_node = n; break; }
+            // no barrier here: the next scan takes the new node from registers, and every later reader of pos[n],
+            // cost[n], parent[n], mask or slot_a sits behind barrier (1) of the next iteration
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) pend[k] = npos[k];
+            pend_j = n;
             ++n;
-            __syncthreads();  // (4) new node visible to the next scan; mask / slot_a free for reuse
         }
         __syncthreads();
 
