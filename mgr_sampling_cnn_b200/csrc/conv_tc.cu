@@ -138,8 +138,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 
 // kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = kBlockM) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // Epilogue of 32 accumulator columns of one output pixel: folded-BN scale/shift, polynomial coordinate term, residual,
@@ -411,6 +411,236 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
+
+// ---- cta_group::2 (CTA pair) primitives ----------------------------------------------------------------------------
+// In a 2-CTA cluster the shared::cluster addresses of the two CTAs differ in bit 24; clearing it addresses the leader.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2,
+                                             int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+            "r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// commit of the pair's MMAs, arriving on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+// arrive on the leader CTA's copy of a barrier (local for the leader, remote for the peer)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar)
+        : "memory");
+}
+
+template <int BLOCK_N, int STAGES>
+struct SmemLayout2 {  // per CTA of a pair: its own A tile and HALF of the B tile per stage
+    static constexpr uint32_t a_stage = kBlockM * 128;
+    static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
+    static constexpr uint32_t off_b = STAGES * a_stage;
+    static constexpr uint32_t off_bar = off_b + STAGES * b_stage;
+    static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4) * 8;
+    static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
+    static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
+};
+
+// conv_gemm2_kernel — conv_gemm_kernel on CTA pairs (tcgen05 cta_group::2).  tcgen05.mma in SS mode is fed from shared
+// memory at ~85 B/clk/SM (profiles/README.md), which caps a 1-CTA M128xN256 MMA at ~86 % and narrower N lower.  A CTA pair
+// issues M256 MMAs: each SM supplies its own 128 A rows and only HALF of B (the other half comes from the peer's shared
+// memory), cutting operand bytes per SM from 4 KB + 32N to 4 KB + 16N per K=16 step.  Both CTAs run a TMA producer (own A
+// tile + own B half, all signalling the leader's barrier) and the epilogue; only the leader issues MMAs and its commits
+// are multicast to the barriers of both CTAs.
+template <int BLOCK_N, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ ConvParams p) {
+    using L = SmemLayout2<BLOCK_N, STAGES>;
+    constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = base + L::off_bar;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
+    float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();       // 0 = leader (issues the MMAs for the pair), 1 = peer
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int total_pairs = ((p.m_tiles + 1) >> 1) * p.n_tiles;  // a pair of CTAs owns two consecutive M tiles
+    const int k_iters = p.ntaps * p.cin_chunks;
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        // the leader's tempty barrier collects the epilogue warps of BOTH CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L::off_tmem),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
+                const int n_tile = pt % p.n_tiles;
+                int m = (pt / p.n_tiles) * 2 + (int)rank;
+                const bool live = m < p.m_tiles;  // an odd tile count leaves the peer of the last pair without work
+                const int tw = m % p.tiles_w; m /= p.tiles_w;
+                const int th = m % p.tiles_h; m /= p.tiles_h;
+                const int td = m % p.tiles_d;
+                const int n = m / p.tiles_d;
+                const int w0 = tw * p.bw * p.stride, h0 = th * p.bh * p.stride, d0 = td * p.bd * p.stride_d;
+                // a dead tile still loads (zero-filled: sample index past the end) so the pair's byte count is constant
+                const int n1 = !live ? 0x3fffffff : (p.idx1 ? __ldg(p.idx1 + n) : n);
+                const int n2 = !live ? 0x3fffffff : (p.idx2 ? __ldg(p.idx2 + n) : n);
+                for (int t = 0; t < p.ntaps; ++t) {
+                    const int cw = w0 + p.tap[t][0], ch = h0 + p.tap[t][1], cd = d0 + p.tap[t][2];
+                    for (int c = 0; c < p.cin_chunks; ++c) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        // one arrival (the leader's) expects the bytes of both CTAs; every load signals the leader's barrier
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * p.a_bytes + p.b_bytes);
+                        const uint32_t lbar = full_bar(stage) & kPeerBitMask;
+                        if (c < p.split_chunk)
+                            tma2_load_5d(base + stage * L::a_stage, &map_a, lbar, c * kBlockK, cw, ch, cd, n1);
+                        else
+                            tma2_load_5d(base + stage * L::a_stage, &map_a2, lbar, (c - p.split_chunk) * kBlockK, cw, ch, cd, n2);
+                        tma2_load_2d(base + L::off_b + stage * L::b_stage, &map_b, lbar, (t * p.cin_chunks + c) * kBlockK,
+                                     n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+            // drain: the leader's multicast commits must not land in a CTA that already exited
+            for (int i = 0; i < STAGES; ++i) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores (M = 256 per instruction) =====
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_N, 256);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+                for (int k = 0; k < k_iters; ++k) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_smem_desc(base + stage * L::a_stage);
+                    const uint64_t bdesc = make_smem_desc(base + L::off_b + stage * L::b_stage);
+#pragma unroll
+                    for (int kk = 0; kk < kBlockK / 16; ++kk)  // UMMA_K = 16: +32 bytes inside the swizzle row
+                        tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                    tc_commit2(empty_bar(stage));  // frees the smem slot in both CTAs once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit2(tfull_bar(acc));  // accumulator complete in both CTAs' tensor memory
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; the two warps of a quarter split the column chunks =====
+        const int sub = warp & 3;
+        const int part = (warp - 2) >> 2;
+        const int row = sub * 32 + lane;
+        const int et = threadIdx.x - 64;  // 0..255
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int last_ntile[2] = {-1, -1}, last_n[2] = {-1, -1};
+        for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
+            const int n_tile = pt % p.n_tiles;
+            int m = (pt / p.n_tiles) * 2 + (int)rank;
+            const bool live = m < p.m_tiles;
+            const int tw = m % p.tiles_w; m /= p.tiles_w;
+            const int th = m % p.tiles_h; m /= p.tiles_h;
+            const int td = m % p.tiles_d;
+            const int n = live ? m / p.tiles_d : 0;
+            float* sc = ss + acc * 8 * BLOCK_N;  // double-buffered by accumulator stage
+            stage_tile_params<BLOCK_N>(p, sc, n_tile * BLOCK_N, n, et, last_ntile[acc] != n_tile,
+                                       last_ntile[acc] != n_tile || last_n[acc] != n);
+            last_ntile[acc] = n_tile; last_n[acc] = n;
+
+            const int wl = row % p.bw, hl = (row / p.bw) % p.bh, dl = row / (p.bw * p.bh);
+            const int w = tw * p.bw + wl, h = th * p.bh + hl, d = td * p.bd + dl;
+            const bool valid = live && row < p.rows && w < p.W && h < p.H && d < p.D;
+
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            float head_acc = 0.f;
+            // fused head: one warp per quarter walks all chunks (the dot product runs over all channels of a pixel)
+            const int c_begin = p.logits ? 0 : part, c_step = p.logits ? 1 : 2;
+            if (!(p.logits && part == 1)) {
+#pragma unroll 1
+                for (int c = c_begin; c < BLOCK_N / 32; c += c_step) {
+                    uint32_t v[32];
+                    tc_ld32(taddr + (uint32_t)(c * 32), v);
+                    if (valid)
+                        epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
+                                       sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc);
+                }
+                if (valid && p.logits) p.logits[(((long long)n * p.oD + d) * p.oH + h) * p.oW + w] = head_acc + p.head_b;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty_bar(acc));  // the leader's MMA thread waits for both CTAs' epilogues
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // neither CTA frees tensor memory or exits while its peer can still touch it
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // conv_halo_kernel — 2D 3x3 stride-1 layers with <= 128 output channels (layer1, layer2, conv7.2, conv8.x).
 //
@@ -628,6 +858,18 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap
     return NRRT_OK;
 }
 
+template <int BLOCK_N, int STAGES>
+int launch_conv2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
+    using L = SmemLayout2<BLOCK_N, STAGES>;
+    auto kern = conv_gemm2_kernel<BLOCK_N, STAGES>;
+    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);  // whole CTA pairs (static cluster dims 2x1x1)
+    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
 template <int BLOCK_N, int A_STAGES, int B_STAGES>
 int launch_halo(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
     using L = HaloLayout<BLOCK_N, A_STAGES, B_STAGES>;
@@ -741,6 +983,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     }
     // 2D 3x3 stride-1 layers with a narrow N are L2-bound in the per-tap kernel: use the slab (halo-reuse) kernel
     const bool halo = !three_d && l->kind == NRRT_CONV_K3S1 && p.n_tiles == 1 && block_n <= 128 && !l->force_per_tap;
+    const bool pair = !halo && block_n >= 128 && l->force_per_tap != 2;  // CTA pairs (cta_group::2) for the per-tap kernel
     if (halo) {
         p.bw = 16; p.bh = 16; p.bd = 1; p.rows = 256;
         p.tiles_w = (p.W + 15) / 16; p.tiles_h = (p.H + 15) / 16; p.tiles_d = 1;
@@ -770,7 +1013,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         const cuuint64_t ktot = (cuuint64_t)p.ntaps * cin_total;
         const cuuint64_t gdim[2] = {ktot, (cuuint64_t)rows_total};
         const cuuint64_t gstr[1] = {ktot * 2};
-        const cuuint32_t box[2] = {64, (cuuint32_t)block_n};
+        const cuuint32_t box[2] = {64, (cuuint32_t)(pair ? block_n / 2 : block_n)};  // a CTA of a pair loads half of B
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = encode(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(l->weight), gdim, gstr, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -783,6 +1026,10 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     if (halo) {
         if (block_n == 128) return launch_halo<128, 4, 4>(ma, ma2, mb, p, sms, st);
         return launch_halo<64, 4, 8>(ma, ma2, mb, p, sms, st);
+    }
+    if (pair) {
+        if (block_n == 256) return launch_conv2<256, 6>(ma, ma2, mb, p, sms, st);
+        return launch_conv2<128, 8>(ma, ma2, mb, p, sms, st);
     }
     if (block_n == 256) return launch_conv<256, 4>(ma, ma2, mb, p, sms, st);
     if (block_n == 128) return launch_conv<128, 6>(ma, ma2, mb, p, sms, st);
