@@ -829,6 +829,193 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
+
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
+    static constexpr uint32_t a_stage = 2 * kSlabBytes;
+    static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
+    static constexpr uint32_t off_b = A_STAGES * a_stage;
+    static constexpr uint32_t off_bar = off_b + B_STAGES * b_stage;
+    static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4) * 8;
+    static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
+    static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
+};
+
+// conv_halo2_kernel — the slab kernel on CTA pairs (cta_group::2): the pair owns two adjacent 16x16 tiles, every MMA is
+// M256 = column block `blk` of both CTAs, and each CTA loads (and feeds from its shared memory) only half of each B tile.
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ ConvParams p) {
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES>;
+    constexpr int TMEM_COLS = 4 * BLOCK_N;  // 2 accumulator stages x 2 column blocks
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = base + L::off_bar;
+    auto afull = [&](int s) { return bar0 + 8u * s; };
+    auto aempty = [&](int s) { return bar0 + 8u * (A_STAGES + s); };
+    auto bfull = [&](int s) { return bar0 + 8u * (2 * A_STAGES + s); };
+    auto bempty = [&](int s) { return bar0 + 8u * (2 * A_STAGES + B_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 2 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
+    float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the pair's MMAs), 1 = peer
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int total_pairs = (p.m_tiles + 1) >> 1;  // a CTA pair owns two consecutive 16x16 tiles; n_tiles == 1
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L::off_tmem),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer: same (chunk, dx, dy) order as the MMA issuer consumes =====
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
+                int m = pt * 2 + (int)rank;
+                const bool live = m < p.m_tiles;
+                const int tw = m % p.tiles_w; m /= p.tiles_w;
+                const int th = m % p.tiles_h;
+                const int n = m / p.tiles_h;
+                const int w0 = tw * 16, h0 = th * 16;
+                const int n1 = !live ? 0x3fffffff : (p.idx1 ? __ldg(p.idx1 + n) : n);
+                const int n2 = !live ? 0x3fffffff : (p.idx2 ? __ldg(p.idx2 + n) : n);
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    const CUtensorMap* am = c < p.split_chunk ? &map_a : &map_a2;
+                    const int cc = (c < p.split_chunk ? c : c - p.split_chunk) * kBlockK;
+                    const int ns = c < p.split_chunk ? n1 : n2;
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(aempty(sa), pa ^ 1u);
+                        if (rank == 0) mbar_expect_tx(afull(sa), 4 * kSlabBytes);  // two slabs from each CTA of the pair
+                        const uint32_t dst = base + sa * L::a_stage;
+                        const uint32_t abar = afull(sa) & kPeerBitMask;
+                        tma2_load_5d(dst, am, abar, cc, w0 - 1 + dx, h0 - 1, 0, ns);
+                        tma2_load_5d(dst + kSlabBytes, am, abar, cc, w0 + 7 + dx, h0 - 1, 0, ns);
+                        if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait(bempty(sb), pb ^ 1u);
+                            if (rank == 0) mbar_expect_tx(bfull(sb), 2 * L::b_stage);  // each CTA loads half of the B tile
+                            tma2_load_2d(base + L::off_b + sb * L::b_stage, &map_b, bfull(sb) & kPeerBitMask,
+                                         ((dy * 3 + dx) * p.cin_chunks + c) * kBlockK, (int)rank * (BLOCK_N / 2));
+                            if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
+                        }
+                    }
+                }
+            }
+            // drain both rings: multicast commits of the leader must not land in a CTA that already exited
+            for (int i = 0; i < A_STAGES; ++i) { mbar_wait(aempty(sa), pa ^ 1u); if (++sa == A_STAGES) { sa = 0; pa ^= 1u; } }
+            for (int i = 0; i < B_STAGES; ++i) { mbar_wait(bempty(sb), pb ^ 1u); if (++sb == B_STAGES) { sb = 0; pb ^= 1u; } }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc(BLOCK_N, 256);  // M 256 = column block `blk` of both CTAs
+            int sa = 0, sb = 0, acc = 0;
+            uint32_t pa = 0, pb = 0, acc_phase = 0;
+            for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BLOCK_N);
+                uint32_t first = 1;
+                for (int c = 0; c < p.cin_chunks; ++c) {
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(afull(sa), pa);
+                        tc_fence_after();
+                        const uint32_t a_base = base + sa * L::a_stage;
+                        for (int dy = 0; dy < 3; ++dy) {
+                            mbar_wait(bfull(sb), pb);
+                            tc_fence_after();
+                            const uint64_t bdesc = make_smem_desc(base + L::off_b + sb * L::b_stage);
+#pragma unroll
+                            for (int blk = 0; blk < 2; ++blk) {
+                                // vertical tap dy = start one pixel row (8 px x 128 B) further down the slab
+                                const uint64_t adesc = make_smem_desc(a_base + blk * kSlabBytes + dy * 1024);
+#pragma unroll
+                                for (int kk = 0; kk < kBlockK / 16; ++kk)
+                                    tc_mma2_f16(d_tmem + (uint32_t)(blk * BLOCK_N), adesc + (uint64_t)(kk * 2),
+                                               bdesc + (uint64_t)(kk * 2), idesc, (first && kk == 0) ? 0u : 1u);
+                            }
+                            first = 0;
+                            tc_commit2(bempty(sb));
+                            if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
+                        }
+                        tc_commit2(aempty(sa));
+                        if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+                    }
+                }
+                tc_commit2(tfull_bar(acc));
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..9: warps 2-5 take column block 0, warps 6-9 column block 1 =====
+        const int sub = warp & 3;
+        const int blk = (warp - 2) >> 2;
+        const int row = sub * 32 + lane;  // row of a column block: (h_l, w_l) = (row / 8, row % 8)
+        const int et = threadIdx.x - 64;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int last_n[2] = {-1, -1};
+        for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
+            int m = pt * 2 + (int)rank;
+            const bool live = m < p.m_tiles;
+            const int tw = m % p.tiles_w; m /= p.tiles_w;
+            const int th = m % p.tiles_h;
+            const int n = live ? m / p.tiles_h : 0;
+            float* sc = ss + acc * 8 * BLOCK_N;
+            stage_tile_params<BLOCK_N>(p, sc, 0, n, et, last_n[acc] < 0, last_n[acc] != n);
+            last_n[acc] = n;
+            const int h = th * 16 + (row >> 3);
+            const int w = tw * 16 + blk * 8 + (row & 7);
+            const bool valid = live && h < p.H && w < p.W;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(acc * 2 * BLOCK_N + blk * BLOCK_N);
+            float head_acc = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                uint32_t v[32];
+                tc_ld32(taddr + (uint32_t)(c * 32), v);
+                if (valid)
+                    epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
+                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc);
+            }
+            if (valid && p.logits) p.logits[((long long)n * p.oH + h) * p.oW + w] = head_acc + p.head_b;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -853,6 +1040,18 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < sms ? total : sms;
+    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+template <int BLOCK_N, int A_STAGES, int B_STAGES>
+int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES>;
+    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES>;
+    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    const int pairs = (p.m_tiles + 1) / 2;
+    const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
     kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
@@ -983,7 +1182,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     }
     // 2D 3x3 stride-1 layers with a narrow N are L2-bound in the per-tap kernel: use the slab (halo-reuse) kernel
     const bool halo = !three_d && l->kind == NRRT_CONV_K3S1 && p.n_tiles == 1 && block_n <= 128 && !l->force_per_tap;
-    const bool pair = !halo && block_n >= 128 && l->force_per_tap != 2;  // CTA pairs (cta_group::2) for the per-tap kernel
+    const bool pair = l->force_per_tap != 2 && (halo || block_n >= 128);  // CTA pairs (cta_group::2)
     if (halo) {
         p.bw = 16; p.bh = 16; p.bd = 1; p.rows = 256;
         p.tiles_w = (p.W + 15) / 16; p.tiles_h = (p.H + 15) / 16; p.tiles_d = 1;
@@ -1023,6 +1222,10 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     int dev = 0, sms = 0;
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (halo && pair) {
+        if (block_n == 128) return launch_halo2<128, 4, 6>(ma, ma2, mb, p, sms, st);
+        return launch_halo2<64, 4, 8>(ma, ma2, mb, p, sms, st);
+    }
     if (halo) {
         if (block_n == 128) return launch_halo<128, 4, 4>(ma, ma2, mb, p, sms, st);
         return launch_halo<64, 4, 8>(ma, ma2, mb, p, sms, st);
