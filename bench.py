@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--ref-sample", type=int, default=None, help="tasks per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-every", type=int, default=16, help="time the conv launches of every n-th micro-batch")
+    ap.add_argument("--layer-table", default=None, help="write the per-layer CUDA-event timings of the sampled launches (csv)")
     return ap.parse_args()
 
 
@@ -286,8 +287,12 @@ def run_graft(args):
                         "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
                         "traffic": None, "peak_source": pk["which"], "launches_timed": n_l,
                         "avg_launch_ms": t_ms / max(n_l, 1), "flops_per_launch_avg": fl / max(n_l, 1),
-                        "step_share": {"cnn_ms": stage[0] / args.steps, "cdf_ms": stage[1] / args.steps,
-                                       "draw_plan_ms": stage[2] / args.steps}}
+                        "step_share": {"cnn_ms": stage[0], "cdf_ms": stage[1], "draw_plan_ms": stage[2]}}  # last timed step
+            if args.layer_table:
+                with open(args.layer_table, "w") as f:
+                    f.write("layer,launches,gflop_per_launch,ms_per_launch,tflops\n")
+                    for name, (n, fl_l, ms_l) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
+                        f.write(f"{name},{n},{fl_l / n / 1e9:.2f},{ms_l / n:.4f},{fl_l / max(ms_l, 1e-9) / 1e9:.1f}\n")
         else:
             roofline = {"bound": "hbm", "kernel": "plan_kernel", "achieved": None, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": None, "traffic": None, "peak_source": pk["which"],

@@ -180,6 +180,10 @@ typedef struct NrrtConvLayer {
     int32_t in_n, in2_n;
     const int32_t* in_index;
     const int32_t* in2_index;
+    /* Optional sample indirection of the residual (int32 [n]): sample b adds row res_index[b] of `res`.  The decoder's
+     * first conv of every stage is linear in torch.cat((up, enc)) (train.py:194-201), so the encoder-side partial sum is
+     * computed once per map and enters the per-task layer here, before the ReLU. */
+    const int32_t* res_index;
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);
@@ -215,6 +219,20 @@ int nrrt_coords_fill(const float* feat, int B, int gh, int gw, int C, int dims, 
  * E: fp32 [B][cases][4][Cout]. */
 int nrrt_coords_poly(const float* feat, int B, int Cc, const float* moments, int cases, int n_uv, int Cout, float a, float b,
                      float* E, void* stream);
+
+/* conv6.0 hoisted out of the per-task path (2D; train.py:192-195).  The layer is linear in its input and only the
+ * coordinate channels depend on the task, so its pre-activation = a per-map tensor (nrrt_conv_layer once per map) + a
+ * per-task piecewise-bilinear field with 16 cases (4 row classes x 4 column classes: first / interior even / interior
+ * odd / last) -- derivation in csrc/conv_aux.cu.
+ * nrrt_poly16: e_up fp32 [B][4][4][Cm] = nrrt_coords_poly output of the ConvTranspose (upconv6) whose result feeds the
+ *   conv; w_taps fp32 [Cm][9][Cout] = the conv's weight over the ConvTranspose channels (tap = ky*3+kx); e_conv fp32
+ *   [B][9][4][Cout] = nrrt_coords_poly output for the conv's own coordinate channels; bias fp32 [Cout];
+ *   (up_h, up_w) = ConvTranspose input grid; work: fp32 scratch [B*16*9*Cout]; P16: fp32 [B][16][4][Cout].
+ * nrrt_poly_relu: out[b] = fp16(relu(pre[pre_index[b]] + P16[b](pixel))) on an (H, W) grid, channels-last, C channels. */
+int nrrt_poly16(const float* e_up, const float* w_taps, const float* e_conv, const float* bias, int B, int Cm, int Cout,
+                int up_h, int up_w, float* work, float* P16, void* stream);
+int nrrt_poly_relu(const void* pre, const int32_t* pre_index, const float* P16, void* out, int B, int H, int W, int C,
+                   void* stream);
 
 /* Encoder reuse: the encoder (conv1 .. conv5) sees only the occupancy map, and the benchmark has 10 tasks per map, so it
  * runs once per distinct map; this copies channels [src_coffset, +C) of sample index[b] of a channels-last fp16 buffer

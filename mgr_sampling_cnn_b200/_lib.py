@@ -33,7 +33,8 @@ class NrrtConvLayer(C.Structure):
                 ("res_coffset", C.c_int64), ("relu", C.c_int32), ("post_scale", C.c_void_p), ("post_shift", C.c_void_p),
                 ("poly", C.c_void_p), ("poly_cases", C.c_int32), ("head_weight", C.c_void_p), ("head_bias", C.c_float),
                 ("logits", C.c_void_p), ("force_per_tap", C.c_int32), ("in2", C.c_void_p), ("in2_cstride", C.c_int64),
-                ("cin2", C.c_int32), ("in_n", C.c_int32), ("in2_n", C.c_int32), ("in_index", C.c_void_p), ("in2_index", C.c_void_p)]
+                ("cin2", C.c_int32), ("in_n", C.c_int32), ("in2_n", C.c_int32), ("in_index", C.c_void_p), ("in2_index", C.c_void_p),
+                ("res_index", C.c_void_p)]
 
 
 _SIGNATURES = {
@@ -62,6 +63,9 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "nrrt_coords_poly": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float,
                                    C.c_void_p, C.c_void_p]),
+    "nrrt_poly16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrrt_poly_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nrrt_gather_channels": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int64,
                                        C.c_void_p, C.c_int, C.c_void_p]),
     "nrrt_head_1x1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),

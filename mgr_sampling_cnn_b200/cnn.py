@@ -34,10 +34,11 @@ class ConvProfiler(object):
     def __init__(self):
         self.active = False
         self.records = []  # (flops, start_event, end_event)
+        self.names = []
 
     class _Ctx(object):
-        def __init__(self, prof, flops):
-            self.prof, self.flops = prof, flops
+        def __init__(self, prof, flops, name=None):
+            self.prof, self.flops, self.name = prof, flops, name
 
         def __enter__(self):
             self.a = torch.cuda.Event(enable_timing=True)
@@ -47,9 +48,18 @@ class ConvProfiler(object):
         def __exit__(self, *exc):
             self.b.record()
             self.prof.records.append((self.flops, self.a, self.b))
+            self.prof.names.append(self.name)
 
-    def launch(self, flops):
-        return ConvProfiler._Ctx(self, flops)
+    def launch(self, flops, name=None):
+        return ConvProfiler._Ctx(self, flops, name)
+
+    def by_layer(self):
+        """{layer name: (launches, flops, milliseconds)} of everything recorded so far; call after a synchronize."""
+        out = {}
+        for (f, a, b), name in zip(self.records, self.names):
+            n, fl, ms = out.get(name, (0, 0.0, 0.0))
+            out[name] = (n + 1, fl + f, ms + a.elapsed_time(b))
+        return out
 
     def totals(self):
         """(launches, total flops, total milliseconds) of everything recorded so far; call after a synchronize."""
@@ -115,21 +125,22 @@ class _Layer(object):
     force_per_tap = False  # tests: run the generic per-tap kernel where the slab kernel would be chosen
 
     def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None, head=None, x2=None,
-            idx=None, idx2=None, n=None):
+            idx=None, idx2=None, n=None, res_idx=None):
         """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W).
         head = (weight fp32 [cout], bias float, logits fp32 tensor): fuse the 1x1 output head, `out` may be None.
         x2: optional second input buffer (K split: channels [x: self.cin | x2: self.cin2]); idx / idx2: optional int32
-        [n] sample indirection of x / x2 (encoder outputs shared per map); n = number of output samples."""
+        [n] sample indirection of x / x2 (encoder outputs shared per map); n = number of output samples;
+        res_idx: optional int32 [n] sample indirection of the residual (per-map partial sums)."""
         n = n if n is not None else (idx.shape[0] if idx is not None else x.shape[0])
-        args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n)
+        args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx)
         prof = self.profiler
         if prof is not None and prof.active:
-            with prof.launch(self.flops(n, grid)):
+            with prof.launch(self.flops(n, grid), getattr(self, "name", None)):
                 self._run(*args)
         else:
             self._run(*args)
 
-    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n):
+    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx=None):
         _lib.count_launch()
         L = _lib.NrrtConvLayer()
         L.dims, L.kind = self.dims, self.kind
@@ -155,6 +166,8 @@ class _Layer(object):
         L.force_per_tap = 1 if self.force_per_tap else 0
         if res is not None:
             L.res, L.res_cstride, L.res_coffset = _ptr(res), res.shape[-1], res_coff
+            if res_idx is not None:
+                L.res_index = _ptr(res_idx)
         L.relu = 1 if self.relu else 0
         if self.post is not None:
             L.post_scale, L.post_shift = _ptr(self.post[0]), _ptr(self.post[1])
@@ -235,17 +248,18 @@ class UNetPlan(object):
         self.poly = d == 2
 
         def conv_split(m, c_up, c_enc, c_coords_in_gemm):
-            """3x3 decoder conv over torch.cat((up, enc, coords)): source 1 = the task's buffer [up | coords (3D only)],
-            source 2 = the encoder output of the task's map.  Input channels are permuted accordingly."""
+            """First 3x3 conv of a decoder stage over torch.cat((up, enc, coords)) (train.py:194-201).  The layer is linear
+            in its input channels up to the ReLU, so it is split into (per-task layer over [up | coords (3D only)] with
+            the bias and the ReLU, per-map layer over the encoder channels without bias or ReLU): the per-map partial sum
+            is computed once per map and enters the per-task layer as an (indexed) residual before the ReLU."""
             w = m.weight
             up, enc, crd = w[:, :c_up], w[:, c_up:c_up + c_enc], w[:, c_up + c_enc:]
-            parts = [up] + ([crd] if c_coords_in_gemm else []) + [enc]
-            wp = torch.cat(parts, dim=1)
+            wp = torch.cat([up] + ([crd] if c_coords_in_gemm else []), dim=1)
             scale, shift = _fold_bn(None, m.bias, m.out_channels, dev)
-            lay = _Layer(d, K3S1, wp.shape[1] - c_enc, m.out_channels, _pack_conv_weight(wp, wp.shape[1], dev), scale, shift,
-                         True, cin_real=wp.shape[1])
-            lay.cin2 = c_enc
-            return lay
+            task = _Layer(d, K3S1, wp.shape[1], m.out_channels, _pack_conv_weight(wp, wp.shape[1], dev), scale, shift, True)
+            one, zero = torch.ones_like(scale), torch.zeros_like(shift)
+            per_map = _Layer(d, K3S1, c_enc, m.out_channels, _pack_conv_weight(enc, c_enc, dev), one, zero, False)
+            return task, per_map
 
         def conv_moments(m, keep):
             """Tap moments of the coordinate slice: [9 border cases][uv = 00,10,01,11][Cc][Cout] fp32."""
@@ -267,19 +281,32 @@ class UNetPlan(object):
         scale = torch.ones(groups * mu.out_channels, dtype=torch.float32, device=dev)
         shift = mu.bias.detach().float().to(dev).repeat(groups).contiguous()
         if self.poly:
-            # upconv6 reads the encoder output x5 only; its coordinate rows become the polynomial moments
+            # upconv6 reads the encoder output x5 only (once per map); its coordinate rows become polynomial moments
             self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(mu.weight[:512], dev), scale, shift, False)
             self.m_up6 = mu.weight.detach().float().to(dev)[512:].permute(2, 3, 0, 1).reshape(4, 1, 512, mu.out_channels).contiguous()
             self.m_c6, self.m_c7, self.m_c8 = conv_moments(model.conv6[0], 768), conv_moments(model.conv7[0], 256), conv_moments(model.conv8[0], 128)
+            # conv6.0 is linear in (upconv6 output | x4 | coords): the whole GEMM runs once per map over (t6m | e4), the
+            # task-dependent part is the 16-case polynomial of nrrt_poly16 applied by nrrt_poly_relu (csrc/conv_aux.cu)
+            m6 = model.conv6[0]
+            w6 = m6.weight[:, :768]
+            one = torch.ones(m6.out_channels, dtype=torch.float32, device=dev)
+            self.c6full = _Layer(d, K3S1, 512, m6.out_channels, _pack_conv_weight(w6, 768, dev), one, torch.zeros_like(one), False,
+                                 cin_real=768)
+            self.c6full.cin2 = 256
+            self.w6taps = m6.weight.detach().float().to(dev)[:, :512].permute(1, 2, 3, 0).reshape(512, 9 * m6.out_channels).contiguous()
+            self.b6 = m6.bias.detach().float().to(dev).contiguous()
         else:
             # source 1 = x5 (per map), source 2 = the interpolated coordinate channels (per task)
             self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(mu.weight, dev), scale, shift, False)
             self.up6.cin2 = 512
             self.up6.cin_real = 1024
         self.up7, self.up8 = convT(model.upconv7), convT(model.upconv8)
-        self.c6 = (conv_split(model.conv6[0], 512, 256, not self.poly), conv(model.conv6[2], K3S1))
-        self.c7 = (conv_split(model.conv7[0], 128, 128, not self.poly), conv(model.conv7[2], K3S1))
-        self.c8 = (conv_split(model.conv8[0], 64, 64, not self.poly), conv(model.conv8[2], K3S1))
+        c60, self.c6e = (None, None) if self.poly else conv_split(model.conv6[0], 512, 256, True)
+        c70, self.c7e = conv_split(model.conv7[0], 128, 128, not self.poly)
+        c80, self.c8e = conv_split(model.conv8[0], 64, 64, not self.poly)
+        self.c6 = (c60, conv(model.conv6[2], K3S1))
+        self.c7 = (c70, conv(model.conv7[2], K3S1))
+        self.c8 = (c80, conv(model.conv8[2], K3S1))
         self.head_w = model.final_conv.weight.detach().float().to(dev).reshape(-1).contiguous()
         self.head_b = float(model.final_conv.bias.detach().float().item())
         self._bufs = {}
@@ -306,7 +333,10 @@ class UNetPlan(object):
             "t0": b(0, 64), "x1": b(0, 64), "a0": b(0, 64), "b0": b(0, 64), "e2": b(0, 64),
             "a1": b(1, 128), "b1": b(1, 128), "d1": b(1, 128), "e3": b(1, 128),
             "a2": b(2, 256), "b2": b(2, 256), "d2": b(2, 256), "e4": b(2, 256),
-            "a3": b(3, 512), "b3": b(3, 512), "d3": b(3, 512), "e5": b(3, 512)})
+            "a3": b(3, 512), "b3": b(3, 512), "d3": b(3, 512), "e5": b(3, 512),
+            # per-map partial sums of conv6.0 / conv7.0 / conv8.0 over the encoder channels (2D: all of conv6.0's GEMM,
+            # over t6m = upconv6(x5) and x4)
+            "r6": b(2, 512), "r7": b(1, 256), "r8": b(0, 128), "t6m": b(2, 512) if self.poly else None})
 
     def _dec_buffers(self, B, grid):
         b = lambda lv, ch: self._buf(B, grid, lv, ch)  # noqa: E731
@@ -315,18 +345,21 @@ class UNetPlan(object):
 
         def make():
             d = {"t8": b(0, t8w), "j": b(0, 128), "t7": b(1, t7w), "g7": b(1, 256), "i": b(1, 128),
-                 "t6": b(2, t6w), "g6": b(2, 512), "h": b(2, 256)}
+                 "g6": b(2, 512), "h": b(2, 256)}
             if not self.poly:
+                d["t6"] = b(2, t6w)
                 d["c5"] = b(3, 512)  # interpolated coordinate channels at the bottleneck (second input of upconv6)
             return d
         return self._cached(("dec", B) + tuple(grid), make)
 
     def activation_bytes(self, B, grid):
         b = list(self._enc_buffers(B, grid).values()) + list(self._dec_buffers(B, grid).values())
-        return sum(t.numel() * t.element_size() for t in b)
+        return sum(t.numel() * t.element_size() for t in b if t is not None)
 
     def layers(self):
         out = [self.stem2, self.up6, self.up7, self.up8] + list(self.c6) + list(self.c7) + list(self.c8)
+        out += [self.c6e, self.c7e, self.c8e] + ([self.c6full] if self.poly else [])
+        out = [l for l in out if l is not None]
         for stg in self.enc:
             for c1, c2, ds in stg:
                 out += [c1, c2] + ([ds] if ds is not None else [])
@@ -336,6 +369,18 @@ class UNetPlan(object):
         self.profiler = prof
         for l in self.layers():
             l.profiler = prof
+        for name in ("stem2", "up6", "up7", "up8", "c6e", "c7e", "c8e", "c6full"):
+            if getattr(self, name, None) is not None:
+                getattr(self, name).name = name
+        for name in ("c6", "c7", "c8"):
+            for i, l in enumerate(getattr(self, name)):
+                if l is not None:
+                    l.name = f"{name}.{i}"
+        for si, stg in enumerate(self.enc):
+            for bi, blk in enumerate(stg):
+                for li, l in enumerate(blk):
+                    if l is not None:
+                        l.name = f"enc{si + 2}.{bi}.{('c1', 'c2', 'ds')[li]}"
 
     def flops_per_sample(self, grid):
         """Algorithmic FLOPs of the tensor-core layers for one sample on input grid (D, H, W) (excludes the 3-/1-channel
@@ -349,9 +394,11 @@ class UNetPlan(object):
             tot += c1.flops(1, gin[s_i]) + c2.flops(1, gout) + c3.flops(1, gout) + c4.flops(1, gout)
             if ds is not None:
                 tot += ds.flops(1, gin[s_i])
-        tot += self.up6.flops(1, g[3]) + self.c6[0].flops(1, g[2]) + self.c6[1].flops(1, g[2])
+        c6_first = self.c6full if self.poly else self.c6[0]
+        tot += self.up6.flops(1, g[3]) + c6_first.flops(1, g[2]) + self.c6[1].flops(1, g[2])
         tot += self.up7.flops(1, g[2]) + self.c7[0].flops(1, g[1]) + self.c7[1].flops(1, g[1])
         tot += self.up8.flops(1, g[1]) + self.c8[0].flops(1, g[0]) + self.c8[1].flops(1, g[0])
+        tot += (0 if self.poly else self.c6e.flops(1, g[2])) + self.c7e.flops(1, g[1]) + self.c8e.flops(1, g[0])
         return tot
 
     def forward(self, x, coords, logits_out=None):
@@ -404,6 +451,18 @@ class UNetPlan(object):
                 _lib.count_launch()
                 check(self.lib.nrrt_coords_poly(_ptr(feat), B, cc, _ptr(mom), cases, n_uv, cout, a, b, _ptr(E), st))
                 prep[name] = E
+            # conv6.0's task-dependent term: 16-case polynomial from upconv6's and conv6.0's own coordinate channels
+            cout = self.b6.shape[0]
+            P16 = torch.empty((B, 16, 4, cout), dtype=torch.float32, device=dev)
+            chunk = 512
+            work = torch.empty((min(B, chunk) * 16 * 9 * cout,), dtype=torch.float32, device=dev)
+            for i in range(0, B, chunk):
+                j = min(B, i + chunk)
+                _lib.count_launch(2)
+                check(self.lib.nrrt_poly16(_ptr(prep["e_up6"][i:j]), _ptr(self.w6taps), _ptr(prep["e_c6"][i:j]), _ptr(self.b6),
+                                           j - i, 512, cout, g[3][1], g[3][2], _ptr(work), _ptr(P16[i:j]), st))
+            prep["p16"] = P16
+            del prep["e_up6"], prep["e_c6"]
         return prep
 
     @staticmethod
@@ -446,6 +505,14 @@ class UNetPlan(object):
         stage(self.enc[1], bf["e2"], g[0], g[1], bf["a1"], bf["b1"], bf["d1"], bf["e3"])
         stage(self.enc[2], bf["e3"], g[1], g[2], bf["a2"], bf["b2"], bf["d2"], bf["e4"])
         stage(self.enc[3], bf["e4"], g[2], g[3], bf["a3"], bf["b3"], bf["d3"], bf["e5"])
+        # encoder-side partial sums of the decoder's first convs (linear in torch.cat((up, enc)), train.py:194-201)
+        if self.poly:
+            self.up6.run(lib, st, bf["e5"], 0, g[3], bf["t6m"], 0)
+            self.c6full.run(lib, st, bf["t6m"], 0, g[2], bf["r6"], 0, x2=bf["e4"])
+        else:
+            self.c6e.run(lib, st, bf["e4"], 0, g[2], bf["r6"], 0)
+        self.c7e.run(lib, st, bf["e3"], 0, g[1], bf["r7"], 0)
+        self.c8e.run(lib, st, bf["e2"], 0, g[0], bf["r8"], 0)
         return bf
 
     def _forward(self, B, grid, coords, logits_out, x=None, occ=None, t2m=None, enc_index=None, prep=None):
@@ -460,7 +527,7 @@ class UNetPlan(object):
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         coords = coords.contiguous().float()
         bf = dict(self._dec_buffers(B, grid))
-        bf.update({k: enc[k] for k in ("e2", "e3", "e4", "e5")})
+        bf.update({k: enc[k] for k in ("e5", "r6", "r7", "r8")})
         g = self._levels(grid)
 
         # coordinate branch (train.py:179-190)
@@ -476,17 +543,20 @@ class UNetPlan(object):
 
         # decoder: every torch.cat of the reference is a K split over (task buffer, encoder output of the task's map)
         ei = enc_index  # None = one encoder sample per task
+        ri = ei  # None = one encoder sample per task (the residual of sample b is row b)
         if self.poly:
-            self.up6.run(lib, st, bf["e5"], 0, g[3], bf["t6"], 0, poly=prep.get("e_up6"), idx=ei, n=B)
+            _lib.count_launch()
+            check(lib.nrrt_poly_relu(_ptr(bf["r6"]), _ptr(ri), _ptr(prep["p16"]), _ptr(bf["g6"]), B, g[2][1], g[2][2],
+                                     bf["g6"].shape[-1], st))
         else:
             self.up6.run(lib, st, bf["e5"], 0, g[3], bf["t6"], 0, x2=bf["c5"], idx=ei, n=B)
-        self.c6[0].run(lib, st, bf["t6"], 0, g[2], bf["g6"], 0, poly=prep.get("e_c6"), x2=bf["e4"], idx2=ei)
+            self.c6[0].run(lib, st, bf["t6"], 0, g[2], bf["g6"], 0, bf["r6"], 0, res_idx=ri)
         self.c6[1].run(lib, st, bf["g6"], 0, g[2], bf["h"], 0)
         self.up7.run(lib, st, bf["h"], 0, g[2], bf["t7"], 0)
-        self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, poly=prep.get("e_c7"), x2=bf["e3"], idx2=ei)
+        self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, bf["r7"], 0, poly=prep.get("e_c7"), res_idx=ri)
         self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
         self.up8.run(lib, st, bf["i"], 0, g[1], bf["t8"], 0)
-        self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, poly=prep.get("e_c8"), x2=bf["e2"], idx2=ei)
+        self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8"), res_idx=ri)
 
         # conv8.2 + final_conv fused: the 64-channel activation is reduced to the logit in the epilogue
         logits = logits_out

@@ -276,6 +276,203 @@ __global__ void __launch_bounds__(256) gather_channels_kernel(const __half* __re
     }
 }
 
+
+// ---- conv6.0 hoisted out of the per-task path (2D) ------------------------------------------------------------------
+// conv6.0 is linear in torch.cat((upconv6(cat(x5, coords_x5)), x4, coords_x4)) (train.py:192-195), and only the
+// coordinate channels depend on the task.  Its pre-activation therefore splits into a per-MAP tensor (tensor cores, once
+// per map) plus a per-TASK field that is piecewise bilinear in the pixel position:
+//   (a) the interpolated coords_x4 channels: the 9-border-case polynomial of nrrt_coords_poly (basis ty = Y/(H-1), tx = X/(W-1));
+//   (b) conv6.0 over the coordinate part of upconv6's output.  That part is, per output parity g = (Y&1, X&1), bilinear
+//       in the ConvTranspose input position (s, t) = (i/(H3-1), j/(W3-1)), (i, j) = (Y>>1, X>>1): U_g = sum_k Eu[g][k] phi_k(s,t),
+//       phi = (1, s, t, st).  A 3x3 tap (dy, dx) of output pixel (Y, X) with parity (a, b) reads parity
+//       g' = ((a+dy)&1, (b+dx)&1) at (i + floor((a+dy)/2), j + floor((b+dx)/2)), so the tap sum is again bilinear, with
+//       coefficients that depend on (a, b) and on which taps fall inside the image: 4 row classes (Y = 0, interior even,
+//       interior odd, Y = H-1) x 4 column classes = 16 cases.
+// sgemm_kernel computes V[b][g][k][tap][co] = sum_c Eu[b][g][k][c] * Wtap[c][tap][co] in fp32 (the coordinate features are
+// O(100) and are never rounded to fp16); poly16_combine_kernel shifts/sums the taps per case, converts to the (ty, tx)
+// basis, adds (a) and the conv bias: P16[b][case][4][co].  poly_relu_kernel then forms the layer's activation
+// relu(pre[map] + P16(task)) for every task.
+constexpr int GM = 128, GN = 128, GK = 16;
+
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                    float* __restrict__ Cm, int M, int N, int K) {
+    __shared__ __align__(16) float sA[GK][GM + 4];  // A tile transposed: [k][m]
+    __shared__ __align__(16) float sB[GK][GN];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    // global -> register staging: A 128 rows x 16 k = 512 float4 (2 per thread), B 16 k x 128 n = 512 float4 (2 per thread)
+    float4 ra[2], rb[2];
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int idx = tid + q * 256;
+            const int row = idx >> 2, k4 = idx & 3;
+            ra[q] = (m0 + row < M) ? __ldg(reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * K + k0 + k4 * 4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int kr = idx >> 5, n4 = idx & 31;
+            rb[q] = __ldg(reinterpret_cast<const float4*>(Bm + (size_t)(k0 + kr) * N + n0 + n4 * 4));
+        }
+    };
+    load_tiles(0);
+    for (int k0 = 0; k0 < K; k0 += GK) {
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int idx = tid + q * 256;
+            const int row = idx >> 2, k4 = idx & 3;
+            sA[k4 * 4 + 0][row] = ra[q].x; sA[k4 * 4 + 1][row] = ra[q].y;
+            sA[k4 * 4 + 2][row] = ra[q].z; sA[k4 * 4 + 3][row] = ra[q].w;
+            const int kr = idx >> 5, n4 = idx & 31;
+            *reinterpret_cast<float4*>(&sB[kr][n4 * 4]) = rb[q];
+        }
+        __syncthreads();
+        if (k0 + GK < K) load_tiles(k0 + GK);
+#pragma unroll
+        for (int kk = 0; kk < GK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sA[kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sB[kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        if (row >= M) continue;
+        float* cp = Cm + (size_t)row * N + n0;
+        *reinterpret_cast<float4*>(cp + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        *reinterpret_cast<float4*>(cp + 64 + tx * 4) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+}
+
+// V: [B][4 g][4 k][9 tap][Cout];  e_conv: [B][9][4][Cout] (basis ty, tx of the conv's grid);  P16: [B][16][4][Cout].
+// a3 = 1/(H3-1), b3 = 1/(W3-1) of the ConvTranspose input grid; ly = (H-1)/(2(H3-1)), lx likewise: s = ly*ty - a*a3/2.
+__global__ void __launch_bounds__(128) poly16_combine_kernel(const float* __restrict__ V, const float* __restrict__ e_conv,
+                                                             const float* __restrict__ bias, int B, int Cout, float a3, float b3,
+                                                             float ly, float lx, float* __restrict__ P16) {
+    const int co = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (co >= Cout || b >= B) return;
+    float acc[16][4];
+#pragma unroll
+    for (int cs = 0; cs < 16; ++cs)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[cs][e] = 0.f;
+    const float* vb = V + (size_t)b * 16 * 9 * Cout + co;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int tap = (dy + 1) * 3 + (dx + 1);
+            float v[4][4];  // [g][k]
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[g][k] = __ldg(vb + ((size_t)(g * 4 + k) * 9 + tap) * Cout);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if ((r == 0 && dy < 0) || (r == 3 && dy > 0)) continue;
+                const int a = r >= 2 ? 1 : 0;
+                const int ap = (a + dy) & 1;
+                const int sy = (a + dy) < 0 ? -1 : ((a + dy) >> 1);  // floor((a+dy)/2)
+                const float my = a3 * ((float)sy - 0.5f * (float)a);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if ((c == 0 && dx < 0) || (c == 3 && dx > 0)) continue;
+                    const int bb = c >= 2 ? 1 : 0;
+                    const int bp = (bb + dx) & 1;
+                    const int sx = (bb + dx) < 0 ? -1 : ((bb + dx) >> 1);
+                    const float mx = b3 * ((float)sx - 0.5f * (float)bb);
+                    const int g = ap * 2 + bp;
+                    float* o = acc[r * 4 + c];
+                    o[0] += v[g][0] + my * v[g][1] + mx * v[g][2] + (my * mx) * v[g][3];
+                    o[1] += ly * (v[g][1] + mx * v[g][3]);
+                    o[2] += lx * (v[g][2] + my * v[g][3]);
+                    o[3] += (ly * lx) * v[g][3];
+                }
+            }
+        }
+    const float bi = __ldg(bias + co);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int c9 = (r == 0 ? 0 : (r == 3 ? 2 : 1)) * 3 + (c == 0 ? 0 : (c == 3 ? 2 : 1));
+            const float* ec = e_conv + (((size_t)b * 9 + c9) * 4) * Cout + co;
+            float* o = P16 + (((size_t)b * 16 + r * 4 + c) * 4) * Cout + co;
+            o[0] = acc[r * 4 + c][0] + __ldg(ec) + bi;
+            o[(size_t)Cout] = acc[r * 4 + c][1] + __ldg(ec + Cout);
+            o[(size_t)2 * Cout] = acc[r * 4 + c][2] + __ldg(ec + 2 * (size_t)Cout);
+            o[(size_t)3 * Cout] = acc[r * 4 + c][3] + __ldg(ec + 3 * (size_t)Cout);
+        }
+}
+
+// out[b][Y][X][:] = fp16(relu(pre[index[b]][Y][X][:] + P0 + ty*P1 + tx*P2 + ty*tx*P3)), P = P16[b][case(Y, X)].
+// One CTA per (row Y, task b): 256 threads = (C/8 channel groups) x pixel lanes; a lane walks X = lane, lane + lanes, ...
+// (lanes is even, so the column parity and hence the interior coefficient set of a thread is fixed and lives in registers).
+__global__ void __launch_bounds__(256) poly_relu_kernel(const __half* __restrict__ pre, const int32_t* __restrict__ index,
+                                                        const float* __restrict__ P16, __half* __restrict__ out, int H, int W,
+                                                        int C, float inv_h, float inv_w) {
+    const int cgs = C >> 3, lanes = 256 / cgs;
+    const int cg = threadIdx.x % cgs, lane = threadIdx.x / cgs;
+    const int Y = blockIdx.x, b = blockIdx.y;
+    const int r = Y == 0 ? 0 : (Y == H - 1 ? 3 : 1 + (Y & 1));
+    const float ty = (float)Y * inv_h;
+    const int src = index ? __ldg(index + b) : b;
+    const __half* prow = pre + (((size_t)src * H + Y) * W) * C + cg * 8;
+    __half* orow = out + (((size_t)b * H + Y) * W) * C + cg * 8;
+    const float* pb = P16 + ((size_t)b * 16 + r * 4) * 4 * C + cg * 8;
+    // row-reduced coefficients of a column class: value = A + tx * Bc
+    auto load_class = [&](int c, float (&A)[8], float (&Bc)[8]) {
+        const float* q = pb + (size_t)c * 4 * C;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4 p0 = __ldg(reinterpret_cast<const float4*>(q + h * 4));
+            const float4 p1 = __ldg(reinterpret_cast<const float4*>(q + C + h * 4));
+            const float4 p2 = __ldg(reinterpret_cast<const float4*>(q + 2 * C + h * 4));
+            const float4 p3 = __ldg(reinterpret_cast<const float4*>(q + 3 * C + h * 4));
+            A[h * 4 + 0] = fmaf(ty, p1.x, p0.x); A[h * 4 + 1] = fmaf(ty, p1.y, p0.y);
+            A[h * 4 + 2] = fmaf(ty, p1.z, p0.z); A[h * 4 + 3] = fmaf(ty, p1.w, p0.w);
+            Bc[h * 4 + 0] = fmaf(ty, p3.x, p2.x); Bc[h * 4 + 1] = fmaf(ty, p3.y, p2.y);
+            Bc[h * 4 + 2] = fmaf(ty, p3.z, p2.z); Bc[h * 4 + 3] = fmaf(ty, p3.w, p2.w);
+        }
+    };
+    float Ai[8], Bi[8];
+    load_class(1 + (lane & 1), Ai, Bi);
+    for (int X = lane; X < W; X += lanes) {
+        float Ae[8], Be[8];
+        const bool edge = X == 0 || X == W - 1;
+        if (edge) load_class(X == 0 ? 0 : 3, Ae, Be);
+        const float tx = (float)X * inv_w;
+        const uint4 pv = __ldg(reinterpret_cast<const uint4*>(prow + (size_t)X * C));
+        const __half2* ph = reinterpret_cast<const __half2*>(&pv);
+        uint4 ov;
+        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(ph[e]);
+            const float a0 = edge ? Ae[2 * e] : Ai[2 * e], a1 = edge ? Ae[2 * e + 1] : Ai[2 * e + 1];
+            const float b0 = edge ? Be[2 * e] : Bi[2 * e], b1 = edge ? Be[2 * e + 1] : Bi[2 * e + 1];
+            const float v0 = fminf(fmaxf(f.x + fmaf(tx, b0, a0), 0.f), 65504.f);
+            const float v1 = fminf(fmaxf(f.y + fmaf(tx, b1, a1), 0.f), 65504.f);
+            oh[e] = __floats2half2_rn(v0, v1);
+        }
+        *reinterpret_cast<uint4*>(orow + (size_t)X * C) = ov;
+    }
+}
+
 int grid_for(long long work, int block) {
     long long g = (work + block - 1) / block;
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -365,6 +562,36 @@ extern "C" int nrrt_head_1x1(const void* in, int64_t pixels, int C, int64_t in_c
     if (pixels == 0) return NRRT_OK;
     head_kernel<<<grid_for(pixels, 256), 256, C * sizeof(float), reinterpret_cast<cudaStream_t>(stream)>>>((const __half*)in, pixels, C,
                                                                                                            in_cstride, weight, bias, logits);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_poly16(const float* e_up, const float* w_taps, const float* e_conv, const float* bias, int B, int Cm,
+                           int Cout, int up_h, int up_w, float* work, float* P16, void* stream) {
+    NRRT_REQUIRE(e_up && w_taps && e_conv && bias && work && P16, "null pointer");
+    NRRT_REQUIRE(B >= 0 && Cm % 16 == 0 && Cout % 128 == 0 && up_h >= 2 && up_w >= 2, "bad poly16 shape");
+    if (B == 0) return NRRT_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int M = B * 16, N = 9 * Cout;
+    sgemm_kernel<<<dim3(N / GN, (M + GM - 1) / GM), 256, 0, st>>>(e_up, w_taps, work, M, N, Cm);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    const int H = 2 * up_h, W = 2 * up_w;
+    const float a3 = 1.0f / (float)(up_h - 1), b3 = 1.0f / (float)(up_w - 1);
+    const float ly = (float)(H - 1) / (2.0f * (float)(up_h - 1)), lx = (float)(W - 1) / (2.0f * (float)(up_w - 1));
+    poly16_combine_kernel<<<dim3((Cout + 127) / 128, B), 128, 0, st>>>(work, e_conv, bias, B, Cout, a3, b3, ly, lx, P16);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_poly_relu(const void* pre, const int32_t* pre_index, const float* P16, void* out, int B, int H, int W,
+                              int C, void* stream) {
+    NRRT_REQUIRE(pre && P16 && out, "null pointer");
+    NRRT_REQUIRE(B >= 0 && H >= 2 && W >= 2 && H % 2 == 0 && W % 2 == 0, "poly_relu needs an even grid (a ConvTranspose k2 s2 output)");
+    NRRT_REQUIRE(C % 8 == 0 && C / 8 <= 128 && 256 % (C / 8) == 0, "C/8 must divide 256 (got C = %d)", C);
+    NRRT_REQUIRE(((uintptr_t)pre & 15) == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)P16 & 15) == 0, "pointers must be 16-byte aligned");
+    if (B == 0) return NRRT_OK;
+    poly_relu_kernel<<<dim3(H, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        (const __half*)pre, pre_index, P16, (__half*)out, H, W, C, 1.0f / (float)(H - 1), 1.0f / (float)(W - 1));
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

@@ -53,6 +53,7 @@ struct ConvParams {
     const float* shift2;
     const __half* res;
     long long res_cstride, res_coffset;
+    const int32_t* res_idx;   // optional sample indirection of the residual (per-map partial sums shared by the tasks of a map)
     int relu;
     const float* poly;   // optional [N][poly_cases][4][cout]: bilinear epilogue term E0 + ty*E1 + tx*E2 + ty*tx*E3
     int poly_cases;      // 9 = 3x3 border cases (row case * 3 + column case); else one case per weight group
@@ -182,7 +183,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
         }
     }
     if (p.res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_cstride + p.res_coffset + co);
+        const long long rpix = p.res_idx ? (((long long)__ldg(p.res_idx + n) * p.oD + od) * p.oH + oh) * p.oW + ow : pix;
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.res_cstride + p.res_coffset + co);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const uint4 rv = __ldg(rp + q);
@@ -1162,6 +1164,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     p.scale2 = l->post_scale; p.shift2 = l->post_shift;
     NRRT_REQUIRE((l->post_scale == nullptr) == (l->post_shift == nullptr), "post_scale and post_shift go together");
     p.res = (const __half*)l->res; p.res_cstride = l->res_cstride; p.res_coffset = l->res_coffset;
+    p.res_idx = l->res ? l->res_index : nullptr;
     p.relu = l->relu;
     p.poly = l->poly;
     p.poly_cases = l->poly_cases;

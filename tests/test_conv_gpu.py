@@ -182,6 +182,62 @@ def test_k_split_two_sources_with_sample_index(cout, sp, cuda_device):
     _check(out, ref, 2, cout)
 
 
+def test_indexed_residual_before_relu(cuda_device):
+    """out = relu(conv(x) + res[index]): the per-map partial sum of a decoder conv enters the per-task layer as a residual."""
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn((5, 64, 24, 40), generator=g).to(dev)
+    res = torch.randn((2, 128, 24, 40), generator=g).to(dev)
+    index = torch.tensor([1, 0, 0, 1, 1], dtype=torch.int32, device=dev)
+    w = (torch.randn((128, 64, 3, 3), generator=g) / 24).to(dev)
+    scale, shift = torch.ones(128, device=dev), torch.randn(128, generator=g).to(dev)
+    layer = cnn._Layer(2, cnn.K3S1, 64, 128, cnn._pack_conv_weight(w, 64, dev), scale, shift.contiguous(), True)
+    out = torch.zeros((5, 1, 24, 40, 128), dtype=torch.float16, device=dev)
+    layer.run(_lib.load(), None, _cl(x), 0, (1, 24, 40), out, 0, _cl(res), 0, res_idx=index)
+    torch.cuda.synchronize()
+    _check(out, _ref(2, cnn.K3S1, x, w, scale, shift, True, res[index.long()]), 2, 128)
+
+
+def test_poly16_matches_conv_over_the_coordinate_field(cuda_device):
+    """nrrt_poly16 + nrrt_poly_relu against the definition: a 3x3 conv over (ConvTranspose polynomial field | bilinear
+    coordinate channels) evaluated densely with torch in fp64, added to an indexed per-map pre-activation, ReLU."""
+    import ctypes as C
+    dev = cuda_device
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(9)
+    B, Cm, Cout, H3, W3 = 3, 32, 128, 6, 10
+    H, W = 2 * H3, 2 * W3
+    e_up = torch.randn((B, 4, 4, Cm), generator=g).to(dev)            # ConvTranspose polynomial per output offset
+    e_conv = torch.randn((B, 9, 4, Cout), generator=g).to(dev)        # the conv's own coordinate polynomial (9 border cases)
+    w = (torch.randn((Cout, Cm, 3, 3), generator=g) / 17).to(dev)
+    bias = torch.randn(Cout, generator=g).to(dev)
+    pre = torch.randn((2, H, W, Cout), generator=g).to(dev).half()
+    index = torch.tensor([1, 0, 1], dtype=torch.int32, device=dev)
+    w_taps = w.permute(1, 2, 3, 0).reshape(Cm, 9 * Cout).contiguous()
+    work = torch.empty(B * 16 * 9 * Cout, dtype=torch.float32, device=dev)
+    P16 = torch.empty((B, 16, 4, Cout), dtype=torch.float32, device=dev)
+    out = torch.empty((B, H, W, Cout), dtype=torch.float16, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(lib.nrrt_poly16(p(e_up), p(w_taps), p(e_conv), p(bias), B, Cm, Cout, H3, W3, p(work), p(P16), None))
+    _lib.check(lib.nrrt_poly_relu(p(pre), p(index), p(P16), p(out), B, H, W, Cout, None))
+    torch.cuda.synchronize()
+    # dense definition in fp64
+    Y, X = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    s, t = (Y >> 1).double() / (H3 - 1), (X >> 1).double() / (W3 - 1)
+    grp = ((Y & 1) * 2 + (X & 1)).long()
+    eu = e_up.double()[:, grp]                                         # [B, H, W, 4, Cm]
+    U = eu[..., 0, :] + s[..., None] * eu[..., 1, :] + t[..., None] * eu[..., 2, :] + (s * t)[..., None] * eu[..., 3, :]
+    q = F.conv2d(U.permute(0, 3, 1, 2), w.double(), padding=1).permute(0, 2, 3, 1)
+    ty, tx = Y.double() / (H - 1), X.double() / (W - 1)
+    rc = torch.where(Y == 0, 0, torch.where(Y == H - 1, 2, 1))
+    cc = torch.where(X == 0, 0, torch.where(X == W - 1, 2, 1))
+    ec = e_conv.double()[:, (rc * 3 + cc).long()]                      # [B, H, W, 4, Cout]
+    poly = ec[..., 0, :] + ty[..., None] * ec[..., 1, :] + tx[..., None] * ec[..., 2, :] + (ty * tx)[..., None] * ec[..., 3, :]
+    ref = torch.relu(pre.double()[index.long()] + q + poly + bias.double())
+    err = (out.double() - ref).abs().max().item()
+    assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), f"max abs err {err}"
+
+
 @pytest.mark.parametrize("three_d", [False, True])
 @pytest.mark.parametrize("bn", [False, True])
 def test_unet_forward_matches_reference_golden(three_d, bn, cuda_device):
