@@ -184,6 +184,7 @@ typedef struct NrrtConvLayer {
      * first conv of every stage is linear in torch.cat((up, enc)) (train.py:194-201), so the encoder-side partial sum is
      * computed once per map and enters the per-task layer here, before the ReLU. */
     const int32_t* res_index;
+    int32_t res_n;           /* samples in the residual buffer (0 = n) */
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);

@@ -166,6 +166,7 @@ class _Layer(object):
         L.force_per_tap = 1 if self.force_per_tap else 0
         if res is not None:
             L.res, L.res_cstride, L.res_coffset = _ptr(res), res.shape[-1], res_coff
+            L.res_n = res.shape[0]
             if res_idx is not None:
                 L.res_index = _ptr(res_idx)
         L.relu = 1 if self.relu else 0

@@ -146,9 +146,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int m = kBlockM) {
 // Epilogue of 32 accumulator columns of one output pixel: folded-BN scale/shift, polynomial coordinate term, residual,
 // ReLU, optional second affine + ReLU, then either the fp16 store into the output channel slice or (fused 1x1 head) a
 // running dot product with the head weights.  col = first GEMM column, lc = its offset inside the staged scale/shift.
+// res_row (pair kernels): this pixel's 128-byte row of the TMA-staged residual piece holding columns [lc & ~63, +64)
+// (SWIZZLE_128B: 16-byte piece j of row r sits at j ^ (r & 7)); nullptr = read the residual from global memory.
 __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[32], int col, int lc, int n, int d,
                                                int h, int w, const float* sc, const float* sh, const float* sc2,
-                                               const float* sh2, const float* pe, int pe_stride, float& head_acc) {
+                                               const float* sh2, const float* pe, int pe_stride, float& head_acc,
+                                               const uint8_t* res_row = nullptr, int res_r7 = 0) {
     const int g = col / p.cout, co = col - g * p.cout;
     int od = d, oh = h, ow = w;
     if (p.up == 2) {
@@ -183,11 +186,12 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
         }
     }
     if (p.res) {
-        const long long rpix = p.res_idx ? (((long long)__ldg(p.res_idx + n) * p.oD + od) * p.oH + oh) * p.oW + ow : pix;
+        const long long rpix = (res_row || !p.res_idx) ? pix : (((long long)__ldg(p.res_idx + n) * p.oD + od) * p.oH + oh) * p.oW + ow;
         const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.res_cstride + p.res_coffset + co);
+        const int j0 = (lc & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint4 rv = __ldg(rp + q);
+            const uint4 rv = res_row ? *reinterpret_cast<const uint4*>(res_row + (((j0 + q) ^ res_r7) << 4)) : __ldg(rp + q);
             const __half2* hv = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -457,17 +461,21 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar)
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar)
         : "memory");
 }
 
-template <int BLOCK_N, int STAGES>
+constexpr int kMaxResPieces = 4;       // 64-channel pieces of a residual tile (BLOCK_N <= 256)
+constexpr uint32_t kResPiece = 16384;  // 128 pixel rows x 128 B (SWIZZLE_128B), 1024-byte aligned
+
+template <int BLOCK_N, int STAGES, bool RES>
 struct SmemLayout2 {  // per CTA of a pair: its own A tile and HALF of the B tile per stage
     static constexpr uint32_t a_stage = kBlockM * 128;
     static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
     static constexpr uint32_t off_b = STAGES * a_stage;
-    static constexpr uint32_t off_bar = off_b + STAGES * b_stage;
-    static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4) * 8;
+    static constexpr uint32_t off_res = off_b + STAGES * b_stage;  // TMA-staged residual tile: BLOCK_N / 64 pieces
+    static constexpr uint32_t off_bar = off_res + (RES ? (BLOCK_N / 64) * kResPiece : 0);
+    static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4 + 2 * kMaxResPieces) * 8;
     static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
     static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
 };
@@ -478,11 +486,16 @@ struct SmemLayout2 {  // per CTA of a pair: its own A tile and HALF of the B til
 // memory), cutting operand bytes per SM from 4 KB + 32N to 4 KB + 16N per K=16 step.  Both CTAs run a TMA producer (own A
 // tile + own B half, all signalling the leader's barrier) and the epilogue; only the leader issues MMAs and its commits
 // are multicast to the barriers of both CTAs.
-template <int BLOCK_N, int STAGES>
+// RES: the residual tile (this CTA's 128 pixels x BLOCK_N channels, fp16) is staged in shared memory by the producer's
+// TMA in 64-channel pieces, each with a full/empty barrier pair, so the epilogue never waits on a global load: the piece
+// of tile i+1 is requested as soon as every epilogue warp has consumed that piece of tile i.
+template <int BLOCK_N, int STAGES, bool RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
-                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ ConvParams p) {
-    using L = SmemLayout2<BLOCK_N, STAGES>;
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ ConvParams p) {
+    using L = SmemLayout2<BLOCK_N, STAGES, RES>;
+    constexpr int RP = BLOCK_N / 64;  // residual pieces
     constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -492,6 +505,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+    auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
+    auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + kMaxResPieces + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
     float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
 
@@ -505,6 +520,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         // the leader's tempty barrier collects the epilogue warps of BOTH CTAs
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+        if (RES) for (int s = 0; s < RP; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kEpiWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -523,7 +539,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0;
-            uint32_t phase = 0;
+            uint32_t phase = 0, rphase = 0;
             for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
                 const int n_tile = pt % p.n_tiles;
                 int m = (pt / p.n_tiles) * 2 + (int)rank;
@@ -551,6 +567,17 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                      n_tile * BLOCK_N + (int)rank * (BLOCK_N / 2));
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
+                }
+                if (RES) {
+                    // residual of this tile (own CTA, own barriers), issued behind the tile's operand loads
+                    const int nr = !live ? 0x3fffffff : (p.res_idx ? __ldg(p.res_idx + n) : n);
+                    for (int s = 0; s < RP; ++s) {
+                        mbar_wait(rempty_bar(s), rphase ^ 1u);
+                        mbar_expect_tx(rfull_bar(s), p.a_bytes);
+                        tma_load_5d(base + L::off_res + s * kResPiece, &map_r, rfull_bar(s),
+                                    (int)p.res_coffset + n_tile * BLOCK_N + s * 64, tw * p.bw, th * p.bh, td * p.bd, nr);
+                    }
+                    rphase ^= 1u;
                 }
             }
             // drain: the leader's multicast commits must not land in a CTA that already exited
@@ -591,7 +618,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int row = sub * 32 + lane;
         const int et = threadIdx.x - 64;  // 0..255
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, rphase = 0;
         int last_ntile[2] = {-1, -1}, last_n[2] = {-1, -1};
         for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
             const int n_tile = pt % p.n_tiles;
@@ -621,12 +648,22 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 for (int c = c_begin; c < BLOCK_N / 32; c += c_step) {
                     uint32_t v[32];
                     tc_ld32(taddr + (uint32_t)(c * 32), v);
+                    const uint8_t* rrow = nullptr;
+                    if (RES) {  // every warp touches each 64-channel piece exactly once (c_step == 2: no fused head with RES)
+                        mbar_wait(rfull_bar(c >> 1), rphase);
+                        rrow = base_ptr + L::off_res + (c >> 1) * kResPiece + row * 128;
+                    }
                     if (valid)
                         epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
-                                       sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc);
+                                       sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7);
+                    if (RES) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(rempty_bar(c >> 1));
+                    }
                 }
                 if (valid && p.logits) p.logits[(((long long)n * p.oD + d) * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             }
+            if (RES) rphase ^= 1u;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty_bar(acc));  // the leader's MMA thread waits for both CTAs' epilogues
@@ -832,24 +869,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 
-template <int BLOCK_N, int A_STAGES, int B_STAGES>
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES>
 struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
     static constexpr uint32_t a_stage = 2 * kSlabBytes;
     static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
     static constexpr uint32_t off_b = A_STAGES * a_stage;
-    static constexpr uint32_t off_bar = off_b + B_STAGES * b_stage;
-    static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4) * 8;
+    static constexpr uint32_t off_res = off_b + B_STAGES * b_stage;  // residual pieces [column block][64-channel chunk]
+    static constexpr uint32_t off_bar = off_res + (RES ? 2 * (BLOCK_N / 64) * kResPiece : 0);
+    static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4 + 2 * kMaxResPieces) * 8;
     static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
     static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
 };
 
 // conv_halo2_kernel — the slab kernel on CTA pairs (cta_group::2): the pair owns two adjacent 16x16 tiles, every MMA is
 // M256 = column block `blk` of both CTAs, and each CTA loads (and feeds from its shared memory) only half of each B tile.
-template <int BLOCK_N, int A_STAGES, int B_STAGES>
+// RES: TMA-staged residual tile as in conv_gemm2_kernel; a piece = (column block, 64-channel chunk) = 128 pixels x 128 B.
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
-                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ ConvParams p) {
-    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES>;
+                 const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_r,
+                 const __grid_constant__ ConvParams p) {
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES>;
+    constexpr int RC = BLOCK_N / 64;  // 64-channel chunks per column block; residual pieces = 2 * RC
     constexpr int TMEM_COLS = 4 * BLOCK_N;  // 2 accumulator stages x 2 column blocks
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -861,6 +902,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto bempty = [&](int s) { return bar0 + 8u * (2 * A_STAGES + B_STAGES + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + s); };
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 2 + s); };
+    auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + s); };
+    auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + kMaxResPieces + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
     float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
 
@@ -873,6 +916,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+        if (RES) for (int s = 0; s < 2 * RC; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kEpiWarps / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -891,7 +935,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // ===== TMA producer: same (chunk, dx, dy) order as the MMA issuer consumes =====
         if (lane == 0) {
             int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
+            uint32_t pa = 0, pb = 0, rphase = 0;
             for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
                 int m = pt * 2 + (int)rank;
                 const bool live = m < p.m_tiles;
@@ -921,6 +965,16 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
                         }
                     }
+                }
+                if (RES) {
+                    const int nr = !live ? 0x3fffffff : (p.res_idx ? __ldg(p.res_idx + n) : n);
+                    for (int s = 0; s < 2 * RC; ++s) {
+                        mbar_wait(rempty_bar(s), rphase ^ 1u);
+                        mbar_expect_tx(rfull_bar(s), kResPiece);
+                        tma_load_5d(base + L::off_res + s * kResPiece, &map_r, rfull_bar(s),
+                                    (int)p.res_coffset + (s % RC) * 64, w0 + (s / RC) * 8, h0, 0, nr);
+                    }
+                    rphase ^= 1u;
                 }
             }
             // drain both rings: multicast commits of the leader must not land in a CTA that already exited
@@ -975,7 +1029,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int row = sub * 32 + lane;  // row of a column block: (h_l, w_l) = (row / 8, row % 8)
         const int et = threadIdx.x - 64;
         int acc = 0;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, rphase = 0;
         int last_n[2] = {-1, -1};
         for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
             int m = pt * 2 + (int)rank;
@@ -997,10 +1051,21 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 uint32_t v[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), v);
+                const int piece = blk * RC + (c >> 1);
+                const uint8_t* rrow = nullptr;
+                if (RES) {
+                    if (!(c & 1)) mbar_wait(rfull_bar(piece), rphase);
+                    rrow = base_ptr + L::off_res + piece * kResPiece + row * 128;
+                }
                 if (valid)
                     epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
-                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc);
+                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7);
+                if (RES && (c & 1)) {  // both 32-column halves of the piece are consumed
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(rempty_bar(piece));
+                }
             }
+            if (RES) rphase ^= 1u;
             if (valid && p.logits) p.logits[((long long)n * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             tc_fence_before();
             __syncwarp();
@@ -1047,26 +1112,30 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap
     return NRRT_OK;
 }
 
-template <int BLOCK_N, int A_STAGES, int B_STAGES>
-int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
-    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES>;
-    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES>;
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES>
+int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const ConvParams& p,
+                 int sms, cudaStream_t st) {
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES>;
+    static_assert(L::total <= 232448, "shared memory budget");
+    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int pairs = (p.m_tiles + 1) / 2;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
-    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
+    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, p);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }
 
-template <int BLOCK_N, int STAGES>
-int launch_conv2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
-    using L = SmemLayout2<BLOCK_N, STAGES>;
-    auto kern = conv_gemm2_kernel<BLOCK_N, STAGES>;
+template <int BLOCK_N, int STAGES, bool RES>
+int launch_conv2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const ConvParams& p,
+                 int sms, cudaStream_t st) {
+    using L = SmemLayout2<BLOCK_N, STAGES, RES>;
+    static_assert(L::total <= 232448, "shared memory budget");
+    auto kern = conv_gemm2_kernel<BLOCK_N, STAGES, RES>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);  // whole CTA pairs (static cluster dims 2x1x1)
-    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
+    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, p);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }
@@ -1222,20 +1291,44 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
     }
+    // pair kernels stage the residual tile through shared memory with TMA (output grid, 64-channel pieces)
+    const bool tma_res = pair && l->res && up == 1 && !l->logits && l->cout % 64 == 0 && l->res_coffset % 64 == 0;
+    CUtensorMap mr = ma;
+    if (tma_res) {
+        const int rn = l->res_n > 0 ? l->res_n : N;
+        const cuuint64_t gdim[5] = {(cuuint64_t)l->res_cstride, (cuuint64_t)p.oW, (cuuint64_t)p.oH, (cuuint64_t)p.oD, (cuuint64_t)rn};
+        const cuuint64_t cs = (cuuint64_t)l->res_cstride * 2;
+        const cuuint64_t gstr[4] = {cs, cs * p.oW, cs * p.oW * p.oH, cs * p.oW * p.oH * p.oD};
+        cuuint32_t box[5] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
+        if (halo) { box[1] = 8; box[2] = 16; box[3] = 1; }  // one column block of the 16x16 tile
+        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        const CUresult r = encode(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(l->res), gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(residual) failed: %d", (int)r);
+    }
     int dev = 0, sms = 0;
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (halo && pair) {
-        if (block_n == 128) return launch_halo2<128, 4, 6>(ma, ma2, mb, p, sms, st);
-        return launch_halo2<64, 4, 8>(ma, ma2, mb, p, sms, st);
+        if (tma_res) {
+            if (block_n == 128) return launch_halo2<128, 3, 5, true>(ma, ma2, mb, mr, p, sms, st);
+            return launch_halo2<64, 4, 8, true>(ma, ma2, mb, mr, p, sms, st);
+        }
+        if (block_n == 128) return launch_halo2<128, 4, 6, false>(ma, ma2, mb, mr, p, sms, st);
+        return launch_halo2<64, 4, 8, false>(ma, ma2, mb, mr, p, sms, st);
     }
     if (halo) {
         if (block_n == 128) return launch_halo<128, 4, 4>(ma, ma2, mb, p, sms, st);
         return launch_halo<64, 4, 8>(ma, ma2, mb, p, sms, st);
     }
     if (pair) {
-        if (block_n == 256) return launch_conv2<256, 6>(ma, ma2, mb, p, sms, st);
-        return launch_conv2<128, 8>(ma, ma2, mb, p, sms, st);
+        if (tma_res) {
+            if (block_n == 256) return launch_conv2<256, 4, true>(ma, ma2, mb, mr, p, sms, st);
+            return launch_conv2<128, 6, true>(ma, ma2, mb, mr, p, sms, st);
+        }
+        if (block_n == 256) return launch_conv2<256, 6, false>(ma, ma2, mb, mr, p, sms, st);
+        return launch_conv2<128, 8, false>(ma, ma2, mb, mr, p, sms, st);
     }
     if (block_n == 256) return launch_conv<256, 4>(ma, ma2, mb, p, sms, st);
     if (block_n == 128) return launch_conv<128, 6>(ma, ma2, mb, p, sms, st);

@@ -1,0 +1,61 @@
+"""Scratch: one encoder pass (8 maps) + decoder micro-batches (10 tasks) of the 2D CNN at 512x512, for ncu captures
+and CUDA-event timing of individual layers.  Not the bench contract.
+
+    python scripts/conv_probe.py [n_decode]     prints the per-layer event timings of the last decode
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from mgr_sampling_cnn_b200 import cnn, train, workload  # noqa: E402
+
+dev = torch.device("cuda:0")
+n_dec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+wl = workload.make_2d(80)
+torch.manual_seed(0)
+model = train.UNet_cooler().eval().to(dev)
+plan = model._plan(dev)
+prof = cnn.ConvProfiler()
+plan.set_profiler(prof)
+occ = torch.from_numpy(wl.occ_maps).to(dev)
+coords = torch.from_numpy(wl.coords).to(dev)
+grid = (1, 512, 512)
+maps = torch.arange(8, dtype=torch.int32, device=dev)
+prep = plan.coords_prepare(coords, grid)
+enc = plan.encode(grid, 8, occ=occ, maps=maps)
+logits = torch.empty((10, 512 * 512), dtype=torch.float32, device=dev)
+for it in range(n_dec):
+    prof.active = it == n_dec - 1
+    m = it % 8
+    rel = torch.full((10,), m, dtype=torch.int32, device=dev)
+    plan.decode(enc, 10, grid, coords[m * 10:(m + 1) * 10], plan.slice_prep(prep, m * 10, (m + 1) * 10), rel, logits)
+torch.cuda.synchronize()
+for name, (n, fl, ms) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
+    print(f"{name:10s} {ms / n:8.4f} ms  {fl / max(ms, 1e-9) / 1e9:8.1f} TFLOP/s")
+
+# epilogue cost decomposition of conv8.0 / conv7.0 (timing only: the variants without poly / residual are not the layer)
+import ctypes as C  # noqa: E402
+lib = plan.lib
+st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+bf = dict(plan._dec_buffers(10, grid))
+bf.update({k: enc[k] for k in ("r7", "r8")})
+g = plan._levels(grid)
+pr = plan.slice_prep(prep, 0, 10)
+rel = torch.zeros(10, dtype=torch.int32, device=dev)
+plan.set_profiler(None)
+for name, layer, x, lv, out, res, poly in (("c8.0", plan.c8[0], bf["t8"], 0, bf["j"], bf["r8"], pr["e_c8"]),
+                                           ("c7.0", plan.c7[0], bf["t7"], 1, bf["g7"], bf["r7"], pr["e_c7"])):
+    for tag, kw in (("poly+res", dict(res=res, poly=poly, res_idx=rel)), ("res", dict(res=res, res_idx=rel)),
+                    ("poly", dict(poly=poly)), ("plain", dict())):
+        ts = []
+        for _ in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            layer.run(lib, st, x, 0, g[lv], out, 0, kw.get("res"), 0, poly=kw.get("poly"), res_idx=kw.get("res_idx"))
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        print(f"{name} {tag:9s} {min(ts):.4f} ms")
