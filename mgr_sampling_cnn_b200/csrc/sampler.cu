@@ -75,153 +75,335 @@ __device__ __forceinline__ float block_reduce_min(float v, float* red, bool is_m
     return r;
 }
 
-// One CTA per task: min/max, then NumPy's pairwise sum of w = h - m with the exact tree: leaves of <= 128 elements with
-// 8 strided accumulators (8 lanes per leaf, lane k owns accumulator k, so a warp reads four 32-byte sectors per load and
-// the 8-way combine ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is three xor-shuffles), then the binary combine tree laid out
-// by the host in `ops`.  The task's row is read from HBM once (min pass) and from L2 afterwards.
-__global__ void __launch_bounds__(256) cdf_stats_kernel(const float* __restrict__ logits, int mode, int64_t cells,
-                                                        const LeafOp* __restrict__ leaves, int n_leaves,
-                                                        const LeafOp* __restrict__ ops, const int32_t* __restrict__ level_off,
-                                                        int n_levels, float4* __restrict__ stats) {
+// ---- exact parallel emulation of the sequential fp32 cumsum ---------------------------------------------------------
+// np.cumsum is a strictly serial chain c_j = fl32(c_{j-1} + p_j) and fp32 addition is not associative, so a plain
+// parallel scan gives different roundings.  But while c stays inside one binade [2^e, 2^(e+1)) it is an integer multiple
+// K * u of u = ulp(c), K in [2^23, 2^24), and for p >= 0 round-to-nearest-even of c + p is integer arithmetic:
+//     q = p / u (exact),  a = floor(q),  f = q - a:      K' = K + a + (f > 1/2)          if f != 1/2
+//                                                        K' = K + a + ((K + a) & 1)       if f == 1/2 (tie -> even)
+// so every element is a function K -> K + d[K & 1] described by the pair (d[0], d[1]) (equal unless the element is a
+// tie), and these functions compose associatively: (f then g)[b] = f[b] + g[(b + f[b]) & 1].  A block-wide scan of the
+// pairs therefore reproduces the serial chain bit for bit as long as K stays below 2^24.  The first element that leaves
+// the binade is found with a block-wide min, evaluated with one real __fadd_rn, and the scan restarts behind it in the new
+// binade (about 25 restarts per 2^18-cell map: c doubles that many times on its way from p_0 to ~1).  c = 0 and
+// subnormal c are the same case with u = 2^-149.  Windows holding a NaN/Inf/negative weight (degenerate heat maps:
+// S = 0 makes every p NaN) fall back to a serial loop on one thread.
+constexpr int kFT = 1024;        // threads per CTA (one task per CTA at a time)
+constexpr int kFV = 8;           // consecutive cells per thread per window
+constexpr int kFW = kFT * kFV;   // cells per window
+constexpr uint32_t kSat = 1u << 26;  // anything >= 2^24 means "left the binade"; saturate so sums never wrap
+
+struct Pair2 {
+    uint32_t d0, d1;
+};
+// correctly rounded w / S (see the Markstein note in cdf_fused_kernel); operands outside the safe range take __fdiv_rn
+__device__ __forceinline__ float div_by(float w, float S, float rS, bool fastdiv) {
+    if (w == 0.f && fastdiv) return 0.f;
+    if (fastdiv && w >= 0x1p-60f && w <= 0x1p60f) {
+        const float q = __fmul_rn(w, rS);
+        const float r = __fmaf_rn(-q, S, w);
+        return __fmaf_rn(r, rS, q);
+    }
+    return __fdiv_rn(w, S);
+}
+__device__ __forceinline__ Pair2 pair_then(const Pair2 f, const Pair2 g) {  // apply f, then g
+    Pair2 r;
+    r.d0 = min(f.d0 + ((f.d0 & 1u) ? g.d1 : g.d0), kSat);
+    r.d1 = min(f.d1 + (((f.d1 + 1u) & 1u) ? g.d1 : g.d0), kSat);
+    return r;
+}
+// the pair of one weight p >= 0 (finite): q = p * 2^(150 - ec) for a running sum with biased exponent field ec (>= 1; 1
+// also covers 0 and subnormals).  The scale is applied as two exact power-of-two factors (2^149 is not a float); the
+// float -> integer conversion saturates, so huge q simply read as "leaves the binade".
+__device__ __forceinline__ void delta_of(float p, float scale_a, float scale_b, uint32_t& delta, bool& tie) {
+    const float q = __fmul_rn(__fmul_rn(p, scale_a), scale_b);  // exact (power-of-two scaling) unless it over/underflows
+    const uint32_t ai = min(__float2uint_rd(q), kSat);          // floor(q), saturated
+    const float f = __fsub_rn(q, (float)ai);                    // exact fraction while q < 2^24 (beyond that: don't care)
+    delta = ai + (f > 0.5f ? 1u : 0u);                          // round half down here; ties are patched by the caller
+    tie = f == 0.5f;
+}
+__device__ __forceinline__ Pair2 pair_of(float p, float scale_a, float scale_b) {
+    uint32_t d;
+    bool tie;
+    delta_of(p, scale_a, scale_b, d, tie);
+    Pair2 r;
+    r.d0 = d + ((tie && (d & 1u)) ? 1u : 0u);   // K even: K + a is odd iff a is odd -> round up to even
+    r.d1 = d + ((tie && !(d & 1u)) ? 1u : 0u);  // K odd
+    return r;
+}
+
+// One CTA per task (persistent over tasks, grid = #SMs so the rows being worked on stay L2-resident between phases):
+//   A. min/max of the raw logits (3D) and min of the heat values                           [row read from HBM]
+//   B. NumPy's pairwise sum of w = h - m with the exact tree: leaves of <= 128 elements with 8 strided accumulators
+//      (8 lanes per leaf, the 8-way combine ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is three xor-shuffles), then the binary
+//      combine tree laid out by the host in `ops`                                           [row read from L2]
+//   C. the exact parallel cumsum above over windows of 8192 cells, CDF written with streaming stores  [row read from L2]
+__global__ void __launch_bounds__(kFT, 1) cdf_fused_kernel(const float* __restrict__ logits, int mode, int B, int64_t cells,
+                                                           const LeafOp* __restrict__ leaves, int n_leaves,
+                                                           const LeafOp* __restrict__ ops, const int32_t* __restrict__ level_off,
+                                                           int n_levels, float4* __restrict__ stats, float* __restrict__ cdf) {
     extern __shared__ float leaf_sum[];  // [n_leaves]
     __shared__ float red[32];
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const float* x = logits + (size_t)b * cells;
-    const bool vec = (cells % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    __shared__ Pair2 wtot[32];
+    __shared__ float s_c;
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* x = logits + (size_t)b * cells;
+        float* out = cdf + (size_t)b * cells;
+        float vmin_s = 0.f, vmax_s = 0.f, m_s = 0.f, S_s = 1.f;  // the task's statistics, as the serial fallback sees them
+        const bool vec = (cells % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        // the reference's arithmetic, serially on one thread (NaN/Inf propagate exactly as in NumPy)
+        auto serial = [&](int64_t from, int64_t to, float c) {
+            for (int64_t j = from; j < to; ++j) {
+                const float pj = __fdiv_rn(__fsub_rn(heat_value(__ldg(x + j), mode, vmin_s, vmax_s), m_s), S_s);
+                c = j == 0 ? pj : __fadd_rn(c, pj);
+                out[j] = c;
+            }
+            return c;
+        };
 
-    float vmin = 0.f, vmax = 0.f;
-    if (mode == 1) {
-        float lo = INFINITY, hi = -INFINITY;
+        // ---- A ----
+        float vmin = 0.f, vmax = 0.f;
+        if (mode == 1) {
+            float lo = INFINITY, hi = -INFINITY;
+            if (vec) {
+                for (int64_t j = tid; j < cells / 4; j += blockDim.x) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + j);
+                    lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
+                    hi = fmaxf(fmaxf(hi, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                }
+            } else {
+                for (int64_t j = tid; j < cells; j += blockDim.x) { const float v = __ldg(x + j); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+            }
+            vmin = block_reduce_min(lo, red, false);
+            vmax = block_reduce_min(hi, red, true);
+        }
+        float m = INFINITY;
         if (vec) {
             for (int64_t j = tid; j < cells / 4; j += blockDim.x) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(x) + j);
-                lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
-                hi = fmaxf(fmaxf(hi, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                m = fminf(fminf(m, fminf(heat_value(v.x, mode, vmin, vmax), heat_value(v.y, mode, vmin, vmax))),
+                          fminf(heat_value(v.z, mode, vmin, vmax), heat_value(v.w, mode, vmin, vmax)));
             }
         } else {
-            for (int64_t j = tid; j < cells; j += blockDim.x) { const float v = __ldg(x + j); lo = fminf(lo, v); hi = fmaxf(hi, v); }
+            for (int64_t j = tid; j < cells; j += blockDim.x) m = fminf(m, heat_value(__ldg(x + j), mode, vmin, vmax));
         }
-        vmin = block_reduce_min(lo, red, false);
-        vmax = block_reduce_min(hi, red, true);
-    }
-    float m = INFINITY;
-    if (vec) {
-        for (int64_t j = tid; j < cells / 4; j += blockDim.x) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(x) + j);
-            m = fminf(fminf(m, fminf(heat_value(v.x, mode, vmin, vmax), heat_value(v.y, mode, vmin, vmax))),
-                      fminf(heat_value(v.z, mode, vmin, vmax), heat_value(v.w, mode, vmin, vmax)));
-        }
-    } else {
-        for (int64_t j = tid; j < cells; j += blockDim.x) m = fminf(m, heat_value(__ldg(x + j), mode, vmin, vmax));
-    }
-    m = block_reduce_min(m, red, false);
+        m = block_reduce_min(m, red, false);
 
-    const int k = tid & 7;
-    for (int l0 = 0; l0 < n_leaves; l0 += blockDim.x / 8) {
-        const int l = l0 + (tid >> 3);
-        const bool on = l < n_leaves;
-        const int off = on ? leaves[l].a : 0, len = on ? leaves[l].b : 0;
-        const float* a = x + off;
-        // every lane reaches the three shuffles at the same program point (leaves of one warp may differ in length)
-        float r = 0.f;
-        int i = 0;
-        if (len >= 8) {
-            r = __fsub_rn(heat_value(__ldg(a + k), mode, vmin, vmax), m);
-            for (i = 8; i < len - (len % 8); i += 8) r = __fadd_rn(r, __fsub_rn(heat_value(__ldg(a + i + k), mode, vmin, vmax), m));
-        }
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
-        float res = r;
-        if (len >= 8) {
-            for (; i < len; ++i) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + i), mode, vmin, vmax), m));
-        } else if (len > 0) {  // n < 8: plain left-to-right sum
-            res = __fsub_rn(heat_value(__ldg(a), mode, vmin, vmax), m);
-            for (int q = 1; q < len; ++q) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + q), mode, vmin, vmax), m));
-        }
-        if (on && k == 0) leaf_sum[l] = res;
-    }
-    __syncthreads();
-    for (int lv = 0; lv < n_levels; ++lv) {  // deepest level first; left child's slot accumulates
-        const int lo = level_off[lv], hi = level_off[lv + 1];
-        for (int o = lo + tid; o < hi; o += blockDim.x) leaf_sum[ops[o].a] = __fadd_rn(leaf_sum[ops[o].a], leaf_sum[ops[o].b]);
-        __syncthreads();
-    }
-    if (tid == 0) stats[b] = make_float4(vmin, vmax, m, leaf_sum[0]);
-}
-
-// Sequential fp32 cumsum with NumPy's rounding (fp32 addition is not associative, so every task's running sum is a
-// strictly serial chain).  One CTA = 32 tasks x 4 warps.  Per chunk of 128 cells: all warps turn the raw logits they
-// prefetched into p = fl32(w / S) and park them in a [32 tasks][128] shared tile (coalesced loads, conflict-free
-// transposed tile); warp 0 carries the 32 running sums through the tile, one task per lane; all warps stream the tile
-// back out coalesced.  The global loads of chunk i+1 are issued before the chain of chunk i, so HBM latency is hidden.
-constexpr int kChainCols = 128;
-constexpr int kChainPitch = kChainCols + 1;
-
-__global__ void __launch_bounds__(128) cdf_chain_kernel(const float* __restrict__ logits, int mode, int B, int64_t cells,
-                                                        const float4* __restrict__ stats, float* __restrict__ cdf) {
-    __shared__ float tile[32 * kChainPitch];
-    __shared__ float4 s_stats[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int b0 = blockIdx.x * 32;
-    const int rows = min(32, B - b0);
-    if (threadIdx.x < 32) s_stats[threadIdx.x] = threadIdx.x < rows ? __ldg(stats + b0 + threadIdx.x) : make_float4(0, 0, 0, 1);
-    __syncthreads();
-    float raw[8][4];   // this thread's 8 task rows (warp*8 ..) x 4 column groups of the current chunk
-    auto load_chunk = [&](int64_t c0) {
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-            const int r = warp * 8 + rr;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int64_t c = c0 + lane + 32 * e;
-                raw[rr][e] = (r < rows && c < cells) ? __ldg(logits + (size_t)(b0 + r) * cells + c) : 0.f;
+        // ---- B ----
+        const int k = tid & 7;
+        for (int l0 = 0; l0 < n_leaves; l0 += blockDim.x / 8) {
+            const int l = l0 + (tid >> 3);
+            const bool on = l < n_leaves;
+            const int off = on ? leaves[l].a : 0, len = on ? leaves[l].b : 0;
+            const float* a = x + off;
+            // every lane reaches the three shuffles at the same program point (leaves of one warp may differ in length)
+            float r = 0.f;
+            int i = 0;
+            if (len >= 8) {
+                r = __fsub_rn(heat_value(__ldg(a + k), mode, vmin, vmax), m);
+                for (i = 8; i < len - (len % 8); i += 8) r = __fadd_rn(r, __fsub_rn(heat_value(__ldg(a + i + k), mode, vmin, vmax), m));
             }
-        }
-    };
-    load_chunk(0);
-    float acc = 0.f;
-    bool first = true;
-    for (int64_t c0 = 0; c0 < cells; c0 += kChainCols) {
-#pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-            const int r = warp * 8 + rr;
-            const float4 st = s_stats[r];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float h = heat_value(raw[rr][e], mode, st.x, st.y);
-                tile[r * kChainPitch + lane + 32 * e] = __fdiv_rn(__fsub_rn(h, st.z), st.w);
+            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+            float res = r;
+            if (len >= 8) {
+                for (; i < len; ++i) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + i), mode, vmin, vmax), m));
+            } else if (len > 0) {  // n < 8: plain left-to-right sum
+                res = __fsub_rn(heat_value(__ldg(a), mode, vmin, vmax), m);
+                for (int q = 1; q < len; ++q) res = __fadd_rn(res, __fsub_rn(heat_value(__ldg(a + q), mode, vmin, vmax), m));
             }
-        }
-        if (c0 + kChainCols < cells) load_chunk(c0 + kChainCols);
-        __syncthreads();
-        if (warp == 0 && lane < rows) {
-            const int nc = (int)min((int64_t)kChainCols, cells - c0);
-            float* row = tile + lane * kChainPitch;
-            int q = 0;
-            if (first && nc > 0) { acc = row[0]; q = 1; first = false; }
-            for (; q + 8 <= nc; q += 8) {
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = row[q + e];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { acc = __fadd_rn(acc, v[e]); v[e] = acc; }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) row[q + e] = v[e];
-            }
-            for (; q < nc; ++q) { acc = __fadd_rn(acc, row[q]); row[q] = acc; }
+            if (on && k == 0) leaf_sum[l] = res;
         }
         __syncthreads();
+        for (int lv = 0; lv < n_levels; ++lv) {  // deepest level first; left child's slot accumulates
+            const int lo = level_off[lv], hi = level_off[lv + 1];
+            for (int o = lo + tid; o < hi; o += blockDim.x) leaf_sum[ops[o].a] = __fadd_rn(leaf_sum[ops[o].a], leaf_sum[ops[o].b]);
+            __syncthreads();
+        }
+        const float S = leaf_sum[0];
+        vmin_s = vmin; vmax_s = vmax; m_s = m; S_s = S;
+        // Markstein: with rS = RN(1/S), q = RN(w*rS), r = w - q*S (exact FMA), RN(q + r*rS) is the correctly rounded w / S
+        // unless S's significand is all ones or something leaves the normal range; those cases use __fdiv_rn
+        const float rS = __frcp_rn(S);
+        const bool fastdiv = S >= 0x1p-60f && S <= 0x1p60f && (__float_as_uint(S) & 0x7fffffu) != 0x7fffffu;
+        if (tid == 0) {
+            if (stats) stats[b] = make_float4(vmin, vmax, m, S);
+            s_c = 0.f;
+        }
+        __syncthreads();
+
+        // ---- C ----
+        for (int64_t w0 = 0; w0 < cells; w0 += kFW) {
+            const int64_t wend = min(cells, w0 + (int64_t)kFW);
+            const int64_t idx0 = w0 + (int64_t)tid * kFV;
+            float p[kFV];
+            if (vec && idx0 + kFV <= cells) {
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-            const int r = warp * 8 + rr;
-            if (r < rows) {
+                for (int h = 0; h < kFV / 4; ++h) {
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(x + idx0) + h);
+                    p[4 * h + 0] = v.x; p[4 * h + 1] = v.y; p[4 * h + 2] = v.z; p[4 * h + 3] = v.w;
+                }
+            } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int64_t c = c0 + lane + 32 * e;
-                    if (c < cells) cdf[(size_t)(b0 + r) * cells + c] = tile[r * kChainPitch + lane + 32 * e];
+                for (int v = 0; v < kFV; ++v) p[v] = idx0 + v < cells ? __ldg(x + idx0 + v) : 0.f;
+            }
+            bool odd = false;
+#pragma unroll
+            for (int v = 0; v < kFV; ++v) {
+                p[v] = div_by(__fsub_rn(heat_value(p[v], mode, vmin, vmax), m), S, rS, fastdiv);
+                if (idx0 + v < cells) odd |= !(p[v] >= 0.f && p[v] < INFINITY);
+            }
+            float c = s_c;
+            if (__syncthreads_or(odd || !(c >= 0.f && c < INFINITY))) {
+                if (tid == 0) s_c = serial(w0, wend, c);  // degenerate window
+                __syncthreads();
+                continue;
+            }
+            int64_t start = w0;
+            for (;;) {
+                const uint32_t cb = __float_as_uint(c);
+                const uint32_t bec = cb >> 23;
+                const uint32_t ec = bec ? bec : 1u;
+                const uint32_t K0 = (cb & 0x7fffffu) | (bec ? 0x800000u : 0u);
+                // 2^(150 - ec) = 2^ea * 2^eb, both factors normal floats
+                const int sh = 150 - (int)ec;            // -104 .. 149
+                const int ea = sh / 2, eb = sh - ea;
+                const float scale_a = __uint_as_float((uint32_t)(ea + 127) << 23), scale_b = __uint_as_float((uint32_t)(eb + 127) << 23);
+                if (tid == 0) s_bad = 0x7fffffff;
+                // per-cell deltas; ties (fraction exactly 1/2, about 2^-17 of the cells) make the thread take the pair path
+                uint32_t dl[kFV];
+                bool any_tie = false;
+                const bool live = idx0 + kFV > start && idx0 < wend;  // warp-uniform for all but one warp
+                uint32_t sum = 0;
+                if (live) {
+#pragma unroll
+                    for (int v = 0; v < kFV; ++v) {
+                        const int64_t idx = idx0 + v;
+                        bool tie;
+                        delta_of(p[v], scale_a, scale_b, dl[v], tie);
+                        if (!(idx >= start && idx < wend)) { dl[v] = 0; tie = false; }
+                        any_tie |= tie;
+                        sum = min(sum + dl[v], kSat);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < kFV; ++v) dl[v] = 0;
+                }
+                Pair2 agg = {sum, sum};
+                if (any_tie) {
+                    agg = Pair2{0u, 0u};
+#pragma unroll
+                    for (int v = 0; v < kFV; ++v) {
+                        const int64_t idx = idx0 + v;
+                        const Pair2 ev = (idx >= start && idx < wend) ? pair_of(p[v], scale_a, scale_b) : Pair2{0u, 0u};
+                        agg = pair_then(agg, ev);
+                    }
+                }
+                Pair2 inc = agg;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    Pair2 t;
+                    t.d0 = __shfl_up_sync(0xffffffffu, inc.d0, o);
+                    t.d1 = __shfl_up_sync(0xffffffffu, inc.d1, o);
+                    if (lane >= o) inc = pair_then(t, inc);
+                }
+                Pair2 ex;
+                ex.d0 = __shfl_up_sync(0xffffffffu, inc.d0, 1);
+                ex.d1 = __shfl_up_sync(0xffffffffu, inc.d1, 1);
+                if (lane == 0) ex = Pair2{0u, 0u};
+                if (lane == 31) wtot[warp] = inc;
+                __syncthreads();
+                if (warp == 0) {
+                    Pair2 t = wtot[lane];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        Pair2 u;
+                        u.d0 = __shfl_up_sync(0xffffffffu, t.d0, o);
+                        u.d1 = __shfl_up_sync(0xffffffffu, t.d1, o);
+                        if (lane >= o) t = pair_then(u, t);
+                    }
+                    Pair2 te;
+                    te.d0 = __shfl_up_sync(0xffffffffu, t.d0, 1);
+                    te.d1 = __shfl_up_sync(0xffffffffu, t.d1, 1);
+                    if (lane == 0) te = Pair2{0u, 0u};
+                    wtot[lane] = te;  // exclusive prefix of the warp totals
+                }
+                __syncthreads();
+                const Pair2 pre = pair_then(wtot[warp], ex);
+                uint32_t K = min(K0 + ((K0 & 1u) ? pre.d1 : pre.d0), kSat);
+                uint32_t Kout[kFV];
+                int bad = 0x7fffffff, bad_v = 0;
+                uint32_t K_before_bad = 0;
+                const uint32_t K_in = K;
+                if (!any_tie) {
+#pragma unroll
+                    for (int v = 0; v < kFV; ++v) { K = min(K + dl[v], kSat); Kout[v] = K; }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < kFV; ++v) {
+                        const int64_t idx = idx0 + v;
+                        const Pair2 ev = (idx >= start && idx < wend) ? pair_of(p[v], scale_a, scale_b) : Pair2{0u, 0u};
+                        K = min(K + ((K & 1u) ? ev.d1 : ev.d0), kSat);
+                        Kout[v] = K;
+                    }
+                }
+                if (live && K >= (1u << 24)) {  // K is monotone: only then can a cell of this thread have left the binade
+                    uint32_t Kp = K_in;
+#pragma unroll
+                    for (int v = 0; v < kFV; ++v) {
+                        const int64_t idx = idx0 + v;
+                        if (idx >= start && idx < wend && Kout[v] >= (1u << 24) && bad == 0x7fffffff) {
+                            bad = (int)(idx - w0); bad_v = v; K_before_bad = Kp;
+                        }
+                        Kp = Kout[v];
+                    }
+                }
+                int wbad = bad;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) wbad = min(wbad, __shfl_xor_sync(0xffffffffu, wbad, o));
+                if (lane == 0 && wbad != 0x7fffffff) atomicMin(&s_bad, wbad);
+                __syncthreads();
+                const int gbad = s_bad;  // window-relative index of the first element that leaves the binade
+                const int64_t stop = gbad == 0x7fffffff ? wend : w0 + gbad;
+                // finished elements [start, stop)
+                auto value_of = [&](uint32_t Kv) { return __uint_as_float(Kv >= 0x800000u ? ((ec << 23) | (Kv & 0x7fffffu)) : Kv); };
+                if (vec && idx0 >= start && idx0 + kFV <= stop) {
+#pragma unroll
+                    for (int h = 0; h < kFV / 4; ++h)
+                        __stcs(reinterpret_cast<float4*>(out + idx0) + h,
+                               make_float4(value_of(Kout[4 * h]), value_of(Kout[4 * h + 1]), value_of(Kout[4 * h + 2]), value_of(Kout[4 * h + 3])));
+                } else {
+#pragma unroll
+                    for (int v = 0; v < kFV; ++v)
+                        if (idx0 + v >= start && idx0 + v < stop) out[idx0 + v] = value_of(Kout[v]);
+                }
+                if (gbad == 0x7fffffff) {
+                    // the thread that owns the window's last cell publishes the running sum
+                    if (wend - 1 >= idx0 && wend - 1 < idx0 + kFV && wend - 1 >= start) s_c = value_of(Kout[(int)(wend - 1 - idx0)]);
+                    __syncthreads();
+                    break;
+                }
+                if (bad == gbad) {  // owner: one real fp32 addition carries the sum into its new binade
+                    float pb = 0.f;
+#pragma unroll
+                    for (int v = 0; v < kFV; ++v) if (v == bad_v) pb = p[v];
+                    const float cn = __fadd_rn(value_of(K_before_bad), pb);
+                    out[w0 + gbad] = cn;
+                    s_c = cn;
+                }
+                __syncthreads();
+                c = s_c;
+                start = w0 + gbad + 1;
+                if (start >= wend) break;
+                if (!(c < INFINITY)) {  // the sum overflowed: finish the window serially, later windows take the serial path
+                    if (tid == 0) s_c = serial(start, wend, c);
+                    break;
                 }
             }
+            __syncthreads();
         }
         __syncthreads();
     }
@@ -433,11 +615,12 @@ extern "C" int nrrt_cdf_build(const float* logits, int mode, int B, int64_t cell
 
     const size_t smem = t.leaves.size() * sizeof(float);
     NRRT_REQUIRE(smem <= 200 * 1024, "map too large for the leaf-sum buffer");
-    NRRT_CUDA_TRY(cudaFuncSetAttribute(cdf_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cdf_stats_kernel<<<B, 256, smem, st>>>(logits, mode, cells, d_leaves, (int)t.leaves.size(), d_ops, d_level,
-                                           (int)level_off.size() - 1, stats);
-    NRRT_CUDA_TRY(cudaGetLastError());
-    cdf_chain_kernel<<<(B + 31) / 32, 128, 0, st>>>(logits, mode, B, cells, stats, cdf);
+    NRRT_CUDA_TRY(cudaFuncSetAttribute(cdf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0;
+    NRRT_CUDA_TRY(cudaGetDevice(&dev));
+    NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cdf_fused_kernel<<<B < sms ? B : sms, kFT, smem, st>>>(logits, mode, B, cells, d_leaves, (int)t.leaves.size(), d_ops, d_level,
+                                                         (int)level_off.size() - 1, stats, cdf);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

@@ -106,7 +106,7 @@ def build_cdf(logits, mode: int, device=None, out: Optional[torch.Tensor] = None
     ws_bytes = lib.nrrt_cdf_workspace_bytes(B, cells)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
     cdf = torch.empty((B, cells), dtype=torch.float32, device=device) if out is None else out
-    _lib.count_launch(2)
+    _lib.count_launch()
     check(lib.nrrt_cdf_build(_ptr(x), mode, B, cells, _ptr(cdf), _ptr(ws), ws_bytes, _stream_ptr(device)))
     return cdf
 
