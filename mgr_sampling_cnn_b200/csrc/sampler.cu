@@ -409,6 +409,389 @@ __global__ void __launch_bounds__(kFT, 1) cdf_fused_kernel(const float* __restri
     }
 }
 
+// ---- cdf_stream_kernel: the same three phases as cdf_fused_kernel, fed by a bulk-copy (TMA) pipeline ------------------
+// The fused kernel above exposes a global-load latency per window.  Here warp 0 is a producer: one thread streams the
+// task's row through a ring of kStages x 32 KB shared-memory stages with cp.async.bulk (1-D TMA) + mbarrier complete_tx,
+// once per phase ([min/max,] min, pairwise sum, cumsum).  The order of the copies does not depend on any result, so the
+// producer runs ahead across windows, phases and tasks and the 16 consumer warps never wait on HBM/L2 latency.  A chunk
+// is a run of whole pairwise-sum leaves (<= 8192 cells), so every phase uses the same chunking and leaves never
+// straddle a stage.  Needs cells % 4 == 0 and 16-byte aligned rows (bulk-copy alignment); other shapes use cdf_fused_kernel.
+constexpr int kSC = 512;                 // consumer threads
+constexpr int kSV = 16;                  // cells per consumer thread per chunk
+constexpr int kChunk = kSC * kSV;        // 8192 cells = 32 KB per stage
+constexpr int kStages = 5;
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void sbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void sbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "SW_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SW_DONE;\n\t"
+        "bra SW_LOOP;\n\t"
+        "SW_DONE:\n\t}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kSC) : "memory"); }
+
+// min (or max) over the 512 consumer threads; every consumer thread gets the result
+__device__ __forceinline__ float consumer_reduce(float v, float* red, bool is_max, int ct) {
+    const int lane = ct & 31, warp = ct >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float t = __shfl_xor_sync(0xffffffffu, v, o);
+        v = is_max ? fmaxf(v, t) : fminf(v, t);
+    }
+    consumer_sync();
+    if (lane == 0) red[warp] = v;
+    consumer_sync();
+    float r = red[0];
+#pragma unroll
+    for (int w = 1; w < kSC / 32; ++w) r = is_max ? fmaxf(r, red[w]) : fminf(r, red[w]);
+    return r;
+}
+
+__global__ void __launch_bounds__(kSC + 32, 1) cdf_stream_kernel(const float* __restrict__ logits, int mode, int B, int64_t cells,
+                                                                 const LeafOp* __restrict__ leaves, int n_leaves,
+                                                                 const LeafOp* __restrict__ ops,
+                                                                 const int32_t* __restrict__ level_off, int n_levels,
+                                                                 const int32_t* __restrict__ chunk_leaf, int n_chunks,
+                                                                 float4* __restrict__ stats, float* __restrict__ cdf) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    float* ring = reinterpret_cast<float*>(smem_raw);                      // [kStages][kChunk]
+    float* leaf_sum = ring + kStages * kChunk;                              // [n_leaves]
+    __shared__ uint64_t bars[2 * kStages];
+    __shared__ float red[kSC / 32];
+    __shared__ Pair2 wtot[kSC / 32];
+    __shared__ float s_c;
+    __shared__ int s_bad;
+    const uint32_t bar0 = s_u32(bars);
+    auto full = [&](int st) { return bar0 + 8u * st; };
+    auto empty = [&](int st) { return bar0 + 8u * (kStages + st); };
+    const int n_phases = mode == 1 ? 4 : 3;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStages; ++i) { sbar_init(full(i), 1); sbar_init(empty(i), kSC / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x < 32) {
+        // ===== producer =====
+        if (threadIdx.x == 0) {
+            int st = 0;
+            uint32_t ph = 0;
+            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+                const float* x = logits + (size_t)b * cells;
+                for (int phase = 0; phase < n_phases; ++phase)
+                    for (int c = 0; c < n_chunks; ++c) {
+                        const int off = __ldg(&leaves[__ldg(chunk_leaf + c)].a);
+                        const int end = c + 1 < n_chunks ? __ldg(&leaves[__ldg(chunk_leaf + c + 1)].a) : (int)cells;
+                        const uint32_t bytes = (uint32_t)(end - off) * 4u;
+                        sbar_wait(empty(st), ph ^ 1u);
+                        sbar_expect_tx(full(st), bytes);
+                        bulk_load(s_u32(ring + st * kChunk), x + off, bytes, full(st));
+                        if (++st == kStages) { st = 0; ph ^= 1u; }
+                    }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int ct = threadIdx.x - 32, lane = ct & 31, warp = ct >> 5;
+    int st = 0;
+    uint32_t ph = 0;
+    auto release = [&]() {
+        __syncwarp();
+        if (lane == 0) sbar_arrive(empty(st));
+        if (++st == kStages) { st = 0; ph ^= 1u; }
+    };
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* x = logits + (size_t)b * cells;
+        float* out = cdf + (size_t)b * cells;
+        float vmin = 0.f, vmax = 0.f;
+        // ---- min / max of the raw logits (3D normalisation) ----
+        if (mode == 1) {
+            float lo = INFINITY, hi = -INFINITY;
+            for (int c = 0; c < n_chunks; ++c) {
+                const int off = __ldg(&leaves[__ldg(chunk_leaf + c)].a);
+                const int end = c + 1 < n_chunks ? __ldg(&leaves[__ldg(chunk_leaf + c + 1)].a) : (int)cells;
+                sbar_wait(full(st), ph);
+                const float4* src = reinterpret_cast<const float4*>(ring + st * kChunk);
+                for (int j = ct; j < (end - off) / 4; j += kSC) {
+                    const float4 v = src[j];
+                    lo = fminf(fminf(lo, fminf(v.x, v.y)), fminf(v.z, v.w));
+                    hi = fmaxf(fmaxf(hi, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                }
+                release();
+            }
+            vmin = consumer_reduce(lo, red, false, ct);
+            vmax = consumer_reduce(hi, red, true, ct);
+        }
+        // ---- A: min of the heat values ----
+        float m = INFINITY;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int off = __ldg(&leaves[__ldg(chunk_leaf + c)].a);
+            const int end = c + 1 < n_chunks ? __ldg(&leaves[__ldg(chunk_leaf + c + 1)].a) : (int)cells;
+            sbar_wait(full(st), ph);
+            const float4* src = reinterpret_cast<const float4*>(ring + st * kChunk);
+            for (int j = ct; j < (end - off) / 4; j += kSC) {
+                const float4 v = src[j];
+                m = fminf(fminf(m, fminf(heat_value(v.x, mode, vmin, vmax), heat_value(v.y, mode, vmin, vmax))),
+                          fminf(heat_value(v.z, mode, vmin, vmax), heat_value(v.w, mode, vmin, vmax)));
+            }
+            release();
+        }
+        m = consumer_reduce(m, red, false, ct);
+        // ---- B: NumPy's pairwise sum (same leaf code as cdf_fused_kernel, operands in shared memory) ----
+        const int k = ct & 7;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int l_begin = __ldg(chunk_leaf + c), l_end = c + 1 < n_chunks ? __ldg(chunk_leaf + c + 1) : n_leaves;
+            const int off0 = __ldg(&leaves[l_begin].a);
+            sbar_wait(full(st), ph);
+            const float* src = ring + st * kChunk;
+            for (int l0 = l_begin; l0 < l_end; l0 += kSC / 8) {
+                const int l = l0 + (ct >> 3);
+                const bool on = l < l_end;
+                const int off = on ? __ldg(&leaves[l].a) - off0 : 0, len = on ? __ldg(&leaves[l].b) : 0;
+                const float* a = src + off;
+                float r = 0.f;
+                int i = 0;
+                if (len >= 8) {
+                    r = __fsub_rn(heat_value(a[k], mode, vmin, vmax), m);
+                    for (i = 8; i < len - (len % 8); i += 8) r = __fadd_rn(r, __fsub_rn(heat_value(a[i + k], mode, vmin, vmax), m));
+                }
+                r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));
+                r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));
+                r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));
+                float res = r;
+                if (len >= 8) {
+                    for (; i < len; ++i) res = __fadd_rn(res, __fsub_rn(heat_value(a[i], mode, vmin, vmax), m));
+                } else if (len > 0) {
+                    res = __fsub_rn(heat_value(a[0], mode, vmin, vmax), m);
+                    for (int q = 1; q < len; ++q) res = __fadd_rn(res, __fsub_rn(heat_value(a[q], mode, vmin, vmax), m));
+                }
+                if (on && k == 0) leaf_sum[l] = res;
+            }
+            release();
+        }
+        consumer_sync();
+        for (int lv = 0; lv < n_levels; ++lv) {
+            const int lo = level_off[lv], hi = level_off[lv + 1];
+            for (int o = lo + ct; o < hi; o += kSC) leaf_sum[ops[o].a] = __fadd_rn(leaf_sum[ops[o].a], leaf_sum[ops[o].b]);
+            consumer_sync();
+        }
+        const float S = leaf_sum[0];
+        const float rS = __frcp_rn(S);
+        const bool fastdiv = S >= 0x1p-60f && S <= 0x1p60f && (__float_as_uint(S) & 0x7fffffu) != 0x7fffffu;
+        const bool regular = S > 0.f && S < INFINITY && fabsf(m) < INFINITY;  // else: NumPy's NaN/Inf arithmetic, serially
+        if (ct == 0) {
+            if (stats) stats[b] = make_float4(vmin, vmax, m, S);
+            s_c = 0.f;
+        }
+        consumer_sync();  // also: every thread has read leaf_sum[0] before the next task overwrites it
+
+        // ---- C: exact parallel cumsum, one chunk = one window ----
+        for (int c = 0; c < n_chunks; ++c) {
+            const int off = __ldg(&leaves[__ldg(chunk_leaf + c)].a);
+            const int end = c + 1 < n_chunks ? __ldg(&leaves[__ldg(chunk_leaf + c + 1)].a) : (int)cells;
+            const int wlen = end - off;
+            sbar_wait(full(st), ph);
+            const float* src = ring + st * kChunk;
+            const int i0 = ct * kSV;  // window-relative index of this thread's first cell
+            float p[kSV];
+#pragma unroll
+            for (int h = 0; h < kSV / 4; ++h) {
+                const float4 v = i0 + 4 * h < wlen ? *reinterpret_cast<const float4*>(src + i0 + 4 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+                p[4 * h + 0] = v.x; p[4 * h + 1] = v.y; p[4 * h + 2] = v.z; p[4 * h + 3] = v.w;
+            }
+            float cprev = s_c;
+            if (!regular || !(cprev >= 0.f && cprev < INFINITY)) {
+                if (ct == 0) {
+                    float cc = cprev;
+                    for (int j = off; j < end; ++j) {
+                        const float pj = __fdiv_rn(__fsub_rn(heat_value(__ldg(x + j), mode, vmin, vmax), m), S);
+                        cc = j == 0 ? pj : __fadd_rn(cc, pj);
+                        out[j] = cc;
+                    }
+                    s_c = cc;
+                }
+                release();
+                consumer_sync();
+                continue;
+            }
+#pragma unroll
+            for (int v = 0; v < kSV; ++v) p[v] = div_by(__fsub_rn(heat_value(p[v], mode, vmin, vmax), m), S, rS, fastdiv);
+            int start = 0;
+            float cur = cprev;
+            for (;;) {
+                const uint32_t cb = __float_as_uint(cur);
+                const uint32_t bec = cb >> 23;
+                const uint32_t ec = bec ? bec : 1u;
+                const uint32_t K0 = (cb & 0x7fffffu) | (bec ? 0x800000u : 0u);
+                const int sh = 150 - (int)ec;
+                const int ea = sh / 2, eb = sh - ea;
+                const float scale_a = __uint_as_float((uint32_t)(ea + 127) << 23), scale_b = __uint_as_float((uint32_t)(eb + 127) << 23);
+                if (ct == 0) s_bad = 0x7fffffff;
+                uint32_t dl[kSV];
+                bool any_tie = false;
+                const bool live = i0 + kSV > start && i0 < wlen;
+                uint32_t sum = 0;
+                if (live) {
+#pragma unroll
+                    for (int v = 0; v < kSV; ++v) {
+                        bool tie;
+                        delta_of(p[v], scale_a, scale_b, dl[v], tie);
+                        if (!(i0 + v >= start && i0 + v < wlen)) { dl[v] = 0; tie = false; }
+                        any_tie |= tie;
+                        sum = min(sum + dl[v], kSat);
+                    }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < kSV; ++v) dl[v] = 0;
+                }
+                Pair2 agg = {sum, sum};
+                if (any_tie) {
+                    agg = Pair2{0u, 0u};
+#pragma unroll
+                    for (int v = 0; v < kSV; ++v) {
+                        const Pair2 ev = (i0 + v >= start && i0 + v < wlen) ? pair_of(p[v], scale_a, scale_b) : Pair2{0u, 0u};
+                        agg = pair_then(agg, ev);
+                    }
+                }
+                Pair2 inc = agg;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    Pair2 t;
+                    t.d0 = __shfl_up_sync(0xffffffffu, inc.d0, o);
+                    t.d1 = __shfl_up_sync(0xffffffffu, inc.d1, o);
+                    if (lane >= o) inc = pair_then(t, inc);
+                }
+                Pair2 ex;
+                ex.d0 = __shfl_up_sync(0xffffffffu, inc.d0, 1);
+                ex.d1 = __shfl_up_sync(0xffffffffu, inc.d1, 1);
+                if (lane == 0) ex = Pair2{0u, 0u};
+                if (lane == 31) wtot[warp] = inc;
+                consumer_sync();
+                if (warp == 0) {
+                    Pair2 t = lane < kSC / 32 ? wtot[lane] : Pair2{0u, 0u};
+#pragma unroll
+                    for (int o = 1; o < kSC / 32; o <<= 1) {
+                        Pair2 u;
+                        u.d0 = __shfl_up_sync(0xffffffffu, t.d0, o);
+                        u.d1 = __shfl_up_sync(0xffffffffu, t.d1, o);
+                        if (lane >= o) t = pair_then(u, t);
+                    }
+                    Pair2 te;
+                    te.d0 = __shfl_up_sync(0xffffffffu, t.d0, 1);
+                    te.d1 = __shfl_up_sync(0xffffffffu, t.d1, 1);
+                    if (lane == 0) te = Pair2{0u, 0u};
+                    if (lane < kSC / 32) wtot[lane] = te;
+                }
+                consumer_sync();
+                const Pair2 pre = pair_then(wtot[warp], ex);
+                uint32_t K = min(K0 + ((K0 & 1u) ? pre.d1 : pre.d0), kSat);
+                const uint32_t K_in = K;
+                uint32_t Kout[kSV];
+                if (!any_tie) {
+#pragma unroll
+                    for (int v = 0; v < kSV; ++v) { K = min(K + dl[v], kSat); Kout[v] = K; }
+                } else {
+#pragma unroll
+                    for (int v = 0; v < kSV; ++v) {
+                        const Pair2 ev = (i0 + v >= start && i0 + v < wlen) ? pair_of(p[v], scale_a, scale_b) : Pair2{0u, 0u};
+                        K = min(K + ((K & 1u) ? ev.d1 : ev.d0), kSat);
+                        Kout[v] = K;
+                    }
+                }
+                int bad = 0x7fffffff, bad_v = 0;
+                uint32_t K_before_bad = 0;
+                if (live && K >= (1u << 24)) {
+                    uint32_t Kp = K_in;
+#pragma unroll
+                    for (int v = 0; v < kSV; ++v) {
+                        if (i0 + v >= start && i0 + v < wlen && Kout[v] >= (1u << 24) && bad == 0x7fffffff) {
+                            bad = i0 + v; bad_v = v; K_before_bad = Kp;
+                        }
+                        Kp = Kout[v];
+                    }
+                }
+                int wbad = bad;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) wbad = min(wbad, __shfl_xor_sync(0xffffffffu, wbad, o));
+                if (lane == 0 && wbad != 0x7fffffff) atomicMin(&s_bad, wbad);
+                consumer_sync();
+                const int gbad = s_bad;
+                const int stop = gbad == 0x7fffffff ? wlen : gbad;
+                auto value_of = [&](uint32_t Kv) { return __uint_as_float(Kv >= 0x800000u ? ((ec << 23) | (Kv & 0x7fffffu)) : Kv); };
+                float* o = out + off + i0;
+                if (i0 >= start && i0 + kSV <= stop) {
+#pragma unroll
+                    for (int h = 0; h < kSV / 4; ++h)
+                        __stcs(reinterpret_cast<float4*>(o) + h, make_float4(value_of(Kout[4 * h]), value_of(Kout[4 * h + 1]),
+                                                                             value_of(Kout[4 * h + 2]), value_of(Kout[4 * h + 3])));
+                } else {
+#pragma unroll
+                    for (int v = 0; v < kSV; ++v)
+                        if (i0 + v >= start && i0 + v < stop) o[v] = value_of(Kout[v]);
+                }
+                if (gbad == 0x7fffffff) {
+                    if (wlen - 1 >= i0 && wlen - 1 < i0 + kSV) {
+                        float last = 0.f;
+#pragma unroll
+                        for (int v = 0; v < kSV; ++v) if (v == wlen - 1 - i0) last = value_of(Kout[v]);
+                        s_c = last;
+                    }
+                    consumer_sync();
+                    break;
+                }
+                if (bad == gbad) {
+                    float pb = 0.f;
+#pragma unroll
+                    for (int v = 0; v < kSV; ++v) if (v == bad_v) pb = p[v];
+                    const float cn = __fadd_rn(value_of(K_before_bad), pb);
+                    out[off + gbad] = cn;
+                    s_c = cn;
+                }
+                consumer_sync();
+                cur = s_c;
+                start = gbad + 1;
+                if (start >= wlen) break;
+                if (!(cur < INFINITY)) {  // the sum overflowed: finish the window serially
+                    if (ct == 0) {
+                        float cc = cur;
+                        for (int j = off + start; j < end; ++j) {
+                            cc = __fadd_rn(cc, __fdiv_rn(__fsub_rn(heat_value(__ldg(x + j), mode, vmin, vmax), m), S));
+                            out[j] = cc;
+                        }
+                        s_c = cc;
+                    }
+                    break;
+                }
+            }
+            // The stage is released only here, after the window: releasing right after the register loads let the
+            // producer's refill of this stage show up in the loaded values on B200 (measured; ptxas may re-materialise
+            // shared-memory loads across the arrive).  The producer is still up to kStages - 1 windows ahead.
+            release();
+            consumer_sync();
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // per-iteration sample draws, one warp per task
 // ------------------------------------------------------------------------------------------------------------------
@@ -575,7 +958,8 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" size_t nrrt_cdf_workspace_bytes(int B, int64_t cells) {
     const size_t max_leaves = (size_t)(cells / 64 + 2);  // every leaf of a split has > 64 elements
-    return align_up((size_t)B * sizeof(float4), 256) + align_up(max_leaves * sizeof(LeafOp), 256) * 2 + 256 * sizeof(int32_t);
+    return align_up((size_t)B * sizeof(float4), 256) + align_up(max_leaves * sizeof(LeafOp), 256) * 2 + 256 * sizeof(int32_t) +
+           align_up(max_leaves * sizeof(int32_t), 256);  // stats | leaves | ops | level offsets | chunk table
 }
 
 extern "C" int nrrt_cdf_build(const float* logits, int mode, int B, int64_t cells, float* cdf, void* workspace,
@@ -615,10 +999,36 @@ extern "C" int nrrt_cdf_build(const float* logits, int mode, int B, int64_t cell
 
     const size_t smem = t.leaves.size() * sizeof(float);
     NRRT_REQUIRE(smem <= 200 * 1024, "map too large for the leaf-sum buffer");
-    NRRT_CUDA_TRY(cudaFuncSetAttribute(cdf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0;
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // streaming (bulk-copy pipelined) kernel when the rows satisfy the copy alignment; chunks = runs of whole leaves
+    const size_t stream_smem = (size_t)kStages * kChunk * sizeof(float) + smem;
+    if (cells % 4 == 0 && ((uintptr_t)logits & 15) == 0 && ((uintptr_t)cdf & 15) == 0 && stream_smem <= 220 * 1024) {
+        std::vector<int32_t> chunk_leaf;
+        int64_t chunk_begin = 0;
+        chunk_leaf.push_back(0);
+        for (size_t l = 0; l < t.leaves.size(); ++l) {
+            const int64_t leaf_end = (int64_t)t.leaves[l].a + t.leaves[l].b;
+            if (leaf_end - chunk_begin > kChunk) {  // this leaf opens a new chunk
+                chunk_leaf.push_back((int32_t)l);
+                chunk_begin = t.leaves[l].a;
+            }
+        }
+        bool aligned = true;  // every chunk start must be 16-byte aligned (leaf offsets are multiples of 8 except for tiny rows)
+        for (int32_t l : chunk_leaf) aligned = aligned && (t.leaves[l].a % 4 == 0);
+        if (aligned && chunk_leaf.size() <= max_leaves) {
+            int32_t* d_chunks = reinterpret_cast<int32_t*>(ws + 256 * sizeof(int32_t));
+            NRRT_CUDA_TRY(cudaMemcpyAsync(d_chunks, chunk_leaf.data(), chunk_leaf.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+            NRRT_CUDA_TRY(cudaFuncSetAttribute(cdf_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_smem));
+            cdf_stream_kernel<<<B < sms ? B : sms, kSC + 32, stream_smem, st>>>(logits, mode, B, cells, d_leaves, (int)t.leaves.size(),
+                                                                             d_ops, d_level, (int)level_off.size() - 1, d_chunks,
+                                                                             (int)chunk_leaf.size(), stats, cdf);
+            NRRT_CUDA_TRY(cudaGetLastError());
+            return NRRT_OK;
+        }
+    }
+    NRRT_CUDA_TRY(cudaFuncSetAttribute(cdf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cdf_fused_kernel<<<B < sms ? B : sms, kFT, smem, st>>>(logits, mode, B, cells, d_leaves, (int)t.leaves.size(), d_ops, d_level,
                                                          (int)level_off.size() - 1, stats, cdf);
     NRRT_CUDA_TRY(cudaGetLastError());
