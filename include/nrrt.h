@@ -185,6 +185,8 @@ typedef struct NrrtConvLayer {
      * computed once per map and enters the per-task layer here, before the ReLU. */
     const int32_t* res_index;
     int32_t res_n;           /* samples in the residual buffer (0 = n) */
+    int32_t no_poly_mma;     /* testing: evaluate the whole polynomial term in the epilogue (default: the interior polynomial
+                                of residual-carrying 3x3 layers is one extra tensor-core MMA per tile) */
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);

@@ -27,7 +27,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int kEpiWarps = 8;                  // two warps per TMEM lane quarter
-constexpr int kThreads = 64 + 32 * kEpiWarps;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+constexpr int kAuxWarp = 2 + kEpiWarps;        // warp 10: coefficient tiles of the polynomial-through-MMA kernels (else idle)
+constexpr int kThreads = 64 + 32 * kEpiWarps + 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 auxiliary
 constexpr int kMaxTaps = 27;
 
 struct ConvParams {
@@ -58,6 +59,7 @@ struct ConvParams {
     const float* poly;   // optional [N][poly_cases][4][cout]: bilinear epilogue term E0 + ty*E1 + tx*E2 + ty*tx*E3
     int poly_cases;      // 9 = 3x3 border cases (row case * 3 + column case); else one case per weight group
     float inv_h, inv_w;  // 1/(H-1), 1/(W-1) of the tile-space grid
+    int pm;              // pair kernels: interior polynomial applied by one extra tcgen05.mma per tile (see pm_* below)
     const float* head_w; // optional fused 1x1 head (cout -> 1): logits[pixel] = head_b + sum_c relu_out[c] * head_w[c]
     float head_b;
     float* logits;
@@ -151,7 +153,8 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int m = kBlockM) {
 __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[32], int col, int lc, int n, int d,
                                                int h, int w, const float* sc, const float* sh, const float* sc2,
                                                const float* sh2, const float* pe, int pe_stride, float& head_acc,
-                                               const uint8_t* res_row = nullptr, int res_r7 = 0) {
+                                               const uint8_t* res_row = nullptr, int res_r7 = 0, bool pm = false,
+                                               int frame = 0) {
     const int g = col / p.cout, co = col - g * p.cout;
     int od = d, oh = h, ow = w;
     if (p.up == 2) {
@@ -167,22 +170,40 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
         if (p.poly_cases == 9)
             kcase = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
         const float ty = (float)h * p.inv_h, tx = (float)w * p.inv_w, tyx = ty * tx;
-        // interior pixels (and ConvTranspose groups) read the tile's coefficients staged in shared memory; only the
-        // one-pixel image frame, whose tap set differs, goes to global memory
-        const bool staged = p.poly_cases != 9 || kcase == 4;
-        const float4* e0 = staged ? reinterpret_cast<const float4*>(pe + lc)
-                                  : reinterpret_cast<const float4*>(p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co);
-        const int es = staged ? pe_stride / 4 : p.cout / 4;
-        const float4* e1 = e0 + es;
-        const float4* e2 = e1 + es;
-        const float4* e3 = e2 + es;
+        if (!pm) {
+            // interior pixels (and ConvTranspose groups) read the tile's coefficients staged in shared memory; only the
+            // one-pixel image frame, whose tap set differs, goes to global memory
+            const bool staged = p.poly_cases != 9 || kcase == 4;
+            const float4* e0 = staged ? reinterpret_cast<const float4*>(pe + lc)
+                                      : reinterpret_cast<const float4*>(p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co);
+            const int es = staged ? pe_stride / 4 : p.cout / 4;
+            const float4* e1 = e0 + es;
+            const float4* e2 = e1 + es;
+            const float4* e3 = e2 + es;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const float4 a0 = e0[q], a1 = e1[q], a2 = e2[q], a3 = e3[q];
-            f[q * 4 + 0] += a0.x + ty * a1.x + tx * a2.x + tyx * a3.x;
-            f[q * 4 + 1] += a0.y + ty * a1.y + tx * a2.y + tyx * a3.y;
-            f[q * 4 + 2] += a0.z + ty * a1.z + tx * a2.z + tyx * a3.z;
-            f[q * 4 + 3] += a0.w + ty * a1.w + tx * a2.w + tyx * a3.w;
+            for (int q = 0; q < 8; ++q) {
+                const float4 a0 = e0[q], a1 = e1[q], a2 = e2[q], a3 = e3[q];
+                f[q * 4 + 0] += a0.x + ty * a1.x + tx * a2.x + tyx * a3.x;
+                f[q * 4 + 1] += a0.y + ty * a1.y + tx * a2.y + tyx * a3.y;
+                f[q * 4 + 2] += a0.z + ty * a1.z + tx * a2.z + tyx * a3.z;
+                f[q * 4 + 3] += a0.w + ty * a1.w + tx * a2.w + tyx * a3.w;
+            }
+        } else if (frame) {
+            // the extra MMA added the interior polynomial to every pixel: frame pixels get (their case - interior), staged per
+            // tile by pm_stage_frame in rows [A_r, B_r, A_c, B_c, C] behind scale/shift: row frame A_r + tx*B_r, column
+            // frame A_c + ty*B_c, corner C
+            const float* fr = sc2 + lc;  // == tile buffer + 2 * BLOCK_N + lc
+            const float* a = frame == 1 ? fr : (frame == 2 ? fr + 2 * pe_stride : fr + 4 * pe_stride);
+            const float t = frame == 1 ? tx : (frame == 2 ? ty : 0.f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 a0 = *reinterpret_cast<const float4*>(a + q * 4);
+                const float4 a1 = frame == 3 ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(a + pe_stride + q * 4);
+                f[q * 4 + 0] += a0.x + t * a1.x;
+                f[q * 4 + 1] += a0.y + t * a1.y;
+                f[q * 4 + 2] += a0.z + t * a1.z;
+                f[q * 4 + 3] += a0.w + t * a1.w;
+            }
         }
     }
     if (p.res) {
@@ -252,6 +273,37 @@ __device__ __forceinline__ void stage_tile_params(const ConvParams& p, float* ds
         for (int i = et; i < 4 * BLOCK_N; i += 32 * kEpiWarps) {
             const int e = i / BLOCK_N, c = i - e * BLOCK_N;
             if (co0 + c < p.cout) dst[(4 + e) * BLOCK_N + c] = __ldg(src + (size_t)e * p.cout + c);
+        }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+}
+
+// PM kernels: per-tile frame corrections (see epilogue_chunk) for a tile that touches the one-pixel image frame, written by
+// the 256 epilogue threads into rows 2..6 of the tile's parameter buffer.  hr / wc = tile-local index of the frame row /
+// column (-1: none), rr / cc = its border case (0 = first, 2 = last).  Tile-uniform: every epilogue thread calls it.
+template <int BLOCK_N>
+__device__ __forceinline__ void pm_stage_frame(const ConvParams& p, float* dst, int n, int et, int h0, int w0, int hr, int wc) {
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    const int rr = hr < 0 ? 1 : (h0 + hr == 0 ? 0 : 2), cc = wc < 0 ? 1 : (w0 + wc == 0 ? 0 : 2);
+    const float ty_r = (float)(h0 + hr) * p.inv_h, tx_c = (float)(w0 + wc) * p.inv_w;
+    const float* base = p.poly + ((size_t)n * 9 * 4) * p.cout;
+    for (int i = et; i < 3 * BLOCK_N; i += 32 * kEpiWarps) {
+        const int which = i / BLOCK_N, c = i - which * BLOCK_N;  // 0: row frame, 1: column frame, 2: corner
+        if ((which == 0 && hr < 0) || (which == 1 && wc < 0) || (which == 2 && (hr < 0 || wc < 0))) continue;
+        const int kcase = which == 0 ? rr * 3 + 1 : (which == 1 ? 3 + cc : rr * 3 + cc);
+        const float* k = base + (size_t)kcase * 4 * p.cout + c;
+        const float* q = base + (size_t)4 * 4 * p.cout + c;
+        const float d0 = __ldg(k) - __ldg(q), d1 = __ldg(k + p.cout) - __ldg(q + p.cout);
+        const float d2 = __ldg(k + 2 * (size_t)p.cout) - __ldg(q + 2 * (size_t)p.cout);
+        const float d3 = __ldg(k + 3 * (size_t)p.cout) - __ldg(q + 3 * (size_t)p.cout);
+        if (which == 0) {
+            dst[2 * BLOCK_N + c] = d0 + ty_r * d1;
+            dst[3 * BLOCK_N + c] = d2 + ty_r * d3;
+        } else if (which == 1) {
+            dst[4 * BLOCK_N + c] = d0 + tx_c * d2;
+            dst[5 * BLOCK_N + c] = d1 + tx_c * d3;
+        } else {
+            dst[6 * BLOCK_N + c] = d0 + ty_r * d1 + tx_c * d2 + ty_r * tx_c * d3;
         }
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -360,7 +412,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else {
+    } else if (warp < kAuxWarp) {
         // ===== epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; the two warps of a quarter split the column chunks =====
         const int sub = warp & 3;
         const int part = (warp - 2) >> 2;
@@ -468,14 +520,111 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
 constexpr int kMaxResPieces = 4;       // 64-channel pieces of a residual tile (BLOCK_N <= 256)
 constexpr uint32_t kResPiece = 16384;  // 128 pixel rows x 128 B (SWIZZLE_128B), 1024-byte aligned
 
-template <int BLOCK_N, int STAGES, bool RES>
+
+// ---- polynomial coordinate term through the tensor core (pair kernels, 3x3 convs) ---------------------------------
+// The epilogue polynomial E0 + ty*E1 + tx*E2 + ty*tx*E3 (4 coefficient loads + 4 FMAs per output value) is the largest
+// single cost of the conv7.0 / conv8.0 epilogues.  Inside one tile it is a rank-4 product: with tile-local pixel
+// coordinates (hl, wl) in [0,16) it equals [1, hl, wl, hl*wl] . [E0', E1', E2', E3'] where the primed coefficients
+// absorb the tile origin (pm_produce_b).  The basis is exact in fp16 and the SAME for every tile, so it is a constant
+// shared-memory A tile written once per CTA; the coefficients are split hi + lo into two fp16 values (22 significant
+// bits) and written per tile as a K = 16 B tile: one extra K=16 MMA per accumulator replaces the whole interior
+// polynomial.  A CTA pair shares B, so the 16 K slots are [tile of CTA 0: 4 hi, 4 lo | tile of CTA 1: 4 hi, 4 lo] and
+// each CTA's basis rows are zero in the other CTA's slots.  Pixels on the image frame (different tap set) get the
+// difference to the interior polynomial in the epilogue.  Both tiles use the no-swizzle K-major canonical layout
+// ((8,n),2):((16 B, SBO), LBO): [k half][row][8 halfs], SBO = 128 B, LBO = rows * 16 B.
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;  // layout type 0: no swizzle
+}
+#define mbar_wait_cluster(bar, parity)                                                    \
+    asm volatile(                                                                         \
+        "{\n\t.reg .pred p;\n\t"                                                         \
+        "WAITC_LOOP:\n\t"                                                                 \
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"       \
+        "@p bra WAITC_DONE;\n\t"                                                          \
+        "bra WAITC_LOOP;\n\t"                                                             \
+        "WAITC_DONE:\n\t}" ::"r"((uint32_t)(bar)), "r"((uint32_t)(parity))                \
+        : "memory")
+__device__ __forceinline__ void mbar_arrive_leader_release(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar)
+        : "memory");
+}
+// basis rows of one 128-pixel block: row r holds [1, hl, wl, hl*wl, 1, hl, wl, hl*wl] in k half `rank`, zeros in the other
+__device__ __forceinline__ void pm_write_basis(uint8_t* tile, int row, int hl, int wl, uint32_t rank) {
+    const __half2 a = __floats2half2_rn(1.0f, (float)hl), b = __floats2half2_rn((float)wl, (float)(hl * wl));
+    uint4 v;
+    v.x = *reinterpret_cast<const uint32_t*>(&a); v.y = *reinterpret_cast<const uint32_t*>(&b); v.z = v.x; v.w = v.y;
+    *reinterpret_cast<uint4*>(tile + rank * 2048u + row * 16) = v;
+    *reinterpret_cast<uint4*>(tile + (1u - rank) * 2048u + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+}
+// B tile of one pair iteration: rows = this CTA's ROWS_B output channels, k half j = tile of CTA j (sample tn[j], origin
+// (th0[j], tw0[j]) in pixels, dead tiles contribute zero).  Run by the auxiliary warp (thread t0 of nt), off the critical
+// path of the epilogue, the TMA producer and the MMA issuer; ends with the writes visible to the async proxy.
+template <int ROWS_B>
+__device__ __forceinline__ void pm_produce_b(const ConvParams& p, uint8_t* bx, int t0, int nt, uint32_t rank, const int (&tn)[2],
+                                             const int (&th0)[2], const int (&tw0)[2], const bool (&tlive)[2]) {
+    constexpr int kMaxItems = (2 * ROWS_B + 31) / 32;  // items per thread of the auxiliary warp
+    float e[kMaxItems][4];
+    // all coefficient loads first (independent, one latency), then the arithmetic
+#pragma unroll
+    for (int i = 0; i < kMaxItems; ++i) {
+        const int it = t0 + i * nt;
+        const int j = it / ROWS_B, r = it - j * ROWS_B;
+        const int co = (int)rank * ROWS_B + r;
+        e[i][0] = e[i][1] = e[i][2] = e[i][3] = 0.f;
+        if (it < 2 * ROWS_B && tlive[j] && co < p.cout) {
+            const float* src = p.poly + (((size_t)tn[j] * 9 + 4) * 4) * p.cout + co;  // interior case
+            e[i][0] = __ldg(src); e[i][1] = __ldg(src + p.cout);
+            e[i][2] = __ldg(src + 2 * (size_t)p.cout); e[i][3] = __ldg(src + 3 * (size_t)p.cout);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxItems; ++i) {
+        const int it = t0 + i * nt;
+        if (it >= 2 * ROWS_B) break;
+        const int j = it / ROWS_B, r = it - j * ROWS_B;
+        const float e0 = e[i][0], e1 = e[i][1], e2 = e[i][2], e3 = e[i][3];
+        const float hy = (float)th0[j] * p.inv_h, wx = (float)tw0[j] * p.inv_w;  // ty, tx of the tile origin
+        const float c0 = e0 + hy * e1 + wx * e2 + hy * wx * e3;
+        const float c1 = p.inv_h * (e1 + wx * e3);
+        const float c2 = p.inv_w * (e2 + hy * e3);
+        const float c3 = p.inv_h * p.inv_w * e3;
+        const float c[4] = {c0, c1, c2, c3};
+        __half hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float cc = fminf(fmaxf(c[q], -65504.f), 65504.f);
+            hi[q] = __float2half_rn(cc);
+            lo[q] = __float2half_rn(cc - __half2float(hi[q]));
+        }
+        uint4 v;
+        __half2 t;
+        t = __halves2half2(hi[0], hi[1]); v.x = *reinterpret_cast<const uint32_t*>(&t);
+        t = __halves2half2(hi[2], hi[3]); v.y = *reinterpret_cast<const uint32_t*>(&t);
+        t = __halves2half2(lo[0], lo[1]); v.z = *reinterpret_cast<const uint32_t*>(&t);
+        t = __halves2half2(lo[2], lo[3]); v.w = *reinterpret_cast<const uint32_t*>(&t);
+        *reinterpret_cast<uint4*>(bx + (uint32_t)j * (ROWS_B * 16u) + r * 16) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+template <int BLOCK_N, int STAGES, bool RES, bool PM>
 struct SmemLayout2 {  // per CTA of a pair: its own A tile and HALF of the B tile per stage
     static constexpr uint32_t a_stage = kBlockM * 128;
     static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
     static constexpr uint32_t off_b = STAGES * a_stage;
     static constexpr uint32_t off_res = off_b + STAGES * b_stage;  // TMA-staged residual tile: BLOCK_N / 64 pieces
-    static constexpr uint32_t off_bar = off_res + (RES ? (BLOCK_N / 64) * kResPiece : 0);
-    static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4 + 2 * kMaxResPieces) * 8;
+    static constexpr uint32_t off_pm = off_res + (RES ? (BLOCK_N / 64) * kResPiece : 0);  // basis tile (4 KB), then 2 coefficient tiles
+    static constexpr uint32_t pm_b = (BLOCK_N / 2) * 32;
+    static constexpr uint32_t off_bar = off_pm + (PM ? 4096 + 2 * pm_b : 0);
+    static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4 + 2 * kMaxResPieces + 2) * 8;
     static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
     static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
 };
@@ -489,12 +638,13 @@ struct SmemLayout2 {  // per CTA of a pair: its own A tile and HALF of the B til
 // RES: the residual tile (this CTA's 128 pixels x BLOCK_N channels, fp16) is staged in shared memory by the producer's
 // TMA in 64-channel pieces, each with a full/empty barrier pair, so the epilogue never waits on a global load: the piece
 // of tile i+1 is requested as soon as every epilogue warp has consumed that piece of tile i.
-template <int BLOCK_N, int STAGES, bool RES>
+// PM: the interior polynomial coordinate term is one extra MMA per tile (pm_* above; 2D 3x3 layers, n_tiles == 1).
+template <int BLOCK_N, int STAGES, bool RES, bool PM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_r,
                  const __grid_constant__ ConvParams p) {
-    using L = SmemLayout2<BLOCK_N, STAGES, RES>;
+    using L = SmemLayout2<BLOCK_N, STAGES, RES, PM>;
     constexpr int RP = BLOCK_N / 64;  // residual pieces
     constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
@@ -507,6 +657,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
     auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
     auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + kMaxResPieces + s); };
+    auto bxfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + 2 * kMaxResPieces + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
     float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
 
@@ -521,6 +672,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // the leader's tempty barrier collects the epilogue warps of BOTH CTAs
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
         if (RES) for (int s = 0; s < RP; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kEpiWarps); }
+        if (PM) for (int s = 0; s < 2; ++s) mbar_init(bxfull_bar(s), 2);  // one arrival per CTA of the pair
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -607,11 +759,17 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tc_commit2(empty_bar(stage));  // frees the smem slot in both CTAs once these MMAs have read it
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
+                if (PM) {
+                    mbar_wait_cluster(bxfull_bar(acc), acc_phase);  // both CTAs' coefficient tiles of this pair iteration
+                    tc_fence_after();
+                    tc_mma2_f16(d_tmem, make_smem_desc_nosw(base + L::off_pm, 2048, 128),
+                               make_smem_desc_nosw(base + L::off_pm + 4096 + acc * L::pm_b, (BLOCK_N / 2) * 16, 128), idesc, 1u);
+                }
                 tc_commit2(tfull_bar(acc));  // accumulator complete in both CTAs' tensor memory
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else {
+    } else if (warp < kAuxWarp) {
         // ===== epilogue warps 2..9: TMEM lanes 32*(warp%4) .. +31; the two warps of a quarter split the column chunks =====
         const int sub = warp & 3;
         const int part = (warp - 2) >> 2;
@@ -630,12 +788,23 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int n = live ? m / p.tiles_d : 0;
             float* sc = ss + acc * 8 * BLOCK_N;  // double-buffered by accumulator stage
             stage_tile_params<BLOCK_N>(p, sc, n_tile * BLOCK_N, n, et, last_ntile[acc] != n_tile,
-                                       last_ntile[acc] != n_tile || last_n[acc] != n);
+                                       !PM && (last_ntile[acc] != n_tile || last_n[acc] != n));
             last_ntile[acc] = n_tile; last_n[acc] = n;
 
             const int wl = row % p.bw, hl = (row / p.bw) % p.bh, dl = row / (p.bw * p.bh);
             const int w = tw * p.bw + wl, h = th * p.bh + hl, d = td * p.bd + dl;
             const bool valid = live && row < p.rows && w < p.W && h < p.H && d < p.D;
+            int frame = 0;
+            if (PM) {
+                const int h0 = th * p.bh, w0 = tw * p.bw;
+                const int hr = h0 == 0 ? 0 : (p.H - 1 - h0 < p.bh ? p.H - 1 - h0 : -1);
+                const int wc = w0 == 0 ? 0 : (p.W - 1 - w0 < p.bw ? p.W - 1 - w0 : -1);
+                if (live && (hr >= 0 || wc >= 0)) {
+                    pm_stage_frame<BLOCK_N>(p, sc, n, et, h0, w0, hr, wc);
+                    const bool on_r = hl == hr, on_c = wl == wc;
+                    frame = on_r ? (on_c ? 3 : 1) : (on_c ? 2 : 0);
+                }
+            }
 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -655,7 +824,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     if (valid)
                         epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
-                                       sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7);
+                                       sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame);
                     if (RES) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(rempty_bar(c >> 1));
@@ -668,6 +837,27 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty_bar(acc));  // the leader's MMA thread waits for both CTAs' epilogues
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (PM) {
+        // ===== auxiliary warp: basis tile once, then the coefficient tile of every pair iteration (stage = iteration & 1) =====
+        for (int r = lane; r < 128; r += 32) pm_write_basis(base_ptr + L::off_pm, r, (r / p.bw) % p.bh, r % p.bw, rank);
+        int it = 0;
+        for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++it) {
+            const int a = it & 1;
+            if (it >= 2) mbar_wait(tfull_bar(a), (uint32_t)(((it >> 1) - 1) & 1));  // MMAs of iteration it - 2 are done
+            int tn[2], th0[2], tw0[2];
+            bool tlive[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                int mj = pt * 2 + j;  // n_tiles == 1
+                tlive[j] = mj < p.m_tiles;
+                tw0[j] = (mj % p.tiles_w) * p.bw; mj /= p.tiles_w;
+                th0[j] = (mj % p.tiles_h) * p.bh; mj /= p.tiles_h;
+                tn[j] = tlive[j] ? mj / p.tiles_d : 0;
+            }
+            pm_produce_b<BLOCK_N / 2>(p, base_ptr + L::off_pm + 4096 + a * L::pm_b, lane, 32, rank, tn, th0, tw0, tlive);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader_release(bxfull_bar(a));
         }
     }
 
@@ -820,7 +1010,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else {
+    } else if (warp < kAuxWarp) {
         // ===== epilogue warps 2..9: warps 2-5 take column block 0, warps 6-9 column block 1 =====
         const int sub = warp & 3;
         const int blk = (warp - 2) >> 2;
@@ -869,14 +1059,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES>
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM>
 struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
     static constexpr uint32_t a_stage = 2 * kSlabBytes;
     static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
     static constexpr uint32_t off_b = A_STAGES * a_stage;
     static constexpr uint32_t off_res = off_b + B_STAGES * b_stage;  // residual pieces [column block][64-channel chunk]
-    static constexpr uint32_t off_bar = off_res + (RES ? 2 * (BLOCK_N / 64) * kResPiece : 0);
-    static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4 + 2 * kMaxResPieces) * 8;
+    static constexpr uint32_t off_pm = off_res + (RES ? 2 * (BLOCK_N / 64) * kResPiece : 0);  // basis tiles (2 x 4 KB), then
+    static constexpr uint32_t pm_b = (BLOCK_N / 2) * 32;                                     // 2 coefficient tiles
+    static constexpr uint32_t off_bar = off_pm + (PM ? 2 * 4096 + 2 * pm_b : 0);
+    static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4 + 2 * kMaxResPieces + 2) * 8;
     static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
     static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
 };
@@ -884,12 +1076,13 @@ struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
 // conv_halo2_kernel — the slab kernel on CTA pairs (cta_group::2): the pair owns two adjacent 16x16 tiles, every MMA is
 // M256 = column block `blk` of both CTAs, and each CTA loads (and feeds from its shared memory) only half of each B tile.
 // RES: TMA-staged residual tile as in conv_gemm2_kernel; a piece = (column block, 64-channel chunk) = 128 pixels x 128 B.
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES>
+// PM: the interior polynomial coordinate term is one extra MMA per accumulator (pm_* above).
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_r,
                  const __grid_constant__ ConvParams p) {
-    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES>;
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM>;
     constexpr int RC = BLOCK_N / 64;  // 64-channel chunks per column block; residual pieces = 2 * RC
     constexpr int TMEM_COLS = 4 * BLOCK_N;  // 2 accumulator stages x 2 column blocks
     extern __shared__ uint8_t smem_raw[];
@@ -904,6 +1097,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 2 + s); };
     auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + s); };
     auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + kMaxResPieces + s); };
+    auto bxfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + 2 * kMaxResPieces + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
     float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
 
@@ -917,6 +1111,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
         if (RES) for (int s = 0; s < 2 * RC; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kEpiWarps / 2); }
+        if (PM) for (int s = 0; s < 2; ++s) mbar_init(bxfull_bar(s), 2);  // one arrival per CTA of the pair
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -1018,11 +1213,20 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
                     }
                 }
+                if (PM) {
+                    mbar_wait_cluster(bxfull_bar(acc), acc_phase);  // both CTAs' coefficient tiles of this pair iteration
+                    tc_fence_after();
+                    const uint64_t bdesc = make_smem_desc_nosw(base + L::off_pm + 2 * 4096 + acc * L::pm_b, (BLOCK_N / 2) * 16, 128);
+#pragma unroll
+                    for (int blk = 0; blk < 2; ++blk)
+                        tc_mma2_f16(d_tmem + (uint32_t)(blk * BLOCK_N), make_smem_desc_nosw(base + L::off_pm + blk * 4096, 2048, 128),
+                                   bdesc, idesc, 1u);
+                }
                 tc_commit2(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
-    } else {
+    } else if (warp < kAuxWarp) {
         // ===== epilogue warps 2..9: warps 2-5 take column block 0, warps 6-9 column block 1 =====
         const int sub = warp & 3;
         const int blk = (warp - 2) >> 2;
@@ -1038,8 +1242,20 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const int th = m % p.tiles_h;
             const int n = live ? m / p.tiles_h : 0;
             float* sc = ss + acc * 8 * BLOCK_N;
-            stage_tile_params<BLOCK_N>(p, sc, 0, n, et, last_n[acc] < 0, last_n[acc] != n);
+            stage_tile_params<BLOCK_N>(p, sc, 0, n, et, last_n[acc] < 0, !PM && last_n[acc] != n);
             last_n[acc] = n;
+            int frame = 0;
+            if (PM) {
+                const int h0 = th * 16, w0 = tw * 16;
+                const int hr = h0 == 0 ? 0 : (p.H - 1 - h0 < 16 ? p.H - 1 - h0 : -1);
+                const int wc = w0 == 0 ? 0 : (p.W - 1 - w0 < 16 ? p.W - 1 - w0 : -1);
+                if (live && (hr >= 0 || wc >= 0)) {
+                    pm_stage_frame<BLOCK_N>(p, sc, n, et, h0, w0, hr, wc);
+                    const bool on_r = (row >> 3) == hr, on_c = blk * 8 + (row & 7) == wc;
+                    frame = on_r ? (on_c ? 3 : 1) : (on_c ? 2 : 0);
+                }
+            }
+
             const int h = th * 16 + (row >> 3);
             const int w = tw * 16 + blk * 8 + (row & 7);
             const bool valid = live && h < p.H && w < p.W;
@@ -1059,7 +1275,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 if (valid)
                     epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
-                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7);
+                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame);
                 if (RES && (c & 1)) {  // both 32-column halves of the piece are consumed
                     __syncwarp();
                     if (lane == 0) mbar_arrive(rempty_bar(piece));
@@ -1071,6 +1287,29 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+    } else if (PM) {
+        // ===== auxiliary warp: basis tiles once, then the coefficient tile of every pair iteration (stage = iteration & 1) =====
+        for (int r = lane; r < 256; r += 32)
+            pm_write_basis(base_ptr + L::off_pm + (r >> 7) * 4096, r & 127, (r & 127) >> 3, (r >> 7) * 8 + (r & 7), rank);
+        int it = 0;
+        for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++it) {
+            const int a = it & 1;
+            // the stage was last read by the MMAs of iteration it - 2: wait for that accumulator's commit
+            if (it >= 2) mbar_wait(tfull_bar(a), (uint32_t)(((it >> 1) - 1) & 1));
+            int tn[2], th0[2], tw0[2];
+            bool tlive[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                int mj = pt * 2 + j;
+                tlive[j] = mj < p.m_tiles;
+                tw0[j] = (mj % p.tiles_w) * 16; mj /= p.tiles_w;
+                th0[j] = (mj % p.tiles_h) * 16;
+                tn[j] = tlive[j] ? mj / p.tiles_h : 0;
+            }
+            pm_produce_b<BLOCK_N / 2>(p, base_ptr + L::off_pm + 2 * 4096 + a * L::pm_b, lane, 32, rank, tn, th0, tw0, tlive);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader_release(bxfull_bar(a));  // one arrival per CTA of the pair
         }
     }
 
@@ -1112,12 +1351,12 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap
     return NRRT_OK;
 }
 
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES>
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM = false>
 int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const ConvParams& p,
                  int sms, cudaStream_t st) {
-    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES>;
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM>;
     static_assert(L::total <= 232448, "shared memory budget");
-    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES>;
+    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES, PM>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int pairs = (p.m_tiles + 1) / 2;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
@@ -1126,12 +1365,12 @@ int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMa
     return NRRT_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool RES>
+template <int BLOCK_N, int STAGES, bool RES, bool PM = false>
 int launch_conv2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const ConvParams& p,
                  int sms, cudaStream_t st) {
-    using L = SmemLayout2<BLOCK_N, STAGES, RES>;
+    using L = SmemLayout2<BLOCK_N, STAGES, RES, PM>;
     static_assert(L::total <= 232448, "shared memory budget");
-    auto kern = conv_gemm2_kernel<BLOCK_N, STAGES, RES>;
+    auto kern = conv_gemm2_kernel<BLOCK_N, STAGES, RES, PM>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);  // whole CTA pairs (static cluster dims 2x1x1)
@@ -1293,6 +1532,10 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     }
     // pair kernels stage the residual tile through shared memory with TMA (output grid, 64-channel pieces)
     const bool tma_res = pair && l->res && up == 1 && !l->logits && l->cout % 64 == 0 && l->res_coffset % 64 == 0;
+    // interior polynomial through the tensor core: 2D 3x3 convs on the pair kernels with a staged residual (conv7.0 / conv8.0)
+    p.pm = (tma_res && l->poly && l->poly_cases == 9 && p.n_tiles == 1 && !l->no_poly_mma && !three_d && !l->post_scale &&
+            ((halo && block_n == 128) || (!halo && block_n == 256 && l->kind == NRRT_CONV_K3S1 && p.rows == 128)) &&
+            p.H > p.bh && p.W > p.bw) ? 1 : 0;  // (a tile holds at most one frame row and one frame column)
     CUtensorMap mr = ma;
     if (tma_res) {
         const int rn = l->res_n > 0 ? l->res_n : N;
@@ -1312,6 +1555,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (halo && pair) {
         if (tma_res) {
+            if (block_n == 128 && p.pm) return launch_halo2<128, 3, 4, true, true>(ma, ma2, mb, mr, p, sms, st);
             if (block_n == 128) return launch_halo2<128, 3, 5, true>(ma, ma2, mb, mr, p, sms, st);
             return launch_halo2<64, 4, 8, true>(ma, ma2, mb, mr, p, sms, st);
         }
@@ -1324,6 +1568,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     }
     if (pair) {
         if (tma_res) {
+            if (block_n == 256 && p.pm) return launch_conv2<256, 4, true, true>(ma, ma2, mb, mr, p, sms, st);
             if (block_n == 256) return launch_conv2<256, 4, true>(ma, ma2, mb, mr, p, sms, st);
             return launch_conv2<128, 6, true>(ma, ma2, mb, mr, p, sms, st);
         }

@@ -238,6 +238,42 @@ def test_poly16_matches_conv_over_the_coordinate_field(cuda_device):
     assert err <= 2e-3 * max(ref.abs().max().item(), 1.0), f"max abs err {err}"
 
 
+@pytest.mark.parametrize("cout,sp", [(128, (40, 56)), (128, (16, 16)), (256, (40, 56)), (256, (24, 32))])
+def test_polynomial_term_through_the_tensor_core(cout, sp, cuda_device):
+    """Residual-carrying 3x3 layers add the interior coordinate polynomial with one extra MMA per tile (fp16 hi + lo
+    coefficients, exact fp16 basis) and patch the image frame in the epilogue: equal to the all-epilogue evaluation and
+    to the dense definition."""
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(21)
+    B, cin = 3, 64
+    x = torch.randn((B, cin) + sp, generator=g).to(dev)
+    res = torch.randn((2, cout) + sp, generator=g).to(dev)
+    index = torch.tensor([1, 0, 1], dtype=torch.int32, device=dev)
+    w = (torch.randn((cout, cin, 3, 3), generator=g) / 24).to(dev)
+    scale, shift = torch.ones(cout, device=dev), torch.randn(cout, generator=g).to(dev)
+    poly = (torch.randn((B, 9, 4, cout), generator=g) * torch.tensor([100.0, 60.0, 60.0, 30.0]).view(1, 1, 4, 1)).to(dev).contiguous()
+    layer = cnn._Layer(2, cnn.K3S1, cin, cout, cnn._pack_conv_weight(w, cin, dev), scale, shift.contiguous(), True)
+    outs = []
+    for no_mma in (False, True):
+        layer.no_poly_mma = no_mma
+        out = torch.zeros((B, 1) + sp + (cout,), dtype=torch.float16, device=dev)
+        layer.run(_lib.load(), None, _cl(x), 0, (1,) + sp, out, 0, _cl(res), 0, poly=poly, res_idx=index)
+        torch.cuda.synchronize()
+        outs.append(out.float())
+    H, W = sp
+    Y, X = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    ty, tx = Y.float() / (H - 1), X.float() / (W - 1)
+    rc = torch.where(Y == 0, 0, torch.where(Y == H - 1, 2, 1))
+    cc = torch.where(X == 0, 0, torch.where(X == W - 1, 2, 1))
+    e = poly[:, (rc * 3 + cc).long()]                                   # [B, H, W, 4, cout]
+    pv = e[..., 0, :] + ty[..., None] * e[..., 1, :] + tx[..., None] * e[..., 2, :] + (ty * tx)[..., None] * e[..., 3, :]
+    ref = F.relu(_ref(2, cnn.K3S1, x, w, scale, shift, False) + res[index.long()].half().float() + pv.permute(0, 3, 1, 2))
+    tol = 2e-3 * max(ref.abs().max().item(), 1.0) + 1e-3
+    for out in outs:
+        assert (_from_cl(out, 2) - ref).abs().max().item() <= tol
+    assert (outs[0] - outs[1]).abs().max().item() <= tol
+
+
 @pytest.mark.parametrize("three_d", [False, True])
 @pytest.mark.parametrize("bn", [False, True])
 def test_unet_forward_matches_reference_golden(three_d, bn, cuda_device):
