@@ -28,7 +28,8 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = 128 bytes = one SWIZZLE_128B row
 constexpr int kEpiWarps = 8;                  // two warps per TMEM lane quarter
 constexpr int kAuxWarp = 2 + kEpiWarps;        // warp 10: coefficient tiles of the polynomial-through-MMA kernels (else idle)
-constexpr int kThreads = 64 + 32 * kEpiWarps + 32;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warp 10 auxiliary
+constexpr int kIssue2Warp = kAuxWarp + 1;      // warp 11: second MMA issuer of the pair slab kernel (else idle)
+constexpr int kThreads = 64 + 32 * kEpiWarps + 64;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue, warps 10-11 as above
 constexpr int kMaxTaps = 27;
 
 struct ConvParams {
@@ -838,7 +839,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (lane == 0) mbar_arrive_leader(tempty_bar(acc));  // the leader's MMA thread waits for both CTAs' epilogues
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (PM) {
+    } else if (PM && warp == kAuxWarp) {
         // ===== auxiliary warp: basis tile once, then the coefficient tile of every pair iteration (stage = iteration & 1) =====
         for (int r = lane; r < 128; r += 32) pm_write_basis(base_ptr + L::off_pm, r, (r / p.bw) % p.bh, r % p.bw, rank);
         int it = 0;
@@ -1107,9 +1108,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int total_pairs = (p.m_tiles + 1) >> 1;  // a CTA pair owns two consecutive 16x16 tiles; n_tiles == 1
 
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
-        for (int s = 0; s < B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
+        // "empty" and accumulator-full barriers collect the commits of both MMA issuers
+        for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 2); }
+        for (int s = 0; s < B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 2); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 2); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
         if (RES) for (int s = 0; s < 2 * RC; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kEpiWarps / 2); }
         if (PM) for (int s = 0; s < 2; ++s) mbar_init(bxfull_bar(s), 2);  // one arrival per CTA of the pair
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1176,35 +1178,36 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             for (int i = 0; i < A_STAGES; ++i) { mbar_wait(aempty(sa), pa ^ 1u); if (++sa == A_STAGES) { sa = 0; pa ^= 1u; } }
             for (int i = 0; i < B_STAGES; ++i) { mbar_wait(bempty(sb), pb ^ 1u); if (++sb == B_STAGES) { sb = 0; pb ^= 1u; } }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
+    } else if (warp == 1 || warp == kIssue2Warp) {
+        // ===== two MMA issuers, one per column block.  A single thread needs ~100 cycles of dependent instructions per
+        // tcgen05.mma (descriptor moves into uniform registers + the elect wrapper), which capped every N <= 128 layer at the
+        // issue rate instead of the tensor pipe; the two column blocks accumulate into disjoint tensor-memory columns, so
+        // they are issued independently.  Every smem-stage / accumulator barrier therefore counts two commits. =====
         if (lane == 0 && rank == 0) {
             constexpr uint32_t idesc = make_idesc(BLOCK_N, 256);  // M 256 = column block `blk` of both CTAs
+            const int blk = warp == 1 ? 0 : 1;
             int sa = 0, sb = 0, acc = 0;
             uint32_t pa = 0, pb = 0, acc_phase = 0;
             for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BLOCK_N);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BLOCK_N + blk * BLOCK_N);
                 uint32_t first = 1;
                 for (int c = 0; c < p.cin_chunks; ++c) {
                     for (int dx = 0; dx < 3; ++dx) {
                         mbar_wait(afull(sa), pa);
                         tc_fence_after();
-                        const uint32_t a_base = base + sa * L::a_stage;
+                        const uint32_t a_base = base + sa * L::a_stage + blk * kSlabBytes;
                         for (int dy = 0; dy < 3; ++dy) {
                             mbar_wait(bfull(sb), pb);
                             tc_fence_after();
                             const uint64_t bdesc = make_smem_desc(base + L::off_b + sb * L::b_stage);
+                            // vertical tap dy = start one pixel row (8 px x 128 B) further down the slab
+                            const uint64_t adesc = make_smem_desc(a_base + dy * 1024);
 #pragma unroll
-                            for (int blk = 0; blk < 2; ++blk) {
-                                // vertical tap dy = start one pixel row (8 px x 128 B) further down the slab
-                                const uint64_t adesc = make_smem_desc(a_base + blk * kSlabBytes + dy * 1024);
-#pragma unroll
-                                for (int kk = 0; kk < kBlockK / 16; ++kk)
-                                    tc_mma2_f16(d_tmem + (uint32_t)(blk * BLOCK_N), adesc + (uint64_t)(kk * 2),
-                                               bdesc + (uint64_t)(kk * 2), idesc, (first && kk == 0) ? 0u : 1u);
-                            }
+                            for (int kk = 0; kk < kBlockK / 16; ++kk)
+                                tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                           (first && kk == 0) ? 0u : 1u);
                             first = 0;
                             tc_commit2(bempty(sb));
                             if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
@@ -1216,11 +1219,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (PM) {
                     mbar_wait_cluster(bxfull_bar(acc), acc_phase);  // both CTAs' coefficient tiles of this pair iteration
                     tc_fence_after();
-                    const uint64_t bdesc = make_smem_desc_nosw(base + L::off_pm + 2 * 4096 + acc * L::pm_b, (BLOCK_N / 2) * 16, 128);
-#pragma unroll
-                    for (int blk = 0; blk < 2; ++blk)
-                        tc_mma2_f16(d_tmem + (uint32_t)(blk * BLOCK_N), make_smem_desc_nosw(base + L::off_pm + blk * 4096, 2048, 128),
-                                   bdesc, idesc, 1u);
+                    tc_mma2_f16(d_tmem, make_smem_desc_nosw(base + L::off_pm + blk * 4096, 2048, 128),
+                               make_smem_desc_nosw(base + L::off_pm + 2 * 4096 + acc * L::pm_b, (BLOCK_N / 2) * 16, 128), idesc, 1u);
                 }
                 tc_commit2(tfull_bar(acc));
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -1288,7 +1288,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (PM) {
+    } else if (PM && warp == kAuxWarp) {
         // ===== auxiliary warp: basis tiles once, then the coefficient tile of every pair iteration (stage = iteration & 1) =====
         for (int r = lane; r < 256; r += 32)
             pm_write_basis(base_ptr + L::off_pm + (r >> 7) * 4096, r & 127, (r & 127) >> 3, (r >> 7) * 8 + (r & 7), rank);
