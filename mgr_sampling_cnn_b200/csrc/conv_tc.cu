@@ -102,6 +102,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// one elected lane of a converged warp (cute::elect_one_sync): the warp runs the issue loop convergently, so descriptor
+// arithmetic stays in uniform registers and each tcgen05.mma needs no per-lane operand broadcast
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -390,7 +401,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected thread) =====
-        if (lane == 0) {
+        {  // the whole warp runs the loop (uniform control flow: descriptors stay in uniform registers); one lane issues
             constexpr uint32_t idesc = make_idesc(BLOCK_N);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -403,13 +414,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(base + stage * L::a_stage);
                     const uint64_t bdesc = make_smem_desc(base + L::off_b + stage * L::b_stage);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < kBlockK / 16; ++kk)  // UMMA_K = 16: +32 bytes inside the swizzle row
-                        tc_mma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
-                    tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+                        for (int kk = 0; kk < kBlockK / 16; ++kk)  // UMMA_K = 16: +32 bytes inside the swizzle row
+                            tc_mma_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                        tc_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(tfull_bar(acc));  // accumulator complete
+                if (elect_one()) tc_commit(tfull_bar(acc));  // accumulator complete
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -741,7 +756,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
     } else if (warp == 1) {
         // ===== MMA issuer: one thread of the leader CTA drives both SMs' tensor cores (M = 256 per instruction) =====
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {  // the whole warp runs the loop (uniform control flow: descriptors stay in uniform registers)
             constexpr uint32_t idesc = make_idesc(BLOCK_N, 256);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -754,19 +769,25 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tc_fence_after();
                     const uint64_t adesc = make_smem_desc(base + stage * L::a_stage);
                     const uint64_t bdesc = make_smem_desc(base + L::off_b + stage * L::b_stage);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < kBlockK / 16; ++kk)  // UMMA_K = 16: +32 bytes inside the swizzle row
-                        tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
-                    tc_commit2(empty_bar(stage));  // frees the smem slot in both CTAs once these MMAs have read it
+                        for (int kk = 0; kk < kBlockK / 16; ++kk)  // UMMA_K = 16: +32 bytes inside the swizzle row
+                            tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (k | kk) ? 1u : 0u);
+                        tc_commit2(empty_bar(stage));  // frees the smem slot in both CTAs once these MMAs have read it
+                    }
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 if (PM) {
                     mbar_wait_cluster(bxfull_bar(acc), acc_phase);  // both CTAs' coefficient tiles of this pair iteration
                     tc_fence_after();
-                    tc_mma2_f16(d_tmem, make_smem_desc_nosw(base + L::off_pm, 2048, 128),
-                               make_smem_desc_nosw(base + L::off_pm + 4096 + acc * L::pm_b, (BLOCK_N / 2) * 16, 128), idesc, 1u);
+                    if (elect_one())
+                        tc_mma2_f16(d_tmem, make_smem_desc_nosw(base + L::off_pm, 2048, 128),
+                                   make_smem_desc_nosw(base + L::off_pm + 4096 + acc * L::pm_b, (BLOCK_N / 2) * 16, 128), idesc, 1u);
+                    __syncwarp();
                 }
-                tc_commit2(tfull_bar(acc));  // accumulator complete in both CTAs' tensor memory
+                if (elect_one()) tc_commit2(tfull_bar(acc));  // accumulator complete in both CTAs' tensor memory
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
@@ -1183,7 +1204,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         // tcgen05.mma (descriptor moves into uniform registers + the elect wrapper), which capped every N <= 128 layer at the
         // issue rate instead of the tensor pipe; the two column blocks accumulate into disjoint tensor-memory columns, so
         // they are issued independently.  Every smem-stage / accumulator barrier therefore counts two commits. =====
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {  // the whole warp runs the loop (uniform control flow); one elected lane issues
             constexpr uint32_t idesc = make_idesc(BLOCK_N, 256);  // M 256 = column block `blk` of both CTAs
             const int blk = warp == 1 ? 0 : 1;
             int sa = 0, sb = 0, acc = 0;
@@ -1204,25 +1225,32 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                             const uint64_t bdesc = make_smem_desc(base + L::off_b + sb * L::b_stage);
                             // vertical tap dy = start one pixel row (8 px x 128 B) further down the slab
                             const uint64_t adesc = make_smem_desc(a_base + dy * 1024);
+                            if (elect_one()) {
 #pragma unroll
-                            for (int kk = 0; kk < kBlockK / 16; ++kk)
-                                tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
-                                           (first && kk == 0) ? 0u : 1u);
+                                for (int kk = 0; kk < kBlockK / 16; ++kk)
+                                    tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                                               (first && kk == 0) ? 0u : 1u);
+                                tc_commit2(bempty(sb));
+                            }
+                            __syncwarp();
                             first = 0;
-                            tc_commit2(bempty(sb));
                             if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
                         }
-                        tc_commit2(aempty(sa));
+                        if (elect_one()) tc_commit2(aempty(sa));
+                        __syncwarp();
                         if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
                     }
                 }
                 if (PM) {
                     mbar_wait_cluster(bxfull_bar(acc), acc_phase);  // both CTAs' coefficient tiles of this pair iteration
                     tc_fence_after();
-                    tc_mma2_f16(d_tmem, make_smem_desc_nosw(base + L::off_pm + blk * 4096, 2048, 128),
-                               make_smem_desc_nosw(base + L::off_pm + 2 * 4096 + acc * L::pm_b, (BLOCK_N / 2) * 16, 128), idesc, 1u);
+                    if (elect_one())
+                        tc_mma2_f16(d_tmem, make_smem_desc_nosw(base + L::off_pm + blk * 4096, 2048, 128),
+                                   make_smem_desc_nosw(base + L::off_pm + 2 * 4096 + acc * L::pm_b, (BLOCK_N / 2) * 16, 128), idesc, 1u);
+                    __syncwarp();
                 }
-                tc_commit2(tfull_bar(acc));
+                if (elect_one()) tc_commit2(tfull_bar(acc));
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
