@@ -187,6 +187,7 @@ typedef struct NrrtConvLayer {
     int32_t res_n;           /* samples in the residual buffer (0 = n) */
     int32_t no_poly_mma;     /* testing: evaluate the whole polynomial term in the epilogue (default: the interior polynomial
                                 of residual-carrying 3x3 layers is one extra tensor-core MMA per tile) */
+    int32_t no_tma_store;    /* testing: direct global stores from the epilogue threads instead of staged TMA stores */
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);

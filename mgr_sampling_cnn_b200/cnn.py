@@ -124,6 +124,7 @@ class _Layer(object):
 
     force_per_tap = False  # tests: run the generic per-tap kernel where the slab kernel would be chosen
     no_poly_mma = False    # tests: evaluate the whole polynomial term in the epilogue
+    no_tma_store = False   # tests: direct global stores instead of the staged TMA-store epilogue
 
     def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None, head=None, x2=None,
             idx=None, idx2=None, n=None, res_idx=None):
@@ -166,6 +167,7 @@ class _Layer(object):
             L.head_weight, L.head_bias, L.logits = _ptr(head[0]), float(head[1]), _ptr(head[2])
         L.force_per_tap = 1 if self.force_per_tap else 0
         L.no_poly_mma = 1 if self.no_poly_mma else 0
+        L.no_tma_store = 1 if self.no_tma_store else 0
         if res is not None:
             L.res, L.res_cstride, L.res_coffset = _ptr(res), res.shape[-1], res_coff
             L.res_n = res.shape[0]

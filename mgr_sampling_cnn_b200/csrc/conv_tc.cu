@@ -60,6 +60,7 @@ struct ConvParams {
     const float* poly;   // optional [N][poly_cases][4][cout]: bilinear epilogue term E0 + ty*E1 + tx*E2 + ty*tx*E3
     int poly_cases;      // 9 = 3x3 border cases (row case * 3 + column case); else one case per weight group
     float inv_h, inv_w;  // 1/(H-1), 1/(W-1) of the tile-space grid
+    int ts;              // pair kernels: output tile staged in shared memory and written with TMA stores (see below)
     int pm;              // pair kernels: interior polynomial applied by one extra tcgen05.mma per tile (see pm_* below)
     const float* head_w; // optional fused 1x1 head (cout -> 1): logits[pixel] = head_b + sum_c relu_out[c] * head_w[c]
     float head_b;
@@ -113,6 +114,24 @@ __device__ __forceinline__ bool elect_one() {
         : "=r"(pred));
     return pred != 0;
 }
+// ---- TMA-store epilogue (pair kernels) ------------------------------------------------------------------------------
+// A thread owns one pixel row of the accumulator, so direct stores put 16 bytes per lane at a 2*Ctot-byte stride: 32 partial
+// sectors per instruction, which made the store path 20-40 % of every full-resolution layer.  Instead the epilogue warps
+// write their fp16 results into 64-channel pieces in shared memory (128 pixel rows x 128 B, SWIZZLE_128B -- for layers with
+// a residual, in place over the staged residual piece they have just read), and the auxiliary warp writes each finished
+// piece with ONE cp.async.bulk.tensor store (full 128-byte lines; TMA clips rows outside the image).
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+// commit the store just issued and wait until it has been read out of shared memory.  (Keeping one store in flight and
+// freeing the piece one step later was measured slower: the next residual load of that piece starts too late.)
+__device__ __forceinline__ void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_drain() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -166,7 +185,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
                                                int h, int w, const float* sc, const float* sh, const float* sc2,
                                                const float* sh2, const float* pe, int pe_stride, float& head_acc,
                                                const uint8_t* res_row = nullptr, int res_r7 = 0, bool pm = false,
-                                               int frame = 0) {
+                                               int frame = 0, uint8_t* stg_row = nullptr) {
     const int g = col / p.cout, co = col - g * p.cout;
     int od = d, oh = h, ow = w;
     if (p.up == 2) {
@@ -248,6 +267,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
         return;
     }
     uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_coffset + co);
+    const int sj0 = (lc & 63) >> 3;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         uint4 ov;
@@ -258,7 +278,8 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
             const float b = fminf(fmaxf(f[q * 8 + e * 2 + 1], -65504.f), 65504.f);
             hv[e] = __floats2half2_rn(a, b);
         }
-        op[q] = ov;
+        if (stg_row) *reinterpret_cast<uint4*>(stg_row + (((sj0 + q) ^ res_r7) << 4)) = ov;  // staged for the TMA store
+        else op[q] = ov;
     }
 }
 
@@ -631,16 +652,16 @@ __device__ __forceinline__ void pm_produce_b(const ConvParams& p, uint8_t* bx, i
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-template <int BLOCK_N, int STAGES, bool RES, bool PM>
+template <int BLOCK_N, int STAGES, bool RES, bool PM, bool TS>
 struct SmemLayout2 {  // per CTA of a pair: its own A tile and HALF of the B tile per stage
     static constexpr uint32_t a_stage = kBlockM * 128;
     static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
     static constexpr uint32_t off_b = STAGES * a_stage;
     static constexpr uint32_t off_res = off_b + STAGES * b_stage;  // TMA-staged residual tile: BLOCK_N / 64 pieces
-    static constexpr uint32_t off_pm = off_res + (RES ? (BLOCK_N / 64) * kResPiece : 0);  // basis tile (4 KB), then 2 coefficient tiles
+    static constexpr uint32_t off_pm = off_res + ((RES || TS) ? (BLOCK_N / 64) * kResPiece : 0);  // basis tile (4 KB), then 2 coefficient tiles
     static constexpr uint32_t pm_b = (BLOCK_N / 2) * 32;
     static constexpr uint32_t off_bar = off_pm + (PM ? 4096 + 2 * pm_b : 0);
-    static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4 + 2 * kMaxResPieces + 2) * 8;
+    static constexpr uint32_t off_tmem = off_bar + (2 * STAGES + 4 + 3 * kMaxResPieces + 2) * 8;
     static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
     static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
 };
@@ -655,12 +676,13 @@ struct SmemLayout2 {  // per CTA of a pair: its own A tile and HALF of the B til
 // TMA in 64-channel pieces, each with a full/empty barrier pair, so the epilogue never waits on a global load: the piece
 // of tile i+1 is requested as soon as every epilogue warp has consumed that piece of tile i.
 // PM: the interior polynomial coordinate term is one extra MMA per tile (pm_* above; 2D 3x3 layers, n_tiles == 1).
-template <int BLOCK_N, int STAGES, bool RES, bool PM>
+// TS: TMA-store epilogue (64-channel pieces shared with the residual staging; the auxiliary warp issues the stores).
+template <int BLOCK_N, int STAGES, bool RES, bool PM, bool TS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_r,
-                 const __grid_constant__ ConvParams p) {
-    using L = SmemLayout2<BLOCK_N, STAGES, RES, PM>;
+                 const __grid_constant__ CUtensorMap map_o, const __grid_constant__ ConvParams p) {
+    using L = SmemLayout2<BLOCK_N, STAGES, RES, PM, TS>;
     constexpr int RP = BLOCK_N / 64;  // residual pieces
     constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
     extern __shared__ uint8_t smem_raw[];
@@ -673,7 +695,8 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
     auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + s); };
     auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + kMaxResPieces + s); };
-    auto bxfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + 2 * kMaxResPieces + s); };
+    auto sdone_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + 2 * kMaxResPieces + s); };
+    auto bxfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 4 + 3 * kMaxResPieces + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
     float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
 
@@ -687,7 +710,10 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         // the leader's tempty barrier collects the epilogue warps of BOTH CTAs
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
-        if (RES) for (int s = 0; s < RP; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kEpiWarps); }
+        if (RES || TS)  // piece free: all epilogue warps, or (TS) the store warp once the piece has been read out
+            for (int s = 0; s < RP; ++s) {
+                mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), TS ? 1 : kEpiWarps); mbar_init(sdone_bar(s), kEpiWarps);
+            }
         if (PM) for (int s = 0; s < 2; ++s) mbar_init(bxfull_bar(s), 2);  // one arrival per CTA of the pair
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -840,38 +866,42 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     uint32_t v[32];
                     tc_ld32(taddr + (uint32_t)(c * 32), v);
                     const uint8_t* rrow = nullptr;
-                    if (RES) {  // every warp touches each 64-channel piece exactly once (c_step == 2: no fused head with RES)
+                    uint8_t* srow = nullptr;
+                    if (RES) {  // every warp touches each 64-channel piece exactly once (c_step == 2: no fused head with RES / TS)
                         mbar_wait(rfull_bar(c >> 1), rphase);
                         rrow = base_ptr + L::off_res + (c >> 1) * kResPiece + row * 128;
+                    } else if (TS) {
+                        mbar_wait(rempty_bar(c >> 1), rphase ^ 1u);  // the previous tile's store has read the piece out
                     }
+                    if (TS) srow = base_ptr + L::off_res + (c >> 1) * kResPiece + row * 128;
                     if (valid)
                         epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
-                                       sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame);
-                    if (RES) {
+                                       sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame, srow);
+                    if (RES || TS) {
+                        if (TS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(rempty_bar(c >> 1));
+                        if (lane == 0) mbar_arrive(TS ? sdone_bar(c >> 1) : rempty_bar(c >> 1));
                     }
                 }
                 if (valid && p.logits) p.logits[(((long long)n * p.oD + d) * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             }
-            if (RES) rphase ^= 1u;
+            if (RES || TS) rphase ^= 1u;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty_bar(acc));  // the leader's MMA thread waits for both CTAs' epilogues
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (PM && warp == kAuxWarp) {
-        // ===== auxiliary warp: basis tile once, then the coefficient tile of every pair iteration (stage = iteration & 1) =====
-        for (int r = lane; r < 128; r += 32) pm_write_basis(base_ptr + L::off_pm, r, (r / p.bw) % p.bh, r % p.bw, rank);
-        int it = 0;
-        for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++it) {
-            const int a = it & 1;
-            if (it >= 2) mbar_wait(tfull_bar(a), (uint32_t)(((it >> 1) - 1) & 1));  // MMAs of iteration it - 2 are done
+    } else if ((PM || TS) && warp == kAuxWarp) {
+        // ===== auxiliary warp: polynomial coefficient tiles one pair iteration ahead (PM) and the TMA stores of finished
+        // output pieces (TS) =====
+        auto produce = [&](int q, int itq) {
+            const int a = itq & 1;
+            if (itq >= 2) mbar_wait(tfull_bar(a), (uint32_t)(((itq >> 1) - 1) & 1));  // MMAs of iteration itq - 2 are done
             int tn[2], th0[2], tw0[2];
             bool tlive[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                int mj = pt * 2 + j;  // n_tiles == 1
+                int mj = q * 2 + j;  // n_tiles == 1
                 tlive[j] = mj < p.m_tiles;
                 tw0[j] = (mj % p.tiles_w) * p.bw; mj /= p.tiles_w;
                 th0[j] = (mj % p.tiles_h) * p.bh; mj /= p.tiles_h;
@@ -880,7 +910,45 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             pm_produce_b<BLOCK_N / 2>(p, base_ptr + L::off_pm + 4096 + a * L::pm_b, lane, 32, rank, tn, th0, tw0, tlive);
             __syncwarp();
             if (lane == 0) mbar_arrive_leader_release(bxfull_bar(a));
+        };
+        if (PM) {
+            for (int r = lane; r < 128; r += 32) pm_write_basis(base_ptr + L::off_pm, r, (r / p.bw) % p.bh, r % p.bw, rank);
+            if (cluster_id < total_pairs) produce(cluster_id, 0);
         }
+        int it = 0;
+        uint32_t sphase = 0;
+        for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++it) {
+            if (PM && pt + n_clusters < total_pairs) produce(pt + n_clusters, it + 1);
+            if (TS) {
+                const int n_tile = pt % p.n_tiles;
+                int m = (pt / p.n_tiles) * 2 + (int)rank;
+                const bool live = m < p.m_tiles;
+                const int tw = m % p.tiles_w; m /= p.tiles_w;
+                const int th = m % p.tiles_h; m /= p.tiles_h;
+                const int td = m % p.tiles_d;
+                const int n = m / p.tiles_d;
+                for (int s = 0; s < RP; ++s) {
+                    mbar_wait(sdone_bar(s), sphase);
+                    if (lane == 0) {
+                        if (live) {
+                            const int col = n_tile * BLOCK_N + s * 64;
+                            const int gq = col / p.cout, co = col - gq * p.cout;  // ConvTranspose: weight group = output offset
+                            int ow = tw * p.bw * p.up, oh = th * p.bh * p.up, od = td * p.bd * p.up_d;
+                            if (p.up == 2) {
+                                if (p.up_d == 2) { od += gq >> 2; oh += (gq >> 1) & 1; ow += gq & 1; }
+                                else { oh += gq >> 1; ow += gq & 1; }
+                            }
+                            tma_store_5d(&map_o, base + L::off_res + s * kResPiece, (int)p.out_coffset + co, ow, oh, od, n);
+                        }
+                        tma_store_commit_and_wait_read();
+                        mbar_arrive(rempty_bar(s));  // free for the next residual load / the next tile's results
+                    }
+                    __syncwarp();
+                }
+                sphase ^= 1u;
+            }
+        }
+        if (TS && lane == 0) tma_store_drain();  // stores complete before the CTA exits
     }
 
     tc_fence_before();
@@ -1081,16 +1149,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM>
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM, bool TS>
 struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
     static constexpr uint32_t a_stage = 2 * kSlabBytes;
     static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
     static constexpr uint32_t off_b = A_STAGES * a_stage;
     static constexpr uint32_t off_res = off_b + B_STAGES * b_stage;  // residual pieces [column block][64-channel chunk]
-    static constexpr uint32_t off_pm = off_res + (RES ? 2 * (BLOCK_N / 64) * kResPiece : 0);  // basis tiles (2 x 4 KB), then
+    static constexpr uint32_t off_pm = off_res + ((RES || TS) ? 2 * (BLOCK_N / 64) * kResPiece : 0);  // basis tiles (2 x 4 KB), then
     static constexpr uint32_t pm_b = (BLOCK_N / 2) * 32;                                     // 2 coefficient tiles
     static constexpr uint32_t off_bar = off_pm + (PM ? 2 * 4096 + 2 * pm_b : 0);
-    static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4 + 2 * kMaxResPieces + 2) * 8;
+    static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4 + 3 * kMaxResPieces + 2) * 8;
     static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
     static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
 };
@@ -1099,12 +1167,13 @@ struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
 // M256 = column block `blk` of both CTAs, and each CTA loads (and feeds from its shared memory) only half of each B tile.
 // RES: TMA-staged residual tile as in conv_gemm2_kernel; a piece = (column block, 64-channel chunk) = 128 pixels x 128 B.
 // PM: the interior polynomial coordinate term is one extra MMA per accumulator (pm_* above).
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM>
+// TS: TMA-store epilogue (pieces shared with the residual staging; the auxiliary warp issues the stores).
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM, bool TS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_r,
-                 const __grid_constant__ ConvParams p) {
-    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM>;
+                 const __grid_constant__ CUtensorMap map_o, const __grid_constant__ ConvParams p) {
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS>;
     constexpr int RC = BLOCK_N / 64;  // 64-channel chunks per column block; residual pieces = 2 * RC
     constexpr int TMEM_COLS = 4 * BLOCK_N;  // 2 accumulator stages x 2 column blocks
     extern __shared__ uint8_t smem_raw[];
@@ -1119,7 +1188,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 2 + s); };
     auto rfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + s); };
     auto rempty_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + kMaxResPieces + s); };
-    auto bxfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + 2 * kMaxResPieces + s); };
+    auto sdone_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + 2 * kMaxResPieces + s); };
+    auto bxfull_bar = [&](int s) { return bar0 + 8u * (2 * A_STAGES + 2 * B_STAGES + 4 + 3 * kMaxResPieces + s); };
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::off_tmem);
     float* ss = reinterpret_cast<float*>(base_ptr + L::off_ss);
 
@@ -1133,7 +1203,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int s = 0; s < A_STAGES; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 2); }
         for (int s = 0; s < B_STAGES; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 2); }
         for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 2); mbar_init(tempty_bar(s), 2 * kEpiWarps); }
-        if (RES) for (int s = 0; s < 2 * RC; ++s) { mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), kEpiWarps / 2); }
+        if (RES || TS)  // piece free: the four warps of its column block, or (TS) the store warp once the piece has been read out
+            for (int s = 0; s < 2 * RC; ++s) {
+                mbar_init(rfull_bar(s), 1); mbar_init(rempty_bar(s), TS ? 1 : kEpiWarps / 2); mbar_init(sdone_bar(s), kEpiWarps / 2);
+            }
         if (PM) for (int s = 0; s < 2; ++s) mbar_init(bxfull_bar(s), 2);  // one arrival per CTA of the pair
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -1297,39 +1370,42 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tc_ld32(taddr + (uint32_t)(c * 32), v);
                 const int piece = blk * RC + (c >> 1);
                 const uint8_t* rrow = nullptr;
+                uint8_t* srow = nullptr;
                 if (RES) {
                     if (!(c & 1)) mbar_wait(rfull_bar(piece), rphase);
                     rrow = base_ptr + L::off_res + piece * kResPiece + row * 128;
+                } else if (TS) {
+                    if (!(c & 1)) mbar_wait(rempty_bar(piece), rphase ^ 1u);  // the previous tile's store has read the piece out
                 }
+                if (TS) srow = base_ptr + L::off_res + piece * kResPiece + row * 128;
                 if (valid)
                     epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
-                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame);
-                if (RES && (c & 1)) {  // both 32-column halves of the piece are consumed
+                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame, srow);
+                if ((RES || TS) && (c & 1)) {  // both 32-column halves of the piece are done
+                    if (TS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(rempty_bar(piece));
+                    if (lane == 0) mbar_arrive(TS ? sdone_bar(piece) : rempty_bar(piece));
                 }
             }
-            if (RES) rphase ^= 1u;
+            if (RES || TS) rphase ^= 1u;
             if (valid && p.logits) p.logits[((long long)n * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-    } else if (PM && warp == kAuxWarp) {
-        // ===== auxiliary warp: basis tiles once, then the coefficient tile of every pair iteration (stage = iteration & 1) =====
-        for (int r = lane; r < 256; r += 32)
-            pm_write_basis(base_ptr + L::off_pm + (r >> 7) * 4096, r & 127, (r & 127) >> 3, (r >> 7) * 8 + (r & 7), rank);
-        int it = 0;
-        for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++it) {
-            const int a = it & 1;
-            // the stage was last read by the MMAs of iteration it - 2: wait for that accumulator's commit
-            if (it >= 2) mbar_wait(tfull_bar(a), (uint32_t)(((it >> 1) - 1) & 1));
+    } else if ((PM || TS) && warp == kAuxWarp) {
+        // ===== auxiliary warp: polynomial coefficient tiles one pair iteration ahead (PM) and the TMA stores of finished
+        // output pieces (TS) =====
+        auto produce = [&](int q, int itq) {  // coefficient tile of pair iteration q (the itq-th of this pair) into stage itq & 1
+            const int a = itq & 1;
+            // the stage was last read by the MMAs of iteration itq - 2: wait for that accumulator's commit
+            if (itq >= 2) mbar_wait(tfull_bar(a), (uint32_t)(((itq >> 1) - 1) & 1));
             int tn[2], th0[2], tw0[2];
             bool tlive[2];
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                int mj = pt * 2 + j;
+                int mj = q * 2 + j;
                 tlive[j] = mj < p.m_tiles;
                 tw0[j] = (mj % p.tiles_w) * 16; mj /= p.tiles_w;
                 th0[j] = (mj % p.tiles_h) * 16;
@@ -1338,7 +1414,39 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             pm_produce_b<BLOCK_N / 2>(p, base_ptr + L::off_pm + 2 * 4096 + a * L::pm_b, lane, 32, rank, tn, th0, tw0, tlive);
             __syncwarp();
             if (lane == 0) mbar_arrive_leader_release(bxfull_bar(a));  // one arrival per CTA of the pair
+        };
+        if (PM) {
+            for (int r = lane; r < 256; r += 32)
+                pm_write_basis(base_ptr + L::off_pm + (r >> 7) * 4096, r & 127, (r & 127) >> 3, (r >> 7) * 8 + (r & 7), rank);
+            if (cluster_id < total_pairs) produce(cluster_id, 0);
         }
+        int it = 0;
+        uint32_t sphase = 0;
+        for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++it) {
+            if (PM && pt + n_clusters < total_pairs) produce(pt + n_clusters, it + 1);
+            if (TS) {
+                int m = pt * 2 + (int)rank;
+                const bool live = m < p.m_tiles;
+                const int tw = m % p.tiles_w; m /= p.tiles_w;
+                const int th = m % p.tiles_h;
+                const int n = m / p.tiles_h;
+                for (int k = 0; k < RC; ++k)
+                    for (int b = 0; b < 2; ++b) {  // order in which the epilogue finishes them
+                        const int piece = b * RC + k;
+                        mbar_wait(sdone_bar(piece), sphase);
+                        if (lane == 0) {
+                            if (live)
+                                tma_store_5d(&map_o, base + L::off_res + piece * kResPiece, (int)p.out_coffset + k * 64,
+                                             tw * 16 + b * 8, th * 16, 0, n);
+                            tma_store_commit_and_wait_read();
+                            mbar_arrive(rempty_bar(piece));  // free for the next residual load / the next tile's results
+                        }
+                        __syncwarp();
+                    }
+                sphase ^= 1u;
+            }
+        }
+        if (TS && lane == 0) tma_store_drain();  // stores complete before the CTA exits
     }
 
     tc_fence_before();
@@ -1379,30 +1487,30 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap
     return NRRT_OK;
 }
 
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM = false>
-int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const ConvParams& p,
-                 int sms, cudaStream_t st) {
-    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM>;
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM = false, bool TS = false>
+int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo,
+                 const ConvParams& p, int sms, cudaStream_t st) {
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS>;
     static_assert(L::total <= 232448, "shared memory budget");
-    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES, PM>;
+    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int pairs = (p.m_tiles + 1) / 2;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
-    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, p);
+    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, mo, p);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }
 
-template <int BLOCK_N, int STAGES, bool RES, bool PM = false>
-int launch_conv2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const ConvParams& p,
-                 int sms, cudaStream_t st) {
-    using L = SmemLayout2<BLOCK_N, STAGES, RES, PM>;
+template <int BLOCK_N, int STAGES, bool RES, bool PM = false, bool TS = false>
+int launch_conv2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo,
+                 const ConvParams& p, int sms, cudaStream_t st) {
+    using L = SmemLayout2<BLOCK_N, STAGES, RES, PM, TS>;
     static_assert(L::total <= 232448, "shared memory budget");
-    auto kern = conv_gemm2_kernel<BLOCK_N, STAGES, RES, PM>;
+    auto kern = conv_gemm2_kernel<BLOCK_N, STAGES, RES, PM, TS>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);  // whole CTA pairs (static cluster dims 2x1x1)
-    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, p);
+    kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, mo, p);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }
@@ -1560,6 +1668,21 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     }
     // pair kernels stage the residual tile through shared memory with TMA (output grid, 64-channel pieces)
     const bool tma_res = pair && l->res && up == 1 && !l->logits && l->cout % 64 == 0 && l->res_coffset % 64 == 0;
+    // TMA-store epilogue: pair kernels with a stored output of whole 64-channel pieces (N = 128 slab kernel for now)
+    p.ts = (pair && block_n >= 128 && !l->logits && l->out && l->cout % 64 == 0 && !l->no_tma_store) ? 1 : 0;
+    CUtensorMap mo = ma;
+    if (p.ts) {
+        const cuuint64_t gdim[5] = {(cuuint64_t)l->out_cstride, (cuuint64_t)p.oW, (cuuint64_t)p.oH, (cuuint64_t)p.oD, (cuuint64_t)N};
+        const cuuint64_t cs = (cuuint64_t)l->out_cstride * 2;
+        const cuuint64_t gstr[4] = {cs, cs * p.oW, cs * p.oW * p.oH, cs * p.oW * p.oH * p.oD};
+        cuuint32_t box[5] = {64, (cuuint32_t)(p.bw * up), (cuuint32_t)(p.bh * up), (cuuint32_t)(p.bd * p.up_d), 1};
+        if (halo) { box[1] = 8; box[2] = 16; box[3] = 1; }
+        const cuuint32_t estr[5] = {1, (cuuint32_t)up, (cuuint32_t)up, (cuuint32_t)p.up_d, 1};
+        const CUresult r = encode(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, l->out, gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
+    }
     // interior polynomial through the tensor core: 2D 3x3 convs on the pair kernels with a staged residual (conv7.0 / conv8.0)
     p.pm = (tma_res && l->poly && l->poly_cases == 9 && p.n_tiles == 1 && !l->no_poly_mma && !three_d && !l->post_scale &&
             ((halo && block_n == 128) || (!halo && block_n == 256 && l->kind == NRRT_CONV_K3S1 && p.rows == 128)) &&
@@ -1582,26 +1705,38 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (halo && pair) {
-        if (tma_res) {
-            if (block_n == 128 && p.pm) return launch_halo2<128, 3, 4, true, true>(ma, ma2, mb, mr, p, sms, st);
-            if (block_n == 128) return launch_halo2<128, 3, 5, true>(ma, ma2, mb, mr, p, sms, st);
-            return launch_halo2<64, 4, 8, true>(ma, ma2, mb, mr, p, sms, st);
+        if (block_n == 128 && p.ts) {
+            if (tma_res && p.pm) return launch_halo2<128, 3, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (tma_res) return launch_halo2<128, 3, 5, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            return launch_halo2<128, 3, 5, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
         }
-        if (block_n == 128) return launch_halo2<128, 4, 6, false>(ma, ma2, mb, mr, p, sms, st);
-        return launch_halo2<64, 4, 8, false>(ma, ma2, mb, mr, p, sms, st);
+        if (tma_res) {
+            if (block_n == 128) return launch_halo2<128, 3, 5, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            return launch_halo2<64, 4, 8, true>(ma, ma2, mb, mr, mo, p, sms, st);
+        }
+        if (block_n == 128) return launch_halo2<128, 4, 6, false>(ma, ma2, mb, mr, mo, p, sms, st);
+        return launch_halo2<64, 4, 8, false>(ma, ma2, mb, mr, mo, p, sms, st);
     }
     if (halo) {
         if (block_n == 128) return launch_halo<128, 4, 4>(ma, ma2, mb, p, sms, st);
         return launch_halo<64, 4, 8>(ma, ma2, mb, p, sms, st);
     }
     if (pair) {
-        if (tma_res) {
-            if (block_n == 256 && p.pm) return launch_conv2<256, 4, true, true>(ma, ma2, mb, mr, p, sms, st);
-            if (block_n == 256) return launch_conv2<256, 4, true>(ma, ma2, mb, mr, p, sms, st);
-            return launch_conv2<128, 6, true>(ma, ma2, mb, mr, p, sms, st);
+        if (p.ts) {
+            if (block_n == 256) {
+                if (tma_res && p.pm) return launch_conv2<256, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
+                if (tma_res) return launch_conv2<256, 4, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+                return launch_conv2<256, 4, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            }
+            if (tma_res) return launch_conv2<128, 6, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            return launch_conv2<128, 6, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
         }
-        if (block_n == 256) return launch_conv2<256, 6, false>(ma, ma2, mb, mr, p, sms, st);
-        return launch_conv2<128, 8, false>(ma, ma2, mb, mr, p, sms, st);
+        if (tma_res) {
+            if (block_n == 256) return launch_conv2<256, 4, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            return launch_conv2<128, 6, true>(ma, ma2, mb, mr, mo, p, sms, st);
+        }
+        if (block_n == 256) return launch_conv2<256, 6, false>(ma, ma2, mb, mr, mo, p, sms, st);
+        return launch_conv2<128, 8, false>(ma, ma2, mb, mr, mo, p, sms, st);
     }
     if (block_n == 256) return launch_conv<256, 4>(ma, ma2, mb, p, sms, st);
     if (block_n == 128) return launch_conv<128, 6>(ma, ma2, mb, p, sms, st);
