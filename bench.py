@@ -54,6 +54,17 @@ def peaks():
     return {"tensor": 1400.0, "hbm": 6650.0, "which": "fallback (B200_PROFILING.md)"}
 
 
+def conv_traffic():
+    """DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of one
+    encoder pass + one decoder micro-batch (profiles/conv_traffic_r1.json), averaged over launches like `achieved`."""
+    path = os.path.join(ROOT, "profiles", "conv_traffic_r1.json")
+    if not os.path.exists(path):
+        return None, "no ncu capture committed"
+    with open(path) as f:
+        t = json.load(f)
+    return t["avg_dram_bytes_per_launch"], t["note"]
+
+
 class ClockSampler(object):
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -144,7 +155,7 @@ def run_reference(args):
         return
     dim = 2 if args.workload.startswith("2d") else 3
     tasks = args.tasks or (4096 if dim == 2 else 1024)
-    n_sample = args.ref_sample or (4 if not args.workload.endswith("uniform") else 32)
+    n_sample = args.ref_sample or (8 if not args.workload.endswith("uniform") else 32)
     wl = make_workload(args.workload, max(n_sample, 10), 0)
     model = None if args.workload.endswith("uniform") else make_model(dim)
     for _ in range(args.warmup):
@@ -283,9 +294,11 @@ def run_graft(args):
         if prof is not None:
             n_l, fl, t_ms = prof.totals()
             ach = fl / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0
-            roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, all layer shapes)",
+            traffic, traffic_note = conv_traffic()
+            roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel / conv_halo2_kernel (tcgen05 implicit-GEMM convolution, all "
+                                                     "34 layer shapes of the forward)",
                         "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                        "traffic": None, "peak_source": pk["which"], "launches_timed": n_l,
+                        "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["which"], "launches_timed": n_l,
                         "avg_launch_ms": t_ms / max(n_l, 1), "flops_per_launch_avg": fl / max(n_l, 1),
                         "step_share": {"cnn_ms": stage[0], "cdf_ms": stage[1], "draw_plan_ms": stage[2]}}  # last timed step
             if args.layer_table:
@@ -300,7 +313,7 @@ def run_graft(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                _, cpu = cpu_arm(args, wl, args.ref_sample or (4 if not uniform else 32), model=None)
+                _, cpu = cpu_arm(args, wl, args.ref_sample or (8 if not uniform else 32), model=None)
             except Exception as exc:  # the baseline is informational; never lose the GPU line over it
                 cpu = {"error": repr(exc)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

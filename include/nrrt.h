@@ -224,6 +224,11 @@ int nrrt_coords_fill(const float* feat, int B, int gh, int gw, int C, int dims, 
 int nrrt_coords_poly(const float* feat, int B, int Cc, const float* moments, int cases, int n_uv, int Cout, float a, float b,
                      float* E, void* stream);
 
+/* nrrt_coords_poly as one fp32 GEMM (the production path for large batches): moments_t = the same moments laid out
+ * [Cc][cases][n_uv][Cout]; work: fp32 scratch [B*4*Cc + B*4*cases*n_uv*Cout]. */
+int nrrt_coords_poly_gemm(const float* feat, int B, int Cc, const float* moments_t, int cases, int n_uv, int Cout, float a,
+                          float b, float* work, float* E, void* stream);
+
 /* conv6.0 hoisted out of the per-task path (2D; train.py:192-195).  The layer is linear in its input and only the
  * coordinate channels depend on the task, so its pre-activation = a per-map tensor (nrrt_conv_layer once per map) + a
  * per-task piecewise-bilinear field with 16 cases (4 row classes x 4 column classes: first / interior even / interior

@@ -290,6 +290,9 @@ class UNetPlan(object):
             self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(mu.weight[:512], dev), scale, shift, False)
             self.m_up6 = mu.weight.detach().float().to(dev)[512:].permute(2, 3, 0, 1).reshape(4, 1, 512, mu.out_channels).contiguous()
             self.m_c6, self.m_c7, self.m_c8 = conv_moments(model.conv6[0], 768), conv_moments(model.conv7[0], 256), conv_moments(model.conv8[0], 128)
+            # the same moments as GEMM operands [Cc][cases * n_uv * Cout] (nrrt_coords_poly_gemm)
+            self.mt = {k: m.permute(2, 0, 1, 3).reshape(m.shape[2], -1).contiguous()
+                       for k, m in (("e_up6", self.m_up6), ("e_c6", self.m_c6), ("e_c7", self.m_c7), ("e_c8", self.m_c8))}
             # conv6.0 is linear in (upconv6 output | x4 | coords): the whole GEMM runs once per map over (t6m | e4), the
             # task-dependent part is the 16-case polynomial of nrrt_poly16 applied by nrrt_poly_relu (csrc/conv_aux.cu)
             m6 = model.conv6[0]
@@ -453,8 +456,17 @@ class UNetPlan(object):
                 E = torch.empty((B, cases, 4, cout), dtype=torch.float32, device=dev)
                 a = 1.0 / (g[lv][1] - 1) if g[lv][1] > 1 else 0.0
                 b = 1.0 / (g[lv][2] - 1) if g[lv][2] > 1 else 0.0
-                _lib.count_launch()
-                check(self.lib.nrrt_coords_poly(_ptr(feat), B, cc, _ptr(mom), cases, n_uv, cout, a, b, _ptr(E), st))
+                if B >= 64:  # one fp32 GEMM over the batch (chunked so that the scratch stays small)
+                    chunk = 512
+                    work = torch.empty((min(B, chunk) * 4 * (cc + cases * n_uv * cout),), dtype=torch.float32, device=dev)
+                    for i in range(0, B, chunk):
+                        j = min(B, i + chunk)
+                        _lib.count_launch(3)
+                        check(self.lib.nrrt_coords_poly_gemm(_ptr(feat[i:j]), j - i, cc, _ptr(self.mt[name]), cases, n_uv, cout, a, b,
+                                                             _ptr(work), _ptr(E[i:j]), st))
+                else:
+                    _lib.count_launch()
+                    check(self.lib.nrrt_coords_poly(_ptr(feat), B, cc, _ptr(mom), cases, n_uv, cout, a, b, _ptr(E), st))
                 prep[name] = E
             # conv6.0's task-dependent term: 16-case polynomial from upconv6's and conv6.0's own coordinate channels
             cout = self.b6.shape[0]

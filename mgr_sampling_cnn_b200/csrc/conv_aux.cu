@@ -473,6 +473,45 @@ __global__ void __launch_bounds__(256) poly_relu_kernel(const __half* __restrict
     }
 }
 
+// ---- nrrt_coords_poly as a GEMM -------------------------------------------------------------------------------------
+// The direct kernel above re-reads the whole moment tensor per 4 tasks (16 ms for conv6.0 at 4096 tasks).  The same
+// contraction is C[(b, g)][(case, uv, co)] = sum_c G[b][g][c] * M[c][(case, uv, co)] with G = corner differences of the
+// coordinate feature (4 vectors per task): one pass of sgemm_kernel, then E is a few scaled sums of C entries.
+__global__ void __launch_bounds__(256) coords_g_kernel(const float* __restrict__ feat, long long total, int Cc, float* __restrict__ G) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / Cc;
+        const int c = (int)(i - b * Cc);
+        const float* f = feat + b * 4 * Cc + c;  // corners p = y*2 + x
+        const float f00 = f[0], f01 = f[Cc], f10 = f[2 * Cc], f11 = f[3 * Cc];
+        float* g = G + b * 4 * Cc + c;
+        g[0] = f00; g[Cc] = f10 - f00; g[2 * Cc] = f01 - f00; g[3 * Cc] = f00 - f01 - f10 + f11;
+    }
+}
+// Cw: [B][4 g][cases][n_uv][Cout];  E: [B][cases][4][Cout]
+__global__ void __launch_bounds__(256) coords_combine_kernel(const float* __restrict__ Cw, long long total, int cases, int n_uv,
+                                                             int Cout, float a, float b, float* __restrict__ E) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % Cout);
+        const long long t = i / Cout;
+        const int k = (int)(t % cases);
+        const long long bb = t / cases;
+        const size_t gs = (size_t)cases * n_uv * Cout;  // stride between the four G rows of a task
+        const float* c0 = Cw + (size_t)bb * 4 * gs + ((size_t)k * n_uv) * Cout + co;
+        float e0, e1, e2, e3;
+        if (n_uv == 1) {
+            e0 = c0[0]; e1 = c0[gs]; e2 = c0[2 * gs]; e3 = c0[3 * gs];
+        } else {  // uv order 00, 10, 01, 11
+            const size_t u = (size_t)Cout;
+            e0 = c0[0] + a * c0[gs + u] + b * c0[2 * gs + 2 * u] + (a * b) * c0[3 * gs + 3 * u];
+            e1 = c0[gs] + b * c0[3 * gs + 2 * u];
+            e2 = c0[2 * gs] + a * c0[3 * gs + u];
+            e3 = c0[3 * gs];
+        }
+        float* e = E + (((size_t)bb * cases + k) * 4) * Cout + co;
+        e[0] = e0; e[Cout] = e1; e[2 * (size_t)Cout] = e2; e[3 * (size_t)Cout] = e3;
+    }
+}
+
 int grid_for(long long work, int block) {
     long long g = (work + block - 1) / block;
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -592,6 +631,26 @@ extern "C" int nrrt_poly_relu(const void* pre, const int32_t* pre_index, const f
     if (B == 0) return NRRT_OK;
     poly_relu_kernel<<<dim3(H, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         (const __half*)pre, pre_index, P16, (__half*)out, H, W, C, 1.0f / (float)(H - 1), 1.0f / (float)(W - 1));
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_coords_poly_gemm(const float* feat, int B, int Cc, const float* moments_t, int cases, int n_uv, int Cout,
+                                     float a, float b, float* work, float* E, void* stream) {
+    NRRT_REQUIRE(feat && moments_t && work && E, "null pointer");
+    NRRT_REQUIRE(B >= 0 && Cc % 16 == 0 && Cout > 0 && cases >= 1 && (n_uv == 1 || n_uv == 4) && (cases * n_uv * Cout) % GN == 0,
+                 "bad coords_poly_gemm shape");
+    if (B == 0) return NRRT_OK;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int N = cases * n_uv * Cout, M = B * 4;
+    float* G = work;                        // [B][4][Cc]
+    float* Cw = work + (size_t)B * 4 * Cc;  // [B*4][N]
+    coords_g_kernel<<<grid_for((long long)B * Cc, 256), 256, 0, st>>>(feat, (long long)B * Cc, Cc, G);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    sgemm_kernel<<<dim3(N / GN, (M + GM - 1) / GM), 256, 0, st>>>(G, moments_t, Cw, M, N, Cc);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    const long long total = (long long)B * cases * Cout;
+    coords_combine_kernel<<<grid_for(total, 256), 256, 0, st>>>(Cw, total, cases, n_uv, Cout, a, b, E);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

@@ -274,6 +274,28 @@ def test_polynomial_term_through_the_tensor_core(cout, sp, cuda_device):
     assert (outs[0] - outs[1]).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("cases,n_uv", [(9, 4), (4, 1)])
+def test_coords_poly_gemm_equals_direct_kernel(cases, n_uv, cuda_device):
+    """The epilogue-polynomial coefficients computed as one fp32 GEMM over the batch (large batches) equal the direct kernel."""
+    import ctypes as C
+    dev = cuda_device
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(31)
+    B, Cc, Cout = 70, 64, 128
+    feat = (torch.randn((B, 4, Cc), generator=g) * 50).to(dev)
+    mom = torch.randn((cases, n_uv, Cc, Cout), generator=g).to(dev)
+    mom_t = mom.permute(2, 0, 1, 3).reshape(Cc, -1).contiguous()
+    a, b = 1.0 / 127, 1.0 / 255
+    E1 = torch.empty((B, cases, 4, Cout), dtype=torch.float32, device=dev)
+    E2 = torch.empty_like(E1)
+    work = torch.empty(B * 4 * (Cc + cases * n_uv * Cout), dtype=torch.float32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(lib.nrrt_coords_poly(p(feat), B, Cc, p(mom), cases, n_uv, Cout, a, b, p(E1), None))
+    _lib.check(lib.nrrt_coords_poly_gemm(p(feat), B, Cc, p(mom_t), cases, n_uv, Cout, a, b, p(work), p(E2), None))
+    torch.cuda.synchronize()
+    assert (E1 - E2).abs().max().item() <= 1e-4 * max(E1.abs().max().item(), 1.0)
+
+
 @pytest.mark.parametrize("three_d", [False, True])
 @pytest.mark.parametrize("bn", [False, True])
 def test_unet_forward_matches_reference_golden(three_d, bn, cuda_device):
