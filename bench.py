@@ -187,6 +187,11 @@ def run_graft(args):
     import torch.distributed as dist
     from mgr_sampling_cnn_b200 import _lib, cnn, engine
 
+    # rank 0 prints ONE JSON line: libraries that write to stdout (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -327,7 +332,8 @@ def run_graft(args):
                            "median_iterations": float(np.median(iters))},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
