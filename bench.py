@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--ref-sample", type=int, default=None, help="tasks per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-every", type=int, default=16, help="time the conv launches of every n-th micro-batch")
+    ap.add_argument("--micro-batch", type=int, default=None, help="tasks per decoder launch (default: GuidedPlanner's)")
+    ap.add_argument("--encoder-batch", type=int, default=None, help="distinct maps per encoder pass (default: GuidedPlanner's)")
     ap.add_argument("--layer-table", default=None, help="write the per-layer CUDA-event timings of the sampled launches (csv)")
     return ap.parse_args()
 
@@ -216,7 +218,9 @@ def run_graft(args):
     model = gp = prof = None
     if not uniform:
         model = make_model(dim, dev)
-        gp = engine.GuidedPlanner(model, dim, wl.shape)
+        gp = engine.GuidedPlanner(model, dim, wl.shape, micro_batch=args.micro_batch)
+        if args.encoder_batch:
+            gp.encoder_batch = args.encoder_batch
         prof = cnn.ConvProfiler()
         model._plan(dev).set_profiler(prof)
     bits = engine.pack_occupancy(d["occ"], dim, dev)
