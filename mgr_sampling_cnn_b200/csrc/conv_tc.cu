@@ -60,6 +60,7 @@ struct ConvParams {
     const float* poly;   // optional [N][poly_cases][4][cout]: bilinear epilogue term E0 + ty*E1 + tx*E2 + ty*tx*E3
     int poly_cases;      // 9 = 3x3 border cases (row case * 3 + column case); else one case per weight group
     float inv_h, inv_w;  // 1/(H-1), 1/(W-1) of the tile-space grid
+    int outer;           // slab kernels: slab loads per input-channel chunk: 3 (dx) in 2D, 9 (dz, dx) in 3D
     int ts;              // pair kernels: output tile staged in shared memory and written with TMA stores (see below)
     int pm;              // pair kernels: interior polynomial applied by one extra tcgen05.mma per tile (see pm_* below)
     const float* head_w; // optional fused 1x1 head (cout -> 1): logits[pixel] = head_b + sum_c relu_out[c] * head_w[c]
@@ -1231,8 +1232,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 int m = pt * 2 + (int)rank;
                 const bool live = m < p.m_tiles;
                 const int tw = m % p.tiles_w; m /= p.tiles_w;
-                const int th = m % p.tiles_h;
-                const int n = m / p.tiles_h;
+                const int th = m % p.tiles_h; m /= p.tiles_h;
+                const int td = m % p.tiles_d;  // 3D: one depth slice per tile (tiles_d = D)
+                const int n = m / p.tiles_d;
                 const int w0 = tw * 16, h0 = th * 16;
                 const int n1 = !live ? 0x3fffffff : (p.idx1 ? __ldg(p.idx1 + n) : n);
                 const int n2 = !live ? 0x3fffffff : (p.idx2 ? __ldg(p.idx2 + n) : n);
@@ -1240,19 +1242,21 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const CUtensorMap* am = c < p.split_chunk ? &map_a : &map_a2;
                     const int cc = (c < p.split_chunk ? c : c - p.split_chunk) * kBlockK;
                     const int ns = c < p.split_chunk ? n1 : n2;
-                    for (int dx = 0; dx < 3; ++dx) {
+                    for (int o = 0; o < p.outer; ++o) {  // (dz, dx): 3 slabs per chunk in 2D, 9 in 3D (depth slice d + dz - 1)
+                        const int dx = o % 3, dz = o / 3;
+                        const int dd = td + dz - (p.outer == 9 ? 1 : 0);
                         mbar_wait(aempty(sa), pa ^ 1u);
                         if (rank == 0) mbar_expect_tx(afull(sa), 4 * kSlabBytes);  // two slabs from each CTA of the pair
                         const uint32_t dst = base + sa * L::a_stage;
                         const uint32_t abar = afull(sa) & kPeerBitMask;
-                        tma2_load_5d(dst, am, abar, cc, w0 - 1 + dx, h0 - 1, 0, ns);
-                        tma2_load_5d(dst + kSlabBytes, am, abar, cc, w0 + 7 + dx, h0 - 1, 0, ns);
+                        tma2_load_5d(dst, am, abar, cc, w0 - 1 + dx, h0 - 1, dd, ns);
+                        tma2_load_5d(dst + kSlabBytes, am, abar, cc, w0 + 7 + dx, h0 - 1, dd, ns);
                         if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
                         for (int dy = 0; dy < 3; ++dy) {
                             mbar_wait(bempty(sb), pb ^ 1u);
                             if (rank == 0) mbar_expect_tx(bfull(sb), 2 * L::b_stage);  // each CTA loads half of the B tile
                             tma2_load_2d(base + L::off_b + sb * L::b_stage, &map_b, bfull(sb) & kPeerBitMask,
-                                         ((dy * 3 + dx) * p.cin_chunks + c) * kBlockK, (int)rank * (BLOCK_N / 2));
+                                         (((dz * 3 + dy) * 3 + dx) * p.cin_chunks + c) * kBlockK, (int)rank * (BLOCK_N / 2));
                             if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
                         }
                     }
@@ -1263,7 +1267,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         mbar_wait(rempty_bar(s), rphase ^ 1u);
                         mbar_expect_tx(rfull_bar(s), kResPiece);
                         tma_load_5d(base + L::off_res + s * kResPiece, &map_r, rfull_bar(s),
-                                    (int)p.res_coffset + (s % RC) * 64, w0 + (s / RC) * 8, h0, 0, nr);
+                                    (int)p.res_coffset + (s % RC) * 64, w0 + (s / RC) * 8, h0, td, nr);
                     }
                     rphase ^= 1u;
                 }
@@ -1288,7 +1292,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 2 * BLOCK_N + blk * BLOCK_N);
                 uint32_t first = 1;
                 for (int c = 0; c < p.cin_chunks; ++c) {
-                    for (int dx = 0; dx < 3; ++dx) {
+                    for (int o = 0; o < p.outer; ++o) {
                         mbar_wait(afull(sa), pa);
                         tc_fence_after();
                         const uint32_t a_base = base + sa * L::a_stage + blk * kSlabBytes;
@@ -1340,8 +1344,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             int m = pt * 2 + (int)rank;
             const bool live = m < p.m_tiles;
             const int tw = m % p.tiles_w; m /= p.tiles_w;
-            const int th = m % p.tiles_h;
-            const int n = live ? m / p.tiles_h : 0;
+            const int th = m % p.tiles_h; m /= p.tiles_h;
+            const int td = m % p.tiles_d;
+            const int n = live ? m / p.tiles_d : 0;
             float* sc = ss + acc * 8 * BLOCK_N;
             stage_tile_params<BLOCK_N>(p, sc, 0, n, et, last_n[acc] < 0, !PM && last_n[acc] != n);
             last_n[acc] = n;
@@ -1379,7 +1384,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 if (TS) srow = base_ptr + L::off_res + piece * kResPiece + row * 128;
                 if (valid)
-                    epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
+                    epilogue_chunk(p, v, c * 32, c * 32, n, td, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
                                    sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame, srow);
                 if ((RES || TS) && (c & 1)) {  // both 32-column halves of the piece are done
                     if (TS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1388,7 +1393,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
             }
             if (RES || TS) rphase ^= 1u;
-            if (valid && p.logits) p.logits[((long long)n * p.oH + h) * p.oW + w] = head_acc + p.head_b;
+            if (valid && p.logits) p.logits[(((long long)n * p.oD + td) * p.oH + h) * p.oW + w] = head_acc + p.head_b;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
@@ -1409,7 +1414,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 tlive[j] = mj < p.m_tiles;
                 tw0[j] = (mj % p.tiles_w) * 16; mj /= p.tiles_w;
                 th0[j] = (mj % p.tiles_h) * 16;
-                tn[j] = tlive[j] ? mj / p.tiles_h : 0;
+                tn[j] = tlive[j] ? mj / p.tiles_h : 0;  // (PM is 2D only: tiles_d == 1)
             }
             pm_produce_b<BLOCK_N / 2>(p, base_ptr + L::off_pm + 2 * 4096 + a * L::pm_b, lane, 32, rank, tn, th0, tw0, tlive);
             __syncwarp();
@@ -1428,8 +1433,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 int m = pt * 2 + (int)rank;
                 const bool live = m < p.m_tiles;
                 const int tw = m % p.tiles_w; m /= p.tiles_w;
-                const int th = m % p.tiles_h;
-                const int n = m / p.tiles_h;
+                const int th = m % p.tiles_h; m /= p.tiles_h;
+                const int td = m % p.tiles_d;
+                const int n = m / p.tiles_d;
                 for (int k = 0; k < RC; ++k)
                     for (int b = 0; b < 2; ++b) {  // order in which the epilogue finishes them
                         const int piece = b * RC + k;
@@ -1437,7 +1443,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         if (lane == 0) {
                             if (live)
                                 tma_store_5d(&map_o, base + L::off_res + piece * kResPiece, (int)p.out_coffset + k * 64,
-                                             tw * 16 + b * 8, th * 16, 0, n);
+                                             tw * 16 + b * 8, th * 16, td, n);
                             tma_store_commit_and_wait_read();
                             mbar_arrive(rempty_bar(piece));  // free for the next residual load / the next tile's results
                         }
@@ -1628,12 +1634,17 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         NRRT_REQUIRE(l->out, "null output pointer");
     }
     // 2D 3x3 stride-1 layers with a narrow N are L2-bound in the per-tap kernel: use the slab (halo-reuse) kernel
-    const bool halo = !three_d && l->kind == NRRT_CONV_K3S1 && p.n_tiles == 1 && block_n <= 128 && !l->force_per_tap;
+    // (3D: per depth slice, when the 16x16 tiles fill the slice and the pair kernel runs it)
+    const bool halo = l->kind == NRRT_CONV_K3S1 && p.n_tiles == 1 && block_n <= 128 && !l->force_per_tap &&
+                      (!three_d || (l->force_per_tap != 2 && p.W % 16 == 0 && p.H % 16 == 0));
     const bool pair = l->force_per_tap != 2 && (halo || block_n >= 128);  // CTA pairs (cta_group::2)
+    p.outer = three_d ? 9 : 3;
     if (halo) {
         p.bw = 16; p.bh = 16; p.bd = 1; p.rows = 256;
-        p.tiles_w = (p.W + 15) / 16; p.tiles_h = (p.H + 15) / 16; p.tiles_d = 1;
-        p.m_tiles = p.tiles_w * p.tiles_h * N;
+        p.tiles_w = (p.W + 15) / 16; p.tiles_h = (p.H + 15) / 16; p.tiles_d = p.D;
+        const long long mt = (long long)p.tiles_w * p.tiles_h * p.tiles_d * N;
+        NRRT_REQUIRE(mt < (1ll << 30), "too many tiles");
+        p.m_tiles = (int)mt;
     }
 
     // activation maps: dims (C, W, H, D, N) over the caller's NDHWC buffers (channel slices of cstride-wide rows)

@@ -101,6 +101,8 @@ CASES = [
     (3, cnn.K1S1, 1, 64, 64, (8, 8, 8)),
     (3, cnn.K3S1, 1, 64, 64, (8, 8, 16)),
     (3, cnn.K3S1, 2, 128, 128, (10, 10, 10)),  # 5x5x5 boxes (125 rows)
+    (3, cnn.K3S1, 2, 64, 64, (4, 16, 32)),     # 3D slab kernel (16x16 tiles per depth slice), N = 64
+    (3, cnn.K3S1, 1, 128, 128, (3, 32, 16)),   # 3D slab kernel, two K chunks, N = 128 (TMA-store epilogue)
     (3, cnn.K3S2, 1, 64, 128, (16, 16, 16)),
     (3, cnn.K1S2, 1, 64, 128, (16, 16, 16)),
     (3, cnn.CONVT, 1, 128, 64, (4, 8, 8)),     # 8 groups x 64 = two N tiles of 256
@@ -272,6 +274,32 @@ def test_polynomial_term_through_the_tensor_core(cout, sp, cuda_device):
     for out in outs:
         assert (_from_cl(out, 2) - ref).abs().max().item() <= tol
     assert (outs[0] - outs[1]).abs().max().item() <= tol
+
+
+def test_3d_slab_kernel_residual_and_head(cuda_device):
+    """3D 3x3x3 layers on the slab kernel: indexed residual (TMA-staged) and the fused 1x1x1 head."""
+    dev = cuda_device
+    g = torch.Generator(device="cpu").manual_seed(41)
+    sp = (5, 16, 16)
+    x = torch.randn((3, 64) + sp, generator=g).to(dev)
+    res = torch.randn((2, 128) + sp, generator=g).to(dev)
+    index = torch.tensor([1, 0, 1], dtype=torch.int32, device=dev)
+    w = (torch.randn((128, 64, 3, 3, 3), generator=g) / 41).to(dev)
+    scale, shift = torch.ones(128, device=dev), torch.randn(128, generator=g).to(dev)
+    layer = cnn._Layer(3, cnn.K3S1, 64, 128, cnn._pack_conv_weight(w, 64, dev), scale, shift.contiguous(), True)
+    out = torch.zeros((3,) + sp + (128,), dtype=torch.float16, device=dev)
+    layer.run(_lib.load(), None, _cl(x), 0, sp, out, 0, _cl(res), 0, res_idx=index)
+    torch.cuda.synchronize()
+    _check(out, _ref(3, cnn.K3S1, x, w, scale, shift, True, res[index.long()]), 3, 128)
+    w2 = (torch.randn((64, 64, 3, 3, 3), generator=g) / 41).to(dev)
+    sc2, sh2 = (torch.rand(64, generator=g) + 0.5).to(dev), torch.randn(64, generator=g).to(dev)
+    hw = torch.randn(64, generator=g).to(dev)
+    layer2 = cnn._Layer(3, cnn.K3S1, 64, 64, cnn._pack_conv_weight(w2, 64, dev), sc2.contiguous(), sh2.contiguous(), True)
+    logits = torch.zeros((3,) + sp, dtype=torch.float32, device=dev)
+    layer2.run(_lib.load(), None, _cl(x), 0, sp, None, 0, head=(hw, -0.5, logits))
+    torch.cuda.synchronize()
+    ref = (_ref(3, cnn.K3S1, x, w2, sc2, sh2, True) * hw.view(1, -1, 1, 1, 1)).sum(1) - 0.5
+    assert (logits - ref).abs().max().item() <= 2e-3 * max(ref.abs().max().item(), 1.0)
 
 
 @pytest.mark.parametrize("cases,n_uv", [(9, 4), (4, 1)])
