@@ -80,3 +80,24 @@ def test_dropin_methods_match_reference_calls(fixture, modname, cuda_device):
     assert planner.compute_search_radius(dim) == H.load("radius")["r2d_512" if dim == 2 else "r3d_80"][99]
     s = planner.generate_random_sample()
     assert len(s) == dim and (occ[s] != 0 if dim == 2 else occ[s] == 0)
+
+
+def test_evaluation_harness_table(cuda_device):
+    """The batched counterpart of test_network_and_algorithms.main(): same columns, lengths = calculate_length(path)."""
+    from mgr_sampling_cnn_b200 import test_network_and_algorithms as harness, engine, workload
+    harness.MAX_ITERATIONS = 600
+    try:
+        df, summary = harness.main(n_tasks=20, device=str(cuda_device))
+    finally:
+        harness.MAX_ITERATIONS = 5000
+    assert list(df.columns.levels[0]) == ["A*", "Neural+RRT*", "RRT*"] and len(df) == 20
+    assert list(summary.index) == ["mean", "median"]
+    assert (df[("RRT*", "Iterations")].astype(int) <= 600).all() and (df[("Neural+RRT*", "Length")].astype(float) >= 0).all()
+    # Length column == calculate_length of the returned path points
+    wl = workload.make_2d(20)
+    import torch
+    bits = engine.pack_occupancy(torch.from_numpy(wl.occ_maps).to(cuda_device), 2, cuda_device)
+    res = engine.plan_batch(bits, wl.task_to_map, wl.starts, wl.goals, dim=2, shape=wl.shape, max_iterations=600, seed=0,
+                            keep_tree=True)
+    for b in range(20):
+        assert harness.calculate_length(res.path_points(b)) == float(res.path_len[b]) == float(df[("RRT*", "Length")][b])
