@@ -55,7 +55,9 @@ typedef struct NrrtPlanParams {
 
 /* Per-task outputs; all arrays caller-allocated, fixed stride, any pointer marked optional may be NULL. */
 typedef struct NrrtPlanOut {
-    double* pos;        /* optional [B][node_stride][dim]  Node.position, insertion order (node index) */
+    double* pos;        /* [B][node_stride][dim]  Node.position, insertion order (node index).  Required: it is also the
+                           kernel's store for nodes with non-integer coordinates (integer nodes are int16 words in
+                           shared memory), filled completely at the end of every task */
     double* cost;       /* required [B][node_stride]       Node.cost (also the kernel's working storage) */
     int32_t* parent;    /* required [B][node_stride]       index of Node.parent, -1 for the start node */
     int32_t* n_nodes;   /* [B] len(self.nodes) */

@@ -7,9 +7,14 @@
 // test; nearest neighbour = lowest index among minimal sqrt'ed distances; near set uses `<=` on the sqrt'ed distance.
 //
 // Layout per CTA (dynamic shared memory):
-//   pos[DIM][cap] fp64 (SoA, node index = insertion order) | occupancy bit grid of the task's map | near bit-mask |
-//   reduction slots.  cost[] and parent[] live in the caller's output arrays in global memory (L2): they are touched
-//   only for the ~20 near nodes of an iteration, which keeps the CTA at 111 KiB so two 2D tasks share one SM.
+//   packed node positions [cap] (node index = insertion order) | occupancy bit grid of the task's map | near bit-mask |
+//   reduction slots.  Positions: almost every node IS its integer sample point (steer only clips when the sample is
+//   farther than the search radius), so a node is one 32-bit (2D) / 64-bit (3D) word of int16 coordinates; a node
+//   with a non-integer coordinate stores a sentinel and keeps its fp64 position in the caller's `pos` array (global
+//   memory, read through L2).  cost[] and parent[] live in the caller's output arrays too: they are touched only for
+//   the ~20 near nodes of an iteration.  That is 53 KiB per 2D task and 105 KiB per 3D task: FOUR 2D tasks (128 threads
+//   each) or two 3D tasks (256 threads) share an SM.  The kernel is latency bound (profiles/planner_r1.md), so tasks in
+//   flight per SM is what buys throughput: with fp64 positions in shared memory (111 / 181 KiB) it was two / one.
 // Parallelism inside an iteration: the two O(n) scans run over all threads; every warp evaluates the connect test
 // redundantly (no barrier); choose-parent/rewire candidates are tested speculatively, one candidate per warp at a time,
 // 100 samples over 32 lanes.  The outcome of loop A does not depend on evaluation order (it is the lexicographic
@@ -38,7 +43,7 @@ struct PlanArgs {
     int B;
     int32_t* queue;
     int words_per_map;
-    int cap;         // node capacity in shared memory (>= max_iterations + 2, even)
+    int cap;         // node capacity in shared memory (>= max_iterations + 2, multiple of 4)
     int mask_words;  // words of the near mask
 };
 
@@ -95,6 +100,40 @@ __device__ __forceinline__ void nn_warp_reduce(double& bs, int& bj) {
 // reference value by < 1e-9 (a few ulps of a number <= 2^15), so whenever v' is farther than 1e-6 from every integer
 // both truncate to the same cell; otherwise (segment ends on integer cells, axis-parallel moves, coincidences) the
 // lane re-evaluates the reference's exact sequence.  t = 0 and d_k = 0 are exact without any division.
+
+// ---- packed node positions ------------------------------------------------------------------------------------------
+template <int DIM> struct PosWord { typedef uint32_t T; };
+template <> struct PosWord<3> { typedef unsigned long long T; };
+constexpr int kPosSentinel = -32768;  // coordinate 0 of a node whose fp64 position lives in global memory
+
+template <int DIM>
+__device__ __forceinline__ void load_pos(const typename PosWord<DIM>::T* __restrict__ pw, const double* gpos, int j,
+                                         double (&o)[DIM]) {
+    const typename PosWord<DIM>::T w = pw[j];
+    const int k0 = (int)(int16_t)(uint16_t)(w & 0xffffu);
+    if (k0 != kPosSentinel) {
+        o[0] = (double)k0;
+        o[1] = (double)(int)(int16_t)(uint16_t)((w >> 16) & 0xffffu);
+        if (DIM == 3) o[DIM - 1] = (double)(int)(int16_t)(uint16_t)(((unsigned long long)w >> 32) & 0xffffu);
+    } else {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) o[k] = __ldcg(gpos + (size_t)j * DIM + k);  // written by this CTA before a barrier
+    }
+}
+// returns the packed word; *exact = false -> sentinel (the caller stores the fp64 position in global memory)
+template <int DIM>
+__device__ __forceinline__ typename PosWord<DIM>::T encode_pos(const double (&v)[DIM], bool* exact) {
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) ok = ok && v[k] == rint(v[k]) && v[k] > -32768.0 && v[k] < 32768.0;
+    *exact = ok;
+    if (!ok) return (typename PosWord<DIM>::T)(uint16_t)(int16_t)kPosSentinel;
+    typename PosWord<DIM>::T w = 0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) w |= (typename PosWord<DIM>::T)(uint16_t)(int16_t)__double2int_rn(v[k]) << (16 * k);
+    return w;
+}
+
 template <int DIM>
 struct Segment {  // per-segment constants of is_collision_free, identical in every lane
     double p1[DIM], dl[DIM], u[DIM], D, step;
@@ -158,18 +197,18 @@ __device__ __forceinline__ bool collision_free_warp(const double (&p1)[DIM], con
 }
 
 template <int DIM, int NT, bool TRACE>
-__global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const PlanArgs a) {
+__global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const PlanArgs a) {
     constexpr int NW = NT / kWarp;
+    typedef typename PosWord<DIM>::T PW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* pos = reinterpret_cast<double*>(smem_raw);                       // [DIM][cap]
-    uint32_t* grid = reinterpret_cast<uint32_t*>(pos + (size_t)DIM * a.cap); // [words_per_map] (padded to 4)
+    PW* pw = reinterpret_cast<PW*>(smem_raw);                                // [cap] packed positions
+    uint32_t* grid = reinterpret_cast<uint32_t*>(pw + a.cap);                // [words_per_map] (padded to 4)
     uint32_t* mask = grid + ((a.words_per_map + 3) & ~3);                    // [mask_words]
     Slot* slot_nn = reinterpret_cast<Slot*>(mask + ((a.mask_words + 3) & ~3)); // [2][NW]
     Slot* slot_a = slot_nn + 2 * NW;                                         // [NW]
     __shared__ int s_task;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cap = a.cap;
     const int max_iter = a.p.max_iterations;
     const int shape[3] = {a.p.shape[0], a.p.shape[1], DIM == 3 ? a.p.shape[2] : 1};
     const double thr = a.p.goal_threshold;
@@ -184,6 +223,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
 
         double* cost = a.out.cost + (size_t)task * a.p.node_stride;
         int32_t* parent = a.out.parent + (size_t)task * a.p.node_stride;
+        double* gpos = a.out.pos + (size_t)task * a.p.node_stride * DIM;  // fp64 positions of the non-integer nodes (+ final dump)
         int32_t* trace = TRACE ? a.out.trace + (size_t)task * a.out.trace_cap * 4 : nullptr;
         int trace_n = 0;
 
@@ -211,8 +251,18 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
         double goal[DIM];
 #pragma unroll
         for (int k = 0; k < DIM; ++k) goal[k] = (double)a.goals[task * DIM + k];
-        if (tid < DIM) pos[tid * cap] = (double)a.starts[task * DIM + tid];  // self.nodes = [Node(start)]
-        if (tid == 0) { cost[0] = 0.0; parent[0] = -1; }
+        if (tid == 0) {  // self.nodes = [Node(start)]
+            double st[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) st[k] = (double)a.starts[task * DIM + k];
+            bool exact;
+            pw[0] = encode_pos<DIM>(st, &exact);
+            if (!exact) {
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) gpos[k] = st[k];
+            }
+            cost[0] = 0.0; parent[0] = -1;
+        }
         __syncthreads();
 
         int n = 1, best_node = -1, goal_node = -1, iters = 0;
@@ -244,8 +294,12 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
             int bj = 0x7fffffff;
             for (int j = tid; j < n; j += NT) {
                 double pj[DIM];
+                if (j == pend_j) {
 #pragma unroll
-                for (int k = 0; k < DIM; ++k) pj[k] = (j == pend_j) ? pend[k] : pos[k * cap + j];
+                    for (int k = 0; k < DIM; ++k) pj[k] = pend[k];
+                } else {
+                    load_pos<DIM>(pw, gpos, j, pj);
+                }
                 const double s = nrrt_sqdist<DIM>(pj, smp);
                 if (s < bs) {
                     bool take = true;
@@ -285,8 +339,9 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
 
             // ---- steer (rrt_star.py:82-98; A.4 with x*x for x**2) ----
             double from[DIM], dr[DIM], npos[DIM];
+            load_pos<DIM>(pw, gpos, ni, from);
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) { from[k] = pos[k * cap + ni]; dr[k] = __dsub_rn(smp[k], from[k]); }
+            for (int k = 0; k < DIM; ++k) dr[k] = __dsub_rn(smp[k], from[k]);
             double s2 = __dadd_rn(__dmul_rn(dr[0], dr[0]), __dmul_rn(dr[1], dr[1]));
             if (DIM == 3) s2 = __dadd_rn(s2, __dmul_rn(dr[DIM - 1], dr[DIM - 1]));
             double dist = sqrt(s2);
@@ -318,8 +373,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
                 bool in = false;
                 if (j < n) {
                     double pj[DIM];
-#pragma unroll
-                    for (int k = 0; k < DIM; ++k) pj[k] = pos[k * cap + j];
+                    load_pos<DIM>(pw, gpos, j, pj);
                     const double s = nrrt_sqdist<DIM>(npos, pj);
                     in = (s <= r2lo) ? true : ((s >= r2hi) ? false : (sqrt(s) <= r));
                 }
@@ -358,8 +412,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) pj[k] = 0.0;
                 if (has) {
-#pragma unroll
-                    for (int k = 0; k < DIM; ++k) pj[k] = pos[k * cap + j];
+                    load_pos<DIM>(pw, gpos, j, pj);
                     cj = __dadd_rn(cost[j], sqrt(nrrt_sqdist<DIM>(pj, npos)));
                 }
                 uint32_t cand = __ballot_sync(0xffffffffu, has && cj < ncost0);
@@ -410,8 +463,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
 #pragma unroll
                 for (int k = 0; k < DIM; ++k) pj[k] = 0.0;
                 if (has) {
-#pragma unroll
-                    for (int k = 0; k < DIM; ++k) pj[k] = pos[k * cap + j];
+                    load_pos<DIM>(pw, gpos, j, pj);
                     cj = __dadd_rn(ncost, sqrt(nrrt_sqdist<DIM>(npos, pj)));
                     cur = cost[j];
                 }
@@ -439,8 +491,18 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
             const double dg = sqrt(nrrt_sqdist<DIM>(npos, goal));
             if (dg < best) { best = dg; best_node = n; }
             const bool reached = dg <= thr;
-            if (tid < DIM) pos[tid * cap + n] = reached ? goal[tid] : npos[tid];  // goal_node.position = self.goal
-            if (tid == 0) { cost[n] = ncost; parent[n] = npar; }
+            if (tid == 0) {
+                double fin[DIM];
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) fin[k] = reached ? goal[k] : npos[k];  // goal_node.position = self.goal
+                bool exact;
+                pw[n] = encode_pos<DIM>(fin, &exact);
+                if (!exact) {
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) gpos[(size_t)n * DIM + k] = fin[k];
+                }
+                cost[n] = ncost; parent[n] = npar;
+            }
             if (reached) { goal_node = n; break; }
             // no barrier here: the next scan takes the new node from registers, and every later reader of pos[n],
             // cost[n], parent[n], mask or slot_a sits behind barrier (1) of the next iteration
@@ -453,9 +515,14 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
 
         // ---- epilogue: scalars, find_path + calculate_length, optional tree dump ----
         const int n_tot = n + (goal_node >= 0 ? 1 : 0);
-        if (a.out.pos) {
-            double* opos = a.out.pos + (size_t)task * a.p.node_stride * DIM;
-            for (int i = tid; i < n_tot * DIM; i += NT) opos[i] = pos[(i % DIM) * cap + i / DIM];
+        for (int j = tid; j < n_tot; j += NT) {  // tree dump: the integer nodes join the fp64 ones already in `pos`
+            const PW w = pw[j];
+            if ((int)(int16_t)(uint16_t)(w & 0xffffu) != kPosSentinel) {
+                double pj[DIM];
+                load_pos<DIM>(pw, gpos, j, pj);
+#pragma unroll
+                for (int k = 0; k < DIM; ++k) gpos[(size_t)j * DIM + k] = pj[k];
+            }
         }
         if (tid == 0) {
             a.out.n_nodes[task] = n;
@@ -479,8 +546,8 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 2 : 1)) plan_kernel(const Plan
                     for (int j = end; j >= 0; j = parent[j]) pi[--q] = j;  // path.reverse()
                     for (int q2 = 0; q2 + 1 < m; ++q2) {                   // calculate_length: forward fp64 sum
                         double u[DIM], v[DIM];
-#pragma unroll
-                        for (int k = 0; k < DIM; ++k) { u[k] = pos[k * cap + pi[q2]]; v[k] = pos[k * cap + pi[q2 + 1]]; }
+                        load_pos<DIM>(pw, gpos, pi[q2], u);
+                        load_pos<DIM>(pw, gpos, pi[q2 + 1], v);
                         len = __dadd_rn(len, sqrt(nrrt_sqdist<DIM>(u, v)));
                     }
                 } else if (m > 0) {
@@ -601,11 +668,11 @@ struct SmemPlan {
 
 SmemPlan smem_plan(const NrrtPlanParams& p, int words_per_map) {
     SmemPlan s;
-    s.nt = p.dim == 2 ? 256 : 512;
-    s.cap = (p.max_iterations + 2 + 1) & ~1;
+    s.nt = p.dim == 2 ? 128 : 256;
+    s.cap = (p.max_iterations + 2 + 3) & ~3;  // packed positions end on a 16-byte boundary (the grid is staged with 16-byte stores)
     s.mask_words = (s.cap + 31) / 32;
     const int nw = s.nt / 32;
-    s.bytes = (size_t)p.dim * s.cap * 8 + (size_t)((words_per_map + 3) & ~3) * 4 + (size_t)((s.mask_words + 3) & ~3) * 4 +
+    s.bytes = (size_t)s.cap * (p.dim == 2 ? 4 : 8) + (size_t)((words_per_map + 3) & ~3) * 4 + (size_t)((s.mask_words + 3) & ~3) * 4 +
               (size_t)3 * nw * sizeof(Slot);
     return s;
 }
@@ -647,7 +714,7 @@ extern "C" int nrrt_plan_batch(const NrrtPlanParams* p, const uint32_t* occ_bits
     NRRT_REQUIRE(p->node_stride >= p->max_iterations + 2, "node_stride %d < max_iterations + 2", p->node_stride);
     if (B == 0) return NRRT_OK;
     NRRT_REQUIRE(occ_bits && task_to_map && radius && samples && starts && goals && queue_counter, "null input pointer");
-    NRRT_REQUIRE(out->cost && out->parent && out->n_nodes && out->iterations && out->status && out->goal_node &&
+    NRRT_REQUIRE(out->pos && out->cost && out->parent && out->n_nodes && out->iterations && out->status && out->goal_node &&
                      out->best_node && out->best_dist, "null required output pointer");
     for (int k = 0; k < p->dim; ++k) NRRT_REQUIRE(p->shape[k] >= 1 && p->shape[k] <= 32767, "bad shape[%d]=%d", k, p->shape[k]);
     const int64_t cells = (int64_t)p->shape[0] * p->shape[1] * (p->dim == 3 ? p->shape[2] : 1);
@@ -663,6 +730,6 @@ extern "C" int nrrt_plan_batch(const NrrtPlanParams* p, const uint32_t* occ_bits
     if (s.bytes > 232448) return nrrt_fail(NRRT_ERR_UNSUPPORTED, "planner needs %zu B shared memory (> 227 KiB): map or max_iterations too large", s.bytes);
     const bool tracing = out->trace != nullptr && out->trace_cap > 0;
     NRRT_CUDA_TRY(cudaMemsetAsync(queue_counter, 0, sizeof(int32_t), st));
-    if (p->dim == 2) return tracing ? launch_plan<2, 256, true>(a, s.bytes, st) : launch_plan<2, 256, false>(a, s.bytes, st);
-    return tracing ? launch_plan<3, 512, true>(a, s.bytes, st) : launch_plan<3, 512, false>(a, s.bytes, st);
+    if (p->dim == 2) return tracing ? launch_plan<2, 128, true>(a, s.bytes, st) : launch_plan<2, 128, false>(a, s.bytes, st);
+    return tracing ? launch_plan<3, 256, true>(a, s.bytes, st) : launch_plan<3, 256, false>(a, s.bytes, st);
 }

@@ -154,7 +154,7 @@ class PlannerBuffers:
         z = lambda *s, dtype=i32: torch.empty(s, dtype=dtype, device=device)  # noqa: E731
         self.cost = z(B, stride, dtype=f64)
         self.parent = z(B, stride)
-        self.pos = z(B, stride, dim, dtype=f64) if keep_tree else None
+        self.pos = z(B, stride, dim, dtype=f64)  # also the kernel's store for nodes with non-integer coordinates
         self.n_nodes, self.iterations, self.status = z(B), z(B), z(B)
         self.goal_node, self.best_node = z(B), z(B)
         self.best_dist = z(B, dtype=f64)
