@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
         const int16_t* smp_base = a.samples + (size_t)task * max_iter * DIM;
         double r_next = __ldg(a.radius);
         double pend[DIM];   // newest node, kept in registers: its shared-memory copy becomes visible at barrier (1)
+        PW pend_w = 0;      // ... and its packed word
         int pend_j = -1;
 #pragma unroll
         for (int k = 0; k < DIM; ++k) pend[k] = 0.0;
@@ -281,8 +282,9 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
             iters = it + 1;
             const double r = r_next;
             double smp[DIM];
+            int si[DIM];  // the sample is always an integer cell
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) smp[k] = (double)smp_next[k];
+            for (int k = 0; k < DIM; ++k) { si[k] = (int)smp_next[k]; smp[k] = (double)smp_next[k]; }
             if (it + 1 < max_iter) {  // next iteration's inputs travel while this one computes
                 r_next = __ldg(a.radius + it + 1);
 #pragma unroll
@@ -290,22 +292,41 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
             }
 
             // ---- find_nearest_neighbor: scan + argmin (strict <, lowest index wins) ----
+            // Integer nodes against the integer sample: the squared distance is an exact integer, distinct integers below
+            // 2^32 have distinct fp64 square roots, so integer order IS the reference's order of sqrt'ed distances (and
+            // it is the value the fp64 path would compute).  Only the rare non-integer nodes take the fp64 path.
             double bs = INFINITY;
             int bj = 0x7fffffff;
+            uint32_t bsi = 0xffffffffu;
+            int bji = 0x7fffffff;
             for (int j = tid; j < n; j += NT) {
-                double pj[DIM];
-                if (j == pend_j) {
-#pragma unroll
-                    for (int k = 0; k < DIM; ++k) pj[k] = pend[k];
+                const bool is_pend = j == pend_j;
+                const PW w = is_pend ? pend_w : pw[j];
+                const int k0 = (int)(int16_t)(uint16_t)(w & 0xffffu);
+                if (k0 != kPosSentinel) {
+                    const int d0 = k0 - si[0];
+                    const int d1 = (int)(int16_t)(uint16_t)((w >> 16) & 0xffffu) - si[1];
+                    uint32_t sq = (uint32_t)(d0 * d0) + (uint32_t)(d1 * d1);
+                    if (DIM == 3) {
+                        const int d2 = (int)(int16_t)(uint16_t)(((unsigned long long)w >> 32) & 0xffffu) - si[DIM - 1];
+                        sq += (uint32_t)(d2 * d2);
+                    }
+                    if (sq < bsi) { bsi = sq; bji = j; }
                 } else {
-                    load_pos<DIM>(pw, gpos, j, pj);
+                    double pj[DIM];
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) pj[k] = is_pend ? pend[k] : __ldcg(gpos + (size_t)j * DIM + k);
+                    const double s = nrrt_sqdist<DIM>(pj, smp);
+                    if (s < bs) {
+                        bool take = true;
+                        if (s > __dmul_rn(bs, NRRT_K_LO)) take = nn_take_slow(s, bs);  // sqrt-tie hazard, rare
+                        if (take) { bs = s; bj = j; }
+                    }
                 }
-                const double s = nrrt_sqdist<DIM>(pj, smp);
-                if (s < bs) {
-                    bool take = true;
-                    if (s > __dmul_rn(bs, NRRT_K_LO)) take = nn_take_slow(s, bs);  // sqrt-tie hazard, rare
-                    if (take) { bs = s; bj = j; }
-                }
+            }
+            if (bji != 0x7fffffff) {  // merge the integer winner (exact as a double) with the fp64 one
+                const double sd = (double)bsi;
+                if (bj == 0x7fffffff || nn_a_wins(sd, bji, bs, bj)) { bs = sd; bj = bji; }
             }
             nn_warp_reduce(bs, bj);
             Slot* snn = slot_nn + (it & 1) * NW;
@@ -368,14 +389,45 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
             // ---- find_nearby_nodes: euclid(new, node) <= r, as a bit mask in insertion order ----
             const double r2 = __dmul_rn(r, r);
             const double r2lo = __dmul_rn(r2, NRRT_K_LO), r2hi = __dmul_rn(r2, NRRT_K_HI);
+            // integer new node against integer nodes: s is an exact integer and sqrt is monotone, so the reference's test
+            // fl(sqrt(s)) <= r is s <= s_max with s_max = the largest integer that passes it (found once per iteration)
+            bool q_exact;
+            const PW qw = encode_pos<DIM>(npos, &q_exact);
+            int qi[DIM];
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) qi[k] = (int)(int16_t)(uint16_t)(((unsigned long long)qw >> (16 * k)) & 0xffffu);
+            uint32_t s_max = 0;
+            bool s_any = false;  // false: no integer passes (cannot happen for r >= 0, kept for safety)
+            if (q_exact) {
+                long long ci = (long long)fmin(floor(r2hi), 4294967295.0);
+                for (; ci >= 0; --ci) {
+                    const double cd = (double)ci;
+                    if ((cd <= r2lo) ? true : ((cd >= r2hi) ? false : (sqrt(cd) <= r))) break;
+                }
+                s_any = ci >= 0;
+                s_max = (uint32_t)(ci >= 0 ? ci : 0);
+            }
             for (int base = 0; base < n; base += NT) {
                 const int j = base + tid;
                 bool in = false;
                 if (j < n) {
-                    double pj[DIM];
-                    load_pos<DIM>(pw, gpos, j, pj);
-                    const double s = nrrt_sqdist<DIM>(npos, pj);
-                    in = (s <= r2lo) ? true : ((s >= r2hi) ? false : (sqrt(s) <= r));
+                    const PW w = pw[j];
+                    const int k0 = (int)(int16_t)(uint16_t)(w & 0xffffu);
+                    if (q_exact && k0 != kPosSentinel) {
+                        const int d0 = k0 - qi[0];
+                        const int d1 = (int)(int16_t)(uint16_t)((w >> 16) & 0xffffu) - qi[1];
+                        uint32_t sq = (uint32_t)(d0 * d0) + (uint32_t)(d1 * d1);
+                        if (DIM == 3) {
+                            const int d2 = (int)(int16_t)(uint16_t)(((unsigned long long)w >> 32) & 0xffffu) - qi[DIM - 1];
+                            sq += (uint32_t)(d2 * d2);
+                        }
+                        in = s_any && sq <= s_max;
+                    } else {
+                        double pj[DIM];
+                        load_pos<DIM>(pw, gpos, j, pj);
+                        const double s = nrrt_sqdist<DIM>(npos, pj);
+                        in = (s <= r2lo) ? true : ((s >= r2hi) ? false : (sqrt(s) <= r));
+                    }
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, in);
                 if (lane == 0 && (base >> 5) + warp < a.mask_words) mask[(base >> 5) + warp] = m;
@@ -508,6 +560,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
             // cost[n], parent[n], mask or slot_a sits behind barrier (1) of the next iteration
 #pragma unroll
             for (int k = 0; k < DIM; ++k) pend[k] = npos[k];
+            pend_w = qw;  // (npos is not the goal here: a reached goal leaves the loop above)
             pend_j = n;
             ++n;
         }
