@@ -231,6 +231,14 @@ int nrrt_coords_poly(const float* feat, int B, int Cc, const float* moments, int
 int nrrt_coords_poly_gemm(const float* feat, int B, int Cc, const float* moments_t, int cases, int n_uv, int Cout, float a,
                           float b, float* work, float* E, void* stream);
 
+/* 3D coordinate channels as a post-pass polynomial (derivation in csrc/conv_aux.cu; ThreeD_train.py:180-191).
+ * nrrt_coords_pieces_3d: feat fp32 [B][6][Cc] (nrrt_coords_branch output on the (2,3) grid) -> A fp32 [B][4][2*Cc], the
+ *   bilinear coefficients of the two h-pieces stacked along channels; nrrt_coords_poly_gemm(A, B, 2*Cc, moments_t, cases = 54,
+ *   n_uv = 4, ...) then yields E fp32 [B][54][4][Cout] (case = (d-border * 6 + h-class) * 3 + w-border).
+ * nrrt_poly_relu_3d: x[b] = fp16(relu(x[b] + E[b](d, h, w))) in place on a channels-last (D, H, W, C) fp16 buffer. */
+int nrrt_coords_pieces_3d(const float* feat, int B, int Cc, float* A, void* stream);
+int nrrt_poly_relu_3d(void* x, const float* E, int B, int D, int H, int W, int C, void* stream);
+
 /* conv6.0 hoisted out of the per-task path (2D; train.py:192-195).  The layer is linear in its input and only the
  * coordinate channels depend on the task, so its pre-activation = a per-map tensor (nrrt_conv_layer once per map) + a
  * per-task piecewise-bilinear field with 16 cases (4 row classes x 4 column classes: first / interior even / interior

@@ -252,7 +252,7 @@ class UNetPlan(object):
         # coordinate grid is only piecewise bilinear).
         self.poly = d == 2
 
-        def conv_split(m, c_up, c_enc, c_coords_in_gemm):
+        def conv_split(m, c_up, c_enc, c_coords_in_gemm, relu=True):
             """First 3x3 conv of a decoder stage over torch.cat((up, enc, coords)) (train.py:194-201).  The layer is linear
             in its input channels up to the ReLU, so it is split into (per-task layer over [up | coords (3D only)] with
             the bias and the ReLU, per-map layer over the encoder channels without bias or ReLU): the per-map partial sum
@@ -261,7 +261,7 @@ class UNetPlan(object):
             up, enc, crd = w[:, :c_up], w[:, c_up:c_up + c_enc], w[:, c_up + c_enc:]
             wp = torch.cat([up] + ([crd] if c_coords_in_gemm else []), dim=1)
             scale, shift = _fold_bn(None, m.bias, m.out_channels, dev)
-            task = _Layer(d, K3S1, wp.shape[1], m.out_channels, _pack_conv_weight(wp, wp.shape[1], dev), scale, shift, True)
+            task = _Layer(d, K3S1, wp.shape[1], m.out_channels, _pack_conv_weight(wp, wp.shape[1], dev), scale, shift, relu)
             one, zero = torch.ones_like(scale), torch.zeros_like(shift)
             per_map = _Layer(d, K3S1, c_enc, m.out_channels, _pack_conv_weight(enc, c_enc, dev), one, zero, False)
             return task, per_map
@@ -280,6 +280,31 @@ class UNetPlan(object):
                     for uv, wgt in enumerate((torch.ones_like(dy * dx), dy * torch.ones_like(dx), dx * torch.ones_like(dy), dy * dx)):
                         out[ry * 3 + rx, uv] = (sub * wgt).sum(dim=(2, 3)).t()
             return out.contiguous()
+
+        def conv_moments3d(m, keep):
+            """3D tap moments of the coordinate slice, the two h-pieces stacked along the channel axis, as the GEMM operand
+            [2*Cc][54 cases * 4 uv * Cout]; case = (d-border * 6 + h-class) * 3 + w-border, uv = 00, 10 (dz), 01 (dy), 11."""
+            wc = m.weight.detach().float().to(dev)[:, keep:]            # [Cout, Cc, 3, 3, 3] (dz, dy, dx)
+            cout, cc = wc.shape[0], wc.shape[1]
+            off = torch.tensor([-1.0, 0.0, 1.0], device=dev)
+            border = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}               # tap indices inside the volume per border case
+            pieces = {0: ([1, 2], []), 1: ([0, 1, 2], []), 2: ([0, 1], [2]), 3: ([0], [1, 2]), 4: ([], [0, 1, 2]), 5: ([], [0, 1])}
+            out = torch.zeros((54, 4, 2 * cc, cout), dtype=torch.float32, device=dev)
+            for dc in range(3):
+                for hc in range(6):
+                    for wcase in range(3):
+                        case = (dc * 6 + hc) * 3 + wcase
+                        for pce in range(2):
+                            dys = pieces[hc][pce]
+                            if not dys:
+                                continue
+                            sub = wc[:, :, border[dc]][:, :, :, dys][:, :, :, :, border[wcase]]   # [Cout, Cc, nz, ny, nx]
+                            dz = off[border[dc]].view(1, 1, -1, 1, 1)
+                            dy = off[dys].view(1, 1, 1, -1, 1)
+                            one = torch.ones_like(dz * dy)
+                            for uv, wgt in enumerate((one, dz * torch.ones_like(dy), dy * torch.ones_like(dz), dz * dy)):
+                                out[case, uv, pce * cc:(pce + 1) * cc] = (sub * wgt).sum(dim=(2, 3, 4)).t()
+            return out.permute(2, 0, 1, 3).reshape(2 * cc, -1).contiguous()
 
         mu = model.upconv6
         groups = 2 ** d
@@ -309,9 +334,14 @@ class UNetPlan(object):
             self.up6.cin2 = 512
             self.up6.cin_real = 1024
         self.up7, self.up8 = convT(model.upconv7), convT(model.upconv8)
-        c60, self.c6e = (None, None) if self.poly else conv_split(model.conv6[0], 512, 256, True)
-        c70, self.c7e = conv_split(model.conv7[0], 128, 128, not self.poly)
-        c80, self.c8e = conv_split(model.conv8[0], 64, 64, not self.poly)
+        # 3D: the coordinate channels leave the GEMM too; their (piecewise bilinear) field and the ReLU are applied by
+        # nrrt_poly_relu_3d after the layer (csrc/conv_aux.cu)
+        c60, self.c6e = (None, None) if self.poly else conv_split(model.conv6[0], 512, 256, False, relu=False)
+        c70, self.c7e = conv_split(model.conv7[0], 128, 128, False, relu=self.poly)
+        c80, self.c8e = conv_split(model.conv8[0], 64, 64, False, relu=self.poly)
+        if not self.poly:
+            self.mt3 = {"e_c6": conv_moments3d(model.conv6[0], 768), "e_c7": conv_moments3d(model.conv7[0], 256),
+                        "e_c8": conv_moments3d(model.conv8[0], 128)}
         self.c6 = (c60, conv(model.conv6[2], K3S1))
         self.c7 = (c70, conv(model.conv7[2], K3S1))
         self.c8 = (c80, conv(model.conv8[2], K3S1))
@@ -349,7 +379,7 @@ class UNetPlan(object):
     def _dec_buffers(self, B, grid):
         b = lambda lv, ch: self._buf(B, grid, lv, ch)  # noqa: E731
         # task-side decoder inputs: the ConvTranspose output, followed (3D) by the interpolated coordinate channels
-        t8w, t7w, t6w = (64, 128, 512) if self.poly else (128, 256, 768)
+        t8w, t7w, t6w = 64, 128, 512  # (the coordinate channels are never materialised next to them)
 
         def make():
             d = {"t8": b(0, t8w), "j": b(0, 128), "t7": b(1, t7w), "g7": b(1, 256), "i": b(1, 128),
@@ -480,6 +510,28 @@ class UNetPlan(object):
                                            j - i, 512, cout, g[3][1], g[3][2], _ptr(work), _ptr(P16[i:j]), st))
             prep["p16"] = P16
             del prep["e_up6"], prep["e_c6"]
+        else:
+            # 3D: post-pass polynomials of conv6.0 / conv7.0 / conv8.0 (54 cases, two h-pieces stacked along the channels)
+            if P != 6:
+                raise ValueError("3D coords must be (B, 1, 2, 3)")
+            g = self._levels(grid)
+            for name, feat, lv, cout in (("e_c6", feats[2], 2, 512), ("e_c7", feats[1], 1, 256), ("e_c8", feats[0], 0, 128)):
+                cc = feat.shape[-1]
+                A = torch.empty((B, 4, 2 * cc), dtype=torch.float32, device=dev)
+                _lib.count_launch()
+                check(self.lib.nrrt_coords_pieces_3d(_ptr(feat), B, cc, _ptr(A), st))
+                E = torch.empty((B, 54, 4, cout), dtype=torch.float32, device=dev)
+                n_cols = 54 * 4 * cout
+                chunk = max(1, min(B, (64 << 20) // (4 * (2 * cc + n_cols))))  # scratch <= 256 MB
+                work = torch.empty((chunk * 4 * (2 * cc + n_cols),), dtype=torch.float32, device=dev)
+                a = 1.0 / (g[lv][0] - 1)
+                b = 1.0 / (g[lv][1] - 1)
+                for i in range(0, B, chunk):
+                    j = min(B, i + chunk)
+                    _lib.count_launch(2)
+                    check(self.lib.nrrt_coords_poly_gemm(_ptr(A[i:j]), j - i, 2 * cc, _ptr(self.mt3[name]), 54, 4, cout, a, b,
+                                                         _ptr(work), _ptr(E[i:j]), st))
+                prep[name] = E
         return prep
 
     @staticmethod
@@ -550,13 +602,16 @@ class UNetPlan(object):
         # coordinate branch (train.py:179-190)
         if prep is None:
             prep = self.coords_prepare(coords, grid)
-        if not self.poly:  # 3D: materialise the interpolated channels next to the ConvTranspose outputs
+        if not self.poly:  # 3D: only the bottleneck coordinate channels (second input of upconv6, 10^3 voxels) are materialised
             gh, gw = coords.shape[2], coords.shape[3]
-            for feat, ch, name, off, lv in ((0, 64, "t8", 64, 0), (1, 128, "t7", 128, 1), (2, 256, "t6", 512, 2), (3, 512, "c5", 0, 3)):
-                t = bf[name]
-                _lib.count_launch()
-                check(lib.nrrt_coords_fill(_ptr(prep["feats"][feat]), B, gh, gw, ch, dims, g[lv][0], g[lv][1], g[lv][2], _ptr(t),
-                                           t.shape[-1], off, st))
+            t = bf["c5"]
+            _lib.count_launch()
+            check(lib.nrrt_coords_fill(_ptr(prep["feats"][3]), B, gh, gw, 512, dims, g[3][0], g[3][1], g[3][2], _ptr(t),
+                                       t.shape[-1], 0, st))
+
+        def post3d(buf, E, lv):  # 3D: coordinate field + ReLU after the first conv of a decoder stage
+            _lib.count_launch()
+            check(lib.nrrt_poly_relu_3d(_ptr(buf), _ptr(E), B, g[lv][0], g[lv][1], g[lv][2], buf.shape[-1], st))
 
         # decoder: every torch.cat of the reference is a K split over (task buffer, encoder output of the task's map)
         ei = enc_index  # None = one encoder sample per task
@@ -568,12 +623,17 @@ class UNetPlan(object):
         else:
             self.up6.run(lib, st, bf["e5"], 0, g[3], bf["t6"], 0, x2=bf["c5"], idx=ei, n=B)
             self.c6[0].run(lib, st, bf["t6"], 0, g[2], bf["g6"], 0, bf["r6"], 0, res_idx=ri)
+            post3d(bf["g6"], prep["e_c6"], 2)
         self.c6[1].run(lib, st, bf["g6"], 0, g[2], bf["h"], 0)
         self.up7.run(lib, st, bf["h"], 0, g[2], bf["t7"], 0)
-        self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, bf["r7"], 0, poly=prep.get("e_c7"), res_idx=ri)
+        self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, bf["r7"], 0, poly=prep.get("e_c7") if self.poly else None, res_idx=ri)
+        if not self.poly:
+            post3d(bf["g7"], prep["e_c7"], 1)
         self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
         self.up8.run(lib, st, bf["i"], 0, g[1], bf["t8"], 0)
-        self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8"), res_idx=ri)
+        self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8") if self.poly else None, res_idx=ri)
+        if not self.poly:
+            post3d(bf["j"], prep["e_c8"], 0)
 
         # conv8.2 + final_conv fused: the 64-channel activation is reduced to the logit in the epilogue
         logits = logits_out

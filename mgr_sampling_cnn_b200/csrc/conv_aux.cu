@@ -512,6 +512,78 @@ __global__ void __launch_bounds__(256) coords_combine_kernel(const float* __rest
     }
 }
 
+// ---- 3D: coordinate channels as a post-pass polynomial ---------------------------------------------------------------
+// ThreeD_UNet_cooler interpolates the (2, 3) coordinate feature trilinearly to (D, H, W) (ThreeD_train.py:180-191): linear
+// in d, PIECEWISE linear in h (3 points: a knot in the middle, which falls between two voxels for even H), constant in w.
+// Per h-piece p the field is bilinear in (td, th) = (d/(D-1), h/(H-1)):  A0 + td*A1 + th*A2 + td*th*A3  with
+//   G0 = f[0][p], G1 = f[1][p]-f[0][p], G2 = f[0][p+1]-f[0][p], G3 = f[0][p]-f[0][p+1]-f[1][p]+f[1][p+1]
+//   A0 = G0 - p*G2, A1 = G1 - p*G3, A2 = 2*G2, A3 = 2*G3                      (source coordinate along h is 2*th).
+// A 3x3x3 conv over it is again bilinear in (td, th) per (d-border, h-class, w-border) case, 3 x 6 x 3 = 54 cases (h-class:
+// first row, inside piece 0, last row of piece 0, first row of piece 1, inside piece 1, last row), with tap moments per
+// piece.  Stacking the two pieces along the channel axis turns this into the 2D contraction: nrrt_coords_poly_gemm with
+// Cc' = 2*Cc, cases = 54 and G given directly.  The conv itself runs without the coordinate channels (K -33...-50 %) and
+// without ReLU; poly_relu3d_kernel adds the field (a per-row constant: it does not depend on w) and applies the ReLU.
+__global__ void __launch_bounds__(256) coords_pieces_kernel(const float* __restrict__ feat, long long total, int Cc,
+                                                            float* __restrict__ A) {
+    // feat [B][6 = a*3 + b][Cc] -> A [B][4][2*Cc] (piece p in channels [p*Cc, (p+1)*Cc))
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / (2 * Cc);
+        const int r = (int)(i - b * 2 * Cc), p = r / Cc, c = r - p * Cc;
+        const float* f = feat + b * 6 * Cc + c;
+        const float f0p = f[(size_t)p * Cc], f0q = f[(size_t)(p + 1) * Cc], f1p = f[(size_t)(3 + p) * Cc], f1q = f[(size_t)(4 + p) * Cc];
+        const float g0 = f0p, g1 = f1p - f0p, g2 = f0q - f0p, g3 = f0p - f0q - f1p + f1q;
+        float* a = A + b * 4 * 2 * Cc + r;
+        a[0] = g0 - (float)p * g2;
+        a[(size_t)2 * Cc] = g1 - (float)p * g3;
+        a[(size_t)4 * Cc] = 2.f * g2;
+        a[(size_t)6 * Cc] = 2.f * g3;
+    }
+}
+
+// x[b][d][h][w][:] = fp16(relu(x + E0 + td*E1 + th*E2 + td*th*E3)), E = E[b][case(d, h, w)]: one CTA per (d, h) row and task.
+__global__ void __launch_bounds__(256) poly_relu3d_kernel(__half* __restrict__ x, const float* __restrict__ E, int D, int H, int W,
+                                                          int C, float inv_d, float inv_h) {
+    const int cgs = C >> 3, lanes = 256 / cgs;
+    const int cg = threadIdx.x % cgs, lane = threadIdx.x / cgs;
+    const int d = blockIdx.x / H, h = blockIdx.x - d * H, b = blockIdx.y;
+    const int dc = d == 0 ? 0 : (d == D - 1 ? 2 : 1);
+    const int hh = H >> 1;
+    const int hc = h == 0 ? 0 : (h == H - 1 ? 5 : (h < hh - 1 ? 1 : (h == hh - 1 ? 2 : (h == hh ? 3 : 4))));
+    const float td = (float)d * inv_d, th = (float)h * inv_h;
+    const float* eb = E + ((size_t)b * 54 + (size_t)(dc * 6 + hc) * 3) * 4 * C + cg * 8;
+    __half* row = x + ((((size_t)b * D + d) * H + h) * W) * C + cg * 8;
+    auto load_class = [&](int wc, float (&A)[8]) {
+        const float* q = eb + (size_t)wc * 4 * C;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(q + k * 4));
+            const float4 e1 = __ldg(reinterpret_cast<const float4*>(q + C + k * 4));
+            const float4 e2 = __ldg(reinterpret_cast<const float4*>(q + 2 * C + k * 4));
+            const float4 e3 = __ldg(reinterpret_cast<const float4*>(q + 3 * C + k * 4));
+            A[k * 4 + 0] = e0.x + td * e1.x + th * (e2.x + td * e3.x);
+            A[k * 4 + 1] = e0.y + td * e1.y + th * (e2.y + td * e3.y);
+            A[k * 4 + 2] = e0.z + td * e1.z + th * (e2.z + td * e3.z);
+            A[k * 4 + 3] = e0.w + td * e1.w + th * (e2.w + td * e3.w);
+        }
+    };
+    float Ai[8];
+    load_class(1, Ai);
+    for (int w = lane; w < W; w += lanes) {
+        float Ae[8];
+        const bool edge = w == 0 || w == W - 1;
+        if (edge) load_class(w == 0 ? 0 : 2, Ae);
+        uint4 v = *reinterpret_cast<const uint4*>(row + (size_t)w * C);
+        __half2* hv = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hv[e]);
+            const float a0 = edge ? Ae[2 * e] : Ai[2 * e], a1 = edge ? Ae[2 * e + 1] : Ai[2 * e + 1];
+            hv[e] = __floats2half2_rn(fminf(fmaxf(f.x + a0, 0.f), 65504.f), fminf(fmaxf(f.y + a1, 0.f), 65504.f));
+        }
+        *reinterpret_cast<uint4*>(row + (size_t)w * C) = v;
+    }
+}
+
 int grid_for(long long work, int block) {
     long long g = (work + block - 1) / block;
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
@@ -635,6 +707,27 @@ extern "C" int nrrt_poly_relu(const void* pre, const int32_t* pre_index, const f
     return NRRT_OK;
 }
 
+extern "C" int nrrt_coords_pieces_3d(const float* feat, int B, int Cc, float* A, void* stream) {
+    NRRT_REQUIRE(feat && A && B >= 0 && Cc > 0, "bad coords_pieces arguments");
+    if (B == 0) return NRRT_OK;
+    const long long total = (long long)B * 2 * Cc;
+    coords_pieces_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(feat, total, Cc, A);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_poly_relu_3d(void* x, const float* E, int B, int D, int H, int W, int C, void* stream) {
+    NRRT_REQUIRE(x && E, "null pointer");
+    NRRT_REQUIRE(B >= 0 && D >= 2 && H >= 4 && H % 2 == 0 && W >= 2, "poly_relu_3d needs D >= 2, even H >= 4, W >= 2");
+    NRRT_REQUIRE(C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0, "C/8 must divide 256 (got C = %d)", C);
+    NRRT_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)E & 15) == 0, "pointers must be 16-byte aligned");
+    if (B == 0) return NRRT_OK;
+    poly_relu3d_kernel<<<dim3(D * H, B), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>((__half*)x, E, D, H, W, C,
+                                                                                         1.0f / (float)(D - 1), 1.0f / (float)(H - 1));
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
 extern "C" int nrrt_coords_poly_gemm(const float* feat, int B, int Cc, const float* moments_t, int cases, int n_uv, int Cout,
                                      float a, float b, float* work, float* E, void* stream) {
     NRRT_REQUIRE(feat && moments_t && work && E, "null pointer");
@@ -643,10 +736,13 @@ extern "C" int nrrt_coords_poly_gemm(const float* feat, int B, int Cc, const flo
     if (B == 0) return NRRT_OK;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int N = cases * n_uv * Cout, M = B * 4;
-    float* G = work;                        // [B][4][Cc]
+    const bool pre_g = cases == 54;         // 3D: feat already holds the polynomial coefficients A (nrrt_coords_pieces_3d)
+    const float* G = pre_g ? feat : work;   // [B][4][Cc]
     float* Cw = work + (size_t)B * 4 * Cc;  // [B*4][N]
-    coords_g_kernel<<<grid_for((long long)B * Cc, 256), 256, 0, st>>>(feat, (long long)B * Cc, Cc, G);
-    NRRT_CUDA_TRY(cudaGetLastError());
+    if (!pre_g) {
+        coords_g_kernel<<<grid_for((long long)B * Cc, 256), 256, 0, st>>>(feat, (long long)B * Cc, Cc, work);
+        NRRT_CUDA_TRY(cudaGetLastError());
+    }
     sgemm_kernel<<<dim3(N / GN, (M + GM - 1) / GM), 256, 0, st>>>(G, moments_t, Cw, M, N, Cc);
     NRRT_CUDA_TRY(cudaGetLastError());
     const long long total = (long long)B * cases * Cout;

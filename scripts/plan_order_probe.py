@@ -30,3 +30,23 @@ print(f"longest first (oracle): {t1:.1f} ms")
 rng = np.random.default_rng(0)
 t2, _, _ = run(rng.permutation(B))
 print(f"random order: {t2:.1f} ms")
+
+# cheap difficulty proxies: straight-line blocked?, start-goal distance, free area in a window around the goal
+occ_free = (wl.occ_maps != 0)
+def line_blocked(m, s, g):
+    t = np.linspace(0.0, 1.0, 64)
+    ys = np.round(s[0] + (g[0] - s[0]) * t).astype(int); xs = np.round(s[1] + (g[1] - s[1]) * t).astype(int)
+    return not occ_free[m, ys, xs].all()
+blocked = np.array([line_blocked(wl.task_to_map[b], wl.starts[b], wl.goals[b]) for b in range(B)])
+dist = np.sqrt(((wl.starts - wl.goals).astype(np.float64) ** 2).sum(1))
+def goal_free(m, g, r=12):
+    y0, y1, x0, x1 = max(g[0] - r, 0), min(g[0] + r + 1, 512), max(g[1] - r, 0), min(g[1] + r + 1, 512)
+    return occ_free[m, y0:y1, x0:x1].mean()
+gfree = np.array([goal_free(wl.task_to_map[b], wl.goals[b]) for b in range(B)])
+from scipy.stats import spearmanr
+cost = it.astype(np.float64) * nn
+for name, v in (("blocked", blocked.astype(float)), ("dist", dist), ("1-goal_free", 1 - gfree)):
+    print(name, "spearman vs cost", round(spearmanr(v, cost).correlation, 3))
+for name, key in (("blocked,dist", blocked * 1000 + dist), ("goal_free", (1 - gfree) * 1000 + blocked * 100 + dist / 10)):
+    t3, _, _ = run(np.argsort(-key, kind="stable"))
+    print(f"proxy order [{name}]: {t3:.1f} ms")
