@@ -139,7 +139,12 @@ typedef enum NrrtConvKind {
     NRRT_CONV_K3S2 = 1,  /* nn.Conv2d/3d(k=3, s=2, p=1): first conv of layer2/3/4 */
     NRRT_CONV_K1S2 = 2,  /* nn.Conv2d/3d(k=1, s=2):      ResNet downsample branch */
     NRRT_CONV_K1S1 = 3,  /* nn.Conv2d/3d(k=1) */
-    NRRT_CONVT_K2S2 = 4  /* nn.ConvTranspose2d/3d(k=2, s=2): upconv6/7/8 */
+    NRRT_CONVT_K2S2 = 4, /* nn.ConvTranspose2d/3d(k=2, s=2): upconv6/7/8 */
+    NRRT_CONV_UPFOLD = 5 /* (2D) nn.ConvTranspose2d(k=2, s=2) composed with the 3x3 conv that consumes it (train.py:196-201:
+                            upconv7 -> conv7[0], upconv8 -> conv8[0]; nothing non-linear in between).  in = the ConvTranspose's
+                            input on its (in_h, in_w) grid, cin = its input channels; out / res / poly live on the
+                            (2 in_h, 2 in_w) grid; weight = fp16 [cout][4 output parities (row, col)][2x2 taps][cin], the
+                            composite weights; poly = nrrt_poly_fold output [n][4][9][4][cout]; res is required. */
 } NrrtConvKind;
 
 /* One fused layer: out = [relu2(post_scale * ] relu( scale * conv(in) + shift + residual ) [ + post_shift)].
@@ -238,6 +243,12 @@ int nrrt_coords_poly_gemm(const float* feat, int B, int Cc, const float* moments
  * nrrt_poly_relu_3d: x[b] = fp16(relu(x[b] + E[b](d, h, w))) in place on a channels-last (D, H, W, C) fp16 buffer. */
 int nrrt_coords_pieces_3d(const float* feat, int B, int Cc, float* A, void* stream);
 int nrrt_poly_relu_3d(void* x, const float* E, int B, int D, int H, int W, int C, void* stream);
+
+/* Epilogue polynomial of a 3x3 conv (nrrt_coords_poly output E [B][9][4][Cout] on the (2H, 2W) grid) re-expressed per
+ * output parity in the tile space of the NRRT_CONV_UPFOLD layer, the (H, W) grid: Ef [B][4][9][4][Cout].  cases_const
+ * (optional, fp32 [9][Cout]) is added to the constant term of border case k: the ConvTranspose bias (train.py:148,154)
+ * seen through the conv taps that fall inside the image. */
+int nrrt_poly_fold(const float* E, const float* cases_const, int B, int Cout, int H, int W, float* Ef, void* stream);
 
 /* conv6.0 hoisted out of the per-task path (2D; train.py:192-195).  The layer is linear in its input and only the
  * coordinate channels depend on the task, so its pre-activation = a per-map tensor (nrrt_conv_layer once per map) + a

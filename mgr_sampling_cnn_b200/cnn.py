@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import check
 
-K3S1, K3S2, K1S2, K1S1, CONVT = 0, 1, 2, 3, 4
+K3S1, K3S2, K1S2, K1S1, CONVT, UPFOLD = 0, 1, 2, 3, 4, 5
 
 
 def _ptr(t):
@@ -102,6 +102,30 @@ def _pack_convT_weight(w, device):
     return w.reshape(groups * cout, cin).to(torch.float16).contiguous()
 
 
+def _fold_weights(wt, bu, wc, device):
+    """ConvTranspose2d(k=2, s=2) (weight wt [cin_low, c_up, 2, 2], bias bu [c_up]) composed with a 3x3 conv over its output
+    (weight wc [cout, c_up, 3, 3]) -- train.py:196-201, nothing non-linear in between.  Output pixel (2i+a, 2j+b) of the conv
+    reads the upsampled pixels (2i+a+dy, 2j+b+dx), i.e. sub-position ((a+dy)%2, (b+dx)%2) of low-resolution pixel
+    (i + (a+dy)//2, j + (b+dx)//2): per output parity (a, b) a 2x2-tap conv over the low-resolution input.
+    Returns (fp16 [cout, 16 * cin_low] = [cout][parity a*2+b][tap][cin_low], tap = (row offset - (a-1)) * 2 + (column
+    offset - (b-1)), composed in fp64;  fp32 [9 border cases][cout] = the ConvTranspose bias seen through the conv taps
+    that fall inside the image, which nrrt_poly_fold adds to the epilogue polynomial)."""
+    wt = wt.detach().to(device).double()
+    wc = wc.detach().to(device).double()
+    cout, cin = wc.shape[0], wt.shape[0]
+    w = torch.zeros((cout, 4, 4, cin), dtype=torch.float64, device=device)
+    for a in range(2):
+        for b in range(2):
+            for dy in (-1, 0, 1):
+                for dx in (-1, 0, 1):
+                    tap = ((a + dy) // 2 - (a - 1)) * 2 + ((b + dx) // 2 - (b - 1))
+                    w[:, a * 2 + b, tap] += wc[:, :, dy + 1, dx + 1] @ wt[:, :, (a + dy) % 2, (b + dx) % 2].t()
+    valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}
+    bu = bu.detach().to(device).double()
+    bc = torch.stack([wc[:, :, valid[r]][:, :, :, valid[c]].sum(dim=(2, 3)) @ bu for r in range(3) for c in range(3)])
+    return w.reshape(cout, 16 * cin).to(torch.float16).contiguous(), bc.float().contiguous()
+
+
 class _Layer(object):
     """One nrrt_conv_layer call with its packed parameters (kept alive here)."""
 
@@ -118,6 +142,8 @@ class _Layer(object):
         sp = [g for i, g in enumerate(grid) if self.dims == 3 or i > 0]
         if self.kind == CONVT:
             return 2.0 * batch * _prod(sp) * (2 ** self.dims) * self.cout * self.cin_real
+        if self.kind == UPFOLD:  # per output pixel (4 per input pixel): 2x2 taps over the low-resolution channels
+            return 2.0 * batch * _prod(sp) * 4 * 4 * self.cout * self.cin_real
         stride = 2 if self.kind in (K3S2, K1S2) else 1
         taps = (3 ** self.dims) if self.kind in (K3S1, K3S2) else 1
         return 2.0 * batch * _prod([(g - 1) // stride + 1 for g in sp]) * self.cout * taps * self.cin_real
@@ -176,8 +202,8 @@ class _Layer(object):
         L.relu = 1 if self.relu else 0
         if self.post is not None:
             L.post_scale, L.post_shift = _ptr(self.post[0]), _ptr(self.post[1])
-        if poly is not None:
-            L.poly, L.poly_cases = _ptr(poly), poly.shape[1]
+        if poly is not None:  # [n, 9, 4, cout], or per output parity [n, 4, 9, 4, cout] for a folded layer
+            L.poly, L.poly_cases = _ptr(poly), poly.shape[-3]
         check(lib.nrrt_conv_layer(C.byref(L), stream))
 
 
@@ -334,6 +360,12 @@ class UNetPlan(object):
             self.up6.cin2 = 512
             self.up6.cin_real = 1024
         self.up7, self.up8 = convT(model.upconv7), convT(model.upconv8)
+
+        def fold(mu, mc, c_up):
+            """upconv7 -> conv7.0 / upconv8 -> conv8.0 as ONE layer (_fold_weights); the conv's bias and ReLU stay."""
+            w, bc = _fold_weights(mu.weight, mu.bias, mc.weight[:, :c_up], dev)
+            scale, shift = _fold_bn(None, mc.bias, mc.out_channels, dev)
+            return _Layer(d, UPFOLD, mu.in_channels, mc.out_channels, w, scale, shift, True), bc
         # 3D: the coordinate channels leave the GEMM too; their (piecewise bilinear) field and the ReLU are applied by
         # nrrt_poly_relu_3d after the layer (csrc/conv_aux.cu)
         c60, self.c6e = (None, None) if self.poly else conv_split(model.conv6[0], 512, 256, False, relu=False)
@@ -342,6 +374,10 @@ class UNetPlan(object):
         if not self.poly:
             self.mt3 = {"e_c6": conv_moments3d(model.conv6[0], 768), "e_c7": conv_moments3d(model.conv7[0], 256),
                         "e_c8": conv_moments3d(model.conv8[0], 128)}
+        # 2D: upconv7 -> conv7.0 and upconv8 -> conv8.0 as one folded layer each (used when the low-resolution grid holds
+        # whole 16x16 tiles; the separate layers above remain for small grids and as the test reference)
+        self.c7f, self.bc7 = fold(model.upconv7, model.conv7[0], 128) if self.poly else (None, None)
+        self.c8f, self.bc8 = fold(model.upconv8, model.conv8[0], 64) if self.poly else (None, None)
         self.c6 = (c60, conv(model.conv6[2], K3S1))
         self.c7 = (c70, conv(model.conv7[2], K3S1))
         self.c8 = (c80, conv(model.conv8[2], K3S1))
@@ -382,13 +418,14 @@ class UNetPlan(object):
         t8w, t7w, t6w = 64, 128, 512  # (the coordinate channels are never materialised next to them)
 
         def make():
-            d = {"t8": b(0, t8w), "j": b(0, 128), "t7": b(1, t7w), "g7": b(1, 256), "i": b(1, 128),
-                 "g6": b(2, 512), "h": b(2, 256)}
+            d = {"j": b(0, 128), "g7": b(1, 256), "i": b(1, 128), "g6": b(2, 512), "h": b(2, 256)}
+            if not self.use_fold(grid):  # the ConvTranspose outputs exist only where the layers run unfolded
+                d["t8"], d["t7"] = b(0, t8w), b(1, t7w)
             if not self.poly:
                 d["t6"] = b(2, t6w)
                 d["c5"] = b(3, 512)  # interpolated coordinate channels at the bottleneck (second input of upconv6)
             return d
-        return self._cached(("dec", B) + tuple(grid), make)
+        return self._cached(("dec", B, self.use_fold(grid)) + tuple(grid), make)
 
     def activation_bytes(self, B, grid):
         b = list(self._enc_buffers(B, grid).values()) + list(self._dec_buffers(B, grid).values())
@@ -396,7 +433,7 @@ class UNetPlan(object):
 
     def layers(self):
         out = [self.stem2, self.up6, self.up7, self.up8] + list(self.c6) + list(self.c7) + list(self.c8)
-        out += [self.c6e, self.c7e, self.c8e] + ([self.c6full] if self.poly else [])
+        out += [self.c6e, self.c7e, self.c8e] + ([self.c6full, self.c7f, self.c8f] if self.poly else [])
         out = [l for l in out if l is not None]
         for stg in self.enc:
             for c1, c2, ds in stg:
@@ -407,7 +444,7 @@ class UNetPlan(object):
         self.profiler = prof
         for l in self.layers():
             l.profiler = prof
-        for name in ("stem2", "up6", "up7", "up8", "c6e", "c7e", "c8e", "c6full"):
+        for name in ("stem2", "up6", "up7", "up8", "c6e", "c7e", "c8e", "c6full", "c7f", "c8f"):
             if getattr(self, name, None) is not None:
                 getattr(self, name).name = name
         for name in ("c6", "c7", "c8"):
@@ -419,6 +456,12 @@ class UNetPlan(object):
                 for li, l in enumerate(blk):
                     if l is not None:
                         l.name = f"enc{si + 2}.{bi}.{('c1', 'c2', 'ds')[li]}"
+
+    fold = True  # tests: False runs ConvTranspose and the conv after it as separate layers
+
+    def use_fold(self, grid):
+        """upconv7/conv7.0 and upconv8/conv8.0 as folded layers: 2D, low-resolution grids of at least one 16x16 tile."""
+        return self.poly and self.fold and min(grid[1], grid[2]) >= 64
 
     def flops_per_sample(self, grid):
         """Algorithmic FLOPs of the tensor-core layers for one sample on input grid (D, H, W) (excludes the 3-/1-channel
@@ -434,8 +477,11 @@ class UNetPlan(object):
                 tot += ds.flops(1, gin[s_i])
         c6_first = self.c6full if self.poly else self.c6[0]
         tot += self.up6.flops(1, g[3]) + c6_first.flops(1, g[2]) + self.c6[1].flops(1, g[2])
-        tot += self.up7.flops(1, g[2]) + self.c7[0].flops(1, g[1]) + self.c7[1].flops(1, g[1])
-        tot += self.up8.flops(1, g[1]) + self.c8[0].flops(1, g[0]) + self.c8[1].flops(1, g[0])
+        if self.use_fold(grid):
+            tot += self.c7f.flops(1, g[2]) + self.c7[1].flops(1, g[1]) + self.c8f.flops(1, g[1]) + self.c8[1].flops(1, g[0])
+        else:
+            tot += self.up7.flops(1, g[2]) + self.c7[0].flops(1, g[1]) + self.c7[1].flops(1, g[1])
+            tot += self.up8.flops(1, g[1]) + self.c8[0].flops(1, g[0]) + self.c8[1].flops(1, g[0])
         tot += (0 if self.poly else self.c6e.flops(1, g[2])) + self.c7e.flops(1, g[1]) + self.c8e.flops(1, g[0])
         return tot
 
@@ -510,6 +556,13 @@ class UNetPlan(object):
                                            j - i, 512, cout, g[3][1], g[3][2], _ptr(work), _ptr(P16[i:j]), st))
             prep["p16"] = P16
             del prep["e_up6"], prep["e_c6"]
+            if self.use_fold(grid):  # per-parity polynomials of the folded layers (tile space = the low-resolution grid)
+                for name, bc, lv in (("e_c7", self.bc7, 2), ("e_c8", self.bc8, 1)):
+                    E = prep[name]
+                    Ef = torch.empty((B, 4) + tuple(E.shape[1:]), dtype=torch.float32, device=dev)
+                    _lib.count_launch()
+                    check(self.lib.nrrt_poly_fold(_ptr(E), _ptr(bc), B, E.shape[-1], g[lv][1], g[lv][2], _ptr(Ef), st))
+                    prep[name] = Ef
         else:
             # 3D: post-pass polynomials of conv6.0 / conv7.0 / conv8.0 (54 cases, two h-pieces stacked along the channels)
             if P != 6:
@@ -625,13 +678,20 @@ class UNetPlan(object):
             self.c6[0].run(lib, st, bf["t6"], 0, g[2], bf["g6"], 0, bf["r6"], 0, res_idx=ri)
             post3d(bf["g6"], prep["e_c6"], 2)
         self.c6[1].run(lib, st, bf["g6"], 0, g[2], bf["h"], 0)
-        self.up7.run(lib, st, bf["h"], 0, g[2], bf["t7"], 0)
-        self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, bf["r7"], 0, poly=prep.get("e_c7") if self.poly else None, res_idx=ri)
+        folded = self.poly and prep["e_c7"].dim() == 5  # coords_prepare decided (use_fold)
+        if folded:
+            self.c7f.run(lib, st, bf["h"], 0, g[2], bf["g7"], 0, bf["r7"], 0, poly=prep["e_c7"], res_idx=ri)
+        else:
+            self.up7.run(lib, st, bf["h"], 0, g[2], bf["t7"], 0)
+            self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, bf["r7"], 0, poly=prep.get("e_c7") if self.poly else None, res_idx=ri)
         if not self.poly:
             post3d(bf["g7"], prep["e_c7"], 1)
         self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
-        self.up8.run(lib, st, bf["i"], 0, g[1], bf["t8"], 0)
-        self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8") if self.poly else None, res_idx=ri)
+        if folded:
+            self.c8f.run(lib, st, bf["i"], 0, g[1], bf["j"], 0, bf["r8"], 0, poly=prep["e_c8"], res_idx=ri)
+        else:
+            self.up8.run(lib, st, bf["i"], 0, g[1], bf["t8"], 0)
+            self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8") if self.poly else None, res_idx=ri)
         if not self.poly:
             post3d(bf["j"], prep["e_c8"], 0)
 

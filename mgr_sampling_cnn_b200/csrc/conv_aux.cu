@@ -589,6 +589,40 @@ int grid_for(long long work, int block) {
     return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
 }
 
+// ---- nrrt_poly_fold: the epilogue polynomial of a 3x3 conv re-expressed for the folded ConvTranspose+conv layer -------
+// (conv_tc.cu, conv_halo2_kernel, p.fold).  The conv's output pixel (h, w) = (2i + a, 2j + b) is pixel (i, j) of parity
+// (a, b) in the folded layer's tile space, the (H, W) low-resolution grid.  With ty = h / (2H - 1) = al_h * ty' + be_h,
+// ty' = i / (H - 1), al_h = 2 (H - 1) / (2H - 1), be_h = a / (2H - 1) (columns alike), the bilinear form
+// E0 + ty E1 + tx E2 + ty tx E3 becomes E0' + ty' E1' + tx' E2' + ty' tx' E3' with the coefficients below.  Border cases:
+// output row 0 exists only in parity a = 0 (tile row 0) and the last output row only in a = 1 (last tile row); the other
+// tile-space frame rows of a parity are interior pixels of the conv and get the interior case (columns alike).
+// `cases_const` [9][Cout] (optional) is added to E0: the ConvTranspose bias seen through the conv taps inside the image.
+__global__ void poly_fold_kernel(const float* __restrict__ E, const float* __restrict__ cases_const, int B, int Cout, float al_h,
+                                 float al_w, float inv_oh, float inv_ow, float* __restrict__ Ef) {
+    const long long total = (long long)B * 36 * Cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cout);
+        long long r = i / Cout;
+        const int kc = (int)(r % 9); r /= 9;
+        const int par = (int)(r % 4);
+        const long long b = r / 4;
+        const int a = par >> 1, bb = par & 1;
+        const int rt = kc / 3, ct = kc % 3;
+        const int ro = (rt == 0 && a == 0) ? 0 : ((rt == 2 && a == 1) ? 2 : 1);
+        const int co = (ct == 0 && bb == 0) ? 0 : ((ct == 2 && bb == 1) ? 2 : 1);
+        const float* src = E + ((b * 9 + ro * 3 + co) * 4) * Cout + c;
+        float e0 = src[0];
+        const float e1 = src[Cout], e2 = src[2 * (size_t)Cout], e3 = src[3 * (size_t)Cout];
+        if (cases_const) e0 += __ldg(cases_const + (ro * 3 + co) * Cout + c);
+        const float bh = (float)a * inv_oh, bw = (float)bb * inv_ow;
+        float* dst = Ef + (((b * 4 + par) * 9 + kc) * 4) * Cout + c;
+        dst[0] = e0 + bh * e1 + bw * e2 + bh * bw * e3;
+        dst[Cout] = al_h * (e1 + bw * e3);
+        dst[2 * (size_t)Cout] = al_w * (e2 + bh * e3);
+        dst[3 * (size_t)Cout] = al_h * al_w * e3;
+    }
+}
+
 }  // namespace
 
 static int stem_launch(int dims, const float* x, const uint8_t* occ, const int32_t* t2m, int n, int cin, int d, int h, int w,
@@ -747,6 +781,17 @@ extern "C" int nrrt_coords_poly_gemm(const float* feat, int B, int Cc, const flo
     NRRT_CUDA_TRY(cudaGetLastError());
     const long long total = (long long)B * cases * Cout;
     coords_combine_kernel<<<grid_for(total, 256), 256, 0, st>>>(Cw, total, cases, n_uv, Cout, a, b, E);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_poly_fold(const float* E, const float* cases_const, int B, int Cout, int H, int W, float* Ef, void* stream) {
+    NRRT_REQUIRE(E && Ef && B >= 0 && Cout > 0 && H >= 2 && W >= 2, "bad poly_fold arguments");
+    if (B == 0) return NRRT_OK;
+    const long long total = (long long)B * 36 * Cout;
+    const float inv_oh = 1.0f / (float)(2 * H - 1), inv_ow = 1.0f / (float)(2 * W - 1);
+    poly_fold_kernel<<<grid_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        E, cases_const, B, Cout, 2.0f * (float)(H - 1) * inv_oh, 2.0f * (float)(W - 1) * inv_ow, inv_oh, inv_ow, Ef);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

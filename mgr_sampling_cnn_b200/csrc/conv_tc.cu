@@ -60,7 +60,9 @@ struct ConvParams {
     const float* poly;   // optional [N][poly_cases][4][cout]: bilinear epilogue term E0 + ty*E1 + tx*E2 + ty*tx*E3
     int poly_cases;      // 9 = 3x3 border cases (row case * 3 + column case); else one case per weight group
     float inv_h, inv_w;  // 1/(H-1), 1/(W-1) of the tile-space grid
-    int outer;           // slab kernels: slab loads per input-channel chunk: 3 (dx) in 2D, 9 (dz, dx) in 3D
+    int outer;           // slab kernels: slab loads per input-channel chunk: 3 (dx) in 2D, 9 (dz, dx) in 3D, 2 when folded
+    int inner;           // slab kernels: vertical taps served by one slab: 3, or 2 when folded
+    int fold;            // pair slab kernel: ConvTranspose(k=2,s=2) folded into the 3x3 conv that follows it (see conv_halo2_kernel)
     int ts;              // pair kernels: output tile staged in shared memory and written with TMA stores (see below)
     int pm;              // pair kernels: interior polynomial applied by one extra tcgen05.mma per tile (see pm_* below)
     const float* head_w; // optional fused 1x1 head (cout -> 1): logits[pixel] = head_b + sum_c relu_out[c] * head_w[c]
@@ -316,11 +318,12 @@ __device__ __forceinline__ void stage_tile_params(const ConvParams& p, float* ds
 // the 256 epilogue threads into rows 2..6 of the tile's parameter buffer.  hr / wc = tile-local index of the frame row /
 // column (-1: none), rr / cc = its border case (0 = first, 2 = last).  Tile-uniform: every epilogue thread calls it.
 template <int BLOCK_N>
-__device__ __forceinline__ void pm_stage_frame(const ConvParams& p, float* dst, int n, int et, int h0, int w0, int hr, int wc) {
+__device__ __forceinline__ void pm_stage_frame(const ConvParams& p, float* dst, int n, int et, int h0, int w0, int hr, int wc,
+                                               int col0 = 0) {
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
     const int rr = hr < 0 ? 1 : (h0 + hr == 0 ? 0 : 2), cc = wc < 0 ? 1 : (w0 + wc == 0 ? 0 : 2);
     const float ty_r = (float)(h0 + hr) * p.inv_h, tx_c = (float)(w0 + wc) * p.inv_w;
-    const float* base = p.poly + ((size_t)n * 9 * 4) * p.cout;
+    const float* base = p.poly + ((size_t)n * 9 * 4) * p.cout + col0;
     for (int i = et; i < 3 * BLOCK_N; i += 32 * kEpiWarps) {
         const int which = i / BLOCK_N, c = i - which * BLOCK_N;  // 0: row frame, 1: column frame, 2: corner
         if ((which == 0 && hr < 0) || (which == 1 && wc < 0) || (which == 2 && (hr < 0 || wc < 0))) continue;
@@ -607,7 +610,7 @@ __device__ __forceinline__ void pm_write_basis(uint8_t* tile, int row, int hl, i
 // path of the epilogue, the TMA producer and the MMA issuer; ends with the writes visible to the async proxy.
 template <int ROWS_B>
 __device__ __forceinline__ void pm_produce_b(const ConvParams& p, uint8_t* bx, int t0, int nt, uint32_t rank, const int (&tn)[2],
-                                             const int (&th0)[2], const int (&tw0)[2], const bool (&tlive)[2]) {
+                                             const int (&th0)[2], const int (&tw0)[2], const bool (&tlive)[2], int col0 = 0) {
     constexpr int kMaxItems = (2 * ROWS_B + 31) / 32;  // items per thread of the auxiliary warp
     float e[kMaxItems][4];
     // all coefficient loads first (independent, one latency), then the arithmetic
@@ -615,7 +618,7 @@ __device__ __forceinline__ void pm_produce_b(const ConvParams& p, uint8_t* bx, i
     for (int i = 0; i < kMaxItems; ++i) {
         const int it = t0 + i * nt;
         const int j = it / ROWS_B, r = it - j * ROWS_B;
-        const int co = (int)rank * ROWS_B + r;
+        const int co = col0 + (int)rank * ROWS_B + r;
         e[i][0] = e[i][1] = e[i][2] = e[i][3] = 0.f;
         if (it < 2 * ROWS_B && tlive[j] && co < p.cout) {
             const float* src = p.poly + (((size_t)tn[j] * 9 + 4) * 4) * p.cout + co;  // interior case
@@ -1169,6 +1172,17 @@ struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
 // RES: TMA-staged residual tile as in conv_gemm2_kernel; a piece = (column block, 64-channel chunk) = 128 pixels x 128 B.
 // PM: the interior polynomial coordinate term is one extra MMA per accumulator (pm_* above).
 // TS: TMA-store epilogue (pieces shared with the residual staging; the auxiliary warp issues the stores).
+// p.fold: ConvTranspose(k=2, s=2) folded into the 3x3 conv that consumes it (train.py:196-201: upconv7 -> conv7.0,
+// upconv8 -> conv8.0; no nonlinearity in between, so the composition is linear).  Output pixel (2i + a, 2j + b) of the conv
+// sees the upsampled pixels (2i + a + dy, 2j + b + dx), which come from the 2 x 2 low-resolution pixels (i + a - 1 .. i + a,
+// j + b - 1 .. j + b): per output parity (a, b) the pair of layers is ONE 2x2-tap convolution over the low-resolution
+// input with composite weights W'[par][tap] = sum of Wconv[dy, dx] * Wup[sub-position] (host: cnn.py fold_weights).
+// The tile space is the low-resolution grid; a pair iteration is (tile pair q, N half nh, parity par); slabs start at
+// (h0 - 1 + a, w0 - 1 + b + dx) and serve two vertical taps; residual tiles are read and results stored through tensor
+// maps with element stride 2 starting at (2 h0 + a, 2 w0 + b).  The ConvTranspose bias reaches the output through the
+// taps that fall inside the image, a per-border-case constant that the host adds to the polynomial's constant term
+// (the polynomial itself is re-expressed per parity in tile-space coordinates: nrrt_poly_fold).  20 % fewer MACs than
+// the two layers, and the upsampled activation (the widest tensor of the stage) is never written or read.
 template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM, bool TS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
@@ -1197,7 +1211,12 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the pair's MMAs), 1 = peer
     const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
-    const int total_pairs = (p.m_tiles + 1) >> 1;  // a CTA pair owns two consecutive 16x16 tiles; n_tiles == 1
+    // a CTA pair owns two consecutive 16x16 tiles; n_tiles == 1 unless folded: pair iteration = (tile pair, N half, parity)
+    const int total_pairs = ((p.m_tiles + 1) >> 1) * (p.fold ? 4 * p.n_tiles : 1);
+    auto decode = [&](int pt, int& q, int& nh, int& par) {
+        if (p.fold) { par = pt & 3; pt >>= 2; nh = pt % p.n_tiles; q = pt / p.n_tiles; }
+        else { par = 0; nh = 0; q = pt; }
+    };
 
     if (warp == 1 && lane == 0) {
         // "empty" and accumulator-full barriers collect the commits of both MMA issuers
@@ -1229,7 +1248,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0, rphase = 0;
             for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
-                int m = pt * 2 + (int)rank;
+                int q, nh, par;
+                decode(pt, q, nh, par);
+                const int fa = par >> 1, fb = par & 1;  // output parity (row, column) of a folded layer
+                int m = q * 2 + (int)rank;
                 const bool live = m < p.m_tiles;
                 const int tw = m % p.tiles_w; m /= p.tiles_w;
                 const int th = m % p.tiles_h; m /= p.tiles_h;
@@ -1243,20 +1265,22 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     const int cc = (c < p.split_chunk ? c : c - p.split_chunk) * kBlockK;
                     const int ns = c < p.split_chunk ? n1 : n2;
                     for (int o = 0; o < p.outer; ++o) {  // (dz, dx): 3 slabs per chunk in 2D, 9 in 3D (depth slice d + dz - 1)
-                        const int dx = o % 3, dz = o / 3;
+                        const int dx = p.fold ? o : o % 3, dz = p.fold ? 0 : o / 3;
                         const int dd = td + dz - (p.outer == 9 ? 1 : 0);
+                        const int xs = w0 - 1 + dx + fb, ys = h0 - 1 + fa;
                         mbar_wait(aempty(sa), pa ^ 1u);
                         if (rank == 0) mbar_expect_tx(afull(sa), 4 * kSlabBytes);  // two slabs from each CTA of the pair
                         const uint32_t dst = base + sa * L::a_stage;
                         const uint32_t abar = afull(sa) & kPeerBitMask;
-                        tma2_load_5d(dst, am, abar, cc, w0 - 1 + dx, h0 - 1, dd, ns);
-                        tma2_load_5d(dst + kSlabBytes, am, abar, cc, w0 + 7 + dx, h0 - 1, dd, ns);
+                        tma2_load_5d(dst, am, abar, cc, xs, ys, dd, ns);
+                        tma2_load_5d(dst + kSlabBytes, am, abar, cc, xs + 8, ys, dd, ns);
                         if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
-                        for (int dy = 0; dy < 3; ++dy) {
+                        for (int dy = 0; dy < p.inner; ++dy) {
                             mbar_wait(bempty(sb), pb ^ 1u);
                             if (rank == 0) mbar_expect_tx(bfull(sb), 2 * L::b_stage);  // each CTA loads half of the B tile
+                            const int tap = p.fold ? (par * 4 + dy * 2 + dx) : ((dz * 3 + dy) * 3 + dx);
                             tma2_load_2d(base + L::off_b + sb * L::b_stage, &map_b, bfull(sb) & kPeerBitMask,
-                                         (((dz * 3 + dy) * 3 + dx) * p.cin_chunks + c) * kBlockK, (int)rank * (BLOCK_N / 2));
+                                         (tap * p.cin_chunks + c) * kBlockK, nh * BLOCK_N + (int)rank * (BLOCK_N / 2));
                             if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
                         }
                     }
@@ -1266,8 +1290,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     for (int s = 0; s < 2 * RC; ++s) {
                         mbar_wait(rempty_bar(s), rphase ^ 1u);
                         mbar_expect_tx(rfull_bar(s), kResPiece);
+                        const int rw = w0 + (s / RC) * 8;
                         tma_load_5d(base + L::off_res + s * kResPiece, &map_r, rfull_bar(s),
-                                    (int)p.res_coffset + (s % RC) * 64, w0 + (s / RC) * 8, h0, td, nr);
+                                    (int)p.res_coffset + nh * BLOCK_N + (s % RC) * 64, p.fold ? 2 * rw + fb : rw,
+                                    p.fold ? 2 * h0 + fa : h0, td, nr);
                     }
                     rphase ^= 1u;
                 }
@@ -1296,7 +1322,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         mbar_wait(afull(sa), pa);
                         tc_fence_after();
                         const uint32_t a_base = base + sa * L::a_stage + blk * kSlabBytes;
-                        for (int dy = 0; dy < 3; ++dy) {
+                        for (int dy = 0; dy < p.inner; ++dy) {
                             mbar_wait(bfull(sb), pb);
                             tc_fence_after();
                             const uint64_t bdesc = make_smem_desc(base + L::off_b + sb * L::b_stage);
@@ -1339,24 +1365,28 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int et = threadIdx.x - 64;
         int acc = 0;
         uint32_t acc_phase = 0, rphase = 0;
-        int last_n[2] = {-1, -1};
+        int last_n[2] = {-1, -1}, last_nh[2] = {-1, -1};
         for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
-            int m = pt * 2 + (int)rank;
+            int q, nh, par;
+            decode(pt, q, nh, par);
+            int m = q * 2 + (int)rank;
             const bool live = m < p.m_tiles;
             const int tw = m % p.tiles_w; m /= p.tiles_w;
             const int th = m % p.tiles_h; m /= p.tiles_h;
             const int td = m % p.tiles_d;
-            const int n = live ? m / p.tiles_d : 0;
+            // folded layers: the polynomial is stored per (sample, parity); n only indexes it (results leave by TMA)
+            const int n = live ? (p.fold ? (m / p.tiles_d) * 4 + par : m / p.tiles_d) : 0;
+            const int col0 = nh * BLOCK_N;
             float* sc = ss + acc * 8 * BLOCK_N;
-            stage_tile_params<BLOCK_N>(p, sc, 0, n, et, last_n[acc] < 0, !PM && last_n[acc] != n);
-            last_n[acc] = n;
+            stage_tile_params<BLOCK_N>(p, sc, col0, n, et, last_nh[acc] != nh, !PM && (last_n[acc] != n || last_nh[acc] != nh));
+            last_n[acc] = n; last_nh[acc] = nh;
             int frame = 0;
             if (PM) {
                 const int h0 = th * 16, w0 = tw * 16;
                 const int hr = h0 == 0 ? 0 : (p.H - 1 - h0 < 16 ? p.H - 1 - h0 : -1);
                 const int wc = w0 == 0 ? 0 : (p.W - 1 - w0 < 16 ? p.W - 1 - w0 : -1);
                 if (live && (hr >= 0 || wc >= 0)) {
-                    pm_stage_frame<BLOCK_N>(p, sc, n, et, h0, w0, hr, wc);
+                    pm_stage_frame<BLOCK_N>(p, sc, n, et, h0, w0, hr, wc, col0);
                     const bool on_r = (row >> 3) == hr, on_c = blk * 8 + (row & 7) == wc;
                     frame = on_r ? (on_c ? 3 : 1) : (on_c ? 2 : 0);
                 }
@@ -1384,7 +1414,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 }
                 if (TS) srow = base_ptr + L::off_res + piece * kResPiece + row * 128;
                 if (valid)
-                    epilogue_chunk(p, v, c * 32, c * 32, n, td, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
+                    epilogue_chunk(p, v, col0 + c * 32, c * 32, n, td, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
                                    sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame, srow);
                 if ((RES || TS) && (c & 1)) {  // both 32-column halves of the piece are done
                     if (TS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1408,15 +1438,18 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (itq >= 2) mbar_wait(tfull_bar(a), (uint32_t)(((itq >> 1) - 1) & 1));
             int tn[2], th0[2], tw0[2];
             bool tlive[2];
+            int qq, nh, par;
+            decode(q, qq, nh, par);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                int mj = q * 2 + j;
+                int mj = qq * 2 + j;
                 tlive[j] = mj < p.m_tiles;
                 tw0[j] = (mj % p.tiles_w) * 16; mj /= p.tiles_w;
                 th0[j] = (mj % p.tiles_h) * 16;
-                tn[j] = tlive[j] ? mj / p.tiles_h : 0;  // (PM is 2D only: tiles_d == 1)
+                tn[j] = tlive[j] ? (p.fold ? (mj / p.tiles_h) * 4 + par : mj / p.tiles_h) : 0;  // (PM is 2D only: tiles_d == 1)
             }
-            pm_produce_b<BLOCK_N / 2>(p, base_ptr + L::off_pm + 2 * 4096 + a * L::pm_b, lane, 32, rank, tn, th0, tw0, tlive);
+            pm_produce_b<BLOCK_N / 2>(p, base_ptr + L::off_pm + 2 * 4096 + a * L::pm_b, lane, 32, rank, tn, th0, tw0, tlive,
+                                      nh * BLOCK_N);
             __syncwarp();
             if (lane == 0) mbar_arrive_leader_release(bxfull_bar(a));  // one arrival per CTA of the pair
         };
@@ -1430,7 +1463,9 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++it) {
             if (PM && pt + n_clusters < total_pairs) produce(pt + n_clusters, it + 1);
             if (TS) {
-                int m = pt * 2 + (int)rank;
+                int q, nh, par;
+                decode(pt, q, nh, par);
+                int m = q * 2 + (int)rank;
                 const bool live = m < p.m_tiles;
                 const int tw = m % p.tiles_w; m /= p.tiles_w;
                 const int th = m % p.tiles_h; m /= p.tiles_h;
@@ -1441,9 +1476,11 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         const int piece = b * RC + k;
                         mbar_wait(sdone_bar(piece), sphase);
                         if (lane == 0) {
-                            if (live)
-                                tma_store_5d(&map_o, base + L::off_res + piece * kResPiece, (int)p.out_coffset + k * 64,
-                                             tw * 16 + b * 8, th * 16, td, n);
+                            if (live) {
+                                const int ow = tw * 16 + b * 8, oh = th * 16;
+                                tma_store_5d(&map_o, base + L::off_res + piece * kResPiece, (int)p.out_coffset + nh * BLOCK_N + k * 64,
+                                             p.fold ? 2 * ow + (par & 1) : ow, p.fold ? 2 * oh + (par >> 1) : oh, td, n);
+                            }
                             tma_store_commit_and_wait_read();
                             mbar_arrive(rempty_bar(piece));  // free for the next residual load / the next tile's results
                         }
@@ -1500,7 +1537,7 @@ int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMa
     static_assert(L::total <= 232448, "shared memory budget");
     auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
-    const int pairs = (p.m_tiles + 1) / 2;
+    const int pairs = ((p.m_tiles + 1) / 2) * (p.fold ? 4 * p.n_tiles : 1);
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
     kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, mo, p);
     NRRT_CUDA_TRY(cudaGetLastError());
@@ -1554,7 +1591,7 @@ void pick_box(int W, int H, int D, int& bw, int& bh, int& bd) {
 extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     NRRT_REQUIRE(l && l->in && l->weight && l->scale && l->shift, "null pointer in conv layer");
     NRRT_REQUIRE(l->dims == 2 || l->dims == 3, "dims must be 2 or 3");
-    NRRT_REQUIRE(l->kind >= 0 && l->kind <= 4, "unknown conv kind %d", l->kind);
+    NRRT_REQUIRE(l->kind >= 0 && l->kind <= 5, "unknown conv kind %d", l->kind);
     NRRT_REQUIRE(l->cin > 0 && l->cin % 64 == 0, "Cin must be a multiple of 64 (got %d)", l->cin);
     NRRT_REQUIRE(l->cin2 >= 0 && l->cin2 % 64 == 0, "Cin2 must be a multiple of 64 (got %d)", l->cin2);
     if (l->cin2 > 0) NRRT_REQUIRE(l->in2 && l->in2_cstride % 8 == 0 && ((uintptr_t)l->in2 & 15) == 0 && l->in2_n >= 1, "bad second input");
@@ -1578,7 +1615,13 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         case NRRT_CONV_K1S2: stride = 2; ksz = 1; pad = 0; break;
         case NRRT_CONV_K1S1: ksz = 1; pad = 0; break;
         case NRRT_CONVT_K2S2: ksz = 1; pad = 0; up = 2; break;
+        case NRRT_CONV_UPFOLD: break;  // tile space = the low-resolution input grid, geometry of a 3x3 stride-1 conv
     }
+    const bool fold = l->kind == NRRT_CONV_UPFOLD;
+    if (fold)
+        NRRT_REQUIRE(!three_d && l->cout % 128 == 0 && l->cin2 == 0 && l->res && l->out && !l->logits && !l->post_scale &&
+                         l->res_coffset % 64 == 0 && !l->force_per_tap && !l->no_tma_store,
+                     "folded ConvTranspose+conv layers: 2D, Cout multiple of 128, with a residual and a stored output");
     auto out_dim = [&](int i) { return (i + 2 * pad - ksz) / stride + 1; };
     p.N = N;
     p.W = out_dim(iW); p.H = out_dim(iH); p.D = three_d ? out_dim(iD) : 1;
@@ -1603,12 +1646,15 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     p.idx1 = l->in_index; p.idx2 = l->in2_index;
     const int groups = up == 2 ? (three_d ? 8 : 4) : 1;
     const int rows_total = groups * l->cout;
-    const int block_n = rows_total % 256 == 0 ? 256 : (rows_total % 128 == 0 ? 128 : 64);
+    const int block_n = fold ? 128 : (rows_total % 256 == 0 ? 256 : (rows_total % 128 == 0 ? 128 : 64));
     NRRT_REQUIRE(rows_total % block_n == 0, "Cout (x groups) = %d must be a multiple of 64", rows_total);
     p.n_tiles = rows_total / block_n;
     p.out = (__half*)l->out; p.out_cstride = l->out_cstride; p.out_coffset = l->out_coffset;
     p.up = up; p.up_d = (up == 2 && three_d) ? 2 : 1;
     p.oW = p.W * up; p.oH = p.H * up; p.oD = p.D * p.up_d;
+    p.fold = fold ? 1 : 0;
+    const int ups = fold ? 2 : 1;  // output grid of a folded layer = 2 x the tile-space grid (p.up stays 1: no weight groups)
+    if (fold) { p.oW = 2 * p.W; p.oH = 2 * p.H; }
     p.cout = l->cout;
     p.scale = l->scale; p.shift = l->shift;
     p.scale2 = l->post_scale; p.shift2 = l->post_shift;
@@ -1635,10 +1681,11 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     }
     // 2D 3x3 stride-1 layers with a narrow N are L2-bound in the per-tap kernel: use the slab (halo-reuse) kernel
     // (3D: per depth slice, when the 16x16 tiles fill the slice and the pair kernel runs it)
-    const bool halo = l->kind == NRRT_CONV_K3S1 && p.n_tiles == 1 && block_n <= 128 && !l->force_per_tap &&
-                      (!three_d || (l->force_per_tap != 2 && p.W % 16 == 0 && p.H % 16 == 0));
+    const bool halo = fold || (l->kind == NRRT_CONV_K3S1 && p.n_tiles == 1 && block_n <= 128 && !l->force_per_tap &&
+                      (!three_d || (l->force_per_tap != 2 && p.W % 16 == 0 && p.H % 16 == 0)));
     const bool pair = l->force_per_tap != 2 && (halo || block_n >= 128);  // CTA pairs (cta_group::2)
-    p.outer = three_d ? 9 : 3;
+    p.outer = fold ? 2 : (three_d ? 9 : 3);
+    p.inner = fold ? 2 : 3;
     if (halo) {
         p.bw = 16; p.bh = 16; p.bd = 1; p.rows = 256;
         p.tiles_w = (p.W + 15) / 16; p.tiles_h = (p.H + 15) / 16; p.tiles_d = p.D;
@@ -1667,7 +1714,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d (box %d,%d,%d stride %d)", (int)r, p.bw, p.bh, p.bd, stride);
     }
     {
-        const cuuint64_t ktot = (cuuint64_t)p.ntaps * cin_total;
+        const cuuint64_t ktot = (cuuint64_t)(fold ? 16 : p.ntaps) * cin_total;  // folded: [4 parities][2x2 taps][Cin]
         const cuuint64_t gdim[2] = {ktot, (cuuint64_t)rows_total};
         const cuuint64_t gstr[1] = {ktot * 2};
         const cuuint32_t box[2] = {64, (cuuint32_t)(pair ? block_n / 2 : block_n)};  // a CTA of a pair loads half of B
@@ -1687,15 +1734,15 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         const cuuint64_t cs = (cuuint64_t)l->out_cstride * 2;
         const cuuint64_t gstr[4] = {cs, cs * p.oW, cs * p.oW * p.oH, cs * p.oW * p.oH * p.oD};
         cuuint32_t box[5] = {64, (cuuint32_t)(p.bw * up), (cuuint32_t)(p.bh * up), (cuuint32_t)(p.bd * p.up_d), 1};
-        if (halo) { box[1] = 8; box[2] = 16; box[3] = 1; }
-        const cuuint32_t estr[5] = {1, (cuuint32_t)up, (cuuint32_t)up, (cuuint32_t)p.up_d, 1};
+        if (halo) { box[1] = 8 * ups; box[2] = 16 * ups; box[3] = 1; }
+        const cuuint32_t estr[5] = {1, (cuuint32_t)(up * ups), (cuuint32_t)(up * ups), (cuuint32_t)p.up_d, 1};
         const CUresult r = encode(&mo, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, l->out, gdim, gstr, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(output) failed: %d", (int)r);
     }
     // interior polynomial through the tensor core: 2D 3x3 convs on the pair kernels with a staged residual (conv7.0 / conv8.0)
-    p.pm = (tma_res && l->poly && l->poly_cases == 9 && p.n_tiles == 1 && !l->no_poly_mma && !three_d && !l->post_scale &&
+    p.pm = (tma_res && l->poly && l->poly_cases == 9 && (p.n_tiles == 1 || fold) && !l->no_poly_mma && !three_d && !l->post_scale &&
             ((halo && block_n == 128) || (!halo && block_n == 256 && l->kind == NRRT_CONV_K3S1 && p.rows == 128)) &&
             p.H > p.bh && p.W > p.bw) ? 1 : 0;  // (a tile holds at most one frame row and one frame column)
     CUtensorMap mr = ma;
@@ -1705,8 +1752,8 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         const cuuint64_t cs = (cuuint64_t)l->res_cstride * 2;
         const cuuint64_t gstr[4] = {cs, cs * p.oW, cs * p.oW * p.oH, cs * p.oW * p.oH * p.oD};
         cuuint32_t box[5] = {64, (cuuint32_t)p.bw, (cuuint32_t)p.bh, (cuuint32_t)p.bd, 1};
-        if (halo) { box[1] = 8; box[2] = 16; box[3] = 1; }  // one column block of the 16x16 tile
-        const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        if (halo) { box[1] = 8 * ups; box[2] = 16 * ups; box[3] = 1; }  // one column block of the 16x16 tile
+        const cuuint32_t estr[5] = {1, (cuuint32_t)ups, (cuuint32_t)ups, 1, 1};
         const CUresult r = encode(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(l->res), gdim, gstr, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1715,6 +1762,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     int dev = 0, sms = 0;
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (fold) NRRT_REQUIRE(pair && tma_res && p.ts, "folded layer: residual / output layout not eligible for the TMA-staged epilogue");
     if (halo && pair) {
         if (block_n == 128 && p.ts) {
             if (tma_res && p.pm) return launch_halo2<128, 3, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);

@@ -276,6 +276,73 @@ def test_polynomial_term_through_the_tensor_core(cout, sp, cuda_device):
     assert (outs[0] - outs[1]).abs().max().item() <= tol
 
 
+@pytest.mark.parametrize("cin,cout,sp", [(128, 128, (32, 48)), (64, 128, (16, 16)), (256, 256, (40, 24)), (128, 256, (17, 33))])
+def test_folded_upconv_conv_layer(cin, cout, sp, cuda_device):
+    """NRRT_CONV_UPFOLD: ConvTranspose2d(k=2, s=2) + bias composed with the 3x3 conv that consumes it (train.py:196-201), with
+    the indexed per-map residual, the per-parity polynomial (nrrt_poly_fold) and the ReLU, against the two torch layers.
+    (16, 16): the polynomial stays in the epilogue; ragged grids: partial tiles; cout 256: two N halves."""
+    import ctypes as C
+    dev = cuda_device
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(cin + cout + sp[0])
+    B, cup = 3, 64
+    H, W = sp
+    x = torch.randn((B, cin) + sp, generator=g).to(dev)
+    wt = (torch.randn((cin, cup, 2, 2), generator=g) / np.sqrt(cin)).to(dev)
+    bu = torch.randn(cup, generator=g).to(dev)
+    wc = (torch.randn((cout, cup, 3, 3), generator=g) / 24).to(dev)
+    shift = torch.randn(cout, generator=g).to(dev).contiguous()
+    res = torch.randn((2, cout, 2 * H, 2 * W), generator=g).to(dev)
+    index = torch.tensor([1, 0, 1], dtype=torch.int32, device=dev)
+    poly = (torch.randn((B, 9, 4, cout), generator=g) * torch.tensor([100.0, 60.0, 60.0, 30.0]).view(1, 1, 4, 1)).to(dev).contiguous()
+    wf, bc = cnn._fold_weights(wt, bu, wc, dev)
+    Ef = torch.empty((B, 4, 9, 4, cout), dtype=torch.float32, device=dev)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(lib.nrrt_poly_fold(p(poly), p(bc), B, cout, H, W, p(Ef), None))
+    layer = cnn._Layer(2, cnn.UPFOLD, cin, cout, wf, torch.ones(cout, device=dev), shift, True)
+    outs = []
+    for no_mma in (False, True):
+        layer.no_poly_mma = no_mma
+        out = torch.full((B, 1, 2 * H, 2 * W, cout), 7.0, dtype=torch.float16, device=dev)
+        layer.run(lib, None, _cl(x), 0, (1, H, W), out, 0, _cl(res), 0, poly=Ef, res_idx=index)
+        torch.cuda.synchronize()
+        outs.append(_from_cl(out, 2))
+    Ho, Wo = 2 * H, 2 * W
+    Y, X = torch.meshgrid(torch.arange(Ho, device=dev), torch.arange(Wo, device=dev), indexing="ij")
+    ty, tx = Y.float() / (Ho - 1), X.float() / (Wo - 1)
+    rc = torch.where(Y == 0, 0, torch.where(Y == Ho - 1, 2, 1))
+    cc = torch.where(X == 0, 0, torch.where(X == Wo - 1, 2, 1))
+    e = poly[:, (rc * 3 + cc).long()]
+    pv = e[..., 0, :] + ty[..., None] * e[..., 1, :] + tx[..., None] * e[..., 2, :] + (ty * tx)[..., None] * e[..., 3, :]
+    up = F.conv_transpose2d(x.half().float(), wt, bu, stride=2)
+    ref = F.relu(F.conv2d(up, wc, shift, padding=1) + res[index.long()].half().float() + pv.permute(0, 3, 1, 2))
+    tol = 3e-3 * max(ref.abs().max().item(), 1.0) + 2e-3
+    for out in outs:
+        assert (out - ref).abs().max().item() <= tol, (out - ref).abs().max().item()
+
+
+def test_folded_decoder_equals_separate_layers(cuda_device):
+    """The 2D forward with upconv7/conv7.0 and upconv8/conv8.0 folded agrees with the same forward through the separate
+    ConvTranspose and conv layers (and both with the fp32 oracle within the 1e-2 tolerance of the north star)."""
+    from mgr_sampling_cnn_b200 import train, workload
+    wl = workload.make_2d(3, size=128)
+    torch.manual_seed(0)
+    model = train.UNet_cooler().eval().to(cuda_device)
+    x = torch.from_numpy((wl.occ_maps[wl.task_to_map] != 0).astype(np.float32))[:, None].repeat(1, 3, 1, 1).to(cuda_device)
+    coords = torch.from_numpy(wl.coords).to(cuda_device)
+    a = model(x, coords).clone()
+    try:
+        cnn.UNetPlan.fold = False
+        b = model(x, coords).clone()
+    finally:
+        cnn.UNetPlan.fold = True
+    with torch.no_grad():
+        ref = cnn_oracle.forward({k: v.float() for k, v in model.state_dict().items()}, x, coords, 2)
+    torch.cuda.synchronize()
+    assert (a - ref).abs().max().item() <= 1e-2 and (b - ref).abs().max().item() <= 1e-2
+    assert (a - b).abs().max().item() <= 5e-3
+
+
 def test_3d_slab_kernel_residual_and_head(cuda_device):
     """3D 3x3x3 layers on the slab kernel: indexed residual (TMA-staged) and the fused 1x1x1 head."""
     dev = cuda_device
