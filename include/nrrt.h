@@ -143,8 +143,10 @@ typedef enum NrrtConvKind {
     NRRT_CONV_UPFOLD = 5 /* (2D) nn.ConvTranspose2d(k=2, s=2) composed with the 3x3 conv that consumes it (train.py:196-201:
                             upconv7 -> conv7[0], upconv8 -> conv8[0]; nothing non-linear in between).  in = the ConvTranspose's
                             input on its (in_h, in_w) grid, cin = its input channels; out / res / poly live on the
-                            (2 in_h, 2 in_w) grid; weight = fp16 [cout][4 output parities (row, col)][2x2 taps][cin], the
-                            composite weights; poly = nrrt_poly_fold output [n][4][9][4][cout]; res is required. */
+                            (2 in_h, 2 in_w) grid; weight = fp16 [cout][16 * cin + 128]: [4 output parities (row, col)][2x2 taps][cin]
+                            composite weights, then 128 identity columns (row r has its 1 in column r % 128) through which the
+                            tensor core accumulates the residual; poly = nrrt_poly_fold output [n][4][9][4][cout]; res is
+                            required. */
 } NrrtConvKind;
 
 /* One fused layer: out = [relu2(post_scale * ] relu( scale * conv(in) + shift + residual ) [ + post_shift)].
@@ -195,6 +197,11 @@ typedef struct NrrtConvLayer {
     int32_t no_poly_mma;     /* testing: evaluate the whole polynomial term in the epilogue (default: the interior polynomial
                                 of residual-carrying 3x3 layers is one extra tensor-core MMA per tile) */
     int32_t no_tma_store;    /* testing: direct global stores from the epilogue threads instead of staged TMA stores */
+    int32_t res_mma;         /* NRRT_CONV_UPFOLD only: accumulate the residual tile with the tensor core (identity columns of the
+                                weight) instead of staging it for the epilogue; same results */
+    int32_t res_group;       /* scheduling hint (pair slab kernel): consecutive samples per group that share residual rows
+                                (res_index: the tasks of one map); tiles run tile-major inside a group so that the shared
+                                residual is read from DRAM once per group.  0 / 1 = sample-major.  Results do not depend on it. */
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);

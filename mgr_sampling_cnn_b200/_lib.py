@@ -35,7 +35,8 @@ class NrrtConvLayer(C.Structure):
                 ("logits", C.c_void_p), ("force_per_tap", C.c_int32), ("in2", C.c_void_p), ("in2_cstride", C.c_int64),
                 ("cin2", C.c_int32), ("in_n", C.c_int32), ("in2_n", C.c_int32), ("in_index", C.c_void_p), ("in2_index", C.c_void_p),
                 ("res_index", C.c_void_p), ("res_n", C.c_int32),
-                ("no_poly_mma", C.c_int32), ("no_tma_store", C.c_int32)]
+                ("no_poly_mma", C.c_int32), ("no_tma_store", C.c_int32),
+                ("res_mma", C.c_int32), ("res_group", C.c_int32)]
 
 
 _SIGNATURES = {

@@ -107,7 +107,7 @@ def _fold_weights(wt, bu, wc, device):
     (weight wc [cout, c_up, 3, 3]) -- train.py:196-201, nothing non-linear in between.  Output pixel (2i+a, 2j+b) of the conv
     reads the upsampled pixels (2i+a+dy, 2j+b+dx), i.e. sub-position ((a+dy)%2, (b+dx)%2) of low-resolution pixel
     (i + (a+dy)//2, j + (b+dx)//2): per output parity (a, b) a 2x2-tap conv over the low-resolution input.
-    Returns (fp16 [cout, 16 * cin_low] = [cout][parity a*2+b][tap][cin_low], tap = (row offset - (a-1)) * 2 + (column
+    Returns (fp16 [cout, 16 * cin_low + 128] = [cout][parity a*2+b][tap][cin_low] + identity columns, tap = (row offset - (a-1)) * 2 + (column
     offset - (b-1)), composed in fp64;  fp32 [9 border cases][cout] = the ConvTranspose bias seen through the conv taps
     that fall inside the image, which nrrt_poly_fold adds to the epilogue polynomial)."""
     wt = wt.detach().to(device).double()
@@ -123,7 +123,11 @@ def _fold_weights(wt, bu, wc, device):
     valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}
     bu = bu.detach().to(device).double()
     bc = torch.stack([wc[:, :, valid[r]][:, :, :, valid[c]].sum(dim=(2, 3)) @ bu for r in range(3) for c in range(3)])
-    return w.reshape(cout, 16 * cin).to(torch.float16).contiguous(), bc.float().contiguous()
+    # + 128 identity columns per N half of 128 output channels: the residual tile is accumulated by the tensor core
+    # (conv_halo2_kernel, p.res_mma)
+    eye = (torch.arange(cout, device=device)[:, None] % 128 == torch.arange(128, device=device)[None, :]).to(torch.float16)
+    wf = torch.cat([w.reshape(cout, 16 * cin).to(torch.float16), eye], dim=1)
+    return wf.contiguous(), bc.float().contiguous()
 
 
 class _Layer(object):
@@ -151,16 +155,18 @@ class _Layer(object):
     force_per_tap = False  # tests: run the generic per-tap kernel where the slab kernel would be chosen
     no_poly_mma = False    # tests: evaluate the whole polynomial term in the epilogue
     no_tma_store = False   # tests: direct global stores instead of the staged TMA-store epilogue
+    res_mma = False        # folded layers: residual accumulated by the tensor core instead of staged for the epilogue
 
     def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None, head=None, x2=None,
-            idx=None, idx2=None, n=None, res_idx=None):
+            idx=None, idx2=None, n=None, res_idx=None, res_group=0):
         """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W).
         head = (weight fp32 [cout], bias float, logits fp32 tensor): fuse the 1x1 output head, `out` may be None.
         x2: optional second input buffer (K split: channels [x: self.cin | x2: self.cin2]); idx / idx2: optional int32
         [n] sample indirection of x / x2 (encoder outputs shared per map); n = number of output samples;
-        res_idx: optional int32 [n] sample indirection of the residual (per-map partial sums)."""
+        res_idx: optional int32 [n] sample indirection of the residual (per-map partial sums); res_group: scheduling hint,
+        consecutive samples that share a residual row (include/nrrt.h)."""
         n = n if n is not None else (idx.shape[0] if idx is not None else x.shape[0])
-        args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx)
+        args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx, res_group)
         prof = self.profiler
         if prof is not None and prof.active:
             with prof.launch(self.flops(n, grid), getattr(self, "name", None)):
@@ -168,7 +174,8 @@ class _Layer(object):
         else:
             self._run(*args)
 
-    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx=None):
+    def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx=None,
+             res_group=0):
         _lib.count_launch()
         L = _lib.NrrtConvLayer()
         L.dims, L.kind = self.dims, self.kind
@@ -194,11 +201,13 @@ class _Layer(object):
         L.force_per_tap = 1 if self.force_per_tap else 0
         L.no_poly_mma = 1 if self.no_poly_mma else 0
         L.no_tma_store = 1 if self.no_tma_store else 0
+        L.res_mma = 1 if self.res_mma else 0
         if res is not None:
             L.res, L.res_cstride, L.res_coffset = _ptr(res), res.shape[-1], res_coff
             L.res_n = res.shape[0]
             if res_idx is not None:
                 L.res_index = _ptr(res_idx)
+                L.res_group = int(res_group)
         L.relu = 1 if self.relu else 0
         if self.post is not None:
             L.post_scale, L.post_shift = _ptr(self.post[0]), _ptr(self.post[1])
@@ -642,9 +651,9 @@ class UNetPlan(object):
         enc = self.encode(grid, Be, x=x, occ=occ, maps=t2m)
         return self.decode(enc, B, grid, coords, prep, enc_index, logits_out)
 
-    def decode(self, enc, B, grid, coords, prep=None, enc_index=None, logits_out=None):
+    def decode(self, enc, B, grid, coords, prep=None, enc_index=None, logits_out=None, res_group=0):
         """Coordinate branch + decoder (train.py:179-203) for B tasks whose encoder outputs are rows enc_index[b]
-        (None: row b) of the buffer set returned by encode()."""
+        (None: row b) of the buffer set returned by encode().  res_group: consecutive tasks per map (scheduling hint)."""
         lib, dims = self.lib, self.dims
         st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         coords = coords.contiguous().float()
@@ -669,29 +678,30 @@ class UNetPlan(object):
         # decoder: every torch.cat of the reference is a K split over (task buffer, encoder output of the task's map)
         ei = enc_index  # None = one encoder sample per task
         ri = ei  # None = one encoder sample per task (the residual of sample b is row b)
+        rg = res_group
         if self.poly:
             _lib.count_launch()
             check(lib.nrrt_poly_relu(_ptr(bf["r6"]), _ptr(ri), _ptr(prep["p16"]), _ptr(bf["g6"]), B, g[2][1], g[2][2],
                                      bf["g6"].shape[-1], st))
         else:
             self.up6.run(lib, st, bf["e5"], 0, g[3], bf["t6"], 0, x2=bf["c5"], idx=ei, n=B)
-            self.c6[0].run(lib, st, bf["t6"], 0, g[2], bf["g6"], 0, bf["r6"], 0, res_idx=ri)
+            self.c6[0].run(lib, st, bf["t6"], 0, g[2], bf["g6"], 0, bf["r6"], 0, res_idx=ri, res_group=rg)
             post3d(bf["g6"], prep["e_c6"], 2)
         self.c6[1].run(lib, st, bf["g6"], 0, g[2], bf["h"], 0)
         folded = self.poly and prep["e_c7"].dim() == 5  # coords_prepare decided (use_fold)
         if folded:
-            self.c7f.run(lib, st, bf["h"], 0, g[2], bf["g7"], 0, bf["r7"], 0, poly=prep["e_c7"], res_idx=ri)
+            self.c7f.run(lib, st, bf["h"], 0, g[2], bf["g7"], 0, bf["r7"], 0, poly=prep["e_c7"], res_idx=ri, res_group=rg)
         else:
             self.up7.run(lib, st, bf["h"], 0, g[2], bf["t7"], 0)
-            self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, bf["r7"], 0, poly=prep.get("e_c7") if self.poly else None, res_idx=ri)
+            self.c7[0].run(lib, st, bf["t7"], 0, g[1], bf["g7"], 0, bf["r7"], 0, poly=prep.get("e_c7") if self.poly else None, res_idx=ri, res_group=rg)
         if not self.poly:
             post3d(bf["g7"], prep["e_c7"], 1)
         self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
         if folded:
-            self.c8f.run(lib, st, bf["i"], 0, g[1], bf["j"], 0, bf["r8"], 0, poly=prep["e_c8"], res_idx=ri)
+            self.c8f.run(lib, st, bf["i"], 0, g[1], bf["j"], 0, bf["r8"], 0, poly=prep["e_c8"], res_idx=ri, res_group=rg)
         else:
             self.up8.run(lib, st, bf["i"], 0, g[1], bf["t8"], 0)
-            self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8") if self.poly else None, res_idx=ri)
+            self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8") if self.poly else None, res_idx=ri, res_group=rg)
         if not self.poly:
             post3d(bf["j"], prep["e_c8"], 0)
 

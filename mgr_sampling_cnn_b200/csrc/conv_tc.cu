@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "nrrt_common.cuh"
 
@@ -62,6 +63,10 @@ struct ConvParams {
     float inv_h, inv_w;  // 1/(H-1), 1/(W-1) of the tile-space grid
     int outer;           // slab kernels: slab loads per input-channel chunk: 3 (dx) in 2D, 9 (dz, dx) in 3D, 2 when folded
     int inner;           // slab kernels: vertical taps served by one slab: 3, or 2 when folded
+    int dbg;             // experiments only (NRRT_CONV_DBG): 1 = no TMA stores, 2 = no epilogue arithmetic
+    int res_k0;          // first K column of the identity block behind the weights (res_mma)
+    int res_mma;         // pair slab kernel: the residual tile enters the accumulator through the tensor core (see below)
+    int group;           // pair slab kernel: samples per scheduling group (tile-major inside a group), see halo_tile
     int fold;            // pair slab kernel: ConvTranspose(k=2,s=2) folded into the 3x3 conv that follows it (see conv_halo2_kernel)
     int ts;              // pair kernels: output tile staged in shared memory and written with TMA stores (see below)
     int pm;              // pair kernels: interior polynomial applied by one extra tcgen05.mma per tile (see pm_* below)
@@ -99,6 +104,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
             "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
+}
+// L2 prefetch of a tile that a later cp.async.bulk.tensor load will fetch (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
@@ -179,23 +190,45 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, int m = kBlockM) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+// fp32 pair -> packed fp16x2 (lo in the low half) with the clamp to the finite fp16 range, and optionally the ReLU, inside
+// the conversion instruction (F2FP.SATFINITE[.RELU]): relu + clamp + pack was 5 instructions per pair of outputs
+__device__ __forceinline__ uint32_t pack_h2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_h2_relu_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // Epilogue of 32 accumulator columns of one output pixel: folded-BN scale/shift, polynomial coordinate term, residual,
 // ReLU, optional second affine + ReLU, then either the fp16 store into the output channel slice or (fused 1x1 head) a
 // running dot product with the head weights.  col = first GEMM column, lc = its offset inside the staged scale/shift.
-// res_row (pair kernels): this pixel's 128-byte row of the TMA-staged residual piece holding columns [lc & ~63, +64)
-// (SWIZZLE_128B: 16-byte piece j of row r sits at j ^ (r & 7)); nullptr = read the residual from global memory.
+// RES_ST (pair kernels, compile time): res_row = this pixel's 128-byte row of the TMA-staged residual piece holding columns
+// [lc & ~63, +64) (SWIZZLE_128B: 16-byte piece j of row r sits at j ^ (r & 7)); else the residual comes from global memory.
+// OUT_ST: the fp16 results go to stg_row (same layout) for the TMA store; else to global memory.
+// The epilogue warps share the SM's issue slots with nothing else that matters, and at full resolution a tile's epilogue
+// (256 pixels x N columns) was ~430 instructions per 32 columns -- longer than the tile's MMAs for K <= 576 (ncu:
+// profiles/conv_fold_r1.md).  Everything the staged paths do not need (pixel offsets, the weight-group division, global
+// pointers) is compiled out of them, and ReLU / clamp ride on the conversion.
+template <bool RES_ST, bool OUT_ST>
 __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[32], int col, int lc, int n, int d,
                                                int h, int w, const float* sc, const float* sh, const float* sc2,
                                                const float* sh2, const float* pe, int pe_stride, float& head_acc,
                                                const uint8_t* res_row = nullptr, int res_r7 = 0, bool pm = false,
                                                int frame = 0, uint8_t* stg_row = nullptr) {
-    const int g = col / p.cout, co = col - g * p.cout;
-    int od = d, oh = h, ow = w;
-    if (p.up == 2) {
-        if (p.up_d == 2) { od = 2 * d + (g >> 2); oh = 2 * h + ((g >> 1) & 1); ow = 2 * w + (g & 1); }
-        else { oh = 2 * h + (g >> 1); ow = 2 * w + (g & 1); }
-    }
-    const long long pix = (((long long)n * p.oD + od) * p.oH + oh) * p.oW + ow;
+    int g = 0, co = col;
+    if (p.up == 2) { g = col / p.cout; co = col - g * p.cout; }
+    auto out_pixel = [&](int ns) -> long long {  // pixel index in the output grid (ConvTranspose: pixel shuffle by group)
+        int od = d, oh = h, ow = w;
+        if (p.up == 2) {
+            if (p.up_d == 2) { od = 2 * d + (g >> 2); oh = 2 * h + ((g >> 1) & 1); ow = 2 * w + (g & 1); }
+            else { oh = 2 * h + (g >> 1); ow = 2 * w + (g & 1); }
+        }
+        return (((long long)ns * p.oD + od) * p.oH + oh) * p.oW + ow;
+    };
     float f[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), sc[lc + i], sh[lc + i]);
@@ -203,10 +236,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
         int kcase = g;
         if (p.poly_cases == 9)
             kcase = (h == 0 ? 0 : (h == p.H - 1 ? 2 : 1)) * 3 + (w == 0 ? 0 : (w == p.W - 1 ? 2 : 1));
-        const float ty = (float)h * p.inv_h, tx = (float)w * p.inv_w, tyx = ty * tx;
         if (!pm) {
             // interior pixels (and ConvTranspose groups) read the tile's coefficients staged in shared memory; only the
             // one-pixel image frame, whose tap set differs, goes to global memory
+            const float ty = (float)h * p.inv_h, tx = (float)w * p.inv_w, tyx = ty * tx;
             const bool staged = p.poly_cases != 9 || kcase == 4;
             const float4* e0 = staged ? reinterpret_cast<const float4*>(pe + lc)
                                       : reinterpret_cast<const float4*>(p.poly + (((size_t)n * p.poly_cases + kcase) * 4) * p.cout + co);
@@ -228,7 +261,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
             // frame A_c + ty*B_c, corner C
             const float* fr = sc2 + lc;  // == tile buffer + 2 * BLOCK_N + lc
             const float* a = frame == 1 ? fr : (frame == 2 ? fr + 2 * pe_stride : fr + 4 * pe_stride);
-            const float t = frame == 1 ? tx : (frame == 2 ? ty : 0.f);
+            const float t = frame == 1 ? (float)w * p.inv_w : (frame == 2 ? (float)h * p.inv_h : 0.f);
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float4 a0 = *reinterpret_cast<const float4*>(a + q * 4);
@@ -240,13 +273,14 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
             }
         }
     }
-    if (p.res) {
-        const long long rpix = (res_row || !p.res_idx) ? pix : (((long long)__ldg(p.res_idx + n) * p.oD + od) * p.oH + oh) * p.oW + ow;
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + rpix * p.res_cstride + p.res_coffset + co);
-        const int j0 = (lc & 63) >> 3;
+    const int j0 = (lc & 63) >> 3;  // first 16-byte piece of these 32 columns inside a staged 128-byte row
+    if (RES_ST || p.res) {
+        const uint4* rp = nullptr;
+        if (!RES_ST) rp = reinterpret_cast<const uint4*>(p.res + out_pixel(p.res_idx ? __ldg(p.res_idx + n) : n) * p.res_cstride +
+                                                         p.res_coffset + co);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const uint4 rv = res_row ? *reinterpret_cast<const uint4*>(res_row + (((j0 + q) ^ res_r7) << 4)) : __ldg(rp + q);
+            const uint4 rv = RES_ST ? *reinterpret_cast<const uint4*>(res_row + (((j0 + q) ^ res_r7) << 4)) : __ldg(rp + q);
             const __half2* hv = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -256,33 +290,42 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
             }
         }
     }
+    if (p.logits || p.scale2) {  // the ReLU as arithmetic only where a float consumer follows; else it rides on the conversion
+        if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
+        }
+        if (p.scale2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(f[i], sc2[lc + i], sh2[lc + i]), 0.0f);
+        }
+        if (p.logits) {  // fused final_conv: the 64-channel activation never goes to memory
+#pragma unroll
+            for (int i = 0; i < 32; ++i) head_acc = fmaf(f[i], __ldg(p.head_w + co + i), head_acc);
+            return;
+        }
+    }
+    uint4 ov[4];
     if (p.relu) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-    }
-    if (p.scale2) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = fmaxf(fmaf(f[i], sc2[lc + i], sh2[lc + i]), 0.0f);
-    }
-    if (p.logits) {  // fused final_conv: the 64-channel activation never goes to memory
-#pragma unroll
-        for (int i = 0; i < 32; ++i) head_acc = fmaf(f[i], __ldg(p.head_w + co + i), head_acc);
-        return;
-    }
-    uint4* op = reinterpret_cast<uint4*>(p.out + pix * p.out_cstride + p.out_coffset + co);
-    const int sj0 = (lc & 63) >> 3;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        uint4 ov;
-        __half2* hv = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float a = fminf(fmaxf(f[q * 8 + e * 2], -65504.f), 65504.f);
-            const float b = fminf(fmaxf(f[q * 8 + e * 2 + 1], -65504.f), 65504.f);
-            hv[e] = __floats2half2_rn(a, b);
+        for (int q = 0; q < 4; ++q) {
+            ov[q].x = pack_h2_relu_sat(f[q * 8 + 0], f[q * 8 + 1]); ov[q].y = pack_h2_relu_sat(f[q * 8 + 2], f[q * 8 + 3]);
+            ov[q].z = pack_h2_relu_sat(f[q * 8 + 4], f[q * 8 + 5]); ov[q].w = pack_h2_relu_sat(f[q * 8 + 6], f[q * 8 + 7]);
         }
-        if (stg_row) *reinterpret_cast<uint4*>(stg_row + (((sj0 + q) ^ res_r7) << 4)) = ov;  // staged for the TMA store
-        else op[q] = ov;
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            ov[q].x = pack_h2_sat(f[q * 8 + 0], f[q * 8 + 1]); ov[q].y = pack_h2_sat(f[q * 8 + 2], f[q * 8 + 3]);
+            ov[q].z = pack_h2_sat(f[q * 8 + 4], f[q * 8 + 5]); ov[q].w = pack_h2_sat(f[q * 8 + 6], f[q * 8 + 7]);
+        }
+    }
+    if (OUT_ST) {  // staged for the TMA store
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(stg_row + (((j0 + q) ^ res_r7) << 4)) = ov[q];
+    } else {
+        uint4* op = reinterpret_cast<uint4*>(p.out + out_pixel(n) * p.out_cstride + p.out_coffset + co);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) op[q] = ov[q];
     }
 }
 
@@ -490,7 +533,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                     uint32_t v[32];
                     tc_ld32(taddr + (uint32_t)(c * 32), v);
                     if (valid)
-                        epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
+                        epilogue_chunk<false, false>(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
                                        sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc);
                 }
                 if (valid && p.logits) p.logits[(((long long)n * p.oD + d) * p.oH + h) * p.oW + w] = head_acc + p.head_b;
@@ -879,7 +922,7 @@ conv_gemm2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     }
                     if (TS) srow = base_ptr + L::off_res + (c >> 1) * kResPiece + row * 128;
                     if (valid)
-                        epilogue_chunk(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
+                        epilogue_chunk<RES, TS>(p, v, n_tile * BLOCK_N + c * 32, c * 32, n, d, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N,
                                        sc + 3 * BLOCK_N, sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame, srow);
                     if (RES || TS) {
                         if (TS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1133,7 +1176,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                 uint32_t v[32];
                 tc_ld32(taddr + (uint32_t)(c * 32), v);
                 if (valid)
-                    epilogue_chunk(p, v, c * 32, c * 32, n, 0, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
+                    epilogue_chunk<false, false>(p, v, c * 32, c * 32, n, 0, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
                                    sc + 4 * BLOCK_N, BLOCK_N, head_acc);
             }
             if (valid && p.logits) p.logits[((long long)n * p.oH + h) * p.oW + w] = head_acc + p.head_b;
@@ -1152,6 +1195,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
 }
 
+
+// Tile m of the pair slab kernel -> (sample n, tile td/th/tw).  Default: sample-major.  p.group > 1: samples are scheduled in
+// groups of p.group consecutive samples, TILE-major inside a group, so that the tiles of the group's samples at one image
+// position run at the same time: the decoder's per-map residual (res_index: the tasks of a map are consecutive samples)
+// is then fetched from DRAM once per group instead of once per sample (conv8.0: 670 of 1470 MB per 10 tasks in ncu).
+__device__ __forceinline__ void halo_tile(const ConvParams& p, int m, int& n, int& td, int& th, int& tw) {
+    const int T = p.tiles_w * p.tiles_h * p.tiles_d;
+    int t;
+    if (p.group > 1) {
+        const int gt = p.group * T;
+        const int g = m / gt, r = m - g * gt;
+        const int left = p.N - g * p.group;
+        const int gs = left < p.group ? (left > 0 ? left : 1) : p.group;  // the last group may be smaller
+        t = r / gs;
+        n = g * p.group + (r - t * gs);
+    } else {
+        n = m / T;
+        t = m - n * T;
+    }
+    tw = t % p.tiles_w; t /= p.tiles_w;
+    th = t % p.tiles_h;
+    td = t / p.tiles_h;
+}
 
 template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM, bool TS>
 struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
@@ -1172,6 +1238,14 @@ struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
 // RES: TMA-staged residual tile as in conv_gemm2_kernel; a piece = (column block, 64-channel chunk) = 128 pixels x 128 B.
 // PM: the interior polynomial coordinate term is one extra MMA per accumulator (pm_* above).
 // TS: TMA-store epilogue (pieces shared with the residual staging; the auxiliary warp issues the stores).
+// p.res_mma (= BLOCK_N / 64 extra K chunks; host sets p.res = nullptr and RES = false): the residual tile is not staged for
+// the epilogue but ACCUMULATED BY THE TENSOR CORE: its two 128-pixel x 64-channel pieces per chunk are loaded into an A
+// stage like slabs (same [pixel row][8 pixels][128 B] layout, vertical tap 0) and multiplied by an identity block appended
+// to the weights (fp16 x 1.0 into the fp32 accumulator: exact).  With the staged variant the residual of tile i+1 could
+// only be requested once the TMA store of tile i had drained the shared piece, so consecutive epilogues were serialised
+// with a store and an L2/DRAM round trip between them (ncu, conv8.0: tensor pipe 42 %, issuer waiting on the accumulator,
+// epilogue waiting on the residual).  Through the A ring the residual is prefetched like any operand; K grows by 64 per
+// 64 output channels.
 // p.fold: ConvTranspose(k=2, s=2) folded into the 3x3 conv that consumes it (train.py:196-201: upconv7 -> conv7.0,
 // upconv8 -> conv8.0; no nonlinearity in between, so the composition is linear).  Output pixel (2i + a, 2j + b) of the conv
 // sees the upsampled pixels (2i + a + dy, 2j + b + dx), which come from the 2 x 2 low-resolution pixels (i + a - 1 .. i + a,
@@ -1251,15 +1325,20 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 int q, nh, par;
                 decode(pt, q, nh, par);
                 const int fa = par >> 1, fb = par & 1;  // output parity (row, column) of a folded layer
-                int m = q * 2 + (int)rank;
+                const int m = q * 2 + (int)rank;
                 const bool live = m < p.m_tiles;
-                const int tw = m % p.tiles_w; m /= p.tiles_w;
-                const int th = m % p.tiles_h; m /= p.tiles_h;
-                const int td = m % p.tiles_d;  // 3D: one depth slice per tile (tiles_d = D)
-                const int n = m / p.tiles_d;
+                int n = 0, td = 0, th = 0, tw = 0;  // 3D: one depth slice per tile (tiles_d = D)
+                if (live) halo_tile(p, m, n, td, th, tw);
                 const int w0 = tw * 16, h0 = th * 16;
                 const int n1 = !live ? 0x3fffffff : (p.idx1 ? __ldg(p.idx1 + n) : n);
                 const int n2 = !live ? 0x3fffffff : (p.idx2 ? __ldg(p.idx2 + n) : n);
+                const int nr = ((!RES && !p.res_mma) || !live) ? 0x3fffffff : (p.res_idx ? __ldg(p.res_idx + n) : n);
+                if ((RES || p.res_mma) && live)  // the residual pieces are loaded behind this tile's operands: start their trip to L2 now
+                    for (int s = 0; s < 2 * RC; ++s) {
+                        const int rw = w0 + (s / RC) * 8;
+                        tma_prefetch_5d(&map_r, (int)p.res_coffset + nh * BLOCK_N + (s % RC) * 64, p.fold ? 2 * rw + fb : rw,
+                                        p.fold ? 2 * h0 + fa : h0, td, nr);
+                    }
                 for (int c = 0; c < p.cin_chunks; ++c) {
                     const CUtensorMap* am = c < p.split_chunk ? &map_a : &map_a2;
                     const int cc = (c < p.split_chunk ? c : c - p.split_chunk) * kBlockK;
@@ -1285,8 +1364,23 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         }
                     }
                 }
+                for (int kc = 0; kc < p.res_mma; ++kc) {  // residual chunk kc as one more A stage + its identity B tile
+                    mbar_wait(aempty(sa), pa ^ 1u);
+                    if (rank == 0) mbar_expect_tx(afull(sa), 4 * kResPiece);  // two pieces from each CTA of the pair
+                    const uint32_t dst = base + sa * L::a_stage;
+                    const uint32_t abar = afull(sa) & kPeerBitMask;
+                    const int rc0 = (int)p.res_coffset + nh * BLOCK_N + kc * 64;
+                    const int rx = p.fold ? 2 * w0 + fb : w0, ry = p.fold ? 2 * h0 + fa : h0, rstep = p.fold ? 16 : 8;
+                    tma2_load_5d(dst, &map_r, abar, rc0, rx, ry, td, nr);
+                    tma2_load_5d(dst + kSlabBytes, &map_r, abar, rc0, rx + rstep, ry, td, nr);
+                    if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+                    mbar_wait(bempty(sb), pb ^ 1u);
+                    if (rank == 0) mbar_expect_tx(bfull(sb), 2 * L::b_stage);
+                    tma2_load_2d(base + L::off_b + sb * L::b_stage, &map_b, bfull(sb) & kPeerBitMask,
+                                 p.res_k0 + kc * kBlockK, nh * BLOCK_N + (int)rank * (BLOCK_N / 2));
+                    if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
+                }
                 if (RES) {
-                    const int nr = !live ? 0x3fffffff : (p.res_idx ? __ldg(p.res_idx + n) : n);
                     for (int s = 0; s < 2 * RC; ++s) {
                         mbar_wait(rempty_bar(s), rphase ^ 1u);
                         mbar_expect_tx(rfull_bar(s), kResPiece);
@@ -1344,6 +1438,24 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
                     }
                 }
+                for (int kc = 0; kc < p.res_mma; ++kc) {  // + residual chunk x identity
+                    mbar_wait(afull(sa), pa);
+                    mbar_wait(bfull(sb), pb);
+                    tc_fence_after();
+                    const uint64_t bdesc = make_smem_desc(base + L::off_b + sb * L::b_stage);
+                    const uint64_t adesc = make_smem_desc(base + sa * L::a_stage + blk * kSlabBytes);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int kk = 0; kk < kBlockK / 16; ++kk)
+                            tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (first && kk == 0) ? 0u : 1u);
+                        tc_commit2(bempty(sb));
+                        tc_commit2(aempty(sa));
+                    }
+                    __syncwarp();
+                    first = 0;
+                    if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
+                    if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
+                }
                 if (PM) {
                     mbar_wait_cluster(bxfull_bar(acc), acc_phase);  // both CTAs' coefficient tiles of this pair iteration
                     tc_fence_after();
@@ -1369,13 +1481,12 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int pt = cluster_id; pt < total_pairs; pt += n_clusters) {
             int q, nh, par;
             decode(pt, q, nh, par);
-            int m = q * 2 + (int)rank;
+            const int m = q * 2 + (int)rank;
             const bool live = m < p.m_tiles;
-            const int tw = m % p.tiles_w; m /= p.tiles_w;
-            const int th = m % p.tiles_h; m /= p.tiles_h;
-            const int td = m % p.tiles_d;
+            int n = 0, td = 0, th = 0, tw = 0;
+            if (live) halo_tile(p, m, n, td, th, tw);
             // folded layers: the polynomial is stored per (sample, parity); n only indexes it (results leave by TMA)
-            const int n = live ? (p.fold ? (m / p.tiles_d) * 4 + par : m / p.tiles_d) : 0;
+            if (p.fold) n = n * 4 + par;
             const int col0 = nh * BLOCK_N;
             float* sc = ss + acc * 8 * BLOCK_N;
             stage_tile_params<BLOCK_N>(p, sc, col0, n, et, last_nh[acc] != nh, !PM && (last_n[acc] != n || last_nh[acc] != nh));
@@ -1413,8 +1524,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (!(c & 1)) mbar_wait(rempty_bar(piece), rphase ^ 1u);  // the previous tile's store has read the piece out
                 }
                 if (TS) srow = base_ptr + L::off_res + piece * kResPiece + row * 128;
-                if (valid)
-                    epilogue_chunk(p, v, col0 + c * 32, c * 32, n, td, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
+                if (valid && !(p.dbg & 2))
+                    epilogue_chunk<RES, TS>(p, v, col0 + c * 32, c * 32, n, td, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
                                    sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame, srow);
                 if ((RES || TS) && (c & 1)) {  // both 32-column halves of the piece are done
                     if (TS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1442,11 +1553,13 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             decode(q, qq, nh, par);
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                int mj = qq * 2 + j;
+                const int mj = qq * 2 + j;
                 tlive[j] = mj < p.m_tiles;
-                tw0[j] = (mj % p.tiles_w) * 16; mj /= p.tiles_w;
-                th0[j] = (mj % p.tiles_h) * 16;
-                tn[j] = tlive[j] ? (p.fold ? (mj / p.tiles_h) * 4 + par : mj / p.tiles_h) : 0;  // (PM is 2D only: tiles_d == 1)
+                int nj = 0, tdj = 0, thj = 0, twj = 0;
+                if (tlive[j]) halo_tile(p, mj, nj, tdj, thj, twj);
+                tw0[j] = twj * 16;
+                th0[j] = thj * 16;
+                tn[j] = p.fold ? nj * 4 + par : nj;
             }
             pm_produce_b<BLOCK_N / 2>(p, base_ptr + L::off_pm + 2 * 4096 + a * L::pm_b, lane, 32, rank, tn, th0, tw0, tlive,
                                       nh * BLOCK_N);
@@ -1458,31 +1571,38 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 pm_write_basis(base_ptr + L::off_pm + (r >> 7) * 4096, r & 127, (r & 127) >> 3, (r >> 7) * 8 + (r & 7), rank);
             if (cluster_id < total_pairs) produce(cluster_id, 0);
         }
-        int it = 0;
+        int it = 0, prev_piece = -1;
         uint32_t sphase = 0;
         for (int pt = cluster_id; pt < total_pairs; pt += n_clusters, ++it) {
             if (PM && pt + n_clusters < total_pairs) produce(pt + n_clusters, it + 1);
             if (TS) {
                 int q, nh, par;
                 decode(pt, q, nh, par);
-                int m = q * 2 + (int)rank;
+                const int m = q * 2 + (int)rank;
                 const bool live = m < p.m_tiles;
-                const int tw = m % p.tiles_w; m /= p.tiles_w;
-                const int th = m % p.tiles_h; m /= p.tiles_h;
-                const int td = m % p.tiles_d;
-                const int n = m / p.tiles_d;
+                int n = 0, td = 0, th = 0, tw = 0;
+                if (live) halo_tile(p, m, n, td, th, tw);
                 for (int k = 0; k < RC; ++k)
                     for (int b = 0; b < 2; ++b) {  // order in which the epilogue finishes them
                         const int piece = b * RC + k;
                         mbar_wait(sdone_bar(piece), sphase);
                         if (lane == 0) {
-                            if (live) {
+                            if (live && !(p.dbg & 1)) {
                                 const int ow = tw * 16 + b * 8, oh = th * 16;
                                 tma_store_5d(&map_o, base + L::off_res + piece * kResPiece, (int)p.out_coffset + nh * BLOCK_N + k * 64,
                                              p.fold ? 2 * ow + (par & 1) : ow, p.fold ? 2 * oh + (par >> 1) : oh, td, n);
                             }
-                            tma_store_commit_and_wait_read();
-                            mbar_arrive(rempty_bar(piece));  // free for the next residual load / the next tile's results
+                            if (RES) {  // the next residual load of this piece waits for it: free it as early as possible
+                                tma_store_commit_and_wait_read();
+                                mbar_arrive(rempty_bar(piece));
+                            } else {    // only the next tile's results need the piece: keep one store in flight
+                                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                                if (prev_piece >= 0) {
+                                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                                    mbar_arrive(rempty_bar(prev_piece));
+                                }
+                                prev_piece = piece;
+                            }
                         }
                         __syncwarp();
                     }
@@ -1653,6 +1773,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     p.up = up; p.up_d = (up == 2 && three_d) ? 2 : 1;
     p.oW = p.W * up; p.oH = p.H * up; p.oD = p.D * p.up_d;
     p.fold = fold ? 1 : 0;
+    p.group = l->res_group > 1 ? l->res_group : 1;
     const int ups = fold ? 2 : 1;  // output grid of a folded layer = 2 x the tile-space grid (p.up stays 1: no weight groups)
     if (fold) { p.oW = 2 * p.W; p.oH = 2 * p.H; }
     p.cout = l->cout;
@@ -1714,7 +1835,8 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
         if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(activations) failed: %d (box %d,%d,%d stride %d)", (int)r, p.bw, p.bh, p.bd, stride);
     }
     {
-        const cuuint64_t ktot = (cuuint64_t)(fold ? 16 : p.ntaps) * cin_total;  // folded: [4 parities][2x2 taps][Cin]
+        // folded: [4 parities][2x2 taps][Cin], then the 128 identity columns that carry the residual (p.res_mma)
+        const cuuint64_t ktot = (cuuint64_t)(fold ? 16 : p.ntaps) * cin_total + (fold ? 128 : 0);
         const cuuint64_t gdim[2] = {ktot, (cuuint64_t)rows_total};
         const cuuint64_t gstr[1] = {ktot * 2};
         const cuuint32_t box[2] = {64, (cuuint32_t)(pair ? block_n / 2 : block_n)};  // a CTA of a pair loads half of B
@@ -1759,17 +1881,32 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled(residual) failed: %d", (int)r);
     }
+    // folded layers: the residual enters through the tensor core (conv_halo2_kernel, p.res_mma), not the epilogue
+    // experiments (scripts/conv_probe.py): NRRT_CONV_DBG bits 1 = no TMA stores, 2 = no epilogue arithmetic, 8 = no polynomial,
+    // 16 = no residual (folded layers); results are wrong with any of them set
+    static const int dbg = getenv("NRRT_CONV_DBG") ? atoi(getenv("NRRT_CONV_DBG")) : 0;
+    p.dbg = dbg;
+    if (fold && (dbg & 8)) { p.pm = 0; p.poly = nullptr; }
+    const bool no_res = fold && (dbg & 16);
+    if (no_res) p.res = nullptr;
+    // residual through the tensor core: +25 % MMA work on conv8.0 buys an epilogue that never waits for the residual; in
+    // the power-capped steady state of bench.py the two variants tie (3435 vs 3447 plans/s), so the staged one (less
+    // tensor work) is the default and this one is opt-in
+    const bool res_mma = fold && l->res_mma && !no_res;
+    const bool res_st = tma_res && !res_mma && !no_res;
+    if (res_mma) { p.res_mma = block_n / 64; p.res_k0 = 16 * cin_total; p.res = nullptr; }
     int dev = 0, sms = 0;
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (fold) NRRT_REQUIRE(pair && tma_res && p.ts, "folded layer: residual / output layout not eligible for the TMA-staged epilogue");
     if (halo && pair) {
         if (block_n == 128 && p.ts) {
-            if (tma_res && p.pm) return launch_halo2<128, 3, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
-            if (tma_res) return launch_halo2<128, 3, 5, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (res_st && p.pm) return launch_halo2<128, 3, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (p.pm) return launch_halo2<128, 3, 4, false, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (res_st) return launch_halo2<128, 3, 5, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
             return launch_halo2<128, 3, 5, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
         }
-        if (tma_res) {
+        if (res_st) {
             if (block_n == 128) return launch_halo2<128, 3, 5, true>(ma, ma2, mb, mr, mo, p, sms, st);
             return launch_halo2<64, 4, 8, true>(ma, ma2, mb, mr, mo, p, sms, st);
         }
@@ -1783,14 +1920,14 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     if (pair) {
         if (p.ts) {
             if (block_n == 256) {
-                if (tma_res && p.pm) return launch_conv2<256, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
-                if (tma_res) return launch_conv2<256, 4, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+                if (res_st && p.pm) return launch_conv2<256, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
+                if (res_st) return launch_conv2<256, 4, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
                 return launch_conv2<256, 4, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
             }
-            if (tma_res) return launch_conv2<128, 6, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (res_st) return launch_conv2<128, 6, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
             return launch_conv2<128, 6, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
         }
-        if (tma_res) {
+        if (res_st) {
             if (block_n == 256) return launch_conv2<256, 4, true>(ma, ma2, mb, mr, mo, p, sms, st);
             return launch_conv2<128, 6, true>(ma, ma2, mb, mr, mo, p, sms, st);
         }

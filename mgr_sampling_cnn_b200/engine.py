@@ -308,7 +308,10 @@ class GuidedPlanner(object):
                 if plan.profiler is not None:
                     plan.profiler.active = self.profile_every > 0 and mbi % self.profile_every == 0
                 mbi += 1
-                plan.decode(enc, j - i, grid, coords[i:j], plan.slice_prep(prep, i, j), rel_d[i:j], out[i:j])
+                # scheduling hint: tasks per map when every map of the micro-batch has the same number of tasks
+                runs = np.diff(np.flatnonzero(np.diff(rel[i:j], prepend=-1, append=-1)))
+                rg = int(runs[0]) if len(runs) and np.all(runs == runs[0]) else 0
+                plan.decode(enc, j - i, grid, coords[i:j], plan.slice_prep(prep, i, j), rel_d[i:j], out[i:j], res_group=rg)
         return out
 
     def plan(self, occ_maps, task_to_map, starts, goals, coords, seed: int = 0, task_ids=None, record_events=False):

@@ -301,12 +301,14 @@ def test_folded_upconv_conv_layer(cin, cout, sp, cuda_device):
     _lib.check(lib.nrrt_poly_fold(p(poly), p(bc), B, cout, H, W, p(Ef), None))
     layer = cnn._Layer(2, cnn.UPFOLD, cin, cout, wf, torch.ones(cout, device=dev), shift, True)
     outs = []
-    for no_mma in (False, True):
-        layer.no_poly_mma = no_mma
+    # group 2 of 3 samples: tile-major schedule, ragged last group; res_mma: residual accumulated by the tensor core
+    for no_mma, group, res_mma in ((False, 0, False), (True, 0, False), (False, 2, False), (False, 0, True), (True, 2, True)):
+        layer.no_poly_mma, layer.res_mma = no_mma, res_mma
         out = torch.full((B, 1, 2 * H, 2 * W, cout), 7.0, dtype=torch.float16, device=dev)
-        layer.run(lib, None, _cl(x), 0, (1, H, W), out, 0, _cl(res), 0, poly=Ef, res_idx=index)
+        layer.run(lib, None, _cl(x), 0, (1, H, W), out, 0, _cl(res), 0, poly=Ef, res_idx=index, res_group=group)
         torch.cuda.synchronize()
         outs.append(_from_cl(out, 2))
+    assert torch.equal(outs[0], outs[2])  # the schedule does not change results
     Ho, Wo = 2 * H, 2 * W
     Y, X = torch.meshgrid(torch.arange(Ho, device=dev), torch.arange(Wo, device=dev), indexing="ij")
     ty, tx = Y.float() / (Ho - 1), X.float() / (Wo - 1)
