@@ -451,7 +451,8 @@ __global__ void __launch_bounds__(256) poly_relu_kernel(const __half* __restrict
     };
     float Ai[8], Bi[8];
     load_class(1 + (lane & 1), Ai, Bi);
-    for (int X = lane; X < W; X += lanes) {
+#pragma unroll 4
+    for (int X = lane; X < W; X += lanes) {  // (unrolled: four 16-byte loads in flight per thread; the kernel is a copy stream)
         float Ae[8], Be[8];
         const bool edge = X == 0 || X == W - 1;
         if (edge) load_class(X == 0 ? 0 : 3, Ae, Be);
@@ -623,6 +624,76 @@ __global__ void poly_fold_kernel(const float* __restrict__ E, const float* __res
     }
 }
 
+// ---- stem_lut_kernel: the first conv fed from a binary 2D occupancy map as a table lookup -----------------------------
+// Map mode in 2D: every input channel is the same {0,1} image (train.py:41-44), so the layer's output at a pixel depends only
+// on the 9 bits of its 3x3 neighbourhood (zero padding = bit 0): relu(bias + sum over set taps of sum_c w[co][c][tap]).
+// Each CTA builds the 512-entry table [pattern][cout] in shared memory (fp32 sums, fp16 entries: 32 KB for cout = 32) and
+// then the kernel is a pure store stream: a warp takes 32 consecutive pixels, each lane computes its pixel's pattern, and
+// the 32 x cout_pad fp16 outputs leave as fully coalesced 512-byte rows (lane l writes 16-byte chunk l % 8 of pixel
+// 4 * step + l / 8, copied from the table or zero for the padding channels).  268 MB per 8 maps at 512^2: HBM-write bound
+// (the per-pixel FMA version spent 0.51 ms per 8 maps, 10x the store time).
+__global__ void __launch_bounds__(256) stem_lut_kernel(const uint8_t* __restrict__ occ, const int32_t* __restrict__ t2m, int n,
+                                                       int cin, int H, int W, const float* __restrict__ wgt,
+                                                       const float* __restrict__ bias, int cout, int cout_pad,
+                                                       __half* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    __half* lut = reinterpret_cast<__half*>(s_raw);                      // [512][cout]
+    float* wsum = reinterpret_cast<float*>(s_raw + (size_t)512 * cout * 2);  // [cout][9] summed over input channels, + bias[cout]
+    for (int i = threadIdx.x; i < cout * 9; i += blockDim.x) {
+        const int co = i / 9, tap = i - co * 9;
+        float a = 0.f;
+        for (int c = 0; c < cin; ++c) a += wgt[(co * cin + c) * 9 + tap];
+        wsum[i] = a;
+    }
+    for (int i = threadIdx.x; i < cout; i += blockDim.x) wsum[cout * 9 + i] = bias[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 512 * cout; i += blockDim.x) {
+        const int pat = i / cout, co = i - pat * cout;
+        float a = wsum[cout * 9 + co];
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+            if ((pat >> tap) & 1) a += wsum[co * 9 + tap];
+        lut[i] = __float2half_rn(fmaxf(a, 0.f));
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long pixels = (long long)n * H * W;
+    const long long n_groups = (pixels + 31) >> 5;
+    const int chunks = cout_pad >> 3;  // 16-byte chunks per pixel
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long grp = warp0; grp < n_groups; grp += n_warps) {
+        const long long pix = (grp << 5) + lane;
+        int pat = 0;
+        if (pix < pixels) {
+            long long t = pix;
+            const int w = (int)(t % W); t /= W;
+            const int h = (int)(t % H);
+            const int b = (int)(t / H);
+            const uint8_t* omap = occ + (size_t)__ldg(t2m + b) * H * W;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int yy = h + dy, xx = w + dx;
+                    if (yy >= 0 && yy < H && xx >= 0 && xx < W && __ldg(omap + (long long)yy * W + xx) != 0)
+                        pat |= 1 << ((dy + 1) * 3 + dx + 1);
+                }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(out + (grp << 5) * cout_pad);
+        const int total = 32 * chunks;  // 16-byte chunks of this group of 32 pixels, contiguous in memory
+        for (int i = lane; i < total; i += 32) {
+            const int px = i / chunks, ch = i - px * chunks;
+            const int ppat = __shfl_sync(0xffffffffu, pat, px);
+            if ((grp << 5) + px < pixels) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (ch * 8 < cout) v = *reinterpret_cast<const uint4*>(lut + (size_t)ppat * cout + ch * 8);
+                dst[i] = v;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 static int stem_launch(int dims, const float* x, const uint8_t* occ, const int32_t* t2m, int n, int cin, int d, int h, int w,
@@ -634,6 +705,12 @@ static int stem_launch(int dims, const float* x, const uint8_t* occ, const int32
     const size_t smem = ((size_t)cout * cin * taps + cout) * sizeof(float);
     const long long pixels = (long long)n * d * h * w;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t lut_smem = (size_t)512 * cout * 2 + ((size_t)cout * 9 + cout) * sizeof(float);
+    if (dims == 2 && occ && lut_smem <= 48 * 1024) {  // binary map input: table lookup + coalesced store stream
+        stem_lut_kernel<<<148 * 4, 256, lut_smem, st>>>(occ, t2m, n, cin, h, w, weight, bias, cout, cout_pad, (__half*)out);
+        NRRT_CUDA_TRY(cudaGetLastError());
+        return NRRT_OK;
+    }
     if (dims == 2) stem_kernel<2><<<grid_for(pixels, 256), 256, smem, st>>>(x, occ, t2m, n, cin, d, h, w, weight, bias, cout, cout_pad, (__half*)out);
     else stem_kernel<3><<<grid_for(pixels, 256), 256, smem, st>>>(x, occ, t2m, n, cin, d, h, w, weight, bias, cout, cout_pad, (__half*)out);
     NRRT_CUDA_TRY(cudaGetLastError());

@@ -345,6 +345,31 @@ def test_folded_decoder_equals_separate_layers(cuda_device):
     assert (a - b).abs().max().item() <= 5e-3
 
 
+def test_stem_from_binary_maps_is_a_table_lookup(cuda_device):
+    """nrrt_stem_conv_maps in 2D (every input channel = the {0,1} occupancy map, train.py:41-44) runs as a 512-entry table
+    lookup; it must equal the generic first conv on the materialised (B, 3, H, W) tensor (ragged pixel count: 3*20*28)."""
+    import ctypes as C
+    dev = cuda_device
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(5)
+    n_maps, H, W, cin, cout, pad = 4, 20, 28, 3, 32, 64
+    occ = (torch.rand((n_maps, H, W), generator=g) < 0.6).to(torch.uint8).mul(255).to(dev)
+    t2m = torch.tensor([2, 0, 3], dtype=torch.int32, device=dev)
+    w = torch.randn((cout, cin * 9), generator=g).to(dev).contiguous()
+    b = torch.randn(cout, generator=g).to(dev)
+    x = (occ[t2m.long()] != 0).float()[:, None].repeat(1, cin, 1, 1).contiguous()
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    o1 = torch.full((3, 1, H, W, pad), 7.0, dtype=torch.float16, device=dev)
+    o2 = torch.full_like(o1, 9.0)
+    _lib.check(lib.nrrt_stem_conv_maps(2, p(occ), p(t2m), 3, cin, 1, H, W, p(w), p(b), cout, pad, p(o1), None))
+    _lib.check(lib.nrrt_stem_conv(2, p(x), 3, cin, 1, H, W, p(w), p(b), cout, pad, p(o2), None))
+    torch.cuda.synchronize()
+    ref = F.relu(F.conv2d(x, w.view(cout, cin, 3, 3), b, padding=1))
+    assert (o1[..., cout:] == 0).all() and (o2[..., cout:] == 0).all()
+    assert (_from_cl(o1[..., :cout], 2) - ref).abs().max().item() <= 4e-3 * max(ref.abs().max().item(), 1.0)
+    assert (o1.float() - o2.float()).abs().max().item() <= 4e-3 * max(ref.abs().max().item(), 1.0)
+
+
 def test_3d_slab_kernel_residual_and_head(cuda_device):
     """3D 3x3x3 layers on the slab kernel: indexed residual (TMA-staged) and the fused 1x1x1 head."""
     dev = cuda_device
