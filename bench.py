@@ -157,7 +157,7 @@ def run_reference(args):
         return
     dim = 2 if args.workload.startswith("2d") else 3
     tasks = args.tasks or (4096 if dim == 2 else 1024)
-    n_sample = args.ref_sample or (8 if not args.workload.endswith("uniform") else 32)
+    n_sample = args.ref_sample or (16 if not args.workload.endswith("uniform") else 32)
     wl = make_workload(args.workload, max(n_sample, 10), 0)
     model = None if args.workload.endswith("uniform") else make_model(dim)
     for _ in range(args.warmup):
@@ -322,7 +322,7 @@ def run_graft(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                _, cpu = cpu_arm(args, wl, args.ref_sample or (8 if not uniform else 32), model=None)
+                _, cpu = cpu_arm(args, wl, args.ref_sample or (16 if not uniform else 32), model=None)
             except Exception as exc:  # the baseline is informational; never lose the GPU line over it
                 cpu = {"error": repr(exc)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
