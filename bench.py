@@ -304,8 +304,8 @@ def run_graft(args):
             n_l, fl, t_ms = prof.totals()
             ach = fl / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0
             traffic, traffic_note = conv_traffic()
-            roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel / conv_halo2_kernel (tcgen05 implicit-GEMM convolution, all "
-                                                     "34 layer shapes of the forward)",
+            roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel / conv_halo2_kernel (tcgen05 implicit-GEMM convolution, every "
+                                                     "layer shape of the forward)",
                         "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
                         "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["which"], "launches_timed": n_l,
                         "avg_launch_ms": t_ms / max(n_l, 1), "flops_per_launch_avg": fl / max(n_l, 1),
