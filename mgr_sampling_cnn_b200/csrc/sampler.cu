@@ -810,25 +810,7 @@ struct DrawArgs {
     int64_t cells;
 };
 
-// first index j in [0, n] with !(cdf[j] < u) (np.searchsorted side='left', fp64 compare, NaN sorts last), 32-ary search
-__device__ __forceinline__ int64_t cdf_search_warp(const float* __restrict__ cdf, int64_t n, double u, int lane) {
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-        const int64_t len = hi - lo;
-        const int64_t step = (len + 31) >> 5;
-        const int64_t q = lo + (int64_t)(lane + 1) * step - 1;
-        bool ge = true;
-        if (q < hi) ge = !((double)__ldg(cdf + q) < u);
-        const uint32_t bal = __ballot_sync(0xffffffffu, ge);
-        const int f = bal ? (__ffs(bal) - 1) : 32;
-        const int64_t qf = lo + (int64_t)(f + 1) * step - 1;
-        lo = lo + (int64_t)f * step;
-        hi = (f < 32 && qf < hi) ? qf : hi;
-        if (lo > hi) lo = hi;
-    }
-    return lo;
-}
-
+// inverse-CDF lookup = first index j in [0, n] with !(cdf[j] < u) (np.searchsorted side='left', fp64 compare, NaN sorts last)
 template <int DIM>
 __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
     const int lane = threadIdx.x & 31;
@@ -842,16 +824,77 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
     const int max_iter = a.p.max_iterations;
     int16_t* out = a.samples + (size_t)b * max_iter * DIM;
 
-    uint64_t k = 0, blk = ~0ull;
-    double u_lane = 0.0;
-    auto next_u = [&]() -> double {  // draws are generated 32 at a time (one per lane) and consumed in order
-        if ((k >> 5) != blk) {
-            blk = k >> 5;
-            u_lane = nrrt_uniform(seed, stream_id, (blk << 5) + lane);
+    // Draws are generated 4 x 32 at a time (lane l holds draws 32 j + l of the group, j = 0..3) and consumed in order.
+    // Speculative inverse-CDF lookup: which draws of the stream are neural samples is only known as the stream is consumed
+    // (bias test, rejection retries), but a lookup has no side effect, so every lane searches ITS four uniforms when the
+    // group is generated: 128 binary searches in flight (four independent chains per lane, 19 dependent probes per group)
+    // instead of one 32-ary warp search (4 dependent probes) per neural draw as it comes up.  The kernel is a chain of
+    // DRAM / L2 round trips (one warp per task); this cut the 3D draw pass from 121 ms to a quarter.
+    // Same partition point as np.searchsorted(side='left'): first j with !(cdf[j] < u).
+    constexpr int NB = 4;
+    uint64_t k = 0, grp = ~0ull;
+    double u_lane[NB] = {0.0, 0.0, 0.0, 0.0};
+    int idx_lane[NB] = {0, 0, 0, 0};
+    uint32_t free_lane = 0u;  // bit j: the cell of lookup j is free
+    const uint32_t* grid_words = grid;
+    auto gen_group = [&]() {  // generate (and look up) the group of 128 draws that holds draw k, if it is not the current one
+        if ((k >> 7) != grp) {
+            grp = k >> 7;
+#pragma unroll
+            for (int j = 0; j < NB; ++j) u_lane[j] = nrrt_uniform(seed, stream_id, (grp << 7) + (uint64_t)(j * 32 + lane));
+            if (cdf) {
+                int lo[NB], hi[NB];
+#pragma unroll
+                for (int j = 0; j < NB; ++j) { lo[j] = 0; hi[j] = (int)a.cells; }
+                bool more = a.cells > 0;
+                while (more) {
+                    float v[NB];
+                    int mid[NB];
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {  // the four loads are independent: issued together
+                        mid[j] = (lo[j] + hi[j]) >> 1;
+                        v[j] = lo[j] < hi[j] ? __ldg(cdf + mid[j]) : 0.f;
+                    }
+                    more = false;
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        if (lo[j] < hi[j]) {
+                            if ((double)v[j] < u_lane[j]) lo[j] = mid[j] + 1; else hi[j] = mid[j];
+                        }
+                        more = more || lo[j] < hi[j];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NB; ++j) idx_lane[j] = lo[j];
+                if (DIM == 3) {  // ... and the occupancy test of the cell each lookup landed on (3D redraws until free)
+                    uint32_t wv[NB];
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        const int64_t c = lo[j] > (int)a.cells - 1 ? a.cells - 1 : (int64_t)lo[j];
+                        wv[j] = __ldg(grid_words + (c >> 5)) >> (c & 31);
+                    }
+                    free_lane = 0u;
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) free_lane |= (wv[j] & 1u) << j;
+                }
+            }
         }
-        const double u = __shfl_sync(0xffffffffu, u_lane, (int)(k & 31));
+    };
+    auto next_u = [&]() -> double {
+        gen_group();
+        const int j = (int)((k >> 5) & 3);
+        const double mine = j == 0 ? u_lane[0] : (j == 1 ? u_lane[1] : (j == 2 ? u_lane[2] : u_lane[3]));
+        const double u = __shfl_sync(0xffffffffu, mine, (int)(k & 31));
         ++k;
         return u;
+    };
+    auto lookup_of = [&](uint64_t kk) -> int {  // speculative lookup of draw kk (of the current group)
+        const int j = (int)((kk >> 5) & 3);
+        const int mine = j == 0 ? idx_lane[0] : (j == 1 ? idx_lane[1] : (j == 2 ? idx_lane[2] : idx_lane[3]));
+        return __shfl_sync(0xffffffffu, mine, (int)(kk & 31));
+    };
+    auto lookup_free = [&](uint64_t kk) -> bool {
+        return (__shfl_sync(0xffffffffu, free_lane, (int)(kk & 31)) >> ((kk >> 5) & 3)) & 1u;
     };
     auto randint0 = [&](int n) -> int {  // random.randint(0, n - 1) on the shared stream
         const int v = __double2int_rd(__dmul_rn(next_u(), (double)n));
@@ -860,6 +903,7 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
     auto is_free = [&](int64_t idx) -> bool { return (__ldg(grid + (idx >> 5)) >> (idx & 31)) & 1u; };
 
     int status = 0;
+    bool checked = false;
     int16_t keep[DIM];
     int8_t keep_flag = 0;
 #pragma unroll
@@ -872,13 +916,33 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
         int rej = 0;
         for (;;) {
             if (use_neural) {
-                const double u = next_u();  // random.uniform(0, 1) = 0 + (1 - 0) * random()
-                int64_t idx = cdf_search_warp(cdf, a.cells, u, lane);
+                if (DIM == 3 && rej > 0) {
+                    // inside a run of redraws every draw is a neural redraw until one lands on a free cell, and the verdicts
+                    // of the current group are already known: skip its failures at once (same draws consumed, same count)
+                    gen_group();
+                    const int p0 = (int)(k & 127);
+                    int pos = -1;
+#pragma unroll
+                    for (int j = 0; j < NB; ++j) {
+                        uint32_t m = __ballot_sync(0xffffffffu, (free_lane >> j) & 1u);
+                        if (j == (p0 >> 5)) m &= 0xffffffffu << (p0 & 31);
+                        if (pos < 0 && j >= (p0 >> 5) && m) pos = j * 32 + __ffs(m) - 1;
+                    }
+                    const int fails = (pos >= 0 ? pos : 128) - p0;  // failed redraws before the next success / the group's end
+                    const int room = a.p.max_reject - rej;          // failures still allowed
+                    if (fails >= room) { k += (uint64_t)room; status = NRRT_SAMPLER_STUCK; break; }
+                    k += (uint64_t)fails;
+                    rej += fails;
+                    if (pos < 0) continue;  // nothing free in the rest of this group: on to the next one
+                }
+                const uint64_t kk = k;  // this draw's position in the stream
+                (void)next_u();         // random.uniform(0, 1) = 0 + (1 - 0) * random()   (generates kk's group if needed)
+                int64_t idx = lookup_of(kk);
                 idx = idx > a.cells - 1 ? a.cells - 1 : idx;  // min(max(index, 0), N - 1)
                 if (DIM == 2) { c[0] = (int)(idx / s1); c[1] = (int)(idx % s1); break; }
                 const int64_t yz = (int64_t)s1 * s2;
                 c[0] = (int)(idx / yz); c[1] = (int)((idx % yz) / s2); c[2] = (int)(idx % s2);
-                if (is_free(idx)) break;
+                if (lookup_free(kk)) break;  // == is_free(idx), tested when the group was generated
             } else if (DIM == 2) {
                 const int x = randint0(s1);  // x = randint(0, map_width - 1)
                 const int y = randint0(s0);  // y = randint(0, map_height - 1)
@@ -891,6 +955,22 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
                 if (is_free(((int64_t)xi * s1 + yi) * s2 + z)) { c[0] = x; c[1] = y; c[2] = z; break; }
             }
             if (++rej >= a.p.max_reject) { status = NRRT_SAMPLER_STUCK; break; }
+            if (DIM == 3 && use_neural && rej == 256 && !checked) {
+                // 256 redraws in a row: decide once whether ANY cell the lookup can return is free (the reference's
+                // `while True` would spin forever otherwise, ThreeD_neural_rrt.py:82-110).  A cell is reachable when it
+                // carries probability mass (cdf[i] > cdf[i-1]); the first and the last cell are treated as reachable
+                // (u = 0 / u above the rounded total land there), so the test never gives up on a task that could succeed.
+                checked = true;
+                bool any = false;
+                const int n = (int)a.cells;
+#pragma unroll 4
+                for (int i = lane; i < n; i += 32) {
+                    const float ci = __ldg(cdf + i);
+                    const float pv = i ? __ldg(cdf + i - 1) : -1.f;
+                    if ((ci > pv || i == n - 1) && is_free(i)) any = true;
+                }
+                if (!__any_sync(0xffffffffu, any)) { status = NRRT_SAMPLER_STUCK; break; }
+            }
         }
         if (lane == (it & 31)) {
 #pragma unroll

@@ -1,5 +1,5 @@
 """Scratch: where the CNN time of one 4096-task batch goes besides the tensor-core layers (CUDA events around
-coords_prepare, the stem kernel, poly_relu; not the bench contract).   python scripts/perf_cnn_split.py [tasks]"""
+coords_prepare, the stem kernel, poly_relu; not the bench contract).   python scripts/perf_cnn_split.py [tasks] [dim]"""
 import os
 import sys
 
@@ -10,13 +10,18 @@ from mgr_sampling_cnn_b200 import _lib, engine, train, workload  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-wl = workload.make_2d(B)
+dim = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+wl = workload.make_2d(B) if dim == 2 else workload.make_3d(B)
 torch.manual_seed(0)
-model = train.UNet_cooler().eval().to(dev)
-gp = engine.GuidedPlanner(model, 2, wl.shape)
+if dim == 2:
+    model = train.UNet_cooler().eval().to(dev)
+else:
+    from mgr_sampling_cnn_b200 import ThreeD_train
+    model = ThreeD_train.ThreeD_UNet_cooler().eval().to(dev)
+gp = engine.GuidedPlanner(model, dim, wl.shape)
 lib = _lib.load()
 names = ["nrrt_conv_layer", "nrrt_stem_conv_maps", "nrrt_coords_branch", "nrrt_coords_poly_gemm", "nrrt_poly16", "nrrt_poly_fold",
-         "nrrt_poly_relu", "nrrt_cdf_build", "nrrt_draw_samples", "nrrt_plan_batch", "nrrt_pack_occupancy"]
+         "nrrt_poly_relu", "nrrt_poly_relu_3d", "nrrt_coords_fill", "nrrt_coords_pieces_3d", "nrrt_cdf_build", "nrrt_draw_samples", "nrrt_plan_batch", "nrrt_pack_occupancy"]
 events = {n: [] for n in names}
 for name in names:
     fn = getattr(lib, name)
@@ -43,3 +48,8 @@ for name, v in events.items():
     tot += ms
     print(f"{name:24s} {len(v):6d} calls {ms:9.2f} ms")
 print(f"sum {tot:.1f} ms of {t0.elapsed_time(t1):.1f} ms (events between every call serialise nothing; gaps = host / torch ops)")
+if res.n_draws is not None:
+    nd = res.n_draws.double().cpu().numpy()
+    import numpy as np  # noqa: E402
+    print(f"draws per task: mean {nd.mean():.0f}, median {np.median(nd):.0f}, max {nd.max():.0f}; per iteration {nd.sum() / res.iterations.double().sum().item():.2f}"
+          f" (draw kernel always draws max_iterations samples: {nd.mean() / 5000:.2f} per sample)")

@@ -100,6 +100,40 @@ def test_neural_draws_match_reference(cuda_device):
         assert np.array_equal(res.neural_flag[0].cpu().numpy(), flags)
 
 
+@pytest.mark.parametrize("free_mass_cells,max_reject", [(3, 100000), (0, 5000), (1, 700)])
+def test_3d_redraw_runs_and_stuck_sampler(free_mass_cells, max_reject, cuda_device):
+    """3D generate_neural_sample redraws until the drawn voxel is free (ThreeD_neural_rrt.py:82-110).  Heat maps whose mass
+    sits almost entirely on occupied voxels give redraw runs of hundreds to thousands of draws: the kernel skips the known
+    failures of a generated group at once and must still consume exactly the draws the sequential sampler consumes
+    (samples, neural flags, draw count, status vs the C oracle).  No free voxel with mass: SAMPLER_STUCK (the reference
+    would spin forever), found by the one-time reachability scan; a bound that trips first: the same status."""
+    rng = np.random.default_rng(7 + free_mass_cells)
+    shape = (16, 16, 16)
+    occ = (rng.random(shape) < 0.5).astype(np.uint8) * 255            # 3D: 0 = free
+    heat = np.where(occ != 0, rng.random(shape) + 0.5, 0.0).astype(np.float32)   # all mass on occupied voxels ...
+    free_idx = np.argwhere(occ == 0)
+    for c in free_idx[rng.choice(len(free_idx), free_mass_cells, replace=False)] if free_mass_cells else []:
+        heat[tuple(c)] = 1.0                                           # ... except a few free ones
+    cdf = engine.build_cdf(heat[None], engine.HEAT_MODE_RAW, cuda_device)
+    cdf_o = po.build_cdf(heat)[0]
+    assert np.array_equal(cdf[0].cpu().numpy(), cdf_o)
+    bits = engine.pack_occupancy(occ[None], 3, cuda_device)
+    n_iter = 40
+    res = engine.plan_batch(bits, np.zeros(1, np.int32), free_idx[:1].astype(np.int32), free_idx[1:2].astype(np.int32), dim=3,
+                            shape=shape, max_iterations=n_iter, cdf=cdf, neural_bias=0.75, seed=11,
+                            task_ids=np.array([5], np.int32), max_reject=max_reject)
+    torch.cuda.synchronize()
+    smp, flags, nd, st = po.draw_samples(3, shape, po.occ_free_3d(occ), cdf_o, 0.75, 11, 5, n_iter, max_reject=max_reject)
+    assert (st != 0) == (free_mass_cells < 3)
+    assert int(res.status[0]) == (3 if st != 0 else int(res.status[0]))
+    if st == 0:
+        assert int(res.n_draws[0]) == nd and nd > 20 * n_iter         # long redraw runs did happen
+        assert np.array_equal(res.samples[0].cpu().numpy(), smp.astype(np.int16))
+        assert np.array_equal(res.neural_flag[0].cpu().numpy(), flags)
+    elif free_mass_cells:  # the bound tripped: exactly the draws the sequential sampler consumed
+        assert int(res.n_draws[0]) == nd
+
+
 def test_uniforms_on_device_match_numpy(cuda_device):
     """The device Philox stream, observed through uniform draws on an all-free map, equals oracle/philox_stream.py."""
     occ = np.full((512, 512), 255, np.uint8)
