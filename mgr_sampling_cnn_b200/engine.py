@@ -249,7 +249,7 @@ class GuidedPlanner(object):
         self.max_iterations, self.neural_bias = max_iterations, neural_bias
         self.goal_threshold = goal_threshold if goal_threshold is not None else (5.0 if dim == 2 else 3.0)
         # tasks per decoder launch: four maps' worth in 2D (fewer, longer launches: +5 % over one map's worth), half a map in 3D
-        self.micro_batch = micro_batch or (40 if dim == 2 else 5)
+        self.micro_batch = micro_batch or (40 if dim == 2 else 10)
         self.pipeline_batch, self.path_cap, self.max_reject = pipeline_batch, path_cap, max_reject
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
