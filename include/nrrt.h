@@ -197,6 +197,9 @@ typedef struct NrrtConvLayer {
     int32_t no_poly_mma;     /* testing: evaluate the whole polynomial term in the epilogue (default: the interior polynomial
                                 of residual-carrying 3x3 layers is one extra tensor-core MMA per tile) */
     int32_t no_tma_store;    /* testing: direct global stores from the epilogue threads instead of staged TMA stores */
+    const float* poly3;      /* optional (3D, 128 output channels, residual, H and W multiples of 16): the coordinate field
+                                E [n][54][4][cout] of nrrt_coords_poly_gemm (cases = 54) added before the ReLU in the epilogue,
+                                instead of the nrrt_poly_relu_3d pass over the stored activation */
     int32_t res_mma;         /* NRRT_CONV_UPFOLD only: accumulate the residual tile with the tensor core (identity columns of the
                                 weight) instead of staging it for the epilogue; same results */
     int32_t res_group;       /* scheduling hint (pair slab kernel): consecutive samples per group that share residual rows

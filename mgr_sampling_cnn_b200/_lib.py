@@ -36,7 +36,7 @@ class NrrtConvLayer(C.Structure):
                 ("cin2", C.c_int32), ("in_n", C.c_int32), ("in2_n", C.c_int32), ("in_index", C.c_void_p), ("in2_index", C.c_void_p),
                 ("res_index", C.c_void_p), ("res_n", C.c_int32),
                 ("no_poly_mma", C.c_int32), ("no_tma_store", C.c_int32),
-                ("res_mma", C.c_int32), ("res_group", C.c_int32)]
+                ("poly3", C.c_void_p), ("res_mma", C.c_int32), ("res_group", C.c_int32)]
 
 
 _SIGNATURES = {

@@ -158,15 +158,16 @@ class _Layer(object):
     res_mma = False        # folded layers: residual accumulated by the tensor core instead of staged for the epilogue
 
     def run(self, lib, stream, x, x_coff, grid, out, out_coff, res=None, res_coff=0, poly=None, head=None, x2=None,
-            idx=None, idx2=None, n=None, res_idx=None, res_group=0):
+            idx=None, idx2=None, n=None, res_idx=None, res_group=0, poly3=None):
         """x/out/res: channels-last fp16 buffers [B, (D,) H, W, Ctot]; grid = input (D, H, W).
         head = (weight fp32 [cout], bias float, logits fp32 tensor): fuse the 1x1 output head, `out` may be None.
         x2: optional second input buffer (K split: channels [x: self.cin | x2: self.cin2]); idx / idx2: optional int32
         [n] sample indirection of x / x2 (encoder outputs shared per map); n = number of output samples;
         res_idx: optional int32 [n] sample indirection of the residual (per-map partial sums); res_group: scheduling hint,
-        consecutive samples that share a residual row (include/nrrt.h)."""
+        consecutive samples that share a residual row (include/nrrt.h); poly3: 3D coordinate field E [n, 54, 4, cout] added in
+        the epilogue together with the ReLU (instead of nrrt_poly_relu_3d over the stored output)."""
         n = n if n is not None else (idx.shape[0] if idx is not None else x.shape[0])
-        args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx, res_group)
+        args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx, res_group, poly3)
         prof = self.profiler
         if prof is not None and prof.active:
             with prof.launch(self.flops(n, grid), getattr(self, "name", None)):
@@ -175,7 +176,7 @@ class _Layer(object):
             self._run(*args)
 
     def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx=None,
-             res_group=0):
+             res_group=0, poly3=None):
         _lib.count_launch()
         L = _lib.NrrtConvLayer()
         L.dims, L.kind = self.dims, self.kind
@@ -208,7 +209,9 @@ class _Layer(object):
             if res_idx is not None:
                 L.res_index = _ptr(res_idx)
                 L.res_group = int(res_group)
-        L.relu = 1 if self.relu else 0
+        L.relu = 1 if (self.relu or poly3 is not None) else 0  # the fused 3D field carries the layer's ReLU with it
+        if poly3 is not None:
+            L.poly3 = _ptr(poly3)
         if self.post is not None:
             L.post_scale, L.post_shift = _ptr(self.post[0]), _ptr(self.post[1])
         if poly is not None:  # [n, 9, 4, cout], or per output parity [n, 4, 9, 4, cout] for a folded layer
@@ -467,6 +470,7 @@ class UNetPlan(object):
                         l.name = f"enc{si + 2}.{bi}.{('c1', 'c2', 'ds')[li]}"
 
     fold = True  # tests: False runs ConvTranspose and the conv after it as separate layers
+    fuse_poly3 = True  # tests: False applies conv8.0's 3D coordinate field with the nrrt_poly_relu_3d post-pass
 
     def use_fold(self, grid):
         """upconv7/conv7.0 and upconv8/conv8.0 as folded layers: 2D, low-resolution grids of at least one 16x16 tile."""
@@ -697,12 +701,16 @@ class UNetPlan(object):
         if not self.poly:
             post3d(bf["g7"], prep["e_c7"], 1)
         self.c7[1].run(lib, st, bf["g7"], 0, g[1], bf["i"], 0)
+        fuse3 = False
         if folded:
             self.c8f.run(lib, st, bf["i"], 0, g[1], bf["j"], 0, bf["r8"], 0, poly=prep["e_c8"], res_idx=ri, res_group=rg)
         else:
             self.up8.run(lib, st, bf["i"], 0, g[1], bf["t8"], 0)
-            self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8") if self.poly else None, res_idx=ri, res_group=rg)
-        if not self.poly:
+            # 3D: conv8.0 adds its coordinate field and the ReLU in the epilogue when the slices hold whole 16x16 tiles
+            fuse3 = (not self.poly) and self.fuse_poly3 and g[0][1] % 16 == 0 and g[0][2] % 16 == 0
+            self.c8[0].run(lib, st, bf["t8"], 0, g[0], bf["j"], 0, bf["r8"], 0, poly=prep.get("e_c8") if self.poly else None, res_idx=ri,
+                           res_group=rg, poly3=prep["e_c8"] if fuse3 else None)
+        if not self.poly and not fuse3:
             post3d(bf["j"], prep["e_c8"], 0)
 
         # conv8.2 + final_conv fused: the 64-channel activation is reduced to the logit in the epilogue

@@ -63,6 +63,8 @@ struct ConvParams {
     float inv_h, inv_w;  // 1/(H-1), 1/(W-1) of the tile-space grid
     int outer;           // slab kernels: slab loads per input-channel chunk: 3 (dx) in 2D, 9 (dz, dx) in 3D, 2 when folded
     int inner;           // slab kernels: vertical taps served by one slab: 3, or 2 when folded
+    const float* poly3;  // pair slab kernel, 3D: [N][54][4][cout] coordinate field (see stage_poly3), applied before the ReLU
+    float inv_d3, inv_h3;  // 1/(D-1), 1/(H-1)
     int dbg;             // experiments only (NRRT_CONV_DBG): 1 = no TMA stores, 2 = no epilogue arithmetic
     int res_k0;          // first K column of the identity block behind the weights (res_mma)
     int res_mma;         // pair slab kernel: the residual tile enters the accumulator through the tensor core (see below)
@@ -203,6 +205,13 @@ __device__ __forceinline__ uint32_t pack_h2_relu_sat(float lo, float hi) {
     return r;
 }
 
+// h-class of a row for the 3D coordinate field (csrc/conv_aux.cu, poly_relu3d_kernel): first row, inside piece 0, last row
+// of piece 0, first row of piece 1, inside piece 1, last row.  Monotone in h.
+__device__ __forceinline__ int hclass3(int h, int H) {
+    const int hh = H >> 1;
+    return h == 0 ? 0 : (h == H - 1 ? 5 : (h < hh - 1 ? 1 : (h == hh - 1 ? 2 : (h == hh ? 3 : 4))));
+}
+
 // Epilogue of 32 accumulator columns of one output pixel: folded-BN scale/shift, polynomial coordinate term, residual,
 // ReLU, optional second affine + ReLU, then either the fp16 store into the output channel slice or (fused 1x1 head) a
 // running dot product with the head weights.  col = first GEMM column, lc = its offset inside the staged scale/shift.
@@ -218,7 +227,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
                                                int h, int w, const float* sc, const float* sh, const float* sc2,
                                                const float* sh2, const float* pe, int pe_stride, float& head_acc,
                                                const uint8_t* res_row = nullptr, int res_r7 = 0, bool pm = false,
-                                               int frame = 0, uint8_t* stg_row = nullptr) {
+                                               int frame = 0, uint8_t* stg_row = nullptr, int slot3 = 0) {
     int g = 0, co = col;
     if (p.up == 2) { g = col / p.cout; co = col - g * p.cout; }
     auto out_pixel = [&](int ns) -> long long {  // pixel index in the output grid (ConvTranspose: pixel shuffle by group)
@@ -271,6 +280,28 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
                 f[q * 4 + 2] += a0.z + t * a1.z;
                 f[q * 4 + 3] += a0.w + t * a1.w;
             }
+        }
+    }
+    if (p.poly3) {
+        // 3D coordinate field of the tile's depth slice: A + th * B per (h-class, channel), staged by stage_poly3 for the
+        // interior w case; the two frame columns (w = 0, W - 1) have their own tap set and read their case from global memory
+        const float th = (float)h * p.inv_h3;
+        if (w != 0 && w != p.W - 1) {
+            const float4* A = reinterpret_cast<const float4*>(sc + (2 + 2 * slot3) * pe_stride + lc);
+            const float4* Bq = reinterpret_cast<const float4*>(sc + (3 + 2 * slot3) * pe_stride + lc);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 a = A[q], b = Bq[q];
+                f[q * 4 + 0] += fmaf(th, b.x, a.x); f[q * 4 + 1] += fmaf(th, b.y, a.y);
+                f[q * 4 + 2] += fmaf(th, b.z, a.z); f[q * 4 + 3] += fmaf(th, b.w, a.w);
+            }
+        } else {
+            const int dc = d == 0 ? 0 : (d == p.D - 1 ? 2 : 1);
+            const float td = (float)d * p.inv_d3;
+            const float* e = p.poly3 + (((size_t)n * 54 + (size_t)(dc * 6 + hclass3(h, p.H)) * 3 + (w == 0 ? 0 : 2)) * 4) * p.cout + co;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                f[i] += __ldg(e + i) + td * __ldg(e + p.cout + i) + th * (__ldg(e + 2 * (size_t)p.cout + i) + td * __ldg(e + 3 * (size_t)p.cout + i));
         }
     }
     const int j0 = (lc & 63) >> 3;  // first 16-byte piece of these 32 columns inside a staged 128-byte row
@@ -385,6 +416,28 @@ __device__ __forceinline__ void pm_stage_frame(const ConvParams& p, float* dst, 
         } else {
             dst[6 * BLOCK_N + c] = d0 + ty_r * d1 + tx_c * d2 + ty_r * tx_c * d3;
         }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+}
+
+// 3D coordinate field in the epilogue (conv8.0 of ThreeD_UNet_cooler; ThreeD_train.py:180-191, derivation in conv_aux.cu).
+// A tile is one depth slice, so td is tile-uniform and the field E0 + td E1 + th (E2 + td E3) is A + th * B per (h-class,
+// channel).  The 256 epilogue threads stage A, B of the (up to 6) h-classes of the tile's rows for the interior w case into
+// rows 2 + 2 q, 3 + 2 q of the tile's parameter buffer (16 rows per accumulator stage in these kernels), q = class - class
+// of the tile's first row.  Replaces the read-modify-write post-pass over the widest activation of the 3D decoder
+// (nrrt_poly_relu_3d: 655 MB in + 655 MB out per 5 tasks).
+template <int BLOCK_N>
+__device__ __forceinline__ void stage_poly3(const ConvParams& p, float* dst, int n, int td, int h0, int et, int col0) {
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
+    const int dc = td == 0 ? 0 : (td == p.D - 1 ? 2 : 1);
+    const float tdf = (float)td * p.inv_d3;
+    const int hc0 = hclass3(h0, p.H), hc1 = hclass3(min(h0 + 15, p.H - 1), p.H);
+    for (int i = et; i < (hc1 - hc0 + 1) * BLOCK_N; i += 32 * kEpiWarps) {
+        const int q = i / BLOCK_N, c = i - q * BLOCK_N;
+        const float* e = p.poly3 + (((size_t)n * 54 + (size_t)(dc * 6 + hc0 + q) * 3 + 1) * 4) * p.cout + col0 + c;
+        const float e0 = __ldg(e), e1 = __ldg(e + p.cout), e2 = __ldg(e + 2 * (size_t)p.cout), e3 = __ldg(e + 3 * (size_t)p.cout);
+        dst[(2 + 2 * q) * BLOCK_N + c] = e0 + tdf * e1;
+        dst[(3 + 2 * q) * BLOCK_N + c] = e2 + tdf * e3;
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
 }
@@ -1219,8 +1272,9 @@ __device__ __forceinline__ void halo_tile(const ConvParams& p, int m, int& n, in
     td = t / p.tiles_h;
 }
 
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM, bool TS>
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM, bool TS, bool P3 = false>
 struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
+    static constexpr int ss_rows = P3 ? 16 : 8;  // parameter rows per accumulator stage (P3: + A, B of up to 6 h-classes)
     static constexpr uint32_t a_stage = 2 * kSlabBytes;
     static constexpr uint32_t b_stage = (BLOCK_N / 2) * 128;
     static constexpr uint32_t off_b = A_STAGES * a_stage;
@@ -1230,7 +1284,7 @@ struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
     static constexpr uint32_t off_bar = off_pm + (PM ? 2 * 4096 + 2 * pm_b : 0);
     static constexpr uint32_t off_tmem = off_bar + (2 * A_STAGES + 2 * B_STAGES + 4 + 3 * kMaxResPieces + 2) * 8;
     static constexpr uint32_t off_ss = (off_tmem + 16 + 15) & ~15u;
-    static constexpr uint32_t total = off_ss + 2 * 8 * BLOCK_N * 4 + 1024;
+    static constexpr uint32_t total = off_ss + 2 * ss_rows * BLOCK_N * 4 + 1024;
 };
 
 // conv_halo2_kernel — the slab kernel on CTA pairs (cta_group::2): the pair owns two adjacent 16x16 tiles, every MMA is
@@ -1257,12 +1311,12 @@ struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
 // taps that fall inside the image, a per-border-case constant that the host adds to the polynomial's constant term
 // (the polynomial itself is re-expressed per parity in tile-space coordinates: nrrt_poly_fold).  20 % fewer MACs than
 // the two layers, and the upsampled activation (the widest tensor of the stage) is never written or read.
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM, bool TS>
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM, bool TS, bool P3 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                  const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_r,
                  const __grid_constant__ CUtensorMap map_o, const __grid_constant__ ConvParams p) {
-    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS>;
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS, P3>;
     constexpr int RC = BLOCK_N / 64;  // 64-channel chunks per column block; residual pieces = 2 * RC
     constexpr int TMEM_COLS = 4 * BLOCK_N;  // 2 accumulator stages x 2 column blocks
     extern __shared__ uint8_t smem_raw[];
@@ -1488,9 +1542,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             // folded layers: the polynomial is stored per (sample, parity); n only indexes it (results leave by TMA)
             if (p.fold) n = n * 4 + par;
             const int col0 = nh * BLOCK_N;
-            float* sc = ss + acc * 8 * BLOCK_N;
+            float* sc = ss + acc * L::ss_rows * BLOCK_N;
             stage_tile_params<BLOCK_N>(p, sc, col0, n, et, last_nh[acc] != nh, !PM && (last_n[acc] != n || last_nh[acc] != nh));
             last_n[acc] = n; last_nh[acc] = nh;
+            if (P3 && live) stage_poly3<BLOCK_N>(p, sc, n, td, th * 16, et, col0);
             int frame = 0;
             if (PM) {
                 const int h0 = th * 16, w0 = tw * 16;
@@ -1526,7 +1581,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 if (TS) srow = base_ptr + L::off_res + piece * kResPiece + row * 128;
                 if (valid && !(p.dbg & 2))
                     epilogue_chunk<RES, TS>(p, v, col0 + c * 32, c * 32, n, td, h, w, sc, sc + BLOCK_N, sc + 2 * BLOCK_N, sc + 3 * BLOCK_N,
-                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame, srow);
+                                   sc + 4 * BLOCK_N, BLOCK_N, head_acc, rrow, row & 7, PM, frame, srow,
+                                   P3 ? hclass3(h, p.H) - hclass3(th * 16, p.H) : 0);
                 if ((RES || TS) && (c & 1)) {  // both 32-column halves of the piece are done
                     if (TS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -1650,12 +1706,12 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap
     return NRRT_OK;
 }
 
-template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM = false, bool TS = false>
+template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM = false, bool TS = false, bool P3 = false>
 int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo,
                  const ConvParams& p, int sms, cudaStream_t st) {
-    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS>;
+    using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS, P3>;
     static_assert(L::total <= 232448, "shared memory budget");
-    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS>;
+    auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS, P3>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
     const int pairs = ((p.m_tiles + 1) / 2) * (p.fold ? 4 * p.n_tiles : 1);
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
@@ -1795,6 +1851,9 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     p.a_bytes = (uint32_t)p.rows * 128u;
     p.b_bytes = (uint32_t)block_n * 128u;
     p.head_w = l->head_weight; p.head_b = l->head_bias; p.logits = l->logits;
+    p.poly3 = l->poly3;
+    p.inv_d3 = p.D > 1 ? 1.0f / (float)(p.D - 1) : 0.f;
+    p.inv_h3 = p.H > 1 ? 1.0f / (float)(p.H - 1) : 0.f;
     if (l->logits) {
         NRRT_REQUIRE(l->head_weight && p.n_tiles == 1 && up == 1, "fused head needs head_weight and all output channels in one N tile");
     } else {
@@ -1899,8 +1958,13 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (fold) NRRT_REQUIRE(pair && tma_res && p.ts, "folded layer: residual / output layout not eligible for the TMA-staged epilogue");
+    if (l->poly3)
+        NRRT_REQUIRE(three_d && halo && pair && block_n == 128 && p.n_tiles == 1 && res_st && p.ts && !l->poly && p.H >= 4 && p.H % 2 == 0 &&
+                         ((uintptr_t)l->poly3 & 15) == 0,
+                     "poly3: 3D 3x3x3 layer with 128 output channels, a residual and whole 16x16 tiles per depth slice");
     if (halo && pair) {
         if (block_n == 128 && p.ts) {
+            if (p.poly3) return launch_halo2<128, 3, 4, true, false, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
             if (res_st && p.pm) return launch_halo2<128, 3, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
             if (p.pm) return launch_halo2<128, 3, 4, false, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
             if (res_st) return launch_halo2<128, 3, 5, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);

@@ -370,6 +370,29 @@ def test_stem_from_binary_maps_is_a_table_lookup(cuda_device):
     assert (o1.float() - o2.float()).abs().max().item() <= 4e-3 * max(ref.abs().max().item(), 1.0)
 
 
+def test_3d_field_in_the_epilogue_equals_the_post_pass(cuda_device):
+    """conv8.0 of the 3D decoder adds its coordinate field and the ReLU in the epilogue (one depth slice per tile: A + th * B
+    per h-class, staged per tile; frame columns from global memory); same logits as the nrrt_poly_relu_3d post-pass and
+    within 1e-2 of the fp32 oracle.  32^3: four 16x16 tiles per slice, the h-classes split between them."""
+    from mgr_sampling_cnn_b200 import ThreeD_train, workload
+    wl = workload.make_3d(3, size=32)
+    torch.manual_seed(0)
+    model = ThreeD_train.ThreeD_UNet_cooler().eval().to(cuda_device)
+    x = torch.from_numpy((wl.occ_maps[wl.task_to_map] != 0).astype(np.float32)).permute(0, 3, 1, 2).contiguous().to(cuda_device)
+    coords = torch.from_numpy(wl.coords).to(cuda_device)
+    a = model(x, coords).clone()
+    try:
+        cnn.UNetPlan.fuse_poly3 = False
+        b = model(x, coords).clone()
+    finally:
+        cnn.UNetPlan.fuse_poly3 = True
+    with torch.no_grad():
+        ref = cnn_oracle.forward({k: v.float() for k, v in model.state_dict().items()}, x, coords, 3)
+    torch.cuda.synchronize()
+    assert (a - ref).abs().max().item() <= 1e-2 and (b - ref).abs().max().item() <= 1e-2
+    assert (a - b).abs().max().item() <= 5e-3
+
+
 def test_3d_slab_kernel_residual_and_head(cuda_device):
     """3D 3x3x3 layers on the slab kernel: indexed residual (TMA-staged) and the fused 1x1x1 head."""
     dev = cuda_device
