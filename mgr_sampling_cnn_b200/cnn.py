@@ -7,6 +7,7 @@ Activations are fp16 channels-last.  The three `torch.cat` calls of the decoder 
 into channel slices of the concat buffers and TMA reads slices back out.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -377,7 +378,9 @@ class UNetPlan(object):
             """upconv7 -> conv7.0 / upconv8 -> conv8.0 as ONE layer (_fold_weights); the conv's bias and ReLU stay."""
             w, bc = _fold_weights(mu.weight, mu.bias, mc.weight[:, :c_up], dev)
             scale, shift = _fold_bn(None, mc.bias, mc.out_channels, dev)
-            return _Layer(d, UPFOLD, mu.in_channels, mc.out_channels, w, scale, shift, True), bc
+            layer = _Layer(d, UPFOLD, mu.in_channels, mc.out_channels, w, scale, shift, True)
+            layer.res_mma = bool(int(os.environ.get("NRRT_RES_MMA", "0")))  # experiments (profiles/conv_fold_r1.md)
+            return layer, bc
         # 3D: the coordinate channels leave the GEMM too; their (piecewise bilinear) field and the ReLU are applied by
         # nrrt_poly_relu_3d after the layer (csrc/conv_aux.cu)
         c60, self.c6e = (None, None) if self.poly else conv_split(model.conv6[0], 512, 256, False, relu=False)

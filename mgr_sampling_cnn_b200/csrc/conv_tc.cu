@@ -1295,7 +1295,7 @@ struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
 // p.res_mma (= BLOCK_N / 64 extra K chunks; host sets p.res = nullptr and RES = false): the residual tile is not staged for
 // the epilogue but ACCUMULATED BY THE TENSOR CORE: its two 128-pixel x 64-channel pieces per chunk are loaded into an A
 // stage like slabs (same [pixel row][8 pixels][128 B] layout, vertical tap 0) and multiplied by an identity block appended
-// to the weights (fp16 x 1.0 into the fp32 accumulator: exact).  With the staged variant the residual of tile i+1 could
+// to the weights (fp16 x 1.0 into the fp32 accumulator: exact; one N = 64 MMA per 64 output channels).  With the staged variant the residual of tile i+1 could
 // only be requested once the TMA store of tile i had drained the shared piece, so consecutive epilogues were serialised
 // with a store and an L2/DRAM round trip between them (ncu, conv8.0: tensor pipe 42 %, issuer waiting on the accumulator,
 // epilogue waiting on the residual).  Through the A ring the residual is prefetched like any operand; K grows by 64 per
@@ -1430,8 +1430,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
                     mbar_wait(bempty(sb), pb ^ 1u);
                     if (rank == 0) mbar_expect_tx(bfull(sb), 2 * L::b_stage);
+                    // identity rows of output channels [kc * 64, +64): an N = 64 MMA, each CTA feeding 32 of them (the tile's
+                    // other rows are loaded but not read)
                     tma2_load_2d(base + L::off_b + sb * L::b_stage, &map_b, bfull(sb) & kPeerBitMask,
-                                 p.res_k0 + kc * kBlockK, nh * BLOCK_N + (int)rank * (BLOCK_N / 2));
+                                 p.res_k0 + kc * kBlockK, nh * BLOCK_N + kc * 64 + (int)rank * 32);
                     if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
                 }
                 if (RES) {
@@ -1498,10 +1500,11 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                     tc_fence_after();
                     const uint64_t bdesc = make_smem_desc(base + L::off_b + sb * L::b_stage);
                     const uint64_t adesc = make_smem_desc(base + sa * L::a_stage + blk * kSlabBytes);
-                    if (elect_one()) {
+                    if (elect_one()) {  // D[:, kc * 64 : +64] += R_kc x I (first == 0 here: the conv taps came before)
+                        constexpr uint32_t idesc64 = make_idesc(64, 256);
 #pragma unroll
                         for (int kk = 0; kk < kBlockK / 16; ++kk)
-                            tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (first && kk == 0) ? 0u : 1u);
+                            tc_mma2_f16(d_tmem + (uint32_t)(kc * 64), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc64, 1u);
                         tc_commit2(bempty(sb));
                         tc_commit2(aempty(sa));
                     }
