@@ -284,6 +284,18 @@ int nrrt_gather_channels(const void* src, int64_t src_cstride, int64_t src_coffs
 int nrrt_head_1x1(const void* in, int64_t pixels, int C, int64_t in_cstride, const float* weight, float bias, float* logits,
                   void* stream);
 
+/* Batched exact shortest grid paths (2D): generate_paths.astar (generate_paths.py:11-74) for B tasks at once -- the "A*"
+ * column of the reference's results table (test_network_and_algorithms.py:148-183) and its task filter (tasks without a
+ * path are deleted, generate_paths.py:111-113).  8-connected moves, cost 1 / sqrt(2), a diagonal step only when both
+ * orthogonal neighbours are free.  A* with the consistent Euclidean heuristic returns a shortest path and every shortest
+ * path has the same numbers of straight and diagonal steps, so the kernel returns those two integers per task (-1, -1 and
+ * length NaN when there is no path) and length = n_straight + n_diag * sqrt(2), the reference's path length up to the
+ * order of its additions.  occ_bits as nrrt_pack_occupancy writes them (1 = free); starts / goals [B][2] = (y, x);
+ * work: [n_slots][H * W] uint64 scratch (one slot per resident CTA, e.g. the SM count); queue: one zeroed int32. */
+int nrrt_grid_paths_2d(const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map, const int32_t* starts,
+                       const int32_t* goals, int B, int H, int W, void* work, int n_slots, int32_t* queue,
+                       int32_t* n_straight, int32_t* n_diag, double* length, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -234,6 +234,35 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
                       n_draws=buf.n_draws if samples is None else None, trace=buf.trace, trace_n=buf.trace_n)
 
 
+def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape: Sequence[int], n_slots: Optional[int] = None):
+    """Shortest 8-connected grid path of every task = the reference's A* (generate_paths.py:11-74): its path length column
+    (test_network_and_algorithms.py:148-183) and its task filter (no path -> the task is deleted, generate_paths.py:111-113).
+    2D; occ_bits from pack_occupancy, starts / goals [B, 2] = (y, x).  Returns (length fp64 [B] (NaN = no path),
+    n_straight int32 [B], n_diagonal int32 [B]) on the device; length = n_straight + n_diagonal * sqrt(2)."""
+    lib = _lib.load()
+    dev = occ_bits.device
+    if dev.type != "cuda":
+        raise _lib.NrrtError("grid_path_lengths needs CUDA tensors: there is no CPU fallback")
+    if len(shape) != 2:
+        raise ValueError("grid_path_lengths is 2D (generate_paths.py); the 3D twin is not built")
+    H, W = int(shape[0]), int(shape[1])
+    t2m = _dev(task_to_map, torch.int32, dev).reshape(-1)
+    st = _dev(starts, torch.int32, dev).reshape(-1, 2).contiguous()
+    gl = _dev(goals, torch.int32, dev).reshape(-1, 2).contiguous()
+    B = t2m.shape[0]
+    n_slots = n_slots or torch.cuda.get_device_properties(dev).multi_processor_count
+    work = torch.empty((max(min(n_slots, B), 1), H * W), dtype=torch.int64, device=dev)
+    queue = torch.zeros(1, dtype=torch.int32, device=dev)
+    ns = torch.empty(B, dtype=torch.int32, device=dev)
+    nd = torch.empty(B, dtype=torch.int32, device=dev)
+    length = torch.empty(B, dtype=torch.float64, device=dev)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    _lib.count_launch()
+    check(lib.nrrt_grid_paths_2d(_ptr(occ_bits), occ_bits.shape[1], _ptr(t2m), _ptr(st), _ptr(gl), B, H, W, _ptr(work),
+                                 work.shape[0], _ptr(queue), _ptr(ns), _ptr(nd), _ptr(length), stream))
+    return length, ns, nd
+
+
 class GuidedPlanner(object):
     """The whole hot path for a batch of tasks: CNN probability maps -> sampler CDFs -> sample draws -> guided RRT*.
 
