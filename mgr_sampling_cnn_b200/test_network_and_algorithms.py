@@ -4,9 +4,11 @@ iterations of RRT* and Neural+RRT* per task, with mean and median — produced b
 
 Differences by design: tasks come from this package's generate_maps / generate_tasks drop-ins (the reference reads a
 private evaluation set), the model is whatever the caller passes (random-init by default: no trained weights ship with
-the reference), the A* column is not computed (out of scope), and `Time` is the batch's wall time divided by
-the number of tasks (the GPU plans thousands of tasks at once; there is no per-task timer to read).  Length is
-calculate_length(path) (test_network_and_algorithms.py:52-56), Iterations the planner's iteration_no.
+the reference), and `Time` is the batch's wall time divided by the number of tasks (the GPU plans thousands of tasks at
+once; there is no per-task timer to read).  Length is calculate_length(path) (test_network_and_algorithms.py:52-56),
+Iterations the planner's iteration_no.  The A* columns (2D; astar_pathfinding, test_network_and_algorithms.py:58-70) come
+from engine.grid_path_lengths: the length of the reference's A* path (a shortest path) for every task at once, NaN where
+the reference's astar returns None; its Iterations column is '-' as in the reference.  3D: A* is not built ('-').
 """
 from time import perf_counter
 
@@ -42,6 +44,15 @@ def _timed(fn, device):
     return perf_counter() - t0, out
 
 
+def astar_pathfinding(wl, device):
+    """astar(occ_map_gray, start, finish) + calculate_length for every task (test_network_and_algorithms.py:58-70), 2D."""
+    occ = torch.from_numpy(wl.occ_maps).to(device)
+    bits = engine.pack_occupancy(occ, 2, device)
+    engine.grid_path_lengths(bits, wl.task_to_map[:1], wl.starts[:1], wl.goals[:1], wl.shape)  # warm-up
+    secs, (length, _, _) = _timed(lambda: engine.grid_path_lengths(bits, wl.task_to_map, wl.starts, wl.goals, wl.shape), device)
+    return secs, length
+
+
 def rrt_star_pathfinding(wl, device, seed=0):
     """rrt_star.RRTStar(...).rrt_star() for every task of the workload (test_network_and_algorithms.py:90-104)."""
     occ = torch.from_numpy(wl.occ_maps).to(device)
@@ -74,12 +85,16 @@ def main(n_tasks=1000, three_d=False, model=None, device="cuda:0", seed=0):
     columns = pd.MultiIndex.from_product([["A*", "RRT*", "Neural+RRT*"], ["Time", "Length", "Iterations"]])
     df = pd.DataFrame(index=range(n), columns=columns)
     df[("A*", "Time")] = df[("A*", "Length")] = df[("A*", "Iterations")] = "-"
+    if not three_d:
+        secs, length = astar_pathfinding(wl, device)
+        df[("A*", "Time")] = secs / n
+        df[("A*", "Length")] = length.cpu().numpy()
     for name, (secs, res) in (("RRT*", rrt_star_pathfinding(wl, device, seed)),
                               ("Neural+RRT*", neural_rrt_star_pathfinding(model, wl, device, seed))):
         df[(name, "Time")] = secs / n
         df[(name, "Length")] = res.path_len.cpu().numpy()
         df[(name, "Iterations")] = res.iterations.cpu().numpy()
-    num = df[[c for c in df.columns if c[0] != "A*"]].astype(float)
+    num = df[[c for c in df.columns if not (df[c] == "-").all()]].astype(float)
     summary = pd.DataFrame({"mean": num.mean(), "median": num.median()}).T
     return df, summary
 

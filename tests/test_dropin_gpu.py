@@ -93,6 +93,11 @@ def test_evaluation_harness_table(cuda_device):
     assert list(df.columns.levels[0]) == ["A*", "Neural+RRT*", "RRT*"] and len(df) == 20
     assert list(summary.index) == ["mean", "median"]
     assert (df[("RRT*", "Iterations")].astype(int) <= 600).all() and (df[("Neural+RRT*", "Length")].astype(float) >= 0).all()
+    # A* column: the shortest grid path bounds every solved RRT* path from below up to the goal threshold (5 px: the RRT* path
+    # ends at the goal, but its vertices are free-space points, not grid moves: allow the two end snaps)
+    astar = df[("A*", "Length")].astype(float).to_numpy()
+    assert np.isfinite(astar).all() and (df[("A*", "Iterations")] == "-").all() and (df[("A*", "Time")].astype(float) > 0).all()
+    assert ("A*", "Length") in summary.columns
     # Length column == calculate_length of the returned path points
     wl = workload.make_2d(20)
     import torch
