@@ -284,17 +284,21 @@ int nrrt_gather_channels(const void* src, int64_t src_cstride, int64_t src_coffs
 int nrrt_head_1x1(const void* in, int64_t pixels, int C, int64_t in_cstride, const float* weight, float bias, float* logits,
                   void* stream);
 
-/* Batched exact shortest grid paths (2D): generate_paths.astar (generate_paths.py:11-74) for B tasks at once -- the "A*"
- * column of the reference's results table (test_network_and_algorithms.py:148-183) and its task filter (tasks without a
- * path are deleted, generate_paths.py:111-113).  8-connected moves, cost 1 / sqrt(2), a diagonal step only when both
- * orthogonal neighbours are free.  A* with the consistent Euclidean heuristic returns a shortest path and every shortest
- * path has the same numbers of straight and diagonal steps, so the kernel returns those two integers per task (-1, -1 and
- * length NaN when there is no path) and length = n_straight + n_diag * sqrt(2), the reference's path length up to the
- * order of its additions.  occ_bits as nrrt_pack_occupancy writes them (1 = free); starts / goals [B][2] = (y, x);
- * work: [n_slots][H * W] uint64 scratch (one slot per resident CTA, e.g. the SM count); queue: one zeroed int32. */
-int nrrt_grid_paths_2d(const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map, const int32_t* starts,
-                       const int32_t* goals, int B, int H, int W, void* work, int n_slots, int32_t* queue,
-                       int32_t* n_straight, int32_t* n_diag, double* length, void* stream);
+/* Batched exact shortest grid paths: generate_paths.astar (generate_paths.py:11-74) and ThreeD_generate_paths.astar
+ * (ThreeD_generate_paths.py:14-97) for B tasks at once -- the "A*" column of the reference's results table
+ * (test_network_and_algorithms.py:58-70,148-183) and its task filter (tasks without a path are deleted,
+ * generate_paths.py:111-113).  2D: 8-connected moves, cost 1 / sqrt(2), a diagonal step only when both orthogonal neighbours
+ * are free.  3D: 26-connected moves, cost 1 / sqrt(2) / sqrt(3); every move needs its three axis-projected cells free (the
+ * reference's `dx != 255` tests are always true, ThreeD_generate_paths.py:55-72).  A* with the consistent Euclidean
+ * heuristic returns a shortest path and every shortest path has the same number of steps of each kind, so the kernel
+ * returns those integers per task, n_steps [B][3] = steps of cost 1, sqrt(2), sqrt(3) (-1 when there is no path, length
+ * NaN), and length = n1 + n2 sqrt(2) + n3 sqrt(3): the reference's path length up to the order of its additions.
+ * occ_bits as nrrt_pack_occupancy writes them (1 = free; 3D maps hold {0 = free, 255}); starts / goals [B][dims] in array-axis
+ * order ((y, x) in 2D, (x, y, z) in 3D, as the planners take them); (s0, s1, s2) = array shape (s2 ignored in 2D);
+ * work: [n_slots][cells] uint64 scratch (one slot per resident CTA, e.g. the SM count); queue: one zeroed int32. */
+int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map, const int32_t* starts,
+                    const int32_t* goals, int B, int s0, int s1, int s2, void* work, int n_slots, int32_t* queue,
+                    int32_t* n_steps, double* length, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,20 +1,24 @@
 // gridpath.cu — batched exact shortest grid paths: the "A*" column of the reference's results table and its task filter.
 //
-// Replaces generate_paths.astar (generate_paths.py:11-74) for thousands of (map, start, goal) tasks at once: 8-connected
-// moves on the 2D occupancy grid, cost 1 / sqrt(2) (:66-72), a diagonal step only when BOTH orthogonal neighbours are free
-// (:45-59), no path -> the task is deleted (:111-113).  A* with the (consistent) Euclidean heuristic returns a shortest
-// path, and every shortest path has the same numbers of straight and diagonal steps (1 and sqrt(2) are rationally
+// Replaces generate_paths.astar (generate_paths.py:11-74) and ThreeD_generate_paths.astar (ThreeD_generate_paths.py:14-97)
+// for thousands of (map, start, goal) tasks at once.  2D: 8-connected moves, cost 1 / sqrt(2) (:66-72), a diagonal step
+// only when BOTH orthogonal neighbours are free (:45-59).  3D: 26-connected moves, cost 1 / sqrt(2) / sqrt(3) (:83-97); the
+// reference compares the move OFFSETS with 255 (`dx != 255`, :55-72), which is always true, so EVERY move -- axis moves
+// included -- needs its three axis-projected cells free (a projection with a zero offset is the current cell itself).
+// No path -> the task is deleted (generate_paths.py:111-113).  A* with the (consistent) Euclidean heuristic returns a
+// shortest path, and every shortest path has the same numbers of steps of each kind (1, sqrt(2), sqrt(3) are rationally
 // independent), so the length the reference reports (calculate_length, test_network_and_algorithms.py:52-56) is
-// n_straight + n_diagonal * sqrt(2) up to the order of its additions.  The kernel computes exactly those two integers.
+// n1 + n2 * sqrt(2) + n3 * sqrt(3) up to the order of its additions.  The kernel computes exactly those integers.
 //
 // Algorithm: label-setting Dijkstra by unit-width buckets (Dial).  Every edge is >= 1 = the bucket width, so no relaxation
 // out of bucket k lands in bucket k: all nodes of a bucket are final when it is processed and can be expanded in parallel;
 // relaxations land in buckets k+1 and k+2 only (max edge < 2), so three shared-memory queues in rotation suffice.
 // One task per CTA (persistent CTAs, atomic task queue).  Node labels live in a per-CTA slot of global memory (8 B per
-// cell, 2 MB at 512^2: L2-resident) as one 64-bit word  [cost in 12.20 fixed point | n_straight:16 | n_diagonal:16]
-// updated with atomicMin: the fixed-point cost a * 2^20 + b * round(sqrt(2) * 2^20) is an exact integer function of (a, b),
-// orders candidates, and carries its step counts with it.  The occupancy grid is staged in shared memory (bit-packed, as
-// in the planner).  A queue overflow (never seen at 512^2 with 12288 entries) degrades that bucket to a scan of all cells.
+// cell, 2 MB at 512^2 / 4 MB at 80^3: L2-resident) as one 64-bit word  [cost in 12.20 fixed point | step counts: 16 + 16
+// bits in 2D, 11 + 11 + 10 in 3D] updated with atomicMin: the fixed-point cost n1 * 2^20 + n2 * round(sqrt(2) * 2^20)
+// + n3 * round(sqrt(3) * 2^20) is an exact integer function of the counts, orders candidates, and carries them with it.  The occupancy grid is staged in shared memory (bit-packed, as
+// in the planner).  A queue overflow (12288 entries per bucket: not seen at 512^2, possible for wide 3D fronts) degrades that bucket to a
+// scan of all cells.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -29,37 +33,45 @@ constexpr int kQCap = 12288;
 constexpr unsigned long long kInf = ~0ull;
 constexpr unsigned long long kK1 = 1ull << 20;   // 1.0
 constexpr unsigned long long kK2 = 1482910ull;   // round(sqrt(2) * 2^20)
+constexpr unsigned long long kK3 = 1816187ull;   // round(sqrt(3) * 2^20)
 
 struct GridPathArgs {
     const uint32_t* occ_bits;
     int words_per_map;
     const int32_t* task_to_map;
-    const int32_t* starts;  // (y, x) as get_start_finish_coordinates returns them (generate_paths.py:81-87)
+    const int32_t* starts;  // [B][DIM]: (y, x) in 2D (generate_paths.py:81-87), (x, y, z) = array axes in 3D
     const int32_t* goals;
-    int B, H, W;
-    unsigned long long* work;  // [gridDim.x][H * W]
+    int B, S0, S1, S2;         // grid shape = array axes (S2 = 1 in 2D)
+    unsigned long long* work;  // [gridDim.x][cells]
     int32_t* queue;            // zeroed task counter
-    int32_t* n_straight;       // [B], -1 = no path
-    int32_t* n_diag;
+    int32_t* n_steps;          // [B][3]: steps of cost 1, sqrt(2), sqrt(3); -1 = no path
     double* length;            // [B], NaN = no path
 };
 
-__device__ __forceinline__ unsigned long long make_key(unsigned a, unsigned b) {
-    return ((a * kK1 + b * kK2) << 32) | ((unsigned long long)a << 16) | (unsigned long long)b;
+template <int DIM>
+__device__ __forceinline__ unsigned long long make_key(unsigned a, unsigned b, unsigned c) {
+    const unsigned long long cost = a * kK1 + b * kK2 + c * kK3;
+    const unsigned long long pay = DIM == 2 ? (((unsigned long long)a << 16) | b)
+                                            : (((unsigned long long)a << 21) | ((unsigned long long)b << 10) | c);
+    return (cost << 32) | pay;
+}
+template <int DIM>
+__device__ __forceinline__ void key_counts(unsigned long long key, unsigned& a, unsigned& b, unsigned& c) {
+    if (DIM == 2) { a = (unsigned)(key >> 16) & 0xffffu; b = (unsigned)key & 0xffffu; c = 0; }
+    else { a = (unsigned)(key >> 21) & 0x7ffu; b = (unsigned)(key >> 10) & 0x7ffu; c = (unsigned)key & 0x3ffu; }
 }
 
+template <int DIM>
 __global__ void __launch_bounds__(kNT, 1) grid_path_kernel(const GridPathArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* grid = reinterpret_cast<uint32_t*>(smem_raw);                 // [words_per_map] (padded to 4)
     uint32_t* q = grid + ((a.words_per_map + 3) & ~3);                      // [3][kQCap]
     __shared__ int cnt[3], ovf[3], s_task, s_state;
     const int tid = threadIdx.x;
-    const int cells = a.H * a.W;
+    const int S12 = a.S1 * a.S2;
+    const int cells = a.S0 * S12;
     unsigned long long* dist = a.work + (size_t)blockIdx.x * cells;
-    auto is_free = [&](int y, int x) -> bool {
-        const int i = y * a.W + x;
-        return (grid[i >> 5] >> (i & 31)) & 1u;
-    };
+    auto is_free = [&](int i) -> bool { return (grid[i >> 5] >> (i & 31)) & 1u; };
     int cur_map = -1;
     for (;;) {
         __syncthreads();
@@ -73,11 +85,16 @@ __global__ void __launch_bounds__(kNT, 1) grid_path_kernel(const GridPathArgs a)
             cur_map = map;
         }
         for (int i = tid; i < cells; i += kNT) dist[i] = kInf;
-        const int sy = a.starts[task * 2], sx = a.starts[task * 2 + 1], gy = a.goals[task * 2], gx = a.goals[task * 2 + 1];
-        const int s = sy * a.W + sx, g = gy * a.W + gx;
+        int s = 0, g = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            const int stride = d == 0 ? S12 : (d == 1 ? a.S2 : 1);
+            s += a.starts[task * DIM + d] * (DIM == 2 ? (d == 0 ? a.S1 : 1) : stride);
+            g += a.goals[task * DIM + d] * (DIM == 2 ? (d == 0 ? a.S1 : 1) : stride);
+        }
         if (tid < 3) { cnt[tid] = 0; ovf[tid] = 0; }
         __syncthreads();
-        if (tid == 0) { dist[s] = make_key(0, 0); q[0] = (uint32_t)s; cnt[0] = 1; s_state = 0; }
+        if (tid == 0) { dist[s] = make_key<DIM>(0, 0, 0); q[0] = (uint32_t)s; cnt[0] = 1; s_state = 0; }
         __syncthreads();
         for (int k = 0; k < 4095; ++k) {
             const int cur = k % 3;
@@ -87,37 +104,50 @@ __global__ void __launch_bounds__(kNT, 1) grid_path_kernel(const GridPathArgs a)
                 const int u = scan ? i : (int)q[cur * kQCap + i];
                 const unsigned long long key = __ldcg(dist + u);  // labels are updated by L2 atomics: never read them through L1
                 if (key == kInf || (int)(key >> 52) != k) continue;  // stale entry: the node moved to an earlier bucket
-                const unsigned na0 = (unsigned)(key >> 16) & 0xffffu, nb0 = (unsigned)key & 0xffffu;
-                const int y = u / a.W, x = u - y * a.W;
+                unsigned n1, n2, n3;
+                key_counts<DIM>(key, n1, n2, n3);
+                // coordinates along the array axes; 2D: (c0, c1) = (y, x) on an (S0, S1) grid, c2 = 0
+                const int c0 = u / S12, r = u - c0 * S12;
+                const int c1 = DIM == 2 ? r : r / a.S2, c2 = DIM == 2 ? 0 : r - c1 * a.S2;
+                const int st1 = DIM == 2 ? 1 : a.S2;
 #pragma unroll
-                for (int dy = -1; dy <= 1; ++dy)
+                for (int d0 = -1; d0 <= 1; ++d0)
 #pragma unroll
-                    for (int dx = -1; dx <= 1; ++dx) {
-                        if (dy == 0 && dx == 0) continue;
-                        const int yy = y + dy, xx = x + dx;
-                        if (yy < 0 || yy >= a.H || xx < 0 || xx >= a.W || !is_free(yy, xx)) continue;
-                        const bool diag = dy != 0 && dx != 0;
-                        if (diag && (!is_free(yy, x) || !is_free(y, xx))) continue;  // no corner cutting
-                        const unsigned long long nk = make_key(na0 + (diag ? 0u : 1u), nb0 + (diag ? 1u : 0u));
-                        const int v = yy * a.W + xx;
-                        if (nk < __ldcg(dist + v)) {  // cheap pre-test: most neighbours are already labelled better
-                            const unsigned long long old = atomicMin(dist + v, nk);
-                            if (nk < old) {
-                                const int bkt = (int)(nk >> 52) % 3;
-                                const int pos = atomicAdd(&cnt[bkt], 1);
-                                if (pos < kQCap) q[bkt * kQCap + pos] = (uint32_t)v;
-                                else ovf[bkt] = 1;
+                    for (int d1 = -1; d1 <= 1; ++d1)
+#pragma unroll
+                        for (int d2 = (DIM == 3 ? -1 : 0); d2 <= (DIM == 3 ? 1 : 0); ++d2) {
+                            const int nz = (d0 != 0) + (d1 != 0) + (d2 != 0);
+                            if (nz == 0) continue;
+                            const int e0 = c0 + d0, e1 = c1 + d1, e2 = c2 + d2;
+                            if (e0 < 0 || e0 >= a.S0 || e1 < 0 || e1 >= a.S1 || e2 < 0 || e2 >= a.S2) continue;
+                            const int v = e0 * S12 + e1 * st1 + e2;
+                            if (!is_free(v)) continue;
+                            if (DIM == 2) {  // no corner cutting: both orthogonal neighbours of a diagonal step are free
+                                if (nz == 2 && (!is_free(e0 * S12 + c1) || !is_free(c0 * S12 + e1))) continue;
+                            } else {         // all three axis-projected cells are free (zero offset: the current cell)
+                                if (!is_free(e0 * S12 + c1 * st1 + c2) || !is_free(c0 * S12 + e1 * st1 + c2) ||
+                                    !is_free(c0 * S12 + c1 * st1 + e2))
+                                    continue;
+                            }
+                            const unsigned long long nk = make_key<DIM>(n1 + (nz == 1), n2 + (nz == 2), n3 + (nz == 3));
+                            if (nk < __ldcg(dist + v)) {  // cheap pre-test: most neighbours are already labelled better
+                                const unsigned long long old = atomicMin(dist + v, nk);
+                                if (nk < old) {
+                                    const int bkt = (int)(nk >> 52) % 3;
+                                    const int pos = atomicAdd(&cnt[bkt], 1);
+                                    if (pos < kQCap) q[bkt * kQCap + pos] = (uint32_t)v;
+                                    else ovf[bkt] = 1;
+                                }
                             }
                         }
-                    }
             }
             __syncthreads();
             if (tid == 0) {
                 const unsigned long long gk = __ldcg(dist + g);
-                const int n1 = (k + 1) % 3, n2 = (k + 2) % 3;
+                const int q1 = (k + 1) % 3, q2 = (k + 2) % 3;
                 cnt[cur] = 0; ovf[cur] = 0;
                 if (gk != kInf && (int)(gk >> 52) <= k) s_state = 1;                                 // goal label final
-                else if (cnt[n1] == 0 && cnt[n2] == 0 && !ovf[n1] && !ovf[n2]) s_state = 2;          // nothing left: no path
+                else if (cnt[q1] == 0 && cnt[q2] == 0 && !ovf[q1] && !ovf[q2]) s_state = 2;          // nothing left: no path
             }
             __syncthreads();
             if (s_state) break;
@@ -125,11 +155,12 @@ __global__ void __launch_bounds__(kNT, 1) grid_path_kernel(const GridPathArgs a)
         if (tid == 0) {
             const unsigned long long gk = __ldcg(dist + g);
             if (s_state == 1 && gk != kInf) {
-                const int na = (int)((gk >> 16) & 0xffffu), nb = (int)(gk & 0xffffu);
-                a.n_straight[task] = na; a.n_diag[task] = nb;
-                a.length[task] = (double)na + (double)nb * 1.4142135623730951;
+                unsigned n1, n2, n3;
+                key_counts<DIM>(gk, n1, n2, n3);
+                a.n_steps[task * 3] = (int)n1; a.n_steps[task * 3 + 1] = (int)n2; a.n_steps[task * 3 + 2] = (int)n3;
+                a.length[task] = (double)n1 + (double)n2 * 1.4142135623730951 + (double)n3 * 1.7320508075688772;
             } else {
-                a.n_straight[task] = -1; a.n_diag[task] = -1;
+                a.n_steps[task * 3] = a.n_steps[task * 3 + 1] = a.n_steps[task * 3 + 2] = -1;
                 a.length[task] = nan("");
             }
         }
@@ -138,22 +169,32 @@ __global__ void __launch_bounds__(kNT, 1) grid_path_kernel(const GridPathArgs a)
 
 }  // namespace
 
-extern "C" int nrrt_grid_paths_2d(const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map, const int32_t* starts,
-                                  const int32_t* goals, int B, int H, int W, void* work, int n_slots, int32_t* queue,
-                                  int32_t* n_straight, int32_t* n_diag, double* length, void* stream) {
-    NRRT_REQUIRE(occ_bits && task_to_map && starts && goals && work && queue && n_straight && n_diag && length, "null pointer");
-    NRRT_REQUIRE(B >= 0 && H >= 1 && W >= 1 && H <= 2048 && W <= 2048 && words_per_map * 32 >= H * W, "bad grid shape");
+extern "C" int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map,
+                               const int32_t* starts, const int32_t* goals, int B, int s0, int s1, int s2, void* work, int n_slots,
+                               int32_t* queue, int32_t* n_steps, double* length, void* stream) {
+    NRRT_REQUIRE(occ_bits && task_to_map && starts && goals && work && queue && n_steps && length, "null pointer");
+    NRRT_REQUIRE(dims == 2 || dims == 3, "dims must be 2 or 3");
+    if (dims == 2) s2 = 1;
+    NRRT_REQUIRE(B >= 0 && s0 >= 1 && s1 >= 1 && s2 >= 1 && s0 <= 2048 && s1 <= 2048 && s2 <= 2048 &&
+                     (long long)words_per_map * 32 >= (long long)s0 * s1 * s2 && (long long)s0 * s1 * s2 < (1ll << 30),
+                 "bad grid shape");
     NRRT_REQUIRE(n_slots >= 1, "need at least one work slot");
     if (B == 0) return NRRT_OK;
     const size_t smem = (size_t)((words_per_map + 3) & ~3) * 4 + (size_t)3 * kQCap * 4;
     NRRT_REQUIRE(smem <= 227 * 1024, "grid too large for shared memory (%zu bytes)", smem);
-    NRRT_CUDA_TRY(cudaFuncSetAttribute(grid_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     GridPathArgs a;
     a.occ_bits = occ_bits; a.words_per_map = words_per_map; a.task_to_map = task_to_map; a.starts = starts; a.goals = goals;
-    a.B = B; a.H = H; a.W = W; a.work = (unsigned long long*)work; a.queue = queue;
-    a.n_straight = n_straight; a.n_diag = n_diag; a.length = length;
+    a.B = B; a.S0 = s0; a.S1 = s1; a.S2 = s2; a.work = (unsigned long long*)work; a.queue = queue;
+    a.n_steps = n_steps; a.length = length;
     const int grid = n_slots < B ? n_slots : B;
-    grid_path_kernel<<<grid, kNT, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dims == 2) {
+        NRRT_CUDA_TRY(cudaFuncSetAttribute(grid_path_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        grid_path_kernel<2><<<grid, kNT, smem, st>>>(a);
+    } else {
+        NRRT_CUDA_TRY(cudaFuncSetAttribute(grid_path_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        grid_path_kernel<3><<<grid, kNT, smem, st>>>(a);
+    }
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

@@ -235,32 +235,34 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
 
 
 def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape: Sequence[int], n_slots: Optional[int] = None):
-    """Shortest 8-connected grid path of every task = the reference's A* (generate_paths.py:11-74): its path length column
-    (test_network_and_algorithms.py:148-183) and its task filter (no path -> the task is deleted, generate_paths.py:111-113).
-    2D; occ_bits from pack_occupancy, starts / goals [B, 2] = (y, x).  Returns (length fp64 [B] (NaN = no path),
-    n_straight int32 [B], n_diagonal int32 [B]) on the device; length = n_straight + n_diagonal * sqrt(2)."""
+    """Shortest grid path of every task = the reference's A* (generate_paths.py:11-74, ThreeD_generate_paths.py:14-97): its
+    path length column (test_network_and_algorithms.py:58-70) and its task filter (no path -> the task is deleted,
+    generate_paths.py:111-113).  occ_bits from pack_occupancy; starts / goals [B, dim] in array-axis order ((y, x) / (x, y, z)).
+    Returns (length fp64 [B] (NaN = no path), n_steps int32 [B, 3] = steps of cost 1, sqrt(2), sqrt(3), -1 = no path) on
+    the device; length = n_steps . (1, sqrt(2), sqrt(3))."""
     lib = _lib.load()
     dev = occ_bits.device
     if dev.type != "cuda":
         raise _lib.NrrtError("grid_path_lengths needs CUDA tensors: there is no CPU fallback")
-    if len(shape) != 2:
-        raise ValueError("grid_path_lengths is 2D (generate_paths.py); the 3D twin is not built")
-    H, W = int(shape[0]), int(shape[1])
+    dim = len(shape)
+    if dim not in (2, 3):
+        raise ValueError("shape must be (H, W) or (X, Y, Z)")
     t2m = _dev(task_to_map, torch.int32, dev).reshape(-1)
-    st = _dev(starts, torch.int32, dev).reshape(-1, 2).contiguous()
-    gl = _dev(goals, torch.int32, dev).reshape(-1, 2).contiguous()
+    st = _dev(starts, torch.int32, dev).reshape(-1, dim).contiguous()
+    gl = _dev(goals, torch.int32, dev).reshape(-1, dim).contiguous()
     B = t2m.shape[0]
+    cells = int(np.prod(shape))
     n_slots = n_slots or torch.cuda.get_device_properties(dev).multi_processor_count
-    work = torch.empty((max(min(n_slots, B), 1), H * W), dtype=torch.int64, device=dev)
+    work = torch.empty((max(min(n_slots, B), 1), cells), dtype=torch.int64, device=dev)
     queue = torch.zeros(1, dtype=torch.int32, device=dev)
-    ns = torch.empty(B, dtype=torch.int32, device=dev)
-    nd = torch.empty(B, dtype=torch.int32, device=dev)
+    steps = torch.empty((B, 3), dtype=torch.int32, device=dev)
     length = torch.empty(B, dtype=torch.float64, device=dev)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.count_launch()
-    check(lib.nrrt_grid_paths_2d(_ptr(occ_bits), occ_bits.shape[1], _ptr(t2m), _ptr(st), _ptr(gl), B, H, W, _ptr(work),
-                                 work.shape[0], _ptr(queue), _ptr(ns), _ptr(nd), _ptr(length), stream))
-    return length, ns, nd
+    s = [int(v) for v in shape] + [1]
+    check(lib.nrrt_grid_paths(dim, _ptr(occ_bits), occ_bits.shape[1], _ptr(t2m), _ptr(st), _ptr(gl), B, s[0], s[1], s[2],
+                              _ptr(work), work.shape[0], _ptr(queue), _ptr(steps), _ptr(length), stream))
+    return length, steps
 
 
 class GuidedPlanner(object):

@@ -6,9 +6,9 @@ Differences by design: tasks come from this package's generate_maps / generate_t
 private evaluation set), the model is whatever the caller passes (random-init by default: no trained weights ship with
 the reference), and `Time` is the batch's wall time divided by the number of tasks (the GPU plans thousands of tasks at
 once; there is no per-task timer to read).  Length is calculate_length(path) (test_network_and_algorithms.py:52-56),
-Iterations the planner's iteration_no.  The A* columns (2D; astar_pathfinding, test_network_and_algorithms.py:58-70) come
-from engine.grid_path_lengths: the length of the reference's A* path (a shortest path) for every task at once, NaN where
-the reference's astar returns None; its Iterations column is '-' as in the reference.  3D: A* is not built ('-').
+Iterations the planner's iteration_no.  The A* columns (astar_pathfinding, test_network_and_algorithms.py:58-70) come from
+engine.grid_path_lengths: the length of the reference's A* path (a shortest path) for every task at once, NaN where the
+reference's astar returns None; its Iterations column is '-' as in the reference.
 """
 from time import perf_counter
 
@@ -45,11 +45,12 @@ def _timed(fn, device):
 
 
 def astar_pathfinding(wl, device):
-    """astar(occ_map_gray, start, finish) + calculate_length for every task (test_network_and_algorithms.py:58-70), 2D."""
+    """astar(occ_map_gray, start, finish) + calculate_length for every task (test_network_and_algorithms.py:58-70; 3D twin:
+    ThreeD_generate_paths.astar)."""
     occ = torch.from_numpy(wl.occ_maps).to(device)
-    bits = engine.pack_occupancy(occ, 2, device)
+    bits = engine.pack_occupancy(occ, wl.dim, device)
     engine.grid_path_lengths(bits, wl.task_to_map[:1], wl.starts[:1], wl.goals[:1], wl.shape)  # warm-up
-    secs, (length, _, _) = _timed(lambda: engine.grid_path_lengths(bits, wl.task_to_map, wl.starts, wl.goals, wl.shape), device)
+    secs, (length, _) = _timed(lambda: engine.grid_path_lengths(bits, wl.task_to_map, wl.starts, wl.goals, wl.shape), device)
     return secs, length
 
 
@@ -85,10 +86,9 @@ def main(n_tasks=1000, three_d=False, model=None, device="cuda:0", seed=0):
     columns = pd.MultiIndex.from_product([["A*", "RRT*", "Neural+RRT*"], ["Time", "Length", "Iterations"]])
     df = pd.DataFrame(index=range(n), columns=columns)
     df[("A*", "Time")] = df[("A*", "Length")] = df[("A*", "Iterations")] = "-"
-    if not three_d:
-        secs, length = astar_pathfinding(wl, device)
-        df[("A*", "Time")] = secs / n
-        df[("A*", "Length")] = length.cpu().numpy()
+    secs, length = astar_pathfinding(wl, device)
+    df[("A*", "Time")] = secs / n
+    df[("A*", "Length")] = length.cpu().numpy()
     for name, (secs, res) in (("RRT*", rrt_star_pathfinding(wl, device, seed)),
                               ("Neural+RRT*", neural_rrt_star_pathfinding(model, wl, device, seed))):
         df[(name, "Time")] = secs / n

@@ -70,10 +70,63 @@ def astar(image, start, finish):  # generate_paths.py:11-42
     return None
 
 
+def _neighbors3d(pos, img):  # ThreeD_generate_paths.py:47-76, quirks included
+    height, width, depth = img.shape
+    result = []
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                # the reference compares the OFFSETS with 255 (`dx == 255`, `dx != 255`): never / always true.  So the zero
+                # move is not skipped (astar() drops it: the current cell is in the closed set), and EVERY move, axis moves
+                # included, needs the three axis-projected cells free -- a projection with a zero offset is the current cell
+                x, y, z = pos[0] + dx, pos[1] + dy, pos[2] + dz
+                if x < 0 or x >= height or y < 0 or y >= width or z < 0 or z >= depth:
+                    continue
+                if img[x, pos[1], pos[2]] == 255 or img[pos[0], y, pos[2]] == 255 or img[pos[0], pos[1], z] == 255:
+                    continue
+                if img[x, y, z] != 255:
+                    result.append((x, y, z))
+    return result
+
+
+def _cost3d(a, b):  # ThreeD_generate_paths.py:83-97
+    n = (abs(a[0] - b[0]) == 1) + (abs(a[1] - b[1]) == 1) + (abs(a[2] - b[2]) == 1)
+    return math.sqrt(3) if n == 3 else (math.sqrt(2) if n == 2 else 1.0)
+
+
+def astar3d(image, start, finish):  # ThreeD_generate_paths.py:14-44 (obstacle = 255, anything else is free)
+    img = np.array(image)
+    start, finish = tuple(int(v) for v in start), tuple(int(v) for v in finish)
+    h3 = lambda a, b: math.sqrt((a[0] - b[0]) ** 2 + (a[1] - b[1]) ** 2 + (a[2] - b[2]) ** 2)  # noqa: E731  (:79-80)
+    open_list, closed, parent = [], set(), {}
+    g = {start: 0}
+    heapq.heappush(open_list, (h3(start, finish), start))
+    while open_list:
+        current = heapq.heappop(open_list)[1]
+        if current == finish:
+            path = []
+            while current in parent:
+                path.append(current)
+                current = parent[current]
+            path.append(start)
+            path.reverse()
+            return path
+        closed.add(current)
+        for nb in _neighbors3d(current, img):
+            if nb in closed or img[nb] == 255:
+                continue
+            cand = g[current] + _cost3d(current, nb)
+            if nb not in g or cand < g[nb]:
+                parent[nb] = current
+                g[nb] = cand
+                heapq.heappush(open_list, (cand + h3(nb, finish), nb))
+    return None
+
+
 def path_length(path):  # test_network_and_algorithms.py:52-56 (scipy's euclidean == sqrt(sum of squares) for these steps)
     length = 0  # sequential +=, as the reference (CPython's sum() of floats is compensated since 3.12: not the same bits)
     for a, b in zip(path[:-1], path[1:]):
-        length += math.sqrt((a[0] - b[0]) ** 2 + (a[1] - b[1]) ** 2)
+        length += math.sqrt(sum((p - q) ** 2 for p, q in zip(a, b)))
     return float(length)
 
 

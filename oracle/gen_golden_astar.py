@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE. Golden A* paths from the UNMODIFIED reference (generate_paths.py:11-74) for tests/golden/astar2d.npz.
+"""TEST INFRASTRUCTURE. Golden A* paths from the UNMODIFIED reference (generate_paths.py:11-74, ThreeD_generate_paths.py:14-97)
+for tests/golden/astar2d.npz and astar3d.npz.
 
 Run in the authoring container only (needs /root/reference):   python oracle/gen_golden_astar.py
 Cases: the 20 tasks of the two 512x512 maps of tests/golden/maps_tasks.npz (generate_maps / generate_tasks output of the
@@ -18,8 +19,11 @@ sys.path.insert(0, _HERE)
 from gen_golden import GOLDEN, parse_name_2d, save  # noqa: E402
 
 
-def load_reference_astar():
-    spec = importlib.util.spec_from_file_location("_ref_generate_paths", "/root/reference/generate_paths.py")
+def load_reference_astar(fname="generate_paths.py"):
+    shim = os.path.join(_HERE, "ref_shim")  # no-op matplotlib etc. (the 3D file imports pyplot at module scope)
+    if shim not in sys.path:
+        sys.path.insert(0, shim)
+    spec = importlib.util.spec_from_file_location("_ref_" + fname[:-3], "/root/reference/" + fname)
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.astar
@@ -82,5 +86,44 @@ def main():
     save("astar2d", n_cases=np.array(len(cases)), **out)
 
 
+def main3d():
+    """3D: a few tasks of the two generated 80^3 maps (the reference's Python A* needs minutes on the long ones, so the three
+    shortest of each map) + random 16^3 mazes + a walled-in goal.  Maps hold {0 = free, 255 = obstacle}."""
+    from gen_golden import parse_name_3d
+    astar = load_reference_astar("ThreeD_generate_paths.py")
+    mt = dict(np.load(os.path.join(GOLDEN, "maps_tasks.npz"), allow_pickle=False))
+    cases = []
+    for mi in (0, 1):
+        occ = mt[f"occ3d_{mi}"]
+        tasks = sorted((parse_name_3d(str(n)) for n in mt[f"names3d_{mi}"]),
+                       key=lambda sg: sum((a - b) ** 2 for a, b in zip(*sg)))
+        cases += [(occ, s, g) for s, g in tasks[:3]]
+    rng = np.random.default_rng(5)
+    for dens in (0.2, 0.35, 0.45, 0.2, 0.35, 0.45):
+        m = (rng.random((16, 16, 16)) < dens).astype(np.uint8) * 255
+        free = np.argwhere(m == 0)
+        s, g = free[rng.integers(len(free))], free[rng.integers(len(free))]
+        cases.append((m, tuple(int(v) for v in s), tuple(int(v) for v in g)))
+    m = np.zeros((10, 10, 10), np.uint8)
+    m[3:8, 3:8, 3:8] = 255
+    m[5, 5, 5] = 0                                   # free pocket inside a solid block: unreachable
+    cases.append((m, (0, 0, 0), (5, 5, 5)))
+    cases.append((np.zeros((6, 6, 6), np.uint8), (2, 2, 2), (2, 2, 2)))
+    out = {}
+    for i, (occ, s, g) in enumerate(cases):
+        path = astar(occ, tuple(s), tuple(g))
+        out[f"occ_{i}"] = occ
+        out[f"start_{i}"] = np.array(s, np.int32)
+        out[f"goal_{i}"] = np.array(g, np.int32)
+        out[f"reached_{i}"] = np.array(path is not None)
+        out[f"path_{i}"] = np.array(path if path else np.zeros((0, 3)), np.int32).reshape(-1, 3)
+        out[f"length_{i}"] = np.array(float(calculate_length(path)) if path else np.nan)
+        print(i, occ.shape, s, g, "len", out[f"length_{i}"], "points", len(out[f"path_{i}"]), flush=True)
+    save("astar3d", n_cases=np.array(len(cases)), **out)
+
+
 if __name__ == "__main__":
-    main()
+    if "--3d" in sys.argv:
+        main3d()
+    else:
+        main()

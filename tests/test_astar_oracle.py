@@ -29,3 +29,15 @@ def test_shortest_path_step_counts_give_the_astar_length():
             assert ns[gy, gx] < 0
             continue
         assert abs(ns[gy, gx] + nd[gy, gx] * np.sqrt(2) - float(g[f"length_{i}"])) <= 1e-9 * max(1.0, float(g[f"length_{i}"]))
+
+
+def test_astar3d_restatement_reproduces_the_reference_paths():
+    """3D twin (ThreeD_generate_paths.py:14-97), including its `== 255` offset comparisons (oracle/astar_oracle.py)."""
+    g = H.load("astar3d")
+    for i in range(int(g["n_cases"])):
+        path = ao.astar3d(g[f"occ_{i}"], g[f"start_{i}"], g[f"goal_{i}"])
+        if not bool(g[f"reached_{i}"]):
+            assert path is None
+            continue
+        assert np.array_equal(np.array(path, np.int32).reshape(-1, 3), g[f"path_{i}"]), f"case {i}"
+        assert abs(ao.path_length(path) - float(g[f"length_{i}"])) <= 1e-12 * max(1.0, float(g[f"length_{i}"]))
