@@ -64,7 +64,10 @@ def conv_traffic():
         return None, "no ncu capture committed"
     with open(path) as f:
         t = json.load(f)
-    return t["avg_dram_bytes_per_launch"], t["note"]
+    note = t["note"]
+    if "algorithmic_bytes_per_launch" in t:
+        note += "; algorithmic bytes of the same launches: %.0f per launch (%s)" % (t["algorithmic_bytes_per_launch"], t["algorithmic_note"])
+    return t["avg_dram_bytes_per_launch"], note
 
 
 class ClockSampler(object):
@@ -307,7 +310,8 @@ def run_graft(args):
             roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel / conv_halo2_kernel (tcgen05 implicit-GEMM convolution, every "
                                                      "layer shape of the forward)",
                         "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                        "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["which"], "launches_timed": n_l,
+                        "traffic": traffic, "traffic_note": traffic_note,
+                        "algorithmic_bytes_per_launch_avg": (sum(prof.bytes) / max(len(prof.bytes), 1)), "peak_source": pk["which"], "launches_timed": n_l,
                         "avg_launch_ms": t_ms / max(n_l, 1), "flops_per_launch_avg": fl / max(n_l, 1),
                         "step_share": {"cnn_ms": stage[0], "cdf_ms": stage[1], "draw_plan_ms": stage[2]}}  # last timed step
             if args.layer_table:

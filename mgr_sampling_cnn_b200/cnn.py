@@ -36,10 +36,11 @@ class ConvProfiler(object):
         self.active = False
         self.records = []  # (flops, start_event, end_event)
         self.names = []
+        self.bytes = []    # algorithmic DRAM bytes of each recorded launch (inputs + weights + residual rows + outputs, once)
 
     class _Ctx(object):
-        def __init__(self, prof, flops, name=None):
-            self.prof, self.flops, self.name = prof, flops, name
+        def __init__(self, prof, flops, name=None, nbytes=0.0):
+            self.prof, self.flops, self.name, self.nbytes = prof, flops, name, nbytes
 
         def __enter__(self):
             self.a = torch.cuda.Event(enable_timing=True)
@@ -50,9 +51,10 @@ class ConvProfiler(object):
             self.b.record()
             self.prof.records.append((self.flops, self.a, self.b))
             self.prof.names.append(self.name)
+            self.prof.bytes.append(self.nbytes)
 
-    def launch(self, flops, name=None):
-        return ConvProfiler._Ctx(self, flops, name)
+    def launch(self, flops, name=None, nbytes=0.0):
+        return ConvProfiler._Ctx(self, flops, name, nbytes)
 
     def by_layer(self):
         """{layer name: (launches, flops, milliseconds)} of everything recorded so far; call after a synchronize."""
@@ -153,6 +155,21 @@ class _Layer(object):
         taps = (3 ** self.dims) if self.kind in (K3S1, K3S2) else 1
         return 2.0 * batch * _prod([(g - 1) // stride + 1 for g in sp]) * self.cout * taps * self.cin_real
 
+    def algorithmic_bytes(self, n, grid, x, x2, res, head):
+        """Bytes one launch has to move if every operand crossed DRAM exactly once: the distinct input samples (per-map
+        sources count once per map), the packed weights, the distinct residual rows, the stored output (or fp32 logits)."""
+        sp_in = _prod([g for i, g in enumerate(grid) if self.dims == 3 or i > 0])
+        up = 2 ** self.dims if self.kind in (CONVT, UPFOLD) else 1
+        stride = 2 if self.kind in (K3S2, K1S2) else 1
+        sp_out = _prod([(g - 1) // stride + 1 for i, g in enumerate(grid) if self.dims == 3 or i > 0]) * up
+        b = 2.0 * min(n, x.shape[0]) * sp_in * self.cin + 2.0 * self.weight.numel()
+        if x2 is not None:
+            b += 2.0 * min(n, x2.shape[0]) * sp_in * self.cin2
+        if res is not None:
+            b += 2.0 * min(n, res.shape[0]) * sp_out * self.cout
+        b += (4.0 * n * sp_out) if head is not None else (2.0 * n * sp_out * self.cout)
+        return b
+
     force_per_tap = False  # tests: run the generic per-tap kernel where the slab kernel would be chosen
     no_poly_mma = False    # tests: evaluate the whole polynomial term in the epilogue
     no_tma_store = False   # tests: direct global stores instead of the staged TMA-store epilogue
@@ -171,7 +188,7 @@ class _Layer(object):
         args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx, res_group, poly3)
         prof = self.profiler
         if prof is not None and prof.active:
-            with prof.launch(self.flops(n, grid), getattr(self, "name", None)):
+            with prof.launch(self.flops(n, grid), getattr(self, "name", None), self.algorithmic_bytes(n, grid, x, x2, res, head)):
                 self._run(*args)
         else:
             self._run(*args)

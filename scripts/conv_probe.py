@@ -25,7 +25,11 @@ coords = torch.from_numpy(wl.coords).to(dev)
 grid = (1, 512, 512)
 maps = torch.arange(8, dtype=torch.int32, device=dev)
 prep = plan.coords_prepare(coords, grid)
+prof.active = True
 enc = plan.encode(grid, 8, occ=occ, maps=maps)
+prof.active = False
+enc_bytes, enc_launches = sum(prof.bytes), len(prof.bytes)
+prof.records.clear(); prof.names.clear(); prof.bytes.clear()
 logits = torch.empty((10, 512 * 512), dtype=torch.float32, device=dev)
 for it in range(n_dec):
     prof.active = it >= max(n_dec - 4, 1)
@@ -35,6 +39,10 @@ for it in range(n_dec):
 torch.cuda.synchronize()
 for name, (n, fl, ms) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
     print(f"{name:10s} {ms / n:8.4f} ms  {fl / max(ms, 1e-9) / 1e9:8.1f} TFLOP/s")
+n_prof = max(n_dec - max(n_dec - 4, 1), 1)  # decode passes recorded
+dec_bytes, dec_launches = sum(prof.bytes) / n_prof, len(prof.bytes) // n_prof
+print(f"algorithmic DRAM bytes of one encoder pass (8 maps) + one decoder micro-batch (10 tasks): "
+      f"{(enc_bytes + dec_bytes) / (enc_launches + dec_launches):.0f} per launch over {enc_launches + dec_launches} launches")
 
 if plan.use_fold(grid):  # the decomposition below times the unfolded conv7.0 / conv8.0
     sys.exit(0)
