@@ -17,8 +17,7 @@
 // cell, 2 MB at 512^2 / 4 MB at 80^3: L2-resident) as one 64-bit word  [cost in 12.20 fixed point | step counts: 16 + 16
 // bits in 2D, 11 + 11 + 10 in 3D] updated with atomicMin: the fixed-point cost n1 * 2^20 + n2 * round(sqrt(2) * 2^20)
 // + n3 * round(sqrt(3) * 2^20) is an exact integer function of the counts, orders candidates, and carries them with it.  The occupancy grid is staged in shared memory (bit-packed, as
-// in the planner).  A queue overflow (12288 entries per bucket: not seen at 512^2, possible for wide 3D fronts) degrades that bucket to a
-// scan of all cells.
+// in the planner).  A queue overflow degrades that bucket to a scan of all cells.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -28,8 +27,10 @@
 
 namespace {
 
-constexpr int kNT = 512;
-constexpr int kQCap = 12288;
+// 2D (512^2: 32 KB grid): 256 threads and 6144-entry queues = 104 KB, two CTAs per SM -- the kernel is barrier / latency
+// bound (ncu: 62 % of stall samples at the two block barriers of a bucket step, issue slots 7 % busy), so tasks in flight
+// per SM is what buys throughput.  3D (80^3: 64 KB grid, wide fronts): 512 threads, 12288-entry queues, one CTA per SM.
+template <int DIM> struct GP { static constexpr int NT = DIM == 2 ? 256 : 512, QCAP = DIM == 2 ? 6144 : 12288, PER_SM = DIM == 2 ? 2 : 1; };
 constexpr unsigned long long kInf = ~0ull;
 constexpr unsigned long long kK1 = 1ull << 20;   // 1.0
 constexpr unsigned long long kK2 = 1482910ull;   // round(sqrt(2) * 2^20)
@@ -62,7 +63,8 @@ __device__ __forceinline__ void key_counts(unsigned long long key, unsigned& a, 
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(kNT, 1) grid_path_kernel(const GridPathArgs a) {
+__global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel(const GridPathArgs a) {
+    constexpr int kNT = GP<DIM>::NT, kQCap = GP<DIM>::QCAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* grid = reinterpret_cast<uint32_t*>(smem_raw);                 // [words_per_map] (padded to 4)
     uint32_t* q = grid + ((a.words_per_map + 3) & ~3);                      // [3][kQCap]
@@ -180,7 +182,7 @@ extern "C" int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per
                  "bad grid shape");
     NRRT_REQUIRE(n_slots >= 1, "need at least one work slot");
     if (B == 0) return NRRT_OK;
-    const size_t smem = (size_t)((words_per_map + 3) & ~3) * 4 + (size_t)3 * kQCap * 4;
+    const size_t smem = (size_t)((words_per_map + 3) & ~3) * 4 + (size_t)3 * (dims == 2 ? GP<2>::QCAP : GP<3>::QCAP) * 4;
     NRRT_REQUIRE(smem <= 227 * 1024, "grid too large for shared memory (%zu bytes)", smem);
     GridPathArgs a;
     a.occ_bits = occ_bits; a.words_per_map = words_per_map; a.task_to_map = task_to_map; a.starts = starts; a.goals = goals;
@@ -190,10 +192,10 @@ extern "C" int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (dims == 2) {
         NRRT_CUDA_TRY(cudaFuncSetAttribute(grid_path_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        grid_path_kernel<2><<<grid, kNT, smem, st>>>(a);
+        grid_path_kernel<2><<<grid, GP<2>::NT, smem, st>>>(a);
     } else {
         NRRT_CUDA_TRY(cudaFuncSetAttribute(grid_path_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        grid_path_kernel<3><<<grid, kNT, smem, st>>>(a);
+        grid_path_kernel<3><<<grid, GP<3>::NT, smem, st>>>(a);
     }
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;

@@ -252,7 +252,7 @@ def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape:
     gl = _dev(goals, torch.int32, dev).reshape(-1, dim).contiguous()
     B = t2m.shape[0]
     cells = int(np.prod(shape))
-    n_slots = n_slots or torch.cuda.get_device_properties(dev).multi_processor_count
+    n_slots = n_slots or torch.cuda.get_device_properties(dev).multi_processor_count * (2 if dim == 2 else 1)  # resident CTAs
     work = torch.empty((max(min(n_slots, B), 1), cells), dtype=torch.int64, device=dev)
     queue = torch.zeros(1, dtype=torch.int32, device=dev)
     steps = torch.empty((B, 3), dtype=torch.int32, device=dev)
