@@ -39,7 +39,10 @@ def parse_args():
     ap.add_argument("--tasks", type=int, default=None, help="tasks per GPU (default: 4096 for 2D, 1024 for 3D)")
     ap.add_argument("--ref-sample", type=int, default=None, help="tasks per step of the CPU arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--profile-every", type=int, default=16, help="time the conv launches of every n-th micro-batch")
+    ap.add_argument("--profile-every", type=int, default=5, help="bracket every n-th conv launch of the timed steps with CUDA events")
+    ap.add_argument("--no-sections", action="store_true", help="skip the secondary sections (2D uniform, 3D 1024, 3D sweep)")
+    ap.add_argument("--section-steps", type=int, default=2)
+    ap.add_argument("--sweep-tasks", type=int, default=4096, help="total tasks of the strong-scaling 3D section")
     ap.add_argument("--micro-batch", type=int, default=None, help="tasks per decoder launch (default: GuidedPlanner's)")
     ap.add_argument("--encoder-batch", type=int, default=None, help="distinct maps per encoder pass (default: GuidedPlanner's)")
     ap.add_argument("--layer-table", default=None, help="write the per-layer CUDA-event timings of the sampled launches (csv)")
@@ -188,9 +191,85 @@ def workload_name(w, tasks):
             "3d_uniform": f"3D uniform-sampling RRT* batch of {tasks} tasks"}[w]
 
 
+FLOPS_NOMINAL = {2: 821.91e9, 3: 2522.27e9}  # 2 x MACs of the 35 conv layers of one reference forward
+
+
+def _rank_workload(name, t0, t1):
+    """Tasks [t0, t1) of the global task list of a workload (task t = task t % 10 of map t // 10; map m is drawn with
+    random.seed(1000 + m), its tasks with random.seed(2000 + m): SURVEY 8(d)).  Returns (workload, global task ids)."""
+    from mgr_sampling_cnn_b200 import workload
+    per = 10
+    m0, m1 = t0 // per, (t1 - 1) // per
+    wl = (workload.make_2d if name.startswith("2d") else workload.make_3d)((m1 - m0 + 1) * per, first_map=m0)
+    lo, hi = t0 - m0 * per, t1 - m0 * per
+    maps_used, t2m = np.unique(wl.task_to_map[lo:hi], return_inverse=True)
+    wl2 = type(wl)(wl.dim, wl.shape, wl.occ_maps[maps_used], t2m.astype(np.int32), wl.starts[lo:hi], wl.goals[lo:hi],
+                   wl.coords[lo:hi], wl.filtered, wl.redrawn)
+    return wl2, np.arange(t0, t1, dtype=np.int32)
+
+
+class Arm(object):
+    """One workload resident on this rank's GPU + the callable that runs one step of the hot path over it."""
+
+    def __init__(self, name, wl, ids, dev, args, profile=False):
+        from mgr_sampling_cnn_b200 import cnn, engine
+        self.name, self.wl, self.dev, self.engine = name, wl, dev, engine
+        self.dim = wl.dim
+        self.uniform = name.endswith("uniform")
+        self.B = len(wl.task_to_map)
+        self.host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
+                     (("occ", wl.occ_maps), ("t2m", wl.task_to_map), ("starts", wl.starts), ("goals", wl.goals),
+                      ("coords", wl.coords), ("ids", ids))}
+        self.d = {k: v.to(dev) for k, v in self.host.items()}
+        self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
+        self.gp = self.prof = self.model = None
+        if not self.uniform:
+            self.model = make_model(self.dim, dev)
+            self.gp = engine.GuidedPlanner(self.model, self.dim, wl.shape, micro_batch=args.micro_batch)
+            if args.encoder_batch:
+                self.gp.encoder_batch = args.encoder_batch
+            if profile:
+                self.prof = cnn.ConvProfiler(args.profile_every)
+                self.model._plan(dev).set_profiler(self.prof)
+        else:
+            self.bits = engine.pack_occupancy(self.d["occ"], self.dim, dev)
+            self.bufs = engine.PlannerBuffers(self.dim, self.B, 5000, 512, False, 0, dev)
+        self.uni_events = []
+
+    def step(self, from_host=False, profile=False):
+        """One pass of the hot path; returns (records [B, 5] fp64 on the device: status, iterations, n_nodes, path points,
+        path length; PlanResult)."""
+        eng, dev = self.engine, self.dev
+        inp = {k: v.to(dev, non_blocking=True) for k, v in self.host.items()} if from_host else self.d
+        if self.uniform:
+            b = self.bits if not from_host else eng.pack_occupancy(inp["occ"], self.dim, dev)
+            ev = None
+            if profile:
+                ev = [torch.cuda.Event(enable_timing=True)]
+                ev[0].record()
+            res = eng.plan_batch(b, inp["t2m"], inp["starts"], inp["goals"], dim=self.dim, shape=self.wl.shape, seed=0,
+                                 task_ids=inp["ids"], buffers=self.bufs, events=ev)
+            if profile:
+                ev.append(torch.cuda.Event(enable_timing=True))
+                ev[-1].record()
+                self.uni_events = ev  # [start, between draw and plan, end]
+        else:
+            res = self.gp.plan(inp["occ"], inp["t2m"], inp["starts"], inp["goals"], inp["coords"], seed=0, task_ids=inp["ids"],
+                               record_events=profile)
+        rec = torch.stack([res.status.double(), res.iterations.double(), res.n_nodes.double(), res.path_n.double(),
+                           res.path_len], 1)
+        return rec, res
+
+    def stage_ms(self):
+        if self.uniform:
+            e = self.uni_events
+            return (0.0, 0.0, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])) if len(e) == 3 else (0.0,) * 4
+        return self.gp.stage_ms()
+
+
 def run_graft(args):
     import torch.distributed as dist
-    from mgr_sampling_cnn_b200 import _lib, cnn, engine
+    from mgr_sampling_cnn_b200 import _lib, sharding
 
     # rank 0 prints ONE JSON line: libraries that write to stdout (NCCL's version banner) go to stderr instead
     sys.stdout.flush()
@@ -206,51 +285,6 @@ def run_graft(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    dim = 2 if args.workload.startswith("2d") else 3
-    uniform = args.workload.endswith("uniform")
-    tasks = args.tasks or (4096 if dim == 2 else 1024)
-    wl = make_workload(args.workload, tasks, rank)
-    B = len(wl.task_to_map)
-
-    # host (pinned) and device copies of the inputs
-    host = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in
-            (("occ", wl.occ_maps), ("t2m", wl.task_to_map), ("starts", wl.starts), ("goals", wl.goals), ("coords", wl.coords))}
-    d = {k: v.to(dev) for k, v in host.items()}
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
-
-    model = gp = prof = None
-    if not uniform:
-        model = make_model(dim, dev)
-        gp = engine.GuidedPlanner(model, dim, wl.shape, micro_batch=args.micro_batch)
-        if args.encoder_batch:
-            gp.encoder_batch = args.encoder_batch
-        prof = cnn.ConvProfiler()
-        model._plan(dev).set_profiler(prof)
-    bits = engine.pack_occupancy(d["occ"], dim, dev)
-    bufs = engine.PlannerBuffers(dim, B, 5000, 512, False, 0, dev) if uniform else None
-    result_keys = ("status", "iterations", "n_nodes", "path_n", "path_len")
-    gather_buf = None
-
-    def step(inp, from_host, profile):
-        if from_host:
-            inp = {k: v.to(dev, non_blocking=True) for k, v in inp.items()}
-        if uniform:
-            b = bits if not from_host else engine.pack_occupancy(inp["occ"], dim, dev)
-            res = engine.plan_batch(b, inp["t2m"], inp["starts"], inp["goals"], dim=dim, shape=wl.shape, seed=0, buffers=bufs)
-        else:
-            gp.profile_every = args.profile_every if profile else 0
-            res = gp.plan(inp["occ"], inp["t2m"], inp["starts"], inp["goals"], inp["coords"], seed=0, record_events=profile)
-        # fixed-size result records; NCCL gather to rank 0 is the only collective of the path
-        rec = torch.stack([res.status.double(), res.iterations.double(), res.n_nodes.double(), res.path_n.double(),
-                           res.path_len], 1)
-        if world > 1:
-            nonlocal gather_buf
-            if gather_buf is None and rank == 0:
-                gather_buf = [torch.empty_like(rec) for _ in range(world)]
-            dist.gather(rec, gather_buf if rank == 0 else None, dst=0)
-        if from_host:
-            rec = rec.cpu()  # device -> host read of the step's results
-        return rec, res
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -258,88 +292,175 @@ def run_graft(args):
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 1)):
-        rec, res = step(d, False, False)
-    sync_all()
-    launches0 = _lib.launches
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run_arm(arm, gidx, n_global, steps, warmup, from_host=False, profile=False):
+        """warmup untimed + `steps` timed steps of `arm`, each followed by the path's only collective: the gather of this
+        rank's result records into rows `gidx` of the [n_global, 5] table on rank 0.  Returns (ms per step: max over
+        ranks, last table on rank 0, last PlanResult)."""
+        out = res = None
+
+        def one(prof):
+            nonlocal out, res
+            rec, res = arm.step(from_host, prof)
+            out = sharding.gather_records(rec, gidx, n_global, dst=0)
+            if from_host and out is not None:
+                out = out.cpu()  # device -> host read of the step's results
+        for _ in range(warmup):
+            one(False)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one(profile)
+        e1.record()
+        sync_all()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps, out, res
+
+    # ---- headline: args.workload, `tasks` per GPU, weak scaling (rank r owns global tasks [r B, (r + 1) B)) ----
+    dim = 2 if args.workload.startswith("2d") else 3
+    tasks = args.tasks or (4096 if dim == 2 else 1024)
+    per_rank = ((tasks + 9) // 10) * 10  # whole maps per rank; the last map of a rank is truncated to `tasks`
+    wl, ids = _rank_workload(args.workload, rank * per_rank, rank * per_rank + tasks)
+    arm = Arm(args.workload, wl, ids, dev, args, profile=True)
+    B = arm.B
+    gidx = torch.arange(rank * B, (rank + 1) * B, device=dev)
     clocks = ClockSampler(local)
+    run_arm(arm, gidx, world * B, 0, max(args.warmup, 1))
+    launches0 = _lib.launches
     if rank == 0:
         clocks.start()
-    stage = [0.0, 0.0, 0.0]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        rec, res = step(d, False, True)
-    e1.record()
-    sync_all()
-    ms = e0.elapsed_time(e1)
+    ms_step, _, res = run_arm(arm, gidx, world * B, args.steps, 0, profile=True)
     launches = _lib.launches - launches0
     clk = clocks.stop() if rank == 0 else None
-    if gp is not None:
-        stage = list(gp.stage_ms())
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max / 1e3)
-
+    stage = arm.stage_ms()
+    value = world * B / (ms_step / 1e3)
     # end to end through the public API with HOST buffers (pinned): H2D of the inputs + D2H of the results every step
-    step(host, True, False)
-    sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        rec_h, _ = step(host, True, False)
-    e1.record()
-    sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * args.steps / (float(t.item()) / 1e3)
-    d2h_bytes = rec_h.numel() * rec_h.element_size()
-
+    ms_e2e, rec_h, _ = run_arm(arm, gidx, world * B, args.steps, 1, from_host=True)
+    e2e_value = world * B / (ms_e2e / 1e3)
+    arm_h2d, arm_uniform = arm.h2d_bytes, arm.uniform
+    d2h_bytes = (rec_h.numel() * rec_h.element_size()) if rec_h is not None else 0
     status = res.status.cpu().numpy()
     iters = res.iterations.cpu().numpy()
+    n_draws = float(res.n_draws.sum().item()) if res.n_draws is not None else 0.0
+    pk = peaks()
+
+    roofline, kernels = None, {}
+    cells = int(np.prod(wl.shape))
+    if arm.prof is not None:
+        prof = arm.prof
+        n_l, fl, t_ms = prof.totals()
+        ach = fl / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0
+        traffic, traffic_note = conv_traffic()
+        fl_step = prof.flops_seen / max(args.steps, 1)   # FLOPs the conv kernels executed in one step (every launch counted)
+        roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel / conv_halo2_kernel (tcgen05 implicit-GEMM convolution, every "
+                                                 "layer shape of the forward)",
+                    "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
+                    "traffic": traffic, "traffic_note": traffic_note,
+                    "how": f"every {prof.sample_every}th conv launch of the timed steps bracketed by CUDA events (uniform over the launch "
+                           "sequence: flops-weighted); achieved = sum(flops) / sum(time) of that sample",
+                    "algorithmic_bytes_per_launch_avg": prof.bytes_seen / max(prof.seen, 1), "peak_source": pk["which"],
+                    "launches_timed": n_l, "launches_per_step": prof.seen / max(args.steps, 1),
+                    "avg_launch_ms": t_ms / max(n_l, 1), "flops_per_launch_avg": fl / max(n_l, 1),
+                    "flops_executed_per_task": fl_step / B, "flops_nominal_per_task": FLOPS_NOMINAL[dim],
+                    "flops_note": "nominal = the reference's forward per task (SURVEY 8d); executed = after the exact rewrites of "
+                                  "DESIGN 4.0 (encoder once per map, linear first convs hoisted per map, coordinate channels as "
+                                  "epilogue polynomial, ConvTranspose folded): work removed, not skipped -- each rewrite has an "
+                                  "equality test",
+                    "step_tflops_executed": fl_step / (ms_step / 1e3) / 1e12,
+                    "step_frac": fl_step / (ms_step / 1e3) / 1e12 / pk["tensor"],
+                    "cnn_stage_frac": fl_step / (max(stage[0], 1e-9) / 1e3) / 1e12 / pk["tensor"],
+                    "step_share": {"cnn_ms": stage[0], "cdf_ms": stage[1], "draw_ms": stage[2], "plan_ms": stage[3]}}  # last timed step
+        cdf_bytes = 8.0 * B * cells
+        kernels["cdf_stream_kernel"] = {"bound": "hbm", "ms": stage[1], "algorithmic_bytes": cdf_bytes,
+                                        "achieved": cdf_bytes / max(stage[1], 1e-9) / 1e6, "peak": pk["hbm"], "unit": "GB/s",
+                                        "frac": cdf_bytes / max(stage[1], 1e-9) / 1e6 / pk["hbm"]}
+        if args.layer_table:
+            with open(args.layer_table, "w") as f:
+                f.write("layer,launches,gflop_per_launch,ms_per_launch,tflops\n")
+                for name, (n, fl_l, ms_l) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
+                    f.write(f"{name},{n},{fl_l / n / 1e9:.2f},{ms_l / n:.4f},{fl_l / max(ms_l, 1e-9) / 1e9:.1f}\n")
+    else:
+        roofline = {"bound": "hbm", "kernel": "plan_kernel", "achieved": None, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": None, "traffic": None, "peak_source": pk["which"],
+                    "note": "planner state lives in shared memory; see DESIGN.md",
+                    "step_share": {"cnn_ms": 0.0, "cdf_ms": 0.0, "draw_ms": stage[2], "plan_ms": stage[3]}}
+    it_sum = float(iters.sum())
+    kernels["draw_kernel"] = {"bound": "latency (dependent L2/DRAM probes, one warp per task)", "ms": stage[2], "draws": n_draws,
+                              "draws_per_s": n_draws / max(stage[2], 1e-9) * 1e3,
+                              "probe_sector_bytes": 32.0 * 18 * 0.75 * it_sum if not arm_uniform else 0.0,
+                              "achieved": (32.0 * 18 * 0.75 * it_sum / max(stage[2], 1e-9) / 1e6) if not arm_uniform else None,
+                              "peak": pk["hbm"], "unit": "GB/s"}
+    kernels["plan_kernel"] = {"bound": "latency (chain of dependent iterations, tree in shared memory)", "ms": stage[3],
+                              "iterations": it_sum, "iterations_per_s": it_sum / max(stage[3], 1e-9) * 1e3,
+                              "hbm_algorithmic_bytes": float(B) * (cells / 8 + 5000 * 2 * dim) + float(res.n_nodes.sum().item()) * 20,
+                              "unit": "GB/s", "peak": pk["hbm"],
+                              "achieved": (float(B) * (cells / 8 + 5000 * 2 * dim) + float(res.n_nodes.sum().item()) * 20) / max(stage[3], 1e-9) / 1e6}
+
+    # ---- secondary sections (the other BASELINE configs), a few steps each; the headline above stays on args.workload ----
+    sections = {}
+    if not args.no_sections:
+        del arm
+        torch.cuda.empty_cache()
+        plan = []
+        if args.workload != "2d_uniform":
+            plan.append(("2d_uniform", "2d_uniform", 4096, "weak"))          # BASELINE configs[2]
+        if args.workload != "3d_neural":
+            plan.append(("3d_neural_1024", "3d_neural", 1024, "weak"))       # BASELINE configs[3]
+        plan.append(("3d_sweep", "3d_neural", args.sweep_tasks, "strong"))   # BASELINE configs[4], scaled (see note)
+        for key, wname, n_tasks, kind in plan:
+            if kind == "weak":
+                pr = ((n_tasks + 9) // 10) * 10
+                swl, sids = _rank_workload(wname, rank * pr, rank * pr + n_tasks)
+                sg, n_global = torch.arange(rank * n_tasks, (rank + 1) * n_tasks, device=dev), world * n_tasks
+            else:
+                idx = sharding.shard_indices(n_tasks, rank, world, interleaved=False)
+                swl, sids = _rank_workload(wname, int(idx[0]), int(idx[-1]) + 1)
+                sg, n_global = torch.from_numpy(idx).to(dev), n_tasks
+            sarm = Arm(wname, swl, sids, dev, args)
+            ms_s, out, sres = run_arm(sarm, sg, n_global, args.section_steps, 1)
+            done = n_global
+            sec = {"workload": workload_name(wname, done if kind == "strong" else sarm.B), "scaling": kind,
+                   "tasks_total": done, "tasks_per_gpu": sarm.B, "steps": args.section_steps, "warmup": 1,
+                   "ms_per_step": ms_s, "value": done / (ms_s / 1e3), "unit": UNIT}
+            if rank == 0 and out is not None:
+                o = out.cpu().numpy()
+                sec.update({"solved_fraction": float(np.mean(o[:, 0] == 0)), "mean_iterations": float(o[:, 1].mean()),
+                            "sampler_stuck": int(np.sum(o[:, 0] == 3)),
+                            # identical at every N when the sharded result equals the single-GPU result (strong sections)
+                            "checksum": {"iterations_sum": int(o[:, 1].sum()), "nodes_sum": int(o[:, 2].sum()),
+                                         "path_len_sum": float(o[:, 4].sum())}})
+            sections[key] = sec
+            del sarm
+            torch.cuda.empty_cache()
+        sections["3d_sweep"]["note"] = (f"BASELINE configs[4] is 65536 tasks; the sweep here is {args.sweep_tasks} tasks of the same generator "
+                                        "(fixed total, contiguous shards via sharding.shard_indices, records gathered with "
+                                        "sharding.gather_records) so that every N fits the bench budget; --sweep-tasks 65536 runs it whole")
+
     if rank == 0:
-        pk = peaks()
-        roofline = None
-        if prof is not None:
-            n_l, fl, t_ms = prof.totals()
-            ach = fl / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0
-            traffic, traffic_note = conv_traffic()
-            roofline = {"bound": "tensor", "kernel": "conv_gemm2_kernel / conv_halo2_kernel (tcgen05 implicit-GEMM convolution, every "
-                                                     "layer shape of the forward)",
-                        "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": ach / pk["tensor"],
-                        "traffic": traffic, "traffic_note": traffic_note,
-                        "algorithmic_bytes_per_launch_avg": (sum(prof.bytes) / max(len(prof.bytes), 1)), "peak_source": pk["which"], "launches_timed": n_l,
-                        "avg_launch_ms": t_ms / max(n_l, 1), "flops_per_launch_avg": fl / max(n_l, 1),
-                        "step_share": {"cnn_ms": stage[0], "cdf_ms": stage[1], "draw_plan_ms": stage[2]}}  # last timed step
-            if args.layer_table:
-                with open(args.layer_table, "w") as f:
-                    f.write("layer,launches,gflop_per_launch,ms_per_launch,tflops\n")
-                    for name, (n, fl_l, ms_l) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
-                        f.write(f"{name},{n},{fl_l / n / 1e9:.2f},{ms_l / n:.4f},{fl_l / max(ms_l, 1e-9) / 1e9:.1f}\n")
-        else:
-            roofline = {"bound": "hbm", "kernel": "plan_kernel", "achieved": None, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": None, "traffic": None, "peak_source": pk["which"],
-                        "note": "planner state lives in shared memory; see DESIGN.md"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                _, cpu = cpu_arm(args, wl, args.ref_sample or (16 if not uniform else 32), model=None)
+                _, cpu = cpu_arm(args, wl, args.ref_sample or (16 if not args.workload.endswith("uniform") else 32), model=None)
             except Exception as exc:  # the baseline is informational; never lose the GPU line over it
                 cpu = {"error": repr(exc)}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64 planner / f16 tensor-core CNN (f32 accumulate)", "data": "synthetic",
                 "config": {"workload": workload_name(args.workload, B), "tasks_per_gpu": B, "maps_per_gpu": int(wl.occ_maps.shape[0]),
                            "max_iterations": 5000, "neural_bias": 0.75, "weights": "random-init seed 0",
                            "task_filter": "start/goal in one free component (redrawn %d)" % wl.redrawn,
                            "l2": "inputs larger than L2 (activations and CDFs are GBs per step)",
+                           "sharding": "rank r owns global tasks [r B, (r+1) B); records gathered to rank 0 (sharding.gather_records)",
                            "solved_fraction": float(np.mean(status == 0)), "mean_iterations": float(iters.mean()),
                            "median_iterations": float(np.median(iters))},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
-                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": arm_h2d, "d2h_bytes_per_step": d2h_bytes},
+                "gpu_launches": launches, "clocks": clk, "roofline": roofline, "kernels": kernels, "sections": sections,
+                "cpu_baseline": cpu}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

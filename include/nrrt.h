@@ -51,6 +51,12 @@ typedef struct NrrtPlanParams {
     double goal_threshold;  /* GOAL_THRESHOLD: 5.0 (2D) / 3.0 (3D) */
     double neural_bias;     /* neural_bias (0.75 in the reference); ignored when cdf == NULL */
     uint64_t seed;          /* Philox key of the sample stream */
+    uint64_t draw_start;    /* index of the first draw to consume from every task's stream (0 = a fresh stream); with
+                               n_draws this lets a caller continue one stream across calls, the way the reference's methods
+                               all consume the one module-level `random` */
+    int32_t sampler_mode;   /* nrrt_draw_samples: 0 = the main loop's `random.random() < neural_bias` switch per sample
+                               (neural_rrt.py:225-228); 1 = generate_neural_sample() only, 2 = generate_random_sample() only
+                               (the methods called directly: no bias draw is consumed) */
 } NrrtPlanParams;
 
 /* Per-task outputs; all arrays caller-allocated, fixed stride, any pointer marked optional may be NULL. */
@@ -216,7 +222,10 @@ int nrrt_stem_conv(int dims, const float* x, int n, int cin, int d, int h, int w
 
 /* Same layer fed straight from the resident uint8 occupancy maps: sample b reads map task_to_map[b] and every input
  * channel is the dataset's {0,1} normalisation of it, x = (occ != 0) (train.py:41-44, ThreeD_train.py:46-50), so the
- * (B,3,H,W) fp32 tensor the reference materialises per task never exists. */
+ * (B,3,H,W) fp32 tensor the reference materialises per task never exists.  3D: a map is the task file's array
+ * [x][y][z] (sizes h, w, d) and the network sees it as the dataset's ToTensorV2 presents it, last axis first:
+ * voxel (d, h, w) of the network input = map[h][w][d] (ThreeD_train.py:59-66; the output is consumed un-transposed,
+ * ThreeD_test_network_and_algorithms.py:98-105). */
 int nrrt_stem_conv_maps(int dims, const uint8_t* occ_maps, const int32_t* task_to_map, int n, int cin, int d, int h, int w,
                         const float* weight, const float* bias, int cout, int cout_pad, void* out, void* stream);
 
@@ -292,7 +301,9 @@ int nrrt_head_1x1(const void* in, int64_t pixels, int C, int64_t in_cstride, con
  * reference's `dx != 255` tests are always true, ThreeD_generate_paths.py:55-72).  A* with the consistent Euclidean
  * heuristic returns a shortest path and every shortest path has the same number of steps of each kind, so the kernel
  * returns those integers per task, n_steps [B][3] = steps of cost 1, sqrt(2), sqrt(3) (-1 when there is no path, length
- * NaN), and length = n1 + n2 sqrt(2) + n3 sqrt(3): the reference's path length up to the order of its additions.
+ * NaN; -2 and length = +inf when the search reached the cost limit of the label format -- 8191 in 2D, 1771 in 3D --
+ * before settling the goal), and length = n1 + n2 sqrt(2) + n3 sqrt(3): the reference's path length up to the order of
+ * its additions.
  * occ_bits as nrrt_pack_occupancy writes them (1 = free; 3D maps hold {0 = free, 255}); starts / goals [B][dims] in array-axis
  * order ((y, x) in 2D, (x, y, z) in 3D, as the planners take them); (s0, s1, s2) = array shape (s2 ignored in 2D);
  * work: [n_slots][cells] uint64 scratch (one slot per resident CTA, e.g. the SM count); queue: one zeroed int32. */

@@ -4,6 +4,8 @@ import glob
 import random  # noqa: F401
 import sys
 
+import numpy as np
+
 from ._planner_base import Node, RRTStarBase, calculate_length, get_from_string  # noqa: F401
 
 MAPS_DIRECTORY = '/home/czarek/mgr/3D_maps/start_finish/*.npy'
@@ -31,3 +33,27 @@ class RRTStar(RRTStarBase):
 
     def search_space_volume(self) -> float:
         return self.map_width * self.map_height * self.map_width  # sic (ThreeD_rrt_star.py:187)
+
+
+def generate_paths(maps=None):
+    """The reference's demo (ThreeD_rrt_star.py:262-280): the first task file of MAPS_DIRECTORY -> one plan.  Plotting is a no-op
+    (out of scope); returns (map_path, path, iterations) of the task it ran, None when the directory is empty."""
+    maps = get_blank_maps_list() if maps is None else maps
+    for map_path in maps:
+        print(map_path)
+        occ_map = np.load(map_path)
+        start, finish = get_start_finish_coordinates(map_path)
+        rrt = RRTStar(occ_map=occ_map, start=start, goal=finish, max_iterations=MAX_ITERATIONS,
+                      goal_threshold=GOAL_THRESHOLD)
+        path, iterations = rrt.rrt_star()
+        if path:
+            print(path)
+            rrt.visualize_path(path)
+        else:
+            print("COULDN'T FIND A PATH FOR THIS EXAMPLE:", map_path)
+        return map_path, path, iterations
+    return None
+
+
+if __name__ == '__main__':
+    generate_paths()

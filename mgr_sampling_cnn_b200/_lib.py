@@ -15,7 +15,7 @@ class NrrtError(RuntimeError):
 class NrrtPlanParams(C.Structure):
     _fields_ = [("dim", C.c_int32), ("shape", C.c_int32 * 3), ("max_iterations", C.c_int32), ("node_stride", C.c_int32),
                 ("max_reject", C.c_int32), ("path_cap", C.c_int32), ("goal_threshold", C.c_double),
-                ("neural_bias", C.c_double), ("seed", C.c_uint64)]
+                ("neural_bias", C.c_double), ("seed", C.c_uint64), ("draw_start", C.c_uint64), ("sampler_mode", C.c_int32)]
 
 
 class NrrtPlanOut(C.Structure):

@@ -6,10 +6,13 @@ Each module exposes the reference's names (`Node`, `RRTStar`, `MAX_ITERATIONS`, 
 same CUDA primitives one call at a time (nrrt_collision_free / nrrt_tree_search / nrrt_draw_samples); only scalar
 bookkeeping (steer, goal test, parent walk, radius lookup) is host Python.
 
-Randomness: the reference draws from the module attribute `random` (CPython's module).  Here every plan consumes the
-Philox stream (seed, task): if the module's `random` attribute carries `.seed` / `.task` (a StreamRandom, the injection
-point of SURVEY.md §8b) those are used; otherwise a 64-bit seed is drawn from `random.getrandbits(64)`, so
-`random.seed(s)` keeps runs reproducible.
+Randomness: the reference draws from the module attribute `random` (CPython's module).  Here every instance consumes ONE
+Philox stream (seed, task) through a draw counter, whichever method draws -- `rrt_star()`, `generate_random_sample()`,
+`generate_neural_sample()` -- the way the reference's methods all consume the one module-level generator.  If the
+module's `random` attribute carries `.seed` / `.task` / `.draws` (a StreamRandom, the injection point of SURVEY.md §8b)
+that stream is used and its `.draws` counter is read and advanced, so reference and drop-in stay in lock-step call by
+call; otherwise the instance takes a 64-bit seed from `random.getrandbits(64)` on first use (`random.seed(s)` keeps
+runs reproducible) and counts its own draws.
 """
 import ctypes as C
 import math
@@ -64,14 +67,27 @@ class RRTStarBase(object):
             h = np.ascontiguousarray(np.asarray(self.heat_map, dtype=np.float32)).reshape(1, -1)
             self._cdf = engine.build_cdf(h, engine.HEAT_MODE_RAW, self._device)
         self._draw_k = 0
+        self._own_seed = None
         self.status = None
 
     # ---- stream identity -------------------------------------------------------------------------------------------
     def _stream(self):
+        """(seed, task, first draw) of the next draw of this instance."""
         rnd = self._module.random
         if hasattr(rnd, "seed") and hasattr(rnd, "task") and not callable(getattr(rnd, "seed")):
-            return int(rnd.seed), int(rnd.task)
-        return int(rnd.getrandbits(64)), 0
+            return int(rnd.seed), int(rnd.task), int(getattr(rnd, "draws", 0))
+        if self._own_seed is None:
+            self._own_seed = int(rnd.getrandbits(64))
+        return self._own_seed, 0, self._draw_k
+
+    def _advance(self, draws: int):
+        rnd = self._module.random
+        if hasattr(rnd, "seed") and hasattr(rnd, "task") and hasattr(rnd, "draws") and not callable(getattr(rnd, "seed")):
+            rnd.draws = int(draws)
+            if hasattr(rnd, "_buf"):
+                rnd._buf = None  # StreamRandom's look-ahead buffer is positioned by .draws
+        else:
+            self._draw_k = int(draws)
 
     @property
     def _shape(self):
@@ -82,14 +98,20 @@ class RRTStarBase(object):
         for pt in (self.start_node.position, self.goal):
             if any(float(v) != int(v) for v in pt):
                 raise _lib.NrrtError("start and goal must be integer-valued cells (as the reference's callers pass them)")
-        seed, task = self._stream()
+        seed, task, first = self._stream()
         res = engine.plan_batch(self._bits, np.zeros(1, np.int32), np.asarray(self.start_node.position, np.float64)[None],
                                 np.asarray(self.goal, np.float64)[None], dim=self._dim, shape=self._shape,
                                 max_iterations=self.max_iterations, goal_threshold=self.goal_threshold, cdf=self._cdf,
                                 neural_bias=self.neural_bias if self._neural else 0.0, seed=seed,
                                 task_ids=np.array([task], np.int32), keep_tree=True,
-                                path_cap=self.max_iterations + 2)
+                                path_cap=self.max_iterations + 2, draw_start=first)
         torch.cuda.synchronize()
+        # the stream stops where the reference's loop stopped drawing: after the sample of the last executed iteration
+        iters = int(res.iterations[0])
+        if 0 < iters < self.max_iterations and int(res.status[0]) != _lib.NRRT_SAMPLER_STUCK:
+            self._advance(self._draw(iters, 0, seed, task, first)[1])
+        else:
+            self._advance(int(res.n_draws[0]))
         n = int(res.n_nodes[0])
         goal_node = int(res.goal_node[0])
         best = int(res.best_node[0])
@@ -118,10 +140,6 @@ class RRTStarBase(object):
         return self.find_path(end), self.iteration_no
 
     # ---- individually callable methods ----------------------------------------------------------------------------
-    def _draw_one(self, neural: bool):
-        """One sampler call on the instance's Philox stream (consumes draws like the reference consumes `random`)."""
-        raise NotImplementedError
-
     def find_nearest_neighbor(self, sample):
         pos = np.array([n.position for n in self.nodes], dtype=np.float64).reshape(len(self.nodes), self._dim)
         nodes = torch.from_numpy(pos).to(self._device)
@@ -198,35 +216,73 @@ class RRTStarBase(object):
     def compute_search_radius(self, dim: int) -> float:
         return float(engine.radius_table(dim, self._shape, max(self.iteration_no, 1))[self.iteration_no - 1])
 
-    def _sample_via_kernel(self, force_neural):
-        """generate_*_sample through nrrt_draw_samples: one iteration, continuing the instance's draw counter is not
-        expressible with a per-call kernel launch, so each call uses a fresh sub-stream (task id = call counter)."""
-        seed, task = self._stream()
+    def _draw(self, n, mode, seed, task, first):
+        """n samples through nrrt_draw_samples from draw `first` of stream (seed, task); mode = NrrtPlanParams.sampler_mode.
+        Returns (samples int16 [n, dim] on the host, index of the draw after the last one consumed)."""
         p = _lib.NrrtPlanParams()
         p.dim = self._dim
         shp = list(self._shape) + [1] * (3 - self._dim)
         for k in range(3):
             p.shape[k] = shp[k]
-        p.max_iterations, p.node_stride, p.max_reject, p.path_cap = 1, 3, 100000, 0
+        p.max_iterations, p.node_stride, p.max_reject, p.path_cap = n, n + 2, 100000, 0
         p.goal_threshold, p.seed = float(self.goal_threshold), seed & (2 ** 64 - 1)
-        p.neural_bias = 2.0 if force_neural else -1.0
+        p.neural_bias = float(self.neural_bias) if self._neural else 0.0
+        p.draw_start, p.sampler_mode = int(first), int(mode)
         dev = self._device
         t2m = torch.zeros(1, dtype=torch.int32, device=dev)
-        ids = torch.tensor([task + self._draw_k], dtype=torch.int32, device=dev)
-        self._draw_k += 1
-        smp = torch.zeros((1, 1, self._dim), dtype=torch.int16, device=dev)
+        ids = torch.tensor([task], dtype=torch.int32, device=dev)
+        smp = torch.zeros((1, n, self._dim), dtype=torch.int16, device=dev)
         st = torch.zeros(1, dtype=torch.int32, device=dev)
+        nd = torch.zeros(1, dtype=torch.int64, device=dev)
         cdf = self._cdf if self._cdf is not None else None
+        _lib.count_launch()
         _lib.check(_lib.load().nrrt_draw_samples(C.byref(p), C.c_void_p(self._bits.data_ptr()), C.c_void_p(t2m.data_ptr()),
                                                  None if cdf is None else C.c_void_p(cdf.data_ptr()), C.c_void_p(ids.data_ptr()),
-                                                 1, C.c_void_p(smp.data_ptr()), None, None, C.c_void_p(st.data_ptr()), None))
+                                                 1, C.c_void_p(smp.data_ptr()), None, C.c_void_p(nd.data_ptr()),
+                                                 C.c_void_p(st.data_ptr()), None))
         torch.cuda.synchronize()
         if int(st[0]) != 0:
             raise _lib.NrrtError("sampler found no admissible cell (the reference would loop forever)")
-        return tuple(int(v) for v in smp[0, 0].cpu().tolist())
+        return smp[0].cpu().numpy(), int(nd[0])
+
+    def _sample_via_kernel(self, force_neural):
+        """generate_*_sample called directly: one sample from the instance's stream, continuing its draw counter and
+        consuming exactly the draws the reference's method consumes (no `random() < neural_bias` draw)."""
+        seed, task, first = self._stream()
+        smp, nxt = self._draw(1, 1 if force_neural else 2, seed, task, first)
+        self._advance(nxt)
+        return tuple(int(v) for v in smp[0].tolist())
 
     def generate_random_sample(self):
         return self._sample_via_kernel(False)
+
+    def rewire_tree(self, new_node):
+        """rrt_star.py:125-147 on host objects (the batched kernel fuses this into the main loop; this is the callable
+        method): near set and collision tests through the CUDA primitives, both loops in the reference's order."""
+        nearby_nodes = self.find_nearby_nodes(new_node)
+        for nearby_node in nearby_nodes:
+            new_cost = nearby_node.cost + _euclid(nearby_node.position, new_node.position)
+            if new_cost < new_node.cost:
+                if self.is_collision_free(nearby_node.position, new_node.position):
+                    new_node.parent.children.remove(new_node)
+                    new_node.parent = nearby_node
+                    nearby_node.children.append(new_node)
+                    new_node.cost = new_cost
+        for node in nearby_nodes:
+            redone_cost = new_node.cost + _euclid(new_node.position, node.position)
+            if redone_cost < node.cost:
+                if self.is_collision_free(new_node.position, node.position):
+                    node.parent.children.remove(node)
+                    node.parent = new_node
+                    new_node.children.append(node)
+                    node.cost = redone_cost
+
+    # plotting is out of scope (DESIGN.md): the reference's matplotlib methods exist as no-ops so that its demo code runs
+    def visualize_tree(self, *a, **k):
+        return None
+
+    def visualize_path(self, *a, **k):
+        return None
 
 
 def _euclid(u, v) -> float:

@@ -7,7 +7,6 @@ Activations are fp16 channels-last.  The three `torch.cat` calls of the decoder 
 into channel slices of the concat buffers and TMA reads slices back out.
 """
 import ctypes as C
-import os
 
 import torch
 
@@ -29,35 +28,52 @@ def _prod(v):
 
 
 class ConvProfiler(object):
-    """CUDA-event timing of individual nrrt_conv_layer launches (bench.py's roofline leg).  Events are recorded on the
-    launching stream around a sampled subset of launches; totals are read after a synchronize."""
+    """CUDA-event timing of individual nrrt_conv_layer launches (bench.py's roofline leg).  While `active`, EVERY launch is
+    counted (launches, FLOPs, algorithmic bytes: host arithmetic only) and every `sample_every`-th launch is bracketed by
+    events on the launching stream -- a uniform sample over the launch sequence (the sequence has period 29 (encoder pass) /
+    6 (decoder micro-batch), coprime with the default 5), so sum(flops) / sum(time) over the sample estimates the
+    flops-weighted rate of the whole step, not of whichever pass a coarser sampling happened to hit."""
 
-    def __init__(self):
+    def __init__(self, sample_every: int = 5):
         self.active = False
-        self.records = []  # (flops, start_event, end_event)
+        self.sample_every = max(int(sample_every), 1)
+        self.seen = 0          # launches while active
+        self.flops_seen = 0.0  # their FLOPs (all of them, timed or not)
+        self.bytes_seen = 0.0
+        self.records = []  # (flops, start_event, end_event) of the timed sample
         self.names = []
-        self.bytes = []    # algorithmic DRAM bytes of each recorded launch (inputs + weights + residual rows + outputs, once)
+        self.bytes = []    # algorithmic DRAM bytes of each timed launch (inputs + weights + residual rows + outputs, once)
+
+    def reset(self):
+        self.seen, self.flops_seen, self.bytes_seen = 0, 0.0, 0.0
+        self.records, self.names, self.bytes = [], [], []
 
     class _Ctx(object):
         def __init__(self, prof, flops, name=None, nbytes=0.0):
             self.prof, self.flops, self.name, self.nbytes = prof, flops, name, nbytes
+            prof.seen += 1
+            prof.flops_seen += flops
+            prof.bytes_seen += nbytes
+            self.timed = prof.seen % prof.sample_every == 0
 
         def __enter__(self):
-            self.a = torch.cuda.Event(enable_timing=True)
-            self.b = torch.cuda.Event(enable_timing=True)
-            self.a.record()
+            if self.timed:
+                self.a = torch.cuda.Event(enable_timing=True)
+                self.b = torch.cuda.Event(enable_timing=True)
+                self.a.record()
 
         def __exit__(self, *exc):
-            self.b.record()
-            self.prof.records.append((self.flops, self.a, self.b))
-            self.prof.names.append(self.name)
-            self.prof.bytes.append(self.nbytes)
+            if self.timed:
+                self.b.record()
+                self.prof.records.append((self.flops, self.a, self.b))
+                self.prof.names.append(self.name)
+                self.prof.bytes.append(self.nbytes)
 
     def launch(self, flops, name=None, nbytes=0.0):
         return ConvProfiler._Ctx(self, flops, name, nbytes)
 
     def by_layer(self):
-        """{layer name: (launches, flops, milliseconds)} of everything recorded so far; call after a synchronize."""
+        """{layer name: (launches, flops, milliseconds)} of the timed sample; call after a synchronize."""
         out = {}
         for (f, a, b), name in zip(self.records, self.names):
             n, fl, ms = out.get(name, (0, 0.0, 0.0))
@@ -65,44 +81,50 @@ class ConvProfiler(object):
         return out
 
     def totals(self):
-        """(launches, total flops, total milliseconds) of everything recorded so far; call after a synchronize."""
+        """(launches, total flops, total milliseconds) of the timed sample; call after a synchronize."""
         ms = sum(a.elapsed_time(b) for _, a, b in self.records)
         return len(self.records), sum(f for f, _, _ in self.records), ms
+
+
+def _cpu(t, dtype=torch.float32):
+    """Parameter -> host tensor.  All packing / folding below is host arithmetic (once per model, a few MB): building a plan
+    launches no GPU kernels of its own, only uploads -- the launch list of a process shows this library's kernels."""
+    return t.detach().to(device="cpu", dtype=dtype)
 
 
 def _fold_bn(bn, conv_bias, cout, device):
     """eval-mode BatchNorm (+ optional conv bias) -> per-channel (scale, shift) in fp32."""
     if bn is None:
-        scale = torch.ones(cout, dtype=torch.float32, device=device)
-        shift = torch.zeros(cout, dtype=torch.float32, device=device) if conv_bias is None else conv_bias.detach().float().to(device)
-        return scale.contiguous(), shift.contiguous()
-    g, b = bn.weight.detach().float().to(device), bn.bias.detach().float().to(device)
-    mu, var = bn.running_mean.detach().float().to(device), bn.running_var.detach().float().to(device)
+        scale = torch.ones(cout, dtype=torch.float32)
+        shift = torch.zeros(cout, dtype=torch.float32) if conv_bias is None else _cpu(conv_bias)
+        return scale.contiguous().to(device), shift.contiguous().to(device)
+    g, b = _cpu(bn.weight), _cpu(bn.bias)
+    mu, var = _cpu(bn.running_mean), _cpu(bn.running_var)
     scale = g / torch.sqrt(var + bn.eps)
     shift = b - mu * scale
     if conv_bias is not None:
-        shift = shift + conv_bias.detach().float().to(device) * scale
-    return scale.contiguous(), shift.contiguous()
+        shift = shift + _cpu(conv_bias) * scale
+    return scale.contiguous().to(device), shift.contiguous().to(device)
 
 
 def _pack_conv_weight(w, cin_pad, device):
     """[cout, cin, (kd,) kh, kw] -> fp16 [cout, taps, cin_pad] (taps in (kd, kh, kw) order, zero-padded channels)."""
-    w = w.detach().to(device=device, dtype=torch.float32)
+    w = _cpu(w)
     cout, cin = w.shape[0], w.shape[1]
     taps = w[0, 0].numel()
     w = w.reshape(cout, cin, taps).permute(0, 2, 1)  # [cout, taps, cin]
-    out = torch.zeros((cout, taps, cin_pad), dtype=torch.float16, device=device)
+    out = torch.zeros((cout, taps, cin_pad), dtype=torch.float16)
     out[:, :, :cin] = w.to(torch.float16)
-    return out.contiguous()
+    return out.contiguous().to(device)
 
 
 def _pack_convT_weight(w, device):
     """ConvTranspose k=2 s=2 weight [cin, cout, (2,) 2, 2] -> fp16 [groups*cout, cin]; group g = offsets in (d,h,w) order."""
-    w = w.detach().to(device=device, dtype=torch.float32)
+    w = _cpu(w)
     cin, cout = w.shape[0], w.shape[1]
     groups = w[0, 0].numel()
     w = w.reshape(cin, cout, groups).permute(2, 1, 0)  # [g, cout, cin]
-    return w.reshape(groups * cout, cin).to(torch.float16).contiguous()
+    return w.reshape(groups * cout, cin).to(torch.float16).contiguous().to(device)
 
 
 def _fold_weights(wt, bu, wc, device):
@@ -113,10 +135,10 @@ def _fold_weights(wt, bu, wc, device):
     Returns (fp16 [cout, 16 * cin_low + 128] = [cout][parity a*2+b][tap][cin_low] + identity columns, tap = (row offset - (a-1)) * 2 + (column
     offset - (b-1)), composed in fp64;  fp32 [9 border cases][cout] = the ConvTranspose bias seen through the conv taps
     that fall inside the image, which nrrt_poly_fold adds to the epilogue polynomial)."""
-    wt = wt.detach().to(device).double()
-    wc = wc.detach().to(device).double()
+    wt = _cpu(wt, torch.float64)
+    wc = _cpu(wc, torch.float64)
     cout, cin = wc.shape[0], wt.shape[0]
-    w = torch.zeros((cout, 4, 4, cin), dtype=torch.float64, device=device)
+    w = torch.zeros((cout, 4, 4, cin), dtype=torch.float64)
     for a in range(2):
         for b in range(2):
             for dy in (-1, 0, 1):
@@ -124,13 +146,13 @@ def _fold_weights(wt, bu, wc, device):
                     tap = ((a + dy) // 2 - (a - 1)) * 2 + ((b + dx) // 2 - (b - 1))
                     w[:, a * 2 + b, tap] += wc[:, :, dy + 1, dx + 1] @ wt[:, :, (a + dy) % 2, (b + dx) % 2].t()
     valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}
-    bu = bu.detach().to(device).double()
+    bu = _cpu(bu, torch.float64)
     bc = torch.stack([wc[:, :, valid[r]][:, :, :, valid[c]].sum(dim=(2, 3)) @ bu for r in range(3) for c in range(3)])
     # + 128 identity columns per N half of 128 output channels: the residual tile is accumulated by the tensor core
     # (conv_halo2_kernel, p.res_mma)
-    eye = (torch.arange(cout, device=device)[:, None] % 128 == torch.arange(128, device=device)[None, :]).to(torch.float16)
+    eye = (torch.arange(cout)[:, None] % 128 == torch.arange(128)[None, :]).to(torch.float16)
     wf = torch.cat([w.reshape(cout, 16 * cin).to(torch.float16), eye], dim=1)
-    return wf.contiguous(), bc.float().contiguous()
+    return wf.contiguous().to(device), bc.float().contiguous().to(device)
 
 
 class _Layer(object):
@@ -254,8 +276,8 @@ class UNetPlan(object):
 
         def convT(m):
             groups = 2 ** d
-            scale = torch.ones(groups * m.out_channels, dtype=torch.float32, device=dev)
-            shift = m.bias.detach().float().to(dev).repeat(groups).contiguous()
+            scale = torch.ones(groups * m.out_channels, dtype=torch.float32).to(dev)
+            shift = _cpu(m.bias).repeat(groups).contiguous().to(dev)
             return _Layer(d, CONVT, m.in_channels, m.out_channels, _pack_convT_weight(m.weight, dev), scale, shift, False)
 
         def first_conv(seq):  # the Conv inside a torchvision Conv3DSimple is the module itself; 2D convs are plain
@@ -270,8 +292,8 @@ class UNetPlan(object):
             bn = model.conv1[1]        # + BatchNorm3d(64) + ReLU left over from torchvision's BasicStem
             post = _fold_bn(bn, None, 64, dev)
         c0, c1 = stem_seq[0], stem_seq[2]
-        self.stem_w = c0.weight.detach().float().to(dev).reshape(c0.out_channels, -1).contiguous()
-        self.stem_b = c0.bias.detach().float().to(dev).contiguous()
+        self.stem_w = _cpu(c0.weight).reshape(c0.out_channels, -1).contiguous().to(dev)
+        self.stem_b = _cpu(c0.bias).contiguous().to(dev)
         self.stem_cin, self.stem_cout = c0.in_channels, c0.out_channels
         self.stem2 = conv(c1, K3S1, None, True, cin_pad=64, post=post)
 
@@ -294,9 +316,9 @@ class UNetPlan(object):
 
         # ---- coordinate branch (fp32, tiny) ----
         # [cout][cin][3][3] -> [tap][cin][cout]: the kernel's threads run over cout
-        self.cw = [m[0].weight.detach().float().to(dev).permute(2, 3, 1, 0).reshape(9, m[0].in_channels, m[0].out_channels).contiguous()
+        self.cw = [_cpu(m[0].weight).permute(2, 3, 1, 0).reshape(9, m[0].in_channels, m[0].out_channels).contiguous().to(dev)
                    for m in (model.conv_coords_64, model.conv_coords_128, model.conv_coords_256, model.conv_coords_512)]
-        self.cb = [m[0].bias.detach().float().to(dev).contiguous() for m in
+        self.cb = [_cpu(m[0].bias).contiguous().to(dev) for m in
                    (model.conv_coords_64, model.conv_coords_128, model.conv_coords_256, model.conv_coords_512)]
         self.cw_ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in self.cw])
         self.cb_ptrs = (C.c_void_p * 4)(*[t.data_ptr() for t in self.cb])
@@ -313,77 +335,72 @@ class UNetPlan(object):
             in its input channels up to the ReLU, so it is split into (per-task layer over [up | coords (3D only)] with
             the bias and the ReLU, per-map layer over the encoder channels without bias or ReLU): the per-map partial sum
             is computed once per map and enters the per-task layer as an (indexed) residual before the ReLU."""
-            w = m.weight
+            w = _cpu(m.weight)
             up, enc, crd = w[:, :c_up], w[:, c_up:c_up + c_enc], w[:, c_up + c_enc:]
             wp = torch.cat([up] + ([crd] if c_coords_in_gemm else []), dim=1)
             scale, shift = _fold_bn(None, m.bias, m.out_channels, dev)
             task = _Layer(d, K3S1, wp.shape[1], m.out_channels, _pack_conv_weight(wp, wp.shape[1], dev), scale, shift, relu)
-            one, zero = torch.ones_like(scale), torch.zeros_like(shift)
+            one = torch.ones(m.out_channels, dtype=torch.float32).to(dev)
+            zero = torch.zeros(m.out_channels, dtype=torch.float32).to(dev)
             per_map = _Layer(d, K3S1, c_enc, m.out_channels, _pack_conv_weight(enc, c_enc, dev), one, zero, False)
             return task, per_map
 
+        # Tap moments of the coordinate slices.  Inside the image a conv over a (piecewise) bilinear field is the field's
+        # value and derivatives times the moments sum_tap w, sum_tap w*dy, ... of the taps that fall inside the image; per
+        # axis the admissible taps of a border case are a 0/1 mask, so every moment is a separable contraction of the weights.
+        off = torch.tensor([-1.0, 0.0, 1.0])
+        border = torch.tensor([[0.0, 1.0, 1.0], [1.0, 1.0, 1.0], [1.0, 1.0, 0.0]])   # first / interior / last row or column
+        pw = torch.stack([torch.ones(3), off])                                       # [order 0 / 1][tap]
+
         def conv_moments(m, keep):
-            """Tap moments of the coordinate slice: [9 border cases][uv = 00,10,01,11][Cc][Cout] fp32."""
-            wc = m.weight.detach().float().to(dev)[:, keep:]            # [Cout, Cc, 3, 3]
-            off = torch.tensor([-1.0, 0.0, 1.0], device=dev)
-            out = torch.zeros((9, 4) + (wc.shape[1], wc.shape[0]), dtype=torch.float32, device=dev)
-            valid = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}                # tap indices inside the image per border case
-            for ry in range(3):
-                for rx in range(3):
-                    sub = wc[:, :, valid[ry]][:, :, :, valid[rx]]       # [Cout, Cc, ny, nx]
-                    dy = off[valid[ry]].view(1, 1, -1, 1)
-                    dx = off[valid[rx]].view(1, 1, 1, -1)
-                    for uv, wgt in enumerate((torch.ones_like(dy * dx), dy * torch.ones_like(dx), dx * torch.ones_like(dy), dy * dx)):
-                        out[ry * 3 + rx, uv] = (sub * wgt).sum(dim=(2, 3)).t()
-            return out.contiguous()
+            """2D: [9 border cases][uv = 00,10,01,11][Cc][Cout] fp32 (uv = order in dy, order in dx)."""
+            wc = _cpu(m.weight)[:, keep:]                                            # [Cout, Cc, 3, 3]
+            my = border[:, None, :] * pw[None, :, :]                                 # [row case][order][dy]
+            out = torch.einsum("ocyx,rsy,qtx->rqtsco", wc, my, my)                   # [ry][rx][order x][order y][Cc][Cout]
+            out = out.reshape(9, 2, 2, wc.shape[1], wc.shape[0])                     # uv index = order_x * 2 + order_y
+            return out.reshape(9, 4, wc.shape[1], wc.shape[0]).contiguous().to(dev)
 
         def conv_moments3d(m, keep):
             """3D tap moments of the coordinate slice, the two h-pieces stacked along the channel axis, as the GEMM operand
             [2*Cc][54 cases * 4 uv * Cout]; case = (d-border * 6 + h-class) * 3 + w-border, uv = 00, 10 (dz), 01 (dy), 11."""
-            wc = m.weight.detach().float().to(dev)[:, keep:]            # [Cout, Cc, 3, 3, 3] (dz, dy, dx)
+            wc = _cpu(m.weight)[:, keep:]                                            # [Cout, Cc, 3, 3, 3] (dz, dy, dx)
             cout, cc = wc.shape[0], wc.shape[1]
-            off = torch.tensor([-1.0, 0.0, 1.0], device=dev)
-            border = {0: [1, 2], 1: [0, 1, 2], 2: [0, 1]}               # tap indices inside the volume per border case
             pieces = {0: ([1, 2], []), 1: ([0, 1, 2], []), 2: ([0, 1], [2]), 3: ([0], [1, 2]), 4: ([], [0, 1, 2]), 5: ([], [0, 1])}
-            out = torch.zeros((54, 4, 2 * cc, cout), dtype=torch.float32, device=dev)
-            for dc in range(3):
-                for hc in range(6):
-                    for wcase in range(3):
-                        case = (dc * 6 + hc) * 3 + wcase
-                        for pce in range(2):
-                            dys = pieces[hc][pce]
-                            if not dys:
-                                continue
-                            sub = wc[:, :, border[dc]][:, :, :, dys][:, :, :, :, border[wcase]]   # [Cout, Cc, nz, ny, nx]
-                            dz = off[border[dc]].view(1, 1, -1, 1, 1)
-                            dy = off[dys].view(1, 1, 1, -1, 1)
-                            one = torch.ones_like(dz * dy)
-                            for uv, wgt in enumerate((one, dz * torch.ones_like(dy), dy * torch.ones_like(dz), dz * dy)):
-                                out[case, uv, pce * cc:(pce + 1) * cc] = (sub * wgt).sum(dim=(2, 3, 4)).t()
-            return out.permute(2, 0, 1, 3).reshape(2 * cc, -1).contiguous()
+            hmask = torch.zeros(6, 2, 3)                                             # [h-class][piece][dy]
+            for hc, pcs in pieces.items():
+                for pce in range(2):
+                    hmask[hc, pce, pcs[pce]] = 1.0
+            mz = border[:, None, :] * pw[None, :, :]                                 # [d case][order z][dz]
+            mh = hmask[:, :, None, :] * pw[None, None, :, :]                         # [h class][piece][order y][dy]
+            t = torch.einsum("oczyx,wx->oczyw", wc, border)                          # w-border cases
+            t = torch.einsum("oczyw,hpty->ocztwhp", t, mh).contiguous()
+            out = torch.einsum("ocztwhp,dsz->dhwtspco", t, mz)                       # [d][h][w][order y][order z][piece][Cc][Cout]
+            out = out.reshape(54, 4, 2 * cc, cout)                                   # uv = order_y * 2 + order_z: 00, 10 (dz), 01 (dy), 11
+            return out.permute(2, 0, 1, 3).reshape(2 * cc, -1).contiguous().to(dev)
 
         mu = model.upconv6
         groups = 2 ** d
-        scale = torch.ones(groups * mu.out_channels, dtype=torch.float32, device=dev)
-        shift = mu.bias.detach().float().to(dev).repeat(groups).contiguous()
+        scale = torch.ones(groups * mu.out_channels, dtype=torch.float32).to(dev)
+        shift = _cpu(mu.bias).repeat(groups).contiguous().to(dev)
         if self.poly:
             # upconv6 reads the encoder output x5 only (once per map); its coordinate rows become polynomial moments
-            self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(mu.weight[:512], dev), scale, shift, False)
-            self.m_up6 = mu.weight.detach().float().to(dev)[512:].permute(2, 3, 0, 1).reshape(4, 1, 512, mu.out_channels).contiguous()
+            self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(_cpu(mu.weight)[:512], dev), scale, shift, False)
+            self.m_up6 = _cpu(mu.weight)[512:].permute(2, 3, 0, 1).reshape(4, 1, 512, mu.out_channels).contiguous().to(dev)
             self.m_c6, self.m_c7, self.m_c8 = conv_moments(model.conv6[0], 768), conv_moments(model.conv7[0], 256), conv_moments(model.conv8[0], 128)
             # the same moments as GEMM operands [Cc][cases * n_uv * Cout] (nrrt_coords_poly_gemm)
-            self.mt = {k: m.permute(2, 0, 1, 3).reshape(m.shape[2], -1).contiguous()
+            self.mt = {k: m.cpu().permute(2, 0, 1, 3).reshape(m.shape[2], -1).contiguous().to(dev)
                        for k, m in (("e_up6", self.m_up6), ("e_c6", self.m_c6), ("e_c7", self.m_c7), ("e_c8", self.m_c8))}
             # conv6.0 is linear in (upconv6 output | x4 | coords): the whole GEMM runs once per map over (t6m | e4), the
             # task-dependent part is the 16-case polynomial of nrrt_poly16 applied by nrrt_poly_relu (csrc/conv_aux.cu)
             m6 = model.conv6[0]
-            w6 = m6.weight[:, :768]
-            one = torch.ones(m6.out_channels, dtype=torch.float32, device=dev)
-            self.c6full = _Layer(d, K3S1, 512, m6.out_channels, _pack_conv_weight(w6, 768, dev), one, torch.zeros_like(one), False,
+            w6 = _cpu(m6.weight)[:, :768]
+            one = torch.ones(m6.out_channels, dtype=torch.float32).to(dev)
+            self.c6full = _Layer(d, K3S1, 512, m6.out_channels, _pack_conv_weight(w6, 768, dev), one,
+                                 torch.zeros(m6.out_channels, dtype=torch.float32).to(dev), False,
                                  cin_real=768)
             self.c6full.cin2 = 256
-            self.w6taps = m6.weight.detach().float().to(dev)[:, :512].permute(1, 2, 3, 0).reshape(512, 9 * m6.out_channels).contiguous()
-            self.b6 = m6.bias.detach().float().to(dev).contiguous()
+            self.w6taps = _cpu(m6.weight)[:, :512].permute(1, 2, 3, 0).reshape(512, 9 * m6.out_channels).contiguous().to(dev)
+            self.b6 = _cpu(m6.bias).contiguous().to(dev)
         else:
             # source 1 = x5 (per map), source 2 = the interpolated coordinate channels (per task)
             self.up6 = _Layer(d, CONVT, 512, mu.out_channels, _pack_convT_weight(mu.weight, dev), scale, shift, False)
@@ -393,10 +410,10 @@ class UNetPlan(object):
 
         def fold(mu, mc, c_up):
             """upconv7 -> conv7.0 / upconv8 -> conv8.0 as ONE layer (_fold_weights); the conv's bias and ReLU stay."""
-            w, bc = _fold_weights(mu.weight, mu.bias, mc.weight[:, :c_up], dev)
+            w, bc = _fold_weights(mu.weight, mu.bias, _cpu(mc.weight)[:, :c_up], dev)
             scale, shift = _fold_bn(None, mc.bias, mc.out_channels, dev)
             layer = _Layer(d, UPFOLD, mu.in_channels, mc.out_channels, w, scale, shift, True)
-            layer.res_mma = bool(int(os.environ.get("NRRT_RES_MMA", "0")))  # experiments (profiles/conv_fold_r1.md)
+            layer.res_mma = UNetPlan.res_mma  # class switch for experiments (profiles/conv_fold_r1.md), never the environment
             return layer, bc
         # 3D: the coordinate channels leave the GEMM too; their (piecewise bilinear) field and the ReLU are applied by
         # nrrt_poly_relu_3d after the layer (csrc/conv_aux.cu)
@@ -413,8 +430,8 @@ class UNetPlan(object):
         self.c6 = (c60, conv(model.conv6[2], K3S1))
         self.c7 = (c70, conv(model.conv7[2], K3S1))
         self.c8 = (c80, conv(model.conv8[2], K3S1))
-        self.head_w = model.final_conv.weight.detach().float().to(dev).reshape(-1).contiguous()
-        self.head_b = float(model.final_conv.bias.detach().float().item())
+        self.head_w = _cpu(model.final_conv.weight).reshape(-1).contiguous().to(dev)
+        self.head_b = float(_cpu(model.final_conv.bias).item())
         self._bufs = {}
         self.profiler = None
 
@@ -490,6 +507,7 @@ class UNetPlan(object):
                         l.name = f"enc{si + 2}.{bi}.{('c1', 'c2', 'ds')[li]}"
 
     fold = True  # tests: False runs ConvTranspose and the conv after it as separate layers
+    res_mma = False  # experiments: folded layers accumulate the residual through the tensor core
     fuse_poly3 = True  # tests: False applies conv8.0's 3D coordinate field with the nrrt_poly_relu_3d post-pass
 
     def use_fold(self, grid):

@@ -38,7 +38,9 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
                         float v = 0.f;
                         if (ok) {
                             // map mode: every input channel is the {0,1}-normalised occupancy map (train.py:41-44)
-                            if (omap) v = __ldg(omap + ((long long)zz * H + yy) * W + xx) != 0 ? 1.f : 0.f;
+                            // 3D: the map file is indexed [x][y][z] and the dataset's ToTensorV2 moves its LAST axis first
+                            // (ThreeD_train.py:59-66), so network voxel (d, h, w) is map cell [x = h][y = w][z = d]
+                            if (omap) v = __ldg(omap + (DIMS == 3 ? ((long long)yy * W + xx) * D + zz : ((long long)zz * H + yy) * W + xx)) != 0 ? 1.f : 0.f;
                             else v = __ldg(x + ((((long long)b * cin + c) * D + zz) * H + yy) * W + xx);
                         }
                         in[c * TAPS + q] = v;

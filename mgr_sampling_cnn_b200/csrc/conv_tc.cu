@@ -1946,7 +1946,12 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     // folded layers: the residual enters through the tensor core (conv_halo2_kernel, p.res_mma), not the epilogue
     // experiments (scripts/conv_probe.py): NRRT_CONV_DBG bits 1 = no TMA stores, 2 = no epilogue arithmetic, 8 = no polynomial,
     // 16 = no residual (folded layers); results are wrong with any of them set
+    // Compiled out of the product build: a stray environment variable must not be able to corrupt every forward.
+#ifdef NRRT_DEBUG_SWITCHES
     static const int dbg = getenv("NRRT_CONV_DBG") ? atoi(getenv("NRRT_CONV_DBG")) : 0;
+#else
+    constexpr int dbg = 0;
+#endif
     p.dbg = dbg;
     if (fold && (dbg & 8)) { p.pm = 0; p.poly = nullptr; }
     const bool no_res = fold && (dbg & 16);

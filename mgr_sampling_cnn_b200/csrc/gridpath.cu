@@ -14,10 +14,9 @@
 // out of bucket k lands in bucket k: all nodes of a bucket are final when it is processed and can be expanded in parallel;
 // relaxations land in buckets k+1 and k+2 only (max edge < 2), so three shared-memory queues in rotation suffice.
 // One task per CTA (persistent CTAs, atomic task queue).  Node labels live in a per-CTA slot of global memory (8 B per
-// cell, 2 MB at 512^2 / 4 MB at 80^3: L2-resident) as one 64-bit word  [cost in 12.20 fixed point | step counts: 16 + 16
-// bits in 2D, 11 + 11 + 10 in 3D] updated with atomicMin: the fixed-point cost n1 * 2^20 + n2 * round(sqrt(2) * 2^20)
-// + n3 * round(sqrt(3) * 2^20) is an exact integer function of the counts, orders candidates, and carries them with it.  The occupancy grid is staged in shared memory (bit-packed, as
-// in the planner).  A queue overflow degrades that bucket to a scan of all cells.
+// cell, 2 MB at 512^2 / 4 MB at 80^3: L2-resident) as one 64-bit word [fixed-point cost | diagonal step counts] (see Fx
+// below) updated with atomicMin: the cost orders candidates and carries the step counts with it.  The occupancy grid is
+// staged in shared memory (bit-packed, as in the planner).  A queue overflow degrades that bucket to a scan of all cells.
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -32,9 +31,20 @@ namespace {
 // per SM is what buys throughput.  3D (80^3: 64 KB grid, wide fronts): 512 threads, 12288-entry queues, one CTA per SM.
 template <int DIM> struct GP { static constexpr int NT = DIM == 2 ? 256 : 512, QCAP = DIM == 2 ? 6144 : 12288, PER_SM = DIM == 2 ? 2 : 1; };
 constexpr unsigned long long kInf = ~0ull;
-constexpr unsigned long long kK1 = 1ull << 20;   // 1.0
-constexpr unsigned long long kK2 = 1482910ull;   // round(sqrt(2) * 2^20)
-constexpr unsigned long long kK3 = 1816187ull;   // round(sqrt(3) * 2^20)
+// Label = [fixed-point cost | step counts of the diagonal kinds]; the number of unit steps is recovered from the cost
+// (n1 = (cost - n2 K2 - n3 K3) >> F, exact), which leaves the cost 38 (2D) / 31 (3D) fraction bits: the fixed-point cost
+// differs from the true one by < n * 2^-(F+1), i.e. < 1.5e-8 (2D, n <= 8191) / < 7e-7 (3D) at the limits below.  2D: two
+// different step-count pairs differ by |da + db sqrt(2)| >= 1 / (|da| + |db| sqrt(2)) > 4e-5 (norm form a^2 - 2 b^2 != 0),
+// so the fixed-point order IS the exact order.  3D: not provable from the norm bound (1e-12 at the limit); for paths of a
+// few hundred steps (80^3 maps) the smallest gap of candidate costs is ~1e-6 against an error < 1e-7.
+// Limits: cost < 8191 (2D) / 1771 (3D: n2 <= 2047, n3 <= 1023 fit their fields); a search that reaches the limit reports
+// n_steps = -2 and length = +inf ("limit") -- never "no path".
+template <int DIM> struct Fx {
+    static constexpr int F = DIM == 2 ? 38 : 31, PAY = DIM == 2 ? 13 : 21, LIMIT = DIM == 2 ? 8191 : 1771;
+    static constexpr unsigned long long K1 = 1ull << F;
+    static constexpr unsigned long long K2 = DIM == 2 ? 388736063997ull : 3037000500ull;  // round(sqrt(2) * 2^F)
+    static constexpr unsigned long long K3 = 3719550787ull;                             // round(sqrt(3) * 2^31)
+};
 
 struct GridPathArgs {
     const uint32_t* occ_bits;
@@ -51,15 +61,17 @@ struct GridPathArgs {
 
 template <int DIM>
 __device__ __forceinline__ unsigned long long make_key(unsigned a, unsigned b, unsigned c) {
-    const unsigned long long cost = a * kK1 + b * kK2 + c * kK3;
-    const unsigned long long pay = DIM == 2 ? (((unsigned long long)a << 16) | b)
-                                            : (((unsigned long long)a << 21) | ((unsigned long long)b << 10) | c);
-    return (cost << 32) | pay;
+    const unsigned long long cost = a * Fx<DIM>::K1 + b * Fx<DIM>::K2 + (DIM == 3 ? c * Fx<DIM>::K3 : 0ull);
+    const unsigned long long pay = DIM == 2 ? (unsigned long long)b : (((unsigned long long)b << 10) | c);
+    return (cost << Fx<DIM>::PAY) | pay;
 }
 template <int DIM>
+__device__ __forceinline__ int key_bucket(unsigned long long key) { return (int)(key >> (Fx<DIM>::PAY + Fx<DIM>::F)); }
+template <int DIM>
 __device__ __forceinline__ void key_counts(unsigned long long key, unsigned& a, unsigned& b, unsigned& c) {
-    if (DIM == 2) { a = (unsigned)(key >> 16) & 0xffffu; b = (unsigned)key & 0xffffu; c = 0; }
-    else { a = (unsigned)(key >> 21) & 0x7ffu; b = (unsigned)(key >> 10) & 0x7ffu; c = (unsigned)key & 0x3ffu; }
+    if (DIM == 2) { b = (unsigned)key & 0x1fffu; c = 0; }
+    else { b = (unsigned)(key >> 10) & 0x7ffu; c = (unsigned)key & 0x3ffu; }
+    a = (unsigned)(((key >> Fx<DIM>::PAY) - b * Fx<DIM>::K2 - (DIM == 3 ? c * Fx<DIM>::K3 : 0ull)) >> Fx<DIM>::F);
 }
 
 template <int DIM>
@@ -98,14 +110,14 @@ __global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel
         __syncthreads();
         if (tid == 0) { dist[s] = make_key<DIM>(0, 0, 0); q[0] = (uint32_t)s; cnt[0] = 1; s_state = 0; }
         __syncthreads();
-        for (int k = 0; k < 4095; ++k) {
+        for (int k = 0; k < Fx<DIM>::LIMIT; ++k) {
             const int cur = k % 3;
             const bool scan = ovf[cur] != 0;
             const int n = scan ? cells : min(cnt[cur], kQCap);
             for (int i = tid; i < n; i += kNT) {
                 const int u = scan ? i : (int)q[cur * kQCap + i];
                 const unsigned long long key = __ldcg(dist + u);  // labels are updated by L2 atomics: never read them through L1
-                if (key == kInf || (int)(key >> 52) != k) continue;  // stale entry: the node moved to an earlier bucket
+                if (key == kInf || key_bucket<DIM>(key) != k) continue;  // stale entry: the node moved to an earlier bucket
                 unsigned n1, n2, n3;
                 key_counts<DIM>(key, n1, n2, n3);
                 // coordinates along the array axes; 2D: (c0, c1) = (y, x) on an (S0, S1) grid, c2 = 0
@@ -135,7 +147,7 @@ __global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel
                             if (nk < __ldcg(dist + v)) {  // cheap pre-test: most neighbours are already labelled better
                                 const unsigned long long old = atomicMin(dist + v, nk);
                                 if (nk < old) {
-                                    const int bkt = (int)(nk >> 52) % 3;
+                                    const int bkt = key_bucket<DIM>(nk) % 3;
                                     const int pos = atomicAdd(&cnt[bkt], 1);
                                     if (pos < kQCap) q[bkt * kQCap + pos] = (uint32_t)v;
                                     else ovf[bkt] = 1;
@@ -148,7 +160,7 @@ __global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel
                 const unsigned long long gk = __ldcg(dist + g);
                 const int q1 = (k + 1) % 3, q2 = (k + 2) % 3;
                 cnt[cur] = 0; ovf[cur] = 0;
-                if (gk != kInf && (int)(gk >> 52) <= k) s_state = 1;                                 // goal label final
+                if (gk != kInf && key_bucket<DIM>(gk) <= k) s_state = 1;                                 // goal label final
                 else if (cnt[q1] == 0 && cnt[q2] == 0 && !ovf[q1] && !ovf[q2]) s_state = 2;          // nothing left: no path
             }
             __syncthreads();
@@ -161,9 +173,9 @@ __global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel
                 key_counts<DIM>(gk, n1, n2, n3);
                 a.n_steps[task * 3] = (int)n1; a.n_steps[task * 3 + 1] = (int)n2; a.n_steps[task * 3 + 2] = (int)n3;
                 a.length[task] = (double)n1 + (double)n2 * 1.4142135623730951 + (double)n3 * 1.7320508075688772;
-            } else {
-                a.n_steps[task * 3] = a.n_steps[task * 3 + 1] = a.n_steps[task * 3 + 2] = -1;
-                a.length[task] = nan("");
+            } else {  // s_state 2: every reachable cell labelled, the goal is not among them; 0: the cost limit was reached
+                a.n_steps[task * 3] = a.n_steps[task * 3 + 1] = a.n_steps[task * 3 + 2] = s_state == 2 ? -1 : -2;
+                a.length[task] = s_state == 2 ? nan("") : __longlong_as_double(0x7ff0000000000000ll);
             }
         }
     }

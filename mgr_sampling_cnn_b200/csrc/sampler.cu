@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
     // DRAM / L2 round trips (one warp per task); this cut the 3D draw pass from 121 ms to a quarter.
     // Same partition point as np.searchsorted(side='left'): first j with !(cdf[j] < u).
     constexpr int NB = 4;
-    uint64_t k = 0, grp = ~0ull;
+    uint64_t k = a.p.draw_start, grp = ~0ull;
     double u_lane[NB] = {0.0, 0.0, 0.0, 0.0};
     int idx_lane[NB] = {0, 0, 0, 0};
     uint32_t free_lane = 0u;  // bit j: the cell of lookup j is free
@@ -902,6 +902,22 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
     };
     auto is_free = [&](int64_t idx) -> bool { return (__ldg(grid + (idx >> 5)) >> (idx & 31)) & 1u; };
 
+    // After 256 redraws in a row: decide once whether ANY cell the lookup can return is free (the reference's `while True`
+    // would spin forever otherwise, ThreeD_neural_rrt.py:82-110).  A cell is reachable when it carries probability mass
+    // (cdf[i] > cdf[i-1]); the first and the last cell are treated as reachable (u = 0 / u above the rounded total land
+    // there), so the test never gives up on a task that could succeed.
+    auto any_reachable_free = [&]() -> bool {
+        bool any = false;
+        const int n = (int)a.cells;
+#pragma unroll 4
+        for (int i = lane; i < n; i += 32) {
+            const float ci = __ldg(cdf + i);
+            const float pv = i ? __ldg(cdf + i - 1) : -1.f;
+            if ((ci > pv || i == n - 1) && is_free(i)) any = true;
+        }
+        return __any_sync(0xffffffffu, any);
+    };
+
     int status = 0;
     bool checked = false;
     int16_t keep[DIM];
@@ -911,7 +927,11 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
     int it = 0;
     for (; it < max_iter && status == 0; ++it) {
         bool use_neural = false;
-        if (cdf) use_neural = next_u() < a.p.neural_bias;  // random.random() < self.neural_bias
+        if (a.p.sampler_mode == 0) {
+            if (cdf) use_neural = next_u() < a.p.neural_bias;  // random.random() < self.neural_bias
+        } else {
+            use_neural = a.p.sampler_mode == 1;                // the sampler method called directly: no bias draw
+        }
         int c[3] = {0, 0, 0};
         int rej = 0;
         for (;;) {
@@ -933,6 +953,10 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
                     if (fails >= room) { k += (uint64_t)room; status = NRRT_SAMPLER_STUCK; break; }
                     k += (uint64_t)fails;
                     rej += fails;
+                    if (rej >= 256 && !checked) {  // (the draw count reported for a stuck task is where the scan ran)
+                        checked = true;
+                        if (!any_reachable_free()) { status = NRRT_SAMPLER_STUCK; break; }
+                    }
                     if (pos < 0) continue;  // nothing free in the rest of this group: on to the next one
                 }
                 const uint64_t kk = k;  // this draw's position in the stream
@@ -955,21 +979,9 @@ __global__ void __launch_bounds__(128) draw_kernel(const DrawArgs a) {
                 if (is_free(((int64_t)xi * s1 + yi) * s2 + z)) { c[0] = x; c[1] = y; c[2] = z; break; }
             }
             if (++rej >= a.p.max_reject) { status = NRRT_SAMPLER_STUCK; break; }
-            if (DIM == 3 && use_neural && rej == 256 && !checked) {
-                // 256 redraws in a row: decide once whether ANY cell the lookup can return is free (the reference's
-                // `while True` would spin forever otherwise, ThreeD_neural_rrt.py:82-110).  A cell is reachable when it
-                // carries probability mass (cdf[i] > cdf[i-1]); the first and the last cell are treated as reachable
-                // (u = 0 / u above the rounded total land there), so the test never gives up on a task that could succeed.
+            if (DIM == 3 && use_neural && rej >= 256 && !checked) {
                 checked = true;
-                bool any = false;
-                const int n = (int)a.cells;
-#pragma unroll 4
-                for (int i = lane; i < n; i += 32) {
-                    const float ci = __ldg(cdf + i);
-                    const float pv = i ? __ldg(cdf + i - 1) : -1.f;
-                    if ((ci > pv || i == n - 1) && is_free(i)) any = true;
-                }
-                if (!__any_sync(0xffffffffu, any)) { status = NRRT_SAMPLER_STUCK; break; }
+                if (!any_reachable_free()) { status = NRRT_SAMPLER_STUCK; break; }
             }
         }
         if (lane == (it & 31)) {
@@ -1123,6 +1135,8 @@ extern "C" int nrrt_draw_samples(const NrrtPlanParams* p, const uint32_t* occ_bi
     NRRT_REQUIRE(B >= 0 && p->max_iterations >= 1 && p->max_reject >= 1, "bad sizes");
     if (B == 0) return NRRT_OK;
     NRRT_REQUIRE(occ_bits && task_to_map && task_ids && samples && draw_status, "null pointer");
+    NRRT_REQUIRE(p->sampler_mode >= 0 && p->sampler_mode <= 2, "sampler_mode must be 0, 1 or 2");
+    NRRT_REQUIRE(p->sampler_mode != 1 || cdf, "sampler_mode 1 (generate_neural_sample) needs a CDF");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     DrawArgs a;
     a.p = *p; a.occ_bits = occ_bits; a.task_to_map = task_to_map; a.cdf = cdf; a.task_ids = task_ids; a.B = B;

@@ -150,6 +150,7 @@ class PlannerBuffers:
     def __init__(self, dim, B, max_iterations, path_cap, keep_tree, trace_cap, device):
         stride = max_iterations + 2
         self.node_stride = stride
+        self.key = (int(dim), int(B), int(max_iterations), max(int(path_cap), 1), int(trace_cap))
         i32, f64 = torch.int32, torch.float64
         z = lambda *s, dtype=i32: torch.empty(s, dtype=dtype, device=device)  # noqa: E731
         self.cost = z(B, stride, dtype=f64)
@@ -174,13 +175,14 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
                max_iterations: int = 5000, goal_threshold: Optional[float] = None, cdf: Optional[torch.Tensor] = None,
                neural_bias: float = 0.75, seed: int = 0, task_ids=None, samples=None, keep_tree: bool = False,
                trace_cap: int = 0, path_cap: int = 512, max_reject: int = 100000,
-               buffers: Optional[PlannerBuffers] = None) -> PlanResult:
+               buffers: Optional[PlannerBuffers] = None, draw_start: int = 0, events: Optional[list] = None) -> PlanResult:
     """Run B independent RRT* plans (`RRTStar(...).rrt_star()` of the four reference modules) on the current stream.
 
     occ_bits   [n_maps, words] from pack_occupancy;  task_to_map [B];  starts/goals [B, dim] int (reference order:
                (y, x) in 2D, (x, y, z) in 3D);  cdf [B, cells] from build_cdf selects the neural modules, None the uniform ones.
     samples    optional pre-drawn sample points [B, max_iterations, dim] int16 (parity level A); otherwise they are
-               drawn on the device from the Philox stream (seed, task_ids[b]).
+               drawn on the device from the Philox stream (seed, task_ids[b]), starting at draw `draw_start`
+               (PlanResult.n_draws = where every stream stopped: pass it on to continue a stream).
     """
     device = occ_bits.device
     if device.type != "cuda":
@@ -198,6 +200,10 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
         raise ValueError("starts, goals, task_to_map and task_ids must agree on the batch size")
     radius = _dev(radius_table(dim, shape, max_iterations), torch.float64, device)
     buf = buffers or PlannerBuffers(dim, B, max_iterations, path_cap, keep_tree, trace_cap, device)
+    kd, kB, kit, kpath, ktrace = buf.key
+    if kd != dim or kB < B or kit != max_iterations or kpath < path_cap or ktrace < trace_cap or buf.cost.device != device:
+        raise ValueError(f"PlannerBuffers were sized for (dim, B, max_iterations, path_cap, trace_cap) = {buf.key} on "
+                         f"{buf.cost.device}; this call needs ({dim}, {B}, {max_iterations}, {path_cap}, {trace_cap}) on {device}")
 
     p = NrrtPlanParams()
     p.dim = dim
@@ -205,6 +211,7 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
         p.shape[k] = shape[k] if k < len(shape) else 1
     p.max_iterations, p.node_stride, p.max_reject, p.path_cap = max_iterations, buf.node_stride, max_reject, path_cap
     p.goal_threshold, p.neural_bias, p.seed = float(goal_threshold), float(neural_bias), int(seed) & (2 ** 64 - 1)
+    p.draw_start, p.sampler_mode = int(draw_start), 0
     st = _stream_ptr(device)
 
     draw_status = None
@@ -215,6 +222,10 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
         check(lib.nrrt_draw_samples(C.byref(p), _ptr(occ_bits), _ptr(task_to_map), _ptr(cdf), _ptr(task_ids), B,
                                     _ptr(buf.samples), _ptr(buf.neural_flag), _ptr(buf.n_draws), _ptr(buf.draw_status), st))
         samples_t, draw_status = buf.samples, buf.draw_status
+        if events is not None:  # measurement only: a CUDA event between the draw pass and the planner
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            events.append(e)
     else:
         samples_t = _dev(samples, torch.int16, device).reshape(B, max_iterations, dim)
 
@@ -227,11 +238,12 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
     _lib.count_launch()
     check(lib.nrrt_plan_batch(C.byref(p), _ptr(occ_bits), _ptr(task_to_map), _ptr(radius), _ptr(samples_t), _ptr(starts),
                               _ptr(goals), _ptr(draw_status), C.byref(out), B, _ptr(buf.queue), st))
-    return PlanResult(n_nodes=buf.n_nodes, iterations=buf.iterations, status=buf.status, goal_node=buf.goal_node,
-                      best_node=buf.best_node, best_dist=buf.best_dist, path_n=buf.path_n, path_idx=buf.path_idx,
-                      path_len=buf.path_len, cost=buf.cost, parent=buf.parent, pos=buf.pos, samples=samples_t,
-                      neural_flag=buf.neural_flag if samples is None else None,
-                      n_draws=buf.n_draws if samples is None else None, trace=buf.trace, trace_n=buf.trace_n)
+    v = (lambda t: t) if kB == B else (lambda t: None if t is None else t[:B])  # a larger buffer set: views of its first B rows
+    return PlanResult(n_nodes=v(buf.n_nodes), iterations=v(buf.iterations), status=v(buf.status), goal_node=v(buf.goal_node),
+                      best_node=v(buf.best_node), best_dist=v(buf.best_dist), path_n=v(buf.path_n), path_idx=v(buf.path_idx),
+                      path_len=v(buf.path_len), cost=v(buf.cost), parent=v(buf.parent), pos=v(buf.pos), samples=v(samples_t),
+                      neural_flag=v(buf.neural_flag) if samples is None else None,
+                      n_draws=v(buf.n_draws) if samples is None else None, trace=v(buf.trace), trace_n=v(buf.trace_n))
 
 
 def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape: Sequence[int], n_slots: Optional[int] = None):
@@ -275,13 +287,14 @@ class GuidedPlanner(object):
 
     def __init__(self, model, dim: int, shape: Sequence[int], max_iterations: int = 5000,
                  goal_threshold: Optional[float] = None, neural_bias: float = 0.75, micro_batch: Optional[int] = None,
-                 pipeline_batch: int = 4096, path_cap: int = 512, max_reject: int = 100000):
+                 pipeline_batch: int = 4096, path_cap: int = 512, max_reject: int = 100000, keep_tree: bool = False):
         self.model, self.dim, self.shape = model, dim, tuple(int(s) for s in shape)
         self.max_iterations, self.neural_bias = max_iterations, neural_bias
         self.goal_threshold = goal_threshold if goal_threshold is not None else (5.0 if dim == 2 else 3.0)
         # tasks per decoder launch: four maps' worth in 2D (fewer, longer launches: +5 % over one map's worth), half a map in 3D
         self.micro_batch = micro_batch or (40 if dim == 2 else 10)
         self.pipeline_batch, self.path_cap, self.max_reject = pipeline_batch, path_cap, max_reject
+        self.keep_tree = keep_tree  # plan() returns the trees, samples and flags too (single pipeline batch only)
         self.device = next(model.parameters()).device
         if self.device.type != "cuda":
             raise _lib.NrrtError("GuidedPlanner needs the model on a CUDA device")
@@ -289,7 +302,6 @@ class GuidedPlanner(object):
         self._bufs = None
         self._logits = None
         self._cdf = None
-        self.profile_every = 0
         self.share_encoder = True
         self.encoder_batch = 8  # distinct maps per encoder pass
 
@@ -304,7 +316,14 @@ class GuidedPlanner(object):
         """CNN logits [B, cells] fp32 for tasks (occ_maps[task_to_map[b]], coords[b]); occ_maps uint8 on the device.
 
         The encoder runs once per distinct map of a micro-batch (tasks of one map are adjacent in the reference's
-        task files, generate_tasks.py:18-24), the decoder once per task."""
+        task files, generate_tasks.py:18-24), the decoder once per task.
+
+        3D: occ_maps are the task files' arrays [x][y][z]; the network sees them last axis first ([z][x][y], the
+        dataset's ToTensorV2, ThreeD_train.py:59-66) and its output is consumed un-transposed as heat[x][y][z]
+        (ThreeD_test_network_and_algorithms.py:98-105, transpose commented out) -- reproduced as is, so only cubic
+        volumes are meaningful (as in the reference)."""
+        if self.dim == 3 and len(set(self.shape)) != 1:
+            raise ValueError("3D maps must be cubic: the reference feeds the network [z][x][y] and reads it back as [x][y][z]")
         plan = self.model._plan(self.device)
         B = task_to_map.shape[0]
         out = out if out is not None else torch.empty((B, self.cells), dtype=torch.float32, device=self.device)
@@ -314,9 +333,7 @@ class GuidedPlanner(object):
         prep = plan.coords_prepare(coords, grid)  # coordinate branch (+ 2D epilogue polynomials) for every task at once
         if not self.share_encoder or np.any(np.diff(t2m_h) < 0):
             # tasks not grouped by map (or sharing disabled): one encoder pass per task
-            for mbi, i in enumerate(range(0, B, mb)):
-                if plan.profiler is not None:
-                    plan.profiler.active = self.profile_every > 0 and mbi % self.profile_every == 0
+            for i in range(0, B, mb):
                 plan.forward_maps(occ_maps, task_to_map[i:i + mb], coords[i:i + mb], logits_out=out[i:i + mb],
                                   prep=plan.slice_prep(prep, i, i + mb))
             return out
@@ -327,18 +344,12 @@ class GuidedPlanner(object):
         uniq_d = torch.from_numpy(uniq.astype(np.int32)).to(self.device, non_blocking=True)
         rel_d = torch.from_numpy(rel).to(self.device, non_blocking=True)
         bounds = list(first) + [B]
-        mbi = 0
         for g0 in range(0, len(uniq), G):
             g1 = min(len(uniq), g0 + G)
-            if plan.profiler is not None:
-                plan.profiler.active = self.profile_every > 0 and (g0 // G) % max(self.profile_every // G, 1) == 0
             enc = plan.encode(grid, g1 - g0, occ=occ_maps, maps=uniq_d[g0:g1])
             lo, hi = bounds[g0], bounds[g1]
             for i in range(lo, hi, mb):
                 j = min(hi, i + mb)
-                if plan.profiler is not None:
-                    plan.profiler.active = self.profile_every > 0 and mbi % self.profile_every == 0
-                mbi += 1
                 # scheduling hint: tasks per map when every map of the micro-batch has the same number of tasks
                 runs = np.diff(np.flatnonzero(np.diff(rel[i:j], prepend=-1, append=-1)))
                 rg = int(runs[0]) if len(runs) and np.all(runs == runs[0]) else 0
@@ -347,8 +358,9 @@ class GuidedPlanner(object):
 
     def plan(self, occ_maps, task_to_map, starts, goals, coords, seed: int = 0, task_ids=None, record_events=False):
         """occ_maps [n_maps, *shape] uint8 (2D: 0 = obstacle; 3D: 0 = free), host or device; the rest per task.
-        Returns a list of PlanResult views (one per pipeline batch) concatenated into one PlanResult of host-side
-        friendly device tensors."""
+        Returns one PlanResult of device tensors holding the per-task result records (copies: a later plan() call does
+        not disturb them).  With keep_tree=True the result also carries the trees / samples / flags as VIEWS of the
+        planner's reusable buffers, valid until the next plan() call; that mode takes B <= pipeline_batch."""
         dev = self.device
         occ = _dev(occ_maps, torch.uint8, dev)
         t2m_host = (task_to_map.cpu().numpy() if isinstance(task_to_map, torch.Tensor) else np.asarray(task_to_map)).reshape(-1)
@@ -357,6 +369,8 @@ class GuidedPlanner(object):
         goals = _dev(goals, torch.int32, dev).reshape(-1, self.dim)
         coords = _dev(coords, torch.float32, dev)
         B = t2m.shape[0]
+        if self.keep_tree and B > self.pipeline_batch:
+            raise ValueError("keep_tree=True needs B <= pipeline_batch")
         ids = _dev(np.arange(B, dtype=np.int32) if task_ids is None else task_ids, torch.int32, dev).reshape(-1)
         bits = pack_occupancy(occ, self.dim, dev)
         mode = HEAT_MODE_2D if self.dim == 2 else HEAT_MODE_3D
@@ -369,7 +383,12 @@ class GuidedPlanner(object):
             if record_events:
                 ev.append([torch.cuda.Event(enable_timing=True) for _ in range(4)])
                 ev[-1][0].record()
+            prof = self.model._plan(dev).profiler
+            if prof is not None:
+                prof.active = bool(record_events)
             self.probability_maps(occ, t2m[b0:b1], coords[b0:b1], out=self._logits, task_to_map_host=t2m_host[b0:b1])
+            if prof is not None:
+                prof.active = False
             if record_events:
                 ev[-1][1].record()
             build_cdf(self._logits, mode, dev, out=self._cdf)
@@ -378,12 +397,12 @@ class GuidedPlanner(object):
             res = plan_batch(bits, t2m[b0:b1], starts[b0:b1], goals[b0:b1], dim=self.dim, shape=self.shape,
                              max_iterations=self.max_iterations, goal_threshold=self.goal_threshold, cdf=self._cdf,
                              neural_bias=self.neural_bias, seed=seed, task_ids=ids[b0:b1], path_cap=self.path_cap,
-                             max_reject=self.max_reject, buffers=self._bufs)
+                             max_reject=self.max_reject, buffers=self._bufs, events=ev[-1] if record_events else None)
             if record_events:
                 ev[-1][3].record()
-            if B > self.pipeline_batch:  # buffers are reused by the next pipeline batch: keep a compact copy
-                res = PlanResult(**{k: (v.clone() if isinstance(v, torch.Tensor) and k in _COMPACT else None)
-                                    for k, v in res.__dict__.items()})
+            # the buffers are reused by the next pipeline batch / the next call: the result records are copies
+            res = PlanResult(**{k: (v.clone() if isinstance(v, torch.Tensor) and k in _COMPACT else (v if self.keep_tree else None))
+                                for k, v in res.__dict__.items()})
             outs.append(res)
         self._events = ev
         if len(outs) == 1:
@@ -391,14 +410,19 @@ class GuidedPlanner(object):
         return PlanResult(**{k: (torch.cat([getattr(o, k) for o in outs]) if k in _COMPACT else None)
                              for k in outs[0].__dict__})
 
+    def last_logits(self) -> torch.Tensor:
+        """Raw network output [B, cells] fp32 of the last pipeline batch of the last plan() call (a view of the reusable buffer)."""
+        return self._logits
+
     def stage_ms(self):
-        """(cnn, cdf, draw+plan) milliseconds of the last plan(record_events=True) call, after a synchronize."""
-        c = d = p = 0.0
-        for e in self._events:
+        """(cnn, cdf, draw, plan) milliseconds of the last plan(record_events=True) call, after a synchronize."""
+        c = d = w = p = 0.0
+        for e in self._events:  # [start, after cnn, after cdf, end, between draw and plan]
             c += e[0].elapsed_time(e[1])
             d += e[1].elapsed_time(e[2])
-            p += e[2].elapsed_time(e[3])
-        return c, d, p
+            w += e[2].elapsed_time(e[4])
+            p += e[4].elapsed_time(e[3])
+        return c, d, w, p
 
 
 _COMPACT = ("n_nodes", "iterations", "status", "goal_node", "best_node", "best_dist", "path_n", "path_idx", "path_len")

@@ -5,6 +5,8 @@ import glob
 import random  # noqa: F401  (module attribute = the randomness injection point, as in the reference)
 import sys
 
+import cv2
+
 from ._planner_base import Node, RRTStarBase, calculate_length, get_from_string  # noqa: F401
 
 MAPS_DIRECTORY = '/home/czarek/mgr/maps/start_finish/*.png'
@@ -34,3 +36,27 @@ class RRTStar(RRTStarBase):
 
     def search_space_volume(self) -> float:
         return self.map_width * self.map_height
+
+
+def generate_paths(maps=None):
+    """The reference's demo (rrt_star.py:277-297): the first task file of MAPS_DIRECTORY -> one plan.  Plotting is a no-op
+    (out of scope); returns (map_path, path, iterations) of the task it ran, None when the directory is empty."""
+    maps = get_blank_maps_list() if maps is None else maps
+    for map_path in maps:
+        print(map_path)
+        occ_map = cv2.imread(map_path, 0)
+        start, finish = get_start_finish_coordinates(map_path)
+        rrt = RRTStar(occ_map=occ_map, start=start, goal=finish, max_iterations=MAX_ITERATIONS,
+                      goal_threshold=GOAL_THRESHOLD)
+        path, iterations = rrt.rrt_star()
+        if path:
+            print(path)
+            rrt.visualize_path(path)
+        else:
+            print("COULDN'T FIND A PATH FOR THIS EXAMPLE:", map_path)
+        return map_path, path, iterations
+    return None
+
+
+if __name__ == '__main__':
+    generate_paths()

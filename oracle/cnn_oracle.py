@@ -5,8 +5,23 @@ Follows train.py:171-203 (UNet_cooler.forward) and ThreeD_train.py:169-204 (Thre
 torchvision's BasicBlock (resnet.py) / VideoResNet BasicBlock, with eval-mode BatchNorm.  Pinned against the reference
 itself by tests/test_cnn_oracle.py on the golden logits in tests/golden/cnn{2d,3d}_seed0*.npz.
 """
+import contextlib
+
 import torch
 import torch.nn.functional as F
+
+
+@contextlib.contextmanager
+def strict_fp32():
+    """The checker is fp32: on CUDA tensors cuDNN / cuBLAS would otherwise be allowed TF32 (10-bit mantissa) convolutions,
+    which with decoder activations of 100-300 is an error of several 1e-3 in the checker itself."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        yield
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def _bn(x, sd, p):
@@ -35,7 +50,12 @@ def _layer(x, sd, p, dims, stride):
 
 
 def forward(sd, x, coords, dims):
-    """sd: state_dict of UNet_cooler (dims=2) / ThreeD_UNet_cooler (dims=3), fp32 CPU or CUDA tensors."""
+    """sd: state_dict of UNet_cooler (dims=2) / ThreeD_UNet_cooler (dims=3), fp32 CPU or CUDA tensors (TF32 disabled)."""
+    with strict_fp32():
+        return _forward(sd, x, coords, dims)
+
+
+def _forward(sd, x, coords, dims):
     mode = "bilinear" if dims == 2 else "trilinear"
     if dims == 2:
         x1 = F.relu(_conv(F.relu(_conv(x, sd, "conv1.0", 2)), sd, "conv1.2", 2))

@@ -41,6 +41,8 @@ def run(state_dict, dim, shape, occ_maps, task_to_map, starts, goals, coords, se
         x = torch.from_numpy(free01)
         if dim == 2:
             x = x[:, None].repeat(1, 3, 1, 1)
+        else:
+            x = x.permute(0, 3, 1, 2).contiguous()  # ToTensorV2: the file's last axis first (ThreeD_train.py:59-66)
         with torch.no_grad():
             logits = cnn_oracle.forward(state_dict, x, torch.from_numpy(coords), dim).numpy()
         cdfs = np.stack([po.build_cdf(heat_from_logits(logits[b, 0], dim))[0] for b in range(B)])

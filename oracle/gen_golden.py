@@ -195,7 +195,49 @@ def gen_cnn():
              randomize_bn=np.int8(bn), **extra)
 
 
-STEPS = {"radius": gen_radius, "maps": gen_maps, "plans": gen_plans, "draws": gen_draws, "cnn": gen_cnn}
+def gen_cnn_full():
+    """One sample at each BASELINE map size (512^2, 80^3) pushed through the reference's own dataset class, model and
+    harness glue (run_reference.run_dataset_cnn).  Stores the map (bit-packed), the tensors the reference fed to the model,
+    the fp32 CPU logits and what the harness hands to the planner."""
+    mt = np.load(os.path.join(GOLDEN, "maps_tasks.npz"))
+    for three_d, key, task_no in ((False, "2d", 0), (True, "3d", 3)):
+        occ = mt[f"occ{key}_0"]
+        name = os.path.basename(str(mt[f"names{key}_0"][task_no]))
+        o = run_job(job="dataset_cnn", three_d=three_d, seed=0, occ_map=occ, name=name)
+        img = o["image"]
+        assert set(np.unique(img)) <= {0.0, 1.0}
+        # the planner-side map must be the file's map again (3D: ToTensorV2 moved the last axis first, the harness undoes it)
+        pm = o["planner_occ_map"]
+        assert np.array_equal((pm[..., 0] if not three_d else pm) != 0, occ != 0)
+        heat = o["heat_map"]
+        save("cnn3d_80_seed0" if three_d else "cnn2d_512_seed0", occ_bits=np.packbits(occ != 0), occ_shape=np.array(occ.shape),
+             file_name=np.array(name), image_bits=np.packbits(img != 0), image_shape=np.array(img.shape), coords=o["coords"],
+             logits=o["logits"], start=o["start"], finish=o["finish"], seed=np.int64(0),
+             heat_nonzero=np.int64(np.count_nonzero(heat)) if three_d else np.int64(-1),
+             heat_argmax=np.array(np.unravel_index(np.argmax(o["logits"][0, 0]), o["logits"][0, 0].shape)))
+
+
+def gen_long_plans():
+    """Plans that run (close to) all MAX_ITERATIONS = 5000 iterations in the reference itself: one best-effort and one
+    late-solved task per dimension, uniform sampler on the Philox stream (level B).  Minutes of CPU each."""
+    mt = np.load(os.path.join(GOLDEN, "maps_tasks.npz"))
+    for name, occ_key, names_key, task_no, seed in (("plan2d_long_0", "occ2d_0", "names2d_0", 0, 91),
+                                                    ("plan2d_long_1", "occ2d_1", "names2d_1", 9, 91),
+                                                    ("plan3d_long_0", "occ3d_0", "names3d_0", 0, 92),
+                                                    ("plan3d_long_1", "occ3d_0", "names3d_0", 5, 92)):
+        three_d = "3d" in name
+        occ = mt[occ_key]
+        start, goal = (parse_name_3d if three_d else parse_name_2d)(str(mt[names_key][task_no]))
+        thr = 3.0 if three_d else 5.0
+        tr = run_job(job="plan", module="ThreeD_rrt_star" if three_d else "rrt_star",
+                     occ_map=occ.astype(np.float64) if three_d else occ, start=np.array(start), goal=np.array(goal),
+                     max_iterations=5000, goal_threshold=thr, stream_seed=seed, stream_task=task_no)
+        save(name, occ_map=np.packbits(occ != 0), occ_shape=np.array(occ.shape), start=np.array(start), goal=np.array(goal),
+             max_iterations=np.int32(5000), goal_threshold=np.float64(thr), stream_seed=np.int64(seed),
+             stream_task=np.int32(task_no), **{"ref_" + k: v for k, v in tr.items()})
+
+
+STEPS = {"radius": gen_radius, "maps": gen_maps, "plans": gen_plans, "draws": gen_draws, "cnn": gen_cnn, "long_plans": gen_long_plans, "cnn_full": gen_cnn_full}
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()

@@ -203,6 +203,56 @@ def run_cnn(job):
     return out
 
 
+def run_dataset_cnn(job):
+    """The reference's own data path in front of the model: a task file written to disk, read back by `MapsDataset`
+    (train.py:38-69 / ThreeD_train.py:38-66: min-max normalisation, coordinates parsed from the file name, ToTensorV2),
+    random-init model forward on CPU fp32, then the evaluation harness's glue: `get_occmap_and_coordinates`
+    (test_network_and_algorithms.py:37-49 / ThreeD_test_network_and_algorithms.py:37-54) and the post-processing in front
+    of the planner (clamp(-3, 1), :109-114 / min-max + 0.96 threshold, :98-105)."""
+    import tempfile
+    from pathlib import Path
+    import torch
+    _patch_torchvision()
+    three_d = bool(job["three_d"])
+    name = str(job["name"])
+    occ = np.asarray(job["occ_map"])
+    with tempfile.TemporaryDirectory() as td:
+        os.makedirs(os.path.join(td, "images"))
+        os.makedirs(os.path.join(td, "masks"))
+        rng = np.random.default_rng(0)
+        if three_d:
+            import ThreeD_train as T
+            np.save(os.path.join(td, "images", name), occ)
+            np.save(os.path.join(td, "masks", name), rng.random(occ.shape))
+        else:
+            import train as T
+            from PIL import Image
+            Image.fromarray(occ).save(os.path.join(td, "images", name))
+            Image.fromarray((rng.random(occ.shape) * 255).astype(np.uint8)).save(os.path.join(td, "masks", name))
+        ds = T.MapsDataset(Path(td), [name], T.MapsDataModule(main_path=Path(td)).transforms)
+        image, mask, coords = ds[0]
+    image, coords = image[None], coords[None]  # DataLoader(batch_size=1)
+    torch.manual_seed(int(job["seed"]))
+    model = (T.ThreeD_UNet_cooler() if three_d else T.UNet_cooler()).eval()
+    with torch.no_grad():
+        output = model(image, coords)
+    if three_d:
+        occ_map = np.array(image[0].detach().cpu().numpy()).transpose((1, 2, 0))
+        c = coords.data.tolist()[0][0]
+        start, finish = tuple(int(v) for v in c[0]), tuple(int(v) for v in c[1])
+        v = np.array(output[0, 0].detach().cpu().numpy())
+        v = ((v - v.min()) / (v.max() - v.min())) * 1.0
+        heat = v.copy()
+        heat[~(v > 0.96)] = 0
+    else:
+        occ_map = np.array(image.data.detach().cpu().numpy()).transpose((0, 2, 3, 1))[0]
+        c = coords.data.tolist()[0][0]
+        start, finish = (int(c[0][1]), int(c[0][0])), (int(c[1][1]), int(c[1][0]))
+        heat = torch.clamp(output, min=-3, max=1).detach().cpu().numpy().transpose((0, 2, 3, 1))
+    return {"image": image.numpy(), "coords": coords.numpy(), "logits": output.numpy(), "planner_occ_map": occ_map,
+            "start": np.array(start), "finish": np.array(finish), "heat_map": heat}
+
+
 def run_gen(job):
     """generate_maps.create_map + generate_tasks.draw_start_and_finish under random.seed (2D or 3D)."""
     three_d = bool(job["three_d"])
@@ -244,7 +294,8 @@ def run_radius(job):
     return {"radius": np.array(out, dtype=np.float64)}
 
 
-JOBS = {"plan": run_plan, "neural_draws": run_neural_draws, "cnn": run_cnn, "gen": run_gen, "radius": run_radius}
+JOBS = {"plan": run_plan, "neural_draws": run_neural_draws, "cnn": run_cnn, "gen": run_gen, "radius": run_radius,
+        "dataset_cnn": run_dataset_cnn}
 
 
 def main():

@@ -1,4 +1,4 @@
-"""Scratch: one encoder pass (8 maps) + decoder micro-batches (10 tasks) of the 2D CNN at 512x512, for ncu captures
+"""Scratch: one encoder pass (8 maps) + decoder micro-batches (40 tasks = 4 maps, the bench's micro-batch) of the 2D CNN at 512x512, for ncu captures
 and CUDA-event timing of individual layers.  Not the bench contract.
 
     python scripts/conv_probe.py [n_decode]     prints the per-layer event timings of the last decode
@@ -15,10 +15,11 @@ from mgr_sampling_cnn_b200 import cnn, train, workload  # noqa: E402
 dev = torch.device("cuda:0")
 n_dec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 wl = workload.make_2d(80)
+MB = 40  # tasks per decoder launch, as GuidedPlanner runs them (engine.py)
 torch.manual_seed(0)
 model = train.UNet_cooler().eval().to(dev)
 plan = model._plan(dev)
-prof = cnn.ConvProfiler()
+prof = cnn.ConvProfiler(sample_every=1)
 plan.set_profiler(prof)
 occ = torch.from_numpy(wl.occ_maps).to(dev)
 coords = torch.from_numpy(wl.coords).to(dev)
@@ -29,19 +30,19 @@ prof.active = True
 enc = plan.encode(grid, 8, occ=occ, maps=maps)
 prof.active = False
 enc_bytes, enc_launches = sum(prof.bytes), len(prof.bytes)
-prof.records.clear(); prof.names.clear(); prof.bytes.clear()
-logits = torch.empty((10, 512 * 512), dtype=torch.float32, device=dev)
+prof.reset()
+logits = torch.empty((MB, 512 * 512), dtype=torch.float32, device=dev)
 for it in range(n_dec):
     prof.active = it >= max(n_dec - 4, 1)
-    m = it % 8
-    rel = torch.full((10,), m, dtype=torch.int32, device=dev)
-    plan.decode(enc, 10, grid, coords[m * 10:(m + 1) * 10], plan.slice_prep(prep, m * 10, (m + 1) * 10), rel, logits, res_group=10)
+    m = (it % 2) * MB
+    rel = (torch.arange(m, m + MB, device=dev) // 10).to(torch.int32)
+    plan.decode(enc, MB, grid, coords[m:m + MB], plan.slice_prep(prep, m, m + MB), rel, logits, res_group=10)
 torch.cuda.synchronize()
 for name, (n, fl, ms) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
     print(f"{name:10s} {ms / n:8.4f} ms  {fl / max(ms, 1e-9) / 1e9:8.1f} TFLOP/s")
 n_prof = max(n_dec - max(n_dec - 4, 1), 1)  # decode passes recorded
 dec_bytes, dec_launches = sum(prof.bytes) / n_prof, len(prof.bytes) // n_prof
-print(f"algorithmic DRAM bytes of one encoder pass (8 maps) + one decoder micro-batch (10 tasks): "
+print(f"algorithmic DRAM bytes of one encoder pass (8 maps) + one decoder micro-batch ({MB} tasks): "
       f"{(enc_bytes + dec_bytes) / (enc_launches + dec_launches):.0f} per launch over {enc_launches + dec_launches} launches")
 
 if plan.use_fold(grid):  # the decomposition below times the unfolded conv7.0 / conv8.0

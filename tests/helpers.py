@@ -8,12 +8,30 @@ from oracle import planner_oracle as po
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 PLAN_FIXTURES = ["plan2d_uniform_mt_0", "plan2d_uniform_mt_1", "plan2d_uniform_stream", "plan2d_neural_stream",
                  "plan3d_uniform_mt_0", "plan3d_uniform_stream", "plan3d_neural_stream"]
-STREAM_FIXTURES = [n for n in PLAN_FIXTURES if n.endswith("_stream")]
+# reference plans at MAX_ITERATIONS = 5000 (uniform sampler on the Philox stream): *_0 run all 5000 iterations (best
+# effort), *_1 are solved after > 4000 iterations
+LONG_FIXTURES = ["plan2d_long_0", "plan2d_long_1", "plan3d_long_0", "plan3d_long_1"]
+STREAM_FIXTURES = [n for n in PLAN_FIXTURES if n.endswith("_stream")] + LONG_FIXTURES
+PLAN_FIXTURES = PLAN_FIXTURES + LONG_FIXTURES
 
 
 def load(name):
     with np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False) as z:
-        return {k: z[k] for k in z.files}
+        g = {k: z[k] for k in z.files}
+    if name in LONG_FIXTURES:  # the map is stored bit-packed (255 = free in 2D / obstacle in 3D)
+        shape = tuple(g["occ_shape"])
+        g["occ_map"] = (np.unpackbits(g["occ_map"])[:int(np.prod(shape))].reshape(shape) * 255).astype(np.uint8)
+    return g
+
+
+def load_full_cnn(name):
+    """cnn2d_512_seed0 / cnn3d_80_seed0 (oracle/gen_golden.py::gen_cnn_full): the occupancy map as the task file holds it
+    (uint8, 255 = free in 2D / obstacle in 3D), the tensor the reference's MapsDataset fed to the model, coords, fp32 logits."""
+    g = load(name)
+    occ_shape, img_shape = tuple(g["occ_shape"]), tuple(g["image_shape"])
+    g["occ"] = (np.unpackbits(g["occ_bits"])[:int(np.prod(occ_shape))].reshape(occ_shape) * 255).astype(np.uint8)
+    g["x"] = np.unpackbits(g["image_bits"])[:int(np.prod(img_shape))].reshape(img_shape).astype(np.float32)
+    return g
 
 
 def fixture_dim(name):

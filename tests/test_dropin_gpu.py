@@ -106,3 +106,131 @@ def test_evaluation_harness_table(cuda_device):
                             keep_tree=True)
     for b in range(20):
         assert harness.calculate_length(res.path_points(b)) == float(res.path_len[b]) == float(df[("RRT*", "Length")][b])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_generate_neural_sample_continues_the_stream_like_the_reference(dim, cuda_device):
+    """300 direct generate_neural_sample() calls: the reference's recorded points AND its draw count, call by call, on
+    the injected stream (no bias draw is consumed by the method itself; 3D redraws until the voxel is free)."""
+    g = H.load("neural_draws")
+    mod = _module("neural_rrt" if dim == 2 else "ThreeD_neural_rrt")
+    if dim == 2:
+        occ = np.repeat((g["occ2d"].astype(np.float32) / 255.0)[:, :, None], 3, axis=2)
+        heat, seed, task, ref, nd = g["heat2d"], int(g["seed2d"]), int(g["task2d"]), g["draws2d"], int(g["ndraws2d"])
+    else:
+        occ = (g["occ3d"] != 0).astype(np.float32)
+        heat, seed, task, ref, nd = g["heat3d"], int(g["seed3d"]), int(g["task3d"]), g["draws3d"], int(g["ndraws3d"])
+    rnd = mod.random = StreamRandom(seed, task)
+    planner = mod.RRTStar(occ, heat, (1,) * dim, (1,) * dim, 10, 1.0, 1.0)
+    out = [planner.generate_neural_sample() for _ in range(60)]
+    assert np.array_equal(np.array(out, np.int32), ref[:60])
+    # host-side draws in between (what the reference's own loop does with `random.random() < bias`) keep the lock-step
+    u_ref = StreamRandom(seed, task)
+    u_ref.draws = rnd.draws
+    assert rnd.random() == u_ref.random()
+    rnd.draws -= 1
+    out += [planner.generate_neural_sample() for _ in range(240)]
+    assert np.array_equal(np.array(out, np.int32), ref) and rnd.draws == nd
+    s = planner.generate_random_sample()
+    assert rnd.draws >= nd + dim and (g["occ2d"][s] != 0 if dim == 2 else g["occ3d"][s] == 0)
+
+
+def test_rrt_star_leaves_the_stream_where_the_reference_left_it(cuda_device):
+    g = H.load("plan2d_neural_stream")
+    mod = _module("neural_rrt")
+    rnd = mod.random = StreamRandom(int(g["stream_seed"]), int(g["stream_task"]))
+    occ = np.repeat((g["occ_map"].astype(np.float32) / 255.0)[:, :, None], 3, axis=2)
+    planner = mod.RRTStar(occ, g["heat_map"], tuple(int(v) for v in g["start"]), tuple(int(v) for v in g["goal"]),
+                          int(g["max_iterations"]), float(g["goal_threshold"]), float(g["neural_bias"]))
+    _, iters = planner.rrt_star()
+    assert iters == int(g["ref_iterations"]) and rnd.draws == int(g["ref_draws"])
+
+
+@pytest.mark.parametrize("fixture,modname", [("plan2d_uniform_mt_0", "rrt_star"), ("plan3d_uniform_mt_0", "ThreeD_rrt_star")])
+def test_main_loop_from_the_callable_methods(fixture, modname, cuda_device):
+    """The reference's loop body (rrt_star.py:184-215) written out with the drop-in's individually callable methods --
+    find_nearest_neighbor, steer, can_connect_nodes, rewire_tree, goal_reached -- on the reference's recorded samples:
+    node positions, parents and costs after 120 iterations equal the reference's tree at that point."""
+    g = H.load(fixture)
+    mod = _module(modname)
+    dim = H.fixture_dim(fixture)
+    occ = g["occ_map"] if dim == 2 else g["occ_map"].astype(np.float64)
+    start, goal = tuple(int(v) for v in g["start"]), tuple(int(v) for v in g["goal"])
+    planner = mod.RRTStar(occ, start, goal, 120, float(g["goal_threshold"]))
+    ref = mod.RRTStar(occ, start, goal, 120, float(g["goal_threshold"]))
+    smp = np.zeros((120, dim))
+    smp[:] = g["ref_samples"][:120]
+    res = __import__("mgr_sampling_cnn_b200.engine", fromlist=["x"]).plan_batch(
+        ref._bits, np.zeros(1, np.int32), np.array([start], np.int32), np.array([goal], np.int32), dim=dim, shape=occ.shape,
+        max_iterations=120, goal_threshold=float(g["goal_threshold"]), samples=smp.astype(np.int16)[None], keep_tree=True)
+    for i in range(120):
+        planner.iteration_no = i + 1
+        planner.search_radius = planner.compute_search_radius(dim)
+        sample = tuple(int(v) for v in g["ref_samples"][i])
+        nearest = planner.find_nearest_neighbor(sample)
+        new = planner.steer(nearest, sample)
+        if planner.can_connect_nodes(nearest, new):
+            planner.rewire_tree(new)
+            if planner.goal_reached(new, planner.goal):
+                break
+            planner.nodes.append(new)
+    n = len(planner.nodes)
+    assert n == int(res.n_nodes[0]) and n > 60
+    index = {id(m): j for j, m in enumerate(planner.nodes)}
+    assert np.array_equal(np.array([m.position for m in planner.nodes], np.float64), res.pos[0, :n].cpu().numpy())
+    assert np.array_equal(np.array([m.cost for m in planner.nodes]), res.cost[0, :n].cpu().numpy())
+    assert np.array_equal(np.array([-1 if m.parent is None else index[id(m.parent)] for m in planner.nodes]),
+                          res.parent[0, :n].cpu().numpy())
+
+
+def _write_task_files(tmp_path, three_d, n=3):
+    """A tiny evaluation set in the reference's on-disk format (generate_tasks.py:76-82 names; train.py:38-60 reader)."""
+    from mgr_sampling_cnn_b200 import workload
+    wl = workload.make_3d(n, size=32) if three_d else workload.make_2d(n, size=128)
+    (tmp_path / "images").mkdir()
+    (tmp_path / "masks").mkdir()
+    names = []
+    for b in range(n):
+        occ = wl.occ_maps[wl.task_to_map[b]]
+        if three_d:
+            s, f = wl.starts[b], wl.goals[b]
+            name = f"map_0_path{b}_sx{s[0]}_sy{s[1]}_sz{s[2]}_fx{f[0]}_fy{f[1]}_fz{f[2]}.npy"
+            np.save(tmp_path / "images" / name, occ)
+            np.save(tmp_path / "masks" / name, np.random.default_rng(b).random(occ.shape))
+        else:
+            import cv2
+            (sy, sx), (fy, fx) = wl.starts[b], wl.goals[b]
+            name = f"map_0_path{b}_sx{sx}_sy{sy}_fx{fx}_fy{fy}.png"
+            cv2.imwrite(str(tmp_path / "images" / name), occ)
+            cv2.imwrite(str(tmp_path / "masks" / name), (np.random.default_rng(b).random(occ.shape) * 255).astype(np.uint8))
+        names.append(name)
+    return wl, names
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+def test_generate_paths_demos(three_d, tmp_path, cuda_device):
+    """generate_paths() of the four modules on task files in the reference's directory layout (weights: a saved random-init
+    state_dict standing in for the trained .pth).  Start / finish as parsed from the file names; a path ends at the goal."""
+    import torch
+    wl, names = _write_task_files(tmp_path, three_d)
+    uni = _module("ThreeD_rrt_star" if three_d else "rrt_star")
+    neu = _module("ThreeD_neural_rrt" if three_d else "neural_rrt")
+    uni.MAPS_DIRECTORY = str(tmp_path / "images" / ("*.npy" if three_d else "*.png"))
+    assert [p.split("/")[-1] for p in uni.get_blank_maps_list()] == sorted(names)
+    uni.MAX_ITERATIONS = neu.MAX_ITERATIONS = 1500
+    try:
+        map_path, path, iters = uni.generate_paths()
+        s, f = uni.get_start_finish_coordinates(map_path)
+        assert 1 <= iters <= 1500 and (not path or tuple(path[0]) == s)
+        from mgr_sampling_cnn_b200 import ThreeD_train, train
+        torch.manual_seed(0)
+        model = (ThreeD_train.ThreeD_UNet_cooler() if three_d else train.UNet_cooler())
+        torch.save(model.state_dict(), tmp_path / "weights.pth")
+        neu.BASE_PATH, neu.MODEL_PATH = tmp_path, str(tmp_path / "weights.pth")
+        assert len(neu.get_blank_maps_list()) == 3
+        out = neu.generate_paths(index=0)
+        assert 1 <= out["neural"][1] <= 1500 and out["neural"][2] > 0
+        if not three_d:
+            assert 1 <= out["plain"][1] <= 1500
+    finally:
+        uni.MAX_ITERATIONS = neu.MAX_ITERATIONS = 5000

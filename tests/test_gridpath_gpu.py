@@ -75,3 +75,70 @@ def test_3d_batch_symmetry_and_bounds(cuda_device):
         d = np.sort(np.abs(wl.starts[b].astype(int) - wl.goals[b].astype(int)))
         free = (d[2] - d[1]) + (d[1] - d[0]) * np.sqrt(2) + d[0] * np.sqrt(3)
         assert fwd[0][b] >= free - 1e-9
+
+
+def _serpentine(h, w):
+    """Walls on every other row with a one-cell door alternating left / right: one corridor of ~h/2 * w cells."""
+    occ = np.full((h, w), 255, np.uint8)
+    for k, r in enumerate(range(1, h, 2)):
+        occ[r, :] = 0
+        occ[r, (w - 1) if k % 2 == 0 else 0] = 255
+    return occ
+
+
+def _diagonal_maze(n=256, period=8, width=4):
+    """Diagonal stripes (free iff (r - c) mod 8 < 4) joined by doors alternately near their two ends: shortest paths run
+    thousands of DIAGONAL steps (a diagonal move needs both orthogonal neighbours free: the stripes are 4 wide)."""
+    r, c = np.mgrid[0:n, 0:n]
+    occ = np.where((r - c) % period < width, 255, 0).astype(np.uint8)
+    for j in range(-n // period, n // period):
+        lo = period * j + width
+        cells = [(rr, rr - d) for d in range(lo, lo + period - width) for rr in range(n) if 0 <= rr - d < n]
+        if not cells:
+            continue
+        s = np.array([rr + cc for rr, cc in cells])
+        target = (s.min() + 6) if j % 2 == 0 else (s.max() - 6)
+        for (rr, cc), sv in zip(cells, s):
+            if abs(sv - target) <= 1:
+                occ[rr, cc] = 255
+    return occ
+
+
+def test_thousands_of_diagonal_steps_exact(cuda_device):
+    """Candidate costs n1 + n2 sqrt(2) with n2 in the thousands are ordered exactly (38 fraction bits): step counts to 64
+    goals spread over the maze equal the oracle's heap Dijkstra."""
+    from oracle import astar_oracle as ao
+    occ = _diagonal_maze()
+    ns, nd = ao.dial_lengths(occ, (1, 0))
+    assert nd.max() > 4000
+    rng = np.random.default_rng(5)
+    cand = np.argwhere(ns >= 0)
+    goals = np.concatenate([cand[rng.choice(len(cand), 63, replace=False)], [[0, 245]]]).astype(np.int32)
+    bits = engine.pack_occupancy(occ[None], 2, cuda_device)
+    length, steps = engine.grid_path_lengths(bits, np.zeros(64, np.int32), np.tile(np.array([[1, 0]], np.int32), (64, 1)),
+                                             goals, occ.shape)
+    torch.cuda.synchronize()
+    steps = steps.cpu().numpy()
+    for b, (gy, gx) in enumerate(goals):
+        assert (int(ns[gy, gx]), int(nd[gy, gx]), 0) == tuple(steps[b].tolist()), f"goal {gy, gx}"
+
+
+def test_long_paths_and_the_cost_limit(cuda_device):
+    """Paths of thousands of steps (far beyond the ~1000 diagonal steps where a 20-bit fraction could misorder candidates):
+    exact step counts vs the oracle's Dijkstra; a path longer than the label format's cost limit (8191) is reported as
+    "limit" (-2, +inf), never as "no path"."""
+    from oracle import astar_oracle as ao
+    small, big = _serpentine(128, 96), _serpentine(512, 512)
+    ns, nd = ao.dial_lengths(small, (0, 0))
+    goal = (126, 95)
+    assert 5000 < ns[goal] + nd[goal] < 8000
+    for occ, g, expect in ((small, goal, (int(ns[goal]), int(nd[goal]), 0)), (big, (510, 511), (-2, -2, -2))):
+        bits = engine.pack_occupancy(occ[None], 2, cuda_device)
+        length, steps = engine.grid_path_lengths(bits, np.zeros(1, np.int32), np.array([[0, 0]], np.int32),
+                                                 np.array([g], np.int32), occ.shape)
+        torch.cuda.synchronize()
+        assert tuple(steps[0].cpu().tolist()) == expect
+        if expect[0] >= 0:
+            assert abs(float(length[0]) - (expect[0] + expect[1] * np.sqrt(2))) <= 1e-9 * float(length[0])
+        else:
+            assert np.isposinf(float(length[0]))

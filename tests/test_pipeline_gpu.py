@@ -1,0 +1,110 @@
+"""GPU parity of the whole path at BASELINE map sizes: CNN logits against logits recorded from the reference itself
+(512^2 and 80^3, fed by the reference's own MapsDataset), and GuidedPlanner.plan end to end against the CPU oracle driven
+by the GPU's own logits (only the CNN is a tolerance comparison, everything after it is bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import planner_oracle as po
+from oracle import cpu_path
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-2  # north_star: CNN probability map <= 1e-2 abs against the fp32 reference forward
+
+
+def _model(three_d, dev):
+    from mgr_sampling_cnn_b200 import ThreeD_train, train
+    torch.manual_seed(0)
+    return (ThreeD_train.ThreeD_UNet_cooler() if three_d else train.UNet_cooler()).eval().to(dev)
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+def test_forward_at_baseline_size_matches_reference_logits(three_d, cuda_device):
+    """UNet_cooler / ThreeD_UNet_cooler.forward(x, coords) on the tensors the reference's dataset produced."""
+    g = H.load_full_cnn("cnn3d_80_seed0" if three_d else "cnn2d_512_seed0")
+    model = _model(three_d, cuda_device)
+    y = model(torch.from_numpy(g["x"]).to(cuda_device), torch.from_numpy(g["coords"]).to(cuda_device))
+    torch.cuda.synchronize()
+    assert y.shape == g["logits"].shape and y.dtype == torch.float32
+    err = np.abs(y.cpu().numpy() - g["logits"]).max()
+    assert err <= TOL, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+def test_probability_maps_from_task_file_match_reference_logits(three_d, cuda_device):
+    """The map-fed path (uint8 task-file arrays -> nrrt_stem_conv_maps -> ...) reproduces the reference's data path:
+    {0,1} normalisation, 3 equal channels in 2D, ToTensorV2's axis order in 3D; the output is consumed un-transposed."""
+    from mgr_sampling_cnn_b200 import engine
+    g = H.load_full_cnn("cnn3d_80_seed0" if three_d else "cnn2d_512_seed0")
+    model = _model(three_d, cuda_device)
+    gp = engine.GuidedPlanner(model, 3 if three_d else 2, g["occ"].shape)
+    occ = torch.from_numpy(g["occ"][None]).to(cuda_device)
+    t2m = torch.zeros(3, dtype=torch.int32, device=cuda_device)
+    coords = torch.from_numpy(np.repeat(g["coords"], 3, 0)).to(cuda_device)
+    coords[1] += 1.0  # a second and a third task on the same map must not disturb the first
+    coords[2] -= 1.0
+    y = gp.probability_maps(occ, t2m, coords)
+    torch.cuda.synchronize()
+    err = np.abs(y[0].cpu().numpy().reshape(g["logits"].shape[2:]) - g["logits"][0, 0]).max()
+    assert err <= TOL, f"max abs err {err}"
+    if three_d:  # orientation check proper: the transposed reading must NOT match
+        wrong = np.abs(y[0].cpu().numpy().reshape(g["logits"].shape[2:]).transpose(1, 2, 0) - g["logits"][0, 0]).max()
+        assert wrong > 10 * TOL
+
+
+def _oracle_tail(dim, shape, occ_maps, t2m, logits, starts, goals, seed, ids, max_iter, thr, res):
+    """GPU logits -> oracle post-processing + CDF + draws + plan; compare everything with the GPU's own results."""
+    rad = po.radius_table(dim, shape, max_iter)
+    samples = res.samples.cpu().numpy()
+    flags = res.neural_flag.cpu().numpy()
+    n_draws = res.n_draws.cpu().numpy()
+    status = res.status.cpu().numpy()
+    n_nodes, iters = res.n_nodes.cpu().numpy(), res.iterations.cpu().numpy()
+    goal_node = res.goal_node.cpu().numpy()
+    parent, cost, pos = res.parent.cpu().numpy(), res.cost.cpu().numpy(), res.pos.cpu().numpy()
+    plen = res.path_len.cpu().numpy()
+    for b in range(len(t2m)):
+        occ = occ_maps[t2m[b]]
+        free = po.occ_free_2d(occ) if dim == 2 else po.occ_free_3d(occ)
+        heat = cpu_path.heat_from_logits(logits[b].reshape(shape), dim)
+        cdf = po.build_cdf(heat)[0]
+        smp, fl, nd, st = po.draw_samples(dim, shape, free, cdf, 0.75, seed, int(ids[b]), max_iter)
+        if st != 0:
+            assert status[b] == po.ST_SAMPLER_STUCK
+            continue
+        assert np.array_equal(samples[b], smp.astype(np.int16)), f"task {b}: sample points differ"
+        assert np.array_equal(flags[b], fl) and n_draws[b] == nd
+        o = po.plan(dim, shape, free, rad, smp.astype(np.float64), starts[b], goals[b], max_iter, thr, pow_mode=1)
+        n = o["n_nodes"] + (1 if o["goal_node"] >= 0 else 0)
+        assert (status[b], n_nodes[b], iters[b], goal_node[b]) == (o["status"], o["n_nodes"], o["iterations"], o["goal_node"])
+        assert np.array_equal(parent[b, :n], o["parent"]), f"task {b}: parents differ"
+        assert np.array_equal(cost[b, :n], o["cost"]) and np.array_equal(pos[b, :n], o["pos"])
+        assert plen[b] == o["path_length"]
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_guided_planner_end_to_end_vs_oracle(dim, cuda_device):
+    """GuidedPlanner.plan on 2 maps / 20 tasks at BASELINE map size, MAX_ITERATIONS = 5000: CNN -> CDF -> draws -> RRT*.
+    The CNN is checked against the fp32 oracle (<= 1e-2); from the GPU's own logits on, samples, neural flags, draw
+    counts, parents, costs, positions and path lengths are bit-equal to the CPU oracle."""
+    from mgr_sampling_cnn_b200 import engine, workload
+    from oracle import cnn_oracle
+    wl = workload.make_2d(20) if dim == 2 else workload.make_3d(20)
+    model = _model(dim == 3, cuda_device)
+    gp = engine.GuidedPlanner(model, dim, wl.shape, keep_tree=True)
+    ids = np.arange(100, 120, dtype=np.int32)
+    res = gp.plan(wl.occ_maps, wl.task_to_map, wl.starts, wl.goals, wl.coords, seed=7, task_ids=ids)
+    torch.cuda.synchronize()
+    logits = gp.last_logits().cpu().numpy()
+    # CNN leg vs the fp32 oracle (strict fp32 on the GPU: TF32 disabled inside cnn_oracle.forward)
+    free01 = torch.from_numpy((wl.occ_maps[wl.task_to_map[:4]] != 0).astype(np.float32)).to(cuda_device)
+    x = free01[:, None].repeat(1, 3, 1, 1) if dim == 2 else free01.permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        ref = cnn_oracle.forward({k: v.float() for k, v in model.state_dict().items()}, x,
+                                 torch.from_numpy(wl.coords[:4]).to(cuda_device), dim)
+    err = np.abs(logits[:4].reshape(ref.shape) - ref.cpu().numpy()).max()
+    assert err <= TOL, f"CNN max abs err {err}"
+    _oracle_tail(dim, wl.shape, wl.occ_maps, wl.task_to_map, logits, wl.starts, wl.goals, 7, ids, 5000,
+                 5.0 if dim == 2 else 3.0, res)
+    assert (res.status.cpu().numpy() == po.ST_SOLVED).sum() >= 1

@@ -51,13 +51,13 @@ def test_replay_reference_samples_bit_exact(name, trace, cuda_device):
     g = H.load(name)
     dim = H.fixture_dim(name)
     mi = int(g["max_iterations"])
-    res = _run_gpu(name, g, cuda_device, samples=H.padded_samples(g, mi, dim), trace_cap=8192 if trace else 0)
+    res = _run_gpu(name, g, cuda_device, samples=H.padded_samples(g, mi, dim), trace_cap=65536 if trace else 0)
     _check_against_reference(res, g, dim)
     if trace:
         ref_it, ref_v, _ = H.ref_trace_int(g, dim)
         o = po.plan(dim, g["occ_map"].shape, H.occ_free(name, g), po.radius_table(dim, g["occ_map"].shape, mi),
                     H.padded_samples(g, mi, dim), g["start"], g["goal"], mi, float(g["goal_threshold"]), pow_mode=1,
-                    trace_cap=20000)
+                    trace_cap=80000)
         tn = int(res.trace_n[0])
         assert tn == len(ref_it) == o["trace_len"]
         tr = res.trace[0, :tn].cpu().numpy()

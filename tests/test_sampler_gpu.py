@@ -110,6 +110,8 @@ def test_3d_redraw_runs_and_stuck_sampler(free_mass_cells, max_reject, cuda_devi
     rng = np.random.default_rng(7 + free_mass_cells)
     shape = (16, 16, 16)
     occ = (rng.random(shape) < 0.5).astype(np.uint8) * 255            # 3D: 0 = free
+    if free_mass_cells == 0:
+        occ[0, 0, 0] = occ[-1, -1, -1] = 255   # the two cells the scan always treats as reachable are occupied as well
     heat = np.where(occ != 0, rng.random(shape) + 0.5, 0.0).astype(np.float32)   # all mass on occupied voxels ...
     free_idx = np.argwhere(occ == 0)
     for c in free_idx[rng.choice(len(free_idx), free_mass_cells, replace=False)] if free_mass_cells else []:
@@ -132,6 +134,8 @@ def test_3d_redraw_runs_and_stuck_sampler(free_mass_cells, max_reject, cuda_devi
         assert np.array_equal(res.neural_flag[0].cpu().numpy(), flags)
     elif free_mass_cells:  # the bound tripped: exactly the draws the sequential sampler consumed
         assert int(res.n_draws[0]) == nd
+    else:  # no free voxel carries mass: found by the one-time scan after 256 redraws, not by burning max_reject draws
+        assert int(res.n_draws[0]) < 1024 < max_reject
 
 
 def test_uniforms_on_device_match_numpy(cuda_device):
