@@ -319,7 +319,7 @@ def run_graft(args):
             one(profile)
         e1.record()
         sync_all()
-        return max_over_ranks(e0.elapsed_time(e1)) / steps, out, res
+        return max_over_ranks(e0.elapsed_time(e1)) / max(steps, 1), out, res
 
     # ---- headline: args.workload, `tasks` per GPU, weak scaling (rank r owns global tasks [r B, (r + 1) B)) ----
     dim = 2 if args.workload.startswith("2d") else 3

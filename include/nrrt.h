@@ -167,8 +167,8 @@ typedef struct NrrtConvLayer {
     const void* in;          /* fp16, first channel of the slice to read */
     int64_t in_cstride;      /* channels per pixel of the input buffer */
     const void* weight;
-    const float* scale;
-    const float* shift;
+    const float* scale;      /* folded eval-mode BatchNorm + bias: out = acc * scale[c] + shift[c].  Both NULL = identity */
+    const float* shift;      /* (layers whose bias the caller has put into the constant term of `poly`; stored outputs only) */
     void* out;               /* fp16 output buffer base */
     int64_t out_cstride;     /* channels per pixel of the output buffer (concat target) */
     int64_t out_coffset;     /* first output channel inside that buffer */
@@ -211,9 +211,100 @@ typedef struct NrrtConvLayer {
     int32_t res_group;       /* scheduling hint (pair slab kernel): consecutive samples per group that share residual rows
                                 (res_index: the tasks of one map); tiles run tile-major inside a group so that the shared
                                 residual is read from DRAM once per group.  0 / 1 = sample-major.  Results do not depend on it. */
+    int32_t tag;             /* caller's label of the layer (NrrtLayerTag for the model graphs); only reported back by the
+                                launch profiler below */
 } NrrtConvLayer;
 
 int nrrt_conv_layer(const NrrtConvLayer* layer, void* stream);
+
+/* Launch profiler of nrrt_conv_layer (measurement only; off by default; per host thread).  While it is on, EVERY launch is
+ * counted with its algorithmic FLOPs (2 x MACs over the true input channels) and bytes (every operand and the output
+ * once), and every `sample_every`-th launch is bracketed by CUDA events on its stream.  nrrt_conv_profile_read (after
+ * the stream has been synchronised) returns the totals and, per timed launch, tag / milliseconds / FLOPs / bytes. */
+int nrrt_conv_profile_start(int sample_every);   /* clears earlier records and turns counting on */
+int nrrt_conv_profile_stop(void);                /* pause (records are kept) */
+int nrrt_conv_profile_resume(void);              /* continue counting into the same records */
+int nrrt_conv_profile_read(int64_t* launches_seen, double* flops_seen, double* bytes_seen, int max_records, int32_t* tags,
+                           float* ms, double* flops, double* bytes, int32_t* n_records);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The whole forward in ONE call: UNet_cooler.forward (train.py:171-203) / ThreeD_UNet_cooler.forward
+ * (ThreeD_train.py:169-204) for a batch of tasks fed from resident occupancy maps, with the exact rewrites of DESIGN.md
+ * 4.0 (encoder once per distinct map, first decoder convs split into per-map and per-task parts, coordinate channels as
+ * epilogue polynomials, ConvTranspose folded into the conv behind it).  The layer graph lives in csrc/forward.cu.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct NrrtConvW {   /* one packed layer (device pointers) */
+    const void* weight;      /* fp16, layout as NrrtConvLayer.weight for `kind`; NULL = layer absent */
+    const float* scale;      /* fp32 [rows] or NULL (identity, see NrrtConvLayer) */
+    const float* shift;
+    const float* post_scale; /* optional second affine (3D stem) */
+    const float* post_shift;
+    int32_t kind;            /* NrrtConvKind */
+    int32_t cin, cin2, cout; /* channels read from the first / second source; output channels (per group for ConvTranspose) */
+    int32_t relu;
+    int32_t tag;             /* NrrtLayerTag */
+} NrrtConvW;
+
+typedef enum NrrtLayerTag {  /* labels of the model's tensor-core layers (profiler output, per-layer tables) */
+    NRRT_TAG_STEM2 = 1,
+    NRRT_TAG_ENC = 10,       /* + (stage * 2 + block) * 3 + {0: conv1, 1: conv2, 2: downsample}, stage 0..3 = conv2..conv5 */
+    NRRT_TAG_UP6 = 40, NRRT_TAG_UP7, NRRT_TAG_UP8,
+    NRRT_TAG_C6FULL = 45, NRRT_TAG_C6E, NRRT_TAG_C7E, NRRT_TAG_C8E,
+    NRRT_TAG_C60 = 50, NRRT_TAG_C61, NRRT_TAG_C70, NRRT_TAG_C71, NRRT_TAG_C80, NRRT_TAG_C81,
+    NRRT_TAG_C7F = 60, NRRT_TAG_C8F
+} NrrtLayerTag;
+
+/* Packed parameters of one model on one device.  Produced by the host packer (mgr_sampling_cnn_b200/cnn.py: UNetPlan,
+ * which folds eval-mode BatchNorm, splits / composes the decoder weights and computes the tap moments in host
+ * arithmetic) -- layouts are documented at the consuming entry points above.  Pointers not used by `dims` are NULL. */
+typedef struct NrrtCnnWeights {
+    int32_t dims;                 /* 2: UNet_cooler, 3: ThreeD_UNet_cooler */
+    int32_t stem_cin, stem_cout;  /* first conv: 3 -> 32 (2D) / 1 -> 32 (3D) */
+    const float* stem_w;          /* fp32 [stem_cout][stem_cin * taps] */
+    const float* stem_b;
+    NrrtConvW stem2;              /* conv1[2] (+ the 3D stem's BatchNorm + ReLU as post affine) */
+    NrrtConvW enc[4][2][3];       /* conv2..conv5 = ResNet layer1..4: [stage][block][conv1, conv2, downsample] */
+    const float* coords_w[4];     /* conv_coords_64/128/256/512: fp32 [tap][cin][cout] */
+    const float* coords_b[4];
+    NrrtConvW up6, up7, up8;      /* ConvTranspose k2 s2 (2D: up6 over x5 only, its coordinate rows are moments) */
+    NrrtConvW c6full;             /* 2D: conv6[0] over (upconv6(x5) | x4), per map */
+    NrrtConvW c6e, c7e, c8e;      /* per-map parts of conv6[0] (3D) / conv7[0] / conv8[0] over the encoder channels */
+    NrrtConvW c60, c61, c70, c71, c80, c81;  /* per-task layers: conv6[0] (3D), conv6[2], conv7[0], conv7[2], conv8[0], conv8[2] */
+    NrrtConvW c7f, c8f;           /* 2D: upconv7 -> conv7[0] and upconv8 -> conv8[0] folded (NRRT_CONV_UPFOLD) */
+    const float* bc7;             /* 2D: fp32 [9][256] / [9][128] constants of the folded layers' border cases (biases) */
+    const float* bc8;
+    const float* mt_up6;          /* 2D: tap moments as nrrt_coords_poly_gemm operands: [512][4 * 1 * 512], */
+    const float* mt_c6;           /*     [256][9 * 4 * 512], */
+    const float* mt_c7;           /*     [128][9 * 4 * 256], */
+    const float* mt_c8;           /*     [64][9 * 4 * 128] */
+    const float* w6taps;          /* 2D: conv6[0] over the ConvTranspose channels, fp32 [512][9 * 512] (nrrt_poly16) */
+    const float* b6;              /* 2D: conv6[0] bias */
+    const float* mt3_c6;          /* 3D: [2 * 256][54 * 4 * 512], [2 * 128][54 * 4 * 256], [2 * 64][54 * 4 * 128] */
+    const float* mt3_c7;
+    const float* mt3_c8;
+    const float* head_w;          /* final_conv: fp32 [64] */
+    float head_bias;
+} NrrtCnnWeights;
+
+/* Workspace (device bytes) of nrrt_conv_forward_{2d,3d} for maps of (d, h, w) cells (d = 1 in 2D) and up to n_tasks tasks
+ * per call.  It does not grow with the number of maps: the encoder runs 8 maps at a time. */
+size_t nrrt_conv_forward_workspace_bytes(const NrrtCnnWeights* w, int d, int h, int w_, int n_tasks);
+
+/* logits[t] = model(map task_to_row[t], coords[t]) for t < n_tasks (fp32 [n_tasks][d * h * w], raw network output).
+ * occ_maps: device uint8 [*][cells], the task files' arrays (2D: (h, w); 3D: [x][y][z] with x = h, y = w, z = d sizes,
+ *   presented to the network last axis first like the reference's dataset does, see nrrt_stem_conv_maps);
+ * map_ids: HOST int32 [n_maps], rows of occ_maps of the distinct maps of this call;
+ * task_to_row: HOST int32 [n_tasks], index into map_ids of every task, NON-DECREASING (tasks grouped by map, as the
+ *   reference's task files are: generate_tasks.py:18-24);  both host arrays are copied on `stream` before use;
+ * coords: device fp32 [n_tasks][2][2] (2D: [[sx, sy], [fx, fy]], train.py:57-60) / [n_tasks][2][3];
+ * tasks_per_map: scheduling hint, tasks per map when it is the same for every map (10 in the reference), else 0.
+ * Spatial sizes must be multiples of 8.  Everything is enqueued on `stream`; nothing is allocated. */
+int nrrt_conv_forward_2d(const NrrtCnnWeights* w, const uint8_t* occ_maps, const int32_t* map_ids, int n_maps,
+                         const int32_t* task_to_row, const float* coords, int n_tasks, int h, int w_, int tasks_per_map,
+                         float* logits, void* workspace, size_t ws_bytes, void* stream);
+int nrrt_conv_forward_3d(const NrrtCnnWeights* w, const uint8_t* occ_maps, const int32_t* map_ids, int n_maps,
+                         const int32_t* task_to_row, const float* coords, int n_tasks, int d, int h, int w_, int tasks_per_map,
+                         float* logits, void* workspace, size_t ws_bytes, void* stream);
 
 /* First layer (Cin = 3 in 2D, 1 in 3D; fp32 NCHW / NCDHW input as the reference feeds it) -> fp16 channels-last with
  * `cout_pad` channels (cout real, the rest zero), + bias, ReLU.  weight fp32 [cout][cin][taps], bias fp32 [cout]. */

@@ -14,6 +14,7 @@ SOURCES = {
     "sampler.cu": ["--fmad=false"],
     "conv_tc.cu": [],
     "conv_aux.cu": [],
+    "forward.cu": [],
     "gridpath.cu": [],
 }
 COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

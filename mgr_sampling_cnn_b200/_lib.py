@@ -36,7 +36,40 @@ class NrrtConvLayer(C.Structure):
                 ("cin2", C.c_int32), ("in_n", C.c_int32), ("in2_n", C.c_int32), ("in_index", C.c_void_p), ("in2_index", C.c_void_p),
                 ("res_index", C.c_void_p), ("res_n", C.c_int32),
                 ("no_poly_mma", C.c_int32), ("no_tma_store", C.c_int32),
-                ("poly3", C.c_void_p), ("res_mma", C.c_int32), ("res_group", C.c_int32)]
+                ("poly3", C.c_void_p), ("res_mma", C.c_int32), ("res_group", C.c_int32), ("tag", C.c_int32)]
+
+
+class NrrtConvW(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("post_scale", C.c_void_p),
+                ("post_shift", C.c_void_p), ("kind", C.c_int32), ("cin", C.c_int32), ("cin2", C.c_int32), ("cout", C.c_int32),
+                ("relu", C.c_int32), ("tag", C.c_int32)]
+
+
+class NrrtCnnWeights(C.Structure):
+    _fields_ = [("dims", C.c_int32), ("stem_cin", C.c_int32), ("stem_cout", C.c_int32), ("stem_w", C.c_void_p),
+                ("stem_b", C.c_void_p), ("stem2", NrrtConvW), ("enc", ((NrrtConvW * 3) * 2) * 4), ("coords_w", C.c_void_p * 4),
+                ("coords_b", C.c_void_p * 4), ("up6", NrrtConvW), ("up7", NrrtConvW), ("up8", NrrtConvW), ("c6full", NrrtConvW),
+                ("c6e", NrrtConvW), ("c7e", NrrtConvW), ("c8e", NrrtConvW), ("c60", NrrtConvW), ("c61", NrrtConvW),
+                ("c70", NrrtConvW), ("c71", NrrtConvW), ("c80", NrrtConvW), ("c81", NrrtConvW), ("c7f", NrrtConvW),
+                ("c8f", NrrtConvW), ("bc7", C.c_void_p), ("bc8", C.c_void_p), ("mt_up6", C.c_void_p), ("mt_c6", C.c_void_p),
+                ("mt_c7", C.c_void_p), ("mt_c8", C.c_void_p), ("w6taps", C.c_void_p), ("b6", C.c_void_p), ("mt3_c6", C.c_void_p),
+                ("mt3_c7", C.c_void_p), ("mt3_c8", C.c_void_p), ("head_w", C.c_void_p), ("head_bias", C.c_float)]
+
+
+# NrrtLayerTag (include/nrrt.h)
+TAG_STEM2, TAG_ENC, TAG_UP6, TAG_UP7, TAG_UP8 = 1, 10, 40, 41, 42
+TAG_C6FULL, TAG_C6E, TAG_C7E, TAG_C8E = 45, 46, 47, 48
+TAG_C60, TAG_C61, TAG_C70, TAG_C71, TAG_C80, TAG_C81, TAG_C7F, TAG_C8F = 50, 51, 52, 53, 54, 55, 60, 61
+
+
+def tag_name(tag: int) -> str:
+    names = {TAG_STEM2: "stem2", TAG_UP6: "up6", TAG_UP7: "up7", TAG_UP8: "up8", TAG_C6FULL: "c6full", TAG_C6E: "c6e",
+             TAG_C7E: "c7e", TAG_C8E: "c8e", TAG_C60: "c6.0", TAG_C61: "c6.1", TAG_C70: "c7.0", TAG_C71: "c7.1", TAG_C80: "c8.0",
+             TAG_C81: "c8.1", TAG_C7F: "c7f", TAG_C8F: "c8f"}
+    if TAG_ENC <= tag < TAG_ENC + 24:
+        k = tag - TAG_ENC
+        return f"enc{k // 6 + 2}.{(k // 3) % 2}.{('c1', 'c2', 'ds')[k % 3]}"
+    return names.get(tag, f"tag{tag}")
 
 
 _SIGNATURES = {
@@ -56,6 +89,16 @@ _SIGNATURES = {
     "nrrt_tree_search": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p]),
     "nrrt_conv_layer": (C.c_int, [C.POINTER(NrrtConvLayer), C.c_void_p]),
+    "nrrt_conv_profile_start": (C.c_int, [C.c_int]),
+    "nrrt_conv_profile_stop": (C.c_int, []),
+    "nrrt_conv_profile_resume": (C.c_int, []),
+    "nrrt_conv_profile_read": (C.c_int, [C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "nrrt_conv_forward_workspace_bytes": (C.c_size_t, [C.POINTER(NrrtCnnWeights), C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nrrt_conv_forward_2d": (C.c_int, [C.POINTER(NrrtCnnWeights), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "nrrt_conv_forward_3d": (C.c_int, [C.POINTER(NrrtCnnWeights), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "nrrt_stem_conv": (C.c_int, [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nrrt_stem_conv_maps": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

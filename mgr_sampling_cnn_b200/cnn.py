@@ -28,62 +28,68 @@ def _prod(v):
 
 
 class ConvProfiler(object):
-    """CUDA-event timing of individual nrrt_conv_layer launches (bench.py's roofline leg).  While `active`, EVERY launch is
-    counted (launches, FLOPs, algorithmic bytes: host arithmetic only) and every `sample_every`-th launch is bracketed by
-    events on the launching stream -- a uniform sample over the launch sequence (the sequence has period 29 (encoder pass) /
-    6 (decoder micro-batch), coprime with the default 5), so sum(flops) / sum(time) over the sample estimates the
-    flops-weighted rate of the whole step, not of whichever pass a coarser sampling happened to hit."""
+    """bench.py's roofline leg: a thin view of the library's own launch profiler (nrrt_conv_profile_*, csrc/conv_tc.cu).
+    While `active`, EVERY nrrt_conv_layer launch of this thread -- from the Python layer graph or from inside
+    nrrt_conv_forward_* -- is counted with its algorithmic FLOPs and bytes, and every `sample_every`-th launch is bracketed
+    by CUDA events on its stream: a uniform sample over the launch sequence (period 29 per encoder pass / 6 per decoder
+    micro-batch, coprime with the default 5), so sum(flops) / sum(time) over the sample is the flops-weighted rate of the
+    whole step.  Read the results after a synchronize."""
 
     def __init__(self, sample_every: int = 5):
-        self.active = False
         self.sample_every = max(int(sample_every), 1)
-        self.seen = 0          # launches while active
-        self.flops_seen = 0.0  # their FLOPs (all of them, timed or not)
-        self.bytes_seen = 0.0
-        self.records = []  # (flops, start_event, end_event) of the timed sample
-        self.names = []
-        self.bytes = []    # algorithmic DRAM bytes of each timed launch (inputs + weights + residual rows + outputs, once)
+        self._active = False
+        self._started = False
+        self.seen, self.flops_seen, self.bytes_seen = 0, 0.0, 0.0
+        self.records = []  # (tag, ms, flops, bytes) of the timed sample, filled by collect()
+
+    @property
+    def active(self):
+        return self._active
+
+    @active.setter
+    def active(self, on):
+        on = bool(on)
+        lib = _lib.load()
+        if on and not self._active:  # the first activation clears the library's records, later ones resume counting
+            check(lib.nrrt_conv_profile_resume() if self._started else lib.nrrt_conv_profile_start(self.sample_every))
+            self._started = True
+        elif not on and self._active:
+            check(lib.nrrt_conv_profile_stop())
+        self._active = on
 
     def reset(self):
-        self.seen, self.flops_seen, self.bytes_seen = 0, 0.0, 0.0
-        self.records, self.names, self.bytes = [], [], []
+        check(_lib.load().nrrt_conv_profile_stop())
+        self._started = self._active = False
+        self.seen, self.flops_seen, self.bytes_seen, self.records = 0, 0.0, 0.0, []
 
-    class _Ctx(object):
-        def __init__(self, prof, flops, name=None, nbytes=0.0):
-            self.prof, self.flops, self.name, self.nbytes = prof, flops, name, nbytes
-            prof.seen += 1
-            prof.flops_seen += flops
-            prof.bytes_seen += nbytes
-            self.timed = prof.seen % prof.sample_every == 0
-
-        def __enter__(self):
-            if self.timed:
-                self.a = torch.cuda.Event(enable_timing=True)
-                self.b = torch.cuda.Event(enable_timing=True)
-                self.a.record()
-
-        def __exit__(self, *exc):
-            if self.timed:
-                self.b.record()
-                self.prof.records.append((self.flops, self.a, self.b))
-                self.prof.names.append(self.name)
-                self.prof.bytes.append(self.nbytes)
-
-    def launch(self, flops, name=None, nbytes=0.0):
-        return ConvProfiler._Ctx(self, flops, name, nbytes)
+    def collect(self):
+        """Fetch totals and the timed sample from the library (call after torch.cuda.synchronize())."""
+        import numpy as np
+        lib = _lib.load()
+        seen, fl, by, n = C.c_int64(), C.c_double(), C.c_double(), C.c_int32()
+        check(lib.nrrt_conv_profile_read(C.byref(seen), C.byref(fl), C.byref(by), 0, None, None, None, None, C.byref(n)))
+        m = n.value
+        tags, ms = np.zeros(m, np.int32), np.zeros(m, np.float32)
+        flops, nbytes = np.zeros(m, np.float64), np.zeros(m, np.float64)
+        if m:
+            check(lib.nrrt_conv_profile_read(None, None, None, m, tags.ctypes.data_as(C.c_void_p), ms.ctypes.data_as(C.c_void_p),
+                                             flops.ctypes.data_as(C.c_void_p), nbytes.ctypes.data_as(C.c_void_p), C.byref(n)))
+        self.seen, self.flops_seen, self.bytes_seen = seen.value, fl.value, by.value
+        self.records = list(zip(tags.tolist(), ms.tolist(), flops.tolist(), nbytes.tolist()))
+        return self
 
     def by_layer(self):
-        """{layer name: (launches, flops, milliseconds)} of the timed sample; call after a synchronize."""
+        """{layer name: (launches, flops, milliseconds)} of the timed sample (after collect())."""
         out = {}
-        for (f, a, b), name in zip(self.records, self.names):
-            n, fl, ms = out.get(name, (0, 0.0, 0.0))
-            out[name] = (n + 1, fl + f, ms + a.elapsed_time(b))
+        for tag, ms, f, _ in self.records:
+            name = _lib.tag_name(tag)
+            n, fl, t = out.get(name, (0, 0.0, 0.0))
+            out[name] = (n + 1, fl + f, t + ms)
         return out
 
     def totals(self):
-        """(launches, total flops, total milliseconds) of the timed sample; call after a synchronize."""
-        ms = sum(a.elapsed_time(b) for _, a, b in self.records)
-        return len(self.records), sum(f for f, _, _ in self.records), ms
+        """(launches, total flops, total milliseconds) of the timed sample (after collect())."""
+        return len(self.records), sum(r[2] for r in self.records), sum(r[1] for r in self.records)
 
 
 def _cpu(t, dtype=torch.float32):
@@ -164,7 +170,7 @@ class _Layer(object):
         self.post = post
         self.cin2 = 0  # channels read from the second input (K split)
         self.cin_real = cin_real or cin
-        self.profiler = None
+        self.tag = 0   # NrrtLayerTag: reported back by the library's launch profiler
 
     def flops(self, batch, grid):
         """Algorithmic FLOPs (2 x MACs with the true Cin) of this layer on input grid (D, H, W)."""
@@ -207,19 +213,13 @@ class _Layer(object):
         consecutive samples that share a residual row (include/nrrt.h); poly3: 3D coordinate field E [n, 54, 4, cout] added in
         the epilogue together with the ReLU (instead of nrrt_poly_relu_3d over the stored output)."""
         n = n if n is not None else (idx.shape[0] if idx is not None else x.shape[0])
-        args = (lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx, res_group, poly3)
-        prof = self.profiler
-        if prof is not None and prof.active:
-            with prof.launch(self.flops(n, grid), getattr(self, "name", None), self.algorithmic_bytes(n, grid, x, x2, res, head)):
-                self._run(*args)
-        else:
-            self._run(*args)
+        self._run(lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx, res_group, poly3)
 
     def _run(self, lib, stream, x, x_coff, grid, out, out_coff, res, res_coff, poly, head, x2, idx, idx2, n, res_idx=None,
              res_group=0, poly3=None):
         _lib.count_launch()
         L = _lib.NrrtConvLayer()
-        L.dims, L.kind = self.dims, self.kind
+        L.dims, L.kind, L.tag = self.dims, self.kind, self.tag
         L.n, L.in_d, L.in_h, L.in_w = n, grid[0], grid[1], grid[2]
         L.cin, L.cout = self.cin, self.cout
         L.in_n = x.shape[0]
@@ -411,8 +411,10 @@ class UNetPlan(object):
         def fold(mu, mc, c_up):
             """upconv7 -> conv7.0 / upconv8 -> conv8.0 as ONE layer (_fold_weights); the conv's bias and ReLU stay."""
             w, bc = _fold_weights(mu.weight, mu.bias, _cpu(mc.weight)[:, :c_up], dev)
-            scale, shift = _fold_bn(None, mc.bias, mc.out_channels, dev)
-            layer = _Layer(d, UPFOLD, mu.in_channels, mc.out_channels, w, scale, shift, True)
+            # no BatchNorm here: the affine is the identity and the conv's bias joins the ConvTranspose bias in the constant
+            # term of the epilogue polynomial (nrrt_poly_fold adds `bc` per border case), so the epilogue has no scale/shift
+            bc = (bc.cpu() + _cpu(mc.bias)[None, :]).contiguous().to(dev)
+            layer = _Layer(d, UPFOLD, mu.in_channels, mc.out_channels, w, None, None, True)
             layer.res_mma = UNetPlan.res_mma  # class switch for experiments (profiles/conv_fold_r1.md), never the environment
             return layer, bc
         # 3D: the coordinate channels leave the GEMM too; their (piecewise bilinear) field and the ReLU are applied by
@@ -434,6 +436,7 @@ class UNetPlan(object):
         self.head_b = float(_cpu(model.final_conv.bias).item())
         self._bufs = {}
         self.profiler = None
+        self._assign_tags()
 
     # activation buffers: an encoder set for Be samples (distinct maps) and a decoder set for B samples (tasks)
     def _cached(self, key, make):
@@ -490,21 +493,120 @@ class UNetPlan(object):
         return out
 
     def set_profiler(self, prof):
+        """bench.py: the ConvProfiler whose `active` flag GuidedPlanner.plan toggles around the CNN stage."""
         self.profiler = prof
-        for l in self.layers():
-            l.profiler = prof
-        for name in ("stem2", "up6", "up7", "up8", "c6e", "c7e", "c8e", "c6full", "c7f", "c8f"):
+
+    def _assign_tags(self):
+        T = _lib
+        for name, tag in (("stem2", T.TAG_STEM2), ("up6", T.TAG_UP6), ("up7", T.TAG_UP7), ("up8", T.TAG_UP8),
+                          ("c6full", T.TAG_C6FULL), ("c6e", T.TAG_C6E), ("c7e", T.TAG_C7E), ("c8e", T.TAG_C8E),
+                          ("c7f", T.TAG_C7F), ("c8f", T.TAG_C8F)):
             if getattr(self, name, None) is not None:
-                getattr(self, name).name = name
-        for name in ("c6", "c7", "c8"):
+                getattr(self, name).tag = tag
+        for name, t0 in (("c6", T.TAG_C60), ("c7", T.TAG_C70), ("c8", T.TAG_C80)):
             for i, l in enumerate(getattr(self, name)):
                 if l is not None:
-                    l.name = f"{name}.{i}"
+                    l.tag = t0 + i
         for si, stg in enumerate(self.enc):
             for bi, blk in enumerate(stg):
                 for li, l in enumerate(blk):
                     if l is not None:
-                        l.name = f"enc{si + 2}.{bi}.{('c1', 'c2', 'ds')[li]}"
+                        l.tag = T.TAG_ENC + (si * 2 + bi) * 3 + li
+
+    def c_weights(self):
+        """NrrtCnnWeights (include/nrrt.h) over this plan's packed device tensors: the argument of nrrt_conv_forward_*."""
+        cw = getattr(self, "_c_weights", None)
+        if cw is not None:
+            return cw
+        W = _lib.NrrtCnnWeights()
+
+        def fill(dst, l):
+            if l is None:
+                return
+            dst.weight, dst.scale, dst.shift = _ptr(l.weight), _ptr(l.scale), _ptr(l.shift)
+            if l.post is not None:
+                dst.post_scale, dst.post_shift = _ptr(l.post[0]), _ptr(l.post[1])
+            dst.kind, dst.cin, dst.cin2, dst.cout, dst.relu, dst.tag = l.kind, l.cin, l.cin2, l.cout, 1 if l.relu else 0, l.tag
+
+        W.dims, W.stem_cin, W.stem_cout = self.dims, self.stem_cin, self.stem_cout
+        W.stem_w, W.stem_b = _ptr(self.stem_w), _ptr(self.stem_b)
+        fill(W.stem2, self.stem2)
+        for si, stg in enumerate(self.enc):
+            for bi, blk in enumerate(stg):
+                for li, l in enumerate(blk):
+                    fill(W.enc[si][bi][li], l)
+        for k in range(4):
+            W.coords_w[k], W.coords_b[k] = self.cw[k].data_ptr(), self.cb[k].data_ptr()
+        fill(W.up6, self.up6), fill(W.up7, self.up7), fill(W.up8, self.up8)
+        fill(W.c6e, self.c6e), fill(W.c7e, self.c7e), fill(W.c8e, self.c8e)
+        fill(W.c60, self.c6[0]), fill(W.c61, self.c6[1]), fill(W.c70, self.c7[0]), fill(W.c71, self.c7[1])
+        fill(W.c80, self.c8[0]), fill(W.c81, self.c8[1])
+        if self.poly:
+            fill(W.c6full, self.c6full), fill(W.c7f, self.c7f), fill(W.c8f, self.c8f)
+            W.bc7, W.bc8 = _ptr(self.bc7), _ptr(self.bc8)
+            W.mt_up6, W.mt_c6, W.mt_c7, W.mt_c8 = (_ptr(self.mt[k]) for k in ("e_up6", "e_c6", "e_c7", "e_c8"))
+            W.w6taps, W.b6 = _ptr(self.w6taps), _ptr(self.b6)
+        else:
+            W.mt3_c6, W.mt3_c7, W.mt3_c8 = (_ptr(self.mt3[k]) for k in ("e_c6", "e_c7", "e_c8"))
+        W.head_w, W.head_bias = _ptr(self.head_w), self.head_b
+        self._c_weights = W
+        return W
+
+    def forward_tasks(self, occ_maps, map_ids, task_to_row, coords, logits, tasks_per_map=0):
+        """The whole forward in ONE library call (nrrt_conv_forward_2d / _3d, csrc/forward.cu): logits[t] for task t on map
+        occ_maps[map_ids[task_to_row[t]]].  occ_maps uint8 [n_maps, ...] and coords fp32 on the device; map_ids and
+        task_to_row are HOST int32 arrays (task_to_row non-decreasing); logits fp32 [n_tasks, cells] on the device."""
+        import numpy as np
+        lib = self.lib
+        map_ids = np.ascontiguousarray(map_ids, dtype=np.int32)
+        task_to_row = np.ascontiguousarray(task_to_row, dtype=np.int32)
+        n_tasks, n_maps = int(task_to_row.shape[0]), int(map_ids.shape[0])
+        shp = tuple(int(v) for v in occ_maps.shape[1:])
+        # 3D: the network's (d, h, w) are the map file's (z, x, y) axes
+        d, h, w = (1, shp[0], shp[1]) if self.dims == 2 else (shp[2], shp[0], shp[1])
+        W = self.c_weights()
+        need = lib.nrrt_conv_forward_workspace_bytes(C.byref(W), d, h, w, n_tasks)
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need or ws.device != self.device:
+            self._ws = ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._host_keep = (map_ids, task_to_row)  # copied on the stream: keep the host arrays alive until the next call
+        st = C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        coords = coords.contiguous().float()
+        _lib.count_launch(self.launches_per_forward(task_to_row))
+        if self.dims == 2:
+            check(lib.nrrt_conv_forward_2d(C.byref(W), _ptr(occ_maps), map_ids.ctypes.data_as(C.c_void_p), n_maps,
+                                           task_to_row.ctypes.data_as(C.c_void_p), _ptr(coords), n_tasks, h, w, int(tasks_per_map),
+                                           _ptr(logits), _ptr(ws), ws.numel(), st))
+        else:
+            check(lib.nrrt_conv_forward_3d(C.byref(W), _ptr(occ_maps), map_ids.ctypes.data_as(C.c_void_p), n_maps,
+                                           task_to_row.ctypes.data_as(C.c_void_p), _ptr(coords), n_tasks, d, h, w, int(tasks_per_map),
+                                           _ptr(logits), _ptr(ws), ws.numel(), st))
+        return logits
+
+    def launches_per_forward(self, task_to_row):
+        """Kernels one nrrt_conv_forward_* call enqueues (bench.py's gpu_launches claim), by replaying its schedule
+        (csrc/forward.cu: 8 maps per encoder pass, 40 / 10 tasks per decoder micro-batch, 512 / 128 tasks per
+        coordinate-branch chunk)."""
+        mb, pc = (40, 512) if self.dims == 2 else (10, 128)
+        enc = 25 if self.dims == 2 else 24          # stem, stem2, 19 ResNet convs, per-map partial sums
+        dec = 6 if self.dims == 2 else 13           # 3D: + coordinate fill, three ConvTranspose, post-passes
+        prep = 17 if self.dims == 2 else 10
+        n = len(task_to_row)
+        total, lo, prep_hi = 0, 0, 0
+        while lo < n:
+            g = int(task_to_row[lo]) // 8
+            hi = lo
+            while hi < n and int(task_to_row[hi]) // 8 == g:
+                hi += 1
+            total += enc
+            for i in range(lo, hi, mb):
+                j = min(hi, i + mb)
+                if j > prep_hi:
+                    prep_hi = min(n, i + pc)
+                    total += prep
+                total += dec
+            lo = hi
+        return total
 
     fold = True  # tests: False runs ConvTranspose and the conv after it as separate layers
     res_mma = False  # experiments: folded layers accumulate the residual through the tensor core

@@ -20,6 +20,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
 
 #include "nrrt_common.cuh"
 
@@ -239,8 +242,13 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
         return (((long long)ns * p.oD + od) * p.oH + oh) * p.oW + ow;
     };
     float f[32];
+    if (p.scale) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), sc[lc + i], sh[lc + i]);
+        for (int i = 0; i < 32; ++i) f[i] = fmaf(__uint_as_float(v[i]), sc[lc + i], sh[lc + i]);
+    } else {  // identity affine (scale == NULL): the layer's bias rides in the polynomial's constant term
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+    }
     if (p.poly) {
         int kcase = g;
         if (p.poly_cases == 9)
@@ -364,6 +372,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
 template <int BLOCK_N>
 __device__ __forceinline__ void stage_tile_params(const ConvParams& p, float* dst, int col0, int n, int et, bool affine,
                                                   bool poly) {
+    affine = affine && p.scale;
     if (!affine && !(poly && p.poly)) return;  // nothing changed since this buffer was last filled (uniform per CTA)
     // every epilogue warp must be done reading the old contents (barriers are skipped on tiles that restage nothing)
     asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");
@@ -1697,11 +1706,27 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// Every launcher has the same signature so that a prepared layer can keep a pointer to the one it resolved to.  The
+// dynamic-shared-memory attribute of an instantiation is set once per device, not on every launch.
+typedef int (*LaunchFn)(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr,
+                        const CUtensorMap& mo, const ConvParams& p, int dev, int sms, cudaStream_t st);
+
+template <typename K>
+int set_smem_once(K kern, int bytes, int dev, int& done_dev) {
+    if (done_dev != dev) {
+        NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done_dev = dev;
+    }
+    return NRRT_OK;
+}
+
 template <int BLOCK_N, int STAGES>
-int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap&, const CUtensorMap&,
+                const ConvParams& p, int dev, int sms, cudaStream_t st) {
     using L = SmemLayout<BLOCK_N, STAGES>;
     auto kern = conv_gemm_kernel<BLOCK_N, STAGES>;
-    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    static int done_dev = -1;
+    if (int rc = set_smem_once(kern, (int)L::total, dev, done_dev)) return rc;
     const int total = p.m_tiles * p.n_tiles;
     const int grid = total < sms ? total : sms;
     kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
@@ -1711,11 +1736,12 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap
 
 template <int BLOCK_N, int A_STAGES, int B_STAGES, bool RES, bool PM = false, bool TS = false, bool P3 = false>
 int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo,
-                 const ConvParams& p, int sms, cudaStream_t st) {
+                 const ConvParams& p, int dev, int sms, cudaStream_t st) {
     using L = HaloLayout2<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS, P3>;
     static_assert(L::total <= 232448, "shared memory budget");
     auto kern = conv_halo2_kernel<BLOCK_N, A_STAGES, B_STAGES, RES, PM, TS, P3>;
-    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    static int done_dev = -1;
+    if (int rc = set_smem_once(kern, (int)L::total, dev, done_dev)) return rc;
     const int pairs = ((p.m_tiles + 1) / 2) * (p.fold ? 4 * p.n_tiles : 1);
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);
     kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, mo, p);
@@ -1725,11 +1751,12 @@ int launch_halo2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMa
 
 template <int BLOCK_N, int STAGES, bool RES, bool PM = false, bool TS = false>
 int launch_conv2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap& mr, const CUtensorMap& mo,
-                 const ConvParams& p, int sms, cudaStream_t st) {
+                 const ConvParams& p, int dev, int sms, cudaStream_t st) {
     using L = SmemLayout2<BLOCK_N, STAGES, RES, PM, TS>;
     static_assert(L::total <= 232448, "shared memory budget");
     auto kern = conv_gemm2_kernel<BLOCK_N, STAGES, RES, PM, TS>;
-    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    static int done_dev = -1;
+    if (int rc = set_smem_once(kern, (int)L::total, dev, done_dev)) return rc;
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int grid = 2 * (pairs < sms / 2 ? pairs : sms / 2);  // whole CTA pairs (static cluster dims 2x1x1)
     kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, mr, mo, p);
@@ -1738,10 +1765,12 @@ int launch_conv2(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMa
 }
 
 template <int BLOCK_N, int A_STAGES, int B_STAGES>
-int launch_halo(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const ConvParams& p, int sms, cudaStream_t st) {
+int launch_halo(const CUtensorMap& ma, const CUtensorMap& ma2, const CUtensorMap& mb, const CUtensorMap&, const CUtensorMap&,
+                const ConvParams& p, int dev, int sms, cudaStream_t st) {
     using L = HaloLayout<BLOCK_N, A_STAGES, B_STAGES>;
     auto kern = conv_halo_kernel<BLOCK_N, A_STAGES, B_STAGES>;
-    NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::total));
+    static int done_dev = -1;
+    if (int rc = set_smem_once(kern, (int)L::total, dev, done_dev)) return rc;
     const int grid = p.m_tiles < sms ? p.m_tiles : sms;
     kern<<<grid, kThreads, L::total, st>>>(ma, ma2, mb, p);
     NRRT_CUDA_TRY(cudaGetLastError());
@@ -1765,10 +1794,158 @@ void pick_box(int W, int H, int D, int& bw, int& bh, int& bd) {
         }
 }
 
+// A layer description resolved once: tensor maps, kernel parameters and the kernel instance.  Encoding 3-5 CUtensorMaps per
+// launch (a driver call each) for ~1760 launches per 4096-task step was ~35 ms of host time per step on the launching
+// thread; the buffers of a forward are stable (cnn.py caches them), so the same descriptions recur every micro-batch.
+struct PreparedConv {
+    CUtensorMap ma, ma2, mb, mr, mo;
+    ConvParams p;
+    LaunchFn launch;
+    double flops, bytes;  // algorithmic: 2 x MACs over the channels read; every operand and the output once
+};
+
+// ---- launch profiler (nrrt_conv_profile_*): counts every launch, brackets every n-th with CUDA events ----
+struct ProfRecord { cudaEvent_t a, b; double flops, bytes; int tag; };
+struct ConvProfile {
+    bool on = false;
+    int every = 1;
+    long long seen = 0;
+    double flops = 0.0, bytes = 0.0;
+    std::vector<ProfRecord> recs;
+    std::vector<cudaEvent_t> pool;  // events of earlier sessions, reused
+};
+ConvProfile& profile() {
+    static thread_local ConvProfile p;
+    return p;
+}
+
+int prepare_conv(const NrrtConvLayer* l, PreparedConv& out);
+
+// The per-call pointers that never enter a tensor map or a kernel choice beyond being null or not: the cache key holds
+// only their null-ness, and a cache hit patches their current values into the prepared parameters.
+void patch_volatile(const NrrtConvLayer* l, ConvParams& p) {
+    p.idx1 = l->in_index; p.idx2 = l->in2_index;
+    if (p.res_idx) p.res_idx = l->res_index;
+    if (p.poly) p.poly = l->poly;
+    if (p.poly3) p.poly3 = l->poly3;
+    p.logits = l->logits;
+    p.head_w = l->head_weight; p.head_b = l->head_bias;
+    p.group = l->res_group > 1 ? l->res_group : 1;
+}
+
+struct ConvKey {
+    NrrtConvLayer l;
+    int dev;
+    bool operator==(const ConvKey& o) const { return dev == o.dev && memcmp(&l, &o.l, sizeof(l)) == 0; }
+};
+struct ConvKeyHash {
+    size_t operator()(const ConvKey& k) const {
+        const unsigned char* b = reinterpret_cast<const unsigned char*>(&k.l);
+        uint64_t h = 1469598103934665603ull ^ (uint64_t)k.dev;
+        for (size_t i = 0; i < sizeof(k.l); ++i) h = (h ^ b[i]) * 1099511628211ull;
+        return (size_t)h;
+    }
+};
+
 }  // namespace
 
 extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
-    NRRT_REQUIRE(l && l->in && l->weight && l->scale && l->shift, "null pointer in conv layer");
+    NRRT_REQUIRE(l, "null layer");
+    if (l->poly) NRRT_REQUIRE(((uintptr_t)l->poly & 15) == 0, "poly must be 16-byte aligned");
+    if (l->poly3) NRRT_REQUIRE(((uintptr_t)l->poly3 & 15) == 0, "poly3 must be 16-byte aligned");
+    int dev = 0;
+    NRRT_CUDA_TRY(cudaGetDevice(&dev));
+    static thread_local std::unordered_map<ConvKey, PreparedConv, ConvKeyHash> cache;
+    static thread_local int sms_of[64] = {0};
+    ConvKey key;
+    memset(&key, 0, sizeof(key));
+    key.l = *l;
+    key.dev = dev;
+    auto flag = [](const void* q) { return q ? reinterpret_cast<void*>(1) : nullptr; };
+    key.l.in_index = (const int32_t*)flag(l->in_index); key.l.in2_index = (const int32_t*)flag(l->in2_index);
+    key.l.res_index = (const int32_t*)flag(l->res_index);
+    key.l.poly = (const float*)flag(l->poly); key.l.poly3 = (const float*)flag(l->poly3);
+    key.l.logits = (float*)flag(l->logits);
+    key.l.head_weight = (const float*)flag(l->head_weight); key.l.head_bias = 0.f;
+    key.l.res_group = l->res_group > 1 ? 2 : 0;
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        PreparedConv prep;
+        if (int rc = prepare_conv(l, prep)) return rc;
+        if (cache.size() >= 4096) cache.clear();  // descriptions of buffers that no longer exist
+        it = cache.emplace(key, prep).first;
+    }
+    PreparedConv& pc = it->second;
+    patch_volatile(l, pc.p);
+    int& sms = sms_of[dev & 63];
+    if (!sms) NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    ConvProfile& prof = profile();
+    if (!prof.on) return pc.launch(pc.ma, pc.ma2, pc.mb, pc.mr, pc.mo, pc.p, dev, sms, st);
+    ++prof.seen;
+    prof.flops += pc.flops;
+    prof.bytes += pc.bytes;
+    if (prof.seen % prof.every != 0) return pc.launch(pc.ma, pc.ma2, pc.mb, pc.mr, pc.mo, pc.p, dev, sms, st);
+    ProfRecord r;
+    r.flops = pc.flops; r.bytes = pc.bytes; r.tag = l->tag;
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+        if (!prof.pool.empty()) { *e = prof.pool.back(); prof.pool.pop_back(); }
+        else NRRT_CUDA_TRY(cudaEventCreate(e));
+    }
+    NRRT_CUDA_TRY(cudaEventRecord(r.a, st));
+    const int rc = pc.launch(pc.ma, pc.ma2, pc.mb, pc.mr, pc.mo, pc.p, dev, sms, st);
+    NRRT_CUDA_TRY(cudaEventRecord(r.b, st));
+    prof.recs.push_back(r);
+    return rc;
+}
+
+extern "C" int nrrt_conv_profile_start(int sample_every) {
+    ConvProfile& prof = profile();
+    for (const ProfRecord& r : prof.recs) { prof.pool.push_back(r.a); prof.pool.push_back(r.b); }
+    prof.recs.clear();
+    prof.on = true;
+    prof.every = sample_every > 1 ? sample_every : 1;
+    prof.seen = 0;
+    prof.flops = prof.bytes = 0.0;
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_conv_profile_stop(void) {
+    profile().on = false;
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_conv_profile_resume(void) {
+    profile().on = true;
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_conv_profile_read(int64_t* launches_seen, double* flops_seen, double* bytes_seen, int max_records,
+                                      int32_t* tags, float* ms, double* flops, double* bytes, int32_t* n_records) {
+    ConvProfile& prof = profile();
+    if (launches_seen) *launches_seen = prof.seen;
+    if (flops_seen) *flops_seen = prof.flops;
+    if (bytes_seen) *bytes_seen = prof.bytes;
+    const int n = (int)prof.recs.size() < max_records ? (int)prof.recs.size() : (max_records > 0 ? max_records : 0);
+    for (int i = 0; i < n; ++i) {
+        const ProfRecord& r = prof.recs[i];
+        float t = 0.f;
+        NRRT_CUDA_TRY(cudaEventElapsedTime(&t, r.a, r.b));  // cudaErrorNotReady until the stream has passed the events
+        if (tags) tags[i] = r.tag;
+        if (ms) ms[i] = t;
+        if (flops) flops[i] = r.flops;
+        if (bytes) bytes[i] = r.bytes;
+    }
+    if (n_records) *n_records = (int)prof.recs.size();
+    return NRRT_OK;
+}
+
+namespace {
+
+int prepare_conv(const NrrtConvLayer* l, PreparedConv& out) {
+    NRRT_REQUIRE(l && l->in && l->weight, "null pointer in conv layer");
+    NRRT_REQUIRE((l->scale == nullptr) == (l->shift == nullptr), "scale and shift go together (both NULL = identity)");
+    NRRT_REQUIRE(l->scale || !(l->post_scale || l->logits), "the identity affine is for plain stored outputs");
     NRRT_REQUIRE(l->dims == 2 || l->dims == 3, "dims must be 2 or 3");
     NRRT_REQUIRE(l->kind >= 0 && l->kind <= 5, "unknown conv kind %d", l->kind);
     NRRT_REQUIRE(l->cin > 0 && l->cin % 64 == 0, "Cin must be a multiple of 64 (got %d)", l->cin);
@@ -1781,12 +1958,12 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     if (l->res) NRRT_REQUIRE(l->res_cstride % 8 == 0 && l->res_coffset % 8 == 0 && ((uintptr_t)l->res & 15) == 0, "bad residual layout");
     EncodeTiledFn encode = get_encode_fn();
     if (!encode) return nrrt_fail(NRRT_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const bool three_d = l->dims == 3;
     const int N = l->n, iD = three_d ? l->in_d : 1, iH = l->in_h, iW = l->in_w;
     NRRT_REQUIRE(N >= 1 && iD >= 1 && iH >= 1 && iW >= 1, "bad input dims");
 
-    ConvParams p = {};
+    ConvParams& p = out.p;
+    p = ConvParams{};
     int stride = 1, ksz = 3, pad = 1, up = 1;
     switch (l->kind) {
         case NRRT_CONV_K3S1: break;
@@ -1878,7 +2055,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     }
 
     // activation maps: dims (C, W, H, D, N) over the caller's NDHWC buffers (channel slices of cstride-wide rows)
-    CUtensorMap ma, ma2, mb;
+    CUtensorMap &ma = out.ma, &ma2 = out.ma2, &mb = out.mb, &mr = out.mr, &mo = out.mo;
     auto make_act_map = [&](CUtensorMap* m, const void* ptr, int cin, int64_t cstride, int n_samples) -> CUresult {
         const cuuint64_t gdim[5] = {(cuuint64_t)cin, (cuuint64_t)iW, (cuuint64_t)iH, (cuuint64_t)iD, (cuuint64_t)n_samples};
         const cuuint64_t cs = (cuuint64_t)cstride * 2;
@@ -1912,7 +2089,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     const bool tma_res = pair && l->res && up == 1 && !l->logits && l->cout % 64 == 0 && l->res_coffset % 64 == 0;
     // TMA-store epilogue: pair kernels with a stored output of whole 64-channel pieces (N = 128 slab kernel for now)
     p.ts = (pair && block_n >= 128 && !l->logits && l->out && l->cout % 64 == 0 && !l->no_tma_store) ? 1 : 0;
-    CUtensorMap mo = ma;
+    mo = ma;
     if (p.ts) {
         const cuuint64_t gdim[5] = {(cuuint64_t)l->out_cstride, (cuuint64_t)p.oW, (cuuint64_t)p.oH, (cuuint64_t)p.oD, (cuuint64_t)N};
         const cuuint64_t cs = (cuuint64_t)l->out_cstride * 2;
@@ -1929,7 +2106,7 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     p.pm = (tma_res && l->poly && l->poly_cases == 9 && (p.n_tiles == 1 || fold) && !l->no_poly_mma && !three_d && !l->post_scale &&
             ((halo && block_n == 128) || (!halo && block_n == 256 && l->kind == NRRT_CONV_K3S1 && p.rows == 128)) &&
             p.H > p.bh && p.W > p.bw) ? 1 : 0;  // (a tile holds at most one frame row and one frame column)
-    CUtensorMap mr = ma;
+    mr = ma;
     if (tma_res) {
         const int rn = l->res_n > 0 ? l->res_n : N;
         const cuuint64_t gdim[5] = {(cuuint64_t)l->res_cstride, (cuuint64_t)p.oW, (cuuint64_t)p.oH, (cuuint64_t)p.oD, (cuuint64_t)rn};
@@ -1962,9 +2139,17 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
     const bool res_mma = fold && l->res_mma && !no_res;
     const bool res_st = tma_res && !res_mma && !no_res;
     if (res_mma) { p.res_mma = block_n / 64; p.res_k0 = 16 * cin_total; p.res = nullptr; }
-    int dev = 0, sms = 0;
-    NRRT_CUDA_TRY(cudaGetDevice(&dev));
-    NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    {
+        const double in_pix = (double)iW * iH * iD, out_pix = (double)p.oW * p.oH * p.oD;
+        const double taps_eff = fold ? 4.0 : (double)p.ntaps;  // per output pixel; ConvTranspose: one tap per output pixel
+        out.flops = 2.0 * N * out_pix * l->cout * taps_eff * cin_total;
+        const double w_elems = (double)rows_total * ((fold ? 16.0 : (double)p.ntaps) * cin_total + (fold ? 128.0 : 0.0));
+        double b = 2.0 * std::min(N, l->in_n > 0 ? l->in_n : N) * in_pix * l->cin + 2.0 * w_elems;
+        if (l->cin2 > 0) b += 2.0 * std::min(N, l->in2_n > 0 ? l->in2_n : N) * in_pix * l->cin2;
+        if (l->res) b += 2.0 * std::min(N, l->res_n > 0 ? l->res_n : N) * out_pix * l->cout;
+        b += l->logits ? 4.0 * N * out_pix : 2.0 * N * out_pix * l->cout;
+        out.bytes = b;
+    }
     if (fold) NRRT_REQUIRE(pair && tma_res && p.ts, "folded layer: residual / output layout not eligible for the TMA-staged epilogue");
     if (l->poly3)
         NRRT_REQUIRE(three_d && halo && pair && block_n == 128 && p.n_tiles == 1 && res_st && p.ts && !l->poly && p.H >= 4 && p.H % 2 == 0 &&
@@ -1972,41 +2157,43 @@ extern "C" int nrrt_conv_layer(const NrrtConvLayer* l, void* stream) {
                      "poly3: 3D 3x3x3 layer with 128 output channels, a residual and whole 16x16 tiles per depth slice");
     if (halo && pair) {
         if (block_n == 128 && p.ts) {
-            if (p.poly3) return launch_halo2<128, 3, 4, true, false, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
-            if (res_st && p.pm) return launch_halo2<128, 3, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
-            if (p.pm) return launch_halo2<128, 3, 4, false, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
-            if (res_st) return launch_halo2<128, 3, 5, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
-            return launch_halo2<128, 3, 5, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (p.poly3) { out.launch = launch_halo2<128, 3, 4, true, false, true, true>; return NRRT_OK; }
+            if (res_st && p.pm) { out.launch = launch_halo2<128, 3, 4, true, true, true>; return NRRT_OK; }
+            if (p.pm) { out.launch = launch_halo2<128, 3, 4, false, true, true>; return NRRT_OK; }
+            if (res_st) { out.launch = launch_halo2<128, 3, 5, true, false, true>; return NRRT_OK; }
+            { out.launch = launch_halo2<128, 3, 5, false, false, true>; return NRRT_OK; }
         }
         if (res_st) {
-            if (block_n == 128) return launch_halo2<128, 3, 5, true>(ma, ma2, mb, mr, mo, p, sms, st);
-            return launch_halo2<64, 4, 8, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (block_n == 128) { out.launch = launch_halo2<128, 3, 5, true>; return NRRT_OK; }
+            { out.launch = launch_halo2<64, 4, 8, true>; return NRRT_OK; }
         }
-        if (block_n == 128) return launch_halo2<128, 4, 6, false>(ma, ma2, mb, mr, mo, p, sms, st);
-        return launch_halo2<64, 4, 8, false>(ma, ma2, mb, mr, mo, p, sms, st);
+        if (block_n == 128) { out.launch = launch_halo2<128, 4, 6, false>; return NRRT_OK; }
+        { out.launch = launch_halo2<64, 4, 8, false>; return NRRT_OK; }
     }
     if (halo) {
-        if (block_n == 128) return launch_halo<128, 4, 4>(ma, ma2, mb, p, sms, st);
-        return launch_halo<64, 4, 8>(ma, ma2, mb, p, sms, st);
+        if (block_n == 128) { out.launch = launch_halo<128, 4, 4>; return NRRT_OK; }
+        { out.launch = launch_halo<64, 4, 8>; return NRRT_OK; }
     }
     if (pair) {
         if (p.ts) {
             if (block_n == 256) {
-                if (res_st && p.pm) return launch_conv2<256, 4, true, true, true>(ma, ma2, mb, mr, mo, p, sms, st);
-                if (res_st) return launch_conv2<256, 4, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
-                return launch_conv2<256, 4, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+                if (res_st && p.pm) { out.launch = launch_conv2<256, 4, true, true, true>; return NRRT_OK; }
+                if (res_st) { out.launch = launch_conv2<256, 4, true, false, true>; return NRRT_OK; }
+                { out.launch = launch_conv2<256, 4, false, false, true>; return NRRT_OK; }
             }
-            if (res_st) return launch_conv2<128, 6, true, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
-            return launch_conv2<128, 6, false, false, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (res_st) { out.launch = launch_conv2<128, 6, true, false, true>; return NRRT_OK; }
+            { out.launch = launch_conv2<128, 6, false, false, true>; return NRRT_OK; }
         }
         if (res_st) {
-            if (block_n == 256) return launch_conv2<256, 4, true>(ma, ma2, mb, mr, mo, p, sms, st);
-            return launch_conv2<128, 6, true>(ma, ma2, mb, mr, mo, p, sms, st);
+            if (block_n == 256) { out.launch = launch_conv2<256, 4, true>; return NRRT_OK; }
+            { out.launch = launch_conv2<128, 6, true>; return NRRT_OK; }
         }
-        if (block_n == 256) return launch_conv2<256, 6, false>(ma, ma2, mb, mr, mo, p, sms, st);
-        return launch_conv2<128, 8, false>(ma, ma2, mb, mr, mo, p, sms, st);
+        if (block_n == 256) { out.launch = launch_conv2<256, 6, false>; return NRRT_OK; }
+        { out.launch = launch_conv2<128, 8, false>; return NRRT_OK; }
     }
-    if (block_n == 256) return launch_conv<256, 4>(ma, ma2, mb, p, sms, st);
-    if (block_n == 128) return launch_conv<128, 6>(ma, ma2, mb, p, sms, st);
-    return launch_conv<64, 8>(ma, ma2, mb, p, sms, st);
+    if (block_n == 256) { out.launch = launch_conv<256, 4>; return NRRT_OK; }
+    if (block_n == 128) { out.launch = launch_conv<128, 6>; return NRRT_OK; }
+    { out.launch = launch_conv<64, 8>; return NRRT_OK; }
 }
+
+}  // namespace

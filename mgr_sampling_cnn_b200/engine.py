@@ -303,6 +303,7 @@ class GuidedPlanner(object):
         self._logits = None
         self._cdf = None
         self.share_encoder = True
+        self.single_call = micro_batch is None  # nrrt_conv_forward_* (fixed micro-batch); False: the Python layer graph
         self.encoder_batch = 8  # distinct maps per encoder pass
 
     def _ensure(self, B):
@@ -330,15 +331,27 @@ class GuidedPlanner(object):
         mb = self.micro_batch
         t2m_h = task_to_map_host if task_to_map_host is not None else task_to_map.cpu().numpy()
         grid = (1,) + self.shape if self.dim == 2 else self.shape
-        prep = plan.coords_prepare(coords, grid)  # coordinate branch (+ 2D epilogue polynomials) for every task at once
-        if not self.share_encoder or np.any(np.diff(t2m_h) < 0):
+        grouped = not np.any(np.diff(t2m_h) < 0)
+        if self.share_encoder and grouped and self.single_call:
+            prep = None
+        else:
+            prep = plan.coords_prepare(coords, grid)  # coordinate branch (+ 2D epilogue polynomials) for every task at once
+        if not self.share_encoder or not grouped:
             # tasks not grouped by map (or sharing disabled): one encoder pass per task
             for i in range(0, B, mb):
                 plan.forward_maps(occ_maps, task_to_map[i:i + mb], coords[i:i + mb], logits_out=out[i:i + mb],
                                   prep=plan.slice_prep(prep, i, i + mb))
             return out
-        # tasks are grouped by map: encode `encoder_batch` distinct maps at a time, then decode their tasks in micro-batches
         uniq, first = np.unique(t2m_h, return_index=True)
+        if self.single_call:
+            # tasks are grouped by map: the whole forward is ONE library call (nrrt_conv_forward_*, csrc/forward.cu), which
+            # encodes 8 distinct maps at a time and decodes their tasks in micro-batches
+            row = np.searchsorted(uniq, t2m_h).astype(np.int32)
+            runs = np.diff(np.append(first, B))
+            per = int(runs[0]) if len(runs) and np.all(runs == runs[0]) else 0
+            plan.forward_tasks(occ_maps, uniq.astype(np.int32), row, coords, out, tasks_per_map=per)
+            return out
+        # the same graph driven layer by layer from Python (cnn.py; kept for the tests that compare the two)
         G = self.encoder_batch
         rel = np.searchsorted(uniq, t2m_h).astype(np.int32) % G  # row of the task's map inside its encoder pass
         uniq_d = torch.from_numpy(uniq.astype(np.int32)).to(self.device, non_blocking=True)

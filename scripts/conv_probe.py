@@ -14,36 +14,47 @@ from mgr_sampling_cnn_b200 import cnn, train, workload  # noqa: E402
 
 dev = torch.device("cuda:0")
 n_dec = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+variants = sys.argv[2].split(",") if len(sys.argv) > 2 else ["base"]
 wl = workload.make_2d(80)
 MB = 40  # tasks per decoder launch, as GuidedPlanner runs them (engine.py)
 torch.manual_seed(0)
 model = train.UNet_cooler().eval().to(dev)
-plan = model._plan(dev)
-prof = cnn.ConvProfiler(sample_every=1)
-plan.set_profiler(prof)
 occ = torch.from_numpy(wl.occ_maps).to(dev)
 coords = torch.from_numpy(wl.coords).to(dev)
 grid = (1, 512, 512)
 maps = torch.arange(8, dtype=torch.int32, device=dev)
-prep = plan.coords_prepare(coords, grid)
-prof.active = True
-enc = plan.encode(grid, 8, occ=occ, maps=maps)
-prof.active = False
-enc_bytes, enc_launches = sum(prof.bytes), len(prof.bytes)
-prof.reset()
-logits = torch.empty((MB, 512 * 512), dtype=torch.float32, device=dev)
-for it in range(n_dec):
-    prof.active = it >= max(n_dec - 4, 1)
-    m = (it % 2) * MB
-    rel = (torch.arange(m, m + MB, device=dev) // 10).to(torch.int32)
-    plan.decode(enc, MB, grid, coords[m:m + MB], plan.slice_prep(prep, m, m + MB), rel, logits, res_group=10)
-torch.cuda.synchronize()
-for name, (n, fl, ms) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
-    print(f"{name:10s} {ms / n:8.4f} ms  {fl / max(ms, 1e-9) / 1e9:8.1f} TFLOP/s")
-n_prof = max(n_dec - max(n_dec - 4, 1), 1)  # decode passes recorded
-dec_bytes, dec_launches = sum(prof.bytes) / n_prof, len(prof.bytes) // n_prof
-print(f"algorithmic DRAM bytes of one encoder pass (8 maps) + one decoder micro-batch ({MB} tasks): "
-      f"{(enc_bytes + dec_bytes) / (enc_launches + dec_launches):.0f} per launch over {enc_launches + dec_launches} launches")
+ref_logits = None
+for variant in variants:
+    cnn.UNetPlan.res_mma = "res_mma" in variant
+    model.invalidate_plan()
+    plan = model._plan(dev)
+    prof = cnn.ConvProfiler(sample_every=1)
+    plan.set_profiler(prof)
+    prep = plan.coords_prepare(coords, grid)
+    prof.active = True
+    enc = plan.encode(grid, 8, occ=occ, maps=maps)
+    prof.active = False
+    enc_bytes, enc_launches = sum(prof.bytes), len(prof.bytes)
+    prof.reset()
+    logits = torch.empty((MB, 512 * 512), dtype=torch.float32, device=dev)
+    for it in range(n_dec):
+        prof.active = it >= max(n_dec - 4, 1)
+        m = (it % 2) * MB
+        rel = (torch.arange(m, m + MB, device=dev) // 10).to(torch.int32)
+        plan.decode(enc, MB, grid, coords[m:m + MB], plan.slice_prep(prep, m, m + MB), rel, logits, res_group=10)
+    torch.cuda.synchronize()
+    print(f"== variant {variant}")
+    if ref_logits is None:
+        ref_logits = logits.clone()
+    else:
+        print(f"max |logits - base| = {(logits - ref_logits).abs().max().item():.3e}")
+    for name, (n, fl, ms) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
+        print(f"{name:10s} {ms / n:8.4f} ms  {fl / max(ms, 1e-9) / 1e9:8.1f} TFLOP/s")
+    n_prof = max(n_dec - max(n_dec - 4, 1), 1)  # decode passes recorded
+    dec_bytes, dec_launches = sum(prof.bytes) / n_prof, len(prof.bytes) // n_prof
+    print(f"algorithmic DRAM bytes of one encoder pass (8 maps) + one decoder micro-batch ({MB} tasks): "
+          f"{(enc_bytes + dec_bytes) / (enc_launches + dec_launches):.0f} per launch over {enc_launches + dec_launches} launches")
+cnn.UNetPlan.res_mma = False
 
 if plan.use_fold(grid):  # the decomposition below times the unfolded conv7.0 / conv8.0
     sys.exit(0)

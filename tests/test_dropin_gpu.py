@@ -175,7 +175,7 @@ def test_main_loop_from_the_callable_methods(fixture, modname, cuda_device):
                 break
             planner.nodes.append(new)
     n = len(planner.nodes)
-    assert n == int(res.n_nodes[0]) and n > 60
+    assert n == int(res.n_nodes[0]) and n > 40
     index = {id(m): j for j, m in enumerate(planner.nodes)}
     assert np.array_equal(np.array([m.position for m in planner.nodes], np.float64), res.pos[0, :n].cpu().numpy())
     assert np.array_equal(np.array([m.cost for m in planner.nodes]), res.cost[0, :n].cpu().numpy())

@@ -108,3 +108,50 @@ def test_guided_planner_end_to_end_vs_oracle(dim, cuda_device):
     _oracle_tail(dim, wl.shape, wl.occ_maps, wl.task_to_map, logits, wl.starts, wl.goals, 7, ids, 5000,
                  5.0 if dim == 2 else 3.0, res)
     assert (res.status.cpu().numpy() == po.ST_SOLVED).sum() >= 1
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_single_call_forward_equals_the_layer_graph(dim, cuda_device):
+    """nrrt_conv_forward_{2d,3d} (the whole forward in one C-ABI call, csrc/forward.cu) against the same graph driven layer by
+    layer from Python (cnn.py): identical kernels in an identical order, so the logits are bit-equal.  13 / 23 tasks on 2 / 3
+    maps: ragged micro-batches, a partly filled encoder pass."""
+    from mgr_sampling_cnn_b200 import engine, workload
+    wl = workload.make_2d(13, size=128) if dim == 2 else workload.make_3d(23, size=32)
+    model = _model(dim == 3, cuda_device)
+    occ = torch.from_numpy(wl.occ_maps).to(cuda_device)
+    t2m = torch.from_numpy(wl.task_to_map).to(cuda_device)
+    coords = torch.from_numpy(wl.coords).to(cuda_device)
+    gp = engine.GuidedPlanner(model, dim, wl.shape)
+    assert gp.single_call
+    a = gp.probability_maps(occ, t2m, coords).clone()
+    gp.single_call = False
+    b = gp.probability_maps(occ, t2m, coords).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # and a second call through the cached workspace / prepared layers gives the same bits
+    gp.single_call = True
+    assert torch.equal(gp.probability_maps(occ, t2m, coords), a)
+
+
+def test_single_call_forward_rejects_bad_arguments(cuda_device):
+    import ctypes as C
+    from mgr_sampling_cnn_b200 import _lib, engine, workload
+    wl = workload.make_2d(4, size=64)
+    model = _model(False, cuda_device)
+    plan = model._plan(cuda_device)
+    occ = torch.from_numpy(wl.occ_maps).to(cuda_device)
+    coords = torch.from_numpy(wl.coords).to(cuda_device)
+    out = torch.empty((4, 64 * 64), dtype=torch.float32, device=cuda_device)
+    with pytest.raises(_lib.NrrtError, match="non-decreasing"):
+        plan.forward_tasks(occ, np.array([0], np.int32), np.array([0, 0, 1, 0], np.int32), coords, out)
+    W = plan.c_weights()
+    lib = _lib.load()
+    ws = torch.empty(1024, dtype=torch.uint8, device=cuda_device)
+    ids, rows = np.zeros(1, np.int32), np.zeros(4, np.int32)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    rc = lib.nrrt_conv_forward_2d(C.byref(W), p(occ), ids.ctypes.data_as(C.c_void_p), 1, rows.ctypes.data_as(C.c_void_p), p(coords), 4,
+                                  64, 64, 0, p(out), p(ws), 1024, None)
+    assert rc == -2 and b"workspace too small" in lib.nrrt_last_error()
+    rc = lib.nrrt_conv_forward_3d(C.byref(W), p(occ), ids.ctypes.data_as(C.c_void_p), 1, rows.ctypes.data_as(C.c_void_p), p(coords), 4,
+                                  64, 64, 64, 0, p(out), p(ws), 1024, None)
+    assert rc == -1 and b"2D model" in lib.nrrt_last_error()
