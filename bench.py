@@ -352,7 +352,7 @@ def run_graft(args):
     roofline, kernels = None, {}
     cells = int(np.prod(wl.shape))
     if arm.prof is not None:
-        prof = arm.prof
+        prof = arm.prof.collect()
         n_l, fl, t_ms = prof.totals()
         ach = fl / (t_ms / 1e3) / 1e12 if t_ms > 0 else 0.0
         traffic, traffic_note = conv_traffic()

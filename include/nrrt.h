@@ -397,10 +397,36 @@ int nrrt_head_1x1(const void* in, int64_t pixels, int C, int64_t in_cstride, con
  * its additions.
  * occ_bits as nrrt_pack_occupancy writes them (1 = free; 3D maps hold {0 = free, 255}); starts / goals [B][dims] in array-axis
  * order ((y, x) in 2D, (x, y, z) in 3D, as the planners take them); (s0, s1, s2) = array shape (s2 ignored in 2D);
+ * axis_only = 1 restricts the moves to the axis steps: reachability by 4- / 6-connected free cells (the task filter);
  * work: [n_slots][cells] uint64 scratch (one slot per resident CTA, e.g. the SM count); queue: one zeroed int32. */
 int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map, const int32_t* starts,
-                    const int32_t* goals, int B, int s0, int s1, int s2, void* work, int n_slots, int32_t* queue,
+                    const int32_t* goals, int B, int s0, int s1, int s2, int axis_only, void* work, int n_slots, int32_t* queue,
                     int32_t* n_steps, double* length, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * On-device workload generation (csrc/generate.cu): the reference's generators with CPython's `random` (MT19937,
+ * random.seed(int), randint) reproduced bit for bit -- seed s here gives the map / the tasks `random.seed(s)` gives there.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* generate_maps.create_map (generate_maps.py:7-44; 2D: (s0, s1) = (height, width), 255 = free, 0 = obstacle / frame) and
+ * ThreeD_generate_maps.create_map (ThreeD_generate_maps.py:5-41; (s0, s1, s2) = array axes x, y, z; 255 = obstacle).
+ * seeds: device int64 [n_maps], one random.seed() per map;  occ_maps: device uint8 [n_maps][cells]. */
+int nrrt_generate_maps(int dims, const int64_t* seeds, int n_maps, int s0, int s1, int s2, uint8_t* occ_maps, void* stream);
+
+/* draw_start_and_finish (generate_tasks.py:27-46, ThreeD_generate_tasks.py:25-48) called n_cand times in a row per map
+ * after random.seed(seeds[m]): candidate (start, goal) pairs in the planners' axis order ((y, x) / (x, y, z)),
+ * [n_maps][n_cand][dims].  n_done[m] = n_cand, or -1 if the map has no admissible cells (the reference would spin). */
+int nrrt_generate_task_candidates(int dims, const int64_t* seeds, int n_maps, int s0, int s1, int s2, const uint8_t* occ_maps,
+                                  int n_cand, int32_t* starts, int32_t* goals, int32_t* n_done, void* stream);
+
+/* The reference pipeline deletes tasks its A* cannot solve (generate_paths.py:111-113), which does not touch the random
+ * stream: keep, per map and in candidate order, the first `per_map` candidates whose reach_steps[q][0] >= 0
+ * (nrrt_grid_paths output for the candidates; NULL = keep all).  Writes the task arrays of the first n_tasks tasks
+ * (the last map may be truncated): task_to_map, starts, goals [n_tasks][dims], coords fp32 [n_tasks][2][dims] (the CNN
+ * input, (x, y[, z]) order: train.py:57-60), *redrawn = candidates skipped, *short_maps = maps that ran out of
+ * candidates (call again with a larger n_cand). */
+int nrrt_select_tasks(int dims, int n_maps, int n_cand, int per_map, int n_tasks, const int32_t* cand_starts,
+                      const int32_t* cand_goals, const int32_t* reach_steps, int32_t* task_to_map, int32_t* starts,
+                      int32_t* goals, float* coords, int32_t* redrawn, int32_t* short_maps, void* stream);
 
 #ifdef __cplusplus
 }

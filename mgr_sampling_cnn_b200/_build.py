@@ -15,6 +15,7 @@ SOURCES = {
     "conv_tc.cu": [],
     "conv_aux.cu": [],
     "forward.cu": [],
+    "generate.cu": [],
     "gridpath.cu": [],
 }
 COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

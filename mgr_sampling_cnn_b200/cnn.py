@@ -685,17 +685,15 @@ class UNetPlan(object):
                 E = torch.empty((B, cases, 4, cout), dtype=torch.float32, device=dev)
                 a = 1.0 / (g[lv][1] - 1) if g[lv][1] > 1 else 0.0
                 b = 1.0 / (g[lv][2] - 1) if g[lv][2] > 1 else 0.0
-                if B >= 64:  # one fp32 GEMM over the batch (chunked so that the scratch stays small)
-                    chunk = 512
-                    work = torch.empty((min(B, chunk) * 4 * (cc + cases * n_uv * cout),), dtype=torch.float32, device=dev)
-                    for i in range(0, B, chunk):
-                        j = min(B, i + chunk)
-                        _lib.count_launch(3)
-                        check(self.lib.nrrt_coords_poly_gemm(_ptr(feat[i:j]), j - i, cc, _ptr(self.mt[name]), cases, n_uv, cout, a, b,
-                                                             _ptr(work), _ptr(E[i:j]), st))
-                else:
-                    _lib.count_launch()
-                    check(self.lib.nrrt_coords_poly(_ptr(feat), B, cc, _ptr(mom), cases, n_uv, cout, a, b, _ptr(E), st))
+                # one fp32 GEMM over the batch (chunked so that the scratch stays small); the same kernels at every batch
+                # size, so that results do not depend on how a caller batches (nrrt_coords_poly is the direct form of it)
+                chunk = 512
+                work = torch.empty((min(B, chunk) * 4 * (cc + cases * n_uv * cout),), dtype=torch.float32, device=dev)
+                for i in range(0, B, chunk):
+                    j = min(B, i + chunk)
+                    _lib.count_launch(3)
+                    check(self.lib.nrrt_coords_poly_gemm(_ptr(feat[i:j]), j - i, cc, _ptr(self.mt[name]), cases, n_uv, cout, a, b,
+                                                         _ptr(work), _ptr(E[i:j]), st))
                 prep[name] = E
             # conv6.0's task-dependent term: 16-case polynomial from upconv6's and conv6.0's own coordinate channels
             cout = self.b6.shape[0]

@@ -55,6 +55,7 @@ struct GridPathArgs {
     int B, S0, S1, S2;         // grid shape = array axes (S2 = 1 in 2D)
     unsigned long long* work;  // [gridDim.x][cells]
     int32_t* queue;            // zeroed task counter
+    int axis_only;             // 1: axis moves only (4- / 6-connected reachability); 0: the reference's A* moves
     int32_t* n_steps;          // [B][3]: steps of cost 1, sqrt(2), sqrt(3); -1 = no path
     double* length;            // [B], NaN = no path
 };
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel
 #pragma unroll
                         for (int d2 = (DIM == 3 ? -1 : 0); d2 <= (DIM == 3 ? 1 : 0); ++d2) {
                             const int nz = (d0 != 0) + (d1 != 0) + (d2 != 0);
-                            if (nz == 0) continue;
+                            if (nz == 0 || (a.axis_only && nz != 1)) continue;
                             const int e0 = c0 + d0, e1 = c1 + d1, e2 = c2 + d2;
                             if (e0 < 0 || e0 >= a.S0 || e1 < 0 || e1 >= a.S1 || e2 < 0 || e2 >= a.S2) continue;
                             const int v = e0 * S12 + e1 * st1 + e2;
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel
 }  // namespace
 
 extern "C" int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map,
-                               const int32_t* starts, const int32_t* goals, int B, int s0, int s1, int s2, void* work, int n_slots,
-                               int32_t* queue, int32_t* n_steps, double* length, void* stream) {
+                               const int32_t* starts, const int32_t* goals, int B, int s0, int s1, int s2, int axis_only,
+                               void* work, int n_slots, int32_t* queue, int32_t* n_steps, double* length, void* stream) {
     NRRT_REQUIRE(occ_bits && task_to_map && starts && goals && work && queue && n_steps && length, "null pointer");
     NRRT_REQUIRE(dims == 2 || dims == 3, "dims must be 2 or 3");
     if (dims == 2) s2 = 1;
@@ -198,7 +199,7 @@ extern "C" int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per
     NRRT_REQUIRE(smem <= 227 * 1024, "grid too large for shared memory (%zu bytes)", smem);
     GridPathArgs a;
     a.occ_bits = occ_bits; a.words_per_map = words_per_map; a.task_to_map = task_to_map; a.starts = starts; a.goals = goals;
-    a.B = B; a.S0 = s0; a.S1 = s1; a.S2 = s2; a.work = (unsigned long long*)work; a.queue = queue;
+    a.B = B; a.S0 = s0; a.S1 = s1; a.S2 = s2; a.axis_only = axis_only ? 1 : 0; a.work = (unsigned long long*)work; a.queue = queue;
     a.n_steps = n_steps; a.length = length;
     const int grid = n_slots < B ? n_slots : B;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -246,12 +246,14 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
                       n_draws=v(buf.n_draws) if samples is None else None, trace=v(buf.trace), trace_n=v(buf.trace_n))
 
 
-def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape: Sequence[int], n_slots: Optional[int] = None):
+def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape: Sequence[int], n_slots: Optional[int] = None,
+                      axis_only: bool = False):
     """Shortest grid path of every task = the reference's A* (generate_paths.py:11-74, ThreeD_generate_paths.py:14-97): its
     path length column (test_network_and_algorithms.py:58-70) and its task filter (no path -> the task is deleted,
     generate_paths.py:111-113).  occ_bits from pack_occupancy; starts / goals [B, dim] in array-axis order ((y, x) / (x, y, z)).
     Returns (length fp64 [B] (NaN = no path), n_steps int32 [B, 3] = steps of cost 1, sqrt(2), sqrt(3), -1 = no path) on
-    the device; length = n_steps . (1, sqrt(2), sqrt(3))."""
+    the device; length = n_steps . (1, sqrt(2), sqrt(3)).  axis_only: axis moves only, i.e. reachability through 4- / 6-connected
+    free cells (the task filter of workload.py; in 2D it accepts exactly the tasks the reference's A* solves)."""
     lib = _lib.load()
     dev = occ_bits.device
     if dev.type != "cuda":
@@ -273,7 +275,7 @@ def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape:
     _lib.count_launch()
     s = [int(v) for v in shape] + [1]
     check(lib.nrrt_grid_paths(dim, _ptr(occ_bits), occ_bits.shape[1], _ptr(t2m), _ptr(st), _ptr(gl), B, s[0], s[1], s[2],
-                              _ptr(work), work.shape[0], _ptr(queue), _ptr(steps), _ptr(length), stream))
+                              1 if axis_only else 0, _ptr(work), work.shape[0], _ptr(queue), _ptr(steps), _ptr(length), stream))
     return length, steps
 
 
@@ -348,7 +350,9 @@ class GuidedPlanner(object):
             # encodes 8 distinct maps at a time and decodes their tasks in micro-batches
             row = np.searchsorted(uniq, t2m_h).astype(np.int32)
             runs = np.diff(np.append(first, B))
-            per = int(runs[0]) if len(runs) and np.all(runs == runs[0]) else 0
+            # scheduling hint: the usual number of tasks per map (the library applies it per micro-batch, only where every
+            # map of the micro-batch has exactly that many tasks; a truncated last map just falls back)
+            per = int(np.bincount(runs).argmax()) if len(runs) else 0
             plan.forward_tasks(occ_maps, uniq.astype(np.int32), row, coords, out, tasks_per_map=per)
             return out
         # the same graph driven layer by layer from Python (cnn.py; kept for the tests that compare the two)

@@ -29,12 +29,13 @@ for variant in variants:
     model.invalidate_plan()
     plan = model._plan(dev)
     prof = cnn.ConvProfiler(sample_every=1)
-    plan.set_profiler(prof)
     prep = plan.coords_prepare(coords, grid)
     prof.active = True
     enc = plan.encode(grid, 8, occ=occ, maps=maps)
     prof.active = False
-    enc_bytes, enc_launches = sum(prof.bytes), len(prof.bytes)
+    torch.cuda.synchronize()
+    prof.collect()
+    enc_bytes, enc_launches = prof.bytes_seen, prof.seen
     prof.reset()
     logits = torch.empty((MB, 512 * 512), dtype=torch.float32, device=dev)
     for it in range(n_dec):
@@ -42,7 +43,9 @@ for variant in variants:
         m = (it % 2) * MB
         rel = (torch.arange(m, m + MB, device=dev) // 10).to(torch.int32)
         plan.decode(enc, MB, grid, coords[m:m + MB], plan.slice_prep(prep, m, m + MB), rel, logits, res_group=10)
+    prof.active = False
     torch.cuda.synchronize()
+    prof.collect()
     print(f"== variant {variant}")
     if ref_logits is None:
         ref_logits = logits.clone()
@@ -51,9 +54,10 @@ for variant in variants:
     for name, (n, fl, ms) in sorted(prof.by_layer().items(), key=lambda kv: -kv[1][2]):
         print(f"{name:10s} {ms / n:8.4f} ms  {fl / max(ms, 1e-9) / 1e9:8.1f} TFLOP/s")
     n_prof = max(n_dec - max(n_dec - 4, 1), 1)  # decode passes recorded
-    dec_bytes, dec_launches = sum(prof.bytes) / n_prof, len(prof.bytes) // n_prof
+    dec_bytes, dec_launches = prof.bytes_seen / n_prof, prof.seen // n_prof
     print(f"algorithmic DRAM bytes of one encoder pass (8 maps) + one decoder micro-batch ({MB} tasks): "
           f"{(enc_bytes + dec_bytes) / (enc_launches + dec_launches):.0f} per launch over {enc_launches + dec_launches} launches")
+    prof.reset()
 cnn.UNetPlan.res_mma = False
 
 if plan.use_fold(grid):  # the decomposition below times the unfolded conv7.0 / conv8.0

@@ -136,12 +136,12 @@ def test_single_call_forward_equals_the_layer_graph(dim, cuda_device):
 def test_single_call_forward_rejects_bad_arguments(cuda_device):
     import ctypes as C
     from mgr_sampling_cnn_b200 import _lib, engine, workload
-    wl = workload.make_2d(4, size=64)
+    wl = workload.make_2d(4, size=128)  # (a 64 x 64 map has no two cells 100 px apart: the generator would never return)
     model = _model(False, cuda_device)
     plan = model._plan(cuda_device)
     occ = torch.from_numpy(wl.occ_maps).to(cuda_device)
     coords = torch.from_numpy(wl.coords).to(cuda_device)
-    out = torch.empty((4, 64 * 64), dtype=torch.float32, device=cuda_device)
+    out = torch.empty((4, 128 * 128), dtype=torch.float32, device=cuda_device)
     with pytest.raises(_lib.NrrtError, match="non-decreasing"):
         plan.forward_tasks(occ, np.array([0], np.int32), np.array([0, 0, 1, 0], np.int32), coords, out)
     W = plan.c_weights()
@@ -150,8 +150,8 @@ def test_single_call_forward_rejects_bad_arguments(cuda_device):
     ids, rows = np.zeros(1, np.int32), np.zeros(4, np.int32)
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
     rc = lib.nrrt_conv_forward_2d(C.byref(W), p(occ), ids.ctypes.data_as(C.c_void_p), 1, rows.ctypes.data_as(C.c_void_p), p(coords), 4,
-                                  64, 64, 0, p(out), p(ws), 1024, None)
+                                  128, 128, 0, p(out), p(ws), 1024, None)
     assert rc == -2 and b"workspace too small" in lib.nrrt_last_error()
     rc = lib.nrrt_conv_forward_3d(C.byref(W), p(occ), ids.ctypes.data_as(C.c_void_p), 1, rows.ctypes.data_as(C.c_void_p), p(coords), 4,
-                                  64, 64, 64, 0, p(out), p(ws), 1024, None)
+                                  128, 128, 128, 0, p(out), p(ws), 1024, None)
     assert rc == -1 and b"2D model" in lib.nrrt_last_error()
