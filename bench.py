@@ -61,8 +61,10 @@ def peaks():
 
 def conv_traffic():
     """DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture of one
-    encoder pass + one decoder micro-batch (profiles/conv_traffic_r1.json), averaged over launches like `achieved`."""
-    path = os.path.join(ROOT, "profiles", "conv_traffic_r1.json")
+    encoder pass + one decoder micro-batch of 40 tasks, the bench's own micro-batch (profiles/conv_traffic_r2.json), averaged
+    over launches like `achieved`.  The like-for-like algorithmic figure of the SAME 29 launches is in the note (the step's
+    own launch mix, `algorithmic_bytes_per_launch_avg`, has more decoder launches per encoder pass)."""
+    path = os.path.join(ROOT, "profiles", "conv_traffic_r2.json")
     if not os.path.exists(path):
         return None, "no ncu capture committed"
     with open(path) as f:

@@ -585,9 +585,9 @@ class UNetPlan(object):
 
     def launches_per_forward(self, task_to_row):
         """Kernels one nrrt_conv_forward_* call enqueues (bench.py's gpu_launches claim), by replaying its schedule
-        (csrc/forward.cu: 8 maps per encoder pass, 40 / 10 tasks per decoder micro-batch, 512 / 128 tasks per
+        (csrc/forward.cu: 8 maps per encoder pass, 40 / 10 tasks per decoder micro-batch, 4096 / 128 tasks per
         coordinate-branch chunk)."""
-        mb, pc = (40, 512) if self.dims == 2 else (10, 128)
+        mb, pc = (40, 4096) if self.dims == 2 else (10, 128)
         enc = 25 if self.dims == 2 else 24          # stem, stem2, 19 ResNet convs, per-map partial sums
         dec = 6 if self.dims == 2 else 13           # 3D: + coordinate fill, three ConvTranspose, post-passes
         prep = 17 if self.dims == 2 else 10

@@ -23,8 +23,11 @@
 namespace {
 
 constexpr int kEncBatch = 8;     // distinct maps per encoder pass
-constexpr int kPrepChunk2 = 512; // tasks per coordinate-branch pass (2D) ...
-constexpr int kPrepChunk3 = 128; // ... and 3D (54-case field: 774 KB per task)
+// tasks per coordinate-branch pass.  The branch is four tiny convs per task (4 tasks per CTA): a pass over 512 tasks is a
+// 128-CTA launch that cannot fill 148 SMs (3.4 ms per pass in ncu, 27 ms per 4096-task step); 4096 tasks per pass
+// cost 0.8 MB of workspace per task (polynomials + GEMM scratch) and run at full width.
+constexpr int kPrepChunk2 = 4096;
+constexpr int kPrepChunk3 = 128; // 3D (54-case field: 774 KB per task + 0.9 MB GEMM scratch)
 
 struct Grid { int d, h, w; };
 inline long long cells(const Grid& g) { return (long long)g.d * g.h * g.w; }

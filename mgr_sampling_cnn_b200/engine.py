@@ -442,4 +442,4 @@ class GuidedPlanner(object):
         return c, d, w, p
 
 
-_COMPACT = ("n_nodes", "iterations", "status", "goal_node", "best_node", "best_dist", "path_n", "path_idx", "path_len")
+_COMPACT = ("n_nodes", "iterations", "status", "goal_node", "best_node", "best_dist", "path_n", "path_idx", "path_len", "n_draws")
