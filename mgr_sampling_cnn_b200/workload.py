@@ -31,6 +31,32 @@ def _labels(free: np.ndarray):
     return ndimage.label(free)[0]  # default structure = 4-connected (2D) / 6-connected (3D)
 
 
+class _BoundedRandom(object):
+    """Stands in for the `random` module attribute of the task-generator drop-ins while a workload is built: same stream
+    (it forwards to CPython's generator), but a bound on the draws of ONE task.  The reference's loops
+    (generate_tasks.py:33-46) pick a free start and then redraw the goal until it is free and 100 px / 20 voxels away from
+    that start: they never return once a start is drawn that has no such cell (any 128 x 128 map has such starts).  The
+    builder raises instead of spinning."""
+
+    def __init__(self, limit: int = 2_000_000):
+        self.limit, self.count = limit, 0
+
+    def randint(self, a, b):
+        self.count += 1
+        if self.count > self.limit:
+            raise ValueError("the reference's task generator would never return on this map: the drawn start has no free "
+                             "cell far enough away (use the reference's map size, or a larger one)")
+        return random.randint(a, b)
+
+
+def _draw_bounded(module, occ):
+    saved, module.random = module.random, _BoundedRandom()
+    try:
+        return module.draw_start_and_finish_coords(occ)
+    finally:
+        module.random = saved
+
+
 def make_2d(n_tasks: int, first_map: int = 0, size: int = 512, filter_unreachable: bool = True) -> Workload:
     per = generate_tasks.TASK_NUMBER_FOR_SINGLE_MAP
     n_maps = (n_tasks + per - 1) // per
@@ -42,7 +68,7 @@ def make_2d(n_tasks: int, first_map: int = 0, size: int = 512, filter_unreachabl
         random.seed(2000 + m)
         k = 0
         while k < per and len(starts) < n_tasks:
-            sx, sy, fx, fy = generate_tasks.draw_start_and_finish_coords(occ)
+            sx, sy, fx, fy = _draw_bounded(generate_tasks, occ)
             if lab is not None and lab[sy, sx] != lab[fy, fx]:
                 redrawn += 1
                 continue
@@ -64,7 +90,7 @@ def make_3d(n_tasks: int, first_map: int = 0, size: int = 80, filter_unreachable
         random.seed(2000 + m)
         k = 0
         while k < per and len(starts) < n_tasks:
-            s, f = ThreeD_generate_tasks.draw_start_and_finish_coords(occ)
+            s, f = _draw_bounded(ThreeD_generate_tasks, occ)
             if lab is not None and lab[s] != lab[f]:
                 redrawn += 1
                 continue

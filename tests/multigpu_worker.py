@@ -23,7 +23,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    wl = workload.make_2d(n_tasks, size=128) if dim == 2 else workload.make_3d(n_tasks, size=32)
+    wl = workload.make_2d(n_tasks, size=256) if dim == 2 else workload.make_3d(n_tasks, size=32)
     idx = sharding.shard_indices(n_tasks, rank, world, interleaved)
     maps_used, t2m = np.unique(wl.task_to_map[idx], return_inverse=True)
     torch.manual_seed(0)
