@@ -32,12 +32,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(_ROOT, "include", "nrrt.h"))
+    # experiment builds (e.g. NRRT_EXTRA_NVCC_FLAGS=-DNRRT_DEBUG_SWITCHES) never mix with product objects: a change of the
+    # flag set rebuilds everything
+    extra_all = os.environ.get("NRRT_EXTRA_NVCC_FLAGS", "").split()
+    stamp = os.path.join(objdir, "flags.txt")
+    old_flags = open(stamp).read() if os.path.exists(stamp) else ""
+    if old_flags != " ".join(extra_all):
+        force = True
+        with open(stamp, "w") as f:
+            f.write(" ".join(extra_all))
     objs, relink = [], force or not os.path.exists(LIB_PATH)
     for name, extra in SOURCES.items():
         src = os.path.join(CSRC, name)
         obj = os.path.join(objdir, name.replace(".cu", ".o"))
         if force or _newer(src, obj) or any(_newer(h, obj) for h in headers):
-            cmd = [nvcc] + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [nvcc] + COMMON + extra + extra_all + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             subprocess.check_call(cmd)
             relink = True
         objs.append(obj)

@@ -12,9 +12,15 @@
 //   farther than the search radius), so a node is one 32-bit (2D) / 64-bit (3D) word of int16 coordinates; a node
 //   with a non-integer coordinate stores a sentinel and keeps its fp64 position in the caller's `pos` array (global
 //   memory, read through L2).  cost[] and parent[] live in the caller's output arrays too: they are touched only for
-//   the ~20 near nodes of an iteration.  That is 53 KiB per 2D task and 105 KiB per 3D task: FOUR 2D tasks (128 threads
-//   each) or two 3D tasks (256 threads) share an SM.  The kernel is latency bound (profiles/planner_r1.md), so tasks in
-//   flight per SM is what buys throughput: with fp64 positions in shared memory (111 / 181 KiB) it was two / one.
+//   the ~20 near nodes of an iteration.
+//   Occupancy is what buys throughput (the kernel is a latency-bound chain of ~5000 dependent iterations per task,
+//   profiles/planner_r1.md): round 1 staged the task's bit grid in shared memory (53 KiB per 2D task, 105 KiB per 3D task:
+//   four / two tasks per SM, and 111 / 120 registers per thread capped it there as well).  Round 2: the production kernels
+//   read the map bits from global memory through L1 (ld.global.nc; the tasks resident on an SM belong to one or two maps, so
+//   their 32 / 64 KiB grids stay in L1 -- same speed as the staged copy at equal occupancy) and are compiled for 8 (2D, 64
+//   registers) / 4 (3D, 64 registers) CTAs per SM: 21 / 41 KiB of shared memory per task.  Measured, 4096 2D uniform tasks:
+//   209.7 ms (4 CTAs, staged) -> 207.1 (4, L1) -> 183.3 (5) -> 173.0 (6) -> 168.0 (7) -> 164.8 (8) -> 182.8 (10: spills take over);
+//   1024 3D tasks: 126.8 -> 104.4 ms (profiles/planner_r2.md).
 // Parallelism inside an iteration: the two O(n) scans run over all threads; every warp evaluates the connect test
 // redundantly (no barrier); choose-parent/rewire candidates are tested speculatively, one candidate per warp at a time,
 // 100 samples over 32 lanes.  The outcome of loop A does not depend on evaluation order (it is the lexicographic
@@ -23,6 +29,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "nrrt_common.cuh"
 
@@ -161,7 +168,9 @@ __device__ __forceinline__ Segment<DIM> segment_setup(const double (&p1)[DIM], c
 }
 
 // sample i (0..99) of the segment: true iff its cell is an obstacle
-template <int DIM>
+// GS = true: `grid` is the CTA's shared-memory copy of the map; false: the map in global memory, read through L1
+// (ld.global.nc: the bit grids of the few maps whose tasks are resident on an SM stay in its L1).
+template <int DIM, bool GS = true>
 __device__ __forceinline__ bool sample_blocked(const Segment<DIM>& sg, int i, const uint32_t* __restrict__ grid,
                                                const int (&shape)[3]) {
     const double t = (i == 99) ? sg.D : __dmul_rn((double)i, sg.step);
@@ -180,30 +189,32 @@ __device__ __forceinline__ bool sample_blocked(const Segment<DIM>& sg, int i, co
         ci = max(0, min(ci, shape[k] - 1));
         idx = idx * shape[k] + ci;
     }
-    return ((grid[idx >> 5] >> (idx & 31)) & 1u) == 0u;
+    const uint32_t wd = GS ? grid[idx >> 5] : __ldg(grid + (idx >> 5));
+    return ((wd >> (idx & 31)) & 1u) == 0u;
 }
 
-template <int DIM>
+template <int DIM, bool GS = true>
 __device__ __forceinline__ bool collision_free_warp(const double (&p1)[DIM], const double (&p2)[DIM],
                                                     const uint32_t* __restrict__ grid, const int (&shape)[3], int lane) {
     const Segment<DIM> sg = segment_setup<DIM>(p1, p2);
     if (sg.same) return false;  // `if point1 == point2: return False`
 #pragma unroll 1
     for (int i = lane; i < 128; i += kWarp) {
-        const bool blocked = i < 100 && sample_blocked<DIM>(sg, i, grid, shape);
+        const bool blocked = i < 100 && sample_blocked<DIM, GS>(sg, i, grid, shape);
         if (__any_sync(0xffffffffu, blocked)) return false;
     }
     return true;
 }
 
-template <int DIM, int NT, bool TRACE>
-__global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const PlanArgs a) {
+template <int DIM, int NT, bool TRACE, bool GS = true, int MINB = (DIM == 2 ? 4 : 2)>
+__global__ void __launch_bounds__(NT, MINB) plan_kernel(const PlanArgs a) {
     constexpr int NW = NT / kWarp;
     typedef typename PosWord<DIM>::T PW;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     PW* pw = reinterpret_cast<PW*>(smem_raw);                                // [cap] packed positions
-    uint32_t* grid = reinterpret_cast<uint32_t*>(pw + a.cap);                // [words_per_map] (padded to 4)
-    uint32_t* mask = grid + ((a.words_per_map + 3) & ~3);                    // [mask_words]
+    uint32_t* grid_s = reinterpret_cast<uint32_t*>(pw + a.cap);              // GS: [words_per_map] (padded to 4)
+    uint32_t* mask = grid_s + (GS ? ((a.words_per_map + 3) & ~3) : 0);       // [mask_words]
+    const uint32_t* grid = grid_s;
     Slot* slot_nn = reinterpret_cast<Slot*>(mask + ((a.mask_words + 3) & ~3)); // [2][NW]
     Slot* slot_a = slot_nn + 2 * NW;                                         // [NW]
     __shared__ int s_task;
@@ -240,12 +251,14 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
 
         // ---- stage the task's occupancy bits (16-byte loads; consecutive tasks of one map reuse the copy) ----
         const int map = a.task_to_map[task];
-        if (map != cur_map) {
+        if (!GS) {
+            grid = a.occ_bits + (size_t)map * a.words_per_map;
+        } else if (map != cur_map) {
             const uint4* src = reinterpret_cast<const uint4*>(a.occ_bits + (size_t)map * a.words_per_map);
-            uint4* dst = reinterpret_cast<uint4*>(grid);
+            uint4* dst = reinterpret_cast<uint4*>(grid_s);
             for (int i = tid; i < (a.words_per_map >> 2); i += NT) dst[i] = __ldg(src + i);
             for (int i = (a.words_per_map & ~3) + tid; i < a.words_per_map; i += NT)
-                grid[i] = __ldg(a.occ_bits + (size_t)map * a.words_per_map + i);
+                grid_s[i] = __ldg(a.occ_bits + (size_t)map * a.words_per_map + i);
             cur_map = map;
         }
         double goal[DIM];
@@ -383,7 +396,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
             bool my_blocked = sg0.same;
             if (warp < 4 && !sg0.same) {
                 const int i = warp * kWarp + lane;
-                my_blocked = i < 100 && sample_blocked<DIM>(sg0, i, grid, shape);
+                my_blocked = i < 100 && sample_blocked<DIM, GS>(sg0, i, grid, shape);
             }
 
             // ---- find_nearby_nodes: euclid(new, node) <= r, as a bit mask in insertion order ----
@@ -476,7 +489,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
                     for (int k = 0; k < DIM; ++k) p1[k] = __shfl_sync(0xffffffffu, pj[k], b);
                     const double cb = __shfl_sync(0xffffffffu, cj, b);
                     if (!(cb < wbest)) continue;  // reference would not call is_collision_free here (uniform per warp)
-                    const bool fr = collision_free_warp<DIM>(p1, npos, grid, shape, lane);
+                    const bool fr = collision_free_warp<DIM, GS>(p1, npos, grid, shape, lane);
                     if (TRACE && lane == 0) {
                         if (trace_n < a.out.trace_cap) {
                             int32_t* t = trace + 4 * trace_n;
@@ -526,7 +539,7 @@ __global__ void __launch_bounds__(NT, (DIM == 2 ? 4 : 2)) plan_kernel(const Plan
                     double p2[DIM];
 #pragma unroll
                     for (int k = 0; k < DIM; ++k) p2[k] = __shfl_sync(0xffffffffu, pj[k], b);
-                    const bool fr = collision_free_warp<DIM>(npos, p2, grid, shape, lane);
+                    const bool fr = collision_free_warp<DIM, GS>(npos, p2, grid, shape, lane);
                     if (TRACE && lane == 0) {
                         if (trace_n < a.out.trace_cap) {
                             int32_t* t = trace + 4 * trace_n;
@@ -719,20 +732,20 @@ struct SmemPlan {
     int cap, mask_words, nt;
 };
 
-SmemPlan smem_plan(const NrrtPlanParams& p, int words_per_map) {
+SmemPlan smem_plan(const NrrtPlanParams& p, int words_per_map, bool grid_in_smem = true) {
     SmemPlan s;
     s.nt = p.dim == 2 ? 128 : 256;
     s.cap = (p.max_iterations + 2 + 3) & ~3;  // packed positions end on a 16-byte boundary (the grid is staged with 16-byte stores)
     s.mask_words = (s.cap + 31) / 32;
     const int nw = s.nt / 32;
-    s.bytes = (size_t)s.cap * (p.dim == 2 ? 4 : 8) + (size_t)((words_per_map + 3) & ~3) * 4 + (size_t)((s.mask_words + 3) & ~3) * 4 +
-              (size_t)3 * nw * sizeof(Slot);
+    s.bytes = (size_t)s.cap * (p.dim == 2 ? 4 : 8) + (grid_in_smem ? (size_t)((words_per_map + 3) & ~3) * 4 : 0) +
+              (size_t)((s.mask_words + 3) & ~3) * 4 + (size_t)3 * nw * sizeof(Slot);
     return s;
 }
 
-template <int DIM, int NT, bool TRACE>
+template <int DIM, int NT, bool TRACE, bool GS = true, int MINB = (DIM == 2 ? 4 : 2)>
 int launch_plan(const PlanArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = plan_kernel<DIM, NT, TRACE>;
+    auto kern = plan_kernel<DIM, NT, TRACE, GS, MINB>;
     NRRT_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 0, per_sm = 0;
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
@@ -750,9 +763,12 @@ int launch_plan(const PlanArgs& a, size_t smem, cudaStream_t st) {
 extern "C" int nrrt_plan_smem_bytes(const NrrtPlanParams* p, size_t* bytes, int* ctas_per_sm) {
     NRRT_REQUIRE(p && (p->dim == 2 || p->dim == 3), "dim must be 2 or 3");
     const int64_t cells = (int64_t)p->shape[0] * p->shape[1] * (p->dim == 3 ? p->shape[2] : 1);
-    const SmemPlan s = smem_plan(*p, (int)nrrt_words_per_map(cells));
+    const SmemPlan s = smem_plan(*p, (int)nrrt_words_per_map(cells), false);  // the production kernels (map bits through L1)
     if (bytes) *bytes = s.bytes;
-    if (ctas_per_sm) *ctas_per_sm = (int)((233472 - 0) / (s.bytes + 1024));
+    if (ctas_per_sm) {
+        const int by_smem = (int)(233472 / (s.bytes + 1024)), by_regs = p->dim == 2 ? 8 : 4;
+        *ctas_per_sm = by_smem < by_regs ? by_smem : by_regs;
+    }
     return NRRT_OK;
 }
 
@@ -780,9 +796,18 @@ extern "C" int nrrt_plan_batch(const NrrtPlanParams* p, const uint32_t* occ_bits
     a.words_per_map = (int)nrrt_words_per_map(cells);
     const SmemPlan s = smem_plan(*p, a.words_per_map);
     a.cap = s.cap; a.mask_words = s.mask_words;
-    if (s.bytes > 232448) return nrrt_fail(NRRT_ERR_UNSUPPORTED, "planner needs %zu B shared memory (> 227 KiB): map or max_iterations too large", s.bytes);
     const bool tracing = out->trace != nullptr && out->trace_cap > 0;
+    const size_t need = tracing ? s.bytes : smem_plan(*p, a.words_per_map, false).bytes;
+    if (need > 232448) return nrrt_fail(NRRT_ERR_UNSUPPORTED, "planner needs %zu B shared memory (> 227 KiB): map or max_iterations too large", need);
     NRRT_CUDA_TRY(cudaMemsetAsync(queue_counter, 0, sizeof(int32_t), st));
-    if (p->dim == 2) return tracing ? launch_plan<2, 128, true>(a, s.bytes, st) : launch_plan<2, 128, false>(a, s.bytes, st);
-    return tracing ? launch_plan<3, 256, true>(a, s.bytes, st) : launch_plan<3, 256, false>(a, s.bytes, st);
+    // Production kernels: map bits through L1, 8 (2D) / 4 (3D) CTAs per SM (see the layout note at the top of the file).
+    // The TRACE kernels (parity tests only) keep the staged copy and the old occupancy: both paths are compared with the
+    // reference's recorded trees, so the two grid paths check each other.
+    if (!tracing) {
+        const SmemPlan g = smem_plan(*p, a.words_per_map, false);
+        if (p->dim == 2) return launch_plan<2, 128, false, false, 8>(a, g.bytes, st);
+        return launch_plan<3, 256, false, false, 4>(a, g.bytes, st);
+    }
+    if (p->dim == 2) return launch_plan<2, 128, true>(a, s.bytes, st);
+    return launch_plan<3, 256, true>(a, s.bytes, st);
 }

@@ -54,10 +54,14 @@ def test_planner_and_sampler_stay_inside_their_buffers(dim, cuda_device):
     res = engine.plan_batch(bits, wl.task_to_map, wl.starts, wl.goals, buffers=bufs, **kw)
     torch.cuda.synchronize()
     arena.check()
-    for k in ("n_nodes", "iterations", "status", "goal_node", "best_node", "path_n", "trace_n", "samples", "neural_flag", "n_draws"):
+    for k in ("n_nodes", "iterations", "status", "goal_node", "best_node", "path_n", "trace_n", "n_draws"):
         assert torch.equal(getattr(res, k), getattr(ref, k)), k
+    drawn = ref.status != _lib.NRRT_SAMPLER_STUCK  # a stuck sampler stops writing sample points where it gives up
+    assert torch.equal(res.samples[drawn], ref.samples[drawn]) and torch.equal(res.neural_flag[drawn], ref.neural_flag[drawn])
     assert torch.equal(res.path_len, ref.path_len)
     for b in range(12):  # rows beyond a task's own nodes / trace records are never written: compare what is defined
+        if not bool(drawn[b]):
+            continue  # the planner skips a task whose sampler gave up: no tree rows are written
         n = int(ref.n_nodes[b]) + (1 if int(ref.goal_node[b]) >= 0 else 0)
         assert torch.equal(res.parent[b, :n], ref.parent[b, :n]) and torch.equal(res.cost[b, :n], ref.cost[b, :n])
         assert torch.equal(res.pos[b, :n], ref.pos[b, :n])
