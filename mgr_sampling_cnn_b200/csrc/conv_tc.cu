@@ -74,6 +74,8 @@ struct ConvParams {
     int group;           // pair slab kernel: samples per scheduling group (tile-major inside a group), see halo_tile
     int fold;            // pair slab kernel: ConvTranspose(k=2,s=2) folded into the 3x3 conv that follows it (see conv_halo2_kernel)
     int ts;              // pair kernels: output tile staged in shared memory and written with TMA stores (see below)
+    int bres;            // pair slab kernel: the layer's whole B (weights) fits the B ring exactly and stays RESIDENT: loaded
+                         // during a CTA's first tile, never again (see conv_halo2_kernel)
     int pm;              // pair kernels: interior polynomial applied by one extra tcgen05.mma per tile (see pm_* below)
     const float* head_w; // optional fused 1x1 head (cout -> 1): logits[pixel] = head_b + sum_c relu_out[c] * head_w[c]
     float head_b;
@@ -1309,6 +1311,10 @@ struct HaloLayout2 {  // per CTA of a pair: its own slabs, half of every B tile
 // with a store and an L2/DRAM round trip between them (ncu, conv8.0: tensor pipe 42 %, issuer waiting on the accumulator,
 // epilogue waiting on the residual).  Through the A ring the residual is prefetched like any operand; K grows by 64 per
 // 64 output channels.
+// p.bres (host: taps x chunks == B_STAGES, 64-output-channel layers): the B ring holds ALL of the layer's weight tiles, one
+// per slot, so the producer fills it during the CTA's first tile and the issuers never wait for or release a B stage
+// again.  These layers are bound by the operand stream from L2 (profiles/conv_decoder_r2.md: conv8.2 pulls 216 KB of
+// slabs + 72 KB of weights per tile at 9 TB/s aggregate); the weights were a quarter of it.
 // p.fold: ConvTranspose(k=2, s=2) folded into the 3x3 conv that consumes it (train.py:196-201: upconv7 -> conv7.0,
 // upconv8 -> conv8.0; no nonlinearity in between, so the composition is linear).  Output pixel (2i + a, 2j + b) of the conv
 // sees the upsampled pixels (2i + a + dy, 2j + b + dx), which come from the 2 x 2 low-resolution pixels (i + a - 1 .. i + a,
@@ -1418,11 +1424,13 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         tma2_load_5d(dst + kSlabBytes, am, abar, cc, xs + 8, ys, dd, ns);
                         if (++sa == A_STAGES) { sa = 0; pa ^= 1u; }
                         for (int dy = 0; dy < p.inner; ++dy) {
-                            mbar_wait(bempty(sb), pb ^ 1u);
-                            if (rank == 0) mbar_expect_tx(bfull(sb), 2 * L::b_stage);  // each CTA loads half of the B tile
-                            const int tap = p.fold ? (par * 4 + dy * 2 + dx) : ((dz * 3 + dy) * 3 + dx);
-                            tma2_load_2d(base + L::off_b + sb * L::b_stage, &map_b, bfull(sb) & kPeerBitMask,
-                                         (tap * p.cin_chunks + c) * kBlockK, nh * BLOCK_N + (int)rank * (BLOCK_N / 2));
+                            if (!p.bres || pt == cluster_id) {  // resident weights: only the CTA's first tile loads them
+                                mbar_wait(bempty(sb), pb ^ 1u);
+                                if (rank == 0) mbar_expect_tx(bfull(sb), 2 * L::b_stage);  // each CTA loads half of the B tile
+                                const int tap = p.fold ? (par * 4 + dy * 2 + dx) : ((dz * 3 + dy) * 3 + dx);
+                                tma2_load_2d(base + L::off_b + sb * L::b_stage, &map_b, bfull(sb) & kPeerBitMask,
+                                             (tap * p.cin_chunks + c) * kBlockK, nh * BLOCK_N + (int)rank * (BLOCK_N / 2));
+                            }
                             if (++sb == B_STAGES) { sb = 0; pb ^= 1u; }
                         }
                     }
@@ -1459,7 +1467,8 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             }
             // drain both rings: multicast commits of the leader must not land in a CTA that already exited
             for (int i = 0; i < A_STAGES; ++i) { mbar_wait(aempty(sa), pa ^ 1u); if (++sa == A_STAGES) { sa = 0; pa ^= 1u; } }
-            for (int i = 0; i < B_STAGES; ++i) { mbar_wait(bempty(sb), pb ^ 1u); if (++sb == B_STAGES) { sb = 0; pb ^= 1u; } }
+            if (!p.bres)  // (resident weights are never released: nothing of the leader's lands on these barriers)
+                for (int i = 0; i < B_STAGES; ++i) { mbar_wait(bempty(sb), pb ^ 1u); if (++sb == B_STAGES) { sb = 0; pb ^= 1u; } }
         }
     } else if (warp == 1 || warp == kIssue2Warp) {
         // ===== two MMA issuers, one per column block.  A single thread needs ~100 cycles of dependent instructions per
@@ -1482,8 +1491,10 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                         tc_fence_after();
                         const uint32_t a_base = base + sa * L::a_stage + blk * kSlabBytes;
                         for (int dy = 0; dy < p.inner; ++dy) {
-                            mbar_wait(bfull(sb), pb);
-                            tc_fence_after();
+                            if (!p.bres || pt == cluster_id) {  // resident weights arrive once, during the first tile
+                                mbar_wait(bfull(sb), pb);
+                                tc_fence_after();
+                            }
                             const uint64_t bdesc = make_smem_desc(base + L::off_b + sb * L::b_stage);
                             // vertical tap dy = start one pixel row (8 px x 128 B) further down the slab
                             const uint64_t adesc = make_smem_desc(a_base + dy * 1024);
@@ -1492,7 +1503,7 @@ conv_halo2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                                 for (int kk = 0; kk < kBlockK / 16; ++kk)
                                     tc_mma2_f16(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
                                                (first && kk == 0) ? 0u : 1u);
-                                tc_commit2(bempty(sb));
+                                if (!p.bres) tc_commit2(bempty(sb));
                             }
                             __syncwarp();
                             first = 0;
@@ -2155,6 +2166,8 @@ int prepare_conv(const NrrtConvLayer* l, PreparedConv& out) {
         NRRT_REQUIRE(three_d && halo && pair && block_n == 128 && p.n_tiles == 1 && res_st && p.ts && !l->poly && p.H >= 4 && p.H % 2 == 0 &&
                          ((uintptr_t)l->poly3 & 15) == 0,
                      "poly3: 3D 3x3x3 layer with 128 output channels, a residual and whole 16x16 tiles per depth slice");
+    // weight tiles one pair iteration consumes: a layer whose count equals an instance's B ring keeps them resident (p.bres)
+    const int k_tiles = (fold || l->res_mma) ? -1 : p.cin_chunks * p.ntaps;
     if (halo && pair) {
         if (block_n == 128 && p.ts) {
             if (p.poly3) { out.launch = launch_halo2<128, 3, 4, true, false, true, true>; return NRRT_OK; }
@@ -2165,10 +2178,17 @@ int prepare_conv(const NrrtConvLayer* l, PreparedConv& out) {
         }
         if (res_st) {
             if (block_n == 128) { out.launch = launch_halo2<128, 3, 5, true>; return NRRT_OK; }
-            { out.launch = launch_halo2<64, 4, 8, true>; return NRRT_OK; }
+            {
+                if (k_tiles == 9) { p.bres = 1; out.launch = launch_halo2<64, 4, 9, true>; return NRRT_OK; }
+                out.launch = launch_halo2<64, 4, 8, true>; return NRRT_OK;
+            }
         }
         if (block_n == 128) { out.launch = launch_halo2<128, 4, 6, false>; return NRRT_OK; }
-        { out.launch = launch_halo2<64, 4, 8, false>; return NRRT_OK; }
+        {
+            if (k_tiles == 9) { p.bres = 1; out.launch = launch_halo2<64, 4, 9, false>; return NRRT_OK; }
+            if (k_tiles == 18) { p.bres = 1; out.launch = launch_halo2<64, 4, 18, false>; return NRRT_OK; }
+            out.launch = launch_halo2<64, 4, 8, false>; return NRRT_OK;
+        }
     }
     if (halo) {
         if (block_n == 128) { out.launch = launch_halo<128, 4, 4>; return NRRT_OK; }
