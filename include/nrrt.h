@@ -428,6 +428,34 @@ int nrrt_select_tasks(int dims, int n_maps, int n_cand, int per_map, int n_tasks
                       const int32_t* cand_goals, const int32_t* reach_steps, int32_t* task_to_map, int32_t* starts,
                       int32_t* goals, float* coords, int32_t* redrawn, int32_t* short_maps, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training-mask makers (csrc/masks.cu): the label images the reference's data pipeline writes next to the
+ * task files and MapsDataset reads back as `mask` (train.py:47-52, ThreeD_train.py:52-57).
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* generate_paths.visualize_path (generate_paths.py:118-169), the saved `path_brightness` image of B tasks:
+ * filled circles of `radius` (10) at every path point (cv2.circle, :129-131), cv2.GaussianBlur with a (ksize, ksize) =
+ * (33, 33) window and sigmaX = sigma = 3 (:134; 8-bit fixed-point arithmetic, BORDER_REFLECT_101), path pixels set to 255
+ * (:136-137), everything zeroed where the map is not above free_above = 240 (:148,155).  Bit-identical to OpenCV 4.x.
+ * occ_maps: uint8 [*][h][w] (255 = free); paths: int32 [B][path_cap][2] (y, x) as astar() returns them
+ * (generate_paths.py:11-74); path_n: int32 [B]; masks: uint8 [B][h][w]. */
+int nrrt_path_masks_2d(const uint8_t* occ_maps, const int32_t* task_to_map, const int32_t* paths, const int32_t* path_n,
+                       int path_cap, int B, int h, int w, int radius, int ksize, double sigma, int free_above, uint8_t* masks,
+                       void* stream);
+/* Host-only: the two tables the kernel above is built on -- half_width[0..radius] of cv2.circle's filled disk per |dy| and
+ * the ksize fixed-point (8.8) Gaussian taps.  No device work. */
+int nrrt_mask_tables_host(int radius, int ksize, double sigma, int32_t* half_width, int32_t* taps);
+
+/* ThreeD_generate_paths.save_and_visualize_path:142-150: vols[b] = zeros with 255 on the voxels of path b.
+ * paths: int32 [B][path_cap][3] (x, y, z) = array axes; vols: uint8 [B][s0][s1][s2]. */
+int nrrt_paths_to_volume(const int32_t* paths, const int32_t* path_n, int path_cap, int B, int s0, int s1, int s2, uint8_t* vols,
+                         void* stream);
+/* ThreeD_enlarge_path.enlarge_the_path (ThreeD_enlarge_path.py:25-65) for B path volumes: every voxel that is free
+ * (occ != 255) and at Chebyshev distance d < layers from a voxel with path == 255 becomes max(path, values[d]);
+ * values_host: HOST uint8 [layers], the reference's `path_value` per shell as its uint8 array stores it (206, 157, 108, 59,
+ * 10 for LAYERS = 5).  out must not alias path_vols.  layers <= 6. */
+int nrrt_enlarge_paths_3d(const uint8_t* occ_maps, const int32_t* task_to_map, const uint8_t* path_vols, int B, int s0, int s1,
+                          int s2, int layers, const uint8_t* values_host, uint8_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ SOURCES = {
     "forward.cu": [],
     "generate.cu": [],
     "gridpath.cu": [],
+    "masks.cu": [],
 }
 COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
           "-I", os.path.join(_ROOT, "include"), "-I", CSRC]

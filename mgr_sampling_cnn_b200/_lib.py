@@ -125,6 +125,12 @@ _SIGNATURES = {
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrrt_select_tasks": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrrt_path_masks_2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    "nrrt_mask_tables_host": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
+    "nrrt_paths_to_volume": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nrrt_enlarge_paths_3d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrrt_head_1x1": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
 }
 
