@@ -456,6 +456,78 @@ int nrrt_paths_to_volume(const int32_t* paths, const int32_t* path_n, int path_c
 int nrrt_enlarge_paths_3d(const uint8_t* occ_maps, const int32_t* task_to_map, const uint8_t* path_vols, int B, int s0, int s1,
                           int s2, int layers, const uint8_t* values_host, uint8_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step: UNet_cooler.training_step (train.py:205-210) = forward in train mode, nn.BCEWithLogitsLoss
+ * (:113), loss.backward(), torch.optim.Adam(lr=1e-3) (:228-229).  The forward convolutions and the data gradients are
+ * nrrt_conv_layer calls (a data gradient is the same convolution with the weights of nrrt_pack_dgrad_weight); the weight
+ * gradients are nrrt_conv_wgrad (csrc/wgrad_tc.cu, tcgen05); the rest are one-pass kernels of csrc/train_ops.cu.
+ * Activations and activation gradients are fp16 channels-last; parameters, their gradients and the Adam state are fp32.
+ * Gradients are computed for loss * grad_scale_inverse (the caller picks the scale: nrrt_bce_with_logits' grad_scale) and
+ * unscaled by nrrt_adam_step.  The host graph is mgr_sampling_cnn_b200/trainer.py.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* Channels-last slice [n][h][w][in_cstride] (channels [0, c) at `in`) -> channel-major fp16, optionally masked by the ReLU
+ * output it belongs to (value kept where relu_mask > 0; NULL = no mask):
+ *   mode 0: out [copies][c][n][h][w]; copies = 1, or 3 for the X operand of a 3x3 weight gradient: copy k holds the image
+ *   shifted by k - 1 pixels along w, out[k][..][x] = in[..][x + k - 1] (zero outside), because a TMA tile row cannot start
+ *   at an odd pixel;  mode 1: out [c][n][2h][2w], value at the even positions, zeros elsewhere (the gradient of a
+ *   stride-2 convolution seen on its input grid);  mode 2: out [4][c][n][h/2][w/2], group (y & 1) * 2 + (x & 1) (the
+ *   gradient of a ConvTranspose k2 s2 seen on its input grid). */
+int nrrt_to_channel_major(const void* in, int64_t in_cstride, const void* relu_mask, int64_t mask_cstride, int n, int h, int w, int c,
+                          int mode, int copies, void* out, void* stream);
+/* dw[co][tap][ci] += sum over pixels dy[co][pixel] * x[ci][pixel + tap] for a ksize x ksize (1 or 3), stride 1, pad ksize / 2
+ * convolution; dy_cm [cout][n][h][w] and x_cm [ksize][cin][n][h][w] (the shifted copies) channel-major fp16
+ * (nrrt_to_channel_major); dw fp32
+ * [cout][ksize * ksize][ci_stride] (taps in (ky, kx) order; the caller zeroes it).  w must be a multiple of 64. */
+int nrrt_conv_wgrad(const void* dy_cm, int cout, const void* x_cm, int cin, int n, int h, int w, int ksize, float* dw, int ci_stride,
+                    void* stream);
+/* g = dy where y > 0 else 0 (y = the stored output of a conv + bias + ReLU layer; NULL = no mask), dbias[c] += sum g
+ * (dbias may be NULL; g may be NULL or alias dy). */
+int nrrt_relu_bwd_sum(const void* dy, int64_t dy_cs, const void* y, int64_t y_cs, void* g, int64_t g_cs, float* dbias, int64_t pixels,
+                      int c, void* stream);
+/* nn.BatchNorm2d in train mode over a raw conv output z: batch statistics (biased variance), running statistics updated
+ * with `momentum` (unbiased variance), y = [relu](gamma * (z - mean) * rstd + beta [+ res]).  save_mean / save_rstd: fp32 [c]
+ * for the backward; scale_shift: fp32 [2c] scratch; work: fp64 [2c] scratch. */
+int nrrt_bn_train_forward(const void* z, int64_t z_cs, int64_t pixels, int c, const float* gamma, const float* beta, float eps,
+                          float momentum, float* running_mean, float* running_var, const void* res, int64_t res_cs, int relu, void* y,
+                          int64_t y_cs, float* save_mean, float* save_rstd, float* scale_shift, double* work, void* stream);
+/* Its backward: g = dy masked by y_mask > 0 (NULL = none); dbeta += sum g; dgamma += sum g * xhat;
+ * dz = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)); g_out (optional) = g, the gradient of the residual branch. */
+int nrrt_bn_train_backward(const void* dy, int64_t dy_cs, const void* y_mask, int64_t y_cs, const void* z, int64_t z_cs, int64_t pixels,
+                           int c, const float* gamma, const float* save_mean, const float* save_rstd, void* dz, int64_t dz_cs,
+                           void* g_out, int64_t g_cs, float* dgamma, float* dbeta, double* work, void* stream);
+/* Channels-last pixel remaps: mode 0 = space to depth, in [n][2h][2w][c] -> out [n][h][w][4c] (channel (a * 2 + b) * c + k =
+ * pixel (2y + a, 2x + b)); mode 1 = zero-stuffing, in [n][h][w][c] -> out [n][2h][2w][c] dense. */
+int nrrt_remap_channels_last(const void* in, int64_t in_cs, void* out, int64_t out_cs, int n, int h, int w, int c, int mode, void* stream);
+/* nn.BCEWithLogitsLoss: *loss_sum = sum of the per-element losses (divide by count for the mean, train.py:113,208);
+ * dlogits (optional) = (sigmoid(z) - t) * grad_scale.  logit_bias (optional, one device float: final_conv's bias, which
+ * lives in the device-resident parameter buffer) is added to logits in place first. */
+int nrrt_bce_with_logits(float* logits, const float* logit_bias, const float* target, int64_t count, float grad_scale, float* dlogits,
+                         double* loss_sum, void* stream);
+/* MapsDataset's mask normalisation (train.py:47-50): target = (mask - min) / (max - min) per sample, float64 then float32. */
+int nrrt_mask_targets(const uint8_t* masks, int B, int64_t cells, float* target, void* stream);
+/* final_conv (1x1, c -> 1) backward: g = x > 0 ? dlogits * weight[k] : 0 (x = the ReLU output feeding the head);
+ * dweight[k] += sum dlogits * x; *dbias += sum dlogits. */
+int nrrt_head_backward(const float* dlogits, const void* x, int64_t x_cs, const float* weight, int64_t pixels, int c, void* g, int64_t g_cs,
+                       float* dweight, float* dbias, void* stream);
+/* torch.optim.Adam (no weight decay / amsgrad) on a flat fp32 buffer; the gradient is multiplied by grad_scale first. */
+int nrrt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, int step, float lr, float beta1,
+                   float beta2, float eps, float grad_scale, void* stream);
+int nrrt_to_half(const float* src, void* dst, int64_t count, void* stream);
+/* Data-gradient weights: dst fp16 [ci_rows][taps][co_cols], dst[ci][taps - 1 - t][co] = w[co][t][ci] (w fp32
+ * [cout][taps][ci_stride]); rows / columns beyond the source are zero. */
+int nrrt_pack_dgrad_weight(const float* w, int cout, int taps, int ci_stride, int ci_rows, int co_cols, void* dst, void* stream);
+/* First conv (cin -> cout from the fp32 NCHW input, train.py:118): dweight[co][ci][tap] += sum g[pixel][co] x[ci][pixel + tap];
+ * dbias[co] += sum g.  g: fp16 channels-last, already masked by the ReLU. */
+int nrrt_stem_wgrad(const float* x, const void* g, int64_t g_cs, int n, int cin, int h, int w, int cout, float* dweight, float* dbias,
+                    void* stream);
+/* Coordinate branch backward (train.py:179-190).  nrrt_coords_fill_backward: dfeat[b][q][k] += sum over pixels of the
+ * bilinear weight of corner q times dcat[b][pixel][k] (the transpose of nrrt_coords_fill on a 2x2 source).
+ * nrrt_coords_layer_backward: one conv_coords_* layer (3x3 + ReLU on the 2x2 grid): g = dfeat_out masked by f_out > 0;
+ * dweight [tap][cin][cout] += ..., dbias += ..., dfeat_in (optional) += W^T g. */
+int nrrt_coords_fill_backward(const void* dcat, int64_t cs, int B, int h, int w, int c, float* dfeat, void* stream);
+int nrrt_coords_layer_backward(const float* dfeat_out, const float* f_out, const float* f_in, const float* weight, int B, int cin, int cout,
+                               float* dweight, float* dbias, float* dfeat_in, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

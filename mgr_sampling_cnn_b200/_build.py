@@ -18,6 +18,8 @@ SOURCES = {
     "generate.cu": [],
     "gridpath.cu": [],
     "masks.cu": [],
+    "wgrad_tc.cu": [],
+    "train_ops.cu": [],
 }
 COMMON = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
           "-I", os.path.join(_ROOT, "include"), "-I", CSRC]

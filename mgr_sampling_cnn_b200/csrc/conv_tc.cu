@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "nrrt_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -82,120 +83,6 @@ struct ConvParams {
     float* logits;
     uint32_t a_bytes, b_bytes;
 };
-
-// ---- PTX wrappers --------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// A macro (not a function) so that profiler samples land on the call site's source line.
-#define mbar_wait(bar, parity)                                                            \
-    asm volatile(                                                                         \
-        "{\n\t.reg .pred p;\n\t"                                                         \
-        "WAIT_LOOP:\n\t"                                                                  \
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"                       \
-        "@p bra WAIT_DONE;\n\t"                                                           \
-        "bra WAIT_LOOP;\n\t"                                                              \
-        "WAIT_DONE:\n\t}" ::"r"((uint32_t)(bar)), "r"((uint32_t)(parity))                 \
-        : "memory")
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
-                                            int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
-            "r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-// L2 prefetch of a tile that a later cp.async.bulk.tensor load will fetch (no shared-memory destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1),
-                 "r"(c2), "r"(c3), "r"(c4)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-        "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-// one elected lane of a converged warp (cute::elect_one_sync): the warp runs the issue loop convergently, so descriptor
-// arithmetic stays in uniform registers and each tcgen05.mma needs no per-lane operand broadcast
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(pred));
-    return pred != 0;
-}
-// ---- TMA-store epilogue (pair kernels) ------------------------------------------------------------------------------
-// A thread owns one pixel row of the accumulator, so direct stores put 16 bytes per lane at a 2*Ctot-byte stride: 32 partial
-// sectors per instruction, which made the store path 20-40 % of every full-resolution layer.  Instead the epilogue warps
-// write their fp16 results into 64-channel pieces in shared memory (128 pixel rows x 128 B, SWIZZLE_128B -- for layers with
-// a residual, in place over the staged residual piece they have just read), and the auxiliary warp writes each finished
-// piece with ONE cp.async.bulk.tensor store (full 128-byte lines; TMA clips rows outside the image).
-__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
-                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-                 : "memory");
-}
-// commit the store just issued and wait until it has been read out of shared memory.  (Keeping one store in flight and
-// freeing the piece one step later was measured slower: the next residual load of that piece starts too late.)
-__device__ __forceinline__ void tma_store_commit_and_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_drain() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (PTX ISA "tcgen05 matrix descriptor"): start address >> 4,
-// LBO (unused for swizzled K-major) = 1, SBO = 1024 B between 8-row groups, version 1, layout type 2 = 128B swizzle.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// kind::f16 instruction descriptor: D = f32, A = B = f16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int n, int m = kBlockM) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
 
 // fp32 pair -> packed fp16x2 (lo in the low half) with the clamp to the finite fp16 range, and optionally the ReLU, inside
 // the conversion instruction (F2FP.SATFINITE[.RELU]): relu + clamp + pack was 5 instructions per pair of outputs

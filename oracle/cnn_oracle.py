@@ -24,7 +24,12 @@ def strict_fp32():
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+_TRAIN = [False]   # train-mode BatchNorm (batch statistics, running statistics updated in `sd`): oracle/train_oracle.py
+
+
 def _bn(x, sd, p):
+    if _TRAIN[0]:
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], True, 0.1, 1e-5)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"], False, 0.0, 1e-5)
 
 

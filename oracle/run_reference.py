@@ -203,6 +203,49 @@ def run_cnn(job):
     return out
 
 
+def run_train_step(job):
+    """One optimisation step of the unmodified reference: UNet_cooler.training_step (train.py:205-210) in train mode, backward,
+    and one step of the optimizer configure_optimizers() returns (train.py:227-234) -- what a Lightning Trainer does per batch."""
+    import torch
+    _patch_torchvision()
+    torch.manual_seed(int(job["seed"]))
+    import train as T
+    model = T.UNet_cooler()
+    model.train()
+    x, y, coords = (torch.from_numpy(np.asarray(job[k])) for k in ("x", "y", "coords"))
+    opt = model.configure_optimizers()["optimizer"]
+    opt.zero_grad()
+    loss = model.training_step((x, y, coords), 0)
+    loss.backward()
+    out = {"loss": np.float64(loss.item())}
+    names, gnorm, gsum = [], [], []
+    keep = set(str(k) for k in job["keep"])
+    alias = {"base_model.layer1.": "conv2.", "base_model.layer2.": "conv3.", "base_model.layer3.": "conv4.", "base_model.layer4.": "conv5."}
+    params = {}
+    for k, p_ in model.named_parameters():   # shared modules are listed once, under base_model.layerN: name them as forward() uses them
+        for a, b in alias.items():
+            if k.startswith(a):
+                k = b + k[len(a):]
+        params[k] = p_
+    for k, p_ in params.items():
+        if p_.grad is None:
+            continue
+        names.append(k)
+        gnorm.append(float(p_.grad.double().norm()))
+        gsum.append(float(p_.grad.double().sum()))
+        if k in keep:
+            out["grad/" + k] = p_.grad.numpy().copy()
+    opt.step()
+    psum = [float(params[k].detach().double().sum()) for k in names]
+    sd = model.state_dict()
+    for k in keep:
+        out["new/" + k] = sd[k].numpy().copy()
+    for k in job["keep_stats"]:
+        out["stat/" + str(k)] = sd[str(k)].numpy().copy()
+    out.update(names=np.array(names), grad_norm=np.array(gnorm), grad_sum=np.array(gsum), param_sum_after=np.array(psum))
+    return out
+
+
 def run_dataset_cnn(job):
     """The reference's own data path in front of the model: a task file written to disk, read back by `MapsDataset`
     (train.py:38-69 / ThreeD_train.py:38-66: min-max normalisation, coordinates parsed from the file name, ToTensorV2),
@@ -294,7 +337,7 @@ def run_radius(job):
     return {"radius": np.array(out, dtype=np.float64)}
 
 
-JOBS = {"plan": run_plan, "neural_draws": run_neural_draws, "cnn": run_cnn, "gen": run_gen, "radius": run_radius,
+JOBS = {"train_step": run_train_step, "plan": run_plan, "neural_draws": run_neural_draws, "cnn": run_cnn, "gen": run_gen, "radius": run_radius,
         "dataset_cnn": run_dataset_cnn}
 
 

@@ -86,3 +86,14 @@ def random_tasks_3d(rng, occ, n):
             out_s.append(s)
             out_g.append(g)
     return np.array(out_s, dtype=np.int32), np.array(out_g, dtype=np.int32)
+
+
+def load_train_batch(name="train2d_seed0"):
+    """The golden training batch as MapsDataset yields it (train.py:38-69): x fp32 [B,3,H,W] in {0,1}, y fp32 [B,1,H,W] in
+    [0,1] (min-max of the mask), coords fp32 [B,1,2,2]; plus the raw uint8 masks and the golden record."""
+    g = load(name)
+    occ = np.unpackbits(g["occ_bits"], axis=-1).astype(np.float32)          # {0, 1}: the min-max normalised map
+    x = np.repeat(occ[:, None], 3, axis=1)
+    m = g["masks"].astype(np.float64)
+    y = np.stack([(k - k.min()) / (k.max() - k.min()) for k in m])[:, None].astype(np.float32)
+    return x, y, g["coords"].astype(np.float32), g["masks"], g

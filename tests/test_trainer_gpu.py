@@ -1,0 +1,98 @@
+"""The training step on the B200 kernels (mgr_sampling_cnn_b200/trainer.py) against the reference's own step recorded in
+tests/golden/train2d_seed0.npz (loss, gradient norms, selected gradients, BatchNorm running statistics) and against the fp32
+torch oracle (oracle/train_oracle.py) for every gradient tensor.
+
+Tolerances.  The forward runs fp16 operands / fp32 accumulate like the inference path (logits <= 1e-2 abs), activation
+gradients are fp16, parameter gradients fp32.  Decoder, coordinate-branch and head gradients (99.99 % of the gradient norm)
+must agree to 5e-3 relative L2 (measured: <= 1.5e-3).  The random-init ENCODER's gradients are 1e3 - 1e7 times smaller and
+ill-conditioned: in a pure fp32 autograd run, rounding the weights to fp16 moves them by 2 - 4 %, and fp16-sized relative
+noise (3e-4 .. 1e-3) on the conv outputs moves them by 2 - 15 % (scripts/train_probe3.py, profiles/train_r2.md), so they
+are held to 15 % here (measured: 0.1 - 11 %)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+def _encoder(key):
+    return key.startswith(("conv1.", "conv2.", "conv3.", "conv4.", "conv5."))
+
+
+def _setup():
+    from mgr_sampling_cnn_b200 import train, trainer
+    x, y, coords, masks, g = H.load_train_batch()
+    torch.manual_seed(0)
+    model = train.UNet_cooler()
+    tr = trainer.UNetTrainer(model, 2, 512, 512, DEV)
+    return model, tr, x, y, coords, masks, g
+
+
+def test_training_step_matches_reference_and_oracle():
+    from oracle import train_oracle
+    model, tr, x, y, coords, masks, g = _setup()
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    xd, cd = torch.from_numpy(x).to(DEV), torch.from_numpy(coords).to(DEV)
+    tr.forward(xd, cd)
+    tr.set_targets(masks_u8=torch.from_numpy(masks))
+    assert torch.equal(tr.target.cpu(), torch.from_numpy(y[:, 0]))           # MapsDataset's normalisation, bit for bit
+    tr.loss_and_grad(True)
+    loss = float(tr.loss_sum.item()) / tr.M
+    assert abs(loss - float(g["loss"])) <= 2e-3 * float(g["loss"]), (loss, float(g["loss"]))
+    tr.backward()
+    torch.cuda.synchronize()
+    grads = {k: v.cpu() for k, v in tr.named(tr.grads, 1.0 / tr.loss_scale).items()}
+    # (1) the reference's own numbers
+    names = [str(n) for n in g["names"]]
+    assert sorted(names) == sorted(grads.keys())
+    worst = 0.0
+    for k, gn in zip(names, g["grad_norm"]):
+        rel = abs(float(grads[k].double().norm()) - gn) / gn
+        worst = max(worst, rel)
+        assert rel <= (0.10 if _encoder(k) else 5e-3), (k, rel)
+    for key in g.keys():
+        if key.startswith("grad/"):
+            ref = torch.from_numpy(g[key])
+            err = float((grads[key[5:]] - ref).norm() / ref.norm())
+            assert err <= (0.15 if _encoder(key[5:]) else 5e-3), (key, err)
+    # (2) every gradient tensor against the fp32 oracle
+    oloss, ograds, ostats, ologits = train_oracle.forward_backward(sd, torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(coords))
+    assert float((tr.logits.cpu() - ologits[:, 0]).abs().max()) <= 1e-2
+    errs = {k: float((grads[k] - ograds[k]).norm() / ograds[k].norm()) for k in ograds}
+    bad = {k: e for k, e in errs.items() if e > (0.15 if _encoder(k) else 5e-3)}
+    assert not bad, bad
+    print("gradient relative L2 errors: max %.3g (%s), median %.3g; norm error vs reference max %.3g" %
+          (max(errs.values()), max(errs, key=errs.get), float(np.median(list(errs.values()))), worst))
+    # (3) BatchNorm running statistics after one step
+    for key in g.keys():
+        if key.startswith("stat/"):
+            name = key[5:]
+            mod = name.rsplit(".", 1)[0]
+            cv = [c for c in tr.convs.values() if c.bn is not None and c.bn[4] is model.get_submodule(mod)][0]
+            got = cv.bn[2 if name.endswith("running_mean") else 3].cpu().numpy()
+            assert np.allclose(got, g[key], rtol=2e-3, atol=2e-4), key
+    # (4) Adam: the first step moves every weight by lr * sign(g) (up to eps); elements whose gradient is numerically zero may flip
+    tr.optimizer_step()
+    tr.export_to(model)
+    new_sd = model.state_dict()
+    for key in g.keys():
+        if key.startswith("new/"):
+            ref, got = g[key], new_sd[key[4:]].cpu().numpy()
+            frac = float((np.abs(got - ref) > 2e-4).mean())
+            assert frac <= (0.15 if _encoder(key[4:]) else 0.02), (key, frac)
+
+
+def test_loss_decreases_and_exported_model_runs():
+    model, tr, x, y, coords, masks, g = _setup()
+    batch = (torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(coords))
+    losses = [float(tr.training_step(batch).item()) for _ in range(8)]
+    assert losses[-1] < 0.8 * losses[0], losses
+    assert all(np.isfinite(losses))
+    tr.export_to(model)
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        out = model(batch[0].to(DEV), batch[2].to(DEV))          # the inference path (eval-mode BatchNorm, folded kernels)
+    assert out.shape == (2, 1, 512, 512) and bool(torch.isfinite(out).all())
