@@ -125,6 +125,53 @@ __global__ void __launch_bounds__(256) coords_kernel(const float* __restrict__ c
     }
 }
 
+// One layer of the branch for SMALL batches (the training step: 3 tasks): the fused kernel above has B / kTB CTAs, i.e. one
+// CTA walking 1.6 M weights alone.  Here a CTA is (64 output channels, kTB tasks) of one layer; same accumulation order per
+// output (bias, then tap-major / ci-inner fmaf), so the results are bit-identical to coords_kernel's.
+__global__ void __launch_bounds__(64) coords_layer_kernel(const float* __restrict__ in, int B, int gh, int gw, int cin, int cout,
+                                                          const float* __restrict__ wt, const float* __restrict__ bias,
+                                                          float* __restrict__ out) {
+    extern __shared__ float s_in[];   // [kTB][P][cin]
+    const int P = gh * gw;
+    const int t0 = blockIdx.y * kTB;
+    const int nt = min(kTB, B - t0);
+    const int co = blockIdx.x * 64 + threadIdx.x;
+    for (int i = threadIdx.x; i < nt * P * cin; i += blockDim.x) s_in[i] = in[(size_t)t0 * P * cin + i];
+    __syncthreads();
+    if (co >= cout) return;
+    float acc[kTB][kMaxP];
+#pragma unroll
+    for (int t = 0; t < kTB; ++t)
+#pragma unroll
+        for (int pp = 0; pp < kMaxP; ++pp) acc[t][pp] = bias[co];
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3 - 1, kx = tap % 3 - 1;
+        const float* wp = wt + (size_t)tap * cin * cout + co;
+        for (int ci = 0; ci < cin; ++ci) {
+            const float w = __ldg(wp + (size_t)ci * cout);
+#pragma unroll
+            for (int pp = 0; pp < kMaxP; ++pp) {
+                if (pp >= P) break;
+                const int y = pp / gw + ky, x = pp % gw + kx;
+                if (y < 0 || y >= gh || x < 0 || x >= gw) continue;
+                const int sp = y * gw + x;
+#pragma unroll
+                for (int t = 0; t < kTB; ++t)
+                    if (t < nt) acc[t][pp] = fmaf(s_in[(t * P + sp) * cin + ci], w, acc[t][pp]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < kTB; ++t) {
+        if (t >= nt) break;
+#pragma unroll
+        for (int pp = 0; pp < kMaxP; ++pp) {
+            if (pp >= P) break;
+            out[((size_t)(t0 + t) * P + pp) * cout + co] = fmaxf(acc[t][pp], 0.f);
+        }
+    }
+}
+
 // ---- align_corners interpolation of the (gh x gw [x 1]) feature into a channel slice (PyTorch's fp32 formulas) -------
 // Output pixels are ordered (b, a0, a1, a2); a0 interpolates the gh axis, a1 the gw axis, a2 is constant
 // (2D: (H, W, 1); 3D: `coords.unsqueeze(-1)` makes the source (2, 3, 1), so the last output axis has a single source cell).
@@ -735,6 +782,17 @@ extern "C" int nrrt_coords_branch(const float* coords, int B, int gh, int gw, co
     NRRT_REQUIRE(coords && weights && biases && feats, "null pointer");
     NRRT_REQUIRE(B >= 0 && gh >= 1 && gh <= 3 && gw >= 1 && gw <= 3, "coords grid must be at most 3x3");
     if (B == 0) return NRRT_OK;
+    if (B <= 64) {   // too few CTAs for the fused kernel: one launch per layer, parallel over output channels
+        const int cins[4] = {1, 64, 128, 256}, couts[4] = {64, 128, 256, 512};
+        const float* in = coords;
+        for (int l = 0; l < 4; ++l) {
+            coords_layer_kernel<<<dim3((couts[l] + 63) / 64, (B + kTB - 1) / kTB), 64, (size_t)kTB * gh * gw * cins[l] * sizeof(float),
+                                  reinterpret_cast<cudaStream_t>(stream)>>>(in, B, gh, gw, cins[l], couts[l], weights[l], biases[l], feats[l]);
+            in = feats[l];
+        }
+        NRRT_CUDA_TRY(cudaGetLastError());
+        return NRRT_OK;
+    }
     coords_kernel<<<(B + kTB - 1) / kTB, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(coords, B, gh, gw, weights[0], biases[0], weights[1], biases[1],
                                                                          weights[2], biases[2], weights[3], biases[3], feats[0],
                                                                          feats[1], feats[2], feats[3]);

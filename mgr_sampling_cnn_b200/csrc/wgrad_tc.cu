@@ -255,11 +255,13 @@ struct CmArgs {
 };
 
 __global__ void __launch_bounds__(256) to_channel_major_kernel(const CmArgs a) {
-    __shared__ __half tile[66][72];                  // pixels x0 - 1 .. x0 + 64
+    // tile_t[c][1 + px]: 64 channels x pixels x0 - 1 .. x0 + 64 of one image row, channel-major (33 words per row: the 8
+    // channel chunks of a pixel land 8 banks apart)
+    __shared__ __half tile_t[64][66];
     const int x0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
     const int n = blockIdx.z / a.H, y = blockIdx.z % a.H;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 66 * 8; i += 256) {          // 66 pixels x 8 chunks of 8 channels
+    for (int i = tid; i < 66 * 8; i += 256) {          // 66 pixels x 8 chunks of 8 channels: 128 contiguous bytes per pixel
         const int px = i >> 3, ch = (i & 7) * 8, x = x0 + px - 1;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (x >= 0 && x < a.W && c0 + ch < a.C) {
@@ -279,22 +281,57 @@ __global__ void __launch_bounds__(256) to_channel_major_kernel(const CmArgs a) {
                 }
             }
         }
-        *reinterpret_cast<uint4*>(&tile[px][ch]) = v;
+        const __half* vh = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tile_t[ch + j][px] = vh[j];
     }
     __syncthreads();
-    for (int i = tid; i < 64 * 64; i += 256) {
-        const int c = i >> 6, px = i & 63, x = x0 + px;
-        if (x >= a.W || c0 + c >= a.C) continue;
+    // a thread writes 8 consecutive pixels of one channel (16 bytes); a warp writes 4 channels x 128 contiguous bytes
+    for (int i = tid; i < 64 * 8; i += 256) {
+        const int c = i >> 3, gp = (i & 7) * 8, x = x0 + gp;
+        if (c0 + c >= a.C || x >= a.W) continue;
+        const __half* src = &tile_t[c][gp + 1];
+        const bool full = x + 8 <= a.W && (a.W & 7) == 0;
         if (a.mode == 0) {
-            for (int k = 0; k < a.copies; ++k)
-                a.out[((((size_t)k * a.C + c0 + c) * a.N + n) * a.H + y) * a.W + x] = tile[px + 1 + k - a.copies / 2][c];
-            continue;
+            for (int k = 0; k < a.copies; ++k) {
+                const int sh = k - a.copies / 2;
+                __align__(16) __half v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = src[j + sh];
+                __half* dst = a.out + ((((size_t)k * a.C + c0 + c) * a.N + n) * a.H + y) * a.W + x;
+                if (full) *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
+                else for (int j = 0; j < 8 && x + j < a.W; ++j) dst[j] = v[j];
+            }
+        } else if (a.mode == 1) {   // row 2y: values at even x, zeros between; row 2y + 1: zeros
+            __half* r0 = a.out + (((size_t)(c0 + c) * a.N + n) * (2 * a.H) + 2 * y) * (2 * a.W) + 2 * x;
+            __half* r1 = r0 + 2 * a.W;
+            const __half z = __float2half(0.f);
+            if (full) {
+                __align__(16) __half v[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { v[2 * j] = src[j]; v[2 * j + 1] = z; }
+                reinterpret_cast<uint4*>(r0)[0] = reinterpret_cast<const uint4*>(v)[0];
+                reinterpret_cast<uint4*>(r0)[1] = reinterpret_cast<const uint4*>(v)[1];
+                reinterpret_cast<uint4*>(r1)[0] = make_uint4(0, 0, 0, 0);
+                reinterpret_cast<uint4*>(r1)[1] = make_uint4(0, 0, 0, 0);
+            } else {
+                for (int j = 0; j < 8 && x + j < a.W; ++j) { r0[2 * j] = src[j]; r0[2 * j + 1] = z; r1[2 * j] = z; r1[2 * j + 1] = z; }
+            }
+        } else {                    // space to depth: even / odd pixels of this row go to groups (y & 1) * 2 + {0, 1}
+            const size_t plane = (size_t)a.C * a.N * (a.H / 2) * (a.W / 2);
+            __half* d0 = a.out + (size_t)((y & 1) * 2) * plane + (((size_t)(c0 + c) * a.N + n) * (a.H / 2) + (y >> 1)) * (a.W / 2) + (x >> 1);
+            __half* d1 = d0 + plane;
+            if (full) {
+                __align__(8) __half e[4];
+                __align__(8) __half o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { e[j] = src[2 * j]; o[j] = src[2 * j + 1]; }
+                *reinterpret_cast<uint2*>(d0) = *reinterpret_cast<const uint2*>(e);
+                *reinterpret_cast<uint2*>(d1) = *reinterpret_cast<const uint2*>(o);
+            } else {
+                for (int j = 0; j < 8 && x + j < a.W; ++j) ((j & 1) ? d1 : d0)[j >> 1] = src[j];
+            }
         }
-        const __half v = tile[px + 1][c];
-        size_t o;
-        if (a.mode == 1) o = (((size_t)(c0 + c) * a.N + n) * (2 * a.H) + 2 * y) * (2 * a.W) + 2 * x;
-        else o = ((((size_t)((y & 1) * 2 + (x & 1)) * a.C + c0 + c) * a.N + n) * (a.H / 2) + (y >> 1)) * (a.W / 2) + (x >> 1);
-        a.out[o] = v;
     }
 }
 
@@ -310,7 +347,7 @@ extern "C" int nrrt_to_channel_major(const void* in, int64_t in_cstride, const v
     NRRT_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)relu_mask & 15) == 0, "pointers must be 16-byte aligned");
     NRRT_REQUIRE((long long)n * h <= 65535, "n * h must be <= 65535");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (mode == 1) NRRT_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)c * n * h * w * 4 * 2, st));
+    NRRT_REQUIRE(((uintptr_t)out & 15) == 0, "out must be 16-byte aligned");
     CmArgs a;
     a.in = (const __half*)in; a.mask = (const __half*)relu_mask; a.out = (__half*)out;
     a.in_cstride = in_cstride; a.mask_cstride = mask_cstride; a.N = n; a.H = h; a.W = w; a.C = c; a.mode = mode; a.copies = copies;
