@@ -29,7 +29,8 @@ constexpr int kNA = 4;   // A ring (dY rows)
 constexpr int kNB = 6;   // B ring (X rows): nky live + prefetch
 
 struct WgradParams {
-    int H, xblocks, strips;       // strips = N * xblocks
+    int H, xblocks, strips;       // work units: strips = N * xblocks * segs (image, 64-pixel column block, row segment)
+    int seg_rows, segs;           // rows per segment, segments per column
     int co, ci;                   // true channel counts
     int nky, nkx, pad;            // 3,3,1 or 1,1,0
     int co_blocks, ci_blocks, splits;
@@ -86,7 +87,6 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int split = t;
     const int per = (p.strips + p.splits - 1) / p.splits;
     const int s_begin = split * per, s_end = min(p.strips, s_begin + per);
-    const int rows_b = p.H + 2 * p.pad;   // operand rows loaded per strip
 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kNA; ++s) { mbar_init(full_a(s), 1); mbar_init(empty_a(s), 1); }
@@ -107,8 +107,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         if (lane == 0) {
             uint32_t a_seq = 0, b_seq = 0;
             for (int s = s_begin; s < s_end; ++s) {
-                const int n = s / p.xblocks, x0 = (s % p.xblocks) * 64;
-                for (int r = -p.pad; r < p.H + p.pad; ++r) {
+                const int seg = s % p.segs, sx = s / p.segs;
+                const int n = sx / p.xblocks, x0 = (sx % p.xblocks) * 64;
+                const int y0 = seg * p.seg_rows, rows = min(p.seg_rows, p.H - y0);
+                for (int r = y0 - p.pad; r < y0 + rows + p.pad; ++r) {
                     {
                         const uint32_t slot = b_seq % kNB, ph = (b_seq / kNB) & 1u;
                         mbar_wait(empty_b(slot), ph ^ 1u);
@@ -118,7 +120,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                         ++b_seq;
                     }
                     const int y = r - p.pad;
-                    if (y >= 0) {
+                    if (y >= y0) {
                         const uint32_t slot = a_seq % kNA, ph = (a_seq / kNA) & 1u;
                         mbar_wait(empty_a(slot), ph ^ 1u);
                         mbar_expect_tx(full_a(slot), (p.dbg & 4) ? 0u : L::a_stage);
@@ -134,7 +136,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         uint32_t a_seq = 0, bq = 0, b_waited = 0;   // b_waited = number of B loads already waited for (they complete in order)
         bool first = true;
         for (int s = s_begin; s < s_end; ++s) {
-            for (int y = 0; y < p.H; ++y) {
+            const int rows = min(p.seg_rows, p.H - (s % p.segs) * p.seg_rows);
+            for (int y = 0; y < rows; ++y) {     // y = row inside the segment
                 const uint32_t a_slot = a_seq % kNA;
                 mbar_wait(full_a(a_slot), (a_seq / kNA) & 1u);
                 const uint32_t need = bq + (uint32_t)(y + 2 * p.pad);   // last B load this k-block reads
@@ -155,14 +158,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     }
                     tc_commit(empty_a(a_slot));
                     tc_commit(empty_b((bq + (uint32_t)y) % kNB));          // operand row y - pad is not needed again
-                    if (y == p.H - 1)
+                    if (y == rows - 1)
                         for (int e = 1; e <= 2 * p.pad; ++e) tc_commit(empty_b((bq + (uint32_t)(y + e)) % kNB));
                 }
                 __syncwarp();
                 first = false;
                 ++a_seq;
             }
-            bq += (uint32_t)rows_b;
+            bq += (uint32_t)(rows + 2 * p.pad);
         }
         if (elect_one()) tc_commit(tfull);
         __syncwarp();
@@ -365,7 +368,7 @@ extern "C" int nrrt_conv_wgrad(const void* dy_cm, int cout, const void* x_cm, in
     NRRT_REQUIRE(((uintptr_t)dy_cm & 15) == 0 && ((uintptr_t)x_cm & 15) == 0, "operands must be 16-byte aligned");
     const int block_n = (cin % 128 == 0 || cin > 192) ? 128 : 64;
     WgradParams p;
-    p.H = h; p.xblocks = w / 64; p.strips = n * p.xblocks;
+    p.H = h; p.xblocks = w / 64;
     p.co = cout; p.ci = cin;
     p.nky = ksize; p.nkx = ksize; p.pad = ksize / 2;
     p.co_blocks = (cout + 127) / 128; p.ci_blocks = (cin + block_n - 1) / block_n;
@@ -378,11 +381,16 @@ extern "C" int nrrt_conv_wgrad(const void* dy_cm, int cout, const void* x_cm, in
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
     NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int tiles = p.co_blocks * p.ci_blocks * p.nkx;
-    int splits = (2 * sms + tiles - 1) / tiles;          // about two waves of CTAs
+    // K split: columns of 64 pixels, cut into row segments (>= 16 rows: a segment re-reads 2 * pad halo rows) until there are
+    // about two waves of CTAs; a CTA accumulates its work units in tensor memory and adds the result once
+    int seg_rows = h;
+    while (seg_rows > 16 && (long long)tiles * n * p.xblocks * ((h + seg_rows - 1) / seg_rows) < 2LL * sms) seg_rows = (seg_rows + 1) / 2;
+    p.seg_rows = seg_rows; p.segs = (h + seg_rows - 1) / seg_rows;
+    p.strips = n * p.xblocks * p.segs;
+    int splits = (2 * sms + tiles - 1) / tiles;
     if (splits > p.strips) splits = p.strips;
     if (splits < 1) splits = 1;
     p.splits = splits;
-    // every split must own at least one strip (a CTA without strips would add uninitialised accumulators: it skips instead)
     CUtensorMap ma, mb;
     if (int rc = make_cm_map(&ma, dy_cm, cout, n, h, w, 128, 0)) return rc;
     if (int rc = make_cm_map(&mb, x_cm, cin, n, h, w, block_n, ksize)) return rc;
