@@ -269,6 +269,69 @@ class Arm(object):
         return self.gp.stage_ms()
 
 
+def train_section(args, dev, rank, world, pk, sync_all, max_over_ranks):
+    """UNet_cooler.training_step + Adam (train.py:205-234) on the B200 kernels, batch_size 3 per GPU (the
+    reference's MapsDataModule default, train.py:73) at 512 x 512, synthetic maps / masks.  N > 1: data parallel, one
+    all-reduce of the flat gradient buffer per step (NCCL), weak scaling."""
+    from mgr_sampling_cnn_b200 import _lib, train, trainer
+    torch.manual_seed(0)
+    model = train.UNet_cooler()
+    B, S = 3, 512
+    tr = trainer.UNetTrainer(model, B, S, S, dev)
+    rng = np.random.default_rng(100 + rank)
+    x = torch.from_numpy((rng.random((B, 1, S, S)) > 0.2).astype(np.float32)).repeat(1, 3, 1, 1).to(dev)
+    y = torch.from_numpy(rng.random((B, 1, S, S)).astype(np.float32)).to(dev)
+    coords = torch.from_numpy(rng.integers(0, S, (B, 1, 2, 2)).astype(np.float32)).to(dev)
+    for _ in range(2):
+        tr.training_step((x, y, coords))
+    sync_all()
+    steps = max(args.section_steps, 2) * 5
+    n0 = _lib.launches
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        loss = tr.training_step((x, y, coords))
+    b.record()
+    sync_all()
+    ms = max_over_ranks(a.elapsed_time(b)) / steps
+    # the weight-gradient kernel alone on the largest layer (conv8[0]: 192 -> 128 channels at 512 x 512, train.py:157)
+    cv = tr.convs["c8.0"]
+    g_cm = tr._cm("g_cm", tr._buf("dx_c8.2", (B, S, S, 128)), 0, 128, 0)
+    x_cm = tr._cm("x_cm", tr.cat8, 0, 192, 0, copies=3)
+    tr._wgrad(cv, g_cm, x_cm, (S, S))
+    torch.cuda.synchronize(dev)
+    a.record()
+    for _ in range(5):
+        tr._wgrad(cv, g_cm, x_cm, (S, S))
+    b.record()
+    torch.cuda.synchronize(dev)
+    wg_ms = a.elapsed_time(b) / 5
+    wg_flops = 2.0 * B * S * S * 128 * 192 * 9
+    sec = {"workload": "UNet_cooler training step (forward in train mode, BCEWithLogits, backward, Adam), batch %d per GPU at %dx%d, synthetic" % (B, S, S),
+           "scaling": "weak (data parallel: one NCCL all-reduce of the %d-float gradient buffer per step)" % tr.n_params if world > 1 else "weak",
+           "steps": steps, "warmup": 2, "ms_per_step": ms, "value": world * B / (ms / 1e3), "unit": "samples/s",
+           "flops_per_step_algorithmic": tr.flops_per_step(), "tflops_algorithmic": world * tr.flops_per_step() / ms / 1e9,
+           "launches_per_step": (_lib.launches - n0) // steps, "loss_last": float(loss.item()),
+           "dtype": "f16 tensor-core operands, f32 accumulate / parameters / optimizer state",
+           "kernels": {"wgrad_kernel": {"bound": "tensor", "layer": "conv8[0] weight gradient, 192 -> 128 channels, K = %d pixels" % (B * S * S),
+                                        "ms": wg_ms, "achieved": wg_flops / wg_ms / 1e9, "peak": pk["tensor"], "unit": "TFLOP/s",
+                                        "frac": wg_flops / wg_ms / 1e9 / pk["tensor"]}}}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:   # the oracle's torch fp32 step on the host cores, once (kind "port": the reference's Lightning loop cannot travel)
+            from oracle import train_oracle
+            sd = {k: v.clone() for k, v in model.state_dict().items()}
+            t0 = time.time()
+            train_oracle.forward_backward(sd, x[:2].cpu(), y[:2].cpu(), coords[:2].cpu())
+            dt = time.time() - t0
+            sec["cpu_baseline"] = {"value": 2 / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": "one forward + backward of 2 samples (oracle/train_oracle.py, torch fp32 CPU)"}
+        except Exception as exc:
+            sec["cpu_baseline"] = {"error": repr(exc)}
+    del tr
+    torch.cuda.empty_cache()
+    return sec
+
+
 def run_graft(args):
     import torch.distributed as dist
     from mgr_sampling_cnn_b200 import _lib, sharding
@@ -439,6 +502,7 @@ def run_graft(args):
             sections[key] = sec
             del sarm
             torch.cuda.empty_cache()
+        sections["train_step"] = train_section(args, dev, rank, world, pk, sync_all, max_over_ranks)
         sections["3d_sweep"]["note"] = (f"BASELINE configs[4] is 65536 tasks; the sweep here is {args.sweep_tasks} tasks of the same generator "
                                         "(fixed total, contiguous shards via sharding.shard_indices, records gathered with "
                                         "sharding.gather_records) so that every N fits the bench budget; --sweep-tasks 65536 runs it whole")

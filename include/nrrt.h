@@ -403,6 +403,15 @@ int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per_map, const
                     const int32_t* goals, int B, int s0, int s1, int s2, int axis_only, void* work, int n_slots, int32_t* queue,
                     int32_t* n_steps, double* length, void* stream);
 
+/* Same search, also returning ONE shortest path per task (what astar() returns to generate_paths(), the input of the mask
+ * makers): paths int32 [B][path_cap][dims] from start to goal in array-axis order, path_n [B] = points on it (0 = no path,
+ * -(points) = longer than path_cap).  The path is read off the final labels (predecessor = lowest legal neighbour whose step
+ * counts are one move smaller); among equal-cost paths the reference's A* returns whichever its heap order meets first, so
+ * length and step kinds agree with it, the individual cells may not. */
+int nrrt_grid_paths_ex(int dims, const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map, const int32_t* starts,
+                       const int32_t* goals, int B, int s0, int s1, int s2, int axis_only, void* work, int n_slots, int32_t* queue,
+                       int32_t* n_steps, double* length, int32_t* paths, int path_cap, int32_t* path_n, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * On-device workload generation (csrc/generate.cu): the reference's generators with CPython's `random` (MT19937,
  * random.seed(int), randint) reproduced bit for bit -- seed s here gives the map / the tasks `random.seed(s)` gives there.
@@ -499,19 +508,28 @@ int nrrt_bn_train_backward(const void* dy, int64_t dy_cs, const void* y_mask, in
  * pixel (2y + a, 2x + b)); mode 1 = zero-stuffing, in [n][h][w][c] -> out [n][2h][2w][c] dense. */
 int nrrt_remap_channels_last(const void* in, int64_t in_cs, void* out, int64_t out_cs, int n, int h, int w, int c, int mode, void* stream);
 /* nn.BCEWithLogitsLoss: *loss_sum = sum of the per-element losses (divide by count for the mean, train.py:113,208);
- * dlogits (optional) = (sigmoid(z) - t) * grad_scale.  logit_bias (optional, one device float: final_conv's bias, which
+ * dlogits (optional) = (sigmoid(z) - t) * grad_scale (or * scale_state[0] when scale_state, the device-resident dynamic loss
+ * scale below, is given).  logit_bias (optional, one device float: final_conv's bias, which
  * lives in the device-resident parameter buffer) is added to logits in place first. */
-int nrrt_bce_with_logits(float* logits, const float* logit_bias, const float* target, int64_t count, float grad_scale, float* dlogits,
-                         double* loss_sum, void* stream);
+int nrrt_bce_with_logits(float* logits, const float* logit_bias, const float* target, int64_t count, float grad_scale,
+                         const float* scale_state, float* dlogits, double* loss_sum, void* stream);
 /* MapsDataset's mask normalisation (train.py:47-50): target = (mask - min) / (max - min) per sample, float64 then float32. */
 int nrrt_mask_targets(const uint8_t* masks, int B, int64_t cells, float* target, void* stream);
 /* final_conv (1x1, c -> 1) backward: g = x > 0 ? dlogits * weight[k] : 0 (x = the ReLU output feeding the head);
  * dweight[k] += sum dlogits * x; *dbias += sum dlogits. */
 int nrrt_head_backward(const float* dlogits, const void* x, int64_t x_cs, const float* weight, int64_t pixels, int c, void* g, int64_t g_cs,
                        float* dweight, float* dbias, void* stream);
-/* torch.optim.Adam (no weight decay / amsgrad) on a flat fp32 buffer; the gradient is multiplied by grad_scale first. */
+/* torch.optim.Adam (no weight decay / amsgrad) on a flat fp32 buffer; the gradient is multiplied by grad_scale first.
+ * Dynamic loss scaling without host synchronisation (activation gradients are fp16): scale_state = 4 device floats
+ * [scale carried by the gradients, good steps in a row, overflow flag, optimizer steps taken].  nrrt_grad_check raises the
+ * flag when a gradient is not finite; nrrt_adam_step with scale_state skips the step when the flag is up, divides the
+ * gradients by scale_state[0] (on top of grad_scale) and takes its bias corrections from scale_state[3] + 1 (`step` is
+ * then ignored); nrrt_loss_scale_update halves the scale after an overflow (not below min_scale), else counts the step and
+ * doubles the scale after growth_interval good steps (not above max_scale), and clears the flag. */
 int nrrt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, int step, float lr, float beta1,
-                   float beta2, float eps, float grad_scale, void* stream);
+                   float beta2, float eps, float grad_scale, const float* scale_state, void* stream);
+int nrrt_grad_check(const float* grad, int64_t count, float* scale_state, void* stream);
+int nrrt_loss_scale_update(float* scale_state, int growth_interval, float max_scale, float min_scale, void* stream);
 int nrrt_to_half(const float* src, void* dst, int64_t count, void* stream);
 /* Data-gradient weights: dst fp16 [ci_rows][taps][co_cols], dst[ci][taps - 1 - t][co] = w[co][t][ci] (w fp32
  * [cout][taps][ci_stride]); rows / columns beyond the source are zero. */

@@ -58,6 +58,9 @@ struct GridPathArgs {
     int axis_only;             // 1: axis moves only (4- / 6-connected reachability); 0: the reference's A* moves
     int32_t* n_steps;          // [B][3]: steps of cost 1, sqrt(2), sqrt(3); -1 = no path
     double* length;            // [B], NaN = no path
+    int32_t* paths;            // optional [B][path_cap][DIM]: one shortest path, start -> goal, array-axis order
+    int32_t* path_n;           // optional [B]: points on it (steps + 1), 0 = no path, -(steps + 1) = longer than path_cap
+    int path_cap;
 };
 
 template <int DIM>
@@ -167,6 +170,64 @@ __global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel
             __syncthreads();
             if (s_state) break;
         }
+        // one shortest path by backtracking the final labels (warp 0; lane = neighbour): the predecessor of a cell with step
+        // counts (n1, n2, n3) is a neighbour whose counts are one step of the move's kind smaller and from which the move is
+        // legal.  Labels at or below the goal's are final.  Among equal-cost paths the reference's A* returns the one its
+        // heap order finds (generate_paths.py:11-74); this one takes the lowest neighbour index -- same length, same kinds.
+        if (a.paths && tid < 32 && s_state == 1) {
+            const unsigned long long gk = __ldcg(dist + g);
+            unsigned n1, n2, n3;
+            key_counts<DIM>(gk, n1, n2, n3);
+            const int steps = (int)(n1 + n2 + n3);
+            int32_t* out = a.paths + (size_t)task * a.path_cap * DIM;
+            if (steps + 1 > a.path_cap) {
+                if (tid == 0) a.path_n[task] = -(steps + 1);
+            } else {
+                if (tid == 0) a.path_n[task] = steps + 1;
+                int u = g;
+                const int st1 = DIM == 2 ? 1 : a.S2;
+                for (int i = steps; i >= 0; --i) {
+                    const int c0 = u / S12, r = u - c0 * S12;
+                    const int c1 = DIM == 2 ? r : r / a.S2, c2 = DIM == 2 ? 0 : r - c1 * a.S2;
+                    if (tid == 0) {
+                        out[i * DIM] = c0; out[i * DIM + 1] = c1;
+                        if (DIM == 3) out[i * DIM + 2] = c2;
+                    }
+                    if (i == 0) break;
+                    key_counts<DIM>(__ldcg(dist + u), n1, n2, n3);
+                    bool ok = false;
+                    int v = 0;
+                    if (tid < (DIM == 2 ? 9 : 27)) {
+                        const int d0 = tid / (DIM == 2 ? 3 : 9) - 1, d1 = (tid / (DIM == 2 ? 1 : 3)) % 3 - 1, d2 = DIM == 2 ? 0 : tid % 3 - 1;
+                        const int nz = (d0 != 0) + (d1 != 0) + (d2 != 0);
+                        const int e0 = c0 - d0, e1 = c1 - d1, e2 = c2 - d2;          // candidate predecessor: it moved by (d0, d1, d2)
+                        if (nz != 0 && !(a.axis_only && nz != 1) && e0 >= 0 && e0 < a.S0 && e1 >= 0 && e1 < a.S1 && e2 >= 0 && e2 < a.S2) {
+                            v = e0 * S12 + e1 * st1 + e2;
+                            bool legal = is_free(v);
+                            if (DIM == 2) legal = legal && (nz != 2 || (is_free(c0 * S12 + e1) && is_free(e0 * S12 + c1)));
+                            else legal = legal && is_free(c0 * S12 + e1 * st1 + e2) && is_free(e0 * S12 + c1 * st1 + e2) &&
+                                         is_free(e0 * S12 + e1 * st1 + c2);       // the move's projected cells, seen from the predecessor
+                            if (legal) {
+                                const unsigned long long vk = __ldcg(dist + v);
+                                if (vk != kInf) {
+                                    unsigned m1, m2, m3;
+                                    key_counts<DIM>(vk, m1, m2, m3);
+                                    ok = m1 + (nz == 1) == n1 && m2 + (nz == 2) == n2 && m3 + (nz == 3) == n3;
+                                }
+                            }
+                        }
+                    }
+                    const unsigned vote = __ballot_sync(0xffffffffu, ok);
+                    if (vote == 0) {             // cannot happen for a final label; never loop on a broken chain
+                        if (tid == 0) a.path_n[task] = 0;
+                        break;
+                    }
+                    u = __shfl_sync(0xffffffffu, v, __ffs(vote) - 1);
+                }
+            }
+        } else if (a.paths && tid == 0 && s_state != 1) {
+            a.path_n[task] = 0;
+        }
         if (tid == 0) {
             const unsigned long long gk = __ldcg(dist + g);
             if (s_state == 1 && gk != kInf) {
@@ -184,9 +245,23 @@ __global__ void __launch_bounds__(GP<DIM>::NT, GP<DIM>::PER_SM) grid_path_kernel
 
 }  // namespace
 
+extern "C" int nrrt_grid_paths_ex(int dims, const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map,
+                                  const int32_t* starts, const int32_t* goals, int B, int s0, int s1, int s2, int axis_only,
+                                  void* work, int n_slots, int32_t* queue, int32_t* n_steps, double* length, int32_t* paths,
+                                  int path_cap, int32_t* path_n, void* stream);
+
 extern "C" int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map,
                                const int32_t* starts, const int32_t* goals, int B, int s0, int s1, int s2, int axis_only,
                                void* work, int n_slots, int32_t* queue, int32_t* n_steps, double* length, void* stream) {
+    return nrrt_grid_paths_ex(dims, occ_bits, words_per_map, task_to_map, starts, goals, B, s0, s1, s2, axis_only, work, n_slots, queue,
+                              n_steps, length, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int nrrt_grid_paths_ex(int dims, const uint32_t* occ_bits, int words_per_map, const int32_t* task_to_map,
+                                  const int32_t* starts, const int32_t* goals, int B, int s0, int s1, int s2, int axis_only,
+                                  void* work, int n_slots, int32_t* queue, int32_t* n_steps, double* length, int32_t* paths,
+                                  int path_cap, int32_t* path_n, void* stream) {
+    NRRT_REQUIRE((paths == nullptr) == (path_n == nullptr) && (paths == nullptr || path_cap >= 1), "paths, path_n and path_cap go together");
     NRRT_REQUIRE(occ_bits && task_to_map && starts && goals && work && queue && n_steps && length, "null pointer");
     NRRT_REQUIRE(dims == 2 || dims == 3, "dims must be 2 or 3");
     if (dims == 2) s2 = 1;
@@ -201,6 +276,7 @@ extern "C" int nrrt_grid_paths(int dims, const uint32_t* occ_bits, int words_per
     a.occ_bits = occ_bits; a.words_per_map = words_per_map; a.task_to_map = task_to_map; a.starts = starts; a.goals = goals;
     a.B = B; a.S0 = s0; a.S1 = s1; a.S2 = s2; a.axis_only = axis_only ? 1 : 0; a.work = (unsigned long long*)work; a.queue = queue;
     a.n_steps = n_steps; a.length = length;
+    a.paths = paths; a.path_n = path_n; a.path_cap = path_cap;
     const int grid = n_slots < B ? n_slots : B;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (dims == 2) {

@@ -231,8 +231,9 @@ __global__ void __launch_bounds__(kEw) remap_kernel(const __half* in, long long 
 
 // nn.BCEWithLogitsLoss (mean): loss_sum += sum max(z, 0) - z t + log1p(exp(-|z|)); dlogits = (sigmoid(z) - t) * grad_scale
 __global__ void __launch_bounds__(256) bce_kernel(float* logits, const float* logit_bias, const float* target, float* dlogits,
-                                                  double* loss_sum, float grad_scale, long long M) {
+                                                  double* loss_sum, float grad_scale, const float* scale_state, long long M) {
     double local = 0.0;
+    if (scale_state) grad_scale = scale_state[0];
     const float zb = logit_bias ? *logit_bias : 0.f;
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < M; i += (long long)gridDim.x * 256) {
         const float z = logits[i] + zb, t = target[i];
@@ -305,7 +306,14 @@ __global__ void __launch_bounds__(kEw) head_bwd_kernel(const float* dl, const __
 
 // torch.optim.Adam (no weight decay, no amsgrad): one flat fp32 parameter buffer
 __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2,
-                                                   float eps, float bc1, float bc2_sqrt, float grad_scale) {
+                                                   float eps, float bc1, float bc2_sqrt, float grad_scale, const float* scale_state) {
+    if (scale_state) {   // dynamic loss scaling: [0] = the scale the gradients carry, [1] = good steps, [2] = overflow flag, [3] = steps taken
+        if (scale_state[2] != 0.f) return;                       // a non-finite gradient: the step is skipped (nrrt_loss_scale_update backs off)
+        grad_scale /= scale_state[0];
+        const float t = scale_state[3] + 1.f;
+        bc1 = 1.f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    }
     for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
         const float gi = g[i] * grad_scale;
         const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -549,12 +557,12 @@ extern "C" int nrrt_remap_channels_last(const void* in, int64_t in_cs, void* out
 }
 
 extern "C" int nrrt_bce_with_logits(float* logits, const float* logit_bias, const float* target, int64_t count, float grad_scale,
-                                    float* dlogits, double* loss_sum, void* stream) {
+                                    const float* scale_state, float* dlogits, double* loss_sum, void* stream) {
     NRRT_REQUIRE(logits && target && loss_sum && count >= 1, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     NRRT_CUDA_TRY(cudaMemsetAsync(loss_sum, 0, sizeof(double), st));
     const long long blocks = (count + 255) / 256;
-    bce_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(logits, logit_bias, target, dlogits, loss_sum, grad_scale, count);
+    bce_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(logits, logit_bias, target, dlogits, loss_sum, grad_scale, scale_state, count);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }
@@ -576,13 +584,42 @@ extern "C" int nrrt_head_backward(const float* dlogits, const void* x, int64_t x
     return NRRT_OK;
 }
 
+namespace {
+__global__ void __launch_bounds__(256) grad_check_kernel(const float* g, long long n, float* scale_state) {
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) bad |= !isfinite(g[i]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) scale_state[2] = 1.f;
+}
+__global__ void scale_update_kernel(float* st, float growth_interval, float max_scale, float min_scale) {
+    if (st[2] != 0.f) { st[0] = fmaxf(st[0] * 0.5f, min_scale); st[1] = 0.f; st[2] = 0.f; return; }
+    st[3] += 1.f;
+    st[1] += 1.f;
+    if (st[1] >= growth_interval) { st[0] = fminf(st[0] * 2.f, max_scale); st[1] = 0.f; }
+}
+}  // namespace
+
+extern "C" int nrrt_grad_check(const float* grad, int64_t count, float* scale_state, void* stream) {
+    NRRT_REQUIRE(grad && scale_state && count >= 1, "bad arguments");
+    const long long blocks = (count + 255) / 256;
+    grad_check_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(grad, count, scale_state);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_loss_scale_update(float* scale_state, int growth_interval, float max_scale, float min_scale, void* stream) {
+    NRRT_REQUIRE(scale_state && growth_interval >= 1 && max_scale >= min_scale && min_scale > 0, "bad arguments");
+    scale_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(scale_state, (float)growth_interval, max_scale, min_scale);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
 extern "C" int nrrt_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t count, int step, float lr,
-                              float beta1, float beta2, float eps, float grad_scale, void* stream) {
+                              float beta1, float beta2, float eps, float grad_scale, const float* scale_state, void* stream) {
     NRRT_REQUIRE(param && grad && exp_avg && exp_avg_sq && count >= 1 && step >= 1, "bad arguments");
     const double bc1 = 1.0 - pow((double)beta1, step), bc2 = 1.0 - pow((double)beta2, step);
     const long long blocks = (count + 255) / 256;
     adam_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, count, lr, beta1,
-                                                                                              beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+                                                                                              beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale, scale_state);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

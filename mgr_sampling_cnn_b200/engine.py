@@ -246,8 +246,16 @@ def plan_batch(occ_bits: torch.Tensor, task_to_map, starts, goals, *, dim: int, 
                       n_draws=v(buf.n_draws) if samples is None else None, trace=v(buf.trace), trace_n=v(buf.trace_n))
 
 
+def grid_paths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape: Sequence[int], path_cap: int = 2048,
+               n_slots: Optional[int] = None):
+    """generate_paths.astar / ThreeD_generate_paths.astar for a batch: (length [B], n_steps [B, 3], paths int32 [B, path_cap, dim]
+    start -> goal in array-axis order, path_n [B]) on the device -- one shortest path per task (the mask makers' input; see
+    nrrt_grid_paths_ex in include/nrrt.h for how ties between equal-cost paths are broken)."""
+    return grid_path_lengths(occ_bits, task_to_map, starts, goals, shape, n_slots=n_slots, path_cap=path_cap)
+
+
 def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape: Sequence[int], n_slots: Optional[int] = None,
-                      axis_only: bool = False):
+                      axis_only: bool = False, path_cap: int = 0):
     """Shortest grid path of every task = the reference's A* (generate_paths.py:11-74, ThreeD_generate_paths.py:14-97): its
     path length column (test_network_and_algorithms.py:58-70) and its task filter (no path -> the task is deleted,
     generate_paths.py:111-113).  occ_bits from pack_occupancy; starts / goals [B, dim] in array-axis order ((y, x) / (x, y, z)).
@@ -274,6 +282,13 @@ def grid_path_lengths(occ_bits: torch.Tensor, task_to_map, starts, goals, shape:
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     _lib.count_launch()
     s = [int(v) for v in shape] + [1]
+    if path_cap > 0:
+        paths = torch.zeros((B, path_cap, dim), dtype=torch.int32, device=dev)
+        path_n = torch.zeros(B, dtype=torch.int32, device=dev)
+        check(lib.nrrt_grid_paths_ex(dim, _ptr(occ_bits), occ_bits.shape[1], _ptr(t2m), _ptr(st), _ptr(gl), B, s[0], s[1], s[2],
+                                     1 if axis_only else 0, _ptr(work), work.shape[0], _ptr(queue), _ptr(steps), _ptr(length),
+                                     _ptr(paths), path_cap, _ptr(path_n), stream))
+        return length, steps, paths, path_n
     check(lib.nrrt_grid_paths(dim, _ptr(occ_bits), occ_bits.shape[1], _ptr(t2m), _ptr(st), _ptr(gl), B, s[0], s[1], s[2],
                               1 if axis_only else 0, _ptr(work), work.shape[0], _ptr(queue), _ptr(steps), _ptr(length), stream))
     return length, steps

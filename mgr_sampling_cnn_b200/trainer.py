@@ -42,7 +42,7 @@ class _Conv(object):
 
 class UNetTrainer(object):
     def __init__(self, model, batch: int, height: int, width: int, device="cuda:0", lr: float = 1e-3, betas=(0.9, 0.999),
-                 eps: float = 1e-8, loss_scale: float = None):
+                 eps: float = 1e-8, loss_scale: float = None, data_parallel: bool = None):
         if not torch.cuda.is_available():
             raise _lib.NrrtError("UNetTrainer needs a CUDA device (sm_100a); there is no CPU fallback")
         if height % 512 or width % 512:
@@ -53,9 +53,19 @@ class UNetTrainer(object):
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.step_count = 0
         self.M = self.B * self.H * self.W
-        # gradients are those of loss * loss_scale (activation gradients are fp16): 128 x the sum-loss keeps the deepest encoder
-        # gradients out of the fp16 subnormals and the largest activation gradient (first block's input, ~3e2) far below 65504
+        # Activation gradients are fp16, so the loss is scaled: dlogits = (sigmoid - t) * g.  g lives on the device
+        # (self.scale_state[0]) and adapts like torch.cuda.amp.GradScaler without a host round trip: a step whose gradients are
+        # not finite is skipped and halves g, 200 good steps double it.  g = 128 keeps the deepest encoder gradients out of the
+        # fp16 subnormals at initialisation.  A fixed `loss_scale` (in units of the mean loss: g = loss_scale / M) turns it off.
+        self.dynamic_scale = loss_scale is None
         self.loss_scale = float(128.0 * self.M if loss_scale is None else loss_scale)
+        self.scale_state = torch.tensor([self.loss_scale / self.M, 0.0, 0.0, 0.0], dtype=torch.float32, device=self.dev)
+        # data parallel: one process per GPU (torch.distributed, NCCL), each rank steps on its own `batch` samples; the flat
+        # gradient buffer is summed across ranks with ONE all-reduce before Adam (the loss is the mean over the global batch,
+        # BatchNorm statistics stay per rank like torch DDP's default)
+        import torch.distributed as dist
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.dp = (self.world > 1) if data_parallel is None else bool(data_parallel and self.world > 1)
         self.model = model
         self._tmp = {}
         self._sched_best, self._sched_bad = math.inf, 0
@@ -489,13 +499,26 @@ class UNetTrainer(object):
     def loss_and_grad(self, with_grad=True):
         _lib.count_launch()
         check(self.lib.nrrt_bce_with_logits(_pp(self.logits), _pp(self.params, self.head_b), _pp(self.target), self.M,
-                                            self.loss_scale / self.M, _pp(self.dlogits) if with_grad else None, _pp(self.loss_sum), self._st()))
+                                            self.loss_scale / self.M, _pp(self.scale_state) if self.dynamic_scale else None,
+                                            _pp(self.dlogits) if with_grad else None, _pp(self.loss_sum), self._st()))
 
     def optimizer_step(self):
         self.step_count += 1
-        _lib.count_launch()
-        check(self.lib.nrrt_adam_step(_pp(self.params), _pp(self.grads), _pp(self.exp_avg), _pp(self.exp_avg_sq), self.n_params, self.step_count,
-                                      self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / self.loss_scale, self._st()))
+        if self.dp:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads)          # a non-finite gradient on any rank shows up on all of them: the skip is collective
+        st = self._st()
+        if self.dynamic_scale:
+            _lib.count_launch(3)
+            check(self.lib.nrrt_grad_check(_pp(self.grads), self.n_params, _pp(self.scale_state), st))
+            check(self.lib.nrrt_adam_step(_pp(self.params), _pp(self.grads), _pp(self.exp_avg), _pp(self.exp_avg_sq), self.n_params, 1,
+                                          self.lr, self.betas[0], self.betas[1], self.eps, 1.0 / (self.M * self.world), _pp(self.scale_state), st))
+            check(self.lib.nrrt_loss_scale_update(_pp(self.scale_state), 200, 65536.0, 2.0 ** -14, st))
+        else:
+            _lib.count_launch()
+            check(self.lib.nrrt_adam_step(_pp(self.params), _pp(self.grads), _pp(self.exp_avg), _pp(self.exp_avg_sq), self.n_params,
+                                          self.step_count, self.lr, self.betas[0], self.betas[1], self.eps,
+                                          1.0 / (self.loss_scale * self.world), None, st))
         self._refresh_weights()
 
     def training_step(self, batch, batch_idx=0, masks_u8=None):

@@ -142,3 +142,54 @@ def test_long_paths_and_the_cost_limit(cuda_device):
             assert abs(float(length[0]) - (expect[0] + expect[1] * np.sqrt(2))) <= 1e-9 * float(length[0])
         else:
             assert np.isposinf(float(length[0]))
+
+
+def _legal_path(occ, path, dim):
+    """Every cell free and every move one the reference's A* may make (generate_paths.py:40-62, ThreeD_generate_paths.py:44-76)."""
+    free = (occ != 0) if dim == 2 else (occ == 0)
+    for p in path:
+        if not free[tuple(p)]:
+            return False
+    for a, b in zip(path[:-1], path[1:]):
+        d = b - a
+        if np.abs(d).max() != 1:
+            return False
+        if dim == 2:
+            if np.abs(d).sum() == 2 and not (free[a[0] + d[0], a[1]] and free[a[0], a[1] + d[1]]):
+                return False
+        else:
+            if not (free[b[0], a[1], a[2]] and free[a[0], b[1], a[2]] and free[a[0], a[1], b[2]]):
+                return False
+    return True
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_extracted_paths_are_shortest_paths(dim, cuda_device):
+    """nrrt_grid_paths_ex: the returned cells form a legal start -> goal path with exactly the reference path's step kinds."""
+    g = H.load(f"astar{dim}d")
+    by_shape = {}
+    for i in range(int(g["n_cases"])):
+        by_shape.setdefault(g[f"occ_{i}"].shape, []).append(i)
+    for shape, idx in by_shape.items():
+        maps = np.stack([g[f"occ_{i}"] for i in idx])
+        bits = engine.pack_occupancy(maps, dim, cuda_device)
+        starts = np.stack([g[f"start_{i}"] for i in idx])
+        goals = np.stack([g[f"goal_{i}"] for i in idx])
+        length, steps, paths, path_n = [t.cpu().numpy() for t in
+                                        engine.grid_paths(bits, np.arange(len(idx), dtype=np.int32), starts, goals, shape, path_cap=1024)]
+        for j, i in enumerate(idx):
+            ref = g[f"path_{i}"]
+            if not bool(g[f"reached_{i}"]):
+                assert path_n[j] == 0
+                continue
+            assert path_n[j] == len(ref), f"case {i}"
+            p = paths[j, :path_n[j]].astype(np.int64)
+            assert np.array_equal(p[0], starts[j]) and np.array_equal(p[-1], goals[j])
+            assert _legal_path(maps[j], p, dim), f"case {i}"
+            kind = np.abs(np.diff(p, axis=0)).sum(axis=1)
+            assert [int((kind == k).sum()) for k in (1, 2, 3)] == steps[j].tolist()
+    # a cap that is too small is reported, not overrun
+    wl = workload.make_2d(10, filter_unreachable=True)
+    bits = engine.pack_occupancy(wl.occ_maps, 2, cuda_device)
+    _, st, paths, pn = [t.cpu().numpy() for t in engine.grid_paths(bits, wl.task_to_map, wl.starts, wl.goals, wl.shape, path_cap=8)]
+    assert (pn == -(st.sum(1) + 1)).all() and not paths.any()

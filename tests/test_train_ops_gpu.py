@@ -113,7 +113,7 @@ def test_bce_head_adam_and_small_ops():
     tref = torch.from_numpy(np.stack([(m - m.min()) / (m.max() - m.min()) for m in mn])).float()
     assert torch.equal(t.cpu(), tref)
     dl, loss = torch.empty(M, device=DEV), torch.zeros(1, dtype=torch.float64, device=DEV)
-    check(lib.nrrt_bce_with_logits(_p(z), None, _p(t), M, 1.0, _p(dl), _p(loss), _st()))
+    check(lib.nrrt_bce_with_logits(_p(z), None, _p(t), M, 1.0, None, _p(dl), _p(loss), _st()))
     zr = z.cpu().clone().requires_grad_(True)
     lref = F.binary_cross_entropy_with_logits(zr, tref.reshape(-1), reduction="sum")
     lref.backward()
@@ -141,9 +141,20 @@ def test_bce_head_adam_and_small_ops():
     pd, m, v = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
     for s, gg in enumerate((g1, g2), 1):
         gd = (gg * 4).to(DEV)
-        check(lib.nrrt_adam_step(_p(pd), _p(gd), _p(m), _p(v), n, s, 1e-3, 0.9, 0.999, 1e-8, 0.25, _st()))
+        check(lib.nrrt_adam_step(_p(pd), _p(gd), _p(m), _p(v), n, s, 1e-3, 0.9, 0.999, 1e-8, 0.25, None, _st()))
         torch.cuda.synchronize()
     assert (pd.cpu() - pr.detach()).abs().max() < 1e-6
+    # the same two steps under the device-resident dynamic loss scale, with an overflowing step in between that must be skipped
+    pd2, m2, v2 = p0.to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    state = torch.tensor([8.0, 0.0, 0.0, 0.0], device=DEV)
+    bad = (g1 * 8).to(DEV); bad[17] = float("inf")
+    for gg in ((g1 * 8).to(DEV), bad, (g2 * 4).to(DEV)):
+        check(lib.nrrt_grad_check(_p(gg), n, _p(state), _st()))
+        check(lib.nrrt_adam_step(_p(pd2), _p(gg), _p(m2), _p(v2), n, 1, 1e-3, 0.9, 0.999, 1e-8, 1.0, _p(state), _st()))
+        check(lib.nrrt_loss_scale_update(_p(state), 1000, 65536.0, 1.0, _st()))
+        torch.cuda.synchronize()
+    assert state.cpu().tolist() == [4.0, 1.0, 0.0, 2.0]           # halved once, two steps taken
+    assert (pd2.cpu() - pr.detach()).abs().max() < 1e-6
     # relu backward + bias sum, remaps, dgrad weight pack
     a, yv = torch.randn(3, 5, 7, 96).half().to(DEV), torch.randn(3, 5, 7, 96).half().to(DEV)
     gq, dbq = torch.empty_like(a), torch.zeros(96, device=DEV)
