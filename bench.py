@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--sweep-tasks", type=int, default=4096, help="total tasks of the strong-scaling 3D section")
     ap.add_argument("--micro-batch", type=int, default=None, help="tasks per decoder launch (default: GuidedPlanner's)")
     ap.add_argument("--encoder-batch", type=int, default=None, help="distinct maps per encoder pass (default: GuidedPlanner's)")
+    ap.add_argument("--train-steps", type=int, default=3000, help="optimisation steps of the trained_guidance section (0 = skip it)")
+    ap.add_argument("--train-maps", type=int, default=600, help="generated maps (x 10 tasks) of its training set")
     ap.add_argument("--layer-table", default=None, help="write the per-layer CUDA-event timings of the sampled launches (csv)")
     return ap.parse_args()
 
@@ -332,6 +334,47 @@ def train_section(args, dev, rank, world, pk, sync_all, max_over_ranks):
     return sec
 
 
+def trained_guidance_section(args, dev):
+    """What SURVEY 8 f3 is for: train UNet_cooler on the device (generated maps, tasks, A* paths, masks: maps 5000.. of the
+    generators, disjoint from the benchmark's maps 0..) and plan 1000 benchmark tasks with uniform sampling, random-init
+    guidance and trained guidance (same tasks, same sample streams).  N = 1 only."""
+    from mgr_sampling_cnn_b200 import engine, train, trainer, workload
+    S, n_eval = 512, 1000
+    wl = workload.make_on_device(2, n_eval, first_map=0, device=dev)
+    bits = engine.pack_occupancy(wl.occ_maps, 2, dev)
+
+    def stats(res, label):
+        st, it = res.status.cpu().numpy(), res.iterations.cpu().numpy()
+        pl = res.path_len.cpu().numpy()
+        return {"label": label, "solved_fraction": float((st == 0).mean()), "mean_iterations": float(it.mean()),
+                "median_iterations": float(np.median(it)), "mean_path_length_solved": float(pl[st == 0].mean()) if (st == 0).any() else None}
+
+    def guided(model, label):
+        planner = engine.GuidedPlanner(model.to(dev).eval(), 2, (S, S), max_iterations=5000)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        planner.plan(wl.occ_maps, wl.task_to_map, wl.starts, wl.goals, wl.coords, seed=7)
+        a.record()
+        res = planner.plan(wl.occ_maps, wl.task_to_map, wl.starts, wl.goals, wl.coords, seed=7)
+        b.record()
+        torch.cuda.synchronize(dev)
+        out = stats(res, label)
+        out["plans_per_s"] = n_eval / (a.elapsed_time(b) / 1e3)
+        return out
+
+    rows = [stats(engine.plan_batch(bits, wl.task_to_map, wl.starts, wl.goals, dim=2, shape=(S, S), max_iterations=5000, seed=7),
+                  "uniform sampling (rrt_star.py)")]
+    torch.manual_seed(0)
+    model = train.UNet_cooler()
+    rows.append(guided(model, "neural, random-init weights (BASELINE configs[1])"))
+    fit = trainer.fit_on_generated(model.cpu(), args.train_maps, args.train_steps, first_map=5000, device=dev)
+    rows.append(guided(model, "neural, trained %d steps on %d generated tasks" % (fit["steps"], fit["train_tasks"])))
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": "2D, %d benchmark tasks (maps 0..%d), 5000 iterations, neural_bias 0.75" % (n_eval, n_eval // 10 - 1),
+            "training": fit, "plans": rows,
+            "note": "training data and evaluation maps come from the reference's own generators (disjoint seeds); everything runs on the GPU"}
+
+
 def run_graft(args):
     import torch.distributed as dist
     from mgr_sampling_cnn_b200 import _lib, sharding
@@ -503,6 +546,8 @@ def run_graft(args):
             del sarm
             torch.cuda.empty_cache()
         sections["train_step"] = train_section(args, dev, rank, world, pk, sync_all, max_over_ranks)
+        if world == 1 and args.train_steps > 0:
+            sections["trained_guidance"] = trained_guidance_section(args, dev)
         sections["3d_sweep"]["note"] = (f"BASELINE configs[4] is 65536 tasks; the sweep here is {args.sweep_tasks} tasks of the same generator "
                                         "(fixed total, contiguous shards via sharding.shard_indices, records gathered with "
                                         "sharding.gather_records) so that every N fits the bench budget; --sweep-tasks 65536 runs it whole")

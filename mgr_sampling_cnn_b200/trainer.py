@@ -569,3 +569,52 @@ class UNetTrainer(object):
         if n.startswith("enc"):
             return int(n[3])
         return {"conv1.2": 0, "up6": 3, "c6.0": 2, "c6.2": 2, "up7": 2, "c7.0": 1, "c7.2": 1, "up8": 1, "c8.0": 0, "c8.2": 0}[n]
+
+
+def generated_training_set(n_maps: int, first_map: int = 5000, size: int = 512, device="cuda:0"):
+    """The reference's data pipeline for n_maps maps x 10 tasks, entirely on the device: generate_maps.create_map +
+    generate_tasks.draw_start_and_finish (csrc/generate.cu, the reference's `random` streams: map m is seed 1000 + m / 2000 + m),
+    generate_paths.astar (csrc/gridpath.cu: one shortest path per task) and generate_paths.visualize_path (csrc/masks.cu).
+    Returns (DeviceWorkload, masks uint8 [tasks, size, size])."""
+    from . import engine, generate_paths, workload
+    dev = torch.device(device)
+    wl = workload.make_on_device(2, n_maps * 10, first_map=first_map, size=size, device=dev)
+    bits = engine.pack_occupancy(wl.occ_maps, 2, dev)
+    _, _, paths, path_n = engine.grid_paths(bits, wl.task_to_map, wl.starts, wl.goals, (size, size), path_cap=4 * size)
+    masks = generate_paths.path_masks(wl.occ_maps, wl.task_to_map, paths, path_n, dev)
+    return wl, masks
+
+
+def fit_on_generated(model, n_maps: int, steps: int, first_map: int = 5000, batch: int = 3, size: int = 512, device="cuda:0", seed: int = 0,
+                     log=None):
+    """Train `model` (UNet_cooler) for `steps` optimisation steps of `batch` random samples of a generated training set; the
+    learning rate is halved at 60 % and 80 % of the run (the reference halves it on validation plateaus, train.py:230).  The
+    trained parameters and running statistics are written back into `model`.  Returns a dict of run statistics."""
+    import time
+    dev = torch.device(device)
+    t0 = time.time()
+    wl, masks = generated_training_set(n_maps, first_map, size, dev)
+    torch.cuda.synchronize(dev)
+    t_data = time.time() - t0
+    tr = UNetTrainer(model, batch, size, size, dev)
+    rng = np.random.default_rng(seed)
+    n = int(masks.shape[0])
+    run, curve = [], []
+    t0 = time.time()
+    for step in range(1, steps + 1):
+        tr.lr = 1e-3 if step <= 0.6 * steps else (5e-4 if step <= 0.8 * steps else 2.5e-4)
+        idx = torch.from_numpy(rng.choice(n, batch, replace=False)).to(dev)
+        occ = wl.occ_maps[wl.task_to_map[idx].long()]
+        x = (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()      # MapsDataset's image tensor (train.py:41-44)
+        run.append(tr.training_step((x, None, wl.coords[idx]), masks_u8=masks[idx]))
+        if step % 250 == 0 or step == steps:
+            curve.append((step, float(torch.stack(run).mean().item())))
+            run = []
+            if log:
+                log("step %d: mean loss %.4f, lr %g, loss scale %g" % (step, curve[-1][1], tr.lr, float(tr.scale_state[0].item())))
+    torch.cuda.synchronize(dev)
+    t_train = time.time() - t0
+    taken = int(tr.scale_state[3].item())
+    tr.export_to(model)
+    return {"train_tasks": n, "train_maps": n_maps, "steps": steps, "steps_taken": taken, "batch": batch, "data_seconds": t_data,
+            "train_seconds": t_train, "samples_per_s": steps * batch / t_train, "loss_curve": curve}

@@ -9,7 +9,7 @@ import numpy as np, torch
 from mgr_sampling_cnn_b200 import engine, generate_paths as gp, train, trainer, workload
 
 n_maps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
-epochs = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+n_steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
 n_eval = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
 dev = torch.device("cuda:0")
 B, S = 3, 512
@@ -43,25 +43,32 @@ print("training set: %d tasks on %d maps generated on the device in %.1f s" % (n
 wl_eval = workload.make_on_device(2, n_eval, first_map=0, device=dev)
 torch.manual_seed(0)
 model = train.UNet_cooler()
-results = [evaluate(model.to(dev).eval(), wl_eval, "random-init weights")]
+bits_eval = engine.pack_occupancy(wl_eval.occ_maps, 2, dev)
+ru = engine.plan_batch(bits_eval, wl_eval.task_to_map, wl_eval.starts, wl_eval.goals, dim=2, shape=(S, S), max_iterations=5000, goal_threshold=5.0,
+                       seed=7)
+torch.cuda.synchronize()
+su, iu = ru.status.cpu().numpy(), ru.iterations.cpu().numpy()
+results = [{"label": "uniform sampling (rrt_star.py)", "solved_fraction": float((su == 0).mean()), "mean_iterations": float(iu.mean()),
+            "median_iterations": float(np.median(iu)), "mean_path_length_solved": float(ru.path_len.cpu().numpy()[su == 0].mean())}]
+print(json.dumps(results[0]))
+results.append(evaluate(model.to(dev).eval(), wl_eval, "random-init weights"))
 model = model.cpu()
 tr = trainer.UNetTrainer(model, B, S, S, dev)
 rng = np.random.default_rng(0)
 t0 = time.time()
-step = 0
-for ep in range(epochs):
-    perm = rng.permutation(n)
-    run = []
-    for i in range(0, n - B + 1, B):
-        idx = torch.from_numpy(perm[i:i + B]).to(dev)
-        occ = wl_train.occ_maps[wl_train.task_to_map[idx].long()]
-        x = (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()
-        loss = tr.training_step((x, None, wl_train.coords[idx]), masks_u8=masks[idx])
-        step += 1
-        if step % 50 == 0:
-            run.append(float(loss.item()))
-    print("epoch %d: %d steps, mean loss (sampled) %.4f, %.1f s" % (ep, step, float(np.mean(run)), time.time() - t0))
-    tr.scheduler_step(float(np.mean(run)))
+run = []
+for step in range(1, n_steps + 1):
+    # the reference halves the rate on a validation plateau (ReduceLROnPlateau, train.py:230); here: fixed halvings late in the run
+    tr.lr = 1e-3 if step <= 0.6 * n_steps else (5e-4 if step <= 0.8 * n_steps else 2.5e-4)
+    idx = torch.from_numpy(rng.choice(n, B, replace=False)).to(dev)
+    occ = wl_train.occ_maps[wl_train.task_to_map[idx].long()]
+    x = (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()
+    run.append(tr.training_step((x, None, wl_train.coords[idx]), masks_u8=masks[idx]))
+    if step % 250 == 0:
+        print("step %d: mean loss %.4f, lr %g, loss scale %g, %.1f s" % (step, float(torch.stack(run).mean().item()), tr.lr,
+                                                                      float(tr.scale_state[0].item()), time.time() - t0))
+        run = []
+step = n_steps
 torch.cuda.synchronize()
 print("trained %d steps in %.1f s (%.1f samples/s)" % (step, time.time() - t0, step * B / (time.time() - t0)))
 tr.export_to(model)
