@@ -184,9 +184,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     if (!(p.dbg & 2))
                     tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ky * BLOCK_N + c * 32), v);
                     if (co < p.co) {
+                        const int ci0 = nb * BLOCK_N + c * 32;
+                        if (ci0 + 32 <= p.ci && (p.ci_stride & 3) == 0) {   // 8 vector reductions of 16 bytes instead of 32 scalar ones
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (nb * BLOCK_N + c * 32 + j < p.ci) atomicAdd(row + c * 32 + j, __uint_as_float(v[j]));
+                            for (int j = 0; j < 32; j += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + c * 32 + j), "f"(__uint_as_float(v[j])),
+                                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                             : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (ci0 + j < p.ci) atomicAdd(row + c * 32 + j, __uint_as_float(v[j]));
+                        }
                     }
                 }
             }
@@ -366,7 +375,7 @@ extern "C" int nrrt_conv_wgrad(const void* dy_cm, int cout, const void* x_cm, in
     NRRT_REQUIRE(n >= 1 && h >= 1 && w >= 64 && w % 64 == 0, "image rows must be a multiple of 64 pixels (got w = %d)", w);
     NRRT_REQUIRE(cout >= 1 && cin >= 1 && ci_stride >= cin, "bad channel counts");
     NRRT_REQUIRE(((uintptr_t)dy_cm & 15) == 0 && ((uintptr_t)x_cm & 15) == 0, "operands must be 16-byte aligned");
-    const int block_n = (cin % 128 == 0 || cin > 192) ? 128 : 64;
+    const int block_n = (cin % 128 == 0 || cin > 192) ? 128 : (cin % 96 == 0 ? 96 : 64);   // 192 channels: two MMAs of N = 96
     WgradParams p;
     p.H = h; p.xblocks = w / 64;
     p.co = cout; p.ci = cin;
@@ -396,5 +405,5 @@ extern "C" int nrrt_conv_wgrad(const void* dy_cm, int cout, const void* x_cm, in
     if (int rc = make_cm_map(&mb, x_cm, cin, n, h, w, block_n, ksize)) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int grid = tiles * splits;
-    return block_n == 128 ? launch_wgrad<128>(ma, mb, p, grid, st) : launch_wgrad<64>(ma, mb, p, grid, st);
+    return block_n == 128 ? launch_wgrad<128>(ma, mb, p, grid, st) : (block_n == 96 ? launch_wgrad<96>(ma, mb, p, grid, st) : launch_wgrad<64>(ma, mb, p, grid, st));
 }
