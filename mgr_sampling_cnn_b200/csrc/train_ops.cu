@@ -314,18 +314,43 @@ __global__ void __launch_bounds__(256) adam_kernel(float* p, const float* g, flo
         bc1 = 1.f - powf(b1, t);
         bc2_sqrt = sqrtf(1.f - powf(b2, t));
     }
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-        const float gi = g[i] * grad_scale;
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi; v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] -= (lr / bc1) * (mi / denom);
+    const float step = lr / bc1;
+    auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+        gi *= grad_scale;
+        mi = b1 * mi + (1.f - b1) * gi;
+        vi = b2 * vi + (1.f - b2) * gi * gi;
+        pi -= step * (mi / (sqrtf(vi) / bc2_sqrt + eps));
+    };
+    const long long n4 = n >> 2;                                 // 16-byte accesses (the buffers are 256-byte aligned torch allocations)
+    float4* p4 = reinterpret_cast<float4*>(p);
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* m4 = reinterpret_cast<float4*>(m);
+    float4* v4 = reinterpret_cast<float4*>(v);
+    const bool aligned = ((((uintptr_t)p) | ((uintptr_t)g) | ((uintptr_t)m) | ((uintptr_t)v)) & 15) == 0;
+    if (aligned) {
+        for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+            float4 pp = p4[i], mm = m4[i], vv = v4[i];
+            const float4 gg = g4[i];
+            upd(pp.x, gg.x, mm.x, vv.x); upd(pp.y, gg.y, mm.y, vv.y); upd(pp.z, gg.z, mm.z, vv.z); upd(pp.w, gg.w, mm.w, vv.w);
+            p4[i] = pp; m4[i] = mm; v4[i] = vv;
+        }
     }
+    for (long long i = (aligned ? n4 * 4 : 0) + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+        upd(p[i], g[i], m[i], v[i]);
 }
 
 __global__ void __launch_bounds__(256) to_half_kernel(const float* src, __half* dst, long long n) {
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) dst[i] = __float2half_rn(src[i]);
+    const bool aligned = ((((uintptr_t)src) | ((uintptr_t)dst)) & 15) == 0;
+    const long long n8 = aligned ? n >> 3 : 0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+        const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+        uint4 o;
+        __half2* h = reinterpret_cast<__half2*>(&o);
+        h[0] = __floats2half2_rn(a.x, a.y); h[1] = __floats2half2_rn(a.z, a.w);
+        h[2] = __floats2half2_rn(b.x, b.y); h[3] = __floats2half2_rn(b.z, b.w);
+        reinterpret_cast<uint4*>(dst)[i] = o;
+    }
+    for (long long i = n8 * 8 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) dst[i] = __float2half_rn(src[i]);
 }
 
 // data-gradient weights of a conv: dst fp16 [ci_rows][taps][co_cols] with dst[ci][taps-1-t][co] = src[co][t][ci]
@@ -656,7 +681,8 @@ extern "C" int nrrt_coords_fill_backward(const void* dcat, int64_t cs, int B, in
     EW_CHECK(c);
     NRRT_REQUIRE(dcat && dfeat && B >= 1 && h >= 1 && w >= 1 && cs % 8 == 0, "bad arguments");
     int gx = ew_grid((long long)h * w, c);
-    if (gx > 64) gx = 64;
+    const int cap = (148 * 4 + B - 1) / B;       // about four blocks per SM over the batch; every block adds 4 c floats with atomics
+    if (gx > cap) gx = cap;
     coords_fill_bwd_kernel<<<dim3(gx, B), kEw, ew_smem(c), (cudaStream_t)stream>>>((const __half*)dcat, cs, h, w, c, dfeat);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
