@@ -298,13 +298,12 @@ def train_section(args, dev, rank, world, pk, sync_all, max_over_ranks):
     ms = max_over_ranks(a.elapsed_time(b)) / steps
     # the weight-gradient kernel alone on the largest layer (conv8[0]: 192 -> 128 channels at 512 x 512, train.py:157)
     cv = tr.convs["c8.0"]
-    g_cm = tr._cm("g_cm", tr._buf("dx_c8.2", (B, S, S, 128)), 0, 128, 0)
-    x_cm = tr._cm("x_cm", tr.cat8, 0, 192, 0, copies=3)
-    tr._wgrad(cv, g_cm, x_cm, (S, S))
+    g = tr._buf("dx_c8.2", (B, S, S, 128))
+    tr._wgrad(cv, g, 0, tr.cat8, 0)
     torch.cuda.synchronize(dev)
     a.record()
     for _ in range(5):
-        tr._wgrad(cv, g_cm, x_cm, (S, S))
+        tr._wgrad(cv, g, 0, tr.cat8, 0)
     b.record()
     torch.cuda.synchronize(dev)
     wg_ms = a.elapsed_time(b) / 5

@@ -63,7 +63,22 @@ struct WgLayout {
     static constexpr uint32_t total = off_tmem + 16 + 1024;
 };
 
-template <int BLOCK_N>
+// MN-major SWIZZLE_128B operand descriptor (channels-last tiles: a K row = one pixel = 128 bytes of 64 channels; 8 pixels
+// form a 1024-byte swizzle atom): SBO = 1024 B between 8-pixel groups, LBO = 8192 B between 64-channel blocks (a block is
+// one TMA box of 64 pixels x 64 channels).  cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(8192 >> 4) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// MN = true: both operands are read straight from the channels-last activation / gradient buffers (MN-major UMMA operands:
+// no layout kernel, no shifted copies -- a tap shift in either direction is a TMA coordinate of an OUTER dimension).
+template <int BLOCK_N, bool MN = false>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
              const __grid_constant__ WgradParams p) {
@@ -115,7 +130,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                         const uint32_t slot = b_seq % kNB, ph = (b_seq / kNB) & 1u;
                         mbar_wait(empty_b(slot), ph ^ 1u);
                         mbar_expect_tx(full_b(slot), (p.dbg & 4) ? 0u : L::b_stage);
-                        if (!(p.dbg & 4))   // the kx shift lives in the operand copy (TMA cannot start a swizzled row off a 16-byte boundary)
+                        if (MN) {
+#pragma unroll
+                            for (int j = 0; j < BLOCK_N / 64; ++j)
+                                tma_load_4d(base + L::off_b + slot * L::b_stage + j * 8192, &map_b, full_b(slot), nb * BLOCK_N + 64 * j,
+                                            x0 + kx - p.pad, r, n);
+                        } else if (!(p.dbg & 4))   // the kx shift lives in the operand copy (TMA cannot start a swizzled row off a 16-byte boundary)
                         tma_load_5d_(base + L::off_b + slot * L::b_stage, &map_b, full_b(slot), x0, r, n, nb * BLOCK_N, kx);
                         ++b_seq;
                     }
@@ -124,7 +144,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                         const uint32_t slot = a_seq % kNA, ph = (a_seq / kNA) & 1u;
                         mbar_wait(empty_a(slot), ph ^ 1u);
                         mbar_expect_tx(full_a(slot), (p.dbg & 4) ? 0u : L::a_stage);
-                        if (!(p.dbg & 4))
+                        if (MN) {
+                            tma_load_4d(base + slot * L::a_stage, &map_a, full_a(slot), cb * 128, x0, y, n);
+                            tma_load_4d(base + slot * L::a_stage + 8192, &map_a, full_a(slot), cb * 128 + 64, x0, y, n);
+                        } else if (!(p.dbg & 4))
                         tma_load_4d(base + slot * L::a_stage, &map_a, full_a(slot), x0, y, n, cb * 128);
                         ++a_seq;
                     }
@@ -132,7 +155,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = make_idesc(BLOCK_N);
+        constexpr uint32_t idesc = make_idesc(BLOCK_N) | (MN ? ((1u << 15) | (1u << 16)) : 0u);   // bits 15 / 16: A / B are MN-major
+        constexpr uint64_t kstep = MN ? (2048 >> 4) : 2;   // one UMMA_K = 16 pixels: two 1024-byte atoms (MN-major) / 32 bytes (K-major)
         uint32_t a_seq = 0, bq = 0, b_waited = 0;   // b_waited = number of B loads already waited for (they complete in order)
         bool first = true;
         for (int s = s_begin; s < s_end; ++s) {
@@ -146,14 +170,15 @@ wgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                     ++b_waited;
                 }
                 tc_fence_after();
-                const uint64_t adesc = make_smem_desc(base + a_slot * L::a_stage);
+                const uint64_t adesc = MN ? make_smem_desc_mn(base + a_slot * L::a_stage) : make_smem_desc(base + a_slot * L::a_stage);
                 if (elect_one()) {
                     for (int ky = 0; ky < p.nky && !(p.dbg & 1); ++ky) {
                         const uint32_t b_slot = (bq + (uint32_t)(y + ky)) % kNB;
-                        const uint64_t bdesc = make_smem_desc(base + L::off_b + b_slot * L::b_stage);
+                        const uint64_t bdesc = MN ? make_smem_desc_mn(base + L::off_b + b_slot * L::b_stage)
+                                                  : make_smem_desc(base + L::off_b + b_slot * L::b_stage);
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
-                            tc_mma_f16(tmem_base + (uint32_t)(ky * BLOCK_N), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc,
+                            tc_mma_f16(tmem_base + (uint32_t)(ky * BLOCK_N), adesc + kstep * kk, bdesc + kstep * kk, idesc,
                                        (first && kk == 0) ? 0u : 1u);
                     }
                     tc_commit(empty_a(a_slot));
@@ -239,10 +264,10 @@ int make_cm_map(CUtensorMap* m, const void* ptr, int C, int N, int H, int W, int
     return NRRT_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool MN = false>
 int launch_wgrad(const CUtensorMap& ma, const CUtensorMap& mb, const WgradParams& p, int grid, cudaStream_t st) {
     using L = WgLayout<BLOCK_N>;
-    auto kern = wgrad_kernel<BLOCK_N>;
+    auto kern = wgrad_kernel<BLOCK_N, MN>;
     static int done_dev = -1;
     int dev = 0;
     NRRT_CUDA_TRY(cudaGetDevice(&dev));
@@ -365,6 +390,74 @@ extern "C" int nrrt_to_channel_major(const void* in, int64_t in_cstride, const v
     a.in_cstride = in_cstride; a.mask_cstride = mask_cstride; a.N = n; a.H = h; a.W = w; a.C = c; a.mode = mode; a.copies = copies;
     to_channel_major_kernel<<<dim3((w + 63) / 64, (c + 63) / 64, n * h), 256, 0, st>>>(a);
     NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+namespace {
+// channels-last fp16 slice [N][H][W][cstride], channels [0, C) at ptr -> map (C, W, H, N), box (64 channels, 64 pixels, 1, 1)
+int make_cl_map(CUtensorMap* m, const void* ptr, int C, int64_t cstride, int N, int H, int W) {
+    EncodeTiledFn enc = wg_encode_fn();
+    if (!enc) return nrrt_fail(NRRT_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+    const cuuint64_t cs = (cuuint64_t)cstride * 2;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {cs, cs * W, cs * W * H};
+    const cuuint32_t box[4] = {64, 64, 1, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return nrrt_fail(NRRT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for channels-last [%d][%d][%d][%d]", (int)r, N, H, W, C);
+    return NRRT_OK;
+}
+
+int wgrad_plan(WgradParams& p, int cout, int cin, int n, int h, int w, int ksize, float* dw, int ci_stride, int block_n, int* grid) {
+    p.H = h; p.xblocks = w / 64;
+    p.co = cout; p.ci = cin;
+    p.nky = ksize; p.nkx = ksize; p.pad = ksize / 2;
+    p.co_blocks = (cout + 127) / 128; p.ci_blocks = (cin + block_n - 1) / block_n;
+    p.dw = dw; p.ci_stride = ci_stride;
+    p.dbg = 0;
+    int dev = 0, sms = 0;
+    NRRT_CUDA_TRY(cudaGetDevice(&dev));
+    NRRT_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int tiles = p.co_blocks * p.ci_blocks * p.nkx;
+    int seg_rows = h;
+    while (seg_rows > 16 && (long long)tiles * n * p.xblocks * ((h + seg_rows - 1) / seg_rows) < 2LL * sms) seg_rows = (seg_rows + 1) / 2;
+    p.seg_rows = seg_rows; p.segs = (h + seg_rows - 1) / seg_rows;
+    p.strips = n * p.xblocks * p.segs;
+    int splits = (2 * sms + tiles - 1) / tiles;
+    if (splits > p.strips) splits = p.strips;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    *grid = tiles * splits;
+    return NRRT_OK;
+}
+}  // namespace
+
+extern "C" int nrrt_conv_wgrad_nhwc(const void* dy, int64_t dy_cstride, int cout, const void* x, int64_t x_cstride, int cin, int n, int h,
+                                    int w, int ksize, float* dw, int ci_stride, void* stream) {
+    NRRT_REQUIRE(dy && x && dw, "null pointer");
+    NRRT_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
+    NRRT_REQUIRE(n >= 1 && h >= 1 && w >= 64 && w % 64 == 0, "image rows must be a multiple of 64 pixels (got w = %d)", w);
+    NRRT_REQUIRE(cout >= 1 && cin >= 1 && ci_stride >= cin, "bad channel counts");
+    NRRT_REQUIRE(dy_cstride % 8 == 0 && x_cstride % 8 == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0,
+                 "operands must be 16-byte aligned with channel strides that are multiples of 8");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    CUtensorMap ma, mb;
+    if (int rc = make_cl_map(&ma, dy, cout, dy_cstride, n, h, w)) return rc;
+    // input channels in runs of 128 (N = 128 MMAs); a remainder of 64 (192, 384 + 64, ...) is a second launch with N = 64
+    const int main_ci = cin >= 128 ? (cin / 128) * 128 : 0, tail_ci = cin - main_ci;
+    for (int part = 0; part < 2; ++part) {
+        const int c0 = part == 0 ? 0 : main_ci, cn = part == 0 ? main_ci : tail_ci;
+        if (cn == 0) continue;
+        const int block_n = part == 0 ? 128 : 64;
+        WgradParams p;
+        int grid = 0;
+        if (int rc = wgrad_plan(p, cout, cn, n, h, w, ksize, dw + c0, ci_stride, block_n, &grid)) return rc;
+        if (int rc = make_cl_map(&mb, (const __half*)x + c0, cn, x_cstride, n, h, w)) return rc;
+        const int rc = block_n == 128 ? launch_wgrad<128, true>(ma, mb, p, grid, st) : launch_wgrad<64, true>(ma, mb, p, grid, st);
+        if (rc) return rc;
+    }
     return NRRT_OK;
 }
 

@@ -347,12 +347,13 @@ class UNetTrainer(object):
                                              mode, copies, _pp(out), self._st()))
         return out
 
-    def _wgrad(self, cv, g_cm, x_cm, grid):
-        """grads[cv.w] += wgrad(g_cm [rows][n][h][w], x_cm [ksize][cin_pad][n][h][w])."""
+    def _wgrad(self, cv, g, g_coff, x, x_coff):
+        """grads[cv.w] += weight gradient from channels-last buffers: g = masked output gradient (channels [g_coff, +rows)), x = the
+        layer's input (channels [x_coff, +cin_pad)), both on the grid the stride-1 form of the layer runs on (nrrt_conv_wgrad_nhwc)."""
         k = 3 if cv.taps == 9 else 1
         _lib.count_launch()
-        check(self.lib.nrrt_conv_wgrad(_pp(g_cm), cv.rows, _pp(x_cm), cv.cin_pad, self.B, grid[0], grid[1], k, _pp(self.grads, cv.w_off),
-                                       cv.cin_pad, self._st()))
+        check(self.lib.nrrt_conv_wgrad_nhwc(_pp(g, g_coff), g.shape[-1], cv.rows, _pp(x, x_coff), x.shape[-1], cv.cin_pad, self.B,
+                                            x.shape[1], x.shape[2], k, _pp(self.grads, cv.w_off), cv.cin_pad, self._st()))
 
     def _relu_bwd(self, dy, dy_off, c, y, y_off, out, dbias_off):
         pixels = dy.shape[0] * dy.shape[1] * dy.shape[2]
@@ -365,9 +366,7 @@ class UNetTrainer(object):
         """conv + bias + ReLU layer: dy (dense, gradient of the stored output y) is masked in place; returns dx (dense)."""
         lib, st = self.lib, self._st()
         self._relu_bwd(dy, 0, cv.cout, y, 0, dy, cv.b_off)
-        g_cm = self._cm("g_cm", dy, 0, cv.cout, 0)
-        x_cm = self._cm("x_cm", x, 0, cv.cin_pad, 0, copies=3)
-        self._wgrad(cv, g_cm, x_cm, self.lv[lv])
+        self._wgrad(cv, dy, 0, x, 0)
         if not need_dx:
             return None
         dx = self._buf("dx_" + cv.name, (self.B,) + self.lv[lv] + (cv.cin_pad,))
@@ -379,13 +378,11 @@ class UNetTrainer(object):
         lib, st = self.lib, self._st()
         for gidx in range(4):   # the bias is stored once per output offset (the forward's layout); all four get the same gradient
             self._relu_bwd(dcat, 0, cv.cout, None, 0, None, cv.b_off + gidx * cv.cout)
-        g_cm = self._cm("g_cm", dcat, 0, cv.cout, 2)
-        x_cm = self._cm("x_cm", x, 0, cv.cin_pad, 0)
-        self._wgrad(cv, g_cm, x_cm, self.lv[lv_in])
         s2d = self._buf("s2d", (self.B,) + self.lv[lv_in] + (4 * cv.cout,))
         _lib.count_launch()
         check(lib.nrrt_remap_channels_last(_pp(dcat), dcat.shape[-1], _pp(s2d), 4 * cv.cout, self.B, self.lv[lv_in][0], self.lv[lv_in][1],
                                            cv.cout, 0, st))
+        self._wgrad(cv, s2d, 0, x, 0)      # a 1x1 weight gradient over the 4 * cout space-to-depth channels
         dx = self._buf("dx_" + cv.name, (self.B,) + self.lv[lv_in] + (cv.cin_pad,))
         cv.dgrad.run(lib, st, s2d, 0, (1,) + self.lv[lv_in], dx, 0)
         return dx
@@ -411,23 +408,22 @@ class UNetTrainer(object):
         shape = (self.B,) + self.lv[si] + (ch,)
         dz2, gres = self._buf("dz2", shape), self._buf("gres", shape)
         self._bn_bwd(c2, dy, dy_off, out, out_off, d["z2"], d["st2"], dz2, g_out=gres)
-        self._wgrad(c2, self._cm("g_cm", dz2, 0, ch, 0), self._cm("x_cm", d["h"], 0, ch, 0, copies=3), self.lv[si])
+        self._wgrad(c2, dz2, 0, d["h"], 0)
         dh = self._buf("dh", shape)
         c2.dgrad.run(lib, st, dz2, 0, (1,) + self.lv[si], dh, 0)
         dz1 = self._buf("dz1", shape)
         self._bn_bwd(c1, dh, 0, d["h"], 0, d["z1"], d["st1"], dz1)
-        x_cm = self._cm("x_cm", xin, xin_off, c1.cin_pad, 0, copies=3)
         gin = (1,) + self.lv[lv_in]
         dx = self._buf("dx_blk%d%d" % (si, bi), (self.B,) + self.lv[lv_in] + (c1.cin_pad,))
         if ds is None:
-            self._wgrad(c1, self._cm("g_cm", dz1, 0, ch, 0), x_cm, self.lv[lv_in])
+            self._wgrad(c1, dz1, 0, xin, xin_off)
             c1.dgrad.run(lib, st, dz1, 0, gin, dx, 0, res=gres, res_coff=0)
             return dx
         # stride-2 block: both convolutions of the input are seen on the input grid through the zero-stuffed gradient
-        self._wgrad(c1, self._cm("g_cm", dz1, 0, ch, 1), x_cm, self.lv[lv_in])
         stuffed = self._buf("stuffed", (self.B,) + self.lv[lv_in] + (ch,))
         _lib.count_launch(2)
         check(lib.nrrt_remap_channels_last(_pp(dz1), ch, _pp(stuffed), ch, self.B, self.lv[si][0], self.lv[si][1], ch, 1, st))
+        self._wgrad(c1, stuffed, 0, xin, xin_off)
         dxa = self._buf("dxa", (self.B,) + self.lv[lv_in] + (c1.cin_pad,))
         if skip is not None:
             c1.dgrad.run(lib, st, stuffed, 0, gin, dxa, 0, res=skip[0], res_coff=skip[1])
@@ -435,8 +431,8 @@ class UNetTrainer(object):
             c1.dgrad.run(lib, st, stuffed, 0, gin, dxa, 0)
         dzd = self._buf("dzd", shape)
         self._bn_bwd(ds, gres, 0, None, 0, d["zd"], d["std"], dzd)
-        self._wgrad(ds, self._cm("g_cm", dzd, 0, ch, 1), x_cm[1], self.lv[lv_in])   # copy 1 = the unshifted image
         check(lib.nrrt_remap_channels_last(_pp(dzd), ch, _pp(stuffed), ch, self.B, self.lv[si][0], self.lv[si][1], ch, 1, st))
+        self._wgrad(ds, stuffed, 0, xin, xin_off)
         ds.dgrad.run(lib, st, stuffed, 0, gin, dx, 0, res=dxa, res_coff=0)
         return dx
 
@@ -451,7 +447,7 @@ class UNetTrainer(object):
         # conv8.2: g8 is already masked by its ReLU
         c = cv["c8.2"]
         self._relu_bwd(g8, 0, 64, None, 0, None, c.b_off)
-        self._wgrad(c, self._cm("g_cm", g8, 0, 64, 0), self._cm("x_cm", self.a8, 0, 128, 0, copies=3), self.lv[0])
+        self._wgrad(c, g8, 0, self.a8, 0)
         d_a8 = self._buf("dx_c8.2", (B,) + self.lv[0] + (128,))
         c.dgrad.run(lib, st, g8, 0, (1,) + self.lv[0], d_a8, 0)
         dcat8 = self._conv_relu_bwd(cv["c8.0"], d_a8, self.a8, self.cat8, 0)

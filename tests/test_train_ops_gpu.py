@@ -208,3 +208,21 @@ def test_stem_wgrad_and_coords_backward():
     assert (dB.cpu() - conv.bias.grad).abs().max() / conv.bias.grad.abs().max() < 1e-3
     rin = fin.grad.permute(0, 2, 3, 1).reshape(B, 4, cin)
     assert (dfin.cpu() - rin).abs().max() / rin.abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("n,h,w,cout,cin,k", [(2, 16, 64, 128, 64, 3), (1, 8, 128, 64, 64, 3), (2, 12, 64, 256, 192, 3),
+                                              (1, 16, 64, 128, 384, 3), (3, 8, 64, 512, 256, 1), (1, 70, 192, 64, 128, 3)])
+def test_wgrad_nhwc_matches_torch(n, h, w, cout, cin, k):
+    """nrrt_conv_wgrad_nhwc: MN-major operands straight from channels-last buffers, here channel SLICES of wider buffers."""
+    torch.manual_seed(5)
+    lib = _lib.load()
+    gbuf = (torch.randn(n, h, w, cout + 64) * 0.5).half().to(DEV)
+    xbuf = torch.randn(n, h, w, cin + 128).half().to(DEV)
+    g, x = gbuf[..., 64:].float().cpu(), xbuf[..., 64:64 + cin].float().cpu()
+    ref = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2).double(), (cout, cin, k, k), g.permute(0, 3, 1, 2).double(), padding=k // 2)
+    dw = torch.zeros(cout, k * k, cin, dtype=torch.float32, device=DEV)
+    check(lib.nrrt_conv_wgrad_nhwc(C.c_void_p(gbuf.data_ptr() + 128), cout + 64, cout, C.c_void_p(xbuf.data_ptr() + 128), cin + 128, cin,
+                                   n, h, w, k, _p(dw), cin, _st()))
+    got = dw.cpu().double().reshape(cout, k, k, cin).permute(0, 3, 1, 2)
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-3, "relative max error %g" % err
