@@ -539,6 +539,9 @@ int nrrt_to_half(const float* src, void* dst, int64_t count, void* stream);
 /* Data-gradient weights: dst fp16 [ci_rows][taps][co_cols], dst[ci][taps - 1 - t][co] = w[co][t][ci] (w fp32
  * [cout][taps][ci_stride]); rows / columns beyond the source are zero. */
 int nrrt_pack_dgrad_weight(const float* w, int cout, int taps, int ci_stride, int ci_rows, int co_cols, void* dst, void* stream);
+/* nrrt_pack_dgrad_weight for all layers of a model in one launch: descs_dev = device int64 [n_layers][8] =
+ * {source offset into params (floats), destination offset into dst_base (halfs), cout, taps, ci_stride, ci_rows, co_cols, 0}. */
+int nrrt_pack_dgrad_weights(const float* params, void* dst_base, const int64_t* descs_dev, int n_layers, void* stream);
 /* First conv (cin -> cout from the fp32 NCHW input, train.py:118): dweight[co][ci][tap] += sum g[pixel][co] x[ci][pixel + tap];
  * dbias[co] += sum g.  g: fp16 channels-last, already masked by the ReLU. */
 int nrrt_stem_wgrad(const float* x, const void* g, int64_t g_cs, int n, int cin, int h, int w, int cout, float* dweight, float* dbias,

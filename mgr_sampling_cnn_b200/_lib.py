@@ -150,6 +150,7 @@ _SIGNATURES = {
     "nrrt_loss_scale_update": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p]),
     "nrrt_to_half": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "nrrt_pack_dgrad_weight": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nrrt_pack_dgrad_weights": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nrrt_stem_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrrt_coords_fill_backward": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nrrt_coords_layer_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -368,6 +368,24 @@ __global__ void __launch_bounds__(256) pack_dgrad_kernel(const float* src, __hal
     }
 }
 
+// the same for every convolution of a model in ONE launch: blockIdx.y = layer, desc = 8 int64 per layer
+// {src offset (floats), dst offset (halfs), co, taps, ci_stride, ci_rows, co_cols, 0}
+__global__ void __launch_bounds__(256) pack_dgrad_batched_kernel(const float* params, __half* dst_base, const long long* descs) {
+    const long long* d = descs + 8 * blockIdx.y;
+    const float* src = params + d[0];
+    __half* dst = dst_base + d[1];
+    const int co = (int)d[2], taps = (int)d[3], ci_stride = (int)d[4], ci_rows = (int)d[5], co_cols = (int)d[6];
+    const long long total = (long long)ci_rows * taps * co_cols;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int o = (int)(i % co_cols);
+        const int t = (int)((i / co_cols) % taps);
+        const int c = (int)(i / ((long long)co_cols * taps));
+        float v = 0.f;
+        if (o < co && c < ci_stride) v = src[((size_t)o * taps + (taps - 1 - t)) * ci_stride + c];
+        dst[i] = __float2half_rn(v);
+    }
+}
+
 // first conv (3 -> 32, train.py:118) weight gradient from the fp32 NCHW input: dW[co][ci][tap] += sum g[p][co] x[ci][p + tap]
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* x, const __half* g, long long g_cs, int N, int cin, int H, int W, int cout,
                                                          float* dw, float* db) {
@@ -662,6 +680,13 @@ extern "C" int nrrt_pack_dgrad_weight(const float* w, int cout, int taps, int ci
     const long long total = (long long)ci_rows * taps * co_cols, blocks = (total + 255) / 256;
     pack_dgrad_kernel<<<(int)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, (cudaStream_t)stream>>>(w, (__half*)dst, cout, taps, ci_stride, ci_rows,
                                                                                                     co_cols);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
+extern "C" int nrrt_pack_dgrad_weights(const float* params, void* dst_base, const int64_t* descs_dev, int n_layers, void* stream) {
+    NRRT_REQUIRE(params && dst_base && descs_dev && n_layers >= 1 && n_layers <= 65535, "bad arguments");
+    pack_dgrad_batched_kernel<<<dim3(148, n_layers), 256, 0, (cudaStream_t)stream>>>(params, (__half*)dst_base, (const long long*)descs_dev);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
 }

@@ -151,8 +151,19 @@ class UNetTrainer(object):
             else:
                 scale, shift = self.ones[:cv.rows], self.params[cv.b_off:cv.b_off + cv.rows]
             cv.fwd = _Layer(2, cv.kind, cv.cin_pad, cv.cout, wv, scale, shift, cv.bn is None and cv.kind != CONVT, cin_real=cv.cin)
-            cv.wd = torch.empty((cv.cin_pad, cv.taps, cv.rows), dtype=torch.float16, device=dev)
-            cv.dgrad = _Layer(2, K3S1 if cv.taps == 9 else K1S1, cv.rows, cv.cin_pad, cv.wd, None, None, False)
+        # data-gradient weights: one flat fp16 buffer, repacked by ONE launch per step.  A 192-channel input (conv8[0]) gets 256
+        # gradient rows (64 of zeros): its data gradient then runs on the 256-wide pair kernel instead of three N = 64 tiles
+        descs, off = [], 0
+        for cv in self.convs.values():
+            cv.dx_ch = 256 if cv.cin_pad == 192 else cv.cin_pad
+            descs.append([cv.w_off, off, cv.rows, cv.taps, cv.cin_pad, cv.dx_ch, cv.rows, 0])
+            cv.wd_off = off
+            off += (cv.dx_ch * cv.taps * cv.rows + 63) // 64 * 64
+        self.wd_all = torch.zeros(off, dtype=torch.float16, device=dev)
+        self.wd_descs = torch.tensor(descs, dtype=torch.int64, device=dev)
+        for cv in self.convs.values():
+            cv.wd = self.wd_all[cv.wd_off:cv.wd_off + cv.dx_ch * cv.taps * cv.rows].view(cv.dx_ch, cv.taps, cv.rows)
+            cv.dgrad = _Layer(2, K3S1 if cv.taps == 9 else K1S1, cv.rows, cv.dx_ch, cv.wd, None, None, False)
         self._refresh_weights()
 
     def _master_view(self, t, cv, what):
@@ -222,12 +233,11 @@ class UNetTrainer(object):
         return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
 
     def _refresh_weights(self):
-        """fp16 mirror of the whole parameter buffer (one launch) + the data-gradient weight layouts (one launch per conv)."""
+        """fp16 mirror of the whole parameter buffer + the data-gradient weight layouts of every conv: two launches."""
         lib, st = self.lib, self._st()
-        _lib.count_launch(1 + len(self.convs))
+        _lib.count_launch(2)
         check(lib.nrrt_to_half(_pp(self.params), _pp(self.params_h), self.n_params, st))
-        for cv in self.convs.values():
-            check(lib.nrrt_pack_dgrad_weight(_pp(self.params, cv.w_off), cv.rows, cv.taps, cv.cin_pad, cv.cin_pad, cv.rows, _pp(cv.wd), st))
+        check(lib.nrrt_pack_dgrad_weights(_pp(self.params), _pp(self.wd_all), _pp(self.wd_descs), len(self.convs), st))
 
     # ----------------------------------------------------------------------------------------------------------- buffers
     def _alloc(self):
@@ -369,7 +379,7 @@ class UNetTrainer(object):
         self._wgrad(cv, dy, 0, x, 0)
         if not need_dx:
             return None
-        dx = self._buf("dx_" + cv.name, (self.B,) + self.lv[lv] + (cv.cin_pad,))
+        dx = self._buf("dx_" + cv.name, (self.B,) + self.lv[lv] + (cv.dx_ch,))     # channels beyond cin_pad (if any) are zeros
         cv.dgrad.run(lib, st, dy, 0, (1,) + self.lv[lv], dx, 0)
         return dx
 
