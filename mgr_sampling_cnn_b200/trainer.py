@@ -52,6 +52,7 @@ class UNetTrainer(object):
         self.B, self.H, self.W = int(batch), int(height), int(width)
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.step_count = 0
+        self._exported_steps = 0
         self.M = self.B * self.H * self.W
         # Activation gradients are fp16, so the loss is scaled: dlogits = (sigmoid - t) * g.  g lives on the device
         # (self.scale_state[0]) and adapts like torch.cuda.amp.GradScaler without a host round trip: a step whose gradients are
@@ -224,7 +225,8 @@ class UNetTrainer(object):
                 if cv.bn is not None:
                     cv.bn[4].running_mean.copy_(cv.bn[2].to(cv.bn[4].running_mean.device))
                     cv.bn[4].running_var.copy_(cv.bn[3].to(cv.bn[4].running_var.device))
-                    cv.bn[4].num_batches_tracked += self.step_count
+                    cv.bn[4].num_batches_tracked += self.step_count - self._exported_steps
+        self._exported_steps = self.step_count
         if hasattr(model, "invalidate_plan"):
             model.invalidate_plan()
         return model

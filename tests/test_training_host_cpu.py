@@ -1,0 +1,35 @@
+"""CPU: the training / mask-maker host layer refuses to run without the CUDA path (no silent fallback), and its host-side
+helpers (path packing, shell values, file-name contract) behave like the reference's."""
+import numpy as np
+import pytest
+import torch
+
+from mgr_sampling_cnn_b200 import ThreeD_enlarge_path as ep
+from mgr_sampling_cnn_b200 import _lib
+from mgr_sampling_cnn_b200 import generate_paths as gp
+
+
+def test_pack_paths_and_layer_values():
+    arr, n = gp.pack_paths([[(1, 2), (3, 4), (5, 6)], [], [(7, 8)]], 2)
+    assert arr.shape == (3, 3, 2) and n.tolist() == [3, 0, 1] and arr[0, 2].tolist() == [5, 6] and not arr[1].any()
+    assert ep.layer_values().tolist() == [206, 157, 108, 59, 10]          # ThreeD_enlarge_path.py:44-50 with LAYERS = 5
+    assert ep.layer_values(3).tolist() == [172, 89, 6]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour of a box without a GPU")
+def test_no_cpu_fallback():
+    from mgr_sampling_cnn_b200 import train, trainer
+    with pytest.raises(_lib.NrrtError):
+        trainer.UNetTrainer(train.UNet_cooler(), 1, 512, 512)
+    with pytest.raises(_lib.NrrtError):
+        gp.path_masks(np.full((1, 64, 64), 255, np.uint8), [0], [[(1, 1)]])
+    with pytest.raises(_lib.NrrtError):
+        ep.enlarge_paths(np.zeros((1, 8, 8, 8), np.uint8), [0], np.zeros((1, 8, 8, 8), np.uint8))
+
+
+def test_trainer_rejects_sizes_the_kernels_do_not_cover():
+    from mgr_sampling_cnn_b200 import train, trainer
+    if not torch.cuda.is_available():
+        pytest.skip("the size check sits behind the CUDA check")
+    with pytest.raises(ValueError):
+        trainer.UNetTrainer(train.UNet_cooler(), 1, 256, 256)
