@@ -45,8 +45,8 @@ def parse_args():
     ap.add_argument("--sweep-tasks", type=int, default=4096, help="total tasks of the strong-scaling 3D section")
     ap.add_argument("--micro-batch", type=int, default=None, help="tasks per decoder launch (default: GuidedPlanner's)")
     ap.add_argument("--encoder-batch", type=int, default=None, help="distinct maps per encoder pass (default: GuidedPlanner's)")
-    ap.add_argument("--train-steps", type=int, default=4000, help="optimisation steps of the trained_guidance section (0 = skip it)")
-    ap.add_argument("--train-maps", type=int, default=600, help="generated maps (x 10 tasks) of its training set")
+    ap.add_argument("--train-steps", type=int, default=6000, help="optimisation steps of the trained_guidance section (0 = skip it)")
+    ap.add_argument("--train-maps", type=int, default=800, help="generated maps (x 10 tasks) of its training set")
     ap.add_argument("--layer-table", default=None, help="write the per-layer CUDA-event timings of the sampled launches (csv)")
     return ap.parse_args()
 

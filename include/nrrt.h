@@ -491,7 +491,8 @@ int nrrt_conv_wgrad(const void* dy_cm, int cout, const void* x_cm, int cin, int 
                     void* stream);
 /* The same weight gradient read straight from the channels-last buffers (no nrrt_to_channel_major): dy [n][h][w][dy_cstride]
  * (channels [0, cout) at `dy`, already masked by the layer's ReLU), x [n][h][w][x_cstride] (channels [0, cin) at `x`).  The
- * tiles are MN-major tensor-core operands, so both tap shifts are TMA coordinates.  w must be a multiple of 64. */
+ * tiles are MN-major tensor-core operands, so both tap shifts are TMA coordinates.  Any w (rows are walked in 64-pixel blocks; a
+ * partial block is zero-filled by TMA). */
 int nrrt_conv_wgrad_nhwc(const void* dy, int64_t dy_cstride, int cout, const void* x, int64_t x_cstride, int cin, int n, int h, int w,
                          int ksize, float* dw, int ci_stride, void* stream);
 /* g = dy where y > 0 else 0 (y = the stored output of a conv + bias + ReLU layer; NULL = no mask), dbias[c] += sum g

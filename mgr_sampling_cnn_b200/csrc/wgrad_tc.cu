@@ -411,7 +411,7 @@ int make_cl_map(CUtensorMap* m, const void* ptr, int C, int64_t cstride, int N, 
 }
 
 int wgrad_plan(WgradParams& p, int cout, int cin, int n, int h, int w, int ksize, float* dw, int ci_stride, int block_n, int* grid) {
-    p.H = h; p.xblocks = w / 64;
+    p.H = h; p.xblocks = (w + 63) / 64;   // a last column block wider than the image reads zeros (TMA fill): correct, just idle MMA rows
     p.co = cout; p.ci = cin;
     p.nky = ksize; p.nkx = ksize; p.pad = ksize / 2;
     p.co_blocks = (cout + 127) / 128; p.ci_blocks = (cin + block_n - 1) / block_n;
@@ -438,7 +438,7 @@ extern "C" int nrrt_conv_wgrad_nhwc(const void* dy, int64_t dy_cstride, int cout
                                     int w, int ksize, float* dw, int ci_stride, void* stream) {
     NRRT_REQUIRE(dy && x && dw, "null pointer");
     NRRT_REQUIRE(ksize == 1 || ksize == 3, "ksize must be 1 or 3");
-    NRRT_REQUIRE(n >= 1 && h >= 1 && w >= 64 && w % 64 == 0, "image rows must be a multiple of 64 pixels (got w = %d)", w);
+    NRRT_REQUIRE(n >= 1 && h >= 1 && w >= 1, "bad grid");
     NRRT_REQUIRE(cout >= 1 && cin >= 1 && ci_stride >= cin, "bad channel counts");
     NRRT_REQUIRE(dy_cstride % 8 == 0 && x_cstride % 8 == 0 && ((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0,
                  "operands must be 16-byte aligned with channel strides that are multiples of 8");

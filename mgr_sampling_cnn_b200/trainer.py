@@ -9,8 +9,8 @@ ConvTranspose through zero-stuffed / space-to-depth views of the gradient), the 
 buffers.  Parameters live in ONE flat fp32 buffer in the kernels' own layouts ([cout][tap][cin] conv weights), with an
 fp16 mirror for the tensor cores, a flat gradient buffer and flat Adam moments: the optimizer is one launch.
 
-2D only (UNet_cooler); image sides must be multiples of 512 (the weight-gradient kernel walks 64-pixel row segments at
-every level, the coarsest being 1/8).  There is no CPU fallback.
+2D only (UNet_cooler); image sides must be multiples of 64 (512 and up keep every level's rows whole 64-pixel blocks for the
+weight-gradient kernel; smaller images run with partly idle blocks at the coarse levels).  There is no CPU fallback.
 """
 import ctypes as C
 import math
@@ -45,8 +45,8 @@ class UNetTrainer(object):
                  eps: float = 1e-8, loss_scale: float = None, data_parallel: bool = None):
         if not torch.cuda.is_available():
             raise _lib.NrrtError("UNetTrainer needs a CUDA device (sm_100a); there is no CPU fallback")
-        if height % 512 or width % 512:
-            raise ValueError("image sides must be multiples of 512")
+        if height % 64 or width % 64:
+            raise ValueError("image sides must be multiples of 64 (three stride-2 stages, 8-pixel tiles at the coarsest)")
         self.lib = _lib.load()
         self.dev = torch.device(device)
         self.B, self.H, self.W = int(batch), int(height), int(width)

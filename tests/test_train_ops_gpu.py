@@ -211,7 +211,8 @@ def test_stem_wgrad_and_coords_backward():
 
 
 @pytest.mark.parametrize("n,h,w,cout,cin,k", [(2, 16, 64, 128, 64, 3), (1, 8, 128, 64, 64, 3), (2, 12, 64, 256, 192, 3),
-                                              (1, 16, 64, 128, 384, 3), (3, 8, 64, 512, 256, 1), (1, 70, 192, 64, 128, 3)])
+                                              (1, 16, 64, 128, 384, 3), (3, 8, 64, 512, 256, 1), (1, 70, 192, 64, 128, 3),
+                                              (2, 16, 32, 128, 64, 3), (1, 24, 96, 64, 128, 3), (2, 8, 8, 256, 128, 1)])
 def test_wgrad_nhwc_matches_torch(n, h, w, cout, cin, k):
     """nrrt_conv_wgrad_nhwc: MN-major operands straight from channels-last buffers, here channel SLICES of wider buffers."""
     torch.manual_seed(5)

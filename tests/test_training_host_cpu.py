@@ -32,4 +32,4 @@ def test_trainer_rejects_sizes_the_kernels_do_not_cover():
     if not torch.cuda.is_available():
         pytest.skip("the size check sits behind the CUDA check")
     with pytest.raises(ValueError):
-        trainer.UNetTrainer(train.UNet_cooler(), 1, 256, 256)
+        trainer.UNetTrainer(train.UNet_cooler(), 1, 200, 256)
