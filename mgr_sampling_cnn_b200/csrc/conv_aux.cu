@@ -125,61 +125,40 @@ __global__ void __launch_bounds__(256) coords_kernel(const float* __restrict__ c
     }
 }
 
-// One layer of the branch for SMALL batches (the training step: 3 tasks): the fused kernel above has B / kTB CTAs, i.e. one
-// CTA walking 1.6 M weights alone.  Here a CTA is (32 output channels, kTB tasks) of one layer and its 256 threads split the
-// input channels 8 ways (partial sums combined in a fixed order through shared memory), so the dependent weight loads of a
-// thread are 1/8 as many and 16 x more CTAs are in flight.
-constexpr int kCoB = 32, kKg = 8;
-__global__ void __launch_bounds__(kCoB * kKg) coords_layer_kernel(const float* __restrict__ in, int B, int gh, int gw, int cin, int cout,
-                                                                  const float* __restrict__ wt, const float* __restrict__ bias,
-                                                                  float* __restrict__ out) {
-    extern __shared__ float sm[];       // [kTB][P][cin] inputs, then [kKg][kTB * P][kCoB] partial sums
+// One layer of the branch for SMALL batches (the training step: 3 tasks; a short last chunk of a planning batch): the fused
+// kernel above has B / kTB CTAs, i.e. one CTA walking 1.6 M weights alone.  Here a thread owns ONE output (task, position,
+// channel) and runs the same chain as coords_kernel -- bias, then fmaf over (tap, ci) in that order -- so the results are
+// bit-identical to the fused kernel's: which kernel a batch size selects must never show in the plans (a sharded run
+// equals the single-GPU run bit for bit).  The weight loads do not depend on the accumulator and pipeline under the chain.
+constexpr int kCoB = 64, kTpB = 4;
+__global__ void __launch_bounds__(kCoB * kTpB) coords_layer_kernel(const float* __restrict__ in, int B, int gh, int gw, int cin, int cout,
+                                                                   const float* __restrict__ wt, const float* __restrict__ bias,
+                                                                   float* __restrict__ out) {
+    extern __shared__ float s_in[];     // [kTpB][P][cin]: the inputs of the tasks this block touches (at most kTpB distinct)
     const int P = gh * gw;
-    const int t0 = blockIdx.y * kTB;
-    const int nt = min(kTB, B - t0);
-    const int lco = threadIdx.x % kCoB, kg = threadIdx.x / kCoB;
-    const int co = blockIdx.x * kCoB + lco;
-    float* s_in = sm;
-    float* s_part = sm + kTB * P * cin;
-    for (int i = threadIdx.x; i < nt * P * cin; i += blockDim.x) s_in[i] = in[(size_t)t0 * P * cin + i];
-    __syncthreads();
-    float acc[kTB][kMaxP];
-#pragma unroll
-    for (int t = 0; t < kTB; ++t)
-#pragma unroll
-        for (int pp = 0; pp < kMaxP; ++pp) acc[t][pp] = 0.f;
-    if (co < cout)
-        for (int tap = 0; tap < 9; ++tap) {
-            const int ky = tap / 3 - 1, kx = tap % 3 - 1;
-            const float* wp = wt + (size_t)tap * cin * cout + co;
-#pragma unroll 4
-            for (int ci = kg; ci < cin; ci += kKg) {
-                const float w = __ldg(wp + (size_t)ci * cout);
-#pragma unroll
-                for (int pp = 0; pp < kMaxP; ++pp) {
-                    if (pp >= P) break;
-                    const int y = pp / gw + ky, x = pp % gw + kx;
-                    if (y < 0 || y >= gh || x < 0 || x >= gw) continue;
-                    const int sp = y * gw + x;
-#pragma unroll
-                    for (int t = 0; t < kTB; ++t)
-                        if (t < nt) acc[t][pp] = fmaf(s_in[(t * P + sp) * cin + ci], w, acc[t][pp]);
-                }
-            }
-        }
-#pragma unroll
-    for (int t = 0; t < kTB; ++t)
-#pragma unroll
-        for (int pp = 0; pp < kMaxP; ++pp)
-            if (pp < P) s_part[(kg * kTB * P + t * P + pp) * kCoB + lco] = acc[t][pp];
-    __syncthreads();
-    for (int i = threadIdx.x; i < nt * P * kCoB; i += blockDim.x) {
-        const int c = i % kCoB, tp = i / kCoB;
-        if (blockIdx.x * kCoB + c >= cout) continue;
-        float v = bias[blockIdx.x * kCoB + c];
-        for (int g = 0; g < kKg; ++g) v += s_part[(g * kTB * P + tp) * kCoB + c];
-        out[((size_t)t0 * P + tp) * cout + blockIdx.x * kCoB + c] = fmaxf(v, 0.f);
+    const int co = blockIdx.x * kCoB + threadIdx.x % kCoB;
+    const int slot = threadIdx.x / kCoB;
+    const int tp0 = blockIdx.y * kTpB;                       // first (task, position) pair of the block
+    const int tp = tp0 + slot;
+    for (int i = threadIdx.x; i < kTpB * P * cin; i += blockDim.x) {
+        const int sl = i / (P * cin), r = i - sl * P * cin;
+        const int t = (tp0 + sl) / P;
+        s_in[i] = t < B ? in[(size_t)t * P * cin + r] : 0.f;
     }
+    __syncthreads();
+    if (co >= cout || tp >= B * P) return;
+    const int pp = tp % P;
+    const float* x = s_in + slot * P * cin;
+    float acc = bias[co];
+    for (int tap = 0; tap < 9; ++tap) {
+        const int y = pp / gw + tap / 3 - 1, xq = pp % gw + tap % 3 - 1;
+        if (y < 0 || y >= gh || xq < 0 || xq >= gw) continue;
+        const float* wp = wt + (size_t)tap * cin * cout + co;
+        const float* xp = x + (y * gw + xq) * cin;
+#pragma unroll 8
+        for (int ci = 0; ci < cin; ++ci) acc = fmaf(xp[ci], __ldg(wp + (size_t)ci * cout), acc);
+    }
+    out[(size_t)tp * cout + co] = fmaxf(acc, 0.f);
 }
 
 // ---- align_corners interpolation of the (gh x gw [x 1]) feature into a channel slice (PyTorch's fp32 formulas) -------
@@ -796,10 +775,8 @@ extern "C" int nrrt_coords_branch(const float* coords, int B, int gh, int gw, co
         const int cins[4] = {1, 64, 128, 256}, couts[4] = {64, 128, 256, 512};
         const float* in = coords;
         for (int l = 0; l < 4; ++l) {
-            const size_t smem = ((size_t)kTB * gh * gw * cins[l] + (size_t)kKg * kTB * gh * gw * kCoB) * sizeof(float);
-            if (smem > 48 * 1024)
-                NRRT_CUDA_TRY(cudaFuncSetAttribute(coords_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            coords_layer_kernel<<<dim3((couts[l] + kCoB - 1) / kCoB, (B + kTB - 1) / kTB), kCoB * kKg, smem,
+            const size_t smem = (size_t)kTpB * gh * gw * cins[l] * sizeof(float);
+            coords_layer_kernel<<<dim3((couts[l] + kCoB - 1) / kCoB, (B * gh * gw + kTpB - 1) / kTpB), kCoB * kTpB, smem,
                                   reinterpret_cast<cudaStream_t>(stream)>>>(in, B, gh, gw, cins[l], couts[l], weights[l], biases[l], feats[l]);
             in = feats[l];
         }

@@ -227,3 +227,31 @@ def test_wgrad_nhwc_matches_torch(n, h, w, cout, cin, k):
     got = dw.cpu().double().reshape(cout, k, k, cin).permute(0, 3, 1, 2)
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     assert err < 2e-3, "relative max error %g" % err
+
+
+@pytest.mark.parametrize("gh,gw", [(2, 2), (2, 3)])
+def test_coords_branch_does_not_depend_on_the_batch_size(gh, gw):
+    """nrrt_coords_branch picks a different kernel for small batches (<= 64 tasks): the features of a task must be the same
+    bits either way, or a sharded planning run would differ from the single-GPU run."""
+    torch.manual_seed(6)
+    lib = _lib.load()
+    chans = [1, 64, 128, 256, 512]
+    ws = [(torch.randn(9, chans[i], chans[i + 1], device=DEV) * (0.5 / np.sqrt(9 * chans[i]))).contiguous() for i in range(4)]
+    bs = [(torch.randn(chans[i + 1], device=DEV) * 0.1).contiguous() for i in range(4)]
+    wp = (C.c_void_p * 4)(*[t.data_ptr() for t in ws])
+    bp = (C.c_void_p * 4)(*[t.data_ptr() for t in bs])
+    coords = (torch.rand(100, 1, gh, gw, device=DEV) * 500).contiguous()
+
+    def run(n):
+        feats = [torch.zeros(n, gh * gw, c, device=DEV) for c in chans[1:]]
+        fp = (C.c_void_p * 4)(*[t.data_ptr() for t in feats])
+        check(lib.nrrt_coords_branch(_p(coords), n, gh, gw, wp, bp, fp, _st()))
+        torch.cuda.synchronize()
+        return feats
+
+    big = run(100)
+    for n in (1, 3, 64):
+        small = run(n)
+        for a, b in zip(small, big):
+            assert torch.equal(a, b[:n]), "batch of %d differs from the batch of 100" % n
+    assert float(big[3].abs().max()) > 0
