@@ -29,6 +29,33 @@ def _pp(t, coff=0):
     return None if t is None else C.c_void_p(t.data_ptr() + coff * t.element_size())
 
 
+class PlateauScheduler(object):
+    """torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, factor=0.5, patience=2) as configure_optimizers() sets it up
+    (train.py:230-234; mode 'min', relative threshold 1e-4, no cooldown, min_lr 0): host logic, monitored on val_loss."""
+
+    def __init__(self, lr: float, factor: float = 0.5, patience: int = 2, threshold: float = 1e-4, min_lr: float = 0.0, eps: float = 1e-8):
+        self.lr, self.factor, self.patience, self.threshold, self.min_lr, self.eps = float(lr), factor, patience, threshold, min_lr, eps
+        self.best, self.num_bad_epochs = math.inf, 0
+
+    def step(self, metric: float) -> float:
+        if metric < self.best * (1.0 - self.threshold):
+            self.best, self.num_bad_epochs = float(metric), 0
+        else:
+            self.num_bad_epochs += 1
+        if self.num_bad_epochs > self.patience:
+            new_lr = max(self.lr * self.factor, self.min_lr)
+            if self.lr - new_lr > self.eps:
+                self.lr = new_lr
+            self.num_bad_epochs = 0
+        return self.lr
+
+    def state_dict(self):
+        return {"lr": self.lr, "best": self.best, "num_bad_epochs": self.num_bad_epochs}
+
+    def load_state_dict(self, d):
+        self.lr, self.best, self.num_bad_epochs = float(d["lr"]), float(d["best"]), int(d["num_bad_epochs"])
+
+
 class _Conv(object):
     """One convolution of the model: where its parameters live in the flat buffers and the layers that run it."""
 
@@ -69,7 +96,7 @@ class UNetTrainer(object):
         self.dp = (self.world > 1) if data_parallel is None else bool(data_parallel and self.world > 1)
         self.model = model
         self._tmp = {}
-        self._sched_best, self._sched_bad = math.inf, 0
+        self.scheduler = PlateauScheduler(self.lr)
         self._build_params(model)
         self._alloc()
 
@@ -550,16 +577,35 @@ class UNetTrainer(object):
         self.loss_and_grad(False)
         return self.loss_sum / self.M
 
-    def scheduler_step(self, val_loss: float, factor: float = 0.5, patience: int = 2, threshold: float = 1e-4):
-        """torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, factor=0.5, patience=2) on val_loss (train.py:230-234)."""
-        if val_loss < self._sched_best * (1.0 - threshold):
-            self._sched_best, self._sched_bad = val_loss, 0
-        else:
-            self._sched_bad += 1
-        if self._sched_bad > patience:
-            self.lr *= factor
-            self._sched_bad = 0
+    def scheduler_step(self, val_loss: float):
+        """ReduceLROnPlateau(factor 0.5, patience 2) on val_loss (train.py:230-234): call once per validation epoch."""
+        self.scheduler.lr = self.lr
+        self.lr = self.scheduler.step(float(val_loss))
         return self.lr
+
+    # -------------------------------------------------------------------------------------------------------- checkpoints
+    def state_dict(self):
+        """Everything a run needs to continue (what Lightning's ModelCheckpoint keeps next to the model's own state_dict): the flat
+        parameter buffer, Adam moments, BatchNorm running statistics, step counters, the loss-scale state, the rate and scheduler."""
+        return {"layout": [self.B, self.H, self.W, self.n_params], "params": self.params.clone(), "exp_avg": self.exp_avg.clone(),
+                "exp_avg_sq": self.exp_avg_sq.clone(), "scale_state": self.scale_state.clone(), "step_count": self.step_count,
+                "lr": self.lr, "scheduler": self.scheduler.state_dict(),
+                "bn": {name: (cv.bn[2].clone(), cv.bn[3].clone()) for name, cv in self.convs.items() if cv.bn is not None}}
+
+    def load_state_dict(self, d):
+        if int(d["layout"][3]) != self.n_params:
+            raise ValueError("checkpoint was written for a different parameter layout")
+        with torch.no_grad():
+            self.params.copy_(d["params"].to(self.dev))
+            self.exp_avg.copy_(d["exp_avg"].to(self.dev))
+            self.exp_avg_sq.copy_(d["exp_avg_sq"].to(self.dev))
+            self.scale_state.copy_(d["scale_state"].to(self.dev))
+            for name, (rm, rv) in d["bn"].items():
+                self.convs[name].bn[2].copy_(rm.to(self.dev))
+                self.convs[name].bn[3].copy_(rv.to(self.dev))
+        self.step_count, self.lr = int(d["step_count"]), float(d["lr"])
+        self.scheduler.load_state_dict(d["scheduler"])
+        self._refresh_weights()
 
     def flops_per_step(self):
         """Algorithmic tensor-core FLOPs of one training step: forward + data gradient + weight gradient of every convolution

@@ -155,3 +155,27 @@ def test_small_images_match_the_oracle():
     errs = {k: float((grads[k] - ref).norm() / ref.norm()) for k, ref in ograds.items()}
     bad = {k: round(e, 4) for k, e in errs.items() if e > (0.25 if _encoder(k) else 2.5e-2)}
     assert not bad, bad
+
+
+def test_checkpoint_resume():
+    """UNetTrainer.state_dict / load_state_dict: a fresh trainer that loads a checkpoint holds the same parameters, optimizer
+    moments, running statistics, counters and loss scale, and its next step moves the weights like the original's next step."""
+    from mgr_sampling_cnn_b200 import train, trainer
+    model, tr, x, y, coords, masks, g = _setup()
+    batch = (torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(coords))
+    for _ in range(2):
+        tr.training_step(batch)
+    tr.lr = 7e-4
+    ck = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in tr.state_dict().items()}        # as torch.save / load would hand it back
+    torch.manual_seed(99)
+    tr2 = trainer.UNetTrainer(train.UNet_cooler(), 2, 512, 512, DEV)                               # different random init
+    tr2.load_state_dict(ck)
+    assert torch.equal(tr2.params, tr.params) and torch.equal(tr2.exp_avg_sq, tr.exp_avg_sq) and torch.equal(tr2.params_h, tr.params_h)
+    assert tr2.scale_state.tolist() == tr.scale_state.tolist() and tr2.lr == 7e-4 and tr2.step_count == 2
+    cv = "enc2.1.c2"
+    assert torch.equal(tr2.convs[cv].bn[2], tr.convs[cv].bn[2]) and torch.equal(tr2.convs[cv].wd, tr.convs[cv].wd)
+    before = tr.params.clone()
+    l1, l2 = float(tr.training_step(batch).item()), float(tr2.training_step(batch).item())
+    assert abs(l1 - l2) <= 1e-3 * abs(l1)                   # same weights, same batch (reductions are atomic: not bit-identical)
+    d1, d2 = tr.params - before, tr2.params - before
+    assert float((d1 - d2).abs().max()) <= 2.0 * 7e-4 and float((d1 * d2 < 0).float().mean()) < 0.05

@@ -33,3 +33,23 @@ def test_trainer_rejects_sizes_the_kernels_do_not_cover():
         pytest.skip("the size check sits behind the CUDA check")
     with pytest.raises(ValueError):
         trainer.UNetTrainer(train.UNet_cooler(), 1, 200, 256)
+
+
+def test_plateau_scheduler_matches_torch():
+    """trainer.PlateauScheduler == torch.optim.lr_scheduler.ReduceLROnPlateau(factor=0.5, patience=2) (train.py:230-234)."""
+    from mgr_sampling_cnn_b200.trainer import PlateauScheduler
+    rng = np.random.default_rng(1)
+    for trial in range(5):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.Adam([p], lr=1e-3)
+        ref = torch.optim.lr_scheduler.ReduceLROnPlateau(opt, factor=0.5, patience=2)
+        mine = PlateauScheduler(1e-3)
+        v = 1.0
+        for epoch in range(40):
+            v = v * (0.97 if rng.random() < 0.4 else 1.0 + 0.02 * rng.random())
+            ref.step(v)
+            assert abs(mine.step(v) - opt.param_groups[0]["lr"]) <= 1e-15, (trial, epoch)
+        d = mine.state_dict()
+        again = PlateauScheduler(123.0)
+        again.load_state_dict(d)
+        assert again.step(v * 2) == mine.step(v * 2)
