@@ -5,6 +5,7 @@ signature and file convention (reads nothing but its arguments, writes the mask 
 The A* search itself (generate_paths.py:11-74) is engine.grid_path_lengths (lengths / task filter); a path to draw is
 supplied by the caller.  There is no CPU fallback."""
 import ctypes as C
+import glob
 import os
 
 import numpy as np
@@ -13,6 +14,7 @@ import torch
 from . import _lib
 from .engine import _dev, _ptr, _require_cuda, _stream_ptr, check
 
+MAPS_DIRECTORY = 'maps/start_finish/*.png'   # the reference hard-codes its author's directory (generate_paths.py:8): set it before use
 CIRCLE_RADIUS = 10       # generate_paths.py:131
 BLUR_KSIZE = 33          # generate_paths.py:134
 BLUR_SIGMA = 3.0         # generate_paths.py:134 passes cv2.BORDER_WRAP (= 3) in the sigmaX position
@@ -69,3 +71,61 @@ def visualize_path(occ_map: np.ndarray, path: list, directory: str):
         import cv2  # only the PNG writer; the arithmetic is the kernel's
         cv2.imwrite(out, mask)
     return mask
+
+
+def astar(image: np.ndarray, start: tuple, finish: tuple):
+    """generate_paths.astar (generate_paths.py:11-74) for one task on the device: a shortest 8-connected path [(y, x), ...] from
+    start to finish (no corner cutting), or None.  Same length and step kinds as the reference's path; among equal-cost paths the
+    cells may differ (include/nrrt.h: nrrt_grid_paths_ex)."""
+    from . import engine
+    device = _require_cuda(None)
+    image = np.asarray(image)
+    bits = engine.pack_occupancy(image[None], 2, device)
+    _, _, paths, n = engine.grid_paths(bits, [0], [list(start)], [list(finish)], image.shape, path_cap=image.shape[0] * image.shape[1])
+    n = int(n[0])
+    if n <= 0:
+        return None
+    return [tuple(int(v) for v in p) for p in paths[0, :n].cpu().numpy()]
+
+
+def get_blank_maps_list() -> list:
+    return sorted(glob.glob(MAPS_DIRECTORY))
+
+
+def get_from_string(path: str, start: str, finish: str) -> str:
+    return path[path.find(start) + 3:path.find(finish)]
+
+
+def get_start_finish_coordinates(path: str) -> tuple:
+    x_start = int(get_from_string(path, "_sx", "_sy"))
+    y_start = int(get_from_string(path, "_sy", "_fx"))
+    x_finish = int(get_from_string(path, "_fx", "_fy"))
+    y_finish = int(get_from_string(path, "_fy", ".png"))
+    return (y_start, x_start), (y_finish, x_finish)
+
+
+def generate_paths(batch: int = 256):
+    """generate_paths.generate_paths (generate_paths.py:100-115): for every task file, the A* path and its mask under paths/; task
+    files without a path are deleted.  Files of one map shape are processed `batch` at a time through the batched kernels."""
+    import cv2  # PNG reader / writer only
+    from . import engine
+    from .ThreeD_generate_paths import _by_shape
+    device = _require_cuda(None)
+    for chunk, maps in _by_shape(get_blank_maps_list(), lambda f: cv2.imread(f, 0), batch):
+        sf = [get_start_finish_coordinates(f) for f in chunk]
+        starts, goals = np.array([a for a, _ in sf], np.int32), np.array([b for _, b in sf], np.int32)
+        t2m = np.arange(len(chunk), dtype=np.int32)
+        bits = engine.pack_occupancy(maps, 2, device)
+        _, _, paths, n = engine.grid_paths(bits, t2m, starts, goals, maps.shape[1:], path_cap=4 * max(maps.shape[1:]))
+        n_host = n.cpu().numpy()
+        if (n_host < 0).any():
+            raise _lib.NrrtError("a path is longer than the path buffer")
+        masks = path_masks(maps, t2m, paths, n.clamp(min=0), device).cpu().numpy()
+        for f, k, m in zip(chunk, n_host, masks):
+            if k == 0:
+                print("COULDN'T FIND A PATH FOR THIS EXAMPLE:", f)
+                os.remove(f)
+                continue
+            out = f.replace('start_finish', 'paths')
+            os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
+            cv2.imwrite(out, m)

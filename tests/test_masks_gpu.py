@@ -74,3 +74,46 @@ def test_enlarge_3d_batched_vs_oracle_80():
         got = ep.enlarge_paths(occs, t2m, vols, layers=layers).cpu().numpy()
         for b in range(6):
             assert np.array_equal(got[b], mo.enlarge_3d(occs[t2m[b]], vols[b], layers)), "task %d layers %d" % (b, layers)
+
+
+def test_generate_paths_file_pipeline(tmp_path):
+    """generate_paths.generate_paths() / ThreeD_generate_paths.generate_paths() on task files: A* path -> mask / path volume next
+    to the task file, unreachable tasks deleted (generate_paths.py:100-115, ThreeD_generate_paths.py:125-138)."""
+    import cv2
+    from mgr_sampling_cnn_b200 import ThreeD_generate_paths as gp3
+    g = np.load(os.path.join(GOLDEN, "astar2d.npz"))
+    d2 = tmp_path / "maps" / "start_finish"
+    d2.mkdir(parents=True)
+    names = {}
+    for i in (0, 2, 20, 22):          # two 512 x 512 tasks, an unreachable pocket, a 16 x 16 wall
+        occ, s, f = g[f"occ_{i}"], g[f"start_{i}"], g[f"goal_{i}"]
+        if occ.shape[0] < 64:
+            big = np.zeros((64, 64), np.uint8)
+            big[:occ.shape[0], :occ.shape[1]] = occ
+            occ = big
+        name = str(d2 / f"map_{i}_path0_sx{s[1]}_sy{s[0]}_fx{f[1]}_fy{f[0]}.png")
+        cv2.imwrite(name, occ)
+        names[i] = (name, occ, tuple(int(v) for v in s), tuple(int(v) for v in f), bool(g[f"reached_{i}"]))
+    gp.MAPS_DIRECTORY = str(d2 / "*.png")
+    gp.generate_paths(batch=3)
+    for i, (name, occ, s, f, reached) in names.items():
+        out = name.replace("start_finish", "paths")
+        if not reached:
+            assert not os.path.exists(name) and not os.path.exists(out)
+            continue
+        path = gp.astar(occ, s, f)
+        assert path[0] == s and path[-1] == f and len(path) == len(g[f"path_{i}"])
+        assert np.array_equal(cv2.imread(out, 0), mo.mask_2d(occ, np.array(path)))
+    g3 = np.load(os.path.join(GOLDEN, "astar3d.npz"))
+    d3 = tmp_path / "3D_maps" / "start_finish"
+    d3.mkdir(parents=True)
+    for i in (0, 12):                 # a task on an 80^3 map, the walled-in goal
+        s, f = g3[f"start_{i}"], g3[f"goal_{i}"]
+        np.save(str(d3 / f"map_{i}_path0_sx{s[0]}_sy{s[1]}_sz{s[2]}_fx{f[0]}_fy{f[1]}_fz{f[2]}.npy"), g3[f"occ_{i}"])
+    gp3.MAPS_DIRECTORY = str(d3 / "*.npy")
+    gp3.generate_paths()
+    left = sorted(os.listdir(d3))
+    assert len(left) == 1 and left[0].startswith("map_0_")
+    vol = np.load(str(tmp_path / "3D_maps" / "paths" / left[0]))
+    assert vol.dtype == g3["occ_0"].dtype and int((vol == 255).sum()) == len(g3["path_0"]) and set(np.unique(vol)) <= {0, 255}
+    assert gp3.astar(g3["occ_12"], tuple(g3["start_12"]), tuple(g3["goal_12"])) is None
