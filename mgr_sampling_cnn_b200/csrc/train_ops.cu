@@ -86,13 +86,25 @@ __global__ void __launch_bounds__(kEw) relu_bwd_sum_kernel(const __half* dy, lon
 __global__ void __launch_bounds__(kEw) bn_stats_kernel(const __half* z, long long z_cs, double* sum, double* sumsq, long long M, int C) {
     const Walk w(C);
     float acc[2][8] = {};
-    if (w.active)
-        for (long long p = (long long)blockIdx.x * w.ppb + w.lane_p; p < M; p += (long long)gridDim.x * w.ppb) {
+    if (w.active) {
+        const long long stride = (long long)gridDim.x * w.ppb;
+        long long p = (long long)blockIdx.x * w.ppb + w.lane_p;
+        for (; p + 3 * stride < M; p += 4 * stride) {          // four independent 16-byte loads in flight per thread
+            float a[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8(z + (p + u * stride) * z_cs + w.chunk * 8, a[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc[0][j] += a[u][j]; acc[1][j] += a[u][j] * a[u][j]; }
+        }
+        for (; p < M; p += stride) {
             float a[8];
             load8(z + p * z_cs + w.chunk * 8, a);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { acc[0][j] += a[j]; acc[1][j] += a[j] * a[j]; }
         }
+    }
     double* const dst[2] = {sum, sumsq};
     reduce_channels<2, double>(w, acc, dst, C);
 }
@@ -511,6 +523,10 @@ int ew_grid(long long M, int C) {
     const long long cap = 148 * 8;
     return (int)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
+int ew_grid_red(long long M, int C) {   // reduction kernels: fewer, longer blocks (every block ends with C atomics per accumulator)
+    const int g = ew_grid(M, C);
+    return g < 148 * 3 ? g : 148 * 3;
+}
 size_t ew_smem(int C) {
     const int chunks = C / 8;
     const int ppb = kEw / chunks > 0 ? kEw / chunks : 1;
@@ -541,7 +557,7 @@ extern "C" int nrrt_bn_train_forward(const void* z, int64_t z_cs, int64_t pixels
     NRRT_REQUIRE(z_cs % 8 == 0 && y_cs % 8 == 0 && res_cs % 8 == 0, "channel strides must be multiples of 8");
     cudaStream_t st = (cudaStream_t)stream;
     NRRT_CUDA_TRY(cudaMemsetAsync(work, 0, 2 * (size_t)c * sizeof(double), st));
-    bn_stats_kernel<<<ew_grid(pixels, c), kEw, ew_smem(c), st>>>((const __half*)z, z_cs, work, work + c, pixels, c);
+    bn_stats_kernel<<<ew_grid_red(pixels, c), kEw, ew_smem(c), st>>>((const __half*)z, z_cs, work, work + c, pixels, c);
     bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(work, work + c, pixels, gamma, beta, eps, momentum, running_mean, running_var,
                                                        save_mean, save_rstd, scale_shift, scale_shift + c, c);
     affine_act_kernel<<<ew_grid(pixels, c), kEw, 0, st>>>((const __half*)z, z_cs, scale_shift, scale_shift + c, (const __half*)res, res_cs,
@@ -573,7 +589,7 @@ extern "C" int nrrt_bn_train_backward(const void* dy, int64_t dy_cs, const void*
     NRRT_REQUIRE(dy_cs % 8 == 0 && y_cs % 8 == 0 && z_cs % 8 == 0 && dz_cs % 8 == 0 && g_cs % 8 == 0, "channel strides must be multiples of 8");
     cudaStream_t st = (cudaStream_t)stream;
     NRRT_CUDA_TRY(cudaMemsetAsync(work, 0, 2 * (size_t)c * sizeof(double), st));
-    bn_bwd_reduce_kernel<<<ew_grid(pixels, c), kEw, ew_smem(c), st>>>((const __half*)dy, dy_cs, (const __half*)y_mask, y_cs, (const __half*)z,
+    bn_bwd_reduce_kernel<<<ew_grid_red(pixels, c), kEw, ew_smem(c), st>>>((const __half*)dy, dy_cs, (const __half*)y_mask, y_cs, (const __half*)z,
                                                                       z_cs, save_mean, save_rstd, work, work + c, pixels, c);
     bn_bwd_apply_kernel<<<ew_grid(pixels, c), kEw, 0, st>>>((const __half*)dy, dy_cs, (const __half*)y_mask, y_cs, (const __half*)z, z_cs,
                                                             save_mean, save_rstd, gamma, work, work + c, (__half*)dz, dz_cs, (__half*)g_out,
