@@ -505,6 +505,11 @@ int nrrt_relu_bwd_sum(const void* dy, int64_t dy_cs, const void* y, int64_t y_cs
 int nrrt_bn_train_forward(const void* z, int64_t z_cs, int64_t pixels, int c, const float* gamma, const float* beta, float eps,
                           float momentum, float* running_mean, float* running_var, const void* res, int64_t res_cs, int relu, void* y,
                           int64_t y_cs, float* save_mean, float* save_rstd, float* scale_shift, double* work, void* stream);
+/* The same layer in eval mode (validation_step under Lightning's model.eval(), train.py:212-217): running statistics, nothing
+ * updated.  scale_shift: fp32 [2c] scratch. */
+int nrrt_bn_eval_forward(const void* z, int64_t z_cs, int64_t pixels, int c, const float* gamma, const float* beta, float eps,
+                         const float* running_mean, const float* running_var, const void* res, int64_t res_cs, int relu, void* y,
+                         int64_t y_cs, float* scale_shift, void* stream);
 /* Its backward: g = dy masked by y_mask > 0 (NULL = none); dbeta += sum g; dgamma += sum g * xhat;
  * dz = gamma * rstd * (g - mean(g) - xhat * mean(g * xhat)); g_out (optional) = g, the gradient of the residual branch. */
 int nrrt_bn_train_backward(const void* dy, int64_t dy_cs, const void* y_mask, int64_t y_cs, const void* z, int64_t z_cs, int64_t pixels,

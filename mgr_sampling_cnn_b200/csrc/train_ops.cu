@@ -566,6 +566,31 @@ extern "C" int nrrt_bn_train_forward(const void* z, int64_t z_cs, int64_t pixels
     return NRRT_OK;
 }
 
+namespace {
+__global__ void bn_eval_params_kernel(const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                                      float* scale, float* shift, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float sc = gamma[c] / sqrtf(running_var[c] + eps);
+    scale[c] = sc;
+    shift[c] = beta[c] - running_mean[c] * sc;
+}
+}  // namespace
+
+extern "C" int nrrt_bn_eval_forward(const void* z, int64_t z_cs, int64_t pixels, int c, const float* gamma, const float* beta, float eps,
+                                    const float* running_mean, const float* running_var, const void* res, int64_t res_cs, int relu, void* y,
+                                    int64_t y_cs, float* scale_shift, void* stream) {
+    EW_CHECK(c);
+    NRRT_REQUIRE(z && y && gamma && beta && running_mean && running_var && scale_shift && pixels >= 1, "null pointer");
+    NRRT_REQUIRE(z_cs % 8 == 0 && y_cs % 8 == 0 && res_cs % 8 == 0, "channel strides must be multiples of 8");
+    cudaStream_t st = (cudaStream_t)stream;
+    bn_eval_params_kernel<<<(c + 127) / 128, 128, 0, st>>>(gamma, beta, running_mean, running_var, eps, scale_shift, scale_shift + c, c);
+    affine_act_kernel<<<ew_grid(pixels, c), kEw, 0, st>>>((const __half*)z, z_cs, scale_shift, scale_shift + c, (const __half*)res, res_cs,
+                                                          relu, (__half*)y, y_cs, pixels, c);
+    NRRT_CUDA_TRY(cudaGetLastError());
+    return NRRT_OK;
+}
+
 extern "C" int nrrt_bn_train_backward(const void* dy, int64_t dy_cs, const void* y_mask, int64_t y_cs, const void* z, int64_t z_cs,
                                       int64_t pixels, int c, const float* gamma, const float* save_mean, const float* save_rstd,
                                       void* dz, int64_t dz_cs, void* g_out, int64_t g_cs, float* dgamma, float* dbeta, double* work,

@@ -95,6 +95,7 @@ class UNetTrainer(object):
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.dp = (self.world > 1) if data_parallel is None else bool(data_parallel and self.world > 1)
         self.model = model
+        self.training = True        # False: BatchNorm layers use their running statistics (validation_step)
         self._tmp = {}
         self.scheduler = PlateauScheduler(self.lr)
         self._build_params(model)
@@ -318,6 +319,12 @@ class UNetTrainer(object):
     def _bn_fwd(self, cv, z, y, y_coff, stats, res=None, res_coff=0, relu=True):
         c = cv.cout
         pixels = z.shape[0] * z.shape[1] * z.shape[2]
+        if not self.training:   # eval mode: running statistics, nothing updated, nothing saved for a backward
+            _lib.count_launch(2)
+            check(self.lib.nrrt_bn_eval_forward(_pp(z), c, pixels, c, _pp(self.params, cv.bn[0]), _pp(self.params, cv.bn[1]), BN_EPS,
+                                                _pp(cv.bn[2]), _pp(cv.bn[3]), _pp(res, res_coff), res.shape[-1] if res is not None else 0,
+                                                1 if relu else 0, _pp(y, y_coff), y.shape[-1], _pp(self.bn_ss), self._st()))
+            return
         _lib.count_launch(3)
         check(self.lib.nrrt_bn_train_forward(_pp(z), c, pixels, c, _pp(self.params, cv.bn[0]), _pp(self.params, cv.bn[1]), BN_EPS, BN_MOMENTUM,
                                              _pp(cv.bn[2]), _pp(cv.bn[3]), _pp(res, res_coff), res.shape[-1] if res is not None else 0,
@@ -569,10 +576,14 @@ class UNetTrainer(object):
         return self.loss_sum / self.M
 
     def validation_step(self, batch, batch_idx=0, masks_u8=None):
-        """UNet_cooler.validation_step (train.py:212-217).  (Like Lightning under model.eval(), a validation pass should use the
-        running statistics: run it through the exported model's forward; this method evaluates with batch statistics.)"""
+        """UNet_cooler.validation_step (train.py:212-217) as Lightning runs it: model.eval(), i.e. BatchNorm with its running
+        statistics, no gradient, nothing updated.  Returns the loss as a device scalar."""
         x, y, coords = batch
-        self.forward(x.to(self.dev, torch.float32).contiguous(), coords.to(self.dev))
+        self.training = False
+        try:
+            self.forward(x.to(self.dev, torch.float32).contiguous(), coords.to(self.dev))
+        finally:
+            self.training = True
         self.set_targets(masks_u8=masks_u8, target=None if y is None else y.to(self.dev, torch.float32))
         self.loss_and_grad(False)
         return self.loss_sum / self.M

@@ -72,7 +72,7 @@ step = n_steps
 torch.cuda.synchronize()
 print("trained %d steps in %.1f s (%.1f samples/s)" % (step, time.time() - t0, step * B / (time.time() - t0)))
 tr.export_to(model)
-# diagnostic: held-out loss with batch statistics (trainer) and with the running statistics (exported model, inference kernels)
+# diagnostic: held-out loss in eval mode through the trainer's graph (validation_step) and through the exported model (inference kernels)
 wl_val, masks_val = training_set(9000, 3)
 model_dev = model.to(dev).eval()
 lt, le = [], []
@@ -84,7 +84,7 @@ for i in range(0, 30, B):
     with torch.no_grad():
         logits = model_dev(x, wl_val.coords[idx])
     le.append(float(torch.nn.functional.binary_cross_entropy_with_logits(logits[:, 0], tr.target).item()))
-print("held-out loss: batch statistics %.4f, running statistics (exported model) %.4f" % (np.mean(lt), np.mean(le)))
+print("held-out loss: validation_step (eval mode) %.4f, exported model through the inference kernels %.4f" % (np.mean(lt), np.mean(le)))
 model = model.cpu()
 del tr
 torch.cuda.empty_cache()

@@ -179,3 +179,23 @@ def test_checkpoint_resume():
     assert abs(l1 - l2) <= 1e-3 * abs(l1)                   # same weights, same batch (reductions are atomic: not bit-identical)
     d1, d2 = tr.params - before, tr2.params - before
     assert float((d1 - d2).abs().max()) <= 2.0 * 7e-4 and float((d1 * d2 < 0).float().mean()) < 0.05
+
+
+def test_validation_step_is_eval_mode():
+    """validation_step = the loss under model.eval() (running statistics), like Lightning's validation loop: it must equal the
+    fp32 oracle's eval-mode loss on the exported weights and must not move any state."""
+    import torch.nn.functional as F
+    from oracle import cnn_oracle
+    model, tr, x, y, coords, masks, g = _setup()
+    batch = (torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(coords))
+    for _ in range(3):
+        tr.training_step(batch)
+    before = (tr.params.clone(), tr.convs["enc1.0.c1"].bn[2].clone(), tr.scale_state.clone())
+    val = float(tr.validation_step(batch).item())
+    assert torch.equal(tr.params, before[0]) and torch.equal(tr.convs["enc1.0.c1"].bn[2], before[1]) and torch.equal(tr.scale_state, before[2])
+    tr.export_to(model)
+    with torch.no_grad():
+        ref = float(F.binary_cross_entropy_with_logits(cnn_oracle.forward(model.state_dict(), batch[0], batch[2], 2), batch[1]))
+    assert abs(val - ref) <= 1e-2 * abs(ref), (val, ref)
+    train_mode = float(tr.training_step(batch).item())           # batch statistics give a different number after three steps
+    assert abs(train_mode - val) > 1e-4
