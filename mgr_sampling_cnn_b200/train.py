@@ -2,8 +2,9 @@
 
 Same zero-argument constructor, same sub-module names and therefore the same 268-key `state_dict` (including the unused
 ResNet stem/fc under `base_model.*`), same `forward(x, coords)` contract: x (B,3,H,W) fp32, coords (B,1,2,2) fp32 ->
-logits (B,1,H,W) fp32.  forward() runs the B200 kernels (cnn.UNetPlan); training and the Lightning hooks are out of
-scope; `MapsDataset` / `MapsDataModule` read the reference's task files (the demos' and the harness's input).  The reference asks torchvision for `pretrained=True` ImageNet weights, which need
+logits (B,1,H,W) fp32.  forward() runs the B200 kernels (cnn.UNetPlan); `training_step` / `configure_optimizers` and the fit loop
+live in trainer.UNetTrainer (`test_training()` below drives it like train.py:273-315); `MapsDataset` / `MapsDataModule` read the
+reference's task files.  The reference asks torchvision for `pretrained=True` ImageNet weights, which need
 a download; here the encoder is random-init (BASELINE.json) and trained weights arrive through `load_state_dict`.
 """
 import os
@@ -125,3 +126,17 @@ class UNet_cooler(CudaForwardMixin, nn.Module):
             nn.Conv2d(128, 64, kernel_size=3, stride=1, padding=1), nn.ReLU(inplace=True),
         )
         self.final_conv = nn.Conv2d(64, 1, kernel_size=1)
+
+
+def test_training(data_module=None, max_epochs: int = 100, device="cuda:0", log=print):
+    """train.py:273-315 without Lightning / Neptune: fit UNet_cooler on the data module (batch_size 3), early stopping on val_loss
+    (patience 10), ReduceLROnPlateau, the best weights saved to MODEL_PATH.  Returns (model, history)."""
+    from . import trainer
+    data_module = data_module or MapsDataModule()
+    data_module.setup("fit")
+    model = UNet_cooler()
+    sample = data_module.train_dataset[0][0]
+    tr = trainer.UNetTrainer(model, data_module._batch_size, int(sample.shape[-2]), int(sample.shape[-1]), device)
+    history = tr.fit(data_module.train_dataloader(), data_module.val_dataloader(), max_epochs=max_epochs, patience=10, log=log)
+    torch.save(model.state_dict(), MODEL_PATH)
+    return model, history

@@ -594,6 +594,46 @@ class UNetTrainer(object):
         self.lr = self.scheduler.step(float(val_loss))
         return self.lr
 
+    def fit(self, train_loader, val_loader=None, max_epochs: int = 100, patience: int = 10, log=None):
+        """The loop `pl.Trainer(max_epochs=100, callbacks=[ModelCheckpoint, EarlyStopping(monitor='val_loss', patience=10)]).fit(...)`
+        runs around the model (train.py:289-310): per epoch every training batch through training_step, the validation set through
+        validation_step (eval mode), ReduceLROnPlateau on the mean val_loss, the best state kept, early stop after `patience`
+        epochs without improvement; then the best state is restored and exported into the module.  Loaders yield
+        (x, y, coords) like MapsDataset; batches whose size is not the trainer's are skipped (the buffers are sized once).
+        Returns the history [(epoch, train_loss, val_loss, lr), ...]."""
+        best, best_state, bad, history = math.inf, None, 0, []
+        for epoch in range(max_epochs):
+            losses = []
+            for batch in train_loader:
+                if batch[0].shape[0] != self.B:
+                    continue
+                losses.append(self.training_step(batch))
+            train_loss = float(torch.stack(losses).mean().item()) if losses else float("nan")
+            val_loss = train_loss
+            if val_loader is not None:
+                vals = [self.validation_step(b) for b in val_loader if b[0].shape[0] == self.B]
+                if vals:
+                    val_loss = float(torch.stack(vals).mean().item())
+            lr = self.scheduler_step(val_loss)
+            history.append((epoch, train_loss, val_loss, lr))
+            if log:
+                log("epoch %d: train_loss %.5f val_loss %.5f lr %g" % (epoch, train_loss, val_loss, lr))
+            if val_loss < best:
+                best, bad = val_loss, 0
+                best_state = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in self.state_dict().items()}
+                best_state["bn"] = {k: (a.cpu(), b.cpu()) for k, (a, b) in best_state["bn"].items()}
+            else:
+                bad += 1
+                if bad >= patience:
+                    break
+        if best_state is not None:
+            keep_lr, keep_sched = self.lr, self.scheduler.state_dict()
+            self.load_state_dict(best_state)
+            self.lr = keep_lr
+            self.scheduler.load_state_dict(keep_sched)
+        self.export_to(self.model)
+        return history
+
     # -------------------------------------------------------------------------------------------------------- checkpoints
     def state_dict(self):
         """Everything a run needs to continue (what Lightning's ModelCheckpoint keeps next to the model's own state_dict): the flat

@@ -199,3 +199,23 @@ def test_validation_step_is_eval_mode():
     assert abs(val - ref) <= 1e-2 * abs(ref), (val, ref)
     train_mode = float(tr.training_step(batch).item())           # batch statistics give a different number after three steps
     assert abs(train_mode - val) > 1e-4
+
+
+def test_fit_loop_early_stopping_and_best_state():
+    """UNetTrainer.fit: epochs over loaders, eval-mode validation, plateau scheduler, early stopping, best state restored and
+    exported (the loop Lightning runs for train.py:289-310)."""
+    from mgr_sampling_cnn_b200 import train, trainer
+    x, y, coords, masks, g = H.load_train_batch()
+    data = [(torch.from_numpy(x[i:i + 1]), torch.from_numpy(y[i:i + 1]), torch.from_numpy(coords[i:i + 1])) for i in (0, 1)]
+    torch.manual_seed(0)
+    model = train.UNet_cooler()
+    tr = trainer.UNetTrainer(model, 1, 512, 512, DEV)
+    ragged = data + [(torch.zeros(2, 3, 512, 512), torch.zeros(2, 1, 512, 512), torch.zeros(2, 1, 2, 2))]   # wrong batch size: skipped
+    hist = tr.fit(ragged * 3, data, max_epochs=4, patience=2)
+    assert 1 <= len(hist) <= 4 and all(np.isfinite(h[1]) and np.isfinite(h[2]) for h in hist)
+    assert tr.step_count >= 6                                          # 6 usable training batches per epoch
+    best = min(h[2] for h in hist)
+    val = float(np.mean([float(tr.validation_step(b).item()) for b in data]))
+    assert abs(val - best) <= 2e-2 * best                              # the restored state is the best epoch's
+    out = model.to(DEV).eval()(data[0][0].to(DEV), data[0][2].to(DEV))   # ... and it is what export_to left in the module
+    assert bool(torch.isfinite(out).all())
