@@ -60,7 +60,9 @@ struct WgLayout {
     static constexpr uint32_t off_b = kNA * a_stage;
     static constexpr uint32_t off_bar = off_b + kNB * b_stage;
     static constexpr uint32_t off_tmem = off_bar + (2 * kNA + 2 * kNB + 1) * 8;
-    static constexpr uint32_t total = off_tmem + 16 + 1024;
+    // at least 120 KB: two CTAs must never share an SM (each allocates all 512 tensor-memory columns; the second would wait forever)
+    static constexpr uint32_t need = off_tmem + 16 + 1024;
+    static constexpr uint32_t total = need > 120u * 1024u ? need : 120u * 1024u;
 };
 
 // MN-major SWIZZLE_128B operand descriptor (channels-last tiles: a K row = one pixel = 128 bytes of 64 channels; 8 pixels
