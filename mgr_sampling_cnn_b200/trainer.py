@@ -96,6 +96,7 @@ class UNetTrainer(object):
         self.dp = (self.world > 1) if data_parallel is None else bool(data_parallel and self.world > 1)
         self.model = model
         self.training = True        # False: BatchNorm layers use their running statistics (validation_step)
+        self.bn_momentum = BN_MOMENTUM
         self._tmp = {}
         self.scheduler = PlateauScheduler(self.lr)
         self._build_params(model)
@@ -326,7 +327,7 @@ class UNetTrainer(object):
                                                 1 if relu else 0, _pp(y, y_coff), y.shape[-1], _pp(self.bn_ss), self._st()))
             return
         _lib.count_launch(3)
-        check(self.lib.nrrt_bn_train_forward(_pp(z), c, pixels, c, _pp(self.params, cv.bn[0]), _pp(self.params, cv.bn[1]), BN_EPS, BN_MOMENTUM,
+        check(self.lib.nrrt_bn_train_forward(_pp(z), c, pixels, c, _pp(self.params, cv.bn[0]), _pp(self.params, cv.bn[1]), BN_EPS, self.bn_momentum,
                                              _pp(cv.bn[2]), _pp(cv.bn[3]), _pp(res, res_coff), res.shape[-1] if res is not None else 0,
                                              1 if relu else 0, _pp(y, y_coff), y.shape[-1], _pp(stats[0]), _pp(stats[1]), _pp(self.bn_ss),
                                              _pp(self.bn_work), self._st()))
@@ -594,6 +595,20 @@ class UNetTrainer(object):
         self.lr = self.scheduler.step(float(val_loss))
         return self.lr
 
+    def recalibrate_batchnorm(self, batches):
+        """Replace the BatchNorm running statistics by the plain average of the batch statistics over `batches` (an iterable of
+        (x, coords)), weights untouched.  With 3 samples per step the exponential average (momentum 0.1) that training leaves
+        behind is a noisy, lagging estimate; the eval-mode model (what the planner runs) is only as good as these numbers."""
+        k = 0
+        try:
+            for x, coords in batches:
+                k += 1
+                self.bn_momentum = 1.0 / k          # running = running * (1 - 1/k) + batch / k: the cumulative mean
+                self.forward(x.to(self.dev, torch.float32).contiguous(), coords.to(self.dev))
+        finally:
+            self.bn_momentum = BN_MOMENTUM
+        return k
+
     def fit(self, train_loader, val_loader=None, max_epochs: int = 100, patience: int = 10, log=None):
         """The loop `pl.Trainer(max_epochs=100, callbacks=[ModelCheckpoint, EarlyStopping(monitor='val_loss', patience=10)]).fit(...)`
         runs around the model (train.py:289-310): per epoch every training batch through training_step, the validation set through
@@ -691,7 +706,7 @@ def generated_training_set(n_maps: int, first_map: int = 5000, size: int = 512, 
 
 
 def fit_on_generated(model, n_maps: int, steps: int, first_map: int = 5000, batch: int = 3, size: int = 512, device="cuda:0", seed: int = 0,
-                     log=None):
+                     log=None, schedule: str = "steps", recalibrate: int = 64):
     """Train `model` (UNet_cooler) for `steps` optimisation steps of `batch` random samples of a generated training set; the
     learning rate is halved at 60 % and 80 % of the run (the reference halves it on validation plateaus, train.py:230).  The
     trained parameters and running statistics are written back into `model`.  Returns a dict of run statistics."""
@@ -707,7 +722,10 @@ def fit_on_generated(model, n_maps: int, steps: int, first_map: int = 5000, batc
     run, curve = [], []
     t0 = time.time()
     for step in range(1, steps + 1):
-        tr.lr = 1e-3 if step <= 0.6 * steps else (5e-4 if step <= 0.8 * steps else 2.5e-4)
+        if schedule == "cosine":   # 100 warm-up steps, then a cosine from 1e-3 down to 2e-5
+            tr.lr = 1e-3 * min(1.0, step / 100.0) * max(0.02, 0.5 * (1.0 + math.cos(math.pi * step / steps)))
+        else:
+            tr.lr = 1e-3 if step <= 0.6 * steps else (5e-4 if step <= 0.8 * steps else 2.5e-4)
         idx = torch.from_numpy(rng.choice(n, batch, replace=False)).to(dev)
         occ = wl.occ_maps[wl.task_to_map[idx].long()]
         x = (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()      # MapsDataset's image tensor (train.py:41-44)
@@ -717,9 +735,25 @@ def fit_on_generated(model, n_maps: int, steps: int, first_map: int = 5000, batc
             run = []
             if log:
                 log("step %d: mean loss %.4f, lr %g, loss scale %g" % (step, curve[-1][1], tr.lr, float(tr.scale_state[0].item())))
+    def sample():
+        idx = torch.from_numpy(rng.choice(n, batch, replace=False)).to(dev)
+        occ = wl.occ_maps[wl.task_to_map[idx].long()]
+        return idx, (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()
+
+    def eval_loss(k=16):
+        vals = []
+        for _ in range(k):
+            idx, x = sample()
+            vals.append(tr.validation_step((x, None, wl.coords[idx]), masks_u8=masks[idx]))
+        return float(torch.stack(vals).mean().item())
+
+    eval_before = eval_loss()
+    if recalibrate > 0:
+        tr.recalibrate_batchnorm(((x, wl.coords[idx]) for idx, x in (sample() for _ in range(recalibrate))))
+    eval_after = eval_loss()
     torch.cuda.synchronize(dev)
     t_train = time.time() - t0
     taken = int(tr.scale_state[3].item())
     tr.export_to(model)
-    return {"train_tasks": n, "train_maps": n_maps, "steps": steps, "steps_taken": taken, "batch": batch, "data_seconds": t_data,
+    return {"eval_mode_loss_before_recalibration": eval_before, "eval_mode_loss": eval_after, "train_tasks": n, "train_maps": n_maps, "steps": steps, "steps_taken": taken, "batch": batch, "data_seconds": t_data,
             "train_seconds": t_train, "samples_per_s": steps * batch / t_train, "loss_curve": curve}
