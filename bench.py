@@ -346,7 +346,8 @@ def trained_guidance_section(args, dev):
         st, it = res.status.cpu().numpy(), res.iterations.cpu().numpy()
         pl = res.path_len.cpu().numpy()
         return {"label": label, "solved_fraction": float((st == 0).mean()), "mean_iterations": float(it.mean()),
-                "median_iterations": float(np.median(it)), "mean_path_length_solved": float(pl[st == 0].mean()) if (st == 0).any() else None}
+                "median_iterations": float(np.median(it)), "mean_path_length_solved": float(pl[st == 0].mean()) if (st == 0).any() else None,
+                "sampler_stuck": int((st == 3).sum()), "no_node_connected": int((st == 2).sum())}
 
     def guided(model, label):
         planner = engine.GuidedPlanner(model.to(dev).eval(), 2, (S, S), max_iterations=5000)
