@@ -691,17 +691,30 @@ class UNetTrainer(object):
         return {"conv1.2": 0, "up6": 3, "c6.0": 2, "c6.2": 2, "up7": 2, "c7.0": 1, "c7.2": 1, "up8": 1, "c8.0": 0, "c8.2": 0}[n]
 
 
-def generated_training_set(n_maps: int, first_map: int = 5000, size: int = 512, device="cuda:0"):
+def generated_training_set(n_maps: int, first_map: int = 5000, size: int = 512, device="cuda:0", timings: dict = None):
     """The reference's data pipeline for n_maps maps x 10 tasks, entirely on the device: generate_maps.create_map +
     generate_tasks.draw_start_and_finish (csrc/generate.cu, the reference's `random` streams: map m is seed 1000 + m / 2000 + m),
     generate_paths.astar (csrc/gridpath.cu: one shortest path per task) and generate_paths.visualize_path (csrc/masks.cu).
-    Returns (DeviceWorkload, masks uint8 [tasks, size, size])."""
+    Returns (DeviceWorkload, masks uint8 [tasks, size, size]); `timings` (optional dict) receives the milliseconds of the three
+    stages (CUDA events)."""
     from . import engine, generate_paths, workload
     dev = torch.device(device)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
     wl = workload.make_on_device(2, n_maps * 10, first_map=first_map, size=size, device=dev)
+    ev[1].record()
     bits = engine.pack_occupancy(wl.occ_maps, 2, dev)
     _, _, paths, path_n = engine.grid_paths(bits, wl.task_to_map, wl.starts, wl.goals, (size, size), path_cap=4 * size)
+    ev[2].record()
     masks = generate_paths.path_masks(wl.occ_maps, wl.task_to_map, paths, path_n, dev)
+    ev[3].record()
+    if timings is not None:
+        torch.cuda.synchronize(dev)
+        n = n_maps * 10
+        timings.update({"maps_and_tasks_ms": ev[0].elapsed_time(ev[1]), "shortest_paths_ms": ev[1].elapsed_time(ev[2]),
+                        "masks_ms": ev[2].elapsed_time(ev[3]), "paths_per_s": n / ev[1].elapsed_time(ev[2]) * 1e3,
+                        "masks_per_s": n / ev[2].elapsed_time(ev[3]) * 1e3,
+                        "masks_algorithmic_GBps": n * size * size * 2 / ev[2].elapsed_time(ev[3]) / 1e6})
     return wl, masks
 
 
@@ -713,7 +726,8 @@ def fit_on_generated(model, n_maps: int, steps: int, first_map: int = 5000, batc
     import time
     dev = torch.device(device)
     t0 = time.time()
-    wl, masks = generated_training_set(n_maps, first_map, size, dev)
+    stage_ms = {}
+    wl, masks = generated_training_set(n_maps, first_map, size, dev, timings=stage_ms)
     torch.cuda.synchronize(dev)
     t_data = time.time() - t0
     tr = UNetTrainer(model, batch, size, size, dev)
@@ -755,5 +769,5 @@ def fit_on_generated(model, n_maps: int, steps: int, first_map: int = 5000, batc
     t_train = time.time() - t0
     taken = int(tr.scale_state[3].item())
     tr.export_to(model)
-    return {"eval_mode_loss_before_recalibration": eval_before, "eval_mode_loss": eval_after, "train_tasks": n, "train_maps": n_maps, "steps": steps, "steps_taken": taken, "batch": batch, "data_seconds": t_data,
+    return {"eval_mode_loss_before_recalibration": eval_before, "eval_mode_loss": eval_after, "train_tasks": n, "train_maps": n_maps, "steps": steps, "steps_taken": taken, "batch": batch, "data_seconds": t_data, "data_stages": stage_ms,
             "train_seconds": t_train, "samples_per_s": steps * batch / t_train, "loss_curve": curve}
