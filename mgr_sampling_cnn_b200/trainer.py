@@ -719,10 +719,12 @@ def generated_training_set(n_maps: int, first_map: int = 5000, size: int = 512, 
 
 
 def fit_on_generated(model, n_maps: int, steps: int, first_map: int = 5000, batch: int = 3, size: int = 512, device="cuda:0", seed: int = 0,
-                     log=None, schedule: str = "steps", recalibrate: int = 64):
+                     log=None, schedule: str = "steps", recalibrate: int = 64, checkpoint_every: int = 1000):
     """Train `model` (UNet_cooler) for `steps` optimisation steps of `batch` random samples of a generated training set; the
-    learning rate is halved at 60 % and 80 % of the run (the reference halves it on validation plateaus, train.py:230).  The
-    trained parameters and running statistics are written back into `model`.  Returns a dict of run statistics."""
+    learning rate is halved at 60 % and 80 % of the run (the reference halves it on validation plateaus, train.py:230); every
+    `checkpoint_every` steps the eval-mode loss on held-out tasks decides which state is kept (ModelCheckpoint on val_loss,
+    train.py:289-294); the kept state's BatchNorm statistics are recalibrated and it is written back into `model`.
+    Returns a dict of run statistics."""
     import time
     dev = torch.device(device)
     t0 = time.time()
@@ -733,41 +735,55 @@ def fit_on_generated(model, n_maps: int, steps: int, first_map: int = 5000, batc
     tr = UNetTrainer(model, batch, size, size, dev)
     rng = np.random.default_rng(seed)
     n = int(masks.shape[0])
-    run, curve = [], []
+    n_val = max(batch * 16, n // 20)                    # the last 5 % of the generated tasks are held out for validation
+    n_train = n - n_val
+
+    def sample(lo, hi):
+        idx = torch.from_numpy(lo + rng.choice(hi - lo, batch, replace=False)).to(dev)
+        occ = wl.occ_maps[wl.task_to_map[idx].long()]
+        return idx, (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()      # MapsDataset's image tensor (train.py:41-44)
+
+    def val_loss(k=16):
+        vals = []
+        for j in range(k):
+            idx = torch.arange(n_train + j * batch, n_train + (j + 1) * batch, device=dev)
+            occ = wl.occ_maps[wl.task_to_map[idx].long()]
+            x = (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()
+            vals.append(tr.validation_step((x, None, wl.coords[idx]), masks_u8=masks[idx]))
+        return float(torch.stack(vals).mean().item())
+
+    run, curve, vcurve = [], [], []
+    best, best_state = math.inf, None
     t0 = time.time()
     for step in range(1, steps + 1):
         if schedule == "cosine":   # 100 warm-up steps, then a cosine from 1e-3 down to 2e-5
             tr.lr = 1e-3 * min(1.0, step / 100.0) * max(0.02, 0.5 * (1.0 + math.cos(math.pi * step / steps)))
         else:
             tr.lr = 1e-3 if step <= 0.6 * steps else (5e-4 if step <= 0.8 * steps else 2.5e-4)
-        idx = torch.from_numpy(rng.choice(n, batch, replace=False)).to(dev)
-        occ = wl.occ_maps[wl.task_to_map[idx].long()]
-        x = (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()      # MapsDataset's image tensor (train.py:41-44)
+        idx, x = sample(0, n_train)
         run.append(tr.training_step((x, None, wl.coords[idx]), masks_u8=masks[idx]))
         if step % 250 == 0 or step == steps:
             curve.append((step, float(torch.stack(run).mean().item())))
             run = []
             if log:
                 log("step %d: mean loss %.4f, lr %g, loss scale %g" % (step, curve[-1][1], tr.lr, float(tr.scale_state[0].item())))
-    def sample():
-        idx = torch.from_numpy(rng.choice(n, batch, replace=False)).to(dev)
-        occ = wl.occ_maps[wl.task_to_map[idx].long()]
-        return idx, (occ != 0).float()[:, None].expand(-1, 3, -1, -1).contiguous()
-
-    def eval_loss(k=16):
-        vals = []
-        for _ in range(k):
-            idx, x = sample()
-            vals.append(tr.validation_step((x, None, wl.coords[idx]), masks_u8=masks[idx]))
-        return float(torch.stack(vals).mean().item())
-
-    eval_before = eval_loss()
-    if recalibrate > 0:
-        tr.recalibrate_batchnorm(((x, wl.coords[idx]) for idx, x in (sample() for _ in range(recalibrate))))
-    eval_after = eval_loss()
-    torch.cuda.synchronize(dev)
+        if step % checkpoint_every == 0 or step == steps:
+            # ModelCheckpoint(monitor='val_loss') of the reference's Trainer (train.py:289-294): the eval-mode loss on the held-out
+            # tasks decides which state is kept
+            v = val_loss()
+            vcurve.append((step, v))
+            if v < best:
+                best, best_state = v, {k: (t.clone() if torch.is_tensor(t) else t) for k, t in tr.state_dict().items()}
     t_train = time.time() - t0
+    eval_before = vcurve[-1][1]
+    if best_state is not None:
+        tr.load_state_dict(best_state)
+    if recalibrate > 0:
+        tr.recalibrate_batchnorm(((x, wl.coords[idx]) for idx, x in (sample(0, n_train) for _ in range(recalibrate))))
+    eval_after = val_loss()
+    torch.cuda.synchronize(dev)
     taken = int(tr.scale_state[3].item())
     tr.export_to(model)
-    return {"eval_mode_loss_before_recalibration": eval_before, "eval_mode_loss": eval_after, "train_tasks": n, "train_maps": n_maps, "steps": steps, "steps_taken": taken, "batch": batch, "data_seconds": t_data, "data_stages": stage_ms,
+    return {"val_loss_last_step": eval_before, "val_loss_best": best, "val_loss_kept_state_recalibrated": eval_after, "val_curve": vcurve,
+            "train_tasks": n_train, "val_tasks": n_val, "train_maps": n_maps, "steps": steps, "steps_taken": taken, "batch": batch, "data_seconds": t_data, "data_stages": stage_ms,
             "train_seconds": t_train, "samples_per_s": steps * batch / t_train, "loss_curve": curve}

@@ -13,6 +13,6 @@ planner = engine.GuidedPlanner(model.to(dev).eval(), 2, (512, 512), max_iteratio
 res = planner.plan(wl.occ_maps, wl.task_to_map, wl.starts, wl.goals, wl.coords, seed=7)
 torch.cuda.synchronize()
 st, it = res.status.cpu().numpy(), res.iterations.cpu().numpy()
-print(json.dumps({"schedule": sched, "steps": steps, "final_loss": fit["loss_curve"][-1][1], "eval_before": fit["eval_mode_loss_before_recalibration"], "eval_after": fit["eval_mode_loss"], "train_s": round(fit["train_seconds"], 1),
+print(json.dumps({"schedule": sched, "steps": steps, "final_loss": fit["loss_curve"][-1][1], "val_last": fit["val_loss_last_step"], "val_best": fit["val_loss_best"], "val_kept": fit["val_loss_kept_state_recalibrated"], "val_curve": fit["val_curve"], "train_s": round(fit["train_seconds"], 1),
                   "solved": float((st == 0).mean()), "mean_it": float(it.mean()), "median_it": float(np.median(it)),
                   "len": float(res.path_len.cpu().numpy()[st == 0].mean())}))
