@@ -219,3 +219,19 @@ def test_fit_loop_early_stopping_and_best_state():
     assert abs(val - best) <= 2e-2 * best                              # the restored state is the best epoch's
     out = model.to(DEV).eval()(data[0][0].to(DEV), data[0][2].to(DEV))   # ... and it is what export_to left in the module
     assert bool(torch.isfinite(out).all())
+
+
+def test_fit_on_generated_runs_the_whole_device_pipeline():
+    """trainer.fit_on_generated: maps, tasks, shortest paths and masks generated on the device, training steps, the best
+    held-out state kept, BatchNorm recalibrated, the module updated (what bench.py's trained_guidance section calls)."""
+    from mgr_sampling_cnn_b200 import train, trainer
+    torch.manual_seed(0)
+    model = train.UNet_cooler()
+    before = model.conv8[0].weight.detach().clone()
+    st = trainer.fit_on_generated(model, 12, 24, first_map=7000, device=DEV, recalibrate=4, checkpoint_every=8)
+    assert st["steps"] == 24 and st["train_tasks"] + st["val_tasks"] == 120 and len(st["val_curve"]) == 3
+    assert np.isfinite(st["val_loss_best"]) and st["val_loss_best"] <= st["val_curve"][0][1] + 1e-12
+    assert st["data_stages"]["masks_per_s"] > 0 and st["loss_curve"][-1][0] == 24
+    assert not torch.equal(model.conv8[0].weight.detach().cpu(), before)
+    out = model.to(DEV).eval()(torch.ones(1, 3, 512, 512, device=DEV), torch.tensor([[[[10., 20.], [400., 300.]]]], device=DEV))
+    assert bool(torch.isfinite(out).all())
