@@ -29,6 +29,45 @@ def _pp(t, coff=0):
     return None if t is None else C.c_void_p(t.data_ptr() + coff * t.element_size())
 
 
+def to_kernel_layout(t, what: str, convT: bool = False, cin_pad: int = None):
+    """torch parameter -> the layout it has in the trainer's flat buffers (pure tensor reshuffling, any device):
+    'w'  conv weight [cout][cin][k][k] -> [cout][taps][cin_pad] (zero-padded channels); ConvTranspose2d weight [cin][cout][2][2] ->
+         [(a, b)][cout][cin], the forward kernel's group-major rows;
+    'b'  bias; a ConvTranspose bias is stored once per output offset (4 copies, all receiving the same gradient);
+    'cw' conv_coords weight [cout][cin][3][3] -> [tap][cin][cout];  'v' anything else, unchanged."""
+    if what == "w":
+        if convT:
+            cin, cout = t.shape[0], t.shape[1]
+            return t.permute(2, 3, 1, 0).reshape(4 * cout, cin)
+        cout, cin = t.shape[0], t.shape[1]
+        w = t.reshape(cout, cin, -1).permute(0, 2, 1)
+        if cin_pad is not None and cin_pad != cin:
+            w = torch.nn.functional.pad(w, (0, cin_pad - cin))
+        return w
+    if what == "b":
+        return t.repeat(4) if convT else t
+    if what == "cw":
+        return t.permute(2, 3, 1, 0)
+    return t
+
+
+def from_kernel_layout(v, what: str, shape, convT: bool = False, cin_pad: int = None):
+    """Inverse of to_kernel_layout: flat buffer segment `v` -> a tensor of the torch parameter's `shape`."""
+    shape = tuple(int(x) for x in shape)
+    if what == "w":
+        if convT:
+            cin, cout = shape[0], shape[1]
+            return v.reshape(2, 2, cout, cin).permute(3, 2, 0, 1).reshape(shape)
+        cout, cin = shape[0], shape[1]
+        taps = int(np.prod(shape[2:]))
+        return v.reshape(cout, taps, cin_pad or cin)[:, :, :cin].permute(0, 2, 1).reshape(shape)
+    if what == "b" and convT:
+        return v[:shape[0]].reshape(shape)
+    if what == "cw":
+        return v.reshape(3, 3, shape[1], shape[0]).permute(3, 2, 0, 1).reshape(shape)
+    return v.reshape(shape)
+
+
 class PlateauScheduler(object):
     """torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, factor=0.5, patience=2) as configure_optimizers() sets it up
     (train.py:230-234; mode 'min', relative threshold 1e-4, no cooldown, min_lr 0): host logic, monitored on val_loss."""
@@ -199,18 +238,8 @@ class UNetTrainer(object):
     def _master_view(self, t, cv, what):
         """torch parameter -> the flat buffer's layout (host-side plumbing at import / export only)."""
         t = t.detach().to(self.dev, torch.float32)
-        if what == "w":
-            if cv.kind == CONVT:   # [cin][cout][2][2] -> [(a, b)][cout][cin]
-                return t.permute(2, 3, 1, 0).reshape(cv.rows, cv.cin)
-            w = t.reshape(cv.cout, cv.cin, cv.taps).permute(0, 2, 1)   # [cout][taps][cin]
-            if cv.cin_pad != cv.cin:
-                w = torch.nn.functional.pad(w, (0, cv.cin_pad - cv.cin))
-            return w
-        if what == "b":
-            return t.repeat(4) if cv.kind == CONVT else t
-        if what == "cw":           # [cout][cin][3][3] -> [tap][cin][cout]
-            return t.permute(2, 3, 1, 0)
-        return t
+        is_conv = isinstance(cv, _Conv)
+        return to_kernel_layout(t, what, convT=is_conv and cv.kind == CONVT, cin_pad=cv.cin_pad if is_conv else None)
 
     def import_from(self, model):
         with torch.no_grad():
@@ -222,18 +251,10 @@ class UNetTrainer(object):
         """[(torch parameter, tensor in its layout)] for a flat buffer laid out like self.params (parameters or gradients)."""
         out = []
         for off, cv, what, p in self.segs:
+            is_conv = isinstance(cv, _Conv)
+            convT = is_conv and cv.kind == CONVT
             n = self._master_view(p, cv, what).numel()
-            v = flat[off:off + n]
-            if what == "w":
-                if cv.kind == CONVT:
-                    v = v.view(2, 2, cv.cout, cv.cin).permute(3, 2, 0, 1)
-                else:
-                    v = v.view(cv.cout, cv.taps, cv.cin_pad)[:, :, :cv.cin].permute(0, 2, 1)
-            elif what == "b" and cv.kind == CONVT:
-                v = v[:cv.cout]
-            elif what == "cw":
-                v = v.view(3, 3, p.shape[1], p.shape[0]).permute(3, 2, 0, 1)
-            out.append((p, v.reshape(p.shape)))
+            out.append((p, from_kernel_layout(flat[off:off + n], what, p.shape, convT=convT, cin_pad=cv.cin_pad if is_conv else None)))
         return out
 
     def named(self, flat, unscale: float = 1.0):

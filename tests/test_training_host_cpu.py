@@ -53,3 +53,27 @@ def test_plateau_scheduler_matches_torch():
         again = PlateauScheduler(123.0)
         again.load_state_dict(d)
         assert again.step(v * 2) == mine.step(v * 2)
+
+
+def test_kernel_layout_round_trip():
+    """trainer.to_kernel_layout / from_kernel_layout: the packing of the reference's parameters into the trainer's flat buffers."""
+    from mgr_sampling_cnn_b200.trainer import from_kernel_layout, to_kernel_layout
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 5, 3, 3, generator=g)                                    # Conv2d weight, channels padded 5 -> 64
+    k = to_kernel_layout(w, "w", cin_pad=64)
+    assert k.shape == (8, 9, 64) and float(k[:, :, 5:].abs().max()) == 0.0
+    assert k[3, 1 * 3 + 2, 4] == w[3, 4, 1, 2]                                  # [cout][tap = ky * 3 + kx][cin]
+    assert torch.equal(from_kernel_layout(k.reshape(-1), "w", w.shape, cin_pad=64), w)
+    wt = torch.randn(6, 4, 2, 2, generator=g)                                   # ConvTranspose2d weight [cin][cout][2][2]
+    kt = to_kernel_layout(wt, "w", convT=True)
+    assert kt.shape == (16, 6) and kt[(1 * 2 + 0) * 4 + 3, 5] == wt[5, 3, 1, 0]  # row = (a * 2 + b) * cout + co
+    assert torch.equal(from_kernel_layout(kt.reshape(-1), "w", wt.shape, convT=True), wt)
+    b = torch.randn(4, generator=g)
+    assert torch.equal(to_kernel_layout(b, "b", convT=True), b.repeat(4))
+    assert torch.equal(from_kernel_layout(b.repeat(4), "b", b.shape, convT=True), b)
+    cw = torch.randn(7, 3, 3, 3, generator=g)                                   # conv_coords weight -> [tap][cin][cout]
+    kc = to_kernel_layout(cw, "cw")
+    assert kc.shape == (3, 3, 3, 7) and kc[2, 0, 1, 6] == cw[6, 1, 2, 0]
+    assert torch.equal(from_kernel_layout(kc.reshape(-1), "cw", cw.shape), cw)
+    v = torch.randn(5, generator=g)
+    assert torch.equal(from_kernel_layout(to_kernel_layout(v, "v").reshape(-1), "v", v.shape), v)
