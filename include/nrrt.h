@@ -469,7 +469,7 @@ int nrrt_enlarge_paths_3d(const uint8_t* occ_maps, const int32_t* task_to_map, c
  * Training step: UNet_cooler.training_step (train.py:205-210) = forward in train mode, nn.BCEWithLogitsLoss
  * (:113), loss.backward(), torch.optim.Adam(lr=1e-3) (:228-229).  The forward convolutions and the data gradients are
  * nrrt_conv_layer calls (a data gradient is the same convolution with the weights of nrrt_pack_dgrad_weight); the weight
- * gradients are nrrt_conv_wgrad (csrc/wgrad_tc.cu, tcgen05); the rest are one-pass kernels of csrc/train_ops.cu.
+ * gradients are nrrt_conv_wgrad_nhwc (csrc/wgrad_tc.cu, tcgen05); the rest are one-pass kernels of csrc/train_ops.cu.
  * Activations and activation gradients are fp16 channels-last; parameters, their gradients and the Adam state are fp32.
  * Gradients are computed for loss * grad_scale_inverse (the caller picks the scale: nrrt_bce_with_logits' grad_scale) and
  * unscaled by nrrt_adam_step.  The host graph is mgr_sampling_cnn_b200/trainer.py.

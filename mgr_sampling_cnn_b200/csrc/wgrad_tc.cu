@@ -3,16 +3,19 @@
 //
 //   dW[co][ky][kx][ci] = sum over (n, y, x) of  dY[n, y, x, co] * X[n, y + ky - 1, x + kx - 1, ci]
 //
-// GEMM view: M = 128 output channels, N = BLOCK_N input channels, K = PIXELS.  Both operands are read channel-major
-// ([C][N][H][W] fp16, written by nrrt_to_channel_major), so a K block of 64 pixels of one image row is one 128-byte
-// SWIZZLE_128B row per channel: plain K-major tcgen05 operands, and a tap shift is a TMA coordinate offset whose
-// out-of-range pixels are zero-filled = the convolution padding.
+// GEMM view: M = 128 output channels, N = BLOCK_N input channels, K = PIXELS.  Two operand paths share the kernel:
+//   MN = true  (nrrt_conv_wgrad_nhwc, the product path): both operands are read straight from the channels-last buffers as
+//     MN-major UMMA operands.  A TMA box of 64 pixels x 64 channels is 64 K-rows of 128 bytes = eight 1024-byte SWIZZLE_128B
+//     atoms; both tap shifts are TMA coordinates of OUTER dimensions and out-of-range pixels are zero-filled = the padding.
+//     Nothing is transposed or copied.
+//   MN = false (nrrt_conv_wgrad, kept as cross-check): operands channel-major ([C][N][H][W], written by
+//     nrrt_to_channel_major), K-major tiles.  The kx shift is then along the innermost dimension, and a swizzled TMA row that
+//     starts at an odd pixel is an illegal instruction (measured): X is written as three copies shifted by -1 / 0 / +1 pixel.
 // One CTA owns (128 co) x (BLOCK_N ci) x (one kx, all ky) and walks image-column strips of 64 pixels row by row: the
 // operand row X[y + 1] loaded for k-block y is the ky = 2 operand of k-block y, the ky = 1 operand of k-block y + 1 and the
 // ky = 0 operand of k-block y + 2 -- each k-block loads ONE A tile and ONE B tile for three MMAs (nky accumulators of
-// BLOCK_N TMEM columns).  The kx shift cannot be a TMA coordinate (a swizzled row must start on a 16-byte boundary:
-// measured, an odd pixel offset in the innermost dimension is an illegal instruction), so nrrt_to_channel_major writes the
-// X operand as three copies shifted by -1 / 0 / +1 pixel, and a CTA reads the copy of its kx.  K is split over CTAs (strips); partial sums are added to the fp32 gradient with red.global.
+// BLOCK_N TMEM columns).  K is split over CTAs (image, column block, row segment); partial sums are added to the fp32
+// gradient with red.global.add.v4.f32.
 // Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue (TMEM -> red.global.add.f32).
 #include <cuda.h>
 #include <cuda_fp16.h>
