@@ -29,3 +29,21 @@ def test_train_oracle_matches_reference_step():
     psum = dict(zip(names, g["param_sum_after"]))
     for k in ("conv8.2.weight", "conv6.0.weight", "conv2.0.conv1.weight"):
         assert abs(float(new[k].double().sum()) - psum[k]) <= 2e-3 * new[k].numel() * 1e-3 + 1e-6, k   # Adam's first step is +-lr
+
+
+def test_oracle_adam_matches_torch_optim():
+    """train_oracle.adam_step (used as the multi-step checker of the trainer) == torch.optim.Adam(lr=1e-3) over three steps."""
+    g = torch.Generator().manual_seed(0)
+    p0 = {"a": torch.randn(40, generator=g), "b": torch.randn(3, 5, generator=g)}
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in p0.items()}
+    opt = torch.optim.Adam(params.values(), lr=1e-3)
+    sd, state = {k: v.clone() for k, v in p0.items()}, {}
+    for step in (1, 2, 3):
+        grads = {k: torch.randn(v.shape, generator=g) for k, v in p0.items()}
+        for k in params:
+            params[k].grad = grads[k].clone()
+        opt.step()
+        new, state = train_oracle.adam_step(sd, grads, state=state, step=step)
+        sd.update(new)
+        for k in params:
+            assert torch.allclose(sd[k], params[k].detach(), rtol=0, atol=2e-7), (k, step)
