@@ -150,21 +150,108 @@ __global__ void __launch_bounds__(256) enlarge3d_kernel(const __grid_constant__ 
     const int tid = threadIdx.x;
     // distance 0 on the path, INF elsewhere and outside the volume
     int touched = 0;
-    for (int i = tid; i < E * E * E; i += 256) {
-        const int z = i % E, y = (i / E) % E, x = i / (E * E);
-        const int gx = x0 - R + x, gy = y0 - R + y, gz = z0 - R + z;
-        uint8_t v = 255;
-        if (gx >= 0 && gx < a.s0 && gy >= 0 && gy < a.s1 && gz >= 0 && gz < a.s2)
-            v = pv[((size_t)gx * a.s1 + gy) * a.s2 + gz] == 255 ? 0 : 255;
-        d0[i] = v;
-        touched |= v == 0;
+    // z rows of whole, aligned words (80^3 maps with LAYERS = 5): the tile + halo is read and written 4 / 16 voxels at a time
+    const bool fast = (a.s2 & 15) == 0 && (R & 3) == 0 && (((uintptr_t)pv | (uintptr_t)occ | (uintptr_t)out) & 15) == 0;
+    if (fast) {
+        const int EW = E >> 2;
+        uint32_t* d0w = reinterpret_cast<uint32_t*>(d0);
+        for (int i = tid; i < E * E * EW; i += 256) {
+            const int wi = i % EW, y = (i / EW) % E, x = i / (EW * E);
+            const int gx = x0 - R + x, gy = y0 - R + y, gz = z0 - R + 4 * wi;
+            uint32_t v = 0xffffffffu;
+            if (gx >= 0 && gx < a.s0 && gy >= 0 && gy < a.s1 && gz >= 0 && gz < a.s2)
+                v = ~__vcmpeq4(*reinterpret_cast<const uint32_t*>(pv + ((size_t)gx * a.s1 + gy) * a.s2 + gz), 0xffffffffu);
+            d0w[i] = v;
+            touched |= v != 0xffffffffu;
+        }
+    } else {
+        for (int i = tid; i < E * E * E; i += 256) {
+            const int z = i % E, y = (i / E) % E, x = i / (E * E);
+            const int gx = x0 - R + x, gy = y0 - R + y, gz = z0 - R + z;
+            uint8_t v = 255;
+            if (gx >= 0 && gx < a.s0 && gy >= 0 && gy < a.s1 && gz >= 0 && gz < a.s2)
+                v = pv[((size_t)gx * a.s1 + gy) * a.s2 + gz] == 255 ? 0 : 255;
+            d0[i] = v;
+            touched |= v == 0;
+        }
     }
     if (!__syncthreads_or(touched)) {   // no path voxel within reach of this tile: the volume is copied through
+        if (fast) {
+            for (int i = tid; i < kT3 * kT3; i += 256) {         // one 16-voxel z row per thread
+                const int gy = y0 + i % kT3, gx = x0 + i / kT3;
+                if (gx >= a.s0 || gy >= a.s1) continue;
+                const size_t g = ((size_t)gx * a.s1 + gy) * a.s2 + z0;
+                *reinterpret_cast<uint4*>(out + g) = *reinterpret_cast<const uint4*>(pv + g);
+            }
+            return;
+        }
         for (int i = tid; i < kT3 * kT3 * kT3; i += 256) {
             const int gz = z0 + i % kT3, gy = y0 + (i / kT3) % kT3, gx = x0 + i / (kT3 * kT3);
             if (gx >= a.s0 || gy >= a.s1 || gz >= a.s2) continue;
             const size_t g = ((size_t)gx * a.s1 + gy) * a.s2 + gz;
             out[g] = pv[g];
+        }
+        return;
+    }
+    if ((E & 3) == 0) {
+        // Even reach (the reference's LAYERS = 5): four voxels of a z row per 32-bit word, byte-SIMD min / max.  A shifted window
+        // of a row is a funnel shift of two neighbouring words; the y and x passes shift by whole rows, i.e. whole words.
+        const int EW = E >> 2;                                   // words per z row of d0
+        const uint32_t* d0w = reinterpret_cast<const uint32_t*>(d0);
+        uint32_t* d1w = reinterpret_cast<uint32_t*>(d1);
+        for (int i = tid; i < E * E * 4; i += 256) {             // z pass: d1[x][y][16 z]
+            const int j = i & 3, row = i >> 2;
+            const uint32_t* rw = d0w + row * EW;
+            uint32_t m = 0xffffffffu;
+            for (int dz = -R; dz <= R; ++dz) {
+                const int o = 4 * j + R + dz, wi = o >> 2;
+                const uint32_t lo = rw[wi], hi = wi + 1 < EW ? rw[wi + 1] : 0u;
+                const uint32_t wv = __funnelshift_r(lo, hi, (o & 3) * 8);
+                m = __vminu4(m, __vmaxu4(wv, (uint32_t)(dz < 0 ? -dz : dz) * 0x01010101u));
+            }
+            d1w[i] = m;
+        }
+        __syncthreads();
+        uint32_t* d0o = reinterpret_cast<uint32_t*>(d0);
+        for (int i = tid; i < E * kT3 * 4; i += 256) {           // y pass into d0 as [E][16][16]
+            const int j = i & 3, y = (i >> 2) % kT3, x = i / (4 * kT3);
+            const uint32_t* src = d1w + (x * E + y + R) * 4 + j;
+            uint32_t m = 0xffffffffu;
+            for (int dy = -R; dy <= R; ++dy) m = __vminu4(m, __vmaxu4(src[dy * 4], (uint32_t)(dy < 0 ? -dy : dy) * 0x01010101u));
+            d0o[i] = m;
+        }
+        __syncthreads();
+        for (int i = tid; i < kT3 * kT3 * 4; i += 256) {         // x pass + paint
+            const int j = i & 3, y = (i >> 2) % kT3, x = i / (4 * kT3);
+            const int gx = x0 + x, gy = y0 + y;
+            if (gx >= a.s0 || gy >= a.s1) continue;
+            const uint32_t* src = d0o + ((x + R) * kT3 + y) * 4 + j;
+            uint32_t m = 0xffffffffu;
+            for (int dx = -R; dx <= R; ++dx) m = __vminu4(m, __vmaxu4(src[dx * kT3 * 4], (uint32_t)(dx < 0 ? -dx : dx) * 0x01010101u));
+            if (fast) {
+                const size_t g = ((size_t)gx * a.s1 + gy) * a.s2 + z0 + 4 * j;
+                const uint32_t pw = *reinterpret_cast<const uint32_t*>(pv + g), ow = *reinterpret_cast<const uint32_t*>(occ + g);
+                uint32_t res = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int mk = (m >> (8 * k)) & 0xff;
+                    uint32_t v = (pw >> (8 * k)) & 0xff;
+                    if (mk < a.layers && ((ow >> (8 * k)) & 0xff) != 255 && a.values[mk] > v) v = a.values[mk];
+                    res |= v << (8 * k);
+                }
+                *reinterpret_cast<uint32_t*>(out + g) = res;
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int gz = z0 + 4 * j + k;
+                if (gz >= a.s2) break;
+                const int mk = (m >> (8 * k)) & 0xff;
+                const size_t g = ((size_t)gx * a.s1 + gy) * a.s2 + gz;
+                uint8_t v = pv[g];
+                if (mk < a.layers && occ[g] != 255 && a.values[mk] > v) v = a.values[mk];
+                out[g] = v;
+            }
         }
         return;
     }
