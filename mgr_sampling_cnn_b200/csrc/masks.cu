@@ -42,81 +42,100 @@ __global__ void __launch_bounds__(256) mask2d_kernel(const __grid_constant__ Mas
     const int R = a.r_eff, RW = kTile + 2 * R, RS = (RW + 3) & ~3;       // region width, row stride of the disk tile
     uint8_t* disk = smem;                                                // [RW][RS]
     uint16_t* hsum = reinterpret_cast<uint16_t*>(smem + ((RW * RS + 15) & ~15));   // [RW][kTile]
-    const int task = blockIdx.z, tx0 = blockIdx.x * kTile, ty0 = blockIdx.y * kTile;
-    const int ry0 = ty0 - R, rx0 = tx0 - R;
+    // A CTA owns one 64-pixel COLUMN of tiles of one task: it takes the bounding box of the path once and walks down the
+    // column; tiles the box (grown by the circle radius and the blur reach) does not touch are zero-filled without looking at
+    // the path again.  (One CTA per tile spent most of the kernel launching 262144 blocks that each rescanned the path.)
+    const int task = blockIdx.y, tx0 = blockIdx.x * kTile;
+    const int rx0 = tx0 - R;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pts = min(a.path_n[task], a.path_cap);
     const int32_t* path = a.paths + (size_t)task * a.path_cap * 2;
     const uint8_t* occ = a.occ + (size_t)a.task_to_map[task] * a.h * a.w;
     uint8_t* mask = a.masks + (size_t)task * a.h * a.w;
-
-    for (int i = tid; i < RW * RS / 4; i += 256) reinterpret_cast<uint32_t*>(disk)[i] = 0u;
+    __shared__ int s_bb[4];
+    if (tid == 0) { s_bb[0] = s_bb[2] = 0x7fffffff; s_bb[1] = s_bb[3] = -0x7fffffff; }
     __syncthreads();
-    // 1. filled circles (cv::circle thickness < 0: row cy + dy spans cx +- half_width[|dy|]), clipped to the image
-    int touched = 0;
-    for (int p = warp; p < n_pts; p += 8) {
-        const int py = path[2 * p], px = path[2 * p + 1];
-        if (py + a.radius < ry0 || py - a.radius >= ry0 + RW || px + a.radius < rx0 || px - a.radius >= rx0 + RW) continue;
-        touched = 1;
-        for (int dy = -a.radius + lane; dy <= a.radius; dy += 32) {
-            const int y = py + dy;
-            if (y < 0 || y >= a.h || y < ry0 || y >= ry0 + RW) continue;
-            const int hw = a.half_width[dy < 0 ? -dy : dy];
-            const int xa = max(max(px - hw, 0), rx0), xb = min(min(px + hw, a.w - 1), rx0 + RW - 1);
-            uint8_t* row = disk + (y - ry0) * RS - rx0;
-            for (int x = xa; x <= xb; ++x) row[x] = 255;
-        }
-    }
-    if (!__syncthreads_or(touched)) {   // no disk reaches this tile or its blur halo (most tiles of a task): the mask is 0 here
-        for (int i = tid; i < kTile * kTile / 4; i += 256) {
-            const int r = i / (kTile / 4), c = (i - r * (kTile / 4)) * 4, y = ty0 + r, x = tx0 + c;
-            if (y >= a.h) continue;
-            if (x + 3 < a.w && (a.w & 3) == 0) *reinterpret_cast<uint32_t*>(mask + (size_t)y * a.w + x) = 0u;
-            else for (int j = 0; j < 4 && x + j < a.w; ++j) mask[(size_t)y * a.w + x + j] = 0;
-        }
-        return;
-    }
-    // 2. BORDER_REFLECT_101 for halo cells outside the image
-    for (int i = tid; i < RW * RW; i += 256) {
-        const int r = i / RW, c = i - r * RW, y = ry0 + r, x = rx0 + c;
-        if (y >= 0 && y < a.h && x >= 0 && x < a.w) continue;
-        const int sy = reflect101(y, a.h) - ry0, sx = reflect101(x, a.w) - rx0;
-        disk[r * RS + c] = (sy >= 0 && sy < RW && sx >= 0 && sx < RW) ? disk[sy * RS + sx] : 0;
-    }
-    __syncthreads();
-    // 3. horizontal pass (8-bit x 8.8 fixed point -> 16 bit; the taps sum to 256 so 255 * 256 is the maximum)
-    for (int i = tid; i < RW * kTile; i += 256) {
-        const int r = i / kTile, c = i - r * kTile;
-        const uint8_t* src = disk + r * RS + c;
-        uint32_t s = 0;
-        for (int k = 0; k <= 2 * R; ++k) s += (uint32_t)a.taps[k] * src[k];
-        hsum[i] = (uint16_t)s;
-    }
-    __syncthreads();
-    // 4. vertical pass, rounding, free-space mask; 4 pixels per thread
-    for (int i = tid; i < kTile * kTile / 4; i += 256) {
-        const int r = i / (kTile / 4), c = (i - r * (kTile / 4)) * 4, y = ty0 + r;
-        if (y >= a.h) continue;
-        uint32_t s[4] = {0, 0, 0, 0};
-        for (int k = 0; k <= 2 * R; ++k) {
-            const uint2 v = *reinterpret_cast<const uint2*>(hsum + (r + k) * kTile + c);
-            const uint32_t t = a.taps[k];
-            s[0] += t * (v.x & 0xffffu); s[1] += t * (v.x >> 16); s[2] += t * (v.y & 0xffffu); s[3] += t * (v.y >> 16);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int x = tx0 + c + j;
-            if (x >= a.w) break;
-            const uint32_t v = min((s[j] + 32768u) >> 16, 255u);
-            mask[(size_t)y * a.w + x] = occ[(size_t)y * a.w + x] > a.free_above ? (uint8_t)v : (uint8_t)0;
-        }
-    }
-    __syncthreads();
-    // 5. the path pixels themselves are set to 255 after the blur (still under the free-space mask)
     for (int p = tid; p < n_pts; p += 256) {
-        const int py = path[2 * p], px = path[2 * p + 1];
-        if (py >= ty0 && py < ty0 + kTile && px >= tx0 && px < tx0 + kTile && py < a.h && px < a.w && py >= 0 && px >= 0)
-            mask[(size_t)py * a.w + px] = occ[(size_t)py * a.w + px] > a.free_above ? 255 : 0;
+        atomicMin(&s_bb[0], path[2 * p]); atomicMax(&s_bb[1], path[2 * p]);
+        atomicMin(&s_bb[2], path[2 * p + 1]); atomicMax(&s_bb[3], path[2 * p + 1]);
+    }
+    __syncthreads();
+    const int reach = a.radius + R;
+    const bool col_hit = n_pts > 0 && s_bb[2] - reach < tx0 + kTile && s_bb[3] + reach >= tx0;
+    const int by0 = s_bb[0] - reach, by1 = s_bb[1] + reach;
+    for (int ty0 = 0; ty0 < a.h; ty0 += kTile) {
+        const int ry0 = ty0 - R;
+        int touched = 0;
+        __syncthreads();                                   // the previous tile is done with the shared-memory buffers
+        if (col_hit && by0 < ty0 + kTile && by1 >= ty0) {   // else: the path cannot reach this tile (touched stays 0)
+            for (int i = tid; i < RW * RS / 4; i += 256) reinterpret_cast<uint32_t*>(disk)[i] = 0u;
+            __syncthreads();
+            // 1. filled circles (cv::circle thickness < 0: row cy + dy spans cx +- half_width[|dy|]), clipped to the image
+            for (int p = warp; p < n_pts; p += 8) {
+                const int py = path[2 * p], px = path[2 * p + 1];
+                if (py + a.radius < ry0 || py - a.radius >= ry0 + RW || px + a.radius < rx0 || px - a.radius >= rx0 + RW) continue;
+                touched = 1;
+                for (int dy = -a.radius + lane; dy <= a.radius; dy += 32) {
+                    const int y = py + dy;
+                    if (y < 0 || y >= a.h || y < ry0 || y >= ry0 + RW) continue;
+                    const int hw = a.half_width[dy < 0 ? -dy : dy];
+                    const int xa = max(max(px - hw, 0), rx0), xb = min(min(px + hw, a.w - 1), rx0 + RW - 1);
+                    uint8_t* row = disk + (y - ry0) * RS - rx0;
+                    for (int x = xa; x <= xb; ++x) row[x] = 255;
+                }
+            }
+        }
+        if (!__syncthreads_or(touched)) {   // no disk reaches this tile or its blur halo (most tiles of a task): the mask is 0 here
+            for (int i = tid; i < kTile * kTile / 4; i += 256) {
+                const int r = i / (kTile / 4), c = (i - r * (kTile / 4)) * 4, y = ty0 + r, x = tx0 + c;
+                if (y >= a.h) continue;
+                if (x + 3 < a.w && (a.w & 3) == 0) *reinterpret_cast<uint32_t*>(mask + (size_t)y * a.w + x) = 0u;
+                else for (int j = 0; j < 4 && x + j < a.w; ++j) mask[(size_t)y * a.w + x + j] = 0;
+            }
+            continue;
+        }
+        // 2. BORDER_REFLECT_101 for halo cells outside the image
+        for (int i = tid; i < RW * RW; i += 256) {
+            const int r = i / RW, c = i - r * RW, y = ry0 + r, x = rx0 + c;
+            if (y >= 0 && y < a.h && x >= 0 && x < a.w) continue;
+            const int sy = reflect101(y, a.h) - ry0, sx = reflect101(x, a.w) - rx0;
+            disk[r * RS + c] = (sy >= 0 && sy < RW && sx >= 0 && sx < RW) ? disk[sy * RS + sx] : 0;
+        }
+        __syncthreads();
+        // 3. horizontal pass (8-bit x 8.8 fixed point -> 16 bit; the taps sum to 256 so 255 * 256 is the maximum)
+        for (int i = tid; i < RW * kTile; i += 256) {
+            const int r = i / kTile, c = i - r * kTile;
+            const uint8_t* src = disk + r * RS + c;
+            uint32_t s = 0;
+            for (int k = 0; k <= 2 * R; ++k) s += (uint32_t)a.taps[k] * src[k];
+            hsum[i] = (uint16_t)s;
+        }
+        __syncthreads();
+        // 4. vertical pass, rounding, free-space mask; 4 pixels per thread
+        for (int i = tid; i < kTile * kTile / 4; i += 256) {
+            const int r = i / (kTile / 4), c = (i - r * (kTile / 4)) * 4, y = ty0 + r;
+            if (y >= a.h) continue;
+            uint32_t s[4] = {0, 0, 0, 0};
+            for (int k = 0; k <= 2 * R; ++k) {
+                const uint2 v = *reinterpret_cast<const uint2*>(hsum + (r + k) * kTile + c);
+                const uint32_t t = a.taps[k];
+                s[0] += t * (v.x & 0xffffu); s[1] += t * (v.x >> 16); s[2] += t * (v.y & 0xffffu); s[3] += t * (v.y >> 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int x = tx0 + c + j;
+                if (x >= a.w) break;
+                const uint32_t v = min((s[j] + 32768u) >> 16, 255u);
+                mask[(size_t)y * a.w + x] = occ[(size_t)y * a.w + x] > a.free_above ? (uint8_t)v : (uint8_t)0;
+            }
+        }
+        __syncthreads();
+        // 5. the path pixels themselves are set to 255 after the blur (still under the free-space mask)
+        for (int p = tid; p < n_pts; p += 256) {
+            const int py = path[2 * p], px = path[2 * p + 1];
+            if (py >= ty0 && py < ty0 + kTile && px >= tx0 && px < tx0 + kTile && py < a.h && px < a.w && py >= 0 && px >= 0)
+                mask[(size_t)py * a.w + px] = occ[(size_t)py * a.w + px] > a.free_above ? 255 : 0;
+        }
     }
 }
 
@@ -367,7 +386,7 @@ extern "C" int nrrt_path_masks_2d(const uint8_t* occ_maps, const int32_t* task_t
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (smem > 48 * 1024) NRRT_CUDA_TRY(cudaFuncSetAttribute(mask2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NRRT_REQUIRE(B <= 65535, "at most 65535 tasks per call");
-    const dim3 grid((w + kTile - 1) / kTile, (h + kTile - 1) / kTile, B);
+    const dim3 grid((w + kTile - 1) / kTile, B);
     mask2d_kernel<<<grid, 256, smem, st>>>(a);
     NRRT_CUDA_TRY(cudaGetLastError());
     return NRRT_OK;
