@@ -5,7 +5,8 @@
 //       blur   = cv2.GaussianBlur(disks, (33, 33), sigmaX = 3)  [8-bit fixed point]    :134
 //       blur[path point] = 255                                                         :136-137
 //       mask   = blur where occ_map > 240, else 0                                      :148,155
-//     One CTA per 64 x 64 output tile: the disks are rasterised straight into shared memory over the tile + blur halo
+//     One CTA per 64-pixel column of tiles of a task (path bounding box taken once; unreachable tiles are zero-filled); per
+//     64 x 64 tile the disks are rasterised straight into shared memory over the tile + blur halo
 //     (they never exist in HBM), out-of-image halo cells are filled by BORDER_REFLECT_101, then the separable fixed-point
 //     blur runs from shared memory (16-bit horizontal sums, 32-bit vertical sums, (v + 2^15) >> 16: OpenCV's
 //     ufixedpoint16 / ufixedpoint32 arithmetic, integers only, so the result is bit-identical).  Algorithmic HBM bytes per
